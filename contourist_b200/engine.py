@@ -1,0 +1,208 @@
+"""ctypes binding of libcontourist_b200.so (include/contourist_b200.h).
+
+This is the only way the Python package computes anything: there is NO CPU fallback.  If the
+shared library is missing or no CUDA device is usable the import / constructor raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcontourist_b200.so")
+
+F32, F64 = 0, 1
+FIELD_ON_DEVICE = 1
+GEOM_F64 = 2
+WANT_NORMALS = 4
+WANT_KEYS = 8
+WANT_CODES = 16
+NO_GEOMETRY = 32
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Mt3dParams(ctypes.Structure):
+    _fields_ = [("field", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("flags", ctypes.c_uint32),
+                ("n0", ctypes.c_int64), ("n1", ctypes.c_int64), ("n2", ctypes.c_int64),
+                ("isovalue", ctypes.c_double), ("origin", ctypes.c_double * 3), ("delta", ctypes.c_double * 3),
+                ("i_lo", ctypes.c_int64), ("i_hi", ctypes.c_int64), ("plane_offset", ctypes.c_int64)]
+
+
+class Mt3dCounts(ctypes.Structure):
+    _fields_ = [("n_verts", ctypes.c_int64), ("n_tris", ctypes.c_int64), ("n_active_cells", ctypes.c_int64),
+                ("n_crossings", ctypes.c_int64), ("n_codes", ctypes.c_int64),
+                ("fmin", ctypes.c_double), ("fmax", ctypes.c_double)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load the CUDA shared library; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(
+            "contourist_b200: %s not found. Build it with `python -m contourist_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32
+    lib.ctr_create.argtypes = [i32, ctypes.POINTER(vp)]
+    lib.ctr_create.restype = i32
+    lib.ctr_destroy.argtypes = [vp]
+    lib.ctr_destroy.restype = None
+    lib.ctr_last_error.argtypes = [vp]
+    lib.ctr_last_error.restype = ctypes.c_char_p
+    lib.ctr_set_stream.argtypes = [vp, vp]
+    lib.ctr_set_stream.restype = i32
+    lib.ctr_set_timing.argtypes = [vp, i32]
+    lib.ctr_set_timing.restype = i32
+    lib.ctr_stage_times.argtypes = [vp, ctypes.POINTER(ctypes.c_float), i32]
+    lib.ctr_stage_times.restype = i32
+    lib.ctr_kernel_launches.argtypes = [vp]
+    lib.ctr_kernel_launches.restype = i64
+    lib.ctr_mt3d_run.argtypes = [vp, ctypes.POINTER(Mt3dParams), ctypes.POINTER(Mt3dCounts)]
+    lib.ctr_mt3d_run.restype = i32
+    lib.ctr_mt3d_fetch.argtypes = [vp] + [vp] * 7
+    lib.ctr_mt3d_fetch.restype = i32
+    lib.ctr_mt3d_device_ptrs.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    lib.ctr_mt3d_device_ptrs.restype = i32
+    _bind_optional(lib)
+    _lib = lib
+    return lib
+
+
+def _bind_optional(lib):
+    """2D / 4D / post-processing entry points (bound when present in this build)."""
+    from . import _bindings
+    _bindings.bind(lib)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Engine(object):
+    """One context = one device + one stream.  Not thread-safe."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.ctr_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise EngineError("ctr_create(device=%d) failed (%d): %s" % (
+                device, rc, self.lib.ctr_last_error(None).decode()))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ctr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.ctr_last_error(self.h).decode()
+            if rc == -1:
+                raise ValueError("%s: %s" % (what, msg))
+            raise EngineError("%s failed (%d): %s" % (what, rc, msg))
+
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.ctr_set_stream(self.h, ctypes.c_void_p(int(cuda_stream))), "ctr_set_stream")
+
+    def set_timing(self, enabled=True):
+        self._check(self.lib.ctr_set_timing(self.h, 1 if enabled else 0), "ctr_set_timing")
+
+    def stage_times(self, n=8):
+        buf = (ctypes.c_float * n)()
+        self._check(self.lib.ctr_stage_times(self.h, buf, n), "ctr_stage_times")
+        return [float(x) for x in buf]
+
+    def kernel_launches(self):
+        return int(self.lib.ctr_kernel_launches(self.h))
+
+    # ------------------------------------------------------------------ 3D
+    def mt3d_run(self, field, value, origin=(0.0, 0.0, 0.0), delta=(1.0, 1.0, 1.0), flags=0,
+                 i_lo=0, i_hi=None, plane_offset=0, shape=None, dtype=None):
+        """field: C-contiguous numpy array [n0,n1,n2] float32/float64, or an integer device pointer
+        (then pass shape, dtype and FIELD_ON_DEVICE).  Returns Mt3dCounts."""
+        p = Mt3dParams()
+        if isinstance(field, np.ndarray):
+            if field.dtype not in (np.float32, np.float64):
+                field = field.astype(np.float64)
+            field = np.ascontiguousarray(field)
+            if field.ndim != 3:
+                raise ValueError("3D field expected")
+            self._keep = field
+            p.field = field.ctypes.data
+            p.dtype = F32 if field.dtype == np.float32 else F64
+            shape = field.shape
+            flags &= ~FIELD_ON_DEVICE
+        else:
+            p.field = int(field)
+            p.dtype = F32 if np.dtype(dtype) == np.float32 else F64
+            flags |= FIELD_ON_DEVICE
+        p.flags = flags
+        p.n0, p.n1, p.n2 = (int(s) for s in shape)
+        p.isovalue = float(value)
+        for a in range(3):
+            p.origin[a] = float(origin[a])
+            p.delta[a] = float(delta[a])
+        p.i_lo = int(i_lo)
+        p.i_hi = int(p.n0 if i_hi is None else i_hi)
+        p.plane_offset = int(plane_offset)
+        c = Mt3dCounts()
+        self._check(self.lib.ctr_mt3d_run(self.h, ctypes.byref(p), ctypes.byref(c)), "ctr_mt3d_run")
+        self._last3 = (flags, c)
+        return c
+
+    def mt3d_fetch(self, verts=True, normals=None, tris=True, keys=None, codes=None):
+        flags, c = self._last3
+        gd = np.float64 if flags & GEOM_F64 else np.float32
+        geom = not (flags & NO_GEOMETRY)
+        out = {}
+        if normals is None:
+            normals = bool(flags & WANT_NORMALS)
+        if keys is None:
+            keys = bool(flags & WANT_KEYS)
+        if codes is None:
+            codes = bool(flags & WANT_CODES)
+        V, T, C = int(c.n_verts), int(c.n_tris), int(c.n_codes)
+        a_v = np.empty((V, 3), dtype=gd) if (verts and geom) else None
+        a_n = np.empty((V, 3), dtype=gd) if (normals and geom) else None
+        a_t = np.empty((T, 3), dtype=np.int32) if (tris and geom) else None
+        a_k = np.empty((V,), dtype=np.uint64) if (keys and geom) else None
+        a_l = np.empty((V,), dtype=np.uint8) if (keys and geom) else None
+        a_c = np.empty((C,), dtype=np.int64) if codes else None
+        a_d = np.empty((C,), dtype=np.uint32) if codes else None
+        self._check(self.lib.ctr_mt3d_fetch(self.h, _ptr(a_v), _ptr(a_n), _ptr(a_t), _ptr(a_k), _ptr(a_l),
+                                            _ptr(a_c), _ptr(a_d)), "ctr_mt3d_fetch")
+        out.update(verts=a_v, normals=a_n, tris=a_t, keys=a_k, lowmin=a_l, cells=a_c, codes=a_d)
+        return out
+
+    def mt3d_device_ptrs(self):
+        v, n, t = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        self._check(self.lib.ctr_mt3d_device_ptrs(self.h, ctypes.byref(v), ctypes.byref(n), ctypes.byref(t)),
+                    "ctr_mt3d_device_ptrs")
+        return v.value, n.value, t.value
+
+
+_default = {}
+
+
+def default_engine(device=0):
+    """Process-wide engine per device (contexts are cheap to keep, expensive to warm)."""
+    e = _default.get(device)
+    if e is None or e.h is None:
+        e = _default[device] = Engine(device)
+    return e

@@ -1,0 +1,121 @@
+/* contourist_b200 -- C ABI of the B200-native isosurface engine (libcontourist_b200.so).
+ *
+ * The reference (AaronWatters/contourist) is pure Python and has NO plugin / FFI / operator
+ * interface; its boundary is the public Python class API.  This header is
+ * therefore the boundary a maintainer binds with ctypes (INTEGRATION.md shows the stub); every entry
+ * point names the reference function(s) whose work it replaces (paths are under
+ * /root/reference/contourist/).
+ *
+ * Conventions
+ *   - All entry points return 0 on success or a negative ctr_status; ctr_last_error() gives text.
+ *   - The caller owns every host buffer; the context owns all device memory and reuses it.
+ *   - Two-phase: *_run() computes on the device and reports sizes, *_fetch() copies the results
+ *     into caller buffers of exactly those sizes (any pointer may be NULL = "not wanted").
+ *   - A context is bound to one device and one stream; it is not thread-safe.  Calls are
+ *     synchronous on return.
+ *   - field[i][j][k] (C order, last axis contiguous) is the sample at grid point (i,j,k): exactly
+ *     the f(i,j,k) the reference's grid-level engines call (tetrahedral.py:129-130).
+ *   - Linear point index lin = (i*n1 + j)*n2 + k.  An edge key names a grid edge by its
+ *     component-wise-min endpoint and direction: 3D key = lin*8 + d, d = di*4+dj*2+dk in 1..7;
+ *     4D key = lin*16 + d, d in 1..15; 2D key = lin*4 + d, d = di*2+dj in 1..3.  This is the
+ *     reference's dict key (p_low, p_high) (tetrahedral.py:184-188) made canonical; `lowmin`
+ *     says which endpoint is the low one.
+ */
+#ifndef CONTOURIST_B200_H
+#define CONTOURIST_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CTR_API __attribute__((visibility("default")))
+#else
+#define CTR_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ctr_ctx ctr_ctx;
+
+typedef enum {
+  CTR_OK = 0,
+  CTR_ERR_BAD_ARG = -1,
+  CTR_ERR_CUDA = -2,
+  CTR_ERR_OOM = -3,
+  CTR_ERR_UNSUPPORTED = -4,
+  CTR_ERR_STATE = -5,
+  CTR_ERR_OVERFLOW = -6
+} ctr_status;
+
+typedef enum { CTR_F32 = 0, CTR_F64 = 1 } ctr_dtype;
+
+/* flags */
+#define CTR_FIELD_ON_DEVICE 1u /* `field` is a device pointer (no H2D copy)                          */
+#define CTR_GEOM_F64 2u        /* positions / normals computed and returned in fp64 (else fp32)      */
+#define CTR_WANT_NORMALS 4u    /* gradient normals (engine extension; the reference computes none)   */
+#define CTR_WANT_KEYS 8u       /* per-vertex edge key + orientation (parity / dedup across slabs)    */
+#define CTR_WANT_CODES 16u     /* compact (cell, 30-bit case code) list of emitting cells            */
+#define CTR_NO_GEOMETRY 32u    /* classification, counts and offsets only                            */
+
+/* ---- context ----------------------------------------------------------------------------------- */
+CTR_API int ctr_create(int device, ctr_ctx** out);
+CTR_API void ctr_destroy(ctr_ctx* ctx);
+/* ctx may be NULL: last error of a failed ctr_create. The pointer stays valid until the next call. */
+CTR_API const char* ctr_last_error(const ctr_ctx* ctx);
+/* Launch on an existing CUDA stream (a cudaStream_t passed as void*), e.g. torch's current stream. */
+CTR_API int ctr_set_stream(ctr_ctx* ctx, void* cuda_stream);
+/* Per-stage device times (ms, CUDA events) of the last *_run when timing is enabled.
+ * 3D stages: 0 H2D, 1 bitplane (classify), 2 count+scan, 3 emit vertices, 4 emit triangles, 5 codes. */
+CTR_API int ctr_set_timing(ctr_ctx* ctx, int enabled);
+CTR_API int ctr_stage_times(ctr_ctx* ctx, float* ms, int n);
+/* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
+CTR_API int64_t ctr_kernel_launches(const ctr_ctx* ctx);
+
+/* ---- 3D marching tetrahedra ---------------------------------------------------------------------
+ * Replaces, for an array-backed field, the reference's
+ *   grid_field.py:64-84     FunctionGrid.find_contour_crossing_grid_segments  (n_crossings, fmin, fmax)
+ *   tetrahedral.py:383-469  border_voxel / find_initial_voxels / expand_voxels (full scan instead of flood fill)
+ *   tetrahedral.py:554-595  enumerate_voxel_triangles / enumerate_tetrahedron_triangles (case codes, triangles)
+ *   tetrahedral.py:176-188,471-512  add_simplex / interpolate_pair / contour_pair_interpolation (keys, positions)
+ *   tetrahedral.py:604-614  extract_surface_geometry vertex numbering (ids = rank of the key)
+ *   tetrahedral.py:83-87 + grid_field.py:89-93  grid -> world coordinates
+ */
+typedef struct {
+  const void* field;    /* n0*n1*n2 samples, host or device (CTR_FIELD_ON_DEVICE)                     */
+  int32_t dtype;        /* ctr_dtype of field                                                        */
+  uint32_t flags;
+  int64_t n0, n1, n2;   /* SAMPLES per axis; voxels have origins in [0, n-2]                          */
+  double isovalue;
+  double origin[3];     /* world = grid*delta + origin (grid_field.py:89-93); use 0 / 1 for grid units */
+  double delta[3];
+  /* z-slab sharding; single GPU: i_lo = 0, i_hi = n0, plane_offset = 0.
+   * Voxel layers and owner planes i in [i_lo, i_hi) are emitted; planes outside are halo (needed:
+   * 1 below for normals, 2 above for the ids of the next shard's first plane).  plane_offset is the
+   * global index of array plane 0; keys and positions are global.                                   */
+  int64_t i_lo, i_hi, plane_offset;
+} ctr_mt3d_params;
+
+typedef struct {
+  int64_t n_verts;        /* vertices emitted by this call (= number of distinct edge keys)           */
+  int64_t n_tris;
+  int64_t n_active_cells; /* voxels that emit at least one triangle                                   */
+  int64_t n_crossings;    /* strictly crossing grid segments, grid_field.py:81                        */
+  int64_t n_codes;        /* entries of the (cell, code) list (CTR_WANT_CODES)                        */
+  double fmin, fmax;      /* grid_field.py:79-80                                                      */
+} ctr_mt3d_counts;
+
+CTR_API int ctr_mt3d_run(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out);
+/* verts/normals: [n_verts][3] float or double (CTR_GEOM_F64); tris: [n_tris][3] vertex ids, local to
+ * this call (0 = first emitted vertex; ids >= n_verts refer to the next shard's vertices);
+ * keys/lowmin: [n_verts]; cells/codes: [n_codes] linear voxel index ((i*(n1-1)+j)*(n2-1)+k, i global)
+ * and 30-bit case code (6 tets x (4-bit low mask | 16 if skipped by allclose)), unordered.            */
+CTR_API int ctr_mt3d_fetch(ctr_ctx* ctx, void* verts, void* normals, int32_t* tris, uint64_t* keys,
+                   uint8_t* lowmin, int64_t* cells, uint32_t* codes);
+/* Device pointers of the last run's outputs (valid until the next *_run on this context).          */
+CTR_API int ctr_mt3d_device_ptrs(ctr_ctx* ctx, void** verts, void** normals, int32_t** tris);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

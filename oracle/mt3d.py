@@ -1,0 +1,460 @@
+"""ORACLE (test infrastructure, not product code) -- 3D marching tetrahedra.
+
+CPU restatement in numpy of the reference's 3D hot path, as a FULL SCAN over every
+voxel (with `segment_endpoints=[]` + `search_for_endpoints()`
+the reference's seeded tracking visits exactly the voxels a full scan finds).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module.  The product (contourist_b200/) never does.
+
+Parity status: PINNED.  Checked against golden vectors produced by running the
+unmodified reference in the build container (tests/golden/make_golden.py ->
+tests/golden/*.npz; tests/test_oracle_golden.py) and against the reference's own
+known-answer test (contourist/test/test_tetrahedral.py:29-37).  Normals are NOT
+computed by the reference (html_demo.py:142 "normals": []), so `normals()` below
+is parity-UNPINNED: it is the definition, not a restatement.
+
+Reference lines restated here (all under /root/reference/contourist/):
+  tetrahedral.py:20-39    CUBE / TETRAHEDRA constants            -> CUBE, TETS
+  tetrahedral.py:383-394  border_voxel (active-voxel predicate)  -> active_cells
+  tetrahedral.py:561-595  enumerate_tetrahedron_triangles        -> tet_cases / extract
+  tetrahedral.py:471-487,506-511 contour_pair_interpolation      -> interpolate
+  tetrahedral.py:190-215  quantize_interpolations                -> postprocess
+  tetrahedral.py:353-375  remove_tiny_simplices                  -> postprocess
+  surface_geometry.py:14-50   clean_triangles                    -> postprocess
+  surface_geometry.py:52-140  orient_triangles                   -> orient
+  grid_field.py:64-84     find_contour_crossing_grid_segments    -> crossing_segments
+  grid_field.py:89-93     from_grid_coordinates                  -> to_world
+
+Conventions shared with the CUDA engine (include/contourist_b200.h):
+  * field[i, j, k] = f at grid point (i, j, k); C order, k contiguous.
+  * voxel origin o in [0, n-2]^3 ("cells"); linear point index lin = (i*n1 + j)*n2 + k.
+  * edge direction code d = di*4 + dj*2 + dk in 1..7 (the 7 Kuhn edge directions);
+    edge key = lin(min endpoint)*8 + d.  `lowmin` = 1 when the min endpoint is the
+    LOW end (f < value), i.e. the reference's key is (min, max); else (max, min).
+  * per-tet case code = 4-bit low mask (bit0 A, bit1 H, bit2 x_k, bit3 y_k for tet
+    [A, H, x_k, y_k]) | 16 if the tet is skipped by np.allclose(values, value);
+    cell code = sum(code_k << 5k), k = 0..5.
+  * 2-2 quads are split with the rule "what the reference would do if `set` were
+    `sorted`": [a, b] = sorted(least), [c, d] = sorted(most); triangles
+    (ad, ac, bc) and (ad, bd, bc)  (tetrahedral.py:592-595).
+"""
+import numpy as np
+
+RTOL = 1e-5
+ATOL = 1e-8
+
+# tetrahedral.py:20-29
+CUBE = np.array([(0, 0, 0), (0, 0, 1), (0, 1, 0), (0, 1, 1),
+                 (1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 1, 1)], dtype=np.int64)
+A, B, C, D, E, F, G, H = range(8)       # corner number = di*4 + dj*2 + dk
+# tetrahedral.py:32-39
+TETS = np.array([[A, H, B, D], [A, H, D, C], [A, H, C, G],
+                 [A, H, G, E], [A, H, E, F], [A, H, F, B]], dtype=np.int64)
+
+
+def _corner_views(field):
+    """8 views of shape (n0-1, n1-1, n2-1): value at each cube corner."""
+    n0, n1, n2 = field.shape
+    out = []
+    for (di, dj, dk) in CUBE:
+        out.append(field[di:n0 - 1 + di, dj:n1 - 1 + dj, dk:n2 - 1 + dk])
+    return out
+
+
+def near_f(fvals, value):
+    """np.allclose(value, fvals) element test: |value - f| <= atol + rtol*|f|  (tetrahedral.py:391)."""
+    fv = fvals.astype(np.float64)
+    return np.abs(value - fv) <= ATOL + RTOL * np.abs(fv)
+
+
+def near_v(fvals, value):
+    """np.allclose(fvals, value) element test: |f - value| <= atol + rtol*|value|  (tetrahedral.py:576)."""
+    fv = fvals.astype(np.float64)
+    return np.abs(fv - value) <= ATOL + RTOL * abs(float(value))
+
+
+def active_cells(field, value):
+    """Boolean (n0-1, n1-1, n2-1): tetrahedral.py:383-394 border_voxel on every in-range voxel."""
+    value = float(value)
+    cs = _corner_views(field)
+    mn = cs[0].astype(np.float64)
+    mx = cs[0].astype(np.float64)
+    allnear = near_f(cs[0], value)
+    for c in cs[1:]:
+        c64 = c.astype(np.float64)
+        mn = np.minimum(mn, c64)
+        mx = np.maximum(mx, c64)
+        allnear &= near_f(c, value)
+    return (~allnear) & (mn <= value) & (mx >= value)
+
+
+def tet_cases(field, value):
+    """uint32 (n0-1, n1-1, n2-1) packed per-cell case codes (see module docstring).
+
+    tetrahedral.py:561-578: low = f < value (strict), high otherwise; a tet is skipped when
+    either side is empty or np.allclose(values, value)."""
+    value = float(value)
+    cs = _corner_views(field)
+    low = [c.astype(np.float64) < value for c in cs]
+    nv = [near_v(c, value) for c in cs]
+    code = np.zeros(cs[0].shape, dtype=np.uint32)
+    for k, tet in enumerate(TETS):
+        m = np.zeros(cs[0].shape, dtype=np.uint32)
+        alln = np.ones(cs[0].shape, dtype=bool)
+        for b, corner in enumerate(tet):
+            m |= low[corner].astype(np.uint32) << b
+            alln &= nv[corner]
+        m |= alln.astype(np.uint32) << 4
+        code |= m << np.uint32(5 * k)
+    return code
+
+
+def tet_emits(code5):
+    """True where a 5-bit tet code produces triangles."""
+    m = code5 & 15
+    return (m != 0) & (m != 15) & ((code5 & 16) == 0)
+
+
+def extract(field, value, geom_dtype=np.float64):
+    """Full-scan raw extraction (before quantize/tiny/clean/orient).
+
+    Returns dict with
+      cells      int64 [Nc]      linear index (over the (n0-1,n1-1,n2-1) cell grid) of emitting cells, sorted
+      codes      uint32 [Nc]     packed case codes of those cells
+      keys       uint64 [V]      sorted unique edge keys
+      lowmin     uint8 [V]       orientation of the reference key (1: (min,max), 0: (max,min))
+      pos        geom_dtype [V,3] grid-coordinate position per key (tetrahedral.py:482-487)
+      tri_keys   uint64 [T,3]    triangles as key triples, in (cell, tet, split) order
+      tris       int32 [T,3]     same as indices into keys
+      tri_cell   int64 [T]       owning cell (linear cell index)
+      tri_tet    uint8 [T]       tet number 0..5
+    """
+    field = np.asarray(field)
+    value = float(value)
+    n0, n1, n2 = field.shape
+    act = active_cells(field, value)
+    code = tet_cases(field, value)
+    emits_any = np.zeros(act.shape, dtype=bool)
+    for k in range(6):
+        emits_any |= tet_emits((code >> np.uint32(5 * k)) & np.uint32(31))
+    sel = act & emits_any
+    ci, cj, ck = np.nonzero(sel)
+    cell_lin = (ci * (n1 - 1) + cj) * (n2 - 1) + ck
+    codes = code[sel]
+    tri_keys = []
+    tri_cell = []
+    tri_tet = []
+    tri_ord = []
+    lin0 = (ci * n1 + cj) * n2 + ck                      # lin of corner A
+    corner_lin = [lin0 + (int(d[0]) * n1 + int(d[1])) * n2 + int(d[2]) for d in CUBE]
+
+    def key_of(ca, cb):
+        # ca, cb corner numbers (python ints); min endpoint = smaller corner number
+        # (corner number order == lexicographic point order inside one cube).
+        lo_c, hi_c = (ca, cb) if ca < cb else (cb, ca)
+        d = hi_c - lo_c           # corner numbers are bit patterns; hi has all bits of lo here
+        return (corner_lin[lo_c].astype(np.uint64) << np.uint64(3)) | np.uint64(d)
+
+    for k, tet in enumerate(TETS):
+        c5 = (codes >> np.uint32(5 * k)) & np.uint32(31)
+        em = tet_emits(c5)
+        for mask in range(1, 15):
+            rows = np.nonzero(em & ((c5 & 15) == mask))[0]
+            if rows.size == 0:
+                continue
+            lows = sorted(int(tet[b]) for b in range(4) if (mask >> b) & 1)
+            highs = sorted(int(tet[b]) for b in range(4) if not (mask >> b) & 1)
+            least, most = lows, highs
+            if len(least) > len(most):
+                least, most = most, least
+            if len(least) == 1:
+                a = least[0]
+                b_, c_, d_ = most
+                tl = [((a, b_), (a, c_), (a, d_))]
+            else:
+                a, b_ = least
+                c_, d_ = most
+                tl = [((a, d_), (a, c_), (b_, c_)), ((a, d_), (b_, d_), (b_, c_))]
+            for s, tri in enumerate(tl):
+                ks = np.stack([key_of(u, w)[rows] for (u, w) in tri], axis=1)
+                tri_keys.append(ks)
+                tri_cell.append(cell_lin[rows])
+                tri_tet.append(np.full(rows.size, k, dtype=np.uint8))
+                tri_ord.append(cell_lin[rows] * 12 + k * 2 + s)
+    if tri_keys:
+        tri_keys = np.concatenate(tri_keys)
+        tri_cell = np.concatenate(tri_cell)
+        tri_tet = np.concatenate(tri_tet)
+        order = np.argsort(np.concatenate(tri_ord), kind="stable")
+        tri_keys, tri_cell, tri_tet = tri_keys[order], tri_cell[order], tri_tet[order]
+    else:
+        tri_keys = np.zeros((0, 3), dtype=np.uint64)
+        tri_cell = np.zeros((0,), dtype=np.int64)
+        tri_tet = np.zeros((0,), dtype=np.uint8)
+    keys = np.unique(tri_keys)
+    tris = np.searchsorted(keys, tri_keys).astype(np.int32)
+    lowmin, pos = interpolate(field, value, keys, geom_dtype)
+    return dict(cells=cell_lin.astype(np.int64), codes=codes, keys=keys, lowmin=lowmin, pos=pos,
+                tri_keys=tri_keys, tris=tris, tri_cell=tri_cell, tri_tet=tri_tet)
+
+
+def key_points(keys, shape):
+    """Decode keys -> (pmin[V,3], pmax[V,3]) integer grid points."""
+    n0, n1, n2 = shape
+    lin = (keys >> np.uint64(3)).astype(np.int64)
+    d = (keys & np.uint64(7)).astype(np.int64)
+    i = lin // (n1 * n2)
+    j = (lin // n2) % n1
+    k = lin % n2
+    pmin = np.stack([i, j, k], axis=1)
+    pmax = pmin + np.stack([(d >> 2) & 1, (d >> 1) & 1, d & 1], axis=1)
+    return pmin, pmax
+
+
+def interpolate(field, value, keys, geom_dtype=np.float64):
+    """tetrahedral.py:471-487: key oriented (low, high) by VALUE (swap iff flow > fhigh);
+    ratio = (z - flow)/(fhigh - flow), or 0.5 when np.allclose(fhigh - flow, 0);
+    x = low + ratio*(high - low) in grid coordinates.
+    geom_dtype float32 mirrors the engine's fp32 geometry mode (same formula in float)."""
+    shape = field.shape
+    pmin, pmax = key_points(keys, shape)
+    fmin = field[pmin[:, 0], pmin[:, 1], pmin[:, 2]]
+    fmax = field[pmax[:, 0], pmax[:, 1], pmax[:, 2]]
+    gd = np.dtype(geom_dtype)
+    fmin = fmin.astype(gd)
+    fmax = fmax.astype(gd)
+    swap = fmin > fmax                       # then low point is pmax
+    lowmin = (~swap).astype(np.uint8)
+    flow = np.where(swap, fmax, fmin)
+    fhigh = np.where(swap, fmin, fmax)
+    plow = np.where(swap[:, None], pmax, pmin).astype(gd)
+    phigh = np.where(swap[:, None], pmin, pmax).astype(gd)
+    z = gd.type(value)
+    den = fhigh - flow
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = (z - flow) / den
+    ratio = np.where(np.abs(den.astype(np.float64)) <= ATOL, gd.type(0.5), ratio).astype(gd)
+    pos = plow + ratio[:, None] * (phigh - plow)
+    return lowmin, pos.astype(gd)
+
+
+def gradient(field):
+    """fp64 central differences (one-sided at the domain boundary), grid units. [n0,n1,n2,3]"""
+    f = field.astype(np.float64)
+    g = np.zeros(f.shape + (3,), dtype=np.float64)
+    for ax in range(3):
+        sl = [slice(None)] * 3
+        lo = list(sl); hi = list(sl); mid = list(sl)
+        mid[ax] = slice(1, -1); lo[ax] = slice(0, -2); hi[ax] = slice(2, None)
+        g[tuple(mid) + (ax,)] = 0.5 * (f[tuple(hi)] - f[tuple(lo)])
+        first = list(sl); first[ax] = 0; second = list(sl); second[ax] = 1
+        g[tuple(first) + (ax,)] = f[tuple(second)] - f[tuple(first)]
+        last = list(sl); last[ax] = -1; prev = list(sl); prev[ax] = -2
+        g[tuple(last) + (ax,)] = f[tuple(last)] - f[tuple(prev)]
+    return g
+
+
+def normals(field, value, keys, geom_dtype=np.float64, delta=(1.0, 1.0, 1.0)):
+    """Gradient normals (parity UNPINNED by the reference -- engine definition):
+    n = normalize( (g(low) + ratio*(g(high) - g(low))) / delta ), g = central-difference gradient
+    (one-sided on the boundary), same `ratio` as the position. Zero gradient -> (0,0,0)."""
+    shape = field.shape
+    gd = np.dtype(geom_dtype)
+    pmin, pmax = key_points(keys, shape)
+    f = field.astype(gd)
+
+    def grad_at(p):
+        out = np.zeros((p.shape[0], 3), dtype=gd)
+        for ax in range(3):
+            n = shape[ax]
+            pl = p.copy(); ph = p.copy()
+            pl[:, ax] = np.maximum(p[:, ax] - 1, 0)
+            ph[:, ax] = np.minimum(p[:, ax] + 1, n - 1)
+            scale = np.where((p[:, ax] == 0) | (p[:, ax] == n - 1), gd.type(1.0), gd.type(0.5))
+            out[:, ax] = (f[ph[:, 0], ph[:, 1], ph[:, 2]] - f[pl[:, 0], pl[:, 1], pl[:, 2]]) * scale
+        return out
+
+    fmin = f[pmin[:, 0], pmin[:, 1], pmin[:, 2]]
+    fmax = f[pmax[:, 0], pmax[:, 1], pmax[:, 2]]
+    swap = fmin > fmax
+    flow = np.where(swap, fmax, fmin)
+    fhigh = np.where(swap, fmin, fmax)
+    den = fhigh - flow
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = (gd.type(value) - flow) / den
+    ratio = np.where(np.abs(den.astype(np.float64)) <= ATOL, gd.type(0.5), ratio).astype(gd)
+    gmin = grad_at(pmin)
+    gmax = grad_at(pmax)
+    glow = np.where(swap[:, None], gmax, gmin)
+    ghigh = np.where(swap[:, None], gmin, gmax)
+    g = glow + ratio[:, None] * (ghigh - glow)
+    g = g / np.asarray(delta, dtype=gd)[None, :]
+    nrm = np.sqrt((g * g).sum(axis=1))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = np.where(nrm[:, None] > 0, g / nrm[:, None], gd.type(0))
+    return out.astype(gd)
+
+
+def crossing_segments(field, value, count_only=False):
+    """grid_field.py:64-84 with skip=1 over an array holding samples 0..N (N+1 per axis):
+    for every v0 in [0,N-1]^3 and v1 = v0 + {0,1}^3, v1 != v0: seed iff (f0-v)*(f1-v) < 0.
+    Returns (maxf, minf, count) or the (v0_lin*8 + d) list."""
+    f = field.astype(np.float64) - float(value)
+    n0, n1, n2 = field.shape
+    base = f[:n0 - 1, :n1 - 1, :n2 - 1]
+    total = 0
+    out = []
+    for c in range(1, 8):
+        di, dj, dk = CUBE[c]
+        nb = f[di:n0 - 1 + di, dj:n1 - 1 + dj, dk:n2 - 1 + dk]
+        hit = (base * nb) < 0
+        if count_only:
+            total += int(hit.sum())
+        else:
+            i, j, k = np.nonzero(hit)
+            out.append((((i * n1 + j) * n2 + k).astype(np.uint64) << np.uint64(3)) | np.uint64(c))
+    fa = field.astype(np.float64)
+    if count_only:
+        return fa.max(), fa.min(), total
+    return fa.max(), fa.min(), np.sort(np.concatenate(out)) if out else np.zeros(0, np.uint64)
+
+
+def to_world(pos, mins, delta):
+    """grid_field.py:89-93."""
+    return np.asarray(pos, dtype=np.float64) * np.asarray(delta, dtype=np.float64) + np.asarray(mins, dtype=np.float64)
+
+
+# ----------------------------------------------------------------------------------------------
+# Stage 4b: the reference's serial post-processing, restated with the engine's deterministic
+# tie-breaks (SURVEY.md section 7 hard part 1: the reference's own choices depend on CPython set/dict order).
+# ----------------------------------------------------------------------------------------------
+
+def postprocess(keys, pos, tris, corner, divisions=10000, epsilon=1e-4, clean=True):
+    """tetrahedral.py:190-215 (quantize), :353-375 (tiny), surface_geometry.py:14-50 (clean).
+
+    Deterministic rules where the reference depends on dict/set order:
+      * quantize: the representative of a bucket is the key with the LARGEST key value
+        (reference: last in dict order, tetrahedral.py:198).
+      * tiny-triangle collapse: triangles are visited in ascending (sorted index triple) order and the
+        merge point is the position of the triangle's smallest vertex index (reference: points[0] in
+        frozenset order, tetrahedral.py:368).
+      * clean: triangles visited in ascending order; vertex renumbering = first use in that order.
+    Returns (vertices[V',3] float64 grid coords, triangles int64 [T',3] unoriented (sorted rows),
+             vertex_map int64 [V] (-1 = dropped))
+    """
+    pos = np.array(pos, dtype=np.float64)
+    corner = np.asarray(corner, dtype=np.int64)
+    V = len(keys)
+    # ---- quantize (topology only; positions unchanged: reference writes a dead attribute) ----
+    expander = ((divisions * 1.0) / corner).astype(np.int64)
+    q = (pos * expander).astype(np.int64)
+    # bucket id
+    _, inv = np.unique(q, axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    rep = np.zeros(inv.max() + 1 if V else 0, dtype=np.int64)
+    np.maximum.at(rep, inv, np.arange(V, dtype=np.int64))      # keys sorted -> largest index = largest key
+    vmap = rep[inv] if V else np.zeros(0, np.int64)
+    t = vmap[tris]
+    keep = (t[:, 0] != t[:, 1]) & (t[:, 0] != t[:, 2]) & (t[:, 1] != t[:, 2])
+    t = np.sort(t[keep], axis=1)
+    t = np.unique(t, axis=0) if len(t) else t.reshape(0, 3)
+    # ---- remove tiny simplices ----
+    inv_corner = 1.0 / corner
+    keep_rows = []
+    for r in range(len(t)):
+        pts = pos[t[r]]
+        dl = (pts.max(axis=0) - pts.min(axis=0)) * inv_corner
+        if dl.max() < epsilon:
+            pos[t[r]] = pts[0].copy()
+        else:
+            keep_rows.append(r)
+    t = t[keep_rows] if len(t) else t
+    used = np.unique(t)
+    remap = -np.ones(V, dtype=np.int64)
+    remap[used] = np.arange(len(used))
+    verts = pos[used]
+    t = remap[t]
+    if not clean:
+        vm = -np.ones(V, dtype=np.int64)
+        vm[used] = np.arange(len(used))
+        return verts, t, vm
+    # ---- clean_triangles ----
+    vertex_map = {}
+    keep_vertices = []
+    keep_tris = set()
+
+    def new_index(i):
+        if i in vertex_map:
+            return vertex_map[i]
+        vertex_map[i] = len(keep_vertices)
+        keep_vertices.append(verts[i])
+        return vertex_map[i]
+
+    for r in range(len(t)):
+        a, b, c = (int(x) for x in t[r])
+        Ap, Bp, Cp = verts[a], verts[b], verts[c]
+        cr = np.cross(Ap - Cp, Bp - Cp)
+        if np.all(np.abs(cr) <= ATOL):
+            for (i, j) in ((a, b), (a, c), (b, c)):
+                if np.all(np.abs(verts[i] - verts[j]) <= ATOL + RTOL * np.abs(verts[j])):
+                    vertex_map[j] = new_index(i)
+        else:
+            keep_tris.add(frozenset(new_index(i) for i in (a, b, c)))
+    out_t = np.array(sorted(tuple(sorted(x)) for x in keep_tris if len(x) == 3), dtype=np.int64).reshape(-1, 3)
+    vm = -np.ones(V, dtype=np.int64)
+    for i_local, i_global in enumerate(used):
+        if i_local in vertex_map:
+            vm[i_global] = vertex_map[i_local]
+    return np.array(keep_vertices, dtype=np.float64).reshape(-1, 3), out_t, vm
+
+
+def orient(verts, tris):
+    """surface_geometry.py:52-140 with compatible_triangle_test = always True.
+    Per connected component (edge adjacency): seed = the triangle at the max-x vertex with the largest
+    |cross.x| (ties: reference keeps the LAST in set order; here the largest sorted triple), wound so
+    cross(a-b, a-c).x > 0 (>= 0 kept as is), propagated across shared edges (DFS, LIFO).
+    Returns sorted list of oriented (i, j, k)."""
+    verts = np.asarray(verts, dtype=np.float64)
+    tl = [tuple(int(x) for x in row) for row in tris]
+    unoriented = set(frozenset(t) for t in tl if len(set(t)) == 3)
+    seg2tri = {}
+    pt2tri = {}
+    for t in sorted(unoriented, key=lambda s: tuple(sorted(s))):
+        a, b, c = sorted(t)
+        for i in (a, b, c):
+            pt2tri.setdefault(i, []).append(t)
+        for e in ((a, b), (b, c), (a, c)):
+            seg2tri.setdefault(frozenset(e), []).append(t)
+    orientations = {}
+    while unoriented:
+        vs = set()
+        for t in unoriented:
+            vs.update(t)
+        max_x, max_index = max((verts[i][0], i) for i in vs)
+        cands = [t for t in pt2tri[max_index] if t in unoriented]
+        init = None
+        maxdot = 0.0
+        for t in cands:
+            a, b, c = (verts[i] for i in sorted(t))
+            dotx = np.cross(a - b, a - c)[0]
+            if abs(dotx) >= abs(maxdot):
+                maxdot = dotx
+                init = t
+        o = tuple(sorted(init))
+        a, b, c = (verts[i] for i in o)
+        if np.cross(a - b, a - c)[0] < 0:
+            o = tuple(reversed(o))
+        stack = [(init, o)]
+        while stack:
+            t, o = stack.pop()
+            orientations[t] = o
+            unoriented.discard(t)
+            a, b, c = o
+            for (i1, i2) in ((c, b), (b, a), (a, c)):
+                e = frozenset((i1, i2))
+                for t2 in seg2tri[e]:
+                    if t2 != t and t2 not in orientations:
+                        (i3,) = t2 - e
+                        stack.append((t2, (i1, i2, i3)))
+    return sorted(orientations.values())

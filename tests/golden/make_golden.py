@@ -1,0 +1,121 @@
+"""Generate golden vectors by running the UNMODIFIED reference (build container only).
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+The reference is driven through its own public classes (Grid3DContour, GridContour4D,
+Multiple2DContourGrid) with an array-backed callable; the raw state is captured after the
+reference's own enumerate step and before its post-processing, then its post-processing is
+run by calling the reference's own methods in the reference's own order
+(tetrahedral.py:528-552, pentatopes.py:101-125).  See ref_harness.py for the py2->py3 shim.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as rh  # noqa: E402
+
+
+def array_callable(arr):
+    shape = arr.shape
+
+    def f(*idx):
+        ii = tuple(min(max(int(i), 0), n - 1) for i, n in zip(idx, shape))
+        return float(arr[ii])
+    return f
+
+
+def strict_seeds(arr, value):
+    """grid_field.py:64-84 restated vectorised ONLY to feed seeds to the reference engine
+    (the reference's own scan needs a FunctionGrid; results are identical, see test)."""
+    d = arr.ndim
+    n = [s - 1 for s in arr.shape]
+    base = arr[tuple(slice(0, k) for k in n)].astype(np.float64) - value
+    seeds = []
+    for c in range(1, 2 ** d):
+        off = [(c >> (d - 1 - a)) & 1 for a in range(d)]
+        nb = arr[tuple(slice(o, k + o) for o, k in zip(off, n))].astype(np.float64) - value
+        idx = np.argwhere(base * nb < 0)
+        for p in idx:
+            seeds.append((tuple(int(x) for x in p), tuple(int(x) + o for x, o in zip(p, off))))
+    return seeds
+
+
+# ------------------------------------------------------------------ 3D
+def fields3d():
+    out = {}
+    n = 13
+    g = np.linspace(-1, 1, n)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    out["sphere13"] = (X * X + Y * Y + Z * Z, 0.5)
+    out["wave11"] = (np.sin(3.1 * X[:11, :11, :11] + 0.3) * np.cos(2.3 * Y[:11, :11, :11]) + 0.7 * Z[:11, :11, :11] ** 2
+                     + 0.25 * np.sin(5 * Z[:11, :11, :11] * X[:11, :11, :11]), 0.2)
+    rng = np.random.default_rng(7)
+    out["noise8"] = (rng.standard_normal((8, 7, 9)).astype(np.float32).astype(np.float64), 0.1)
+    out["ints7"] = (rng.integers(-1, 2, size=(7, 7, 7)).astype(np.float64), 0.0)
+    plate = 0.3 + 1e-7 * rng.standard_normal((6, 6, 6))
+    plate[3:, :, :] += 0.4 * rng.standard_normal((3, 6, 6))
+    out["plateau6"] = (plate, 0.3)
+    return out
+
+
+def run3d(arr, value):
+    T = rh.load("tetrahedral")
+    f = array_callable(arr)
+    corner = [s - 1 for s in arr.shape]
+    seeds = strict_seeds(arr, value)
+    t0 = time.time()
+    G = T.Grid3DContour(corner[0], corner[1], corner[2], f, value, seeds)
+    # tetrahedral.py:535-540
+    G.find_initial_voxels()
+    while G.new_surface_voxels:
+        G.expand_voxels()
+    for triple in G.surface_voxels:
+        G.enumerate_voxel_triangles(triple)
+    corner_a = np.array(corner)
+    vox = np.array(sorted(v for v in G.surface_voxels
+                          if all(0 <= v[a] < corner[a] for a in range(3))), dtype=np.int64).reshape(-1, 3)
+    n_leak = len(G.surface_voxels) - len(vox)
+    pairs = list(G.interpolated_contour_pairs.keys())
+    simplices = []
+    for s in G.simplex_sets:
+        pts = np.array([p for pair in s for p in pair])
+        owner = pts.min(axis=0)
+        if np.all(owner >= 0) and np.all(owner < corner_a):
+            simplices.append(sorted(s))
+    simplices = sorted(simplices)
+    used = sorted(set(pair for s in simplices for pair in s))
+    raw_low = np.array([p[0] for p in used], dtype=np.int64).reshape(-1, 3)
+    raw_high = np.array([p[1] for p in used], dtype=np.int64).reshape(-1, 3)
+    raw_pos = np.array([G.interpolated_contour_pairs[p] for p in used], dtype=np.float64).reshape(-1, 3)
+    kidx = {p: i for i, p in enumerate(used)}
+    raw_tris = np.array([[kidx[p] for p in s] for s in simplices], dtype=np.int64).reshape(-1, 3)
+    # tetrahedral.py:541-552 (reference post-processing, its own code)
+    G.quantize_interpolations()
+    G.remove_tiny_simplices()
+    pts, tris = G.extract_points_and_triangles(True)
+    dt = time.time() - t0
+    fin_pts = np.array(pts, dtype=np.float64).reshape(-1, 3)
+    fin_tris = np.array(tris, dtype=np.int64).reshape(-1, 3)
+    return dict(field=arr, value=np.float64(value), voxels=vox, n_leak=np.int64(n_leak),
+                key_low=raw_low, key_high=raw_high, key_pos=raw_pos, tris=raw_tris,
+                final_points=fin_pts, final_tris=fin_tris, n_seeds=np.int64(len(seeds)),
+                seconds=np.float64(dt))
+
+
+def main():
+    which = sys.argv[1:] or ["3d"]
+    if "3d" in which:
+        for name, (arr, value) in fields3d().items():
+            g = run3d(arr, value)
+            np.savez_compressed(os.path.join(HERE, "mt3d_%s.npz" % name), **g)
+            print(name, arr.shape, "voxels", len(g["voxels"]), "leak", int(g["n_leak"]), "keys", len(g["key_low"]),
+                  "tris", len(g["tris"]), "final", g["final_points"].shape, g["final_tris"].shape,
+                  "%.1fs" % g["seconds"])
+
+
+if __name__ == "__main__":
+    main()
