@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: marching-tetrahedra extraction of a 512^3 fp32 volume on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 512]
+
+One "step" = one pass of the hot path over one synthetic 512^3 volume per GPU (BASELINE.json configs[2]:
+CT-like fp32 volume, single isovalue, indexed mesh with normals).  N > 1 (torchrun, one rank per GPU):
+weak scaling, each rank owns a 512-plane z-slab (+halo) of a (512*N) x 512 x 512 volume, extracts it
+independently and joins an NCCL all-gather of (n_verts, n_tris) -> global vertex offsets.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section 6 for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ISOVALUE = 0.5
+METRIC = "Gvoxels/s, 512^3 fp32 marching-tetrahedra extraction (indexed mesh + normals)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(object):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def _oracle_slab(args):
+    """Worker: numpy oracle (restatement of the reference's algorithm) on one z-slab."""
+    sub, value = args
+    from oracle import mt3d
+    r = mt3d.extract(sub, value, np.float32)
+    mt3d.normals(sub, value, r["keys"], np.float32)
+    return len(r["keys"]), len(r["tris"])
+
+
+def cpu_field(n_planes, n, seed=0):
+    """Host sample of the CT-like field family: n_planes x n x n fp32 (same generator family, numpy)."""
+    rng = np.random.default_rng(seed)
+    cen = rng.uniform(0.15, 0.85, size=(48, 3))
+    sig = rng.uniform(0.03, 0.12, size=(48, 3))
+    amp = rng.uniform(0.5, 1.0, size=48)
+    x = (np.arange(n_planes, dtype=np.float32) / max(n_planes - 1, 1) * 0.5 + 0.25).reshape(-1, 1, 1)
+    y = (np.arange(n, dtype=np.float32) / (n - 1)).reshape(1, -1, 1)
+    z = (np.arange(n, dtype=np.float32) / (n - 1)).reshape(1, 1, -1)
+    f = np.zeros((n_planes, n, n), dtype=np.float32)
+    for q in range(48):
+        f += np.float32(amp[q]) * np.exp(-0.5 * (((x - cen[q, 0]) / sig[q, 0]) ** 2 + ((y - cen[q, 1]) / sig[q, 1]) ** 2
+                                                 + ((z - cen[q, 2]) / sig[q, 2]) ** 2)).astype(np.float32)
+    f += (0.02 * rng.standard_normal(f.shape)).astype(np.float32) / 3.0
+    return f
+
+
+def time_oracle(field, value, cores):
+    """Oracle port over `cores` processes (independent z-slabs with a one-plane overlap)."""
+    import multiprocessing as mp
+    n0 = field.shape[0]
+    bounds = [round(r * (n0 - 1) / cores) for r in range(cores + 1)]
+    jobs = [(np.ascontiguousarray(field[bounds[r]:bounds[r + 1] + 1]), value) for r in range(cores)
+            if bounds[r + 1] > bounds[r]]
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_oracle_slab(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_oracle_slab, jobs)
+    dt = time.perf_counter() - t0
+    return dt, sum(r[1] for r in res)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference itself cannot
+    travel to the GPU box and would need hours at this size) on all host cores,
+    on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    n = 192
+    planes = max(cores * 6 + 1, 49)
+    field = cpu_field(planes, n)
+    vox = field.size
+    times = []
+    tris = 0
+    for s in range(args.warmup + args.steps):
+        dt, tris = time_oracle(field, ISOVALUE, cores)
+        if s >= args.warmup:
+            times.append(dt)
+    tot = sum(times)
+    val = vox * len(times) / tot / 1e9
+    sample = "%dx%dx%d fp32 sub-volume of the CT-like field per step, numpy oracle port, %d processes" % (planes, n, n, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Gvoxels/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / len(times) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "512^3 fp32 CT-like volume, isovalue 0.5 (BASELINE configs[2]); bounded sample: " + sample},
+            "mtris_per_s": tris * len(times) / tot / 1e6,
+            "cpu_baseline": {"value": val, "unit": "Gvoxels/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from contourist_b200 import engine as E
+    from contourist_b200 import synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.n
+    # this rank's slab of the (n*world) x n x n volume, with halo planes (1 below, 2 above)
+    n_total = n * world
+    a, b = rank * n, (rank + 1) * n
+    lo, hi = max(a - 1, 0), min(b + 2, n_total)
+    field = synthetic.ct_like(n, lo, hi, device=dev, n_total=n_total)
+    shape = (hi - lo, n, n)
+    eng = E.Engine(local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_timing(True)
+    flags = E.WANT_NORMALS
+    counts_dev = torch.zeros(2, dtype=torch.int64, device=dev)
+    gathered = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+
+    def step():
+        c = eng.mt3d_run(field.data_ptr(), ISOVALUE, shape=shape, dtype=np.float32, flags=flags,
+                         i_lo=a - lo, i_hi=b - lo, plane_offset=lo)
+        if world > 1:
+            counts_dev.copy_(torch.tensor([c.n_verts, c.n_tris], dtype=torch.int64), non_blocking=True)
+            dist.all_gather_into_tensor(gathered, counts_dev)     # -> exclusive scan = global vertex offsets
+        return c
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        c = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.kernel_launches()
+    stage_acc = np.zeros(8)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c = step()
+        stage_acc += np.array(eng.stage_times(8))
+    ev1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = eng.kernel_launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([c.n_tris, c.n_verts], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_step = float(tmax.item()) / args.steps
+    vox_all = float(n) ** 3 * world
+    value = vox_all / (ms_step * 1e-3) / 1e9
+    n_tris_all, n_verts_all = int(tot[0].item()), int(tot[1].item())
+
+    # ---- end-to-end through the C ABI with HOST buffers (H2D of the field + D2H of the mesh in the timed region)
+    host_field = torch.empty(field.shape, dtype=torch.float32, pin_memory=True)
+    host_field.copy_(field)
+    hf = host_field.numpy()
+    e2e_times = []
+    outs = None
+    for s in range(0 if args.no_e2e else 2 + max(1, min(args.steps, 5))):
+        barrier()
+        t1 = time.perf_counter()
+        ce = eng.mt3d_run(hf, ISOVALUE, flags=flags, i_lo=a - lo, i_hi=b - lo, plane_offset=lo)
+        outs = eng.mt3d_fetch()
+        if world > 1:
+            counts_dev.copy_(torch.tensor([ce.n_verts, ce.n_tris], dtype=torch.int64))
+            dist.all_gather_into_tensor(gathered, counts_dev)
+        barrier()
+        if s >= 2:
+            e2e_times.append(time.perf_counter() - t1)
+    e2e_t = torch.tensor([float(np.mean(e2e_times)) if e2e_times else float('nan')], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = vox_all / float(e2e_t.item()) / 1e9
+    h2d = hf.nbytes
+    d2h = (outs["verts"].nbytes + outs["normals"].nbytes + outs["tris"].nbytes) if outs else 0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    st = stage_acc / args.steps                       # ms: 0 H2D, 1 bitplane, 2 count+scan, 3 verts, 4 tris
+    field_bytes = float(np.prod(shape)) * 4
+    bit_ms = st[1]
+    achieved = field_bytes / (bit_ms * 1e-3) / 1e9 if bit_ms > 0 else None
+    alg_total = float(n) ** 3 * 4 + c.n_verts * 24 + c.n_tris * 12        # field + V*(3p+3p) + T*12
+    pipe_gbs = alg_total / (ms_step * 1e-3) / 1e9
+    # CPU baseline: oracle port, 1 core, bounded sample of the same field family
+    sub = cpu_field(33, 160)
+    t_cpu, _ = time_oracle(sub, ISOVALUE, 1) if not args.no_e2e else (float('nan'), 0)
+    cpu_val = sub.size / t_cpu / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2]: %d^3 fp32 CT-like volume per GPU (48 Gaussian blobs + smoothed noise), "
+                               "isovalue 0.5, indexed mesh + gradient normals, fp32 geometry" % n,
+                   "volume": [n_total, n, n], "sharding": "z-slabs, 1 plane halo below / 2 above, NCCL all-gather of counts",
+                   "l2": "inputs (%.0f MB field) larger than the 126 MB L2; no explicit flush" % (field_bytes / 1e6)},
+        "mtris_per_s": n_tris_all / (ms_step * 1e-3) / 1e6, "n_tris": n_tris_all, "n_verts": n_verts_all,
+        "stage_ms": {"bitplane": st[1], "count_scan": st[2], "emit_verts": st[3], "emit_tris": st[4],
+                     "wall_ms_per_step": wall / args.steps * 1e3},
+        "roofline": {"bound": "hbm", "kernel": "k_bitplane (field -> low/near bitplanes, the only full-field pass)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                     "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": field_bytes},
+        "pipeline_roofline": {"algorithmic_bytes": alg_total, "achieved": pipe_gbs, "frac": pipe_gbs / peak,
+                              "note": "whole step: (field + V*24 + T*12) / device time of the step"},
+        "cpu_baseline": {"value": cpu_val, "unit": "Gvoxels/s", "cores": 1, "kind": "port",
+                         "sample": "33x160x160 fp32 sub-volume of the CT-like field, numpy oracle port (extract + normals)"},
+        "e2e": {"value": e2e_val, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "note": "ctr_mt3d_run + ctr_mt3d_fetch with pinned host field and host outputs"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg and the CPU baseline (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

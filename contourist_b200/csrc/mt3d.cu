@@ -17,6 +17,7 @@
 // near bitplane and re-evaluated from the samples in fp64 (cell_emit_exact / edge_used_exact); everything
 // else is decided by bit logic.  There is no CPU fallback anywhere.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -35,17 +36,31 @@ __constant__ uint8_t c_tetmask[8][8];
 __constant__ uint8_t c_tet[6][4];
 
 struct Counters {                    // device counter block (mirrored to pinned host memory)
+  // stage 1 (bitplane)
   unsigned long long min_key;        // order-preserving encoding of fmin
   unsigned long long max_key;        // order-preserving encoding of fmax
+  unsigned int any_near;
+  unsigned int pad0;
+  // stage 2 (count + scan): zeroed before every launch of k_count_scan
   unsigned long long n_cells;        // emitting voxels
   unsigned long long n_cross;        // strict crossings
   unsigned long long total_vt;       // packed totals over the scanned range: T << 31 | V
-  unsigned long long total_act;      // packed active-word counts: actT << 31 | actV
+  unsigned long long total_act;      // packed list lengths: voxels << 31 | owners
   unsigned long long v_emit;         // vertex count at the start of plane i_hi (vertices this call emits)
-  unsigned int any_near;
   unsigned int ticket;
-  unsigned int n_codes;
-  unsigned int pad;
+  unsigned int pad1;
+};
+constexpr size_t COUNTERS_STAGE2_OFFSET = 24;
+
+// exact n / d for 32-bit n, d via one 64-bit multiply-high (M = ceil(2^64 / d))
+struct FastDiv {
+  unsigned long long M;
+  unsigned d;
+  __host__ void init(unsigned dd) {
+    d = dd;
+    M = dd <= 1 ? 0ull : (~0ull / dd) + 1ull;
+  }
+  __device__ __forceinline__ unsigned div(unsigned n) const { return d <= 1 ? n : (unsigned)__umul64hi((unsigned long long)n, M); }
 };
 
 template <typename T>
@@ -58,8 +73,18 @@ struct Grid {
   long long plane_offset;
   double v;                          // isovalue
   double tolv;                       // 1e-8 + 1e-5*|v|
-  int any_near;                      // filled in-kernel from *near_flag
-  const unsigned* near_flag;
+  // allclose handling is local: rowflag[i*n1+j] != 0 iff some sample of rows (i..i+2, j..j+2) lies inside the
+  // conservative allclose hull; kernels copy it into any_near before touching a word of row (i, j).
+  int any_near;
+  const uint8_t* rowflag;
+  FastDiv divW, divN1;
+  __device__ __forceinline__ void word_coords(unsigned gw, int& i, int& j, int& w) const {
+    unsigned row = divW.div(gw);
+    w = (int)(gw - row * (unsigned)W);
+    unsigned ii = divN1.div(row);
+    i = (int)ii;
+    j = (int)(row - ii * (unsigned)n1);
+  }
 };
 
 __device__ __forceinline__ unsigned long long order_key(double x) {
@@ -68,66 +93,300 @@ __device__ __forceinline__ unsigned long long order_key(double x) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stage 1: field -> bitplanes.  One warp converts 32 consecutive samples of a row per step.
+// Stage 1: field -> low bitplane (the only pass over the whole field; HBM-bound), plus the "any sample
+// near the isovalue" flag and optional min/max.  Near words are written with the low words; a word
+// that has a near sample also raises the (dilated) row flags that switch later stages to their exact paths.
+//   k_bitplane_generic : any shape (rows padded to whole words), one warp converts 32 samples per step.
+//   k_bitplane_vec     : rows a multiple of 32 samples: the volume is one linear stream; 128-bit loads.
+//   k_bitplane_tma     : same stream staged through shared memory by TMA bulk copies (cp.async.bulk +
+//                        mbarrier full/empty ring): one producer lane + 8 consumer warps per CTA; consumers
+//                        read the staged samples bank-conflict-free and ballot straight into bit words.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int UNROLL>
-__global__ void __launch_bounds__(256) k_bitplane(const T* __restrict__ f, long long nrows, int n2, int W,
-                                                  T thr, T near_lo, T near_hi, uint32_t* __restrict__ bits,
-                                                  uint32_t* __restrict__ nbits, Counters* ctr) {
-  const unsigned lane = lane_id();
-  const long long nwords = nrows * W;
-  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
-  long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  T mn = INFINITY, mx = -INFINITY;
-  unsigned anynear = 0;
-  for (; g < nwords; g += warps * UNROLL) {
-    T val[UNROLL];
-    bool ok[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      long long gu = g + (long long)u * warps;
-      ok[u] = false;
-      val[u] = (T)0;
-      if (gu < nwords) {
-        long long row = gu / W;
-        int w = (int)(gu - row * W);
-        int k = w * 32 + (int)lane;
-        if (k < n2) {
-          ok[u] = true;
-          val[u] = __ldg(f + row * (long long)n2 + k);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      long long gu = g + (long long)u * warps;
-      if (gu < nwords) {                       // warp-uniform
-        bool lo = ok[u] && (val[u] < thr);
-        bool nr = ok[u] && (val[u] >= near_lo) && (val[u] <= near_hi);
-        unsigned wl = __ballot_sync(0xffffffffu, lo);
-        unsigned wn = __ballot_sync(0xffffffffu, nr);
-        if (lane == 0) {
-          bits[gu] = wl;
-          nbits[gu] = wn;
-        }
-        anynear |= wn;
-        if (ok[u]) {
-          mn = fmin(mn, val[u]);               // fmin/fmax ignore NaN
-          mx = fmax(mx, val[u]);
-        }
-      }
-    }
-  }
+struct RowGeom {
+  uint8_t* rowflag;
+  FastDiv divW, divN1;
+  int n1;
+};
+
+// a word of row `row` holds a near sample: flag every word-row whose 3x3 row neighbourhood contains it
+__device__ __noinline__ void flag_rows(const RowGeom& rg, unsigned row) {
+  const unsigned i = rg.divN1.div(row), j = row - i * (unsigned)rg.n1;
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b)
+      if ((int)i - a >= 0 && (int)j - b >= 0) rg.rowflag[(size_t)(i - a) * rg.n1 + (j - b)] = 1;
+}
+
+template <typename T>
+__device__ __forceinline__ void minmax_commit(T mn, T mx, bool anynear, Counters* ctr) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
-  if (lane == 0) {
-    atomicMin(&ctr->min_key, order_key((double)mn));
-    atomicMax(&ctr->max_key, order_key((double)mx));
-    if (anynear) atomicOr(&ctr->any_near, 1u);
+  (void)anynear;
+  if (lane_id() == 0) {
+    if (mn <= mx) {
+      atomicMin(&ctr->min_key, order_key((double)mn));
+      atomicMax(&ctr->max_key, order_key((double)mx));
+    }
   }
+}
+
+template <typename T, int UNROLL, bool MINMAX>
+__global__ void __launch_bounds__(256) k_bitplane_generic(const T* __restrict__ f, unsigned nrows, int n2, int W,
+                                                          T thr, T near_lo, T near_hi, uint32_t* __restrict__ bits,
+                                                          uint32_t* __restrict__ nbits, RowGeom rg, Counters* ctr) {
+  const unsigned lane = lane_id();
+  const unsigned nwords = nrows * (unsigned)W;
+  const unsigned warps = gridDim.x * (blockDim.x >> 5);
+  unsigned g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  T mn = INFINITY, mx = -INFINITY;
+  bool anynear = false;
+  for (; g < nwords; g += warps * UNROLL) {
+    T val[UNROLL];
+    bool ok[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      unsigned gu = g + (unsigned)u * warps;
+      ok[u] = false;
+      val[u] = (T)0;
+      if (gu < nwords) {
+        unsigned row = gu / (unsigned)W;
+        int k = (int)(gu - row * (unsigned)W) * 32 + (int)lane;
+        if (k < n2) {
+          ok[u] = true;
+          val[u] = __ldg(f + (size_t)row * n2 + k);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      unsigned gu = g + (unsigned)u * warps;
+      if (gu < nwords) {                       // warp-uniform
+        unsigned wl = __ballot_sync(0xffffffffu, ok[u] && (val[u] < thr));
+        unsigned wn = __ballot_sync(0xffffffffu, ok[u] && (val[u] >= near_lo) && (val[u] <= near_hi));
+        if (lane == 0) {
+          bits[gu] = wl;
+          nbits[gu] = wn;
+          if (wn) flag_rows(rg, gu / (unsigned)W);
+        }
+        if (ok[u]) {
+          if (MINMAX) {
+            mn = fmin(mn, val[u]);             // fmin/fmax ignore NaN
+            mx = fmax(mx, val[u]);
+          }
+        }
+      }
+    }
+  }
+  minmax_commit(mn, mx, anynear, ctr);
+}
+
+// 16 bytes = VEC samples per lane; one warp-wide 128-bit load covers 32*VEC samples = VEC bit words.
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  static constexpr int VEC = 4;
+  typedef float4 type;
+  __device__ static __forceinline__ void get(const float4& v, float out[4]) { out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w; }
+};
+template <>
+struct Vec16<double> {
+  static constexpr int VEC = 2;
+  typedef double2 type;
+  __device__ static __forceinline__ void get(const double2& v, double out[2]) { out[0] = v.x; out[1] = v.y; }
+};
+
+template <typename T, int UNROLL, bool MINMAX>
+__global__ void __launch_bounds__(256) k_bitplane_vec(const T* __restrict__ f, size_t nsamp, T thr, T near_lo, T near_hi,
+                                                      uint32_t* __restrict__ bits, uint32_t* __restrict__ nbits, RowGeom rg,
+                                                      Counters* ctr) {
+  typedef typename Vec16<T>::type V;
+  constexpr int VEC = Vec16<T>::VEC;
+  constexpr int GROUP = 32 / VEC;               // lanes per output word
+  const unsigned lane = lane_id();
+  const size_t nchunks = (nsamp + 32 * VEC - 1) / (32 * VEC);
+  const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
+  size_t c = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  T mn = INFINITY, mx = -INFINITY;
+  bool anynear = false;
+  const V* fv = reinterpret_cast<const V*>(f);
+  for (; c < nchunks; c += warps * UNROLL) {
+    V v[UNROLL];
+    bool ok[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      size_t cu = c + (size_t)u * warps;
+      size_t s0 = (cu * 32 + lane) * VEC;
+      ok[u] = cu < nchunks && s0 < nsamp;
+      if (ok[u]) v[u] = __ldcs(fv + cu * 32 + lane);       // streaming load (evict-first)
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      size_t cu = c + (size_t)u * warps;
+      if (cu >= nchunks) continue;                          // warp-uniform
+      T x[VEC];
+      Vec16<T>::get(v[u], x);
+      unsigned lo = 0, nr = 0;
+      if (ok[u]) {
+        T m4 = x[0], M4 = x[0];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+          lo |= (x[q] < thr ? 1u : 0u) << q;
+          m4 = fmin(m4, x[q]);
+          M4 = fmax(M4, x[q]);
+        }
+        if (MINMAX) {
+          mn = fmin(mn, m4);
+          mx = fmax(mx, M4);
+        }
+        if (!(M4 < near_lo || m4 > near_hi)) {              // rarely taken: some sample may be in the hull
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) nr |= ((x[q] >= near_lo) && (x[q] <= near_hi) ? 1u : 0u) << q;
+        }
+      }
+      unsigned wl = lo << (VEC * (lane & (GROUP - 1)));
+#pragma unroll
+      for (int o = 1; o < GROUP; o <<= 1) wl |= __shfl_xor_sync(0xffffffffu, wl, o);
+      unsigned wn = 0;
+      if (__any_sync(0xffffffffu, nr != 0)) {               // rare
+        wn = nr << (VEC * (lane & (GROUP - 1)));
+#pragma unroll
+        for (int o = 1; o < GROUP; o <<= 1) wn |= __shfl_xor_sync(0xffffffffu, wn, o);
+      }
+      if ((lane & (GROUP - 1)) == 0 && ok[u]) {
+        const size_t word = cu * VEC + lane / GROUP;
+        bits[word] = wl;
+        nbits[word] = wn;
+        if (wn) flag_rows(rg, rg.divW.div((unsigned)word));
+      }
+    }
+  }
+  minmax_commit(mn, mx, anynear, ctr);
+}
+
+// ---- TMA (bulk async copy) variant ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int TMA_STAGES = 6;
+constexpr int TMA_CHUNK = 16384;                 // bytes per stage
+constexpr int TMA_CONSUMER_WARPS = 8;
+
+template <typename T, bool MINMAX>
+__global__ void __launch_bounds__((TMA_CONSUMER_WARPS + 1) * 32) k_bitplane_tma(const T* __restrict__ f, size_t nbytes,
+                                                                                  T thr, T near_lo, T near_hi,
+                                                                                  uint32_t* __restrict__ bits,
+                                                                                  uint32_t* __restrict__ nbits, RowGeom rg,
+                                                                                  Counters* ctr) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)TMA_STAGES * TMA_CHUNK);
+  uint64_t* empty = full + TMA_STAGES;
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TMA_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], TMA_CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const size_t nchunks = (nbytes + TMA_CHUNK - 1) / TMA_CHUNK;
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(f);
+  if (warp == TMA_CONSUMER_WARPS) {
+    if (lane == 0) {
+      unsigned it = 0;
+      for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+        const int s = it % TMA_STAGES;
+        const unsigned ph = (it / TMA_STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);                           // first round passes immediately
+        size_t off = c * (size_t)TMA_CHUNK;
+        unsigned bytes = (unsigned)((nbytes - off) < (size_t)TMA_CHUNK ? (nbytes - off) : (size_t)TMA_CHUNK);
+        mbar_expect_tx(&full[s], bytes);
+        tma_bulk_g2s(smem + (size_t)s * TMA_CHUNK, src + off, bytes, &full[s]);
+      }
+    }
+    return;
+  }
+  constexpr int NW = TMA_CHUNK / (32 * (int)sizeof(T));          // bit words per stage
+  constexpr int WPW = NW / TMA_CONSUMER_WARPS;                   // words per warp per stage (<= 32)
+  static_assert(WPW >= 1 && WPW <= 32, "stage geometry");
+  T mn = INFINITY, mx = -INFINITY;
+  bool anynear = false;
+  unsigned it = 0;
+  for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+    const int s = it % TMA_STAGES;
+    const unsigned ph = (it / TMA_STAGES) & 1u;
+    const size_t off = c * (size_t)TMA_CHUNK;
+    const unsigned bytes = (unsigned)((nbytes - off) < (size_t)TMA_CHUNK ? (nbytes - off) : (size_t)TMA_CHUNK);
+    const unsigned words_here = bytes / (32u * (unsigned)sizeof(T));
+    const T* sv = reinterpret_cast<const T*>(smem + (size_t)s * TMA_CHUNK) + (size_t)warp * WPW * 32;
+    mbar_wait(&full[s], ph);
+    T val[WPW];
+#pragma unroll
+    for (int q = 0; q < WPW; ++q) val[q] = sv[q * 32 + lane];    // conflict-free: lane <-> bank
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);                       // stage is in registers: release it early
+    unsigned mine = 0, mine_n = 0;
+    const unsigned wbase = warp * WPW;
+    bool nearhere = false;
+#pragma unroll
+    for (int q = 0; q < WPW; ++q) {
+      if (wbase + q >= words_here) break;                        // warp-uniform: partial last chunk
+      unsigned wl = __ballot_sync(0xffffffffu, val[q] < thr);
+      if ((int)lane == q) mine = wl;
+      nearhere |= (val[q] >= near_lo) && (val[q] <= near_hi);
+      if (MINMAX) {
+        mn = fmin(mn, val[q]);
+        mx = fmax(mx, val[q]);
+      }
+    }
+    const size_t word0 = off / (32 * sizeof(T)) + wbase;
+    if (__any_sync(0xffffffffu, nearhere)) {                     // rare: materialise the near words of this warp
+#pragma unroll
+      for (int q = 0; q < WPW; ++q) {
+        if (wbase + q >= words_here) break;
+        unsigned wn = __ballot_sync(0xffffffffu, (val[q] >= near_lo) && (val[q] <= near_hi));
+        if ((int)lane == q) {
+          mine_n = wn;
+          if (wn) flag_rows(rg, rg.divW.div((unsigned)(word0 + q)));
+        }
+      }
+    }
+    if ((int)lane < WPW && wbase + lane < words_here) {
+      bits[word0 + lane] = mine;
+      nbits[word0 + lane] = mine_n;
+    }
+  }
+  minmax_commit(mn, mx, anynear, ctr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -144,7 +403,7 @@ __device__ __forceinline__ double sample(const Grid<T>& g, int i, int j, int k) 
 
 // 6-bit mask of the tets of voxel (i,j,k) that emit triangles; also returns the 30-bit case code.
 template <typename T>
-__device__ unsigned cell_emit_exact(const Grid<T>& g, int i, int j, int k, unsigned* code_out) {
+__device__ __noinline__ unsigned cell_emit_exact(const Grid<T>& g, int i, int j, int k, unsigned* code_out) {
   if (code_out) *code_out = 0;
   if (i < 0 || j < 0 || k < 0 || i >= g.n0 - 1 || j >= g.n1 - 1 || k >= g.n2 - 1) return 0;
   double fv[8];
@@ -177,7 +436,7 @@ __device__ unsigned cell_emit_exact(const Grid<T>& g, int i, int j, int k, unsig
 
 // Is the crossing edge p -> p+d used by any emitted triangle?  (OR over the voxels / tets that contain it.)
 template <typename T>
-__device__ bool edge_used_exact(const Grid<T>& g, int i, int j, int k, int d) {
+__device__ __noinline__ bool edge_used_exact(const Grid<T>& g, int i, int j, int k, int d) {
   for (int s = 0; s < 8; ++s) {
     if (s & d) continue;
     unsigned tm = c_tetmask[d][s];
@@ -273,125 +532,198 @@ __device__ __forceinline__ void tet_words(const Planes& pl, const Planes* npl, u
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stage 2: counts per word + fused decoupled-lookback scan.
+// used-edge words of an owner word (index d-1), allclose-ambiguous edges resolved exactly (serial, rare)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __noinline__ void resolve_used_exact(const Grid<T>& g, int i, int j, int w, uint32_t used[7]) {
+  Planes npl;
+  load_planes(g, g.nbits, i, j, w, npl);
+  for (int d = 1; d <= 7; ++d) {
+    uint32_t c = used[d - 1] & npl.P[0] & dir_plane(npl, d);
+    while (c) {
+      int b = __ffs(c) - 1;
+      c &= c - 1;
+      if (!edge_used_exact(g, i, j, w * 32 + b, d)) used[d - 1] &= ~(1u << b);
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void owner_used(const Grid<T>& g, const Planes& pl, int i, int j, int w, uint32_t used[7]) {
+  cross_words(pl, used);
+  if (g.any_near) resolve_used_exact(g, i, j, w, used);
+}
+
+__device__ __forceinline__ unsigned gather7(const uint32_t u[7], int b) {
+  unsigned m = 0;
+#pragma unroll
+  for (int d = 0; d < 7; ++d) m |= ((u[d] >> b) & 1u) << d;
+  return m;
+}
+
+__device__ __forceinline__ unsigned tet_mask_of(unsigned corner8, int t) {
+  // tets [A,H,x,y] with (x,y) = (B,D),(D,C),(C,G),(G,E),(E,F),(F,B)  (tetrahedral.py:32-39)
+  const int xs[6] = {1, 3, 2, 6, 4, 5};
+  const int ys[6] = {3, 2, 6, 4, 5, 1};
+  return (corner8 & 1u) | (((corner8 >> 7) & 1u) << 1) | (((corner8 >> xs[t]) & 1u) << 2) | (((corner8 >> ys[t]) & 1u) << 3);
+}
+
+// strict-crossing correction and exact tet counts of one word: the rare, allclose-dependent part of stage 2
+template <typename T>
+__device__ __noinline__ void count_word_exact(const Grid<T>& g, const Planes& pl, int i, int j, int w, bool cells_ok,
+                                              unsigned& ncross, unsigned& ntri, uint32_t& emitting) {
+  Planes npl;
+  load_planes(g, g.nbits, i, j, w, npl);
+  if (cells_ok) {
+    uint32_t xs[7];
+    cross_words(pl, xs);
+    for (int d = 1; d <= 7; ++d) {
+      // not strict when the HIGH endpoint equals the isovalue exactly (then (f0-v)*(f1-v) == 0)
+      uint32_t A = pl.P[0], O = dir_plane(pl, d);
+      uint32_t c = xs[d - 1] & pl.kp1 & ((~A & npl.P[0]) | (~O & dir_plane(npl, d)));
+      while (c) {
+        int b = __ffs(c) - 1;
+        c &= c - 1;
+        bool a_high = !((A >> b) & 1u);
+        int k = w * 32 + b;
+        double fh = a_high ? sample(g, i, j, k) : sample(g, i + ((d >> 2) & 1), j + ((d >> 1) & 1), k + (d & 1));
+        if (fh == g.v) --ncross;
+      }
+    }
+    uint32_t odd[6], two[6], cand;
+    tet_words(pl, &npl, pl.kp1, odd, two, cand);
+    while (cand) {
+      int b = __ffs(cand) - 1;
+      cand &= cand - 1;
+      // remove the fast-path contribution of this voxel, add the exact one
+      for (int q = 0; q < 6; ++q) ntri -= ((odd[q] >> b) & 1u) + 2u * ((two[q] >> b) & 1u);
+      emitting &= ~(1u << b);
+      unsigned e = cell_emit_exact(g, i, j, w * 32 + b, nullptr);
+      if (e) emitting |= 1u << b;
+      for (int q = 0; q < 6; ++q)
+        if ((e >> q) & 1u) ntri += ((odd[q] >> b) & 1u) ? 1u : 2u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 2: per-word counts from the bitplanes + fused single-pass decoupled-lookback scan.
+//   A  every thread tests 4 words of the tile (does anything cross here?) and the block compacts the
+//      interesting ones in shared memory;
+//   B  interesting words are dealt out evenly: vertex / triangle / owner / voxel counts per word;
+//   C  block scan + decoupled look-back across tiles -> exclusive offsets per word;
+//   D  interesting words again: write vbase and the compacted, ordered lists of
+//        active owners (own_id = word<<13 | bit<<8 | p_low<<7 | mask7, own_voff = first vertex id)
+//        active voxels (cell_id = word<<19 | bit<<14 | emit6<<8 | corner8, cell_toff = first triangle).
 // ------------------------------------------------------------------------------------------------
 constexpr int CS_THREADS = 256;
 constexpr int CS_ITEMS = 4;
 constexpr int CS_TILE = CS_THREADS * CS_ITEMS;
 
-template <typename T>
-__global__ void __launch_bounds__(CS_THREADS) k_count_scan(Grid<T> gin, long long word0, long long nwords_scan,
-                                                           uint32_t* __restrict__ vbase, uint32_t* __restrict__ tbase,
-                                                           uint32_t* __restrict__ list_v, uint32_t* __restrict__ list_t,
-                                                           unsigned long long* status_vt, unsigned long long* status_act,
-                                                           Counters* ctr, int ntiles) {
-  __shared__ unsigned s_tile;
-  __shared__ unsigned long long s_warp_vt[CS_THREADS / 32], s_warp_act[CS_THREADS / 32];
-  __shared__ unsigned long long s_excl_vt, s_excl_act;
-  Grid<T> g = gin;
-  g.any_near = (int)*gin.near_flag;
-  if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket, 1u);
-  __syncthreads();
-  const int tile = (int)s_tile;
-  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+struct CsShared {
+  uint32_t own[CS_TILE], emit[CS_TILE];
+  uint32_t pv[CS_TILE], pt[CS_TILE], po[CS_TILE], pc[CS_TILE];
+  unsigned short cv[CS_TILE], ct[CS_TILE];
+  unsigned short list[CS_TILE];
+  unsigned long long warp_vt[CS_THREADS / 32], warp_act[CS_THREADS / 32];
+  unsigned long long excl_vt, excl_act;
+  unsigned tile, nint;
+};
 
-  unsigned cv[CS_ITEMS], ct[CS_ITEMS];
-  bool emitv[CS_ITEMS];
-  unsigned ncells = 0, ncross = 0;
-  const long long plane_words = (long long)g.n1 * g.W;
-  const long long first = (long long)tile * CS_TILE + (long long)threadIdx.x * CS_ITEMS;
+template <typename T>
+__global__ void __launch_bounds__(CS_THREADS) k_count_scan(Grid<T> gin, unsigned word0, unsigned nwords_scan,
+                                                           uint32_t* __restrict__ vbase,
+                                                           unsigned long long* __restrict__ own_id,
+                                                           uint32_t* __restrict__ own_voff,
+                                                           unsigned long long* __restrict__ cell_id,
+                                                           uint32_t* __restrict__ cell_toff, unsigned cap_own,
+                                                           unsigned cap_cell, unsigned long long* status_vt,
+                                                           unsigned long long* status_act, Counters* ctr, int ntiles) {
+  __shared__ CsShared sh;
+  Grid<T> g = gin;
+  g.any_near = 0;
+  if (threadIdx.x == 0) {
+    sh.tile = atomicAdd(&ctr->ticket, 1u);
+    sh.nint = 0;
+  }
+  __syncthreads();
+  const int tile = (int)sh.tile;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
+  const unsigned emit_end = (unsigned)g.i_hi * plane_words;      // words below this are emitted
+  const unsigned tile0 = (unsigned)tile * CS_TILE;
+
+  // ---- A: dense quick test, 4 strided words per thread
 #pragma unroll
-  for (int it = 0; it < CS_ITEMS; ++it) {
-    cv[it] = 0;
-    ct[it] = 0;
-    emitv[it] = false;
-    long long rel = first + it;
-    if (rel >= nwords_scan) continue;
-    long long gw = word0 + rel;
-    long long row = gw / g.W;
-    int w = (int)(gw - row * g.W);
-    int i = (int)(row / g.n1), j = (int)(row - (long long)i * g.n1);
-    Planes pl, npl;
+  for (int q = 0; q < CS_ITEMS; ++q) {
+    const unsigned wl = (unsigned)q * CS_THREADS + threadIdx.x;
+    const unsigned rel = tile0 + wl;
+    bool interesting = false;
+    if (rel < nwords_scan) {
+      int i, j, w;
+      g.word_coords(word0 + rel, i, j, w);
+      Planes pl;
+      load_planes(g, g.bits, i, j, w, pl);
+      uint32_t x[7];
+      cross_words(pl, x);
+      interesting = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6]) != 0;
+    }
+    sh.cv[wl] = 0;
+    sh.ct[wl] = 0;
+    sh.own[wl] = 0;
+    sh.emit[wl] = 0;
+    const unsigned m = __ballot_sync(0xffffffffu, interesting);
+    unsigned base = 0;
+    if (lane == 0 && m) base = atomicAdd(&sh.nint, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (interesting) sh.list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)wl;
+  }
+  __syncthreads();
+  const unsigned nint = sh.nint;
+
+  // ---- B: counts of the interesting words, one word per thread per round
+  unsigned ncross = 0, ncells = 0;
+  for (unsigned idx = threadIdx.x; idx < nint; idx += CS_THREADS) {
+    const unsigned wl = sh.list[idx];
+    const unsigned gw = word0 + tile0 + wl;
+    int i, j, w;
+    g.word_coords(gw, i, j, w);
+    g.any_near = g.rowflag[(size_t)i * g.n1 + j];
+    Planes pl;
     load_planes(g, g.bits, i, j, w, pl);
     uint32_t x[7];
-    cross_words(pl, x);
-    if (g.any_near) load_planes(g, g.nbits, i, j, w, npl);
-    // ---- vertices owned by this word (edge p -> p+d is used iff it crosses, modulo allclose skips)
+    owner_used(g, pl, i, j, w, x);
     unsigned v = 0;
+    uint32_t any = 0;
 #pragma unroll
-    for (int d = 1; d <= 7; ++d) {
-      uint32_t xd = x[d - 1];
-      if (g.any_near) {
-        uint32_t c = xd & npl.P[0] & dir_plane(npl, d);
-        xd &= ~c;
-        while (c) {
-          int b = __ffs(c) - 1;
-          c &= c - 1;
-          if (edge_used_exact(g, i, j, w * 32 + b, d)) ++v;
-        }
-      }
-      v += __popc(xd);
+    for (int d = 0; d < 7; ++d) {
+      v += __popc(x[d]);
+      any |= x[d];
     }
-    cv[it] = v;
-    emitv[it] = v && gw < (long long)g.i_hi * plane_words;
-    // ---- strict crossings for owners inside the voxel range (grid_field.py:64-84)
-    if (pl.has_i1 && pl.has_j1) {
+    const bool cells_ok = pl.has_i1 && pl.has_j1 && i < g.i_hi;
+    unsigned t = 0;
+    uint32_t em = 0;
+    if (cells_ok) {
+      // strict crossings for owners inside the voxel range (grid_field.py:64-84)
+      uint32_t xs[7];
+      cross_words(pl, xs);
 #pragma unroll
-      for (int d = 1; d <= 7; ++d) {
-        uint32_t xd = x[d - 1] & pl.kp1;
-        ncross += __popc(xd);
-        if (g.any_near) {
-          // not strict when the HIGH endpoint equals the isovalue exactly (then (f0-v)*(f1-v) == 0)
-          uint32_t A = pl.P[0], O = dir_plane(pl, d);
-          uint32_t c = xd & ((~A & npl.P[0]) | (~O & dir_plane(npl, d)));
-          while (c) {
-            int b = __ffs(c) - 1;
-            c &= c - 1;
-            bool a_high = !((A >> b) & 1u);
-            int k = w * 32 + b;
-            double fh = a_high ? sample(g, i, j, k) : sample(g, i + ((d >> 2) & 1), j + ((d >> 1) & 1), k + (d & 1));
-            if (fh == g.v) --ncross;
-          }
-        }
-      }
-    }
-    // ---- triangles of the voxels in this word
-    if (pl.has_i1 && pl.has_j1 && i < g.i_hi) {
+      for (int d = 0; d < 7; ++d) ncross += __popc(xs[d] & pl.kp1);
       uint32_t odd[6], two[6], cand;
-      tet_words(pl, g.any_near ? &npl : nullptr, pl.kp1, odd, two, cand);
-      uint32_t emitting = 0;
-      unsigned t = 0;
+      tet_words(pl, nullptr, pl.kp1, odd, two, cand);
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
-        t += __popc(odd[q] & ~cand) + 2 * __popc(two[q] & ~cand);
-        emitting |= (odd[q] | two[q]) & ~cand;
+        t += __popc(odd[q]) + 2 * __popc(two[q]);
+        em |= odd[q] | two[q];
       }
-      while (cand) {
-        int b = __ffs(cand) - 1;
-        cand &= cand - 1;
-        unsigned e = cell_emit_exact(g, i, j, w * 32 + b, nullptr);
-        if (e) emitting |= 1u << b;
-#pragma unroll
-        for (int q = 0; q < 6; ++q)
-          if ((e >> q) & 1u) t += ((odd[q] >> b) & 1u) ? 1u : 2u;
-      }
-      ct[it] = t;
-      ncells += __popc(emitting);
     }
+    if (g.any_near) count_word_exact(g, pl, i, j, w, cells_ok, ncross, t, em);
+    sh.cv[wl] = (unsigned short)v;
+    sh.ct[wl] = (unsigned short)t;
+    sh.own[wl] = gw < emit_end ? any : 0u;
+    sh.emit[wl] = em;
+    ncells += __popc(em);
   }
-  // ---- block scan of (V, T) and (activeV, activeT), packed 31 bits each
-  unsigned long long loc_vt = 0, loc_act = 0;
-#pragma unroll
-  for (int it = 0; it < CS_ITEMS; ++it) {
-    loc_vt += ((unsigned long long)ct[it] << 31) | cv[it];
-    loc_act += ((unsigned long long)(ct[it] ? 1u : 0u) << 31) | (emitv[it] ? 1u : 0u);
-  }
-  unsigned long long inc_vt = warp_incl_scan_u64(loc_vt), inc_act = warp_incl_scan_u64(loc_act);
-  if (lane == 31) {
-    s_warp_vt[warp] = inc_vt;
-    s_warp_act[warp] = inc_act;
-  }
-  // block-level counters
   unsigned long long cc = ((unsigned long long)ncross << 32) | ncells;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cc += __shfl_xor_sync(0xffffffffu, cc, o);
@@ -400,93 +732,161 @@ __global__ void __launch_bounds__(CS_THREADS) k_count_scan(Grid<T> gin, long lon
     if (cc >> 32) atomicAdd(&ctr->n_cross, cc >> 32);
   }
   __syncthreads();
+
+  // ---- C: scan.  Thread t owns the 4 consecutive words 4t..4t+3 (linear order)
+  unsigned long long loc_vt = 0, loc_act = 0;
+  unsigned long long item_vt[CS_ITEMS], item_act[CS_ITEMS];
+#pragma unroll
+  for (int it = 0; it < CS_ITEMS; ++it) {
+    const unsigned wl = threadIdx.x * CS_ITEMS + it;
+    item_vt[it] = ((unsigned long long)sh.ct[wl] << 31) | sh.cv[wl];
+    item_act[it] = ((unsigned long long)__popc(sh.emit[wl]) << 31) | (unsigned)__popc(sh.own[wl]);
+    loc_vt += item_vt[it];
+    loc_act += item_act[it];
+  }
+  unsigned long long inc_vt = warp_incl_scan_u64(loc_vt), inc_act = warp_incl_scan_u64(loc_act);
+  if (lane == 31) {
+    sh.warp_vt[warp] = inc_vt;
+    sh.warp_act[warp] = inc_act;
+  }
+  __syncthreads();
   unsigned long long woff_vt = 0, woff_act = 0, blk_vt = 0, blk_act = 0;
 #pragma unroll
   for (int q = 0; q < CS_THREADS / 32; ++q) {
     if (q < (int)warp) {
-      woff_vt += s_warp_vt[q];
-      woff_act += s_warp_act[q];
+      woff_vt += sh.warp_vt[q];
+      woff_act += sh.warp_act[q];
     }
-    blk_vt += s_warp_vt[q];
-    blk_act += s_warp_act[q];
+    blk_vt += sh.warp_vt[q];
+    blk_act += sh.warp_act[q];
   }
   if (warp == 0) {
     unsigned long long e = lb_lookback(status_vt, tile, blk_vt);
-    if (lane == 0) s_excl_vt = e;
+    if (lane == 0) sh.excl_vt = e;
   } else if (warp == 1) {
     unsigned long long e = lb_lookback(status_act, tile, blk_act);
-    if (lane == 0) s_excl_act = e;
+    if (lane == 0) sh.excl_act = e;
   }
   __syncthreads();
-  unsigned long long run_vt = s_excl_vt + woff_vt + inc_vt - loc_vt;
-  unsigned long long run_act = s_excl_act + woff_act + inc_act - loc_act;
+  unsigned long long run_vt = sh.excl_vt + woff_vt + inc_vt - loc_vt;
+  unsigned long long run_act = sh.excl_act + woff_act + inc_act - loc_act;
+  {
+    uint32_t vb[CS_ITEMS];
 #pragma unroll
-  for (int it = 0; it < CS_ITEMS; ++it) {
-    long long rel = first + it;
-    if (rel >= nwords_scan) break;
-    long long gw = word0 + rel;
-    unsigned vb = (unsigned)(run_vt & 0x7fffffffull), tb = (unsigned)(run_vt >> 31);
-    vbase[gw] = vb;
-    tbase[gw] = tb;
-    if (g.i_hiv > g.i_hi && gw == (long long)g.i_hi * plane_words) ctr->v_emit = vb;
-    if (emitv[it]) list_v[(unsigned)(run_act & 0x7fffffffull)] = (uint32_t)gw;
-    if (ct[it]) list_t[(unsigned)(run_act >> 31)] = (uint32_t)gw;
-    run_vt += ((unsigned long long)ct[it] << 31) | cv[it];
-    run_act += ((unsigned long long)(ct[it] ? 1u : 0u) << 31) | (emitv[it] ? 1u : 0u);
+    for (int it = 0; it < CS_ITEMS; ++it) {
+      const unsigned wl = threadIdx.x * CS_ITEMS + it;
+      vb[it] = (uint32_t)(run_vt & 0x7fffffffull);
+      sh.pv[wl] = vb[it];
+      sh.pt[wl] = (uint32_t)(run_vt >> 31);
+      sh.po[wl] = (uint32_t)(run_act & 0x7fffffffull);
+      sh.pc[wl] = (uint32_t)(run_act >> 31);
+      run_vt += item_vt[it];
+      run_act += item_act[it];
+    }
+    const unsigned rel0 = tile0 + threadIdx.x * CS_ITEMS;
+#pragma unroll
+    for (int it = 0; it < CS_ITEMS; ++it) {
+      if (rel0 + it < nwords_scan) {
+        vbase[word0 + rel0 + it] = vb[it];
+        if (g.i_hiv > g.i_hi && word0 + rel0 + it == emit_end) ctr->v_emit = vb[it];
+      }
+    }
   }
   if (tile == ntiles - 1 && threadIdx.x == 0) {
-    ctr->total_vt = s_excl_vt + blk_vt;
-    ctr->total_act = s_excl_act + blk_act;
+    ctr->total_vt = sh.excl_vt + blk_vt;
+    ctr->total_act = sh.excl_act + blk_act;
   }
-}
+  __syncthreads();
 
-// ------------------------------------------------------------------------------------------------
-// used-edge words of an owner word, computed cooperatively by one warp (exact resolution via ballot)
-// ------------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void owner_used_warp(const Grid<T>& g, int i, int j, int w, uint32_t used[7], uint32_t* Aword) {
-  if (i >= g.n0 || j >= g.n1 || w >= g.W) {
+  // ---- D: compacted owner / voxel lists
+  for (unsigned idx = threadIdx.x; idx < nint; idx += CS_THREADS) {
+    const unsigned wl = sh.list[idx];
+    uint32_t mo = sh.own[wl], me = sh.emit[wl];
+    if (!(mo | me)) continue;
+    const unsigned gw = word0 + tile0 + wl;
+    int i, j, w;
+    g.word_coords(gw, i, j, w);
+    g.any_near = g.rowflag[(size_t)i * g.n1 + j];
+    Planes pl;
+    load_planes(g, g.bits, i, j, w, pl);
+    if (mo) {
+      uint32_t x[7];
+      owner_used(g, pl, i, j, w, x);
+      unsigned vrun = sh.pv[wl], orun = sh.po[wl];
+      while (mo) {
+        const int b = __ffs(mo) - 1;
+        mo &= mo - 1;
+        const unsigned m7 = gather7(x, b);
+        if (orun < cap_own) {
+          own_id[orun] = ((unsigned long long)gw << 13) | ((unsigned)b << 8) | (((pl.P[0] >> b) & 1u) << 7) | m7;
+          own_voff[orun] = vrun;
+        }
+        ++orun;
+        vrun += __popc(m7);
+      }
+    }
+    if (me) {
+      unsigned trun = sh.pt[wl], crun = sh.pc[wl];
+      Planes npl;
+      if (g.any_near) load_planes(g, g.nbits, i, j, w, npl);
+      while (me) {
+        const int b = __ffs(me) - 1;
+        me &= me - 1;
+        unsigned c8 = 0;
 #pragma unroll
-    for (int d = 0; d < 7; ++d) used[d] = 0;
-    if (Aword) *Aword = 0;
-    return;
-  }
-  Planes pl;
-  load_planes(g, g.bits, i, j, w, pl);
-  cross_words(pl, used);
-  if (Aword) *Aword = pl.P[0];
-  if (g.any_near) {
-    Planes npl;
-    load_planes(g, g.nbits, i, j, w, npl);
-    const unsigned lane = lane_id();
+        for (int c = 0; c < 8; ++c) c8 |= ((corner_plane(pl, c) >> b) & 1u) << c;
+        unsigned emit = 0;
 #pragma unroll
-    for (int d = 1; d <= 7; ++d) {
-      uint32_t c = used[d - 1] & npl.P[0] & dir_plane(npl, d);
-      if (c) {                                   // warp-uniform
-        bool r = ((c >> lane) & 1u) && edge_used_exact(g, i, j, w * 32 + (int)lane, d);
-        uint32_t fix = __ballot_sync(0xffffffffu, r);
-        used[d - 1] = (used[d - 1] & ~c) | fix;
+        for (int t = 0; t < 6; ++t) {
+          const unsigned tm = tet_mask_of(c8, t);
+          if (tm != 0 && tm != 15) emit |= 1u << t;
+        }
+        if (g.any_near) {
+          unsigned n8 = 0;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) n8 |= ((corner_plane(npl, c) >> b) & 1u) << c;
+          bool cand = false;
+#pragma unroll
+          for (int t = 0; t < 6; ++t) cand = cand || (((emit >> t) & 1u) && tet_mask_of(n8, t) == 15);
+          if (cand) emit = cell_emit_exact(g, i, j, w * 32 + b, nullptr);
+        }
+        unsigned nt = 0;
+#pragma unroll
+        for (int t = 0; t < 6; ++t)
+          if ((emit >> t) & 1u) nt += (__popc(tet_mask_of(c8, t)) == 2) ? 2u : 1u;
+        if (crun < cap_cell) {
+          cell_id[crun] = ((unsigned long long)gw << 19) | ((unsigned)b << 14) | (emit << 8) | c8;
+          cell_toff[crun] = trun;
+        }
+        ++crun;
+        trun += nt;
       }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stage 3: vertices.  One warp per active owner word; lane = owner point.
+// Stage 3: vertices.  A warp takes 32 active owner points, then deals their 1..7 owned edges out to its
+// lanes one vertex per lane per round (balanced; consecutive lanes write consecutive vertex ids).
 // ------------------------------------------------------------------------------------------------
 template <typename T, typename G>
 __device__ __forceinline__ void grad_at(const Grid<T>& g, int i, int j, int k, G out[3]) {
-  const int n[3] = {g.n0, g.n1, g.n2};
-  const int p[3] = {i, j, k};
-#pragma unroll
-  for (int ax = 0; ax < 3; ++ax) {
-    int lo[3] = {i, j, k}, hi[3] = {i, j, k};
-    lo[ax] = p[ax] > 0 ? p[ax] - 1 : 0;
-    hi[ax] = p[ax] < n[ax] - 1 ? p[ax] + 1 : n[ax] - 1;
-    G s = (p[ax] == 0 || p[ax] == n[ax] - 1) ? (G)1 : (G)0.5;
-    G a = (G)g.f[((long long)hi[0] * g.n1 + hi[1]) * g.n2 + hi[2]];
-    G b = (G)g.f[((long long)lo[0] * g.n1 + lo[1]) * g.n2 + lo[2]];
-    out[ax] = (a - b) * s;
+  const long long s1 = g.n2, s0 = (long long)g.n1 * g.n2;
+  const T* c = g.f + ((long long)i * g.n1 + j) * g.n2 + k;
+  {
+    const bool lo = i > 0, hi = i < g.n0 - 1;
+    G a = (G)c[hi ? s0 : 0], b = (G)c[lo ? -s0 : 0];
+    out[0] = (a - b) * ((lo && hi) ? (G)0.5 : (G)1);
+  }
+  {
+    const bool lo = j > 0, hi = j < g.n1 - 1;
+    G a = (G)c[hi ? s1 : 0], b = (G)c[lo ? -s1 : 0];
+    out[1] = (a - b) * ((lo && hi) ? (G)0.5 : (G)1);
+  }
+  {
+    const bool lo = k > 0, hi = k < g.n2 - 1;
+    G a = (G)c[hi ? 1 : 0], b = (G)c[lo ? -1 : 0];
+    out[2] = (a - b) * ((lo && hi) ? (G)0.5 : (G)1);
   }
 }
 
@@ -494,228 +894,277 @@ __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double shfl_g(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ float shfl_g(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 struct Xform {
   double origin[3], delta[3];
 };
 
 template <typename T, typename G>
-__global__ void __launch_bounds__(128) k_emit_verts(Grid<T> gin, const uint32_t* __restrict__ list_v, unsigned n_active,
-                                                    const uint32_t* __restrict__ vbase, Xform xf, G* __restrict__ verts,
-                                                    G* __restrict__ normals, unsigned long long* __restrict__ keys,
-                                                    uint8_t* __restrict__ lowmin) {
-  Grid<T> g = gin;
-  g.any_near = (int)*gin.near_flag;
+__global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned long long* __restrict__ own_id,
+                                                    const uint32_t* __restrict__ own_voff, unsigned n_own, Xform xf,
+                                                    G* __restrict__ verts, G* __restrict__ normals,
+                                                    unsigned long long* __restrict__ keys, uint8_t* __restrict__ lowmin) {
   const unsigned lane = lane_id();
-  unsigned a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (a >= n_active) return;
-  const long long gw = list_v[a];
-  long long row = gw / g.W;
-  const int w = (int)(gw - row * g.W);
-  const int i = (int)(row / g.n1), j = (int)(row - (long long)i * g.n1);
-  uint32_t used[7], Aw;
-  owner_used_warp(g, i, j, w, used, &Aw);
-  const uint32_t below = (1u << lane) - 1u;
-  unsigned rank = 0, m7 = 0;
-#pragma unroll
-  for (int d = 0; d < 7; ++d) {
-    rank += __popc(used[d] & below);
-    m7 |= ((used[d] >> lane) & 1u) << d;
+  const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;          // owner index of this lane
+  const unsigned warp_first = a - lane;
+  if (warp_first >= n_own) return;
+  const bool have = a < n_own;
+  const unsigned long long oid = have ? own_id[a] : 0ull;
+  const unsigned voff = have ? own_voff[a] : 0u;
+  const unsigned m7 = (unsigned)oid & 127u;
+  int i = 0, j = 0, w = 0;
+  g.word_coords((unsigned)(oid >> 13), i, j, w);
+  const int k = w * 32 + (int)((oid >> 8) & 31u);
+  G fp = (G)0, gp[3] = {(G)0, (G)0, (G)0};
+  if (have) {
+    fp = (G)g.f[((long long)i * g.n1 + j) * g.n2 + k];
+    if (normals) grad_at<T, G>(g, i, j, k, gp);
   }
-  if (!m7) return;
-  unsigned id = vbase[gw] + rank;
-  const int k = w * 32 + (int)lane;
-  const bool p_low = (Aw >> lane) & 1u;
-  const G fp = (G)g.f[((long long)i * g.n1 + j) * g.n2 + k];
+  const unsigned cnt = __popc(m7);
+  const unsigned incl = warp_incl_scan_u32(cnt);
+  const unsigned excl = incl - cnt;
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  const unsigned vfirst = __shfl_sync(0xffffffffu, voff, 0);        // ids of a warp's vertices are consecutive
   const G v = (G)g.v;
-  G gp[3];
-  if (normals) grad_at<T, G>(g, i, j, k, gp);
-  const long long lin = (((long long)i + g.plane_offset) * g.n1 + j) * g.n2 + k;
-#pragma unroll 1
-  for (int d = 1; d <= 7; ++d) {
-    if (!((m7 >> (d - 1)) & 1u)) continue;
+  for (unsigned base = 0; base < total; base += 32) {
+    const unsigned vtx = base + lane;
+    const bool act = vtx < total;
+    // owner o = last lane whose exclusive prefix <= vtx  (binary search over the warp's prefixes)
+    int o = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int probe = o + step;
+      const unsigned e = __shfl_sync(0xffffffffu, excl, probe & 31);
+      if (probe < 32 && e <= vtx) o = probe;
+    }
+    // owners with zero vertices never appear in the list (cnt >= 1), so prefixes are strictly increasing
+    const unsigned o_excl = __shfl_sync(0xffffffffu, excl, o);
+    const unsigned o_m7 = __shfl_sync(0xffffffffu, m7, o);
+    const unsigned o_lo = __shfl_sync(0xffffffffu, (unsigned)((oid >> 7) & 1u), o);
+    const int oi = __shfl_sync(0xffffffffu, i, o), oj = __shfl_sync(0xffffffffu, j, o), ok = __shfl_sync(0xffffffffu, k, o);
+    const G ofp = shfl_g(fp, o);
+    G ogp[3];
+    if (normals) {
+      ogp[0] = shfl_g(gp[0], o);
+      ogp[1] = shfl_g(gp[1], o);
+      ogp[2] = shfl_g(gp[2], o);
+    }
+    if (!act) continue;
+    const int d = (int)__fns(o_m7, 0, (int)(vtx - o_excl) + 1) + 1;   // (n+1)-th set bit -> direction 1..7
+    const bool p_low = o_lo != 0;
+    const size_t id = (size_t)vfirst + vtx;
     const int di = (d >> 2) & 1, dj = (d >> 1) & 1, dk = d & 1;
-    const G fq = (G)g.f[((long long)(i + di) * g.n1 + (j + dj)) * g.n2 + (k + dk)];
+    const G fq = (G)g.f[((long long)(oi + di) * g.n1 + (oj + dj)) * g.n2 + (ok + dk)];
     // tetrahedral.py:476-487: key oriented (low, high) by value; ratio = (z-flow)/(fhigh-flow), 0.5 if ~0
-    const G flow = p_low ? fp : fq, fhigh = p_low ? fq : fp;
+    const G flow = p_low ? ofp : fq, fhigh = p_low ? fq : ofp;
     const G den = fhigh - flow;
-    G ratio = (fabs((double)den) <= 1e-8) ? (G)0.5 : (v - flow) / den;
+    const G ratio = (fabs((double)den) <= 1e-8) ? (G)0.5 : (v - flow) / den;
     // x = low + ratio*(high - low); (high-low) is +-1 or 0 per axis so the product is exact
-    const G sgn = p_low ? (G)1 : (G)-1;
-    const int pl[3] = {p_low ? i : i + di, p_low ? j : j + dj, p_low ? k : k + dk};
+    const G step = p_low ? ratio : -ratio;
+    const int pl[3] = {p_low ? oi : oi + di, p_low ? oj : oj + dj, p_low ? ok : ok + dk};
     const int dd[3] = {di, dj, dk};
-    G pos[3];
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
-      G base = (G)pl[ax];
-      if (ax == 0) base = (G)((long long)pl[0] + g.plane_offset);
-      G x = dd[ax] ? add_rn(base, mul_rn(ratio, sgn)) : base;
-      pos[ax] = add_rn(mul_rn(x, (G)xf.delta[ax]), (G)xf.origin[ax]);   // grid_field.py:93
+      const G b0 = (ax == 0) ? (G)((long long)pl[0] + g.plane_offset) : (G)pl[ax];
+      const G x = dd[ax] ? add_rn(b0, step) : b0;
+      verts[id * 3 + ax] = add_rn(mul_rn(x, (G)xf.delta[ax]), (G)xf.origin[ax]);   // grid_field.py:93
     }
-    verts[(size_t)id * 3 + 0] = pos[0];
-    verts[(size_t)id * 3 + 1] = pos[1];
-    verts[(size_t)id * 3 + 2] = pos[2];
     if (normals) {
       G gq[3];
-      grad_at<T, G>(g, i + di, j + dj, k + dk, gq);
+      grad_at<T, G>(g, oi + di, oj + dj, ok + dk, gq);
       G nn[3], len2 = 0;
 #pragma unroll
       for (int ax = 0; ax < 3; ++ax) {
-        G gl = p_low ? gp[ax] : gq[ax], gh = p_low ? gq[ax] : gp[ax];
-        nn[ax] = (gl + ratio * (gh - gl)) / (G)xf.delta[ax];
-        len2 += nn[ax] * nn[ax];
+        const G gl = p_low ? ogp[ax] : gq[ax], gh = p_low ? gq[ax] : ogp[ax];
+        nn[ax] = add_rn(gl, mul_rn(ratio, gh - gl)) / (G)xf.delta[ax];
+        len2 = add_rn(len2, mul_rn(nn[ax], nn[ax]));
       }
-      G len = sqrt(len2);
-      normals[(size_t)id * 3 + 0] = len > (G)0 ? nn[0] / len : (G)0;
-      normals[(size_t)id * 3 + 1] = len > (G)0 ? nn[1] / len : (G)0;
-      normals[(size_t)id * 3 + 2] = len > (G)0 ? nn[2] / len : (G)0;
+      const G len = sqrt(len2);
+      const G inv = len > (G)0 ? (G)1 / len : (G)0;
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) normals[id * 3 + ax] = nn[ax] * inv;
     }
     if (keys) {
+      const long long lin = (((long long)oi + g.plane_offset) * g.n1 + oj) * g.n2 + ok;
       keys[id] = ((unsigned long long)lin << 3) | (unsigned)d;
       lowmin[id] = p_low ? 1 : 0;
     }
-    ++id;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stage 4: triangles.  One warp per active voxel word; lane = voxel.
+// Stage 4: triangles.  One thread per active voxel.  The ids of the voxel's 19 edges come from
+// vbase[word] + rank of the edge among the used edges of its owner's word (popcounts of crossing words).
 // ------------------------------------------------------------------------------------------------
-constexpr int ET_WARPS = 4;
+constexpr int ET_THREADS = 128;
+__constant__ uint32_t c_tri_packed[6 * 16];    // n | slot0<<2 | slot1<<7 | ... (6 slots x 5 bits)
 
+// exact (allclose-aware) owner ids of a voxel: the rare path, kept out of line
 template <typename T>
-__global__ void __launch_bounds__(ET_WARPS * 32) k_emit_tris(Grid<T> gin, const uint32_t* __restrict__ list_t,
-                                                             unsigned n_active, const uint32_t* __restrict__ vbase,
-                                                             const uint32_t* __restrict__ tbase, int* __restrict__ tris) {
-  __shared__ unsigned s_ids[ET_WARPS][19][32];
-  Grid<T> g = gin;
-  g.any_near = (int)*gin.near_flag;
-  const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
-  unsigned a = blockIdx.x * ET_WARPS + wib;
-  if (a >= n_active) return;
-  const long long gw = list_t[a];
-  long long row = gw / g.W;
-  const int w = (int)(gw - row * g.W);
-  const int i = (int)(row / g.n1), j = (int)(row - (long long)i * g.n1);
-
-  // owner (idbase, mask7) at bit `lane` and `lane+1` for the 4 owner rows (a,b)
-  unsigned idb[8], msk[8];   // index = corner s = a*4 + b*2 + dk
-#pragma unroll
+__device__ __noinline__ void owner_ids_exact(const Grid<T>& g, const uint32_t* __restrict__ vbase, int i, int j, int w, int b,
+                                             unsigned idb[8], unsigned msk[8]) {
+  const uint32_t below = (1u << b) - 1u;
   for (int ab = 0; ab < 4; ++ab) {
     const int ii = i + (ab >> 1), jj = j + (ab & 1);
-    uint32_t u[7], un[7];
-    owner_used_warp(g, ii, jj, w, u, nullptr);
-    const bool lane31_next = (w + 1 < g.W);
-    if (lane31_next) owner_used_warp(g, ii, jj, w + 1, un, nullptr);   // warp-uniform branch
-    const long long wi = ((long long)ii * g.n1 + jj) * g.W + w;
-    const bool row_ok = ii < g.n0 && jj < g.n1;
-    const unsigned base0 = row_ok ? vbase[wi] : 0u;
-    const uint32_t below = (1u << lane) - 1u;
-    unsigned rank = 0, m0 = 0, m1 = 0;
-#pragma unroll
-    for (int d = 0; d < 7; ++d) {
-      rank += __popc(u[d] & below);
-      m0 |= ((u[d] >> lane) & 1u) << d;
-      if (lane < 31) m1 |= ((u[d] >> (lane + 1)) & 1u) << d;
-    }
-    unsigned id0 = base0 + rank, id1 = id0 + __popc(m0);
-    if (lane == 31) {
-      m1 = 0;
-      id1 = 0;
-      if (lane31_next && row_ok) {
-        id1 = vbase[wi + 1];
-#pragma unroll
-        for (int d = 0; d < 7; ++d) m1 |= (un[d] & 1u) << d;
-      }
+    Planes pl;
+    load_planes(g, g.bits, ii, jj, w, pl);
+    uint32_t u[7];
+    owner_used(g, pl, ii, jj, w, u);
+    const unsigned wi = ((unsigned)ii * (unsigned)g.n1 + (unsigned)jj) * (unsigned)g.W + (unsigned)w;
+    unsigned rank = 0;
+    for (int d = 0; d < 7; ++d) rank += __popc(u[d] & below);
+    const unsigned m0 = gather7(u, b);
+    const unsigned id0 = vbase[wi] + rank;
+    unsigned m1, id1;
+    if (b < 31) {
+      m1 = gather7(u, b + 1);
+      id1 = id0 + __popc(m0);
+    } else {
+      Planes pn;
+      load_planes(g, g.bits, ii, jj, w + 1, pn);
+      uint32_t un[7];
+      owner_used(g, pn, ii, jj, w + 1, un);
+      m1 = gather7(un, 0);
+      id1 = vbase[wi + 1];
     }
     idb[ab * 2 + 0] = id0;
     msk[ab * 2 + 0] = m0;
     idb[ab * 2 + 1] = id1;
     msk[ab * 2 + 1] = m1;
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> gin, const unsigned long long* __restrict__ cell_id,
+                                                          const uint32_t* __restrict__ cell_toff, unsigned n_cells,
+                                                          const uint32_t* __restrict__ vbase, int* __restrict__ tris) {
+  __shared__ unsigned s_ids[19][ET_THREADS];
+  __shared__ uint32_t s_tab[96];
+  Grid<T> g = gin;
+  if (threadIdx.x < 96) s_tab[threadIdx.x] = c_tri_packed[threadIdx.x];
+  __syncthreads();
+  unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_cells) return;
+  const unsigned long long cid = cell_id[a];
+  const unsigned c8 = (unsigned)cid & 255u, emit = (unsigned)(cid >> 8) & 63u;
+  const int b = (int)((cid >> 14) & 31u);
+  int i, j, w;
+  g.word_coords((unsigned)(cid >> 19), i, j, w);
+  g.any_near = g.rowflag[(size_t)i * g.n1 + j];
+
+  unsigned idb[8], msk[8];   // owner (first vertex id, mask7); index = corner s = a*4 + b*2 + dk
+  if (g.any_near) {
+    owner_ids_exact(g, vbase, i, j, w, b, idb, msk);
+  } else {
+    // rows (i+a, j+c), a,c in 0..2: word w (R) and the word after it (N)
+    uint32_t R[3][3], N[3][3];
+    const bool next_ok = (w + 1 < g.W);
+#pragma unroll
+    for (int ra = 0; ra < 3; ++ra)
+#pragma unroll
+      for (int rc = 0; rc < 3; ++rc) {
+        const bool ok = (i + ra < g.n0) && (j + rc < g.n1);
+        uint32_t r = 0, nx = 0;
+        if (ok) {
+          const uint32_t* p = g.bits + ((size_t)(i + ra) * g.n1 + (j + rc)) * g.W + w;
+          r = p[0];
+          if (next_ok) nx = p[1];
+        }
+        R[ra][rc] = r;
+        N[ra][rc] = nx;
+      }
+    const int rem = g.n2 - w * 32;
+    const uint32_t kpt = low_mask(rem), kp1 = low_mask(rem - 1);
+    const uint32_t below = (1u << b) - 1u;
+    const bool nkpt = (rem - 32) > 0, nkp1 = (rem - 33) > 0;       // validity of bit 0 of the next word
+#pragma unroll
+    for (int ab = 0; ab < 4; ++ab) {
+      const int ra = ab >> 1, rc = ab & 1;
+      const uint32_t vi = (i + ra + 1 < g.n0) ? 0xffffffffu : 0u, vj = (j + rc + 1 < g.n1) ? 0xffffffffu : 0u;
+      const uint32_t A = R[ra][rc];
+      uint32_t u[7];
+#define CTR_S(x, y) ((R[x][y] >> 1) | (N[x][y] << 31))
+      u[0] = (A ^ CTR_S(ra, rc)) & kp1;
+      u[1] = (A ^ R[ra][rc + 1]) & kpt & vj;
+      u[2] = (A ^ CTR_S(ra, rc + 1)) & kp1 & vj;
+      u[3] = (A ^ R[ra + 1][rc]) & kpt & vi;
+      u[4] = (A ^ CTR_S(ra + 1, rc)) & kp1 & vi;
+      u[5] = (A ^ R[ra + 1][rc + 1]) & kpt & vi & vj;
+      u[6] = (A ^ CTR_S(ra + 1, rc + 1)) & kp1 & vi & vj;
+#undef CTR_S
+      const unsigned wi = ((unsigned)(i + ra) * (unsigned)g.n1 + (unsigned)(j + rc)) * (unsigned)g.W + (unsigned)w;
+      unsigned rank = 0;
+#pragma unroll
+      for (int d = 0; d < 7; ++d) rank += __popc(u[d] & below);
+      const unsigned m0 = gather7(u, b);
+      const unsigned id0 = vbase[wi] + rank;
+      unsigned m1, id1;
+      if (b < 31) {
+        m1 = gather7(u, b + 1);
+        id1 = id0 + __popc(m0);
+      } else {
+        // k+1 is bit 0 of the next word (it exists: the voxel is in range); its k+1 neighbour is bit 1
+        const uint32_t A1 = N[ra][rc] & 1u;
+        const uint32_t vi1 = vi & 1u, vj1 = vj & 1u;
+        const uint32_t p1 = nkpt ? 1u : 0u, q1 = nkp1 ? 1u : 0u;
+        m1 = ((A1 ^ ((N[ra][rc] >> 1) & 1u)) & q1) | (((A1 ^ (N[ra][rc + 1] & 1u)) & p1 & vj1) << 1) |
+             (((A1 ^ ((N[ra][rc + 1] >> 1) & 1u)) & q1 & vj1) << 2) | (((A1 ^ (N[ra + 1][rc] & 1u)) & p1 & vi1) << 3) |
+             (((A1 ^ ((N[ra + 1][rc] >> 1) & 1u)) & q1 & vi1) << 4) |
+             (((A1 ^ (N[ra + 1][rc + 1] & 1u)) & p1 & vi1 & vj1) << 5) |
+             (((A1 ^ ((N[ra + 1][rc + 1] >> 1) & 1u)) & q1 & vi1 & vj1) << 6);
+        id1 = vbase[wi + 1];
+      }
+      idb[ab * 2 + 0] = id0;
+      msk[ab * 2 + 0] = m0;
+      idb[ab * 2 + 1] = id1;
+      msk[ab * 2 + 1] = m1;
+    }
+  }
 #pragma unroll
   for (int e = 0; e < 19; ++e) {
-    const int s = c_edge_s[e], d = c_edge_d[e];               // constant-bank loads (uniform)
-    s_ids[wib][e][lane] = idb[s] + __popc(msk[s] & ((1u << (d - 1)) - 1u));
+    const int s = c_edge_s[e], d = c_edge_d[e];
+    s_ids[e][threadIdx.x] = idb[s] + __popc(msk[s] & ((1u << (d - 1)) - 1u));
   }
-  // voxel classification
-  Planes pl;
-  load_planes(g, g.bits, i, j, w, pl);
-  const bool cell_ok = pl.has_i1 && pl.has_j1 && ((pl.kp1 >> lane) & 1u);
-  unsigned cb = 0;
+  size_t o = cell_toff[a];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) cb |= ((corner_plane(pl, c) >> lane) & 1u) << c;
-  unsigned tm[6];
-  unsigned emit = 0;
-#pragma unroll
-  for (int t = 0; t < 6; ++t) {
-    unsigned m = 0;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) m |= ((cb >> c_tet[t][b]) & 1u) << b;
-    tm[t] = m;
-    if (cell_ok && m != 0 && m != 15) emit |= 1u << t;
-  }
-  if (g.any_near && emit) {
-    Planes npl;
-    load_planes(g, g.nbits, i, j, w, npl);
-    unsigned nb = 0;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) nb |= ((corner_plane(npl, c) >> lane) & 1u) << c;
-    bool cand = false;
-#pragma unroll
-    for (int t = 0; t < 6; ++t) {
-      bool alln = true;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) alln = alln && ((nb >> c_tet[t][b]) & 1u);
-      cand = cand || (alln && ((emit >> t) & 1u));
-    }
-    if (cand) emit = cell_emit_exact(g, i, j, w * 32 + (int)lane, nullptr);
-  }
-  unsigned nt = 0;
-#pragma unroll
-  for (int t = 0; t < 6; ++t)
-    if ((emit >> t) & 1u) nt += c_tri_n[t][tm[t]];
-  unsigned incl = warp_incl_scan_u32(nt);
-  size_t o = (size_t)tbase[gw] + incl - nt;
-  __syncwarp();
-#pragma unroll 1
   for (int t = 0; t < 6; ++t) {
     if (!((emit >> t) & 1u)) continue;
-    const unsigned m = tm[t];
-    const int n = c_tri_n[t][m];
-    for (int q = 0; q < n; ++q) {
-      int* dst = tris + o * 3;
-      dst[0] = (int)s_ids[wib][c_tri_e[t][m][q * 3 + 0]][lane];
-      dst[1] = (int)s_ids[wib][c_tri_e[t][m][q * 3 + 1]][lane];
-      dst[2] = (int)s_ids[wib][c_tri_e[t][m][q * 3 + 2]][lane];
-      ++o;
+    const uint32_t e = s_tab[t * 16 + tet_mask_of(c8, t)];
+    int* dst = tris + o * 3;
+    dst[0] = (int)s_ids[(e >> 2) & 31u][threadIdx.x];
+    dst[1] = (int)s_ids[(e >> 7) & 31u][threadIdx.x];
+    dst[2] = (int)s_ids[(e >> 12) & 31u][threadIdx.x];
+    if ((e & 3u) == 2u) {
+      dst[3] = (int)s_ids[(e >> 17) & 31u][threadIdx.x];
+      dst[4] = (int)s_ids[(e >> 22) & 31u][threadIdx.x];
+      dst[5] = (int)s_ids[(e >> 27) & 31u][threadIdx.x];
     }
+    o += e & 3u;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Parity output: (voxel, case code) of emitting voxels, recomputed from the samples (independent of the
-// bit logic above).  Unordered (slot by atomic).
+// Parity output: (voxel, case code) of emitting voxels, recomputed from the samples in fp64
+// (independent of the bit logic above).  Same order as the voxel list.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(128) k_codes(Grid<T> g, const uint32_t* __restrict__ list_t, unsigned n_active,
-                                               long long* __restrict__ cells, uint32_t* __restrict__ codes,
-                                               Counters* ctr) {
-  const unsigned lane = lane_id();
-  unsigned a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (a >= n_active) return;
-  const long long gw = list_t[a];
-  long long row = gw / g.W;
-  const int w = (int)(gw - row * g.W);
-  const int i = (int)(row / g.n1), j = (int)(row - (long long)i * g.n1);
-  const int k = w * 32 + (int)lane;
+__global__ void __launch_bounds__(256) k_codes(Grid<T> g, const unsigned long long* __restrict__ cell_id, unsigned n_cells,
+                                               long long* __restrict__ cells, uint32_t* __restrict__ codes) {
+  unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_cells) return;
+  const unsigned long long cid = cell_id[a];
+  const int b = (int)((cid >> 14) & 31u);
+  const unsigned gw = (unsigned)(cid >> 19);
+  const unsigned row = gw / (unsigned)g.W;
+  const int w = (int)(gw - row * (unsigned)g.W);
+  const int i = (int)(row / (unsigned)g.n1), j = (int)(row - (unsigned)i * (unsigned)g.n1);
+  const int k = w * 32 + b;
   unsigned code = 0;
   unsigned e = cell_emit_exact(g, i, j, k, &code);
-  if (e) {
-    unsigned slot = atomicAdd(&ctr->n_codes, 1u);
-    cells[slot] = (((long long)i + g.plane_offset) * (g.n1 - 1) + j) * (long long)(g.n2 - 1) + k;
-    codes[slot] = code;
-  }
+  cells[a] = e ? (((long long)i + g.plane_offset) * (g.n1 - 1) + j) * (long long)(g.n2 - 1) + k : -1;
+  codes[a] = code;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -731,6 +1180,14 @@ int load_tables(ctr_ctx* ctx) {
   CTR_CUDA(ctx, cudaMemcpyToSymbol(c_edge_d, CTR_EDGE3_D_H, sizeof(CTR_EDGE3_D_H)));
   CTR_CUDA(ctx, cudaMemcpyToSymbol(c_tetmask, CTR_TETMASK3_H, sizeof(CTR_TETMASK3_H)));
   CTR_CUDA(ctx, cudaMemcpyToSymbol(c_tet, CTR_TET3_H, sizeof(CTR_TET3_H)));
+  uint32_t packed[96];
+  for (int t = 0; t < 6; ++t)
+    for (int m = 0; m < 16; ++m) {
+      uint32_t e = CTR_TRI3_N_H[t][m];
+      for (int q = 0; q < 6; ++q) e |= (uint32_t)(CTR_TRI3_E_H[t][m][q] & 31u) << (2 + 5 * q);
+      packed[t * 16 + m] = e;
+    }
+  CTR_CUDA(ctx, cudaMemcpyToSymbol(c_tri_packed, packed, sizeof(packed)));
   if (ctx->device < 64) g_tables_loaded[ctx->device] = true;
   return 0;
 }
@@ -763,6 +1220,64 @@ void thresholds<float>(double v, float& thr, float& nlo, float& nhi) {
   if ((double)nhi < v + r) nhi = nextafterf(nhi, INFINITY);
 }
 
+enum BitplaneKind { BP_AUTO = 0, BP_GENERIC = 1, BP_VEC = 2, BP_TMA = 3 };
+
+BitplaneKind bitplane_choice() {
+  const char* e = getenv("CTR_BITPLANE");
+  if (!e) return BP_AUTO;
+  if (!strcmp(e, "generic")) return BP_GENERIC;
+  if (!strcmp(e, "vec")) return BP_VEC;
+  if (!strcmp(e, "tma")) return BP_TMA;
+  return BP_AUTO;
+}
+
+template <typename T, bool MINMAX>
+int launch_bitplane(ctr_ctx* ctx, const T* dfield, int n0, int n1, int n2, int W, double iso, Counters* dctr) {
+  cudaStream_t st = ctx->stream;
+  T thr, nlo, nhi;
+  thresholds<T>(iso, thr, nlo, nhi);
+  const unsigned nrows = (unsigned)n0 * (unsigned)n1;
+  const size_t nsamp = (size_t)nrows * n2;
+  const size_t nwords = (size_t)nrows * W;
+  const bool linear_ok = (n2 % 32 == 0) && (((uintptr_t)dfield) % 16 == 0);
+  BitplaneKind kind = bitplane_choice();
+  if (kind == BP_AUTO) kind = linear_ok ? BP_TMA : BP_GENERIC;
+  if (!linear_ok) kind = BP_GENERIC;
+  uint32_t* bits = (uint32_t*)ctx->bits.p;
+  uint32_t* nbits = (uint32_t*)ctx->nbits.p;
+  RowGeom rg;
+  rg.rowflag = (uint8_t*)ctx->aux[4].p;
+  rg.divW.init((unsigned)W);
+  rg.divN1.init((unsigned)n1);
+  rg.n1 = n1;
+  CTR_CUDA(ctx, cudaMemsetAsync(rg.rowflag, 0, (size_t)nrows, st));
+  if (kind == BP_TMA) {
+    static bool attr_set[4] = {false, false, false, false};
+    const int smem = TMA_STAGES * TMA_CHUNK + 2 * TMA_STAGES * 8 + 64;
+    const int ti = (sizeof(T) == 4 ? 0 : 1) + (MINMAX ? 2 : 0);
+    if (!attr_set[ti]) {
+      CTR_CUDA(ctx, cudaFuncSetAttribute(k_bitplane_tma<T, MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set[ti] = true;
+    }
+    const size_t nbytes = nsamp * sizeof(T);
+    const size_t nchunks = (nbytes + TMA_CHUNK - 1) / TMA_CHUNK;
+    int blocks = (int)std::min<size_t>(nchunks, (size_t)ctx->sm_count * 2);
+    k_bitplane_tma<T, MINMAX><<<blocks, (TMA_CONSUMER_WARPS + 1) * 32, smem, st>>>(dfield, nbytes, thr, nlo, nhi, bits, nbits, rg, dctr);
+  } else if (kind == BP_VEC) {
+    const size_t nchunks = (nsamp + 32 * Vec16<T>::VEC - 1) / (32 * Vec16<T>::VEC);
+    size_t need = (nchunks + 8 * 4 - 1) / (8 * 4);
+    int blocks = (int)std::min<size_t>(std::max<size_t>(need, 1), (size_t)ctx->sm_count * 8);
+    k_bitplane_vec<T, 4, MINMAX><<<blocks, 256, 0, st>>>(dfield, nsamp, thr, nlo, nhi, bits, nbits, rg, dctr);
+  } else {
+    size_t need = (nwords + 8 * 4 - 1) / (8 * 4);
+    int blocks = (int)std::min<size_t>(std::max<size_t>(need, 1), (size_t)ctx->sm_count * 8);
+    k_bitplane_generic<T, 4, MINMAX><<<blocks, 256, 0, st>>>(dfield, nrows, n2, W, thr, nlo, nhi, bits, nbits, rg, dctr);
+  }
+  ctx->launches++;
+  CTR_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
 template <typename T>
 int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   const int n0 = (int)p->n0, n1 = (int)p->n1, n2 = (int)p->n2;
@@ -771,7 +1286,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   const long long nwords = nrows * W;
   const size_t nsamp = (size_t)nrows * n2;
   cudaStream_t st = ctx->stream;
-  if (nwords >= (1ll << 31)) return ctr_fail(ctx, CTR_ERR_UNSUPPORTED, "volume too large for 32-bit word indices");
+  if (nwords >= (1ll << 31) - 64) return ctr_fail(ctx, CTR_ERR_UNSUPPORTED, "volume too large for 32-bit word indices");
   int rc;
   if ((rc = load_tables(ctx))) return rc;
   ctr_stage_mark(ctx, 0);
@@ -784,13 +1299,11 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
     dfield = (const T*)ctx->field.p;
   }
   ctr_stage_mark(ctx, 1);
-  if ((rc = ctr_ensure(ctx, ctx->bits, (size_t)(nwords + 1) * 4))) return rc;
-  if ((rc = ctr_ensure(ctx, ctx->nbits, (size_t)(nwords + 1) * 4))) return rc;
-  if ((rc = ctr_ensure(ctx, ctx->vbase, (size_t)(nwords + 1) * 4))) return rc;
-  if ((rc = ctr_ensure(ctx, ctx->tbase, (size_t)(nwords + 1) * 4))) return rc;
-  if ((rc = ctr_ensure(ctx, ctx->list_v, (size_t)(nwords + 1) * 4))) return rc;
-  if ((rc = ctr_ensure(ctx, ctx->list_t, (size_t)(nwords + 1) * 4))) return rc;
+  if ((rc = ctr_ensure(ctx, ctx->bits, (size_t)(nwords + 4) * 4))) return rc;
+  if ((rc = ctr_ensure(ctx, ctx->nbits, (size_t)(nwords + 4) * 4))) return rc;
+  if ((rc = ctr_ensure(ctx, ctx->vbase, (size_t)(nwords + 4) * 4))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->counters, sizeof(Counters)))) return rc;
+  if ((rc = ctr_ensure(ctx, ctx->aux[4], (size_t)nrows + 16))) return rc;
   if (!ctx->counters_host) CTR_CUDA(ctx, cudaMallocHost(&ctx->counters_host, 256));
 
   Counters init;
@@ -801,19 +1314,12 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters.p, ctx->counters_host, sizeof init, cudaMemcpyHostToDevice, st));
   Counters* dctr = (Counters*)ctx->counters.p;
 
-  T thr, nlo, nhi;
-  thresholds<T>(p->isovalue, thr, nlo, nhi);
-  {
-    const int warps_per_block = 8;
-    long long need = (nwords + warps_per_block * 4 - 1) / (warps_per_block * 4);
-    int blocks = (int)std::min<long long>(need, (long long)ctx->sm_count * 8);
-    if (blocks < 1) blocks = 1;
-    k_bitplane<T, 4><<<blocks, 256, 0, st>>>(dfield, nrows, n2, W, thr, nlo, nhi, (uint32_t*)ctx->bits.p,
-                                             (uint32_t*)ctx->nbits.p, dctr);
-    ctx->launches++;
-  }
+  if (p->flags & CTR_WANT_MINMAX)
+    rc = launch_bitplane<T, true>(ctx, dfield, n0, n1, n2, W, p->isovalue, dctr);
+  else
+    rc = launch_bitplane<T, false>(ctx, dfield, n0, n1, n2, W, p->isovalue, dctr);
+  if (rc) return rc;
   ctr_stage_mark(ctx, 2);
-  Counters h;
 
   Grid<T> g;
   g.f = dfield;
@@ -827,30 +1333,56 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   g.v = p->isovalue;
   g.tolv = 1e-8 + 1e-5 * fabs(p->isovalue);
   g.any_near = 0;
-  g.near_flag = &dctr->any_near;
+  g.rowflag = (const uint8_t*)ctx->aux[4].p;
+  g.divW.init((unsigned)W);
+  g.divN1.init((unsigned)n1);
 
   const long long plane_words = (long long)n1 * W;
-  const long long word0 = (long long)g.i_lo * plane_words;
-  const long long nscan = (long long)(g.i_hiv - g.i_lo) * plane_words;
+  const unsigned word0 = (unsigned)((long long)g.i_lo * plane_words);
+  const unsigned nscan = (unsigned)((long long)(g.i_hiv - g.i_lo) * plane_words);
   const int ntiles = (int)((nscan + CS_TILE - 1) / CS_TILE);
   if ((rc = ctr_ensure(ctx, ctx->tile_state, (size_t)ntiles * 16 + 16))) return rc;
-  CTR_CUDA(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, (size_t)ntiles * 16, st));
   unsigned long long* st_vt = (unsigned long long*)ctx->tile_state.p;
   unsigned long long* st_act = st_vt + ntiles;
-  if (ntiles > 0) {
-    k_count_scan<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (uint32_t*)ctx->vbase.p, (uint32_t*)ctx->tbase.p,
-                                                   (uint32_t*)ctx->list_v.p, (uint32_t*)ctx->list_t.p, st_vt, st_act,
-                                                   dctr, ntiles);
-    ctx->launches++;
+  // list capacities: grow-only guesses; k_count_scan never writes past them and reports the true lengths
+  DevBuf& b_own_id = ctx->aux[0];
+  DevBuf& b_own_voff = ctx->aux[1];
+  DevBuf& b_cell_id = ctx->aux[2];
+  DevBuf& b_cell_toff = ctx->aux[3];
+  size_t want_own = std::max<size_t>((size_t)nwords / 2, 1 << 14), want_cell = want_own;
+  Counters h;
+  unsigned long long totV = 0, totT = 0, nOwn = 0, nCell = 0;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    if ((rc = ctr_ensure(ctx, b_own_id, want_own * 8))) return rc;
+    if ((rc = ctr_ensure(ctx, b_own_voff, want_own * 4))) return rc;
+    if ((rc = ctr_ensure(ctx, b_cell_id, want_cell * 8))) return rc;
+    if ((rc = ctr_ensure(ctx, b_cell_toff, want_cell * 4))) return rc;
+    const unsigned cap_own = (unsigned)std::min<size_t>(std::min(b_own_id.cap / 8, b_own_voff.cap / 4), 0x7fffffffu);
+    const unsigned cap_cell = (unsigned)std::min<size_t>(std::min(b_cell_id.cap / 8, b_cell_toff.cap / 4), 0x7fffffffu);
+    CTR_CUDA(ctx, cudaMemsetAsync((char*)dctr + COUNTERS_STAGE2_OFFSET, 0, sizeof(Counters) - COUNTERS_STAGE2_OFFSET, st));
+    CTR_CUDA(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, (size_t)ntiles * 16, st));
+    if (ntiles > 0) {
+      k_count_scan<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (uint32_t*)ctx->vbase.p,
+                                                     (unsigned long long*)b_own_id.p, (uint32_t*)b_own_voff.p,
+                                                     (unsigned long long*)b_cell_id.p, (uint32_t*)b_cell_toff.p, cap_own,
+                                                     cap_cell, st_vt, st_act, dctr, ntiles);
+      ctx->launches++;
+    }
+    CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CTR_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(&h, ctx->counters_host, sizeof h);
+    totV = h.total_vt & 0x7fffffffull;
+    totT = h.total_vt >> 31;
+    nOwn = h.total_act & 0x7fffffffull;
+    nCell = h.total_act >> 31;
+    if (nOwn <= cap_own && nCell <= cap_cell) break;
+    if (attempt == 2) return ctr_fail(ctx, CTR_ERR_STATE, "list capacity did not converge");
+    want_own = std::max<size_t>(nOwn, want_own);
+    want_cell = std::max<size_t>(nCell, want_cell);
   }
   ctr_stage_mark(ctx, 3);
-  CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-  CTR_CUDA(ctx, cudaStreamSynchronize(st));
-  memcpy(&h, ctx->counters_host, sizeof h);
-  const unsigned long long totV = h.total_vt & 0x7fffffffull, totT = h.total_vt >> 31;
-  const unsigned actV = (unsigned)(h.total_act & 0x7fffffffull), actT = (unsigned)(h.total_act >> 31);
   const unsigned long long nV = (g.i_hiv > g.i_hi) ? h.v_emit : totV;
-  if (totV >= 0x7fffffffull || totT >= 0x7fffffffull)
+  if (totV >= 0x7ffffff0ull || totT >= 0x7ffffff0ull)
     return ctr_fail(ctx, CTR_ERR_OVERFLOW, "more than 2^31 vertices or triangles in one call; shard the volume");
 
   out->n_verts = (int64_t)nV;
@@ -858,8 +1390,9 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   out->n_active_cells = (int64_t)h.n_cells;
   out->n_crossings = (int64_t)h.n_cross;
   out->n_codes = 0;
-  out->fmin = key_to_double(h.min_key);
-  out->fmax = key_to_double(h.max_key);
+  const bool mm = (p->flags & CTR_WANT_MINMAX) && h.min_key != ~0ull;
+  out->fmin = mm ? key_to_double(h.min_key) : NAN;
+  out->fmax = mm ? key_to_double(h.max_key) : NAN;
 
   const bool f64 = (p->flags & CTR_GEOM_F64) != 0;
   const size_t gsz = f64 ? 8 : 4;
@@ -879,27 +1412,27 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
     }
     unsigned long long* dkeys = (p->flags & CTR_WANT_KEYS) ? (unsigned long long*)ctx->keys.p : nullptr;
     uint8_t* dlow = (p->flags & CTR_WANT_KEYS) ? (uint8_t*)ctx->lowmin.p : nullptr;
-    if (actV) {
-      int blocks = (int)((actV + 3) / 4);
+    if (nOwn) {
+      int blocks = (int)((nOwn + 255) / 256);
+      const unsigned long long* oid = (const unsigned long long*)b_own_id.p;
+      const uint32_t* ovo = (const uint32_t*)b_own_voff.p;
       if (f64) {
-        k_emit_verts<T, double><<<blocks, 128, 0, st>>>(g, (const uint32_t*)ctx->list_v.p, actV,
-                                                        (const uint32_t*)ctx->vbase.p, xf, (double*)ctx->verts.p,
+        k_emit_verts<T, double><<<blocks, 256, 0, st>>>(g, oid, ovo, (unsigned)nOwn, xf, (double*)ctx->verts.p,
                                                         (p->flags & CTR_WANT_NORMALS) ? (double*)ctx->normals.p : nullptr,
                                                         dkeys, dlow);
       } else {
-        k_emit_verts<T, float><<<blocks, 128, 0, st>>>(g, (const uint32_t*)ctx->list_v.p, actV,
-                                                       (const uint32_t*)ctx->vbase.p, xf, (float*)ctx->verts.p,
+        k_emit_verts<T, float><<<blocks, 256, 0, st>>>(g, oid, ovo, (unsigned)nOwn, xf, (float*)ctx->verts.p,
                                                        (p->flags & CTR_WANT_NORMALS) ? (float*)ctx->normals.p : nullptr,
                                                        dkeys, dlow);
       }
       ctx->launches++;
     }
     ctr_stage_mark(ctx, 4);
-    if (actT) {
-      int blocks = (int)((actT + ET_WARPS - 1) / ET_WARPS);
-      k_emit_tris<T><<<blocks, ET_WARPS * 32, 0, st>>>(g, (const uint32_t*)ctx->list_t.p, actT,
-                                                       (const uint32_t*)ctx->vbase.p, (const uint32_t*)ctx->tbase.p,
-                                                       (int*)ctx->tris.p);
+    if (nCell) {
+      int blocks = (int)((nCell + ET_THREADS - 1) / ET_THREADS);
+      k_emit_tris<T><<<blocks, ET_THREADS, 0, st>>>(g, (const unsigned long long*)b_cell_id.p,
+                                                    (const uint32_t*)b_cell_toff.p, (unsigned)nCell,
+                                                    (const uint32_t*)ctx->vbase.p, (int*)ctx->tris.p);
       ctx->launches++;
     }
     ctr_stage_mark(ctx, 5);
@@ -908,14 +1441,14 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
     ctr_stage_mark(ctx, 5);
   }
   if (p->flags & CTR_WANT_CODES) {
-    if ((rc = ctr_ensure(ctx, ctx->cells, (size_t)h.n_cells * 8 + 8))) return rc;
-    if ((rc = ctr_ensure(ctx, ctx->codes, (size_t)h.n_cells * 4 + 4))) return rc;
-    if (actT) {
-      k_codes<T><<<(actT + 3) / 4, 128, 0, st>>>(g, (const uint32_t*)ctx->list_t.p, actT, (long long*)ctx->cells.p,
-                                                 (uint32_t*)ctx->codes.p, dctr);
+    if ((rc = ctr_ensure(ctx, ctx->cells, (size_t)nCell * 8 + 8))) return rc;
+    if ((rc = ctr_ensure(ctx, ctx->codes, (size_t)nCell * 4 + 4))) return rc;
+    if (nCell) {
+      k_codes<T><<<(unsigned)((nCell + 255) / 256), 256, 0, st>>>(g, (const unsigned long long*)b_cell_id.p, (unsigned)nCell,
+                                                                   (long long*)ctx->cells.p, (uint32_t*)ctx->codes.p);
       ctx->launches++;
     }
-    out->n_codes = (int64_t)h.n_cells;
+    out->n_codes = (int64_t)nCell;
   }
   ctr_stage_mark(ctx, 6);
   CTR_CUDA(ctx, cudaGetLastError());

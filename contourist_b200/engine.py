@@ -18,6 +18,7 @@ WANT_NORMALS = 4
 WANT_KEYS = 8
 WANT_CODES = 16
 NO_GEOMETRY = 32
+WANT_MINMAX = 64
 
 
 class EngineError(RuntimeError):

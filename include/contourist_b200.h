@@ -57,6 +57,7 @@ typedef enum { CTR_F32 = 0, CTR_F64 = 1 } ctr_dtype;
 #define CTR_WANT_KEYS 8u       /* per-vertex edge key + orientation (parity / dedup across slabs)    */
 #define CTR_WANT_CODES 16u     /* compact (cell, 30-bit case code) list of emitting cells            */
 #define CTR_NO_GEOMETRY 32u    /* classification, counts and offsets only                            */
+#define CTR_WANT_MINMAX 64u    /* field min / max (grid_field.py:79-80); NaN in the counts otherwise   */
 
 /* ---- context ----------------------------------------------------------------------------------- */
 CTR_API int ctr_create(int device, ctr_ctx** out);

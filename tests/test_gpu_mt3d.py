@@ -1,0 +1,200 @@
+"""GPU parity: the CUDA 3D path (through the C ABI) against the numpy oracle and the reference goldens."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import mt3d
+
+pytestmark = pytest.mark.gpu
+
+FILES = sorted(glob.glob(os.path.join(GOLDEN, "mt3d_*.npz")))
+
+
+def run_and_compare(engine, field, value, geom64=True, origin=(0, 0, 0), delta=(1, 1, 1)):
+    from contourist_b200 import engine as E
+    flags = E.WANT_KEYS | E.WANT_CODES | E.WANT_NORMALS | E.WANT_MINMAX | (E.GEOM_F64 if geom64 else 0)
+    c = engine.mt3d_run(field, value, origin=origin, delta=delta, flags=flags)
+    o = engine.mt3d_fetch()
+    gd = np.float64 if geom64 else np.float32
+    r = mt3d.extract(field, value, gd)
+    assert c.n_verts == len(r["keys"]) and c.n_tris == len(r["tris"])
+    # bit-exact: active set, case codes, edge keys, key orientation, topology
+    assert np.array_equal(o["keys"], r["keys"])
+    assert np.array_equal(o["lowmin"], r["lowmin"])
+    assert np.array_equal(np.sort(o["tris"], axis=1), np.sort(r["tris"], axis=1))
+    order = np.argsort(o["cells"])
+    assert np.array_equal(o["cells"][order], r["cells"])
+    assert np.array_equal(o["codes"][order], r["codes"])
+    assert c.n_active_cells == len(r["cells"])
+    mx, mn, ncross = mt3d.crossing_segments(field, value, count_only=True)
+    assert c.n_crossings == ncross and c.fmin == mn and c.fmax == mx
+    # geometry
+    world = (r["pos"].astype(gd) * np.asarray(delta, gd) + np.asarray(origin, gd)).astype(gd)
+    if geom64:
+        assert np.array_equal(o["verts"], world)          # fp64 mode: 0 ulp (north_star asks 1e-6 rel)
+    else:
+        np.testing.assert_allclose(o["verts"], world, rtol=1e-4, atol=1e-5)   # fp32 mode: 1e-4 rel
+    nr = mt3d.normals(field, value, r["keys"], gd, delta=delta)
+    np.testing.assert_allclose(o["normals"], nr, rtol=1e-9 if geom64 else 1e-4, atol=1e-11 if geom64 else 1e-4)
+    return c, o, r
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_golden_fields(engine, path, dtype):
+    g = np.load(path)
+    field = g["field"].astype(dtype)
+    c, o, r = run_and_compare(engine, field, float(g["value"]), geom64=(dtype == np.float64))
+    if dtype == np.float64:
+        # straight against the reference's own output (not via the oracle)
+        n0, n1, n2 = field.shape
+        klow, khigh = g["key_low"], g["key_high"]
+        pmin = np.minimum(klow, khigh)
+        d = np.maximum(klow, khigh) - pmin
+        gk = ((((pmin[:, 0] * n1 + pmin[:, 1]) * n2 + pmin[:, 2]).astype(np.uint64) << np.uint64(3))
+              | (d[:, 0] * 4 + d[:, 1] * 2 + d[:, 2]).astype(np.uint64))
+        srt = np.argsort(gk)
+        assert np.array_equal(gk[srt], o["keys"])
+        assert np.array_equal(g["key_pos"][srt], o["verts"])
+        assert len(g["tris"]) == c.n_tris
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 2), (3, 2, 33), (33, 17, 70), (5, 64, 31), (40, 40, 40), (9, 9, 129)])
+def test_random_fields_ragged_shapes(engine, shape):
+    rng = np.random.default_rng(sum(shape))
+    run_and_compare(engine, rng.standard_normal(shape), 0.05)
+
+
+def test_world_transform_and_f32_field_f64_geometry(engine):
+    g = np.linspace(-1, 1, 49)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    f = (X * X + 0.5 * Y * Y + Z * Z + 0.1 * np.sin(7 * X)).astype(np.float32)
+    run_and_compare(engine, f, 0.5, geom64=True, origin=(-1.0, -1.0, -1.0), delta=(1 / 24.0, 1 / 24.0, 1 / 24.0))
+    run_and_compare(engine, f, 0.5, geom64=False, origin=(-1.0, 2.0, 0.5), delta=(0.25, 0.5, 2.0))
+
+
+def test_exact_equality_and_plateaus(engine):
+    rng = np.random.default_rng(3)
+    ints = rng.integers(-2, 3, size=(21, 19, 37)).astype(np.float32)       # many samples == isovalue
+    run_and_compare(engine, ints, 0.0, geom64=False)
+    run_and_compare(engine, ints.astype(np.float64), 1.0)
+    shape = (12, 12, 40)                                                    # patchy allclose(value) plateau
+    plate = np.where(rng.random(shape) < 0.6, 0.3 + 1e-7 * rng.standard_normal(shape),
+                     0.3 + 0.4 * rng.standard_normal(shape))
+    c, o, r = run_and_compare(engine, plate, 0.3)
+    skipped = ((r["codes"][:, None] >> (5 * np.arange(6, dtype=np.uint32))[None, :]) & 16).any()
+    assert skipped
+
+
+def test_empty_and_constant_fields(engine):
+    from contourist_b200 import engine as E
+    for f in (np.zeros((8, 8, 8)), np.full((4, 5, 6), 2.0, dtype=np.float32)):
+        c = engine.mt3d_run(f, 1.0, flags=E.WANT_KEYS)
+        assert c.n_verts == 0 and c.n_tris == 0 and c.n_active_cells == 0
+        o = engine.mt3d_fetch()
+        assert o["verts"].shape == (0, 3) and o["tris"].shape == (0, 3)
+    c = engine.mt3d_run(np.full((4, 4, 4), 1.0), 1.0)     # f == v everywhere: all "high", all allclose
+    assert c.n_tris == 0
+
+
+def test_triangles_wound_toward_high_side(engine):
+    from contourist_b200 import engine as E
+    g = np.linspace(-1, 1, 41)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    f = X * X + Y * Y + Z * Z                      # increases outward: normals must point outward
+    engine.mt3d_run(f, 0.5, flags=E.GEOM_F64 | E.WANT_NORMALS)
+    o = engine.mt3d_fetch()
+    P, t = o["verts"], o["tris"]
+    fn = np.cross(P[t[:, 1]] - P[t[:, 0]], P[t[:, 2]] - P[t[:, 0]])
+    cen = (P[t[:, 0]] + P[t[:, 1]] + P[t[:, 2]]) / 3 - 20.0
+    area = np.linalg.norm(fn, axis=1)
+    big = area > 1e-9                      # samples exactly on the isovalue give zero-area triangles
+    assert big.sum() > 0.9 * len(t)
+    assert ((fn * cen).sum(axis=1)[big] > 0).all()
+    gn = o["normals"][t[:, 0]]
+    assert ((fn * gn).sum(axis=1)[big] > 0).all()
+
+
+def test_bad_arguments_raise(engine):
+    with pytest.raises(ValueError):
+        engine.mt3d_run(np.zeros((1, 4, 4)), 0.0)
+    with pytest.raises(ValueError):
+        engine.mt3d_run(np.zeros((4, 4, 4)), float("nan"))
+    with pytest.raises(ValueError):
+        engine.mt3d_run(np.zeros((4, 4, 4)), 0.0, delta=(1, 0, 1))
+
+
+def test_slab_sharding_matches_single_run(engine):
+    """Multi-GPU decomposition emulated on one device: N z-slabs with halo planes reproduce the single-run
+    mesh exactly (global keys, positions, and triangles after adding each shard's vertex offset)."""
+    from contourist_b200 import engine as E
+    rng = np.random.default_rng(11)
+    g = np.linspace(-1, 1, 50)
+    X, Y, Z = np.meshgrid(g, g[:31], g[:37], indexing="ij")
+    f = (np.sin(4 * X) * np.cos(3 * Y) + Z * Z + 0.05 * rng.standard_normal(X.shape)).astype(np.float32)
+    flags = E.WANT_KEYS | E.WANT_NORMALS | E.GEOM_F64
+    c0 = engine.mt3d_run(f, 0.2, flags=flags)
+    ref = engine.mt3d_fetch()
+    n0 = f.shape[0]
+    for nshard in (2, 3, 7):
+        bounds = [round(r * n0 / nshard) for r in range(nshard + 1)]
+        keys, verts, normals, tris, voff = [], [], [], [], 0
+        for r in range(nshard):
+            a, b = bounds[r], bounds[r + 1]
+            lo = max(a - 1, 0)
+            hi = min(b + 2, n0)
+            sub = np.ascontiguousarray(f[lo:hi])
+            c = engine.mt3d_run(sub, 0.2, flags=flags, i_lo=a - lo, i_hi=b - lo, plane_offset=lo)
+            o = engine.mt3d_fetch()
+            keys.append(o["keys"]); verts.append(o["verts"]); normals.append(o["normals"])
+            tris.append(o["tris"].astype(np.int64) + voff)
+            voff += c.n_verts
+        assert np.array_equal(np.concatenate(keys), ref["keys"])
+        assert np.array_equal(np.concatenate(verts), ref["verts"])
+        np.testing.assert_allclose(np.concatenate(normals), ref["normals"], rtol=1e-12, atol=1e-14)
+        assert np.array_equal(np.concatenate(tris), ref["tris"].astype(np.int64))
+
+
+def test_full_size_properties_512(engine):
+    """BASELINE config 3 size: 512^3 fp32 CT-like volume.  Size-independent properties: the mesh is a closed
+    2-manifold away from the domain boundary (every interior edge shared by exactly 2 triangles with opposite
+    direction), Euler-consistent counts, indices in range, and per-stage counts agree with a z-slab re-run."""
+    import torch
+    from contourist_b200 import engine as E
+    from contourist_b200 import synthetic
+    n = 512
+    f = synthetic.ct_like(n, device="cuda")
+    c = engine.mt3d_run(f.data_ptr(), 0.5, shape=(n, n, n), dtype=np.float32, flags=E.WANT_NORMALS | E.WANT_KEYS)
+    o = engine.mt3d_fetch()
+    t = o["tris"].astype(np.int64)
+    assert t.min() >= 0 and t.max() < c.n_verts and c.n_tris > 1000000
+    assert np.array_equal(np.unique(t), np.arange(c.n_verts))            # every vertex used
+    assert (np.diff(o["keys"].astype(np.int64)) > 0).all()               # ids are ranks of sorted unique keys
+    # directed edges: each appears once; interior edges have their reverse
+    e = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]])
+    code = e[:, 0] * c.n_verts + e[:, 1]
+    assert len(np.unique(code)) == len(code)
+    rev = e[:, 1] * c.n_verts + e[:, 0]
+    has_rev = np.isin(code, rev)
+    # edges without a reverse lie on the domain boundary
+    P = o["verts"]
+    lone = e[~has_rev]
+    pa, pb = P[lone[:, 0]], P[lone[:, 1]]
+    on_face = ((pa == 0) & (pb == 0)) | ((pa == n - 1) & (pb == n - 1))
+    assert on_face.any(axis=1).all()
+    nn = np.linalg.norm(o["normals"], axis=1)
+    assert np.all((np.abs(nn - 1) < 1e-3) | (nn == 0))
+    # slab re-run (2 shards) reproduces counts
+    half = n // 2
+    c_a = engine.mt3d_run(f.data_ptr(), 0.5, shape=(half + 2, n, n), dtype=np.float32, flags=E.NO_GEOMETRY,
+                          i_lo=0, i_hi=half)
+    c_b = engine.mt3d_run(f[half - 1:].data_ptr(), 0.5, shape=(n - half + 1, n, n), dtype=np.float32,
+                          flags=E.NO_GEOMETRY, i_lo=1, i_hi=n - half + 1, plane_offset=half - 1)
+    assert c_a.n_verts + c_b.n_verts == c.n_verts
+    assert c_a.n_tris + c_b.n_tris == c.n_tris
+    assert c_a.n_active_cells + c_b.n_active_cells == c.n_active_cells
+    del f
+    torch.cuda.empty_cache()
