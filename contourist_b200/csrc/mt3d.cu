@@ -339,8 +339,12 @@ __global__ void __launch_bounds__((TMA_CONSUMER_WARPS + 1) * 32) k_bitplane_tma(
   constexpr int NW = TMA_CHUNK / (32 * (int)sizeof(T));          // bit words per stage
   constexpr int WPW = NW / TMA_CONSUMER_WARPS;                   // words per warp per stage (<= 32)
   static_assert(WPW >= 1 && WPW <= 32, "stage geometry");
+  uint32_t* swords = reinterpret_cast<uint32_t*>(empty + TMA_STAGES) + warp * 32;   // per-warp word staging
+  // conservative centre / radius form of the hull test: |x - vc| <= vr  (superset of [near_lo, near_hi])
+  const T vc = (T)0.5 * near_lo + (T)0.5 * near_hi;
+  const T vr = (near_hi - near_lo) * (T)0.55 + fabs(vc) * (T)1e-6 + (T)1e-30;
   T mn = INFINITY, mx = -INFINITY;
-  bool anynear = false;
+  const bool anynear = false;
   unsigned it = 0;
   for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
     const int s = it % TMA_STAGES;
@@ -355,36 +359,42 @@ __global__ void __launch_bounds__((TMA_CONSUMER_WARPS + 1) * 32) k_bitplane_tma(
     for (int q = 0; q < WPW; ++q) val[q] = sv[q * 32 + lane];    // conflict-free: lane <-> bank
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);                       // stage is in registers: release it early
-    unsigned mine = 0, mine_n = 0;
     const unsigned wbase = warp * WPW;
-    bool nearhere = false;
+    const size_t word0 = off / (32 * sizeof(T)) + wbase;
+    if (words_here < (unsigned)NW) {
+      // partial last chunk: samples past the end are stale shared memory; neutralise them
+#pragma unroll
+      for (int q = 0; q < WPW; ++q)
+        if (wbase + q >= words_here) val[q] = INFINITY;
+    }
+    T dist = INFINITY;
 #pragma unroll
     for (int q = 0; q < WPW; ++q) {
-      if (wbase + q >= words_here) break;                        // warp-uniform: partial last chunk
-      unsigned wl = __ballot_sync(0xffffffffu, val[q] < thr);
-      if ((int)lane == q) mine = wl;
-      nearhere |= (val[q] >= near_lo) && (val[q] <= near_hi);
+      const unsigned wl = __ballot_sync(0xffffffffu, val[q] < thr);
+      if (lane == 0) swords[q] = wl;
+      dist = fmin(dist, fabs(val[q] - vc));                     // NaN never wins: not near
       if (MINMAX) {
         mn = fmin(mn, val[q]);
         mx = fmax(mx, val[q]);
       }
     }
-    const size_t word0 = off / (32 * sizeof(T)) + wbase;
-    if (__any_sync(0xffffffffu, nearhere)) {                     // rare: materialise the near words of this warp
+    unsigned mine_n = 0;
+    if (__any_sync(0xffffffffu, dist <= vr)) {                   // rare: materialise the near words of this warp
 #pragma unroll
       for (int q = 0; q < WPW; ++q) {
-        if (wbase + q >= words_here) break;
-        unsigned wn = __ballot_sync(0xffffffffu, (val[q] >= near_lo) && (val[q] <= near_hi));
+        const unsigned wn = __ballot_sync(0xffffffffu, (val[q] >= near_lo) && (val[q] <= near_hi));
         if ((int)lane == q) {
           mine_n = wn;
           if (wn) flag_rows(rg, rg.divW.div((unsigned)(word0 + q)));
         }
       }
     }
+    __syncwarp();
     if ((int)lane < WPW && wbase + lane < words_here) {
-      bits[word0 + lane] = mine;
+      bits[word0 + lane] = swords[lane];
       nbits[word0 + lane] = mine_n;
     }
+    __syncwarp();
   }
   minmax_commit(mn, mx, anynear, ctr);
 }
@@ -631,7 +641,7 @@ struct CsShared {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(CS_THREADS) k_count_scan(Grid<T> gin, unsigned word0, unsigned nwords_scan,
+__global__ void __launch_bounds__(CS_THREADS, 3) k_count_scan(Grid<T> gin, unsigned word0, unsigned nwords_scan,
                                                            uint32_t* __restrict__ vbase,
                                                            unsigned long long* __restrict__ own_id,
                                                            uint32_t* __restrict__ own_voff,
@@ -705,10 +715,15 @@ __global__ void __launch_bounds__(CS_THREADS) k_count_scan(Grid<T> gin, unsigned
     uint32_t em = 0;
     if (cells_ok) {
       // strict crossings for owners inside the voxel range (grid_field.py:64-84)
-      uint32_t xs[7];
-      cross_words(pl, xs);
+      if (!g.any_near) {
 #pragma unroll
-      for (int d = 0; d < 7; ++d) ncross += __popc(xs[d] & pl.kp1);
+        for (int d = 0; d < 7; ++d) ncross += __popc(x[d] & pl.kp1);
+      } else {
+        uint32_t xs[7];
+        cross_words(pl, xs);
+#pragma unroll
+        for (int d = 0; d < 7; ++d) ncross += __popc(xs[d] & pl.kp1);
+      }
       uint32_t odd[6], two[6], cand;
       tet_words(pl, nullptr, pl.kp1, odd, two, cand);
 #pragma unroll
@@ -1253,7 +1268,7 @@ int launch_bitplane(ctr_ctx* ctx, const T* dfield, int n0, int n1, int n2, int W
   CTR_CUDA(ctx, cudaMemsetAsync(rg.rowflag, 0, (size_t)nrows, st));
   if (kind == BP_TMA) {
     static bool attr_set[4] = {false, false, false, false};
-    const int smem = TMA_STAGES * TMA_CHUNK + 2 * TMA_STAGES * 8 + 64;
+    const int smem = TMA_STAGES * TMA_CHUNK + 2 * TMA_STAGES * 8 + TMA_CONSUMER_WARPS * 32 * 4 + 64;
     const int ti = (sizeof(T) == 4 ? 0 : 1) + (MINMAX ? 2 : 0);
     if (!attr_set[ti]) {
       CTR_CUDA(ctx, cudaFuncSetAttribute(k_bitplane_tma<T, MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
