@@ -191,6 +191,54 @@ class Engine(object):
         out.update(verts=a_v, normals=a_n, tris=a_t, keys=a_k, lowmin=a_l, cells=a_c, codes=a_d)
         return out
 
+    # ------------------------------------------------------------------ 2D
+    def mt2d_run(self, field, levels, origin=(0.0, 0.0), delta=(1.0, 1.0), flags=0, i_lo=0, i_hi=None,
+                 row_offset=0, shape=None, dtype=None):
+        """field: numpy [n0,n1] float32/float64 or device pointer (+shape, dtype); levels: strictly increasing."""
+        from ._bindings import Mt2dParams, Mt2dCounts
+        p = Mt2dParams()
+        if isinstance(field, np.ndarray):
+            if field.dtype not in (np.float32, np.float64):
+                field = field.astype(np.float64)
+            field = np.ascontiguousarray(field)
+            if field.ndim != 2:
+                raise ValueError("2D field expected")
+            self._keep = field
+            p.field = field.ctypes.data
+            p.dtype = F32 if field.dtype == np.float32 else F64
+            shape = field.shape
+            flags &= ~FIELD_ON_DEVICE
+        else:
+            p.field = int(field)
+            p.dtype = F32 if np.dtype(dtype) == np.float32 else F64
+            flags |= FIELD_ON_DEVICE
+        lv = np.ascontiguousarray(np.asarray(levels, dtype=np.float64))
+        self._keep_levels = lv
+        p.flags = flags
+        p.n0, p.n1 = (int(s) for s in shape)
+        p.levels = lv.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        p.nlevels = int(lv.shape[0])
+        for a in range(2):
+            p.origin[a] = float(origin[a])
+            p.delta[a] = float(delta[a])
+        p.i_lo = int(i_lo)
+        p.i_hi = int(p.n0 if i_hi is None else i_hi)
+        p.row_offset = int(row_offset)
+        c = Mt2dCounts()
+        self._check(self.lib.ctr_mt2d_run(self.h, ctypes.byref(p), ctypes.byref(c)), "ctr_mt2d_run")
+        self._last2 = (flags, c)
+        return c
+
+    def mt2d_fetch(self):
+        flags, c = self._last2
+        gd = np.float64 if flags & GEOM_F64 else np.float32
+        S = int(c.n_segments)
+        lvl = np.empty((S,), dtype=np.uint8)
+        keys = np.empty((S, 2), dtype=np.uint64)
+        pos = np.empty((S, 2, 2), dtype=gd)
+        self._check(self.lib.ctr_mt2d_fetch(self.h, _ptr(lvl), _ptr(keys), _ptr(pos)), "ctr_mt2d_fetch")
+        return dict(level=lvl, keys=keys, pos=pos)
+
     def mt3d_device_ptrs(self):
         v, n, t = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
         self._check(self.lib.ctr_mt3d_device_ptrs(self.h, ctypes.byref(v), ctypes.byref(n), ctypes.byref(t)),

@@ -116,6 +116,39 @@ CTR_API int ctr_mt3d_fetch(ctr_ctx* ctx, void* verts, void* normals, int32_t* tr
 /* Device pointers of the last run's outputs (valid until the next *_run on this context).          */
 CTR_API int ctr_mt3d_device_ptrs(ctr_ctx* ctx, void** verts, void** normals, int32_t** tris);
 
+/* ---- 2D marching triangles, all levels in one pass ------------------------------------------------
+ * Replaces, for an array-backed field, the reference's
+ *   multiple_2d_contour.py:63-75 + :50-61  search_grid_for_crossings / classify_endpoint_values
+ *   triangulated.py:198-213,307-378        search_grid / find_initial_contour_pairs / expand_contour_pairs /
+ *                                          find_all_adjacent_contour_pairs / contour_pair_interpolation
+ *   triangulated.py:66-77,295-305          adjacent_pairs / find_adjacencies   (segments = linked key pairs)
+ *   multiple_2d_contour.py:100-108         Linear2DContour.get_values          (fmin / fmax)
+ * field[i][j], points in range are 0 <= i < n0, 0 <= j < n1 (no extra sample, unlike 3D/4D).
+ * Edge key = ((lin(min endpoint)*4 + d) << 1) | lowmin, d = di*2 + dj in {1,2,3}; the reference's key (p, q) has
+ * lowmin = 1, (q, p) has lowmin = 0 (both exist when f(p) == f(q) == level).                        */
+typedef struct {
+  const void* field;
+  int32_t dtype;
+  uint32_t flags;          /* CTR_FIELD_ON_DEVICE, CTR_GEOM_F64, CTR_NO_GEOMETRY, CTR_WANT_MINMAX            */
+  int64_t n0, n1;
+  const double* levels;    /* host array, strictly increasing                                                */
+  int32_t nlevels;         /* 1..64                                                                          */
+  int32_t reserved;
+  double origin[2], delta[2];
+  int64_t i_lo, i_hi, row_offset;   /* row-band sharding: squares of rows [i_lo, i_hi); single GPU 0, n0, 0    */
+} ctr_mt2d_params;
+
+typedef struct {
+  int64_t n_segments;
+  int64_t n_active_squares;
+  double fmin, fmax;
+} ctr_mt2d_counts;
+
+CTR_API int ctr_mt2d_run(ctr_ctx* ctx, const ctr_mt2d_params* p, ctr_mt2d_counts* out);
+/* seg_level [n_segments] index into levels; seg_keys [n_segments][2]; seg_pos [n_segments][2][2] float|double
+ * (world coordinates of the two end points).  Order: by square, triangle, level.                          */
+CTR_API int ctr_mt2d_fetch(ctr_ctx* ctx, uint8_t* seg_level, uint64_t* seg_keys, void* seg_pos);
+
 #ifdef __cplusplus
 }
 #endif

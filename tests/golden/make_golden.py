@@ -119,3 +119,66 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ------------------------------------------------------------------ 2D
+def fields2d():
+    out = {}
+    n = 21
+    g = np.linspace(-2, 2, n)
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    out["osc21"] = (np.sqrt(np.sin(3 * X + Y * Y) ** 2 + np.cos(4 * Y + X * X) ** 2), [0.3, 0.6, 0.9, 1.2])
+    rng = np.random.default_rng(5)
+    out["noise"] = (rng.standard_normal((12, 15)), [-0.5, 0.0, 0.7])
+    out["ints"] = (rng.integers(0, 4, size=(9, 11)).astype(np.float64), [0.5, 1.0, 2.0])
+    return out
+
+
+def run2d(arr, levels):
+    M = rh.load("multiple_2d_contour")
+    T = rh.load("triangulated")
+    G = rh.load("grid_field")
+    n0, n1 = arr.shape
+
+    def f(x, y):
+        return float(arr[min(max(int(round(x)), 0), n0 - 1), min(max(int(round(y)), 0), n1 - 1)])
+    grid = G.FunctionGrid((0, 0), (n0 - 1, n1 - 1), (1, 1), f)
+    assert tuple(grid.grid_dimensions) == (n0, n1)
+    C = M.Multiple2DContourGrid(grid, levels)
+    t0 = time.time()
+    # multiple_2d_contour.py:17-30, keeping each level's contour maker so its raw state can be read
+    C.classify_endpoints()
+    out = dict(field=arr, levels=np.array(sorted(levels), dtype=np.float64))
+    for li, value in enumerate(sorted(C.value_to_endpoints)):
+        endpoints = C.value_to_endpoints[value]
+        try:
+            cm = T.DxDy2DContourGrid(grid, value, endpoints)
+            seqs = cm.get_contour_sequences()
+        except AssertionError as e:
+            print("   level", value, "reference assertion:", e)
+            out["L%d_failed" % li] = np.int64(1)
+            continue
+        pairs = sorted(cm.contour_maker.interpolated_contour_pairs.keys())
+        out["L%d_low" % li] = np.array([p[0] for p in pairs], dtype=np.int64).reshape(-1, 2)
+        out["L%d_high" % li] = np.array([p[1] for p in pairs], dtype=np.int64).reshape(-1, 2)
+        out["L%d_pos" % li] = np.array([cm.contour_maker.interpolated_contour_pairs[p] for p in pairs],
+                                       dtype=np.float64).reshape(-1, 2)
+        out["L%d_closed" % li] = np.array([c for c, _ in cm.grid_contours], dtype=np.int64)
+        out["L%d_len" % li] = np.array([len(p) for _, p in cm.grid_contours], dtype=np.int64)
+        out["L%d_pts" % li] = (np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 2) for _, p in cm.grid_contours])
+                               if cm.grid_contours else np.zeros((0, 2)))
+        trip = sorted(sorted(t) for t in cm.contour_maker.triangle_triples)
+        out["L%d_triples" % li] = np.array(trip, dtype=np.int64).reshape(-1, 3, 2)
+    out["seconds"] = np.float64(time.time() - t0)
+    return out
+
+
+def main2d():
+    for name, (arr, levels) in fields2d().items():
+        g = run2d(arr, levels)
+        np.savez_compressed(os.path.join(HERE, "mt2d_%s.npz" % name), **g)
+        print(name, arr.shape, [(k, g[k].shape) for k in sorted(g) if k.endswith("_low")], "%.1fs" % g["seconds"])
+
+
+if __name__ == "__main__" and "2d" in sys.argv[1:]:
+    main2d()
