@@ -44,7 +44,7 @@ struct ctr_ctx {
   int64_t last_counts[8] = {};
 
   // 2D / 4D extra outputs are declared in their own translation units via these generic slots
-  DevBuf aux[12];
+  DevBuf aux[32];
 };
 
 static inline int ctr_fail(ctr_ctx* ctx, int code, const char* what, const char* detail = "") {

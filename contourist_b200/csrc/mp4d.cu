@@ -1,0 +1,1094 @@
+// 4D marching pentatopes on sm_100a: f(x,y,z,t) = v over a regular 4D grid -> tetrahedra of a 3-manifold,
+// then (morph stage) time-binning, instant/tiny filtering and slicing of every tetrahedron into morph triangles.
+// Same bitplane-first architecture as mt3d.cu:
+//   stage 1 (bitplane.cuh) : the field is streamed ONCE into low / near bitplanes (TMA bulk copies);
+//   k4_count_scan          : per 32-hypervoxel word, from the bitplanes: distinct crossing edges (15 Kuhn
+//                            directions per owner), tetrahedra (24 pentatopes x {1,3}), decoupled-lookback scan,
+//                            compacted owner / hypervoxel lists;
+//   k4_emit_verts          : edge crossings in 4D (tetrahedral.py:471-487);
+//   k4_emit_tets           : per hypervoxel, 24 pentatopes (pentatopes.py:15-26,223-291) -> tets of vertex ids;
+//   k4_bin / k4_tet_filter / k4_slice_count / k4_slice_emit : pentatopes.py:162-189, tetrahedral.py:353-375
+//                            (predicate), morph_geometry.py:145-237.
+#include "bitplane.cuh"
+#include "tables.h"
+
+namespace {
+
+__constant__ uint8_t c4_pent[24][5];
+__constant__ uint8_t c4_edge_s[CTR_NEDGE4];
+__constant__ uint8_t c4_edge_d[CTR_NEDGE4];
+__constant__ uint32_t c4_pentmask[16][16];
+__device__ uint8_t d4_tet_n[24][32];
+__device__ uint8_t d4_tet_e[24][32][12];
+
+struct Counters4 {
+  unsigned long long min_key, max_key;
+  unsigned int pad0, pad1;
+  unsigned long long n_cells, n_cross, total_vt, total_act, v_emit;
+  unsigned int ticket, pad2;
+};
+constexpr size_t C4_STAGE2_OFFSET = 24;
+
+template <typename T>
+struct Grid4 {
+  const T* f;
+  const uint32_t* bits;
+  const uint32_t* nbits;
+  const uint8_t* rowflag;
+  int n0, n1, n2, n3, W;
+  double v, tolv;
+  int any_near;
+  FastDiv divW, divN2, divN1;
+  __device__ __forceinline__ void word_coords(unsigned gw, int& i, int& j, int& k, int& w) const {
+    unsigned row = divW.div(gw);
+    w = (int)(gw - row * (unsigned)W);
+    unsigned ij = divN2.div(row);
+    k = (int)(row - ij * (unsigned)n2);
+    unsigned ii = divN1.div(ij);
+    i = (int)ii;
+    j = (int)(ij - ii * (unsigned)n1);
+  }
+  __device__ __forceinline__ size_t row_of(int i, int j, int k) const { return ((size_t)i * n1 + j) * n2 + k; }
+};
+
+template <typename T>
+__device__ __forceinline__ double sample4(const Grid4<T>& g, int i, int j, int k, int l) {
+  return (double)g.f[g.row_of(i, j, k) * g.n3 + l];
+}
+
+__device__ __forceinline__ bool near_a4(double f, double v) {
+  return fabs(v - f) <= __dadd_rn(1e-8, __dmul_rn(1e-5, fabs(f)));
+}
+
+// 24-bit mask of the pentatopes of hypervoxel (i,j,k,l) that emit tetrahedra (exact, fp64, from the samples)
+template <typename T>
+__device__ __noinline__ unsigned cell_emit_exact4(const Grid4<T>& g, int i, int j, int k, int l, uint8_t* codes24) {
+  if (i < 0 || j < 0 || k < 0 || l < 0 || i >= g.n0 - 1 || j >= g.n1 - 1 || k >= g.n2 - 1 || l >= g.n3 - 1) {
+    if (codes24)
+      for (int p = 0; p < 24; ++p) codes24[p] = 0;
+    return 0;
+  }
+  bool all_a = true;
+  unsigned low = 0, nb = 0;
+  for (int c = 0; c < 16; ++c) {
+    const double fv = sample4(g, i + ((c >> 3) & 1), j + ((c >> 2) & 1), k + ((c >> 1) & 1), l + (c & 1));
+    all_a = all_a && near_a4(fv, g.v);
+    low |= (fv < g.v ? 1u : 0u) << c;
+    nb |= (fabs(fv - g.v) <= g.tolv ? 1u : 0u) << c;
+  }
+  unsigned emit = 0;
+  for (int p = 0; p < 24; ++p) {
+    unsigned m = 0, alln = 1;
+    for (int b = 0; b < 5; ++b) {
+      const int c = c4_pent[p][b];
+      m |= ((low >> c) & 1u) << b;
+      alln &= (nb >> c) & 1u;
+    }
+    if (codes24) codes24[p] = (uint8_t)(m | (alln << 5));
+    if (m != 0 && m != 31 && !alln) emit |= 1u << p;
+  }
+  return all_a ? 0u : emit;
+}
+
+template <typename T>
+__device__ __noinline__ bool edge_used_exact4(const Grid4<T>& g, int i, int j, int k, int l, int d) {
+  for (int s = 0; s < 16; ++s) {
+    if (s & d) continue;
+    const unsigned pm = c4_pentmask[d][s];
+    if (!pm) continue;
+    const unsigned e = cell_emit_exact4(g, i - ((s >> 3) & 1), j - ((s >> 2) & 1), k - ((s >> 1) & 1), l - (s & 1), nullptr);
+    if (e & pm) return true;
+  }
+  return false;
+}
+
+// rows (i+a, j+b, k+c), a,b,c in {0,1}: P = bits at l, S = bits at l+1
+struct Planes4 {
+  uint32_t P[8], S[8];
+  uint32_t kpt, kp1;
+  bool has[8];                 // row abc exists
+};
+
+__device__ __forceinline__ uint32_t low_mask4(int n) { return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
+
+template <typename T>
+__device__ __forceinline__ void load_planes4(const Grid4<T>& g, const uint32_t* __restrict__ plane, int i, int j, int k, int w,
+                                             Planes4& pl) {
+  const int rem = g.n3 - w * 32;
+  pl.kpt = low_mask4(rem);
+  pl.kp1 = low_mask4(rem - 1);
+#pragma unroll
+  for (int abc = 0; abc < 8; ++abc) {
+    const int a = abc >> 2, b = (abc >> 1) & 1, c = abc & 1;
+    const bool ok = (i + a < g.n0) && (j + b < g.n1) && (k + c < g.n2);
+    uint32_t p = 0, nx = 0;
+    if (ok) {
+      const size_t base = g.row_of(i + a, j + b, k + c) * g.W + w;
+      p = plane[base];
+      if (w + 1 < g.W) nx = plane[base + 1];
+    }
+    pl.has[abc] = ok;
+    pl.P[abc] = p;
+    pl.S[abc] = (p >> 1) | (nx << 31);
+  }
+}
+
+__device__ __forceinline__ uint32_t corner_plane4(const Planes4& pl, int c) { return (c & 1) ? pl.S[c >> 1] : pl.P[c >> 1]; }
+
+// crossing words for the 15 edge directions of the owner row (index d-1), masked to edges inside the grid
+__device__ __forceinline__ void cross_words4(const Planes4& pl, uint32_t x[15]) {
+  const uint32_t A = pl.P[0];
+#pragma unroll
+  for (int d = 1; d <= 15; ++d) {
+    const int abc = d >> 1;
+    const uint32_t other = (d & 1) ? pl.S[abc] : pl.P[abc];
+    const uint32_t valid = ((d & 1) ? pl.kp1 : pl.kpt) & (pl.has[abc] ? 0xffffffffu : 0u);
+    x[d - 1] = (A ^ other) & valid;
+  }
+}
+
+// per word: number of tetrahedra and mask of emitting hypervoxels (fast, bit-sliced; no allclose handling);
+// cand = hypervoxels that have a crossing pentatope whose 5 corners are all near
+__device__ __forceinline__ void pent_words4(const Planes4& pl, const Planes4* npl, uint32_t cellmask, unsigned& ntet,
+                                            uint32_t& emitting, uint32_t& cand) {
+  ntet = 0;
+  emitting = 0;
+  cand = 0;
+#pragma unroll
+  for (int p = 0; p < 24; ++p) {
+    const uint32_t v0 = corner_plane4(pl, c4_pent[p][0]), v1 = corner_plane4(pl, c4_pent[p][1]),
+                   v2 = corner_plane4(pl, c4_pent[p][2]), v3 = corner_plane4(pl, c4_pent[p][3]),
+                   v4 = corner_plane4(pl, c4_pent[p][4]);
+    const uint32_t dif = ((v0 ^ v1) | (v0 ^ v2) | (v0 ^ v3) | (v0 ^ v4)) & cellmask;
+    // bit-sliced population count of the 5 low bits: n = s0 + 2*t0 + 4*t1
+    const uint32_t a0 = v0 ^ v1 ^ v2, a1 = (v0 & v1) | (v2 & (v0 ^ v1));
+    const uint32_t b0 = v3 ^ v4, b1 = v3 & v4;
+    const uint32_t c = a0 & b0;
+    const uint32_t t0 = a1 ^ b1 ^ c;                 // set <=> 2 or 3 low corners -> 3 tetrahedra, else 1
+    ntet += __popc(dif) + 2 * __popc(dif & t0);
+    emitting |= dif;
+    if (npl) {
+      const uint32_t nn = corner_plane4(*npl, c4_pent[p][0]) & corner_plane4(*npl, c4_pent[p][1]) &
+                          corner_plane4(*npl, c4_pent[p][2]) & corner_plane4(*npl, c4_pent[p][3]) &
+                          corner_plane4(*npl, c4_pent[p][4]);
+      cand |= nn & dif;
+    }
+  }
+}
+
+template <typename T>
+__device__ __noinline__ void resolve_used_exact4(const Grid4<T>& g, int i, int j, int k, int w, uint32_t used[15]) {
+  Planes4 npl;
+  load_planes4(g, g.nbits, i, j, k, w, npl);
+  for (int d = 1; d <= 15; ++d) {
+    const int abc = d >> 1;
+    uint32_t c = used[d - 1] & npl.P[0] & ((d & 1) ? npl.S[abc] : npl.P[abc]);
+    while (c) {
+      const int b = __ffs(c) - 1;
+      c &= c - 1;
+      if (!edge_used_exact4(g, i, j, k, w * 32 + b, d)) used[d - 1] &= ~(1u << b);
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void owner_used4(const Grid4<T>& g, const Planes4& pl, int i, int j, int k, int w, uint32_t used[15]) {
+  cross_words4(pl, used);
+  if (g.any_near) resolve_used_exact4(g, i, j, k, w, used);
+}
+
+__device__ __forceinline__ unsigned gather15(const uint32_t u[15], int b) {
+  unsigned m = 0;
+#pragma unroll
+  for (int d = 0; d < 15; ++d) m |= ((u[d] >> b) & 1u) << d;
+  return m;
+}
+
+__device__ __forceinline__ unsigned pent_mask_of(unsigned corner16, int p) {
+  unsigned m = 0;
+#pragma unroll
+  for (int b = 0; b < 5; ++b) m |= ((corner16 >> c4_pent[p][b]) & 1u) << b;
+  return m;
+}
+
+__device__ __forceinline__ unsigned ntet_of_mask(unsigned m) {       // pentatopes.py:246-291
+  const int n = __popc(m);
+  return (n == 0 || n == 5) ? 0u : ((n == 1 || n == 4) ? 1u : 3u);
+}
+
+template <typename T>
+__device__ __noinline__ void count_word_exact4(const Grid4<T>& g, const Planes4& pl, int i, int j, int k, int w,
+                                               unsigned& ntet, uint32_t& emitting, uint32_t cand) {
+  while (cand) {
+    const int b = __ffs(cand) - 1;
+    cand &= cand - 1;
+    unsigned c16 = 0;
+    for (int c = 0; c < 16; ++c) c16 |= ((corner_plane4(pl, c) >> b) & 1u) << c;
+    for (int p = 0; p < 24; ++p) ntet -= ntet_of_mask(pent_mask_of(c16, p));
+    emitting &= ~(1u << b);
+    const unsigned e = cell_emit_exact4(g, i, j, k, w * 32 + b, nullptr);
+    if (e) emitting |= 1u << b;
+    for (int p = 0; p < 24; ++p)
+      if ((e >> p) & 1u) ntet += ntet_of_mask(pent_mask_of(c16, p));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// count + scan (same phase structure as k_count_scan in mt3d.cu)
+// ------------------------------------------------------------------------------------------------
+constexpr int C4_THREADS = 256;
+constexpr int C4_ITEMS = 4;
+constexpr int C4_TILE = C4_THREADS * C4_ITEMS;
+
+struct C4Shared {
+  uint32_t own[C4_TILE], emit[C4_TILE];
+  uint32_t pv[C4_TILE], pt[C4_TILE], po[C4_TILE], pc[C4_TILE];
+  unsigned short cv[C4_TILE], ct[C4_TILE];
+  unsigned short list[C4_TILE];
+  unsigned long long warp_vt[C4_THREADS / 32], warp_act[C4_THREADS / 32];
+  unsigned long long excl_vt, excl_act;
+  unsigned tile, nint;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(C4_THREADS, 2) k4_count_scan(Grid4<T> gin, unsigned nwords, uint32_t* __restrict__ vbase,
+                                                               unsigned long long* __restrict__ own_id,
+                                                               uint32_t* __restrict__ own_voff,
+                                                               unsigned long long* __restrict__ cell_id,
+                                                               uint32_t* __restrict__ cell_toff, unsigned cap_own,
+                                                               unsigned cap_cell, unsigned long long* status_vt,
+                                                               unsigned long long* status_act, Counters4* ctr, int ntiles) {
+  __shared__ C4Shared sh;
+  Grid4<T> g = gin;
+  g.any_near = 0;
+  if (threadIdx.x == 0) {
+    sh.tile = atomicAdd(&ctr->ticket, 1u);
+    sh.nint = 0;
+  }
+  __syncthreads();
+  const int tile = (int)sh.tile;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const unsigned tile0 = (unsigned)tile * C4_TILE;
+  // ---- A: quick test
+#pragma unroll 1
+  for (int q = 0; q < C4_ITEMS; ++q) {
+    const unsigned wl = (unsigned)q * C4_THREADS + threadIdx.x;
+    const unsigned gw = tile0 + wl;
+    bool interesting = false;
+    if (gw < nwords) {
+      int i, j, k, w;
+      g.word_coords(gw, i, j, k, w);
+      Planes4 pl;
+      load_planes4(g, g.bits, i, j, k, w, pl);
+      uint32_t any = 0;
+#pragma unroll
+      for (int d = 1; d <= 15; ++d) {
+        const int abc = d >> 1;
+        const uint32_t other = (d & 1) ? pl.S[abc] : pl.P[abc];
+        const uint32_t valid = ((d & 1) ? pl.kp1 : pl.kpt) & (pl.has[abc] ? 0xffffffffu : 0u);
+        any |= (pl.P[0] ^ other) & valid;
+      }
+      interesting = any != 0;
+    }
+    sh.cv[wl] = 0;
+    sh.ct[wl] = 0;
+    sh.own[wl] = 0;
+    sh.emit[wl] = 0;
+    const unsigned m = __ballot_sync(0xffffffffu, interesting);
+    unsigned base = 0;
+    if (lane == 0 && m) base = atomicAdd(&sh.nint, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (interesting) sh.list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)wl;
+  }
+  __syncthreads();
+  const unsigned nint = sh.nint;
+  // ---- B: counts
+  unsigned ncross = 0, ncells = 0;
+  for (unsigned idx = threadIdx.x; idx < nint; idx += C4_THREADS) {
+    const unsigned wl = sh.list[idx];
+    const unsigned gw = tile0 + wl;
+    int i, j, k, w;
+    g.word_coords(gw, i, j, k, w);
+    g.any_near = g.rowflag[g.row_of(i, j, k)];
+    Planes4 pl;
+    load_planes4(g, g.bits, i, j, k, w, pl);
+    uint32_t x[15];
+    owner_used4(g, pl, i, j, k, w, x);
+    unsigned v = 0;
+    uint32_t any = 0;
+#pragma unroll
+    for (int d = 0; d < 15; ++d) {
+      v += __popc(x[d]);
+      any |= x[d];
+    }
+    const bool cells_ok = pl.has[7];
+    unsigned t = 0;
+    uint32_t em = 0;
+    if (cells_ok) {
+      uint32_t xs[15];
+      cross_words4(pl, xs);
+      Planes4 npl;
+      if (g.any_near) load_planes4(g, g.nbits, i, j, k, w, npl);
+#pragma unroll
+      for (int d = 1; d <= 15; ++d) {
+        uint32_t xd = xs[d - 1] & pl.kp1;
+        ncross += __popc(xd);
+        if (g.any_near) {           // not strict when the high endpoint equals the isovalue exactly
+          const int abc = d >> 1;
+          const uint32_t A = pl.P[0], O = (d & 1) ? pl.S[abc] : pl.P[abc];
+          const uint32_t nO = (d & 1) ? npl.S[abc] : npl.P[abc];
+          uint32_t c = xd & ((~A & npl.P[0]) | (~O & nO));
+          while (c) {
+            const int b = __ffs(c) - 1;
+            c &= c - 1;
+            const bool a_high = !((A >> b) & 1u);
+            const int l = w * 32 + b;
+            const double fh = a_high ? sample4(g, i, j, k, l)
+                                     : sample4(g, i + ((d >> 3) & 1), j + ((d >> 2) & 1), k + ((d >> 1) & 1), l + (d & 1));
+            if (fh == g.v) --ncross;
+          }
+        }
+      }
+      uint32_t cand;
+      pent_words4(pl, g.any_near ? &npl : nullptr, pl.kp1, t, em, cand);
+      if (cand) count_word_exact4(g, pl, i, j, k, w, t, em, cand);
+    }
+    sh.cv[wl] = (unsigned short)v;
+    sh.ct[wl] = (unsigned short)t;
+    sh.own[wl] = any;
+    sh.emit[wl] = em;
+    ncells += __popc(em);
+  }
+  unsigned long long cc = ((unsigned long long)ncross << 32) | ncells;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cc += __shfl_xor_sync(0xffffffffu, cc, o);
+  if (lane == 0 && cc) {
+    if (cc & 0xffffffffull) atomicAdd(&ctr->n_cells, cc & 0xffffffffull);
+    if (cc >> 32) atomicAdd(&ctr->n_cross, cc >> 32);
+  }
+  __syncthreads();
+  // ---- C: scan
+  unsigned long long loc_vt = 0, loc_act = 0, item_vt[C4_ITEMS], item_act[C4_ITEMS];
+#pragma unroll
+  for (int it = 0; it < C4_ITEMS; ++it) {
+    const unsigned wl = threadIdx.x * C4_ITEMS + it;
+    item_vt[it] = ((unsigned long long)sh.ct[wl] << 31) | sh.cv[wl];
+    item_act[it] = ((unsigned long long)__popc(sh.emit[wl]) << 31) | (unsigned)__popc(sh.own[wl]);
+    loc_vt += item_vt[it];
+    loc_act += item_act[it];
+  }
+  const unsigned long long inc_vt = warp_incl_scan_u64(loc_vt), inc_act = warp_incl_scan_u64(loc_act);
+  if (lane == 31) {
+    sh.warp_vt[warp] = inc_vt;
+    sh.warp_act[warp] = inc_act;
+  }
+  __syncthreads();
+  unsigned long long woff_vt = 0, woff_act = 0, blk_vt = 0, blk_act = 0;
+#pragma unroll
+  for (int q = 0; q < C4_THREADS / 32; ++q) {
+    if (q < (int)warp) {
+      woff_vt += sh.warp_vt[q];
+      woff_act += sh.warp_act[q];
+    }
+    blk_vt += sh.warp_vt[q];
+    blk_act += sh.warp_act[q];
+  }
+  if (warp == 0) {
+    unsigned long long e = lb_lookback(status_vt, tile, blk_vt);
+    if (lane == 0) sh.excl_vt = e;
+  } else if (warp == 1) {
+    unsigned long long e = lb_lookback(status_act, tile, blk_act);
+    if (lane == 0) sh.excl_act = e;
+  }
+  __syncthreads();
+  unsigned long long run_vt = sh.excl_vt + woff_vt + inc_vt - loc_vt;
+  unsigned long long run_act = sh.excl_act + woff_act + inc_act - loc_act;
+#pragma unroll
+  for (int it = 0; it < C4_ITEMS; ++it) {
+    const unsigned wl = threadIdx.x * C4_ITEMS + it;
+    sh.pv[wl] = (uint32_t)(run_vt & 0x7fffffffull);
+    sh.pt[wl] = (uint32_t)(run_vt >> 31);
+    sh.po[wl] = (uint32_t)(run_act & 0x7fffffffull);
+    sh.pc[wl] = (uint32_t)(run_act >> 31);
+    if (tile0 + wl < nwords) vbase[tile0 + wl] = sh.pv[wl];
+    run_vt += item_vt[it];
+    run_act += item_act[it];
+  }
+  if (tile == ntiles - 1 && threadIdx.x == 0) {
+    ctr->total_vt = sh.excl_vt + blk_vt;
+    ctr->total_act = sh.excl_act + blk_act;
+  }
+  __syncthreads();
+  // ---- D: lists
+  for (unsigned idx = threadIdx.x; idx < nint; idx += C4_THREADS) {
+    const unsigned wl = sh.list[idx];
+    uint32_t mo = sh.own[wl], me = sh.emit[wl];
+    if (!(mo | me)) continue;
+    const unsigned gw = tile0 + wl;
+    int i, j, k, w;
+    g.word_coords(gw, i, j, k, w);
+    g.any_near = g.rowflag[g.row_of(i, j, k)];
+    Planes4 pl;
+    load_planes4(g, g.bits, i, j, k, w, pl);
+    if (mo) {
+      uint32_t x[15];
+      owner_used4(g, pl, i, j, k, w, x);
+      unsigned vrun = sh.pv[wl], orun = sh.po[wl];
+      while (mo) {
+        const int b = __ffs(mo) - 1;
+        mo &= mo - 1;
+        const unsigned m15 = gather15(x, b);
+        if (orun < cap_own) {
+          own_id[orun] = ((unsigned long long)gw << 21) | ((unsigned)b << 16) | (((pl.P[0] >> b) & 1u) << 15) | m15;
+          own_voff[orun] = vrun;
+        }
+        ++orun;
+        vrun += __popc(m15);
+      }
+    }
+    if (me) {
+      unsigned trun = sh.pt[wl], crun = sh.pc[wl];
+      Planes4 npl;
+      if (g.any_near) load_planes4(g, g.nbits, i, j, k, w, npl);
+      while (me) {
+        const int b = __ffs(me) - 1;
+        me &= me - 1;
+        unsigned c16 = 0;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) c16 |= ((corner_plane4(pl, c) >> b) & 1u) << c;
+        unsigned nt = 0;
+        bool cand = false;
+        if (g.any_near) {
+          unsigned n16 = 0;
+          for (int c = 0; c < 16; ++c) n16 |= ((corner_plane4(npl, c) >> b) & 1u) << c;
+          for (int p = 0; p < 24; ++p) {
+            const unsigned m = pent_mask_of(c16, p);
+            cand = cand || (m != 0 && m != 31 && pent_mask_of(n16, p) == 31);
+          }
+        }
+        if (cand) {
+          const unsigned e = cell_emit_exact4(g, i, j, k, w * 32 + b, nullptr);
+          for (int p = 0; p < 24; ++p)
+            if ((e >> p) & 1u) nt += ntet_of_mask(pent_mask_of(c16, p));
+        } else {
+#pragma unroll 1
+          for (int p = 0; p < 24; ++p) nt += ntet_of_mask(pent_mask_of(c16, p));
+        }
+        if (crun < cap_cell) {
+          cell_id[crun] = ((unsigned long long)gw << 22) | ((unsigned)b << 17) | ((cand ? 1u : 0u) << 16) | c16;
+          cell_toff[crun] = trun;
+        }
+        ++crun;
+        trun += nt;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// vertices: one thread per (owner, owned edge) pair, dealt out per warp as in mt3d.cu
+// ------------------------------------------------------------------------------------------------
+struct Xform4 {
+  double origin[4], delta[4];
+};
+__device__ __forceinline__ double mul_rn4(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn4(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn4(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn4(float a, float b) { return __fadd_rn(a, b); }
+
+template <typename T, typename G>
+__global__ void __launch_bounds__(256) k4_emit_verts(Grid4<T> g, const unsigned long long* __restrict__ own_id,
+                                                     const uint32_t* __restrict__ own_voff, unsigned n_own, Xform4 xf,
+                                                     G* __restrict__ verts, unsigned long long* __restrict__ keys,
+                                                     uint8_t* __restrict__ lowmin) {
+  const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_own) return;
+  const unsigned long long oid = own_id[a];
+  unsigned id = own_voff[a];
+  const unsigned m15 = (unsigned)oid & 0x7fffu;
+  const bool p_low = (oid >> 15) & 1u;
+  int i, j, k, w;
+  g.word_coords((unsigned)(oid >> 21), i, j, k, w);
+  const int l = w * 32 + (int)((oid >> 16) & 31u);
+  const G fp = (G)g.f[g.row_of(i, j, k) * g.n3 + l];
+  const G v = (G)g.v;
+  const unsigned long long lin = (unsigned long long)(g.row_of(i, j, k) * g.n3 + l);
+#pragma unroll 1
+  for (int d = 1; d <= 15; ++d) {
+    if (!((m15 >> (d - 1)) & 1u)) continue;
+    const int dd[4] = {(d >> 3) & 1, (d >> 2) & 1, (d >> 1) & 1, d & 1};
+    const G fq = (G)g.f[g.row_of(i + dd[0], j + dd[1], k + dd[2]) * g.n3 + l + dd[3]];
+    const G flow = p_low ? fp : fq, fhigh = p_low ? fq : fp;
+    const G den = fhigh - flow;
+    const G ratio = (fabs((double)den) <= 1e-8) ? (G)0.5 : (v - flow) / den;
+    const G step = p_low ? ratio : -ratio;
+    const int p0[4] = {i, j, k, l};
+#pragma unroll
+    for (int ax = 0; ax < 4; ++ax) {
+      const G b0 = (G)(p_low ? p0[ax] : p0[ax] + dd[ax]);
+      const G x = dd[ax] ? add_rn4(b0, step) : b0;
+      verts[(size_t)id * 4 + ax] = add_rn4(mul_rn4(x, (G)xf.delta[ax]), (G)xf.origin[ax]);
+    }
+    if (keys) {
+      keys[id] = (lin << 4) | (unsigned)d;
+      lowmin[id] = p_low ? 1 : 0;
+    }
+    ++id;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tetrahedra: one thread per hypervoxel
+// ------------------------------------------------------------------------------------------------
+constexpr int E4_THREADS = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(E4_THREADS) k4_emit_tets(Grid4<T> gin, const unsigned long long* __restrict__ cell_id,
+                                                           const uint32_t* __restrict__ cell_toff, unsigned n_cells,
+                                                           const uint32_t* __restrict__ vbase, int* __restrict__ tets,
+                                                           uint8_t* __restrict__ codes) {
+  __shared__ unsigned s_ids[CTR_NEDGE4][E4_THREADS];
+  Grid4<T> g = gin;
+  const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_cells) return;
+  const unsigned long long cid = cell_id[a];
+  const unsigned c16 = (unsigned)cid & 0xffffu;
+  const bool cand = (cid >> 16) & 1u;
+  const int b = (int)((cid >> 17) & 31u);
+  int i, j, k, w;
+  g.word_coords((unsigned)(cid >> 22), i, j, k, w);
+  g.any_near = g.rowflag[g.row_of(i, j, k)];
+  // owner (first vertex id, mask15) for the 16 corners: owner rows abc (8) x {l, l+1}
+  unsigned idb[16], msk[16];
+  const uint32_t below = (1u << b) - 1u;
+#pragma unroll 1
+  for (int abc = 0; abc < 8; ++abc) {
+    const int ii = i + (abc >> 2), jj = j + ((abc >> 1) & 1), kk = k + (abc & 1);
+    Planes4 pl;
+    load_planes4(g, g.bits, ii, jj, kk, w, pl);
+    uint32_t u[15];
+    owner_used4(g, pl, ii, jj, kk, w, u);
+    const size_t wi = g.row_of(ii, jj, kk) * g.W + w;
+    unsigned rank = 0;
+#pragma unroll
+    for (int d = 0; d < 15; ++d) rank += __popc(u[d] & below);
+    const unsigned m0 = gather15(u, b);
+    const unsigned id0 = vbase[wi] + rank;
+    unsigned m1, id1;
+    if (b < 31) {
+      m1 = gather15(u, b + 1);
+      id1 = id0 + __popc(m0);
+    } else {
+      Planes4 pn;
+      load_planes4(g, g.bits, ii, jj, kk, w + 1, pn);
+      uint32_t un[15];
+      owner_used4(g, pn, ii, jj, kk, w + 1, un);
+      m1 = gather15(un, 0);
+      id1 = vbase[wi + 1];
+    }
+    idb[abc * 2 + 0] = id0;
+    msk[abc * 2 + 0] = m0;
+    idb[abc * 2 + 1] = id1;
+    msk[abc * 2 + 1] = m1;
+  }
+#pragma unroll
+  for (int e = 0; e < CTR_NEDGE4; ++e) {
+    const int s = c4_edge_s[e], d = c4_edge_d[e];
+    s_ids[e][threadIdx.x] = idb[s] + __popc(msk[s] & ((1u << (d - 1)) - 1u));
+  }
+  unsigned emit = 0xffffffu;
+  if (cand) emit = cell_emit_exact4(g, i, j, k, w * 32 + b, nullptr);
+  if (codes) cell_emit_exact4(g, i, j, k, w * 32 + b, codes + (size_t)a * 24);
+  size_t o = cell_toff[a];
+#pragma unroll 1
+  for (int p = 0; p < 24; ++p) {
+    const unsigned m = pent_mask_of(c16, p);
+    if (m == 0 || m == 31 || !((emit >> p) & 1u)) continue;
+    const int n = d4_tet_n[p][m];
+    for (int q = 0; q < n; ++q) {
+      int* dst = tets + o * 4;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) dst[r] = (int)s_ids[d4_tet_e[p][m][q * 4 + r]][threadIdx.x];
+      ++o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// morph stage (grid coordinates, fp64): pentatopes.py:162-189, tetrahedral.py:353-375, morph_geometry.py:145-237
+// ------------------------------------------------------------------------------------------------
+__global__ void k4_bin(double* __restrict__ verts, unsigned nv, double min_interval) {
+  const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nv) return;
+  const double t = verts[(size_t)a * 4 + 3];
+  verts[(size_t)a * 4 + 3] = __dmul_rn(trunc(t / min_interval), min_interval);      // pentatopes.py:168-169
+}
+
+struct MorphParams {
+  double inv_corner[4];
+  double eps_instant, eps_tiny, eps_gap, eps_in, t_eps;
+};
+
+// keep[t] = 1 unless the tet is instantaneous (t extent < eps_instant) or tiny (every extent/corner < eps_tiny)
+__global__ void k4_tet_filter(const double* __restrict__ verts, const int* __restrict__ tets, unsigned nt, MorphParams mp,
+                              uint8_t* __restrict__ keep) {
+  const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nt) return;
+  double mn[4], mx[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const double* p = verts + (size_t)tets[(size_t)a * 4 + r] * 4;
+#pragma unroll
+    for (int ax = 0; ax < 4; ++ax) {
+      const double x = p[ax];
+      mn[ax] = r == 0 ? x : fmin(mn[ax], x);
+      mx[ax] = r == 0 ? x : fmax(mx[ax], x);
+    }
+  }
+  const bool instant = (mx[3] - mn[3]) < mp.eps_instant;
+  double ext = 0;
+#pragma unroll
+  for (int ax = 0; ax < 4; ++ax) ext = fmax(ext, __dmul_rn(mx[ax] - mn[ax], mp.inv_corner[ax]));
+  const bool tiny = ext < mp.eps_tiny;
+  keep[a] = (instant || tiny) ? 0 : 1;
+}
+
+// slices of one tetrahedron: returns the number of morph triangles; if out != nullptr writes them as
+// 3 segments x (low id, high id) with the deterministic 4-edge split (first edge in (ab,ac,ad,bc,bd,cd) order
+// of the id-sorted vertices + the edge disjoint from it are the shared pair).
+__device__ __forceinline__ int slice_tet(const double* __restrict__ verts, const int* __restrict__ tet, const MorphParams& mp,
+                                         int* __restrict__ out) {
+  int v[4] = {tet[0], tet[1], tet[2], tet[3]};
+#pragma unroll
+  for (int x = 0; x < 3; ++x)
+#pragma unroll
+    for (int y = 0; y < 3 - x; ++y)
+      if (v[y] > v[y + 1]) {
+        const int tmp = v[y];
+        v[y] = v[y + 1];
+        v[y + 1] = tmp;
+      }
+  if (v[0] == v[1] || v[1] == v[2] || v[2] == v[3]) return 0;
+  double tv[4], ts[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) ts[r] = tv[r] = verts[(size_t)v[r] * 4 + 3];
+#pragma unroll
+  for (int x = 0; x < 3; ++x)
+#pragma unroll
+    for (int y = 0; y < 3 - x; ++y)
+      if (ts[y] > ts[y + 1]) {
+        const double tmp = ts[y];
+        ts[y] = ts[y + 1];
+        ts[y + 1] = tmp;
+      }
+  const int ea[6] = {0, 0, 0, 1, 1, 2}, eb[6] = {1, 2, 3, 2, 3, 3};
+  int n = 0;
+#pragma unroll 1
+  for (int gap = 0; gap < 3; ++gap) {
+    if (!((ts[gap + 1] - ts[gap]) > mp.eps_gap)) continue;
+    const double mid = 0.5 * (ts[gap + 1] + ts[gap]);
+    int inter[6], ni = 0;
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      double v1 = tv[ea[e]], v2 = tv[eb[e]];
+      if (v1 > v2) {
+        const double tmp = v1;
+        v1 = v2;
+        v2 = tmp;
+      }
+      if (mid + mp.eps_in < v1 || mid - mp.eps_in > v2) continue;     // morph_geometry.py:218
+      inter[ni++] = e;
+    }
+    int ntri = 0, tri[2][3];
+    if (ni == 3) {
+      tri[0][0] = inter[0]; tri[0][1] = inter[1]; tri[0][2] = inter[2];
+      ntri = 1;
+    } else if (ni == 4) {                                            // morph_geometry.py:176-186
+      const int p1 = inter[0];
+      int p2 = -1;
+      for (int q = 1; q < 4; ++q) {
+        const int e = inter[q];
+        if (ea[e] != ea[p1] && ea[e] != eb[p1] && eb[e] != ea[p1] && eb[e] != eb[p1]) p2 = e;
+      }
+      if (p2 >= 0) {
+        for (int q = 1; q < 4; ++q)
+          if (inter[q] != p2) {
+            tri[ntri][0] = p1; tri[ntri][1] = p2; tri[ntri][2] = inter[q];
+            ++ntri;
+          }
+      }
+    }
+    for (int q = 0; q < ntri; ++q) {
+      bool kill = false;                                             // pentatopes.py:339-348
+      for (int r = 0; r < 3; ++r) {
+        const int e = tri[q][r];
+        if (fabs(tv[ea[e]] - tv[eb[e]]) <= mp.t_eps) kill = true;
+      }
+      if (kill) continue;
+      if (out) {
+        for (int r = 0; r < 3; ++r) {
+          const int e = tri[q][r];
+          const int i0 = v[ea[e]], i1 = v[eb[e]];
+          const bool swap = tv[ea[e]] > tv[eb[e]];           // morph_geometry.py:13-17: low t first
+          out[(size_t)n * 6 + r * 2 + 0] = swap ? i1 : i0;
+          out[(size_t)n * 6 + r * 2 + 1] = swap ? i0 : i1;
+        }
+      }
+      ++n;
+    }
+  }
+  return n;
+}
+
+constexpr int SL_THREADS = 256;
+struct SlCounters {
+  unsigned long long total;
+  unsigned int ticket, pad;
+};
+
+__global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict__ verts, const int* __restrict__ tets,
+                                                       const uint8_t* __restrict__ keep, unsigned nt, MorphParams mp,
+                                                       unsigned long long* status, SlCounters* ctr, int ntiles,
+                                                       int* __restrict__ out, unsigned cap) {
+  __shared__ unsigned s_tile;
+  __shared__ unsigned long long s_warp[SL_THREADS / 32], s_excl;
+  if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket, 1u);
+  __syncthreads();
+  const int tile = (int)s_tile;
+  const unsigned a = (unsigned)tile * SL_THREADS + threadIdx.x;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  int n = 0;
+  if (a < nt && keep[a]) n = slice_tet(verts, tets + (size_t)a * 4, mp, nullptr);
+  const unsigned long long inc = warp_incl_scan_u64((unsigned long long)n);
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  unsigned long long woff = 0, blk = 0;
+#pragma unroll
+  for (int q = 0; q < SL_THREADS / 32; ++q) {
+    if (q < (int)warp) woff += s_warp[q];
+    blk += s_warp[q];
+  }
+  if (warp == 0) {
+    unsigned long long e = lb_lookback(status, tile, blk);
+    if (lane == 0) s_excl = e;
+  }
+  __syncthreads();
+  const unsigned long long off = s_excl + woff + inc - (unsigned long long)n;
+  if (n && off + n <= cap) slice_tet(verts, tets + (size_t)a * 4, mp, out + off * 6);
+  if (tile == ntiles - 1 && threadIdx.x == 0) ctr->total = s_excl + blk;
+}
+
+__global__ void k4_trange(const double* __restrict__ verts, unsigned nv, MinMaxKeys* mm) {
+  double mn = INFINITY, mx = -INFINITY;
+  for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < nv; a += gridDim.x * blockDim.x) {
+    const double t = verts[(size_t)a * 4 + 3];
+    mn = fmin(mn, t);
+    mx = fmax(mx, t);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane_id() == 0 && mn <= mx) {
+    atomicMin(&mm->min_key, order_key(mn));
+    atomicMax(&mm->max_key, order_key(mx));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+bool g4_tables_loaded[64] = {};
+
+int load_tables4(ctr_ctx* ctx) {
+  if (ctx->device < 64 && g4_tables_loaded[ctx->device]) return 0;
+  CTR_CUDA(ctx, cudaMemcpyToSymbol(c4_pent, CTR_PENT4_H, sizeof(CTR_PENT4_H)));
+  CTR_CUDA(ctx, cudaMemcpyToSymbol(c4_edge_s, CTR_EDGE4_S_H, sizeof(CTR_EDGE4_S_H)));
+  CTR_CUDA(ctx, cudaMemcpyToSymbol(c4_edge_d, CTR_EDGE4_D_H, sizeof(CTR_EDGE4_D_H)));
+  CTR_CUDA(ctx, cudaMemcpyToSymbol(c4_pentmask, CTR_PENTMASK4_H, sizeof(CTR_PENTMASK4_H)));
+  CTR_CUDA(ctx, cudaMemcpyToSymbol(d4_tet_n, CTR_TET4_N_H, sizeof(CTR_TET4_N_H)));
+  CTR_CUDA(ctx, cudaMemcpyToSymbol(d4_tet_e, CTR_TET4_E_H, sizeof(CTR_TET4_E_H)));
+  if (ctx->device < 64) g4_tables_loaded[ctx->device] = true;
+  return 0;
+}
+
+// buffers of the 4D path: generic slots 12.. of the context
+struct Bufs4 {
+  DevBuf &own_id, &own_voff, &cell_id, &cell_toff, &rowflag, &verts, &keys, &lowmin, &tets, &codes, &keep, &mverts, &mtris,
+      &slstate;
+  explicit Bufs4(ctr_ctx* c)
+      : own_id(c->aux[12]), own_voff(c->aux[13]), cell_id(c->aux[14]), cell_toff(c->aux[15]), rowflag(c->aux[16]),
+        verts(c->aux[17]), keys(c->aux[18]), lowmin(c->aux[19]), tets(c->aux[20]), codes(c->aux[21]), keep(c->aux[22]),
+        mverts(c->aux[23]), mtris(c->aux[24]), slstate(c->aux[25]) {}
+};
+
+template <typename T>
+int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
+  const int n0 = (int)p->n0, n1 = (int)p->n1, n2 = (int)p->n2, n3 = (int)p->n3;
+  const int W = (n3 + 31) / 32;
+  const long long nrows = (long long)n0 * n1 * n2;
+  const long long nwords = nrows * W;
+  const size_t nsamp = (size_t)nrows * n3;
+  cudaStream_t st = ctx->stream;
+  if (nwords >= (1ll << 31) - 64) return ctr_fail(ctx, CTR_ERR_UNSUPPORTED, "4D field too large for 32-bit word indices");
+  Bufs4 B(ctx);
+  int rc;
+  if ((rc = load_tables4(ctx))) return rc;
+  ctr_stage_mark(ctx, 0);
+  const T* df;
+  if (p->flags & CTR_FIELD_ON_DEVICE) {
+    df = (const T*)p->field;
+  } else {
+    if ((rc = ctr_ensure(ctx, ctx->field, nsamp * sizeof(T)))) return rc;
+    CTR_CUDA(ctx, cudaMemcpyAsync(ctx->field.p, p->field, nsamp * sizeof(T), cudaMemcpyHostToDevice, st));
+    df = (const T*)ctx->field.p;
+  }
+  ctr_stage_mark(ctx, 1);
+  if ((rc = ctr_ensure(ctx, ctx->bits, (size_t)(nwords + 4) * 4))) return rc;
+  if ((rc = ctr_ensure(ctx, ctx->nbits, (size_t)(nwords + 4) * 4))) return rc;
+  if ((rc = ctr_ensure(ctx, ctx->vbase, (size_t)(nwords + 4) * 4))) return rc;
+  if ((rc = ctr_ensure(ctx, ctx->counters, 256))) return rc;
+  if ((rc = ctr_ensure(ctx, B.rowflag, (size_t)nrows + 16))) return rc;
+  if (!ctx->counters_host) CTR_CUDA(ctx, cudaMallocHost(&ctx->counters_host, 256));
+  Counters4 init;
+  memset(&init, 0, sizeof init);
+  init.min_key = ~0ull;
+  memcpy(ctx->counters_host, &init, sizeof init);
+  CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters.p, ctx->counters_host, sizeof init, cudaMemcpyHostToDevice, st));
+  Counters4* dctr = (Counters4*)ctx->counters.p;
+  if (p->flags & CTR_WANT_MINMAX)
+    rc = launch_bitplane<T, true>(ctx, df, (unsigned)nrows, n3, W, n1, n2, p->isovalue, (uint32_t*)ctx->bits.p,
+                                  (uint32_t*)ctx->nbits.p, (uint8_t*)B.rowflag.p, (MinMaxKeys*)dctr);
+  else
+    rc = launch_bitplane<T, false>(ctx, df, (unsigned)nrows, n3, W, n1, n2, p->isovalue, (uint32_t*)ctx->bits.p,
+                                   (uint32_t*)ctx->nbits.p, (uint8_t*)B.rowflag.p, (MinMaxKeys*)dctr);
+  if (rc) return rc;
+  ctr_stage_mark(ctx, 2);
+  Grid4<T> g;
+  g.f = df;
+  g.bits = (const uint32_t*)ctx->bits.p;
+  g.nbits = (const uint32_t*)ctx->nbits.p;
+  g.rowflag = (const uint8_t*)B.rowflag.p;
+  g.n0 = n0; g.n1 = n1; g.n2 = n2; g.n3 = n3; g.W = W;
+  g.v = p->isovalue;
+  g.tolv = 1e-8 + 1e-5 * fabs(p->isovalue);
+  g.any_near = 0;
+  g.divW.init((unsigned)W);
+  g.divN2.init((unsigned)n2);
+  g.divN1.init((unsigned)n1);
+  const int ntiles = (int)((nwords + C4_TILE - 1) / C4_TILE);
+  if ((rc = ctr_ensure(ctx, ctx->tile_state, (size_t)ntiles * 16 + 16))) return rc;
+  unsigned long long* st_vt = (unsigned long long*)ctx->tile_state.p;
+  unsigned long long* st_act = st_vt + ntiles;
+  size_t want_own = std::max<size_t>((size_t)nwords / 2, 1 << 14), want_cell = want_own;
+  Counters4 h;
+  unsigned long long totV = 0, totT = 0, nOwn = 0, nCell = 0;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    if ((rc = ctr_ensure(ctx, B.own_id, want_own * 8))) return rc;
+    if ((rc = ctr_ensure(ctx, B.own_voff, want_own * 4))) return rc;
+    if ((rc = ctr_ensure(ctx, B.cell_id, want_cell * 8))) return rc;
+    if ((rc = ctr_ensure(ctx, B.cell_toff, want_cell * 4))) return rc;
+    const unsigned cap_own = (unsigned)std::min<size_t>(std::min(B.own_id.cap / 8, B.own_voff.cap / 4), 0x7fffffffu);
+    const unsigned cap_cell = (unsigned)std::min<size_t>(std::min(B.cell_id.cap / 8, B.cell_toff.cap / 4), 0x7fffffffu);
+    CTR_CUDA(ctx, cudaMemsetAsync((char*)dctr + C4_STAGE2_OFFSET, 0, sizeof(Counters4) - C4_STAGE2_OFFSET, st));
+    CTR_CUDA(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, (size_t)ntiles * 16, st));
+    k4_count_scan<T><<<ntiles, C4_THREADS, 0, st>>>(g, (unsigned)nwords, (uint32_t*)ctx->vbase.p,
+                                                    (unsigned long long*)B.own_id.p, (uint32_t*)B.own_voff.p,
+                                                    (unsigned long long*)B.cell_id.p, (uint32_t*)B.cell_toff.p, cap_own,
+                                                    cap_cell, st_vt, st_act, dctr, ntiles);
+    ctx->launches++;
+    CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, dctr, sizeof(Counters4), cudaMemcpyDeviceToHost, st));
+    CTR_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(&h, ctx->counters_host, sizeof h);
+    totV = h.total_vt & 0x7fffffffull;
+    totT = h.total_vt >> 31;
+    nOwn = h.total_act & 0x7fffffffull;
+    nCell = h.total_act >> 31;
+    if (nOwn <= cap_own && nCell <= cap_cell) break;
+    if (attempt == 2) return ctr_fail(ctx, CTR_ERR_STATE, "list capacity did not converge");
+    want_own = std::max<size_t>(nOwn, want_own);
+    want_cell = std::max<size_t>(nCell, want_cell);
+  }
+  ctr_stage_mark(ctx, 3);
+  if (totV >= 0x7ffffff0ull || totT >= 0x7ffffff0ull)
+    return ctr_fail(ctx, CTR_ERR_OVERFLOW, "more than 2^31 vertices or tetrahedra in one call; shard the field");
+  out->n_verts = (int64_t)totV;
+  out->n_tets = (int64_t)totT;
+  out->n_active_cells = (int64_t)h.n_cells;
+  out->n_crossings = (int64_t)h.n_cross;
+  out->n_morph_tris = 0;
+  const bool mm = (p->flags & CTR_WANT_MINMAX) && h.min_key != ~0ull;
+  out->fmin = mm ? key_to_double(h.min_key) : NAN;
+  out->fmax = mm ? key_to_double(h.max_key) : NAN;
+  out->t_min = out->t_max = NAN;
+  const bool f64 = (p->flags & CTR_GEOM_F64) != 0;
+  const size_t gsz = f64 ? 8 : 4;
+  if (!(p->flags & CTR_NO_GEOMETRY)) {
+    if ((rc = ctr_ensure(ctx, B.verts, (size_t)totV * 4 * gsz + 16))) return rc;
+    if ((rc = ctr_ensure(ctx, B.tets, (size_t)totT * 16 + 16))) return rc;
+    if (p->flags & CTR_WANT_KEYS) {
+      if ((rc = ctr_ensure(ctx, B.keys, (size_t)totV * 8 + 16))) return rc;
+      if ((rc = ctr_ensure(ctx, B.lowmin, (size_t)totV + 16))) return rc;
+    }
+    if (p->flags & CTR_WANT_CODES)
+      if ((rc = ctr_ensure(ctx, B.codes, (size_t)nCell * 24 + 16))) return rc;
+    Xform4 xf;
+    for (int a = 0; a < 4; ++a) {
+      xf.origin[a] = p->origin[a];
+      xf.delta[a] = p->delta[a];
+    }
+    unsigned long long* dkeys = (p->flags & CTR_WANT_KEYS) ? (unsigned long long*)B.keys.p : nullptr;
+    uint8_t* dlow = (p->flags & CTR_WANT_KEYS) ? (uint8_t*)B.lowmin.p : nullptr;
+    if (nOwn) {
+      const int blocks = (int)((nOwn + 255) / 256);
+      if (f64)
+        k4_emit_verts<T, double><<<blocks, 256, 0, st>>>(g, (const unsigned long long*)B.own_id.p, (const uint32_t*)B.own_voff.p,
+                                                         (unsigned)nOwn, xf, (double*)B.verts.p, dkeys, dlow);
+      else
+        k4_emit_verts<T, float><<<blocks, 256, 0, st>>>(g, (const unsigned long long*)B.own_id.p, (const uint32_t*)B.own_voff.p,
+                                                        (unsigned)nOwn, xf, (float*)B.verts.p, dkeys, dlow);
+      ctx->launches++;
+    }
+    ctr_stage_mark(ctx, 4);
+    if (nCell) {
+      const int blocks = (int)((nCell + E4_THREADS - 1) / E4_THREADS);
+      k4_emit_tets<T><<<blocks, E4_THREADS, 0, st>>>(g, (const unsigned long long*)B.cell_id.p, (const uint32_t*)B.cell_toff.p,
+                                                     (unsigned)nCell, (const uint32_t*)ctx->vbase.p, (int*)B.tets.p,
+                                                     (p->flags & CTR_WANT_CODES) ? (uint8_t*)B.codes.p : nullptr);
+      ctx->launches++;
+    }
+    ctr_stage_mark(ctx, 5);
+    // ---- morph stage: always in grid coordinates and fp64 (its thresholds are defined there)
+    if ((p->flags & CTR_MORPH) && totV && totT) {
+      if ((rc = ctr_ensure(ctx, B.mverts, (size_t)totV * 32 + 16))) return rc;
+      if ((rc = ctr_ensure(ctx, B.keep, (size_t)totT + 16))) return rc;
+      Xform4 unit;
+      for (int a = 0; a < 4; ++a) {
+        unit.origin[a] = 0.0;
+        unit.delta[a] = 1.0;
+      }
+      k4_emit_verts<T, double><<<(int)((nOwn + 255) / 256), 256, 0, st>>>(g, (const unsigned long long*)B.own_id.p,
+                                                                          (const uint32_t*)B.own_voff.p, (unsigned)nOwn, unit,
+                                                                          (double*)B.mverts.p, nullptr, nullptr);
+      const double corner_t = (double)(n3 - 1);
+      k4_bin<<<(int)((totV + 255) / 256), 256, 0, st>>>((double*)B.mverts.p, (unsigned)totV, corner_t * (1.0 / p->nbins));
+      // t range of the binned vertices (for the zero-duration threshold, pentatopes.py:336-337)
+      MinMaxKeys mk;
+      mk.min_key = ~0ull;
+      mk.max_key = 0ull;
+      memcpy(ctx->counters_host, &mk, sizeof mk);
+      CTR_CUDA(ctx, cudaMemcpyAsync(dctr, ctx->counters_host, sizeof mk, cudaMemcpyHostToDevice, st));
+      k4_trange<<<ctx->sm_count * 4, 256, 0, st>>>((const double*)B.mverts.p, (unsigned)totV, (MinMaxKeys*)dctr);
+      CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, dctr, sizeof mk, cudaMemcpyDeviceToHost, st));
+      CTR_CUDA(ctx, cudaStreamSynchronize(st));
+      memcpy(&mk, ctx->counters_host, sizeof mk);
+      const double tmin = key_to_double(mk.min_key), tmax = key_to_double(mk.max_key);
+      out->t_min = tmin;
+      out->t_max = tmax;
+      MorphParams mp;
+      const int nn[4] = {n0, n1, n2, n3};
+      for (int a = 0; a < 4; ++a) mp.inv_corner[a] = 1.0 / (double)(nn[a] - 1);
+      mp.eps_instant = 1e-7;
+      mp.eps_tiny = 1e-3;
+      mp.eps_gap = 1e-4;
+      mp.eps_in = 1e-5;
+      mp.t_eps = 1e-7 * (tmax - tmin);
+      k4_tet_filter<<<(int)((totT + 255) / 256), 256, 0, st>>>((const double*)B.mverts.p, (const int*)B.tets.p, (unsigned)totT,
+                                                               mp, (uint8_t*)B.keep.p);
+      ctx->launches += 4;
+      const int sl_tiles = (int)((totT + SL_THREADS - 1) / SL_THREADS);
+      if ((rc = ctr_ensure(ctx, B.slstate, (size_t)sl_tiles * 8 + 64))) return rc;
+      size_t want = std::max<size_t>((size_t)totT * 2, 1 << 14);
+      unsigned long long nmt = 0;
+      for (int attempt = 0; attempt < 3; ++attempt) {
+        if ((rc = ctr_ensure(ctx, B.mtris, want * 24))) return rc;
+        const unsigned cap = (unsigned)std::min<size_t>(B.mtris.cap / 24, 0x7fffffffu);
+        SlCounters* slc = (SlCounters*)((char*)B.slstate.p + (size_t)sl_tiles * 8);
+        CTR_CUDA(ctx, cudaMemsetAsync(B.slstate.p, 0, (size_t)sl_tiles * 8 + 32, st));
+        k4_slice<<<sl_tiles, SL_THREADS, 0, st>>>((const double*)B.mverts.p, (const int*)B.tets.p, (const uint8_t*)B.keep.p,
+                                                  (unsigned)totT, mp, (unsigned long long*)B.slstate.p, slc, sl_tiles,
+                                                  (int*)B.mtris.p, cap);
+        ctx->launches++;
+        CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, slc, sizeof(SlCounters), cudaMemcpyDeviceToHost, st));
+        CTR_CUDA(ctx, cudaStreamSynchronize(st));
+        SlCounters hs;
+        memcpy(&hs, ctx->counters_host, sizeof hs);
+        nmt = hs.total;
+        if (nmt <= cap) break;
+        if (attempt == 2) return ctr_fail(ctx, CTR_ERR_STATE, "morph triangle capacity did not converge");
+        want = nmt;
+      }
+      out->n_morph_tris = (int64_t)nmt;
+    }
+    ctr_stage_mark(ctx, 6);
+  }
+  CTR_CUDA(ctx, cudaGetLastError());
+  CTR_CUDA(ctx, cudaStreamSynchronize(st));
+  if (ctx->timing) {
+    for (int s = 0; s < 6; ++s) {
+      ctx->stage_ms[s] = 0.f;
+      if (ctx->ev_set[s] && ctx->ev_set[s + 1]) cudaEventElapsedTime(&ctx->stage_ms[s], ctx->ev[s], ctx->ev[s + 1]);
+    }
+  }
+  ctx->last_kind = 4;
+  ctx->last_flags = p->flags;
+  ctx->last_counts[0] = (int64_t)totV;
+  ctx->last_counts[1] = (int64_t)totT;
+  ctx->last_counts[2] = (p->flags & CTR_WANT_CODES) ? (int64_t)nCell : 0;
+  ctx->last_counts[3] = out->n_morph_tris;
+  out->n_codes = ctx->last_counts[2];
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int ctr_mp4d_run(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
+  if (!ctx) return CTR_ERR_BAD_ARG;
+  if (!p || !out || !p->field) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "null argument");
+  if (p->n0 < 2 || p->n1 < 2 || p->n2 < 2 || p->n3 < 2) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "grid must have at least 2 samples per axis");
+  if (!(p->isovalue == p->isovalue)) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "isovalue is NaN");
+  if ((p->flags & CTR_MORPH) && p->nbins < 1) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "nbins must be >= 1");
+  for (int a = 0; a < 4; ++a)
+    if (p->delta[a] == 0.0) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "delta must be non-zero");
+  CTR_CUDA(ctx, cudaSetDevice(ctx->device));
+  memset(out, 0, sizeof *out);
+  ctx->last_kind = 0;
+  if (p->dtype == CTR_F32) return run4d<float>(ctx, p, out);
+  if (p->dtype == CTR_F64) return run4d<double>(ctx, p, out);
+  return ctr_fail(ctx, CTR_ERR_BAD_ARG, "dtype must be CTR_F32 or CTR_F64");
+}
+
+extern "C" int ctr_mp4d_fetch(ctr_ctx* ctx, void* verts, int32_t* tets, uint64_t* keys, uint8_t* lowmin, uint8_t* codes,
+                              int64_t* cells, double* morph_verts, uint8_t* keep, int32_t* morph_tris) {
+  if (!ctx) return CTR_ERR_BAD_ARG;
+  if (ctx->last_kind != 4) return ctr_fail(ctx, CTR_ERR_STATE, "no completed ctr_mp4d_run to fetch from");
+  if (ctx->last_flags & CTR_NO_GEOMETRY) return ctr_fail(ctx, CTR_ERR_STATE, "run had CTR_NO_GEOMETRY");
+  CTR_CUDA(ctx, cudaSetDevice(ctx->device));
+  Bufs4 B(ctx);
+  const uint32_t fl = ctx->last_flags;
+  const size_t gsz = (fl & CTR_GEOM_F64) ? 8 : 4;
+  const size_t nV = (size_t)ctx->last_counts[0], nT = (size_t)ctx->last_counts[1], nC = (size_t)ctx->last_counts[2],
+               nM = (size_t)ctx->last_counts[3];
+  cudaStream_t st = ctx->stream;
+  if (verts && nV) CTR_CUDA(ctx, cudaMemcpyAsync(verts, B.verts.p, nV * 4 * gsz, cudaMemcpyDeviceToHost, st));
+  if (tets && nT) CTR_CUDA(ctx, cudaMemcpyAsync(tets, B.tets.p, nT * 16, cudaMemcpyDeviceToHost, st));
+  if (keys || lowmin) {
+    if (!(fl & CTR_WANT_KEYS)) return ctr_fail(ctx, CTR_ERR_STATE, "run did not compute keys");
+    if (keys && nV) CTR_CUDA(ctx, cudaMemcpyAsync(keys, B.keys.p, nV * 8, cudaMemcpyDeviceToHost, st));
+    if (lowmin && nV) CTR_CUDA(ctx, cudaMemcpyAsync(lowmin, B.lowmin.p, nV, cudaMemcpyDeviceToHost, st));
+  }
+  if (codes || cells) {
+    if (!(fl & CTR_WANT_CODES)) return ctr_fail(ctx, CTR_ERR_STATE, "run did not compute case codes");
+    if (codes && nC) CTR_CUDA(ctx, cudaMemcpyAsync(codes, B.codes.p, nC * 24, cudaMemcpyDeviceToHost, st));
+    if (cells && nC) CTR_CUDA(ctx, cudaMemcpyAsync(cells, B.cell_id.p, nC * 8, cudaMemcpyDeviceToHost, st));
+  }
+  if (morph_verts || keep || morph_tris) {
+    if (!(fl & CTR_MORPH)) return ctr_fail(ctx, CTR_ERR_STATE, "run did not include the morph stage");
+    if (morph_verts && nV) CTR_CUDA(ctx, cudaMemcpyAsync(morph_verts, B.mverts.p, nV * 32, cudaMemcpyDeviceToHost, st));
+    if (keep && nT) CTR_CUDA(ctx, cudaMemcpyAsync(keep, B.keep.p, nT, cudaMemcpyDeviceToHost, st));
+    if (morph_tris && nM) CTR_CUDA(ctx, cudaMemcpyAsync(morph_tris, B.mtris.p, nM * 24, cudaMemcpyDeviceToHost, st));
+  }
+  CTR_CUDA(ctx, cudaStreamSynchronize(st));
+  return 0;
+}

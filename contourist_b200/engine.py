@@ -19,6 +19,7 @@ WANT_KEYS = 8
 WANT_CODES = 16
 NO_GEOMETRY = 32
 WANT_MINMAX = 64
+MORPH = 128
 
 
 class EngineError(RuntimeError):
@@ -238,6 +239,73 @@ class Engine(object):
         pos = np.empty((S, 2, 2), dtype=gd)
         self._check(self.lib.ctr_mt2d_fetch(self.h, _ptr(lvl), _ptr(keys), _ptr(pos)), "ctr_mt2d_fetch")
         return dict(level=lvl, keys=keys, pos=pos)
+
+    # ------------------------------------------------------------------ 4D
+    def mp4d_run(self, field, value, origin=(0.0,) * 4, delta=(1.0,) * 4, flags=0, nbins=100, shape=None, dtype=None):
+        """field: numpy [n0,n1,n2,n3] float32/float64 (last axis = time) or device pointer (+shape, dtype)."""
+        from ._bindings import Mp4dParams, Mp4dCounts
+        p = Mp4dParams()
+        if isinstance(field, np.ndarray):
+            if field.dtype not in (np.float32, np.float64):
+                field = field.astype(np.float64)
+            field = np.ascontiguousarray(field)
+            if field.ndim != 4:
+                raise ValueError("4D field expected")
+            self._keep = field
+            p.field = field.ctypes.data
+            p.dtype = F32 if field.dtype == np.float32 else F64
+            shape = field.shape
+            flags &= ~FIELD_ON_DEVICE
+        else:
+            p.field = int(field)
+            p.dtype = F32 if np.dtype(dtype) == np.float32 else F64
+            flags |= FIELD_ON_DEVICE
+        p.flags = flags
+        p.n0, p.n1, p.n2, p.n3 = (int(s) for s in shape)
+        p.isovalue = float(value)
+        for a in range(4):
+            p.origin[a] = float(origin[a])
+            p.delta[a] = float(delta[a])
+        p.nbins = int(nbins)
+        c = Mp4dCounts()
+        self._check(self.lib.ctr_mp4d_run(self.h, ctypes.byref(p), ctypes.byref(c)), "ctr_mp4d_run")
+        self._last4 = (flags, c, tuple(int(s) for s in shape))
+        return c
+
+    def mp4d_fetch(self, verts=True, tets=True, morph=None):
+        flags, c, shape = self._last4
+        gd = np.float64 if flags & GEOM_F64 else np.float32
+        V, T, C, M = int(c.n_verts), int(c.n_tets), int(c.n_codes), int(c.n_morph_tris)
+        keys = bool(flags & WANT_KEYS)
+        codes = bool(flags & WANT_CODES)
+        if morph is None:
+            morph = bool(flags & MORPH)
+        a_v = np.empty((V, 4), dtype=gd) if verts else None
+        a_t = np.empty((T, 4), dtype=np.int32) if tets else None
+        a_k = np.empty((V,), dtype=np.uint64) if keys else None
+        a_l = np.empty((V,), dtype=np.uint8) if keys else None
+        a_c = np.empty((C, 24), dtype=np.uint8) if codes else None
+        a_i = np.empty((C,), dtype=np.int64) if codes else None
+        a_mv = np.empty((V, 4), dtype=np.float64) if morph else None
+        a_kp = np.empty((T,), dtype=np.uint8) if morph else None
+        a_mt = np.empty((M, 3, 2), dtype=np.int32) if morph else None
+        self._check(self.lib.ctr_mp4d_fetch(self.h, _ptr(a_v), _ptr(a_t), _ptr(a_k), _ptr(a_l), _ptr(a_c), _ptr(a_i),
+                                            _ptr(a_mv), _ptr(a_kp), _ptr(a_mt)), "ctr_mp4d_fetch")
+        cells = None
+        if codes:
+            # packed (word << 22 | bit << 17 | ...) -> linear hypervoxel index over the (n-1)^4 cell grid
+            n0, n1, n2, n3 = shape
+            W = (n3 + 31) // 32
+            gw = (a_i.astype(np.uint64) >> np.uint64(22)).astype(np.int64)
+            bit = ((a_i.astype(np.uint64) >> np.uint64(17)) & np.uint64(31)).astype(np.int64)
+            row, w = gw // W, gw % W
+            l = w * 32 + bit
+            k = row % n2
+            j = (row // n2) % n1
+            i = row // (n2 * n1)
+            cells = ((i * (n1 - 1) + j) * (n2 - 1) + k) * (n3 - 1) + l
+        return dict(verts=a_v, tets=a_t, keys=a_k, lowmin=a_l, codes=a_c, cells=cells, morph_verts=a_mv, keep=a_kp,
+                    morph_tris=a_mt)
 
     def mt3d_device_ptrs(self):
         v, n, t = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()

@@ -58,6 +58,7 @@ typedef enum { CTR_F32 = 0, CTR_F64 = 1 } ctr_dtype;
 #define CTR_WANT_CODES 16u     /* compact (cell, 30-bit case code) list of emitting cells            */
 #define CTR_NO_GEOMETRY 32u    /* classification, counts and offsets only                            */
 #define CTR_WANT_MINMAX 64u    /* field min / max (grid_field.py:79-80); NaN in the counts otherwise   */
+#define CTR_MORPH 128u         /* 4D only: run the morph stage (time binning, filtering, slicing)     */
 
 /* ---- context ----------------------------------------------------------------------------------- */
 CTR_API int ctr_create(int device, ctr_ctx** out);
@@ -148,6 +149,44 @@ CTR_API int ctr_mt2d_run(ctr_ctx* ctx, const ctr_mt2d_params* p, ctr_mt2d_counts
 /* seg_level [n_segments] index into levels; seg_keys [n_segments][2]; seg_pos [n_segments][2][2] float|double
  * (world coordinates of the two end points).  Order: by square, triangle, level.                          */
 CTR_API int ctr_mt2d_fetch(ctr_ctx* ctx, uint8_t* seg_level, uint64_t* seg_keys, void* seg_pos);
+
+/* ---- 4D marching pentatopes + morph triangles ---------------------------------------------------
+ * Replaces, for an array-backed field f[i][j][k][l] (l = time, contiguous), the reference's
+ *   pentatopes.py:101-106,216-291   find_tetrahedra (flood fill -> full scan), enumerate_voxel_tetrahedra,
+ *                                   enumerate_pentatope_tetrahedra (24 Kuhn pentatopes, 1 or 3 tetrahedra each)
+ *   tetrahedral.py:471-512          contour_pair_interpolation in 4D (keys, positions)
+ * and, with CTR_MORPH (always in grid coordinates, fp64),
+ *   pentatopes.py:162-169           bin_times(nbins)
+ *   pentatopes.py:171-189           drop_instant_tetrahedra(1e-7)
+ *   tetrahedral.py:353-375          remove_tiny_simplices(1e-3): the predicate (vertex merging: DESIGN.md)
+ *   morph_geometry.py:145-237       triangulate_tetrahedron_at_midpoints / add_tetrahedron / interpolate_pair_3d
+ *   pentatopes.py:336-348           removal of triangles with a zero-duration segment                    */
+typedef struct {
+  const void* field;
+  int32_t dtype;
+  uint32_t flags;
+  int64_t n0, n1, n2, n3;
+  double isovalue;
+  double origin[4], delta[4];
+  int32_t nbins;            /* bin_times: 100 in the reference */
+  int32_t reserved;
+} ctr_mp4d_params;
+
+typedef struct {
+  int64_t n_verts, n_tets, n_active_cells, n_crossings, n_codes, n_morph_tris;
+  double fmin, fmax;
+  double t_min, t_max;      /* t range of the binned vertices (grid units); NaN without CTR_MORPH          */
+} ctr_mp4d_counts;
+
+CTR_API int ctr_mp4d_run(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out);
+/* verts [n_verts][4] float|double world coords; tets [n_tets][4] vertex ids; keys/lowmin [n_verts];
+ * codes [n_codes][24] per-pentatope case codes (5-bit low mask | 32 if skipped) and cells [n_codes] packed
+ * (word << 22 | bit << 17 | ...) hypervoxel ids of the emitting hypervoxels;
+ * morph_verts [n_verts][4] fp64 grid coordinates after bin_times; keep [n_tets] 0/1 after the instant / tiny filter;
+ * morph_tris [n_morph_tris][3][2]: three segments (low-t vertex id, high-t vertex id) per morph triangle,
+ * duplicates not removed.                                                                                */
+CTR_API int ctr_mp4d_fetch(ctr_ctx* ctx, void* verts, int32_t* tets, uint64_t* keys, uint8_t* lowmin, uint8_t* codes,
+                           int64_t* cells, double* morph_verts, uint8_t* keep, int32_t* morph_tris);
 
 #ifdef __cplusplus
 }

@@ -182,3 +182,89 @@ def main2d():
 
 if __name__ == "__main__" and "2d" in sys.argv[1:]:
     main2d()
+
+
+# ------------------------------------------------------------------ 4D
+def fields4d():
+    out = {}
+    n, nt = 7, 4
+    g = np.linspace(-2, 2, n)
+    t = np.linspace(0, 1, nt)
+    X, Y, Z, T_ = np.meshgrid(g, g, g, t, indexing="ij")
+    bar = 3 * np.sqrt(X * X + Z * Z)
+    g2 = 3 * np.sqrt((1 - np.sqrt(X * X + Y * Y)) ** 2 + Z * Z)
+    out["morph7"] = (T_ * bar + (1 - T_) * g2, 1.2)
+    rng = np.random.default_rng(13)
+    out["noise4"] = (rng.standard_normal((4, 3, 4, 3)), 0.2)
+    out["ints4"] = (rng.integers(-1, 2, size=(3, 4, 3, 4)).astype(np.float64), 0.0)
+    return out
+
+
+def run4d(arr, value):
+    P = rh.load("pentatopes")
+    f = array_callable(arr)
+    corner = [s - 1 for s in arr.shape]
+    seeds = strict_seeds(arr, value)
+    t0 = time.time()
+    G = P.GridContour4D(corner, f, value, seeds)
+    # pentatopes.py:101-106
+    G.find_initial_voxels()
+    while G.new_surface_voxels:
+        G.expand_voxels()
+    for quad in G.surface_voxels:
+        G.enumerate_voxel_tetrahedra(quad)
+    corner_a = np.array(corner)
+    vox = np.array(sorted(v for v in G.surface_voxels if all(0 <= v[a] < corner[a] for a in range(4))),
+                   dtype=np.int64).reshape(-1, 4)
+    simplices = []
+    for s in G.simplex_sets:
+        pts = np.array([p for pair in s for p in pair])
+        owner = pts.min(axis=0)
+        if np.all(owner >= 0) and np.all(owner < corner_a):
+            simplices.append(sorted(s))
+    simplices = sorted(simplices)
+    used = sorted(set(pair for s in simplices for pair in s))
+    raw_low = np.array([p[0] for p in used], dtype=np.int64).reshape(-1, 4)
+    raw_high = np.array([p[1] for p in used], dtype=np.int64).reshape(-1, 4)
+    raw_pos = np.array([np.array(G.interpolated_contour_pairs[p]) for p in used], dtype=np.float64).reshape(-1, 4)
+    kidx = {p: i for i, p in enumerate(used)}
+    raw_tets = np.array([[kidx[p] for p in s] for s in simplices if len(s) == 4], dtype=np.int64).reshape(-1, 4)
+    # restrict the reference's state to in-range simplices so its post-processing is comparable
+    G.simplex_sets = set(frozenset(s) for s in simplices)
+    G.interpolated_contour_pairs = {p: G.interpolated_contour_pairs[p] for p in used}
+    # pentatopes.py:107-125 (not flatten, not smooth)
+    import io
+    import contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        G.bin_times()
+        binned_pos = np.array([np.array(G.interpolated_contour_pairs[p]) for p in used], dtype=np.float64).reshape(-1, 4)
+        G.drop_instant_tetrahedra()
+        after_drop = sorted(sorted(kidx[p] for p in s) for s in G.simplex_sets)
+        G.remove_tiny_simplices(epsilon=1e-3)
+        after_tiny = sorted(sorted(kidx[p] for p in s) for s in G.simplex_sets)
+        tiny_pos = np.array([np.array(G.interpolated_contour_pairs[p]) for p in used], dtype=np.float64).reshape(-1, 4)
+        mt = G.collect_morph_triangles()
+    # express the MorphTriangles in terms of the `used` key numbering
+    order = list(G.interpolated_contour_pairs.keys())
+    remap = np.array([kidx[p] for p in order], dtype=np.int64)
+    segs = np.array([(remap[i], remap[j]) for (i, j) in mt.segment_point_indices], dtype=np.int64).reshape(-1, 2)
+    tris = np.array([list(t) for t in mt.triangle_segment_indices], dtype=np.int64).reshape(-1, 3)
+    dt = time.time() - t0
+    return dict(field=arr, value=np.float64(value), voxels=vox, key_low=raw_low, key_high=raw_high, key_pos=raw_pos,
+                tets=raw_tets, binned_pos=binned_pos, tets_after_drop=np.array(after_drop, dtype=np.int64).reshape(-1, 4),
+                tets_after_tiny=np.array(after_tiny, dtype=np.int64).reshape(-1, 4), tiny_pos=tiny_pos,
+                morph_points=np.array(mt.points4d)[np.argsort(remap)] if len(remap) else np.zeros((0, 4)),
+                morph_segments=segs, morph_triangles=tris, n_seeds=np.int64(len(seeds)), seconds=np.float64(dt))
+
+
+def main4d():
+    for name, (arr, value) in fields4d().items():
+        g = run4d(arr, value)
+        np.savez_compressed(os.path.join(HERE, "mp4d_%s.npz" % name), **g)
+        print(name, arr.shape, "voxels", len(g["voxels"]), "keys", len(g["key_low"]), "tets", len(g["tets"]),
+              "after drop", len(g["tets_after_drop"]), "after tiny", len(g["tets_after_tiny"]),
+              "morph", g["morph_segments"].shape, g["morph_triangles"].shape, "%.1fs" % g["seconds"])
+
+
+if __name__ == "__main__" and "4d" in sys.argv[1:]:
+    main4d()
