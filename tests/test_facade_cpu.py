@@ -1,0 +1,113 @@
+"""CPU: the reference's own host-side tests re-expressed against the drop-in facade
+(contourist/test/test_field2d.py, test_triangulated.py TestMisc / TestAdjacentPairs), plus facade host logic."""
+import numpy as np
+import pytest
+
+from contourist_b200 import field2d, grid_field, morph_geometry, surface_geometry, triangulated
+
+EXPECT_SVG = """
+<svg height="300.0" width="300" viewBox="-1 -1 2 2">
+<path stroke-width="0.02" stroke="black" fill="none" d="M0.00 0.00 L0.00 1.00 L1.00 1.00 Z" />
+<path stroke-width="0.02" stroke="black" fill="none" d="M-1.00 -1.00 L-1.00 0.00" />
+</svg>
+"""
+
+
+def make_grid(materialize, cache):
+    def function(x, y):
+        return (x + 100) * 1000 + (y + 100)
+    return field2d.Function2DGrid(-10, -20, 30, 50, 10.0, 20.0, function, materialize, cache)
+
+
+@pytest.mark.parametrize("materialize,cache", [(False, False), (False, True), (True, False)])
+def test_f2dgrid(materialize, cache):
+    grid = make_grid(materialize, cache)
+    for _ in (1, 2):
+        assert np.allclose(grid.to_grid_coordinates((-10, -20)), (0, 0))
+        assert np.allclose(grid.from_grid_coordinates((0, 0)), (-10, -20))
+        assert np.allclose(grid.to_grid_coordinates((0, 0)), (1, 1))
+        assert np.allclose(grid.from_grid_coordinates((1, 1)), (0, 0))
+        assert np.allclose(grid.grid_function(0, 0), 90080)
+        assert np.allclose(grid.grid_function(4, 3), 130140)
+        S = set(tuple(int(v) for v in x) for x in grid.surrounding_vertices((5, 5)))
+        assert S == set([(1, 2), (1, 1), (2, 1), (2, 2)])
+    if materialize:
+        expect = [[90080.0, 90100.0, 90120.0, 90140.0], [100080.0, 100100.0, 100120.0, 100140.0],
+                  [110080.0, 110100.0, 110120.0, 110140.0], [120080.0, 120100.0, 120120.0, 120140.0],
+                  [130080.0, 130100.0, 130120.0, 130140.0]]
+        assert np.allclose(grid.materialized_array, expect)
+        assert grid.cache == {}
+    elif cache:
+        assert grid.materialized_array is None
+        assert grid.cache == {(0, 0): 90080.0, (4, 3): 130140.0}
+    else:
+        assert grid.materialized_array is None and len(grid.cache) == 0
+
+
+def test_samples_vectorised_equals_loop():
+    import math
+
+    def vec(x, y, z):
+        return x * x + np.sin(y) - z
+
+    def scalar(x, y, z):
+        return x * x + math.sin(y) - z          # math.sin rejects arrays -> per-point loop
+    a = grid_field.FunctionGrid([0, 0, 0], [1, 2, 1], [0.25, 0.5, 0.5], vec).samples(1)
+    b = grid_field.FunctionGrid([0, 0, 0], [1, 2, 1], [0.25, 0.5, 0.5], scalar).samples(1)
+    assert a.shape == (6, 6, 4) and np.allclose(a, b)
+
+
+def test_svg():
+    cseqs = [(True, [(0, 0), (0, 1), (1, 1)]), (False, [(-1, -1), (-1, 0)])]
+    assert triangulated.contour_sequences_to_svg(cseqs).strip() == EXPECT_SVG.strip()
+
+
+def test_adjacent_pairs():
+    adj = list(triangulated.adjacent_pairs((0, 0), (0, 1)))
+    assert adj == [((0, 0), (-1, 0)), ((0, 0), (1, 1)), ((1, 1), (0, 1)), ((-1, 0), (0, 1))]
+    assert set(triangulated.adjacent_pairs((0, 0), (1, 0))) == set(
+        [((0, -1), (1, 0)), ((0, 0), (0, -1)), ((1, 1), (1, 0)), ((0, 0), (1, 1))])
+    assert set(triangulated.adjacent_pairs((0, 0), (-1, -1))) == set(
+        [((0, -1), (-1, -1)), ((-1, 0), (-1, -1)), ((0, 0), (0, -1)), ((0, 0), (-1, 0))])
+
+
+def test_chain_segments_open_and_closed():
+    k = np.array([[1, 2], [2, 3], [10, 11], [11, 12], [12, 10]], dtype=np.uint64)
+    pos = {1: (0, 0), 2: (1, 0), 3: (2, 0), 10: (5, 5), 11: (6, 5), 12: (5, 6)}
+    p = np.array([[pos[int(a)], pos[int(b)]] for a, b in k], dtype=float)
+    out = triangulated.chain_segments(k, p)
+    assert [(c, len(q)) for c, q in out] == [(False, 3), (True, 3)]
+    assert np.allclose(out[0][1], [(0, 0), (1, 0), (2, 0)])
+
+
+def test_orient_triangles_outward_two_components():
+    V = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], float)
+    T = np.array([[0, 2, 4], [2, 1, 4], [1, 3, 4], [3, 0, 4], [2, 0, 5], [1, 2, 5], [3, 1, 5], [0, 3, 5]])
+    rng = np.random.default_rng(0)
+    V2 = np.concatenate([V, V * 0.5 + 5.0])
+    T2 = np.concatenate([T, T + 6])
+    T2 = np.array([t[::-1] if rng.random() < 0.5 else t for t in T2])
+    o = np.array(surface_geometry.SurfaceGeometry(V2, T2).orient_triangles())
+    n = np.cross(V2[o[:, 1]] - V2[o[:, 0]], V2[o[:, 2]] - V2[o[:, 0]])
+    cen = V2[o].mean(axis=1)
+    cen = np.where((cen > 2.5).any(axis=1)[:, None], cen - 5.0, cen)
+    assert ((n * cen).sum(axis=1) > 0).all()
+
+
+def test_morph_triangles_json_layout():
+    pts = [(0, 0, 0, 0), (0, 0, 1, 0), (2, 3, 2, 3), (3, 2, 3, 5)]
+    mt = morph_geometry.MorphTriangles(pts, [(0, 1), (2, 1), (0, 2), (1, 3)], [(0, 1, 2), (0, 2, 3)])
+    assert mt.segment_point_indices.tolist() == [[0, 1], [1, 2], [0, 2], [1, 3]]       # low t first
+    import json
+    d = json.loads(mt.to_json())
+    assert d["counts"] == [4, 4, 2] and d["max_value"] == 5.0 and d["min_value"] == 0.0
+    assert d["positions"][-4:] == [999999, 666666, 999999, 999999]
+    assert d["segments"] == [0, 1, 1, 2, 0, 2, 1, 3] and len(d["triangles"]) == 6
+
+
+def test_engine_import_fails_loudly_without_library(monkeypatch, tmp_path):
+    from contourist_b200 import engine
+    monkeypatch.setattr(engine, "_lib", None)
+    monkeypatch.setattr(engine, "LIB_PATH", str(tmp_path / "missing.so"))
+    with pytest.raises(engine.EngineError):
+        engine.load_library()
