@@ -383,7 +383,7 @@ BitplaneKind bitplane_choice() {
 
 template <typename T, bool MINMAX>
 int launch_bitplane(ctr_ctx* ctx, const T* dfield, unsigned nrows, int n2, int W, int rb, int rc, double iso,
-                    uint32_t* bits, uint32_t* nbits, uint8_t* rowflag, MinMaxKeys* dctr) {
+                    uint32_t* bits, uint32_t* nbits, uint8_t* rowflag, MinMaxKeys* dctr, bool clear_rowflag = true) {
   cudaStream_t st = ctx->stream;
   T thr, nlo, nhi;
   thresholds<T>(iso, thr, nlo, nhi);
@@ -400,7 +400,7 @@ int launch_bitplane(ctr_ctx* ctx, const T* dfield, unsigned nrows, int n2, int W
   rg.divRb.init((unsigned)rb);
   rg.rb = rb;
   rg.rc = rc;
-  CTR_CUDA(ctx, cudaMemsetAsync(rg.rowflag, 0, (size_t)nrows, st));
+  if (clear_rowflag) CTR_CUDA(ctx, cudaMemsetAsync(rg.rowflag, 0, (size_t)nrows, st));
   if (kind == BP_TMA) {
     static bool attr_set[4] = {false, false, false, false};
     const int smem = TMA_STAGES * TMA_CHUNK + 2 * TMA_STAGES * 8 + TMA_CONSUMER_WARPS * 32 * 4 + 64;

@@ -34,6 +34,7 @@ struct ctr_ctx {
   DevBuf list_v, list_t;     // compacted active word lists (uint32 word index)
   DevBuf tile_state;         // decoupled-lookback status words
   DevBuf counters;           // small block of device counters (see each path)
+  DevBuf vox_tab;            // 3D: corner bits -> triangle list of a voxel (256 x 12 words)
   void* counters_host = nullptr;  // pinned mirror
 
   // outputs (3D)
@@ -42,6 +43,7 @@ struct ctr_ctx {
   int last_kind = 0;         // 0 none, 3 = mt3d, 2 = mt2d, 4 = mp4d
   uint32_t last_flags = 0;
   int64_t last_counts[8] = {};
+  size_t spec_v = 0, spec_t = 0;   // 3D output-pool capacities (vertices, triangles) kept from earlier runs
 
   // 2D / 4D extra outputs are declared in their own translation units via these generic slots
   DevBuf aux[32];

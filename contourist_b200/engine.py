@@ -314,6 +314,27 @@ class Engine(object):
         return v.value, n.value, t.value
 
 
+def canonical_mesh(out):
+    """Key-sorted copy of an mt3d_fetch() result (needs WANT_KEYS).
+
+    The engine numbers vertices word-major (32 samples along k), then by edge direction, then by k -- deterministic,
+    but not the lexicographic order of the edge keys.  Parity checks (and anyone who wants ids = rank of the key)
+    sort here: vertices / normals / keys / lowmin reordered by key, triangle ids remapped, triangle order kept."""
+    keys = out["keys"]
+    perm = np.argsort(keys, kind="stable")
+    inv = np.empty(len(perm), dtype=np.int64)
+    inv[perm] = np.arange(len(perm), dtype=np.int64)
+    res = dict(out)
+    for name in ("verts", "normals", "keys", "lowmin"):
+        if out.get(name) is not None:
+            res[name] = out[name][perm]
+    if out.get("tris") is not None:
+        t = out["tris"].astype(np.int64)
+        local = t < len(perm)                      # ids >= n_verts belong to the next shard (sharded runs)
+        res["tris"] = np.where(local, inv[np.minimum(t, len(perm) - 1)] if len(perm) else t, t).astype(out["tris"].dtype)
+    return res
+
+
 _default = {}
 
 

@@ -43,8 +43,14 @@ def test_isosurface_facade_equals_oracle_world_coords(engine):
     arr = S.grid.samples(1)
     assert arr.shape == (18, 18, 18)
     r = mt3d.extract(arr, 0.5)
-    assert np.array_equal(pts, r["pos"] * 0.125 + (-1.0))
-    assert np.array_equal(np.sort(tris, axis=1), np.sort(r["tris"], axis=1))
+    # canonical form (the engine's vertex order is word / direction / k, the oracle's is by edge key): each triangle
+    # as the sorted tuple of its three world positions, the mesh as the sorted list of those
+    world = r["pos"] * 0.125 + (-1.0)
+    assert len(pts) == len(world) and len(tris) == len(r["tris"])
+
+    def canon(P, T):
+        return sorted(tuple(sorted(tuple(P[i]) for i in t)) for t in np.asarray(T))
+    assert canon(np.asarray(pts), tris) == canon(world, r["tris"])
     mx, mn, nseg = mt3d.crossing_segments(arr, 0.5, count_only=True)
     assert len(S.grid_endpoints) == nseg
     v0, v1 = S.grid_endpoints[0]

@@ -77,7 +77,8 @@ def main():
     print("kernel:", kname[:100])
     print("total warp-instructions %d, thread-instructions %d, stall samples %d" % (tot[0], tot[2], tot[1]))
     print("%-26s %12s %6s %10s %6s" % ("line", "warp-inst", "%", "samples", "%"))
-    for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+    key = 0 if "--by-inst" in sys.argv else 1
+    for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][key])[:top]:
         name = "%s:%d" % ln if ln else "?"
         print("%-26s %12d %6.2f %10d %6.2f" % (name, a[0], 100.0 * a[0] / max(tot[0], 1), a[1], 100.0 * a[1] / max(tot[1], 1)))
 
