@@ -46,6 +46,7 @@ struct Counters {                    // device counter block (mirrored to pinned
   unsigned long long v_emit;         // vertex count at the start of plane i_hi (vertices this call emits)
   unsigned int ticket;
   unsigned int n_codes;              // slots handed out by k_codes
+  unsigned int claim_v, claim_t;     // next unclaimed segment batch of the persistent stage 3 / 4 kernels
 };
 
 
@@ -579,12 +580,6 @@ __device__ __forceinline__ float inv_sqrt(float a) { return rsqrtf(a); }
 template <typename T, typename G>
 __device__ __forceinline__ void grad_at(const Grid<T>& g, const T* __restrict__ c, int i, int j, int k, long long s0,
                                         long long s1, G out[3]) {
-  if (i > 0 && i < g.n0 - 1 && j > 0 && j < g.n1 - 1 && k > 0 && k < g.n2 - 1) {
-    out[0] = ((G)c[s0] - (G)c[-s0]) * (G)0.5;
-    out[1] = ((G)c[s1] - (G)c[-s1]) * (G)0.5;
-    out[2] = ((G)c[1] - (G)c[-1]) * (G)0.5;
-    return;
-  }
   {
     const bool lo = i > 0, hi = i < g.n0 - 1;
     G a = (G)c[hi ? s0 : 0], b = (G)c[lo ? -s0 : 0];
@@ -625,19 +620,28 @@ constexpr int EV_THREADS = 256;
 constexpr int EV_WARPS = EV_THREADS / 32;
 constexpr int EV_BLOCKS_PER_SM = 4;
 constexpr int SEG_WORDS = 64;                        // words per warp step in stages 3 and 4 (two per lane)
+constexpr unsigned SEG_BATCH = 4;                    // segments claimed per atomic
 
 template <typename T, typename G>
 __global__ void __launch_bounds__(EV_THREADS, EV_BLOCKS_PER_SM)
     k_emit_verts(const __grid_constant__ Grid<T> g, unsigned word0, unsigned nwords_emit, const uint2* __restrict__ wpre,
                  const uint2* __restrict__ wdir, const __grid_constant__ Xform<G> xf, G* __restrict__ verts,
-                 G* __restrict__ normals, unsigned long long* __restrict__ keys, uint8_t* __restrict__ lowmin, unsigned cap_v) {
+                 G* __restrict__ normals, unsigned long long* __restrict__ keys, uint8_t* __restrict__ lowmin, unsigned cap_v,
+                 unsigned* claim) {
   __shared__ uint32_t s_x[EV_WARPS][SEG_WORDS][10];  // 7 used-edge words, the word's own low bits, dirpack
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   uint32_t (*sx)[10] = s_x[warp];
   const G v = (G)g.v;
   const long long s1 = g.n2, s0 = (long long)g.n1 * g.n2;
   const unsigned nseg = (nwords_emit + SEG_WORDS - 1) / SEG_WORDS;
-  for (unsigned seg = blockIdx.x * EV_WARPS + warp; seg < nseg; seg += gridDim.x * EV_WARPS) {
+  // segments are claimed in batches of SEG_BATCH by an atomic counter (work per segment varies by orders of magnitude)
+  for (unsigned seg = 0, seg_end = 0;; ++seg) {
+    if (seg == seg_end) {
+      if (lane == 0) seg = atomicAdd(claim, SEG_BATCH);
+      seg = __shfl_sync(0xffffffffu, seg, 0);
+      seg_end = seg + SEG_BATCH;
+    }
+    if (seg >= nseg) break;
     const unsigned seg0 = seg * SEG_WORDS;
     unsigned cnt[2] = {0, 0}, vb0 = 0;
     {
@@ -711,6 +715,13 @@ __global__ void __launch_bounds__(EV_THREADS, EV_BLOCKS_PER_SM)
       const int di = (d >> 2) & 1, dj = (d >> 1) & 1, dk = d & 1;
       const T* cp = g.f + ((long long)oi * g.n1 + oj) * g.n2 + ok;
       const T* cq = cp + (di ? s0 : 0) + (dj ? s1 : 0) + dk;
+      // all samples this vertex needs are requested before the first one is used (one memory latency per round)
+      const bool inner = normals && oi > 0 && oi + di < g.n0 - 1 && oj > 0 && oj + dj < g.n1 - 1 && ok > 0 && ok + dk < g.n2 - 1;
+      T sp[6], sq[6];
+      if (inner) {
+        sp[0] = cp[s0]; sp[1] = cp[-s0]; sp[2] = cp[s1]; sp[3] = cp[-s1]; sp[4] = cp[1]; sp[5] = cp[-1];
+        sq[0] = cq[s0]; sq[1] = cq[-s0]; sq[2] = cq[s1]; sq[3] = cq[-s1]; sq[4] = cq[1]; sq[5] = cq[-1];
+      }
       const G fp = (G)*cp, fq = (G)*cq;
       // tetrahedral.py:476-487: key oriented (low, high) by value; ratio = (z-flow)/(fhigh-flow), 0.5 if ~0
       const G flow = p_low ? fp : fq, fhigh = p_low ? fq : fp;
@@ -729,8 +740,16 @@ __global__ void __launch_bounds__(EV_THREADS, EV_BLOCKS_PER_SM)
       }
       if (normals) {
         G gp[3], gq[3];
-        grad_at<T, G>(g, cp, oi, oj, ok, s0, s1, gp);
-        grad_at<T, G>(g, cq, oi + di, oj + dj, ok + dk, s0, s1, gq);
+        if (inner) {
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) {
+            gp[ax] = ((G)sp[2 * ax] - (G)sp[2 * ax + 1]) * (G)0.5;
+            gq[ax] = ((G)sq[2 * ax] - (G)sq[2 * ax + 1]) * (G)0.5;
+          }
+        } else {
+          grad_at<T, G>(g, cp, oi, oj, ok, s0, s1, gp);
+          grad_at<T, G>(g, cq, oi + di, oj + dj, ok + dk, s0, s1, gq);
+        }
         G nn[3], len2 = 0;
 #pragma unroll
         for (int ax = 0; ax < 3; ++ax) {
@@ -821,7 +840,8 @@ __device__ __noinline__ unsigned cell_emit_near(const Grid<T>& g, int i, int j, 
 template <typename T>
 __global__ void __launch_bounds__(ET_THREADS, ET_BLOCKS_PER_SM)
     k_emit_tris(const __grid_constant__ Grid<T> g, unsigned word0, unsigned nwords_emit, const uint2* __restrict__ wpre,
-                const uint2* __restrict__ wdir, const uint32_t* __restrict__ vox_tab, int* __restrict__ tris, unsigned cap_t) {
+                const uint2* __restrict__ wdir, const uint32_t* __restrict__ vox_tab, int* __restrict__ tris, unsigned cap_t,
+                unsigned* claim) {
   __shared__ unsigned s_ids[ET_WARPS][19][32];
   __shared__ int s_stage[ET_WARPS][32 * 12 * 3];
   __shared__ uint32_t s_ew[ET_WARPS][SEG_WORDS][6];   // emitting-voxel word, 4 bit planes of per-voxel triangle counts, tbase
@@ -833,7 +853,13 @@ __global__ void __launch_bounds__(ET_THREADS, ET_BLOCKS_PER_SM)
   const unsigned uW = (unsigned)g.W;
   const size_t gcap = (size_t)cap_t * 3;
   const unsigned nseg = (nwords_emit + SEG_WORDS - 1) / SEG_WORDS;
-  for (unsigned seg = blockIdx.x * ET_WARPS + warp; seg < nseg; seg += gridDim.x * ET_WARPS) {
+  for (unsigned seg = 0, seg_end = 0;; ++seg) {
+    if (seg == seg_end) {
+      if (lane == 0) seg = atomicAdd(claim, SEG_BATCH);
+      seg = __shfl_sync(0xffffffffu, seg, 0);
+      seg_end = seg + SEG_BATCH;
+    }
+    if (seg >= nseg) break;
     const unsigned seg0 = seg * SEG_WORDS;
     unsigned tcnt[2] = {0, 0}, tb[2] = {0, 0};
     {
@@ -906,6 +932,13 @@ __global__ void __launch_bounds__(ET_THREADS, ET_BLOCKS_PER_SM)
           S[ab] = __funnelshift_r(P[ab], nx, 1);
           c8 |= (__funnelshift_r(P[ab], nx, b) & 3u) << (ab * 2);    // bits b, b+1 of the row = corners (ab, dk)
         }
+        unsigned vb[4], vb1[4];
+        uint2 dp[4], dp1[4];
+#pragma unroll
+        for (int ab = 0; ab < 4; ++ab) {
+          vb[ab] = wpre[wi[ab]].x;
+          dp[ab] = wdir[wi[ab]];
+        }
         // used-edge words per owner row (index ab) and direction (index d-1); only the 14 that voxel edges use
         uint32_t X[4][7];
         if (near) {
@@ -917,13 +950,6 @@ __global__ void __launch_bounds__(ET_THREADS, ET_BLOCKS_PER_SM)
           X[1][0] = P[1] ^ S[1]; X[1][3] = P[1] ^ P[3]; X[1][4] = P[1] ^ S[3];
           X[2][0] = P[2] ^ S[2]; X[2][1] = P[2] ^ P[3]; X[2][2] = P[2] ^ S[3];
           X[3][0] = P[3] ^ S[3];
-        }
-        unsigned vb[4], vb1[4];
-        uint2 dp[4], dp1[4];
-#pragma unroll
-        for (int ab = 0; ab < 4; ++ab) {
-          vb[ab] = wpre[wi[ab]].x;
-          dp[ab] = wdir[wi[ab]];
         }
         // owner points at k+1: bit b+1 of the same word, or (b == 31) bit 0 of the next word with rank 0
         uint32_t below1 = below | (1u << b);
@@ -1228,7 +1254,8 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
     if ((r = ctr_ensure(ctx, ctx->tris, ct * 12, true))) return r;
     return 0;
   };
-  auto launch_emit = [&](size_t cv, size_t ct) -> int {
+  auto launch_emit = [&](size_t cv, size_t ct, bool again) -> int {
+    if (again) CTR_CUDA(ctx, cudaMemsetAsync(&dctr->claim_v, 0, 2 * sizeof(unsigned), st));
     const unsigned capv = (unsigned)std::min<size_t>(cv, 0x7fffffffu), capt = (unsigned)std::min<size_t>(ct, 0x7fffffffu);
     unsigned long long* dkeys = want_k ? (unsigned long long*)ctx->keys.p : nullptr;
     uint8_t* dlow = want_k ? (uint8_t*)ctx->lowmin.p : nullptr;
@@ -1239,16 +1266,16 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
       const uint2* wdir = (const uint2*)ctx->tbase.p;
       if (f64)
         k_emit_verts<T, double><<<vb, EV_THREADS, 0, st>>>(g, word0, nemit, wpre, wdir, xd, (double*)ctx->verts.p,
-                                                            want_n ? (double*)ctx->normals.p : nullptr, dkeys, dlow, capv);
+                                                            want_n ? (double*)ctx->normals.p : nullptr, dkeys, dlow, capv, &dctr->claim_v);
       else
         k_emit_verts<T, float><<<vb, EV_THREADS, 0, st>>>(g, word0, nemit, wpre, wdir, xs, (float*)ctx->verts.p,
-                                                           want_n ? (float*)ctx->normals.p : nullptr, dkeys, dlow, capv);
+                                                           want_n ? (float*)ctx->normals.p : nullptr, dkeys, dlow, capv, &dctr->claim_v);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_verts");
       ctr_stage_mark(ctx, 4);
       const unsigned tb = std::min<unsigned>((segs + ET_WARPS - 1) / ET_WARPS, (unsigned)ctx->sm_count * ET_BLOCKS_PER_SM);
       k_emit_tris<T><<<tb, ET_THREADS, 0, st>>>(g, word0, nemit, wpre, wdir, (const uint32_t*)ctx->vox_tab.p,
-                                                (int*)ctx->tris.p, capt);
+                                                (int*)ctx->tris.p, capt, &dctr->claim_t);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_tris");
     } else {
@@ -1272,7 +1299,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   const bool speculate = geom && ctx->spec_v > 0 && ctx->spec_t > 0 && !(p->flags & CTR_WANT_CODES);
   if (speculate) {
     if ((rc = ensure_outputs(ctx->spec_v, ctx->spec_t))) return rc;
-    if ((rc = launch_emit(ctx->spec_v, ctx->spec_t))) return rc;
+    if ((rc = launch_emit(ctx->spec_v, ctx->spec_t, false))) return rc;
     if ((rc = read_counts())) return rc;
     emitted = nV <= ctx->spec_v && totT <= ctx->spec_t;
   } else {
@@ -1284,7 +1311,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
     ctx->spec_v = std::max<size_t>(ctx->spec_v, (size_t)nV + (size_t)nV / 4 + 1024);
     ctx->spec_t = std::max<size_t>(ctx->spec_t, (size_t)totT + (size_t)totT / 4 + 1024);
     if ((rc = ensure_outputs(ctx->spec_v, ctx->spec_t))) return rc;
-    if ((rc = launch_emit(ctx->spec_v, ctx->spec_t))) return rc;
+    if ((rc = launch_emit(ctx->spec_v, ctx->spec_t, speculate))) return rc;
   } else if (!geom) {
     ctr_stage_mark(ctx, 4);
     ctr_stage_mark(ctx, 5);
