@@ -187,7 +187,7 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     eng.set_timing(True)
-    flags = E.WANT_NORMALS
+    flags = E.WANT_NORMALS if not os.environ.get("CTR_BENCH_NO_NORMALS") else 0   # (diagnostic switch; the metric needs normals)
     counts_dev = torch.zeros(2, dtype=torch.int64, device=dev)
     gathered = torch.zeros(2 * world, dtype=torch.int64, device=dev)
 
@@ -245,7 +245,7 @@ def run_ours(args):
         barrier()
         t1 = time.perf_counter()
         ce = eng.mt3d_run(hf, ISOVALUE, flags=flags, i_lo=a - lo, i_hi=b - lo, plane_offset=lo)
-        outs = eng.mt3d_fetch()
+        outs = eng.mt3d_fetch(pinned=True)
         if world > 1:
             counts_dev.copy_(torch.tensor([ce.n_verts, ce.n_tris], dtype=torch.int64))
             dist.all_gather_into_tensor(gathered, counts_dev)
@@ -264,10 +264,21 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
-    st = stage_acc / args.steps                       # ms: 0 H2D, 1 bitplane, 2 count+scan, 3 verts, 4 tris
+    st = stage_acc / args.steps                       # ms: 0 H2D, 1 classify, 2 count+scan, 3 verts, 4 tris
     field_bytes = float(np.prod(shape)) * 4
-    bit_ms = st[1]
-    achieved = field_bytes / (bit_ms * 1e-3) / 1e9 if bit_ms > 0 else None
+    # SURVEY 8(d) algorithmic bytes: 4 B per voxel read (stage 1), 24 B per vertex (stage 3), 12 B per triangle (stage 4);
+    # the scan (stage 2) moves no algorithmic bytes -- it is pure overhead and is charged to the whole-step figure.
+    stages = {"k_bitplane_tma (stage 1: field -> low/near bitplanes, the only full-field pass)": (st[1], field_bytes),
+              "k_emit_verts (stage 3: positions + normals)": (st[3], c.n_verts * 24.0),
+              "k_emit_tris (stage 4: indexed triangles)": (st[4], c.n_tris * 12.0)}
+    dom = max(stages, key=lambda k: stages[k][0])     # dominant = the kernel with the largest share of the step
+    dom_ms, dom_bytes = stages[dom]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
+    per_stage = {k.split(" ")[0]: {"ms": v[0], "algorithmic_bytes": v[1],
+                                   "gbs": (v[1] / (v[0] * 1e-3) / 1e9) if v[0] > 0 else None,
+                                   "frac": (v[1] / (v[0] * 1e-3) / 1e9 / peak) if v[0] > 0 else None}
+                 for k, v in stages.items()}
+    per_stage["k_count_scan"] = {"ms": st[2], "algorithmic_bytes": 0.0, "gbs": 0.0, "frac": 0.0}
     alg_total = float(n) ** 3 * 4 + c.n_verts * 24 + c.n_tris * 12        # field + V*(3p+3p) + T*12
     pipe_gbs = alg_total / (ms_step * 1e-3) / 1e9
     # CPU baseline: oracle port, 1 core, bounded sample of the same field family
@@ -285,16 +296,17 @@ def run_ours(args):
         "mtris_per_s": n_tris_all / (ms_step * 1e-3) / 1e6, "n_tris": n_tris_all, "n_verts": n_verts_all,
         "stage_ms": {"bitplane": st[1], "count_scan": st[2], "emit_verts": st[3], "emit_tris": st[4],
                      "wall_ms_per_step": wall / args.steps * 1e3},
-        "roofline": {"bound": "hbm", "kernel": "k_bitplane (field -> low/near bitplanes, the only full-field pass)",
+        "roofline": {"bound": "hbm", "kernel": dom,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": field_bytes},
+                     "algorithmic_bytes_per_launch": dom_bytes, "per_stage": per_stage},
         "pipeline_roofline": {"algorithmic_bytes": alg_total, "achieved": pipe_gbs, "frac": pipe_gbs / peak,
                               "note": "whole step: (field + V*24 + T*12) / device time of the step"},
         "cpu_baseline": {"value": cpu_val, "unit": "Gvoxels/s", "cores": 1, "kind": "port",
                          "sample": "33x160x160 fp32 sub-volume of the CT-like field, numpy oracle port (extract + normals)"},
         "e2e": {"value": e2e_val, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "note": "ctr_mt3d_run + ctr_mt3d_fetch with pinned host field and host outputs"},
+                "note": "ctr_mt3d_run + ctr_mt3d_fetch with host buffers (page-locked): H2D of the field and D2H of "
+                        "vertices, normals and triangles inside the timed region"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line))

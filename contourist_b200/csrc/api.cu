@@ -53,6 +53,9 @@ extern "C" void ctr_destroy(ctr_ctx* c) {
   if (c->counters_host) cudaFreeHost(c->counters_host);
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -82,3 +85,21 @@ extern "C" int ctr_stage_times(ctr_ctx* c, float* ms, int n) {
 }
 
 extern "C" int64_t ctr_kernel_launches(const ctr_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int ctr_host_alloc(ctr_ctx* c, uint64_t bytes, void** out) {
+  if (!c || !out) return CTR_ERR_BAD_ARG;
+  *out = nullptr;
+  CTR_CUDA(c, cudaSetDevice(c->device));
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return ctr_fail(c, CTR_ERR_OOM, "cudaHostAlloc failed", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+extern "C" int ctr_host_free(ctr_ctx* c, void* p) {
+  if (!c) return CTR_ERR_BAD_ARG;
+  if (p) CTR_CUDA(c, cudaFreeHost(p));
+  return 0;
+}

@@ -19,6 +19,8 @@ struct ctr_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t stream2 = nullptr;      // side stream: stage 4 runs beside stage 3
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   int64_t launches = 0;
   bool timing = false;
@@ -43,7 +45,8 @@ struct ctr_ctx {
   int last_kind = 0;         // 0 none, 3 = mt3d, 2 = mt2d, 4 = mp4d
   uint32_t last_flags = 0;
   int64_t last_counts[8] = {};
-  size_t spec_v = 0, spec_t = 0;   // 3D output-pool capacities (vertices, triangles) kept from earlier runs
+  // 3D: capacities of the output pools / work lists kept from earlier runs, last list lengths, launch coverage
+  size_t spec_v = 0, spec_t = 0, spec_own = 0, spec_cell = 0, last_own = 0, last_cell = 0, cover_own = 0, cover_cell = 0;
 
   // 2D / 4D extra outputs are declared in their own translation units via these generic slots
   DevBuf aux[32];

@@ -39,16 +39,17 @@ struct Counters {                    // device counter block (mirrored to pinned
   // stage 1 (bitplane)
   unsigned long long min_key;        // order-preserving encoding of fmin
   unsigned long long max_key;        // order-preserving encoding of fmax
-  // stage 2 (count + scan)
+  unsigned int any_near;
+  unsigned int pad0;
+  // stage 2 (count + scan): zeroed before every launch of k_count_scan
   unsigned long long n_cells;        // emitting voxels
   unsigned long long n_cross;        // strict crossings
   unsigned long long total_vt;       // packed totals over the scanned range: T << 31 | V
+  unsigned long long total_act;      // packed list lengths: voxels << 31 | owners
   unsigned long long v_emit;         // vertex count at the start of plane i_hi (vertices this call emits)
   unsigned int ticket;
-  unsigned int n_codes;              // slots handed out by k_codes
-  unsigned int claim_v, claim_t;     // next unclaimed segment batch of the persistent stage 3 / 4 kernels
+  unsigned int pad1;
 };
-
 
 
 template <typename T>
@@ -62,7 +63,8 @@ struct Grid {
   double v;                          // isovalue
   double tolv;                       // 1e-8 + 1e-5*|v|
   // allclose handling is local: rowflag[i*n1+j] != 0 iff some sample of rows (i..i+2, j..j+2) lies inside the
-  // conservative allclose hull; kernels read it (`near`) before touching a word of row (i, j).
+  // conservative allclose hull; kernels copy it into any_near before touching a word of row (i, j).
+  int any_near;
   const uint8_t* rowflag;
   FastDiv divW, divN1;
   __device__ __forceinline__ void word_coords(unsigned gw, int& i, int& j, int& w) const {
@@ -163,7 +165,7 @@ __device__ __forceinline__ void load_planes(const Grid<T>& g, const uint32_t* __
       bool ok = (a == 0 || pl.has_i1) && (b == 0 || pl.has_j1);
       uint32_t p = 0, nx = 0;
       if (ok) {
-        const unsigned base = ((unsigned)(i + a) * (unsigned)g.n1 + (unsigned)(j + b)) * (unsigned)g.W + (unsigned)w;
+        long long base = ((long long)(i + a) * g.n1 + (j + b)) * g.W + w;
         p = plane[base];
         if (w + 1 < g.W) nx = plane[base + 1];
       }
@@ -235,10 +237,16 @@ __device__ __noinline__ void resolve_used_exact(const Grid<T>& g, int i, int j, 
 }
 
 template <typename T>
-__device__ __forceinline__ void owner_used(const Grid<T>& g, bool near, const Planes& pl, int i, int j, int w,
-                                           uint32_t used[7]) {
+__device__ __forceinline__ void owner_used(const Grid<T>& g, const Planes& pl, int i, int j, int w, uint32_t used[7]) {
   cross_words(pl, used);
-  if (near) resolve_used_exact(g, i, j, w, used);
+  if (g.any_near) resolve_used_exact(g, i, j, w, used);
+}
+
+__device__ __forceinline__ unsigned gather7(const uint32_t u[7], int b) {
+  unsigned m = 0;
+#pragma unroll
+  for (int d = 0; d < 7; ++d) m |= ((u[d] >> b) & 1u) << d;
+  return m;
 }
 
 __device__ __forceinline__ unsigned tet_mask_of(unsigned corner8, int t) {
@@ -248,18 +256,17 @@ __device__ __forceinline__ unsigned tet_mask_of(unsigned corner8, int t) {
   return (corner8 & 1u) | (((corner8 >> 7) & 1u) << 1) | (((corner8 >> xs[t]) & 1u) << 2) | (((corner8 >> ys[t]) & 1u) << 3);
 }
 
-// Exact (allclose-aware) corrections of one word, the rare part of stages 2 and 4:
-//   *ncross : strict-crossing count (grid_field.py:81): a crossing whose HIGH endpoint equals the isovalue is not strict;
-//   odd/two : bits of tets that do not emit under the exact rules (tetrahedral.py:391,576) are cleared.
+// strict-crossing correction and exact tet counts of one word: the rare, allclose-dependent part of stage 2
 template <typename T>
-__device__ __noinline__ void word_exact_fix(const Grid<T>& g, const Planes& pl, int i, int j, int w, unsigned* ncross,
-                                            uint32_t odd[6], uint32_t two[6]) {
+__device__ __noinline__ void count_word_exact(const Grid<T>& g, const Planes& pl, int i, int j, int w, bool cells_ok,
+                                              unsigned& ncross, unsigned& ntri, uint32_t& emitting) {
   Planes npl;
   load_planes(g, g.nbits, i, j, w, npl);
-  if (ncross) {
+  if (cells_ok) {
     uint32_t xs[7];
     cross_words(pl, xs);
     for (int d = 1; d <= 7; ++d) {
+      // not strict when the HIGH endpoint equals the isovalue exactly (then (f0-v)*(f1-v) == 0)
       uint32_t A = pl.P[0], O = dir_plane(pl, d);
       uint32_t c = xs[d - 1] & pl.kp1 & ((~A & npl.P[0]) | (~O & dir_plane(npl, d)));
       while (c) {
@@ -268,318 +275,297 @@ __device__ __noinline__ void word_exact_fix(const Grid<T>& g, const Planes& pl, 
         bool a_high = !((A >> b) & 1u);
         int k = w * 32 + b;
         double fh = a_high ? sample(g, i, j, k) : sample(g, i + ((d >> 2) & 1), j + ((d >> 1) & 1), k + (d & 1));
-        if (fh == g.v) --*ncross;
+        if (fh == g.v) --ncross;
       }
     }
+    uint32_t odd[6], two[6], cand;
+    tet_words(pl, &npl, pl.kp1, odd, two, cand);
+    while (cand) {
+      int b = __ffs(cand) - 1;
+      cand &= cand - 1;
+      // remove the fast-path contribution of this voxel, add the exact one
+      for (int q = 0; q < 6; ++q) ntri -= ((odd[q] >> b) & 1u) + 2u * ((two[q] >> b) & 1u);
+      emitting &= ~(1u << b);
+      unsigned e = cell_emit_exact(g, i, j, w * 32 + b, nullptr);
+      if (e) emitting |= 1u << b;
+      for (int q = 0; q < 6; ++q)
+        if ((e >> q) & 1u) ntri += ((odd[q] >> b) & 1u) ? 1u : 2u;
+    }
   }
-  uint32_t o2[6], t2[6], cand;
-  tet_words(pl, &npl, pl.kp1, o2, t2, cand);
-  while (cand) {
-    int b = __ffs(cand) - 1;
-    cand &= cand - 1;
-    const unsigned e = cell_emit_exact(g, i, j, w * 32 + b, nullptr);
-    const uint32_t keep = ~(1u << b);
-    for (int q = 0; q < 6; ++q)
-      if (!((e >> q) & 1u)) {
-        odd[q] &= keep;
-        two[q] &= keep;
-      }
-  }
-}
-
-// carry-save adders over bit-sliced counters (one counter per bit position of the word)
-__device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t& s, uint32_t& cy) {
-  const uint32_t ab = a ^ b;
-  s = ab ^ c;
-  cy = (a & b) | (c & ab);
-}
-// per-voxel number of triangles (0..12) = sum(odd) + 2*sum(two) as four bit planes
-__device__ __forceinline__ void slice_tris(const uint32_t odd[6], const uint32_t two[6], uint32_t s[4]) {
-  uint32_t a0, a1, a2, b0, b1, b2, p, q, cp, cq, c;
-  full_add(odd[0], odd[1], odd[2], p, cp);
-  full_add(odd[3], odd[4], odd[5], q, cq);
-  a0 = p ^ q;
-  c = p & q;
-  full_add(cp, cq, c, a1, a2);
-  full_add(two[0], two[1], two[2], p, cp);
-  full_add(two[3], two[4], two[5], q, cq);
-  b0 = p ^ q;
-  c = p & q;
-  full_add(cp, cq, c, b1, b2);
-  // count = A + 2B
-  s[0] = a0;
-  s[1] = a1 ^ b0;
-  const uint32_t k1 = a1 & b0;
-  uint32_t k2;
-  full_add(a2, b1, k1, s[2], k2);
-  s[3] = b2 ^ k2;          // count <= 12: no carry out of bit 3
-}
-
-// n-th (0-based) set bit of x; x has more than n bits set.  (__fns costs ~50 instructions; this is ~25.)
-__device__ __forceinline__ int nth_set_bit(uint32_t x, unsigned n) {
-  int b = 0;
-#pragma unroll
-  for (int step = 16; step > 0; step >>= 1) {
-    const uint32_t below = (1u << (b + step)) - 1u;      // b + step <= 31
-    if ((unsigned)__popc(x & below) <= n) b += step;
-  }
-  return b;
-}
-
-// Vertex order inside a word: direction-major, then bit (k).  dirpack byte q-1 (q = 1..6) = number of used edges of
-// the word in the directions before direction index q (index = d-1); id = vbase[word] + dirbase(q) + rank of the bit.
-// Kept as two 32-bit halves (bytes 0..3 | bytes 4..5) so that every extraction is a 32-bit shift.
-__device__ __forceinline__ uint2 dir_pack(const uint32_t x[7]) {
-  unsigned c = 0;
-  uint2 dp = make_uint2(0u, 0u);
-#pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    c += __popc(x[q]);
-    if (q < 4) dp.x |= c << (8 * q);
-    else dp.y |= c << (8 * (q - 4));
-  }
-  return dp;
-}
-__device__ __forceinline__ unsigned dir_base(uint2 dp, int q) {   // q = d-1 in 0..6 (compile-time constant when unrolled)
-  return q == 0 ? 0u : q <= 4 ? (dp.x >> (8 * (q - 1))) & 255u : (dp.y >> (8 * (q - 5))) & 255u;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stage 2: per-word counts from the bitplanes + exclusive scan, in ONE launch of a few hundred CTAs.
-// A CTA takes a contiguous chunk of words (ticket order) and
-//   1  walks it in sub-tiles of 1024 words: every thread tests 4 words (does anything cross here?), the CTA
-//      compacts the interesting ones in shared memory and deals them out evenly: vertex / triangle counts
-//      (popcounts of bit-sliced words) -> shared memory, per-direction prefix (dirpack) -> wdir[word];
-//   2  publishes the chunk aggregate and sums the aggregates of ALL earlier chunks (one status word each, read
-//      in parallel by the CTA's threads: no serial look-back chain; earlier tickets have started, so no deadlock);
-//   3  scans its counts warp-contiguously (lane = word: coalesced) -> wpre[word] = (vbase, tbase).
-// Nothing is compacted for the later stages: they expand words -> vertices / voxels themselves, warp by warp.
+// Stage 2: per-word counts from the bitplanes + fused single-pass decoupled-lookback scan.
+//   A  every thread tests 4 words of the tile (does anything cross here?) and the block compacts the
+//      interesting ones in shared memory;
+//   B  interesting words are dealt out evenly: vertex / triangle / owner / voxel counts per word;
+//   C  block scan + decoupled look-back across tiles -> exclusive offsets per word;
+//   D  interesting words again: write vbase and the compacted, ordered lists of
+//        active owners (own_id = word<<13 | bit<<8 | p_low<<7 | mask7, own_voff = first vertex id)
+//        active voxels (cell_id = word<<19 | bit<<14 | emit6<<8 | corner8, cell_toff = first triangle).
 // ------------------------------------------------------------------------------------------------
 constexpr int CS_THREADS = 256;
 constexpr int CS_ITEMS = 4;
-constexpr int CS_SUB = CS_THREADS * CS_ITEMS;
-constexpr unsigned CS_MAX_CHUNK = 14 * 1024;          // words per chunk: 4 bytes of shared memory each
+constexpr int CS_TILE = CS_THREADS * CS_ITEMS;
 
-#define CTR_ST_VALID (1ull << 63)
-
-__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* s_warp) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();                                   // s_warp may still be read from a previous use
-  if (lane_id() == 0) s_warp[threadIdx.x >> 5] = v;
-  __syncthreads();
-  unsigned long long t = 0;
-#pragma unroll
-  for (int q = 0; q < CS_THREADS / 32; ++q) t += s_warp[q];
-  return t;
-}
-
-// quick test of one word: does any of its 7 x 32 owned edges cross?  32-bit word indices, no masks beyond the row ends
-template <typename T>
-__device__ __forceinline__ bool word_interesting(const Grid<T>& g, unsigned gw, unsigned plane_words) {
-  const unsigned row = g.divW.div(gw);
-  const unsigned w = gw - row * (unsigned)g.W;
-  const unsigned i = g.divN1.div(row);
-  const unsigned j = row - i * (unsigned)g.n1;
-  const bool hi = (int)i + 1 < g.n0, hj = (int)j + 1 < g.n1, hw = (int)w + 1 < g.W;
-  const uint32_t* p = g.bits + gw;
-  const uint32_t A = p[0];
-  const int rem = g.n2 - (int)w * 32;
-  const uint32_t kpt = low_mask(rem), kp1 = low_mask(rem - 1);
-  uint32_t any_t = 0, any_1 = 0;                     // crossings towards k (kpt mask) and towards k+1 (kp1 mask)
-  {
-    const uint32_t n0 = hw ? p[1] : 0u;
-    any_1 |= A ^ __funnelshift_r(A, n0, 1);
-  }
-  if (hj) {
-    const uint32_t b = p[g.W], nb = hw ? p[g.W + 1] : 0u;
-    any_t |= A ^ b;
-    any_1 |= A ^ __funnelshift_r(b, nb, 1);
-  }
-  if (hi) {
-    const uint32_t b = p[plane_words], nb = hw ? p[plane_words + 1] : 0u;
-    any_t |= A ^ b;
-    any_1 |= A ^ __funnelshift_r(b, nb, 1);
-    if (hj) {
-      const uint32_t c = p[plane_words + g.W], nc = hw ? p[plane_words + g.W + 1] : 0u;
-      any_t |= A ^ c;
-      any_1 |= A ^ __funnelshift_r(c, nc, 1);
-    }
-  }
-  return ((any_t & kpt) | (any_1 & kp1)) != 0;
-}
+struct CsShared {
+  uint32_t own[CS_TILE], emit[CS_TILE];
+  uint32_t pv[CS_TILE], pt[CS_TILE], po[CS_TILE], pc[CS_TILE];
+  unsigned short cv[CS_TILE], ct[CS_TILE];
+  unsigned short list[CS_TILE];
+  unsigned long long warp_vt[CS_THREADS / 32], warp_act[CS_THREADS / 32];
+  unsigned long long excl_vt, excl_act;
+  unsigned tile, nint;
+};
 
 template <typename T>
-__global__ void __launch_bounds__(CS_THREADS, 3) k_count_scan(const __grid_constant__ Grid<T> g, unsigned word0,
-                                                              unsigned nwords_scan, unsigned chunk, uint2* __restrict__ wpre,
-                                                              uint2* __restrict__ wdir, unsigned long long* status,
-                                                              Counters* ctr, int nchunks) {
-  extern __shared__ uint32_t s_cnt[];                // per word of the chunk: t << 16 | v
-  __shared__ unsigned short s_list[CS_SUB];
-  __shared__ unsigned long long s_warp[CS_THREADS / 32];
-  __shared__ unsigned s_tile, s_nint;
-  if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket, 1u);
+__global__ void __launch_bounds__(CS_THREADS, 3) k_count_scan(Grid<T> gin, unsigned word0, unsigned nwords_scan,
+                                                           uint32_t* __restrict__ vbase,
+                                                           unsigned long long* __restrict__ own_id,
+                                                           uint32_t* __restrict__ own_voff,
+                                                           unsigned long long* __restrict__ cell_id,
+                                                           uint32_t* __restrict__ cell_toff, unsigned cap_own,
+                                                           unsigned cap_cell, unsigned long long* status_vt,
+                                                           unsigned long long* status_act, Counters* ctr, int ntiles) {
+  __shared__ CsShared sh;
+  Grid<T> g = gin;
+  g.any_near = 0;
+  if (threadIdx.x == 0) {
+    sh.tile = atomicAdd(&ctr->ticket, 1u);
+    sh.nint = 0;
+  }
   __syncthreads();
-  const unsigned c = s_tile;
+  const int tile = (int)sh.tile;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
   const unsigned emit_end = (unsigned)g.i_hi * plane_words;      // words below this are emitted
-  const unsigned c0 = c * chunk;
-  const unsigned cn = min(chunk, nwords_scan - c0);
+  const unsigned tile0 = (unsigned)tile * CS_TILE;
 
-  // ---- 1: counts
-  unsigned ncross = 0, ncells = 0;
-  for (unsigned sub = 0; sub < cn; sub += CS_SUB) {
-    if (threadIdx.x == 0) s_nint = 0;
-    __syncthreads();
+  // ---- A: dense quick test, 4 strided words per thread
 #pragma unroll
-    for (int q = 0; q < CS_ITEMS; ++q) {
-      const unsigned wl = (unsigned)q * CS_THREADS + threadIdx.x;
-      bool interesting = false;
-      if (sub + wl < cn) {
-        interesting = word_interesting(g, word0 + c0 + sub + wl, plane_words);
-        s_cnt[sub + wl] = 0;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, interesting);
-      unsigned base = 0;
-      if (lane == 0 && m) base = atomicAdd(&s_nint, (unsigned)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (interesting) s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)wl;
-    }
-    __syncthreads();
-    const unsigned nint = s_nint;
-    for (unsigned idx = threadIdx.x; idx < nint; idx += CS_THREADS) {
-      const unsigned wl = s_list[idx];
-      const unsigned gw = word0 + c0 + sub + wl;
+  for (int q = 0; q < CS_ITEMS; ++q) {
+    const unsigned wl = (unsigned)q * CS_THREADS + threadIdx.x;
+    const unsigned rel = tile0 + wl;
+    bool interesting = false;
+    if (rel < nwords_scan) {
       int i, j, w;
-      g.word_coords(gw, i, j, w);
-      const bool near = g.rowflag[(unsigned)i * (unsigned)g.n1 + (unsigned)j] != 0;
+      g.word_coords(word0 + rel, i, j, w);
       Planes pl;
       load_planes(g, g.bits, i, j, w, pl);
       uint32_t x[7];
-      owner_used(g, near, pl, i, j, w, x);
-      unsigned v = 0;
-#pragma unroll
-      for (int d = 0; d < 7; ++d) v += __popc(x[d]);
-      if (v) wdir[gw] = dir_pack(x);
-      unsigned t = 0;
-      if (pl.has_i1 && pl.has_j1 && i < g.i_hi) {
-        // strict crossings for owners inside the voxel range (grid_field.py:64-84)
-        unsigned nc = 0;
-        if (!near) {
-#pragma unroll
-          for (int d = 0; d < 7; ++d) nc += __popc(x[d] & pl.kp1);
-        } else {
-          uint32_t xs[7];
-          cross_words(pl, xs);
-#pragma unroll
-          for (int d = 0; d < 7; ++d) nc += __popc(xs[d] & pl.kp1);
-        }
-        uint32_t odd[6], two[6], cand;
-        tet_words(pl, nullptr, pl.kp1, odd, two, cand);
-        if (near) word_exact_fix(g, pl, i, j, w, &nc, odd, two);
-        uint32_t em = 0;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          t += __popc(odd[q]) + 2 * __popc(two[q]);
-          em |= odd[q] | two[q];
-        }
-        ncross += nc;
-        ncells += __popc(em);
-      }
-      s_cnt[sub + wl] = (t << 16) | v;
+      cross_words(pl, x);
+      interesting = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6]) != 0;
     }
+    sh.cv[wl] = 0;
+    sh.ct[wl] = 0;
+    sh.own[wl] = 0;
+    sh.emit[wl] = 0;
+    const unsigned m = __ballot_sync(0xffffffffu, interesting);
+    unsigned base = 0;
+    if (lane == 0 && m) base = atomicAdd(&sh.nint, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (interesting) sh.list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)wl;
   }
-  {
-    unsigned long long cc = ((unsigned long long)ncross << 32) | ncells;
+  __syncthreads();
+  const unsigned nint = sh.nint;
+
+  // ---- B: counts of the interesting words, one word per thread per round
+  unsigned ncross = 0, ncells = 0;
+  for (unsigned idx = threadIdx.x; idx < nint; idx += CS_THREADS) {
+    const unsigned wl = sh.list[idx];
+    const unsigned gw = word0 + tile0 + wl;
+    int i, j, w;
+    g.word_coords(gw, i, j, w);
+    g.any_near = g.rowflag[(size_t)i * g.n1 + j];
+    Planes pl;
+    load_planes(g, g.bits, i, j, w, pl);
+    uint32_t x[7];
+    owner_used(g, pl, i, j, w, x);
+    unsigned v = 0;
+    uint32_t any = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cc += __shfl_xor_sync(0xffffffffu, cc, o);
-    if (lane == 0 && cc) {
-      if (cc & 0xffffffffull) atomicAdd(&ctr->n_cells, cc & 0xffffffffull);
-      if (cc >> 32) atomicAdd(&ctr->n_cross, cc >> 32);
+    for (int d = 0; d < 7; ++d) {
+      v += __popc(x[d]);
+      any |= x[d];
     }
+    const bool cells_ok = pl.has_i1 && pl.has_j1 && i < g.i_hi;
+    unsigned t = 0;
+    uint32_t em = 0;
+    if (cells_ok) {
+      // strict crossings for owners inside the voxel range (grid_field.py:64-84)
+      if (!g.any_near) {
+#pragma unroll
+        for (int d = 0; d < 7; ++d) ncross += __popc(x[d] & pl.kp1);
+      } else {
+        uint32_t xs[7];
+        cross_words(pl, xs);
+#pragma unroll
+        for (int d = 0; d < 7; ++d) ncross += __popc(xs[d] & pl.kp1);
+      }
+      uint32_t odd[6], two[6], cand;
+      tet_words(pl, nullptr, pl.kp1, odd, two, cand);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        t += __popc(odd[q]) + 2 * __popc(two[q]);
+        em |= odd[q] | two[q];
+      }
+    }
+    if (g.any_near) count_word_exact(g, pl, i, j, w, cells_ok, ncross, t, em);
+    sh.cv[wl] = (unsigned short)v;
+    sh.ct[wl] = (unsigned short)t;
+    sh.own[wl] = gw < emit_end ? any : 0u;
+    sh.emit[wl] = em;
+    ncells += __popc(em);
+  }
+  unsigned long long cc = ((unsigned long long)ncross << 32) | ncells;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cc += __shfl_xor_sync(0xffffffffu, cc, o);
+  if (lane == 0 && cc) {
+    if (cc & 0xffffffffull) atomicAdd(&ctr->n_cells, cc & 0xffffffffull);
+    if (cc >> 32) atomicAdd(&ctr->n_cross, cc >> 32);
   }
   __syncthreads();
 
-  // ---- 2: chunk aggregate (T << 31 | V), published; exclusive prefix = sum over all earlier chunks
-  // warp q scans the contiguous words [q*per, (q+1)*per) of the chunk in step 3; its total is needed first
-  const unsigned per = ((cn + CS_THREADS - 1) / CS_THREADS) * 32u;          // multiple of 32, 8*per >= cn
-  const unsigned wbeg = min(warp * per, cn), wend = min(wbeg + per, cn);
-  unsigned long long wsum = 0;
-  for (unsigned q = wbeg + lane; q < wend; q += 32) {
-    const uint32_t e = s_cnt[q];
-    wsum += ((unsigned long long)(e >> 16) << 31) | (e & 0xffffu);
-  }
+  // ---- C: scan.  Thread t owns the 4 consecutive words 4t..4t+3 (linear order)
+  unsigned long long loc_vt = 0, loc_act = 0;
+  unsigned long long item_vt[CS_ITEMS], item_act[CS_ITEMS];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-  if (lane == 0) s_warp[warp] = wsum;
+  for (int it = 0; it < CS_ITEMS; ++it) {
+    const unsigned wl = threadIdx.x * CS_ITEMS + it;
+    item_vt[it] = ((unsigned long long)sh.ct[wl] << 31) | sh.cv[wl];
+    item_act[it] = ((unsigned long long)__popc(sh.emit[wl]) << 31) | (unsigned)__popc(sh.own[wl]);
+    loc_vt += item_vt[it];
+    loc_act += item_act[it];
+  }
+  unsigned long long inc_vt = warp_incl_scan_u64(loc_vt), inc_act = warp_incl_scan_u64(loc_act);
+  if (lane == 31) {
+    sh.warp_vt[warp] = inc_vt;
+    sh.warp_act[warp] = inc_act;
+  }
   __syncthreads();
-  unsigned long long agg = 0, woff = 0;
+  unsigned long long woff_vt = 0, woff_act = 0, blk_vt = 0, blk_act = 0;
 #pragma unroll
   for (int q = 0; q < CS_THREADS / 32; ++q) {
-    if (q < (int)warp) woff += s_warp[q];
-    agg += s_warp[q];
+    if (q < (int)warp) {
+      woff_vt += sh.warp_vt[q];
+      woff_act += sh.warp_act[q];
+    }
+    blk_vt += sh.warp_vt[q];
+    blk_act += sh.warp_act[q];
   }
-  if (threadIdx.x == 0) lb_store(&status[c], CTR_ST_VALID | agg);
-  unsigned long long pre = 0;
-  for (unsigned p = threadIdx.x; p < c; p += CS_THREADS) {
-    unsigned long long s;
-    do {
-      s = lb_load(&status[p]);
-    } while (!(s & CTR_ST_VALID));
-    pre += s & ~CTR_ST_VALID;
+  if (warp == 0) {
+    unsigned long long e = lb_lookback(status_vt, tile, blk_vt);
+    if (lane == 0) sh.excl_vt = e;
+  } else if (warp == 1) {
+    unsigned long long e = lb_lookback(status_act, tile, blk_act);
+    if (lane == 0) sh.excl_act = e;
   }
-  const unsigned long long excl = block_sum_u64(pre, s_warp);
+  __syncthreads();
+  unsigned long long run_vt = sh.excl_vt + woff_vt + inc_vt - loc_vt;
+  unsigned long long run_act = sh.excl_act + woff_act + inc_act - loc_act;
+  {
+    uint32_t vb[CS_ITEMS];
+#pragma unroll
+    for (int it = 0; it < CS_ITEMS; ++it) {
+      const unsigned wl = threadIdx.x * CS_ITEMS + it;
+      vb[it] = (uint32_t)(run_vt & 0x7fffffffull);
+      sh.pv[wl] = vb[it];
+      sh.pt[wl] = (uint32_t)(run_vt >> 31);
+      sh.po[wl] = (uint32_t)(run_act & 0x7fffffffull);
+      sh.pc[wl] = (uint32_t)(run_act >> 31);
+      run_vt += item_vt[it];
+      run_act += item_act[it];
+    }
+    const unsigned rel0 = tile0 + threadIdx.x * CS_ITEMS;
+#pragma unroll
+    for (int it = 0; it < CS_ITEMS; ++it) {
+      if (rel0 + it < nwords_scan) {
+        vbase[word0 + rel0 + it] = vb[it];
+        if (g.i_hiv > g.i_hi && word0 + rel0 + it == emit_end) ctr->v_emit = vb[it];
+      }
+    }
+  }
+  if (tile == ntiles - 1 && threadIdx.x == 0) {
+    ctr->total_vt = sh.excl_vt + blk_vt;
+    ctr->total_act = sh.excl_act + blk_act;
+  }
+  __syncthreads();
 
-  // ---- 3: warp-contiguous scan, coalesced (vbase, tbase) writes
-  unsigned long long run = excl + woff;
-  uint2* out = wpre + word0 + c0;
-  const unsigned emit_rel = emit_end - (word0 + c0);             // wraps to a huge value when emit_end is before this chunk
-  for (unsigned q0 = wbeg; q0 < wend; q0 += 32) {
-    const unsigned q = q0 + lane;
-    unsigned long long val = 0;
-    if (q < wend) {
-      const uint32_t e = s_cnt[q];
-      val = ((unsigned long long)(e >> 16) << 31) | (e & 0xffffu);
+  // ---- D: compacted owner / voxel lists
+  for (unsigned idx = threadIdx.x; idx < nint; idx += CS_THREADS) {
+    const unsigned wl = sh.list[idx];
+    uint32_t mo = sh.own[wl], me = sh.emit[wl];
+    if (!(mo | me)) continue;
+    const unsigned gw = word0 + tile0 + wl;
+    int i, j, w;
+    g.word_coords(gw, i, j, w);
+    g.any_near = g.rowflag[(size_t)i * g.n1 + j];
+    Planes pl;
+    load_planes(g, g.bits, i, j, w, pl);
+    if (mo) {
+      uint32_t x[7];
+      owner_used(g, pl, i, j, w, x);
+      unsigned vrun = sh.pv[wl], orun = sh.po[wl];
+      while (mo) {
+        const int b = __ffs(mo) - 1;
+        mo &= mo - 1;
+        const unsigned m7 = gather7(x, b);
+        if (orun < cap_own) {
+          own_id[orun] = ((unsigned long long)gw << 13) | ((unsigned)b << 8) | (((pl.P[0] >> b) & 1u) << 7) | m7;
+          own_voff[orun] = vrun;
+        }
+        ++orun;
+        vrun += __popc(m7);
+      }
     }
-    const unsigned long long inc = warp_incl_scan_u64(val);
-    if (q < wend) {
-      const unsigned long long ex = run + inc - val;
-      const uint32_t vb = (uint32_t)ex & 0x7fffffffu;
-      out[q] = make_uint2(vb, (uint32_t)(ex >> 31));
-      if (q == emit_rel && g.i_hiv > g.i_hi) ctr->v_emit = vb;
+    if (me) {
+      unsigned trun = sh.pt[wl], crun = sh.pc[wl];
+      Planes npl;
+      if (g.any_near) load_planes(g, g.nbits, i, j, w, npl);
+      while (me) {
+        const int b = __ffs(me) - 1;
+        me &= me - 1;
+        unsigned c8 = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) c8 |= ((corner_plane(pl, c) >> b) & 1u) << c;
+        unsigned emit = 0;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+          const unsigned tm = tet_mask_of(c8, t);
+          if (tm != 0 && tm != 15) emit |= 1u << t;
+        }
+        if (g.any_near) {
+          unsigned n8 = 0;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) n8 |= ((corner_plane(npl, c) >> b) & 1u) << c;
+          bool cand = false;
+#pragma unroll
+          for (int t = 0; t < 6; ++t) cand = cand || (((emit >> t) & 1u) && tet_mask_of(n8, t) == 15);
+          if (cand) emit = cell_emit_exact(g, i, j, w * 32 + b, nullptr);
+        }
+        unsigned nt = 0;
+#pragma unroll
+        for (int t = 0; t < 6; ++t)
+          if ((emit >> t) & 1u) nt += (__popc(tet_mask_of(c8, t)) == 2) ? 2u : 1u;
+        if (crun < cap_cell) {
+          cell_id[crun] = ((unsigned long long)gw << 19) | ((unsigned)b << 14) | (emit << 8) | c8;
+          cell_toff[crun] = trun;
+        }
+        ++crun;
+        trun += nt;
+      }
     }
-    run += __shfl_sync(0xffffffffu, inc, 31);
-  }
-  if (c == (unsigned)nchunks - 1 && threadIdx.x == 0) {
-    const unsigned long long tot = excl + agg;
-    ctr->total_vt = tot;
-    wpre[word0 + nwords_scan] = make_uint2((uint32_t)(tot & 0x7fffffffull), (uint32_t)(tot >> 31));   // sentinel
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stage 3: vertices.  Persistent warps; a warp takes 64 consecutive words at a time (2048 owner points, two words per
-// lane).  Each lane recomputes the used-edge words of its words into shared memory, then the warp deals the
-// segment's vertices out one per lane per round: a lane finds its word by binary search over the warp's prefix
-// sums (shuffles), the direction from the word's dirpack and the owner point as the n-th set bit of that direction's
-// word.  Consecutive lanes write consecutive vertex ids.  The id of an edge is a perfect hash of its key:
-// vbase[word] + dirbase + rank (the reference's dict dedup, tetrahedral.py:184-188, without a table).
+// Stage 3: vertices.  A warp takes 32 active owner points, then deals their 1..7 owned edges out to its
+// lanes one vertex per lane per round (balanced; consecutive lanes write consecutive vertex ids).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
-// geometry-mode arithmetic: IEEE in fp64 mode (bit-exact vs the oracle); fast approximations in fp32 mode (1e-4 rel)
-__device__ __forceinline__ double quot(double a, double b) { return a / b; }
-__device__ __forceinline__ float quot(float a, float b) { return __fdividef(a, b); }
-__device__ __forceinline__ double inv_sqrt(double a) { return 1.0 / sqrt(a); }
-__device__ __forceinline__ float inv_sqrt(float a) { return rsqrtf(a); }
-
-// central differences (one-sided on the boundary), in grid units
 template <typename T, typename G>
-__device__ __forceinline__ void grad_at(const Grid<T>& g, const T* __restrict__ c, int i, int j, int k, long long s0,
-                                        long long s1, G out[3]) {
+__device__ __forceinline__ void grad_at(const Grid<T>& g, int i, int j, int k, G out[3]) {
+  const long long s1 = g.n2, s0 = (long long)g.n1 * g.n2;
+  const T* c = g.f + ((long long)i * g.n1 + j) * g.n2 + k;
   {
     const bool lo = i > 0, hi = i < g.n0 - 1;
     G a = (G)c[hi ? s0 : 0], b = (G)c[lo ? -s0 : 0];
@@ -597,480 +583,287 @@ __device__ __forceinline__ void grad_at(const Grid<T>& g, const T* __restrict__ 
   }
 }
 
-template <typename G>
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double shfl_g(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ float shfl_g(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
 struct Xform {
-  G origin[3], delta[3], inv_delta[3];
-  G den_tol;                 // largest G <= 1e-8 (np.allclose(fhigh - flow, 0), tetrahedral.py:483)
+  double origin[3], delta[3];
 };
 
-// lane o of the warp = last lane whose exclusive prefix <= slot (prefixes are non-decreasing; lanes with a
-// zero count are skipped because the next lane has the same prefix)
-__device__ __forceinline__ int warp_find_owner(unsigned excl, unsigned slot) {
-  int o = 0;
-#pragma unroll
-  for (int step = 16; step > 0; step >>= 1) {
-    const int probe = o + step;
-    const unsigned e = __shfl_sync(0xffffffffu, excl, probe & 31);
-    if (probe < 32 && e <= slot) o = probe;
-  }
-  return o;
-}
-
-constexpr int EV_THREADS = 256;
-constexpr int EV_WARPS = EV_THREADS / 32;
-constexpr int EV_BLOCKS_PER_SM = 4;
-constexpr int SEG_WORDS = 64;                        // words per warp step in stages 3 and 4 (two per lane)
-constexpr unsigned SEG_BATCH = 4;                    // segments claimed per atomic
-
 template <typename T, typename G>
-__global__ void __launch_bounds__(EV_THREADS, EV_BLOCKS_PER_SM)
-    k_emit_verts(const __grid_constant__ Grid<T> g, unsigned word0, unsigned nwords_emit, const uint2* __restrict__ wpre,
-                 const uint2* __restrict__ wdir, const __grid_constant__ Xform<G> xf, G* __restrict__ verts,
-                 G* __restrict__ normals, unsigned long long* __restrict__ keys, uint8_t* __restrict__ lowmin, unsigned cap_v,
-                 unsigned* claim) {
-  __shared__ uint32_t s_x[EV_WARPS][SEG_WORDS][10];  // 7 used-edge words, the word's own low bits, dirpack
-  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-  uint32_t (*sx)[10] = s_x[warp];
+__global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned long long* __restrict__ own_id,
+                                                    const uint32_t* __restrict__ own_voff, const Counters* __restrict__ ctr,
+                                                    unsigned cap_own, unsigned cap_v, Xform xf,
+                                                    G* __restrict__ verts, G* __restrict__ normals,
+                                                    unsigned long long* __restrict__ keys, uint8_t* __restrict__ lowmin) {
+  // the list length comes from the device counters: the launch may precede the host's read of the counts
+  const unsigned n_own = min((unsigned)(ctr->total_act & 0x7fffffffull), cap_own);
+  const unsigned lane = lane_id();
+  const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;          // owner index of this lane
+  const unsigned warp_first = a - lane;
+  if (warp_first >= n_own) return;
+  const bool have = a < n_own;
+  const unsigned long long oid = have ? own_id[a] : 0ull;
+  const unsigned voff = have ? own_voff[a] : 0u;
+  const unsigned m7 = (unsigned)oid & 127u;
+  int i = 0, j = 0, w = 0;
+  g.word_coords((unsigned)(oid >> 13), i, j, w);
+  const int k = w * 32 + (int)((oid >> 8) & 31u);
+  G fp = (G)0, gp[3] = {(G)0, (G)0, (G)0};
+  if (have) {
+    fp = (G)g.f[((long long)i * g.n1 + j) * g.n2 + k];
+    if (normals) grad_at<T, G>(g, i, j, k, gp);
+  }
+  const unsigned cnt = __popc(m7);
+  const unsigned incl = warp_incl_scan_u32(cnt);
+  const unsigned excl = incl - cnt;
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  const unsigned vfirst = __shfl_sync(0xffffffffu, voff, 0);        // ids of a warp's vertices are consecutive
   const G v = (G)g.v;
-  const long long s1 = g.n2, s0 = (long long)g.n1 * g.n2;
-  const unsigned nseg = (nwords_emit + SEG_WORDS - 1) / SEG_WORDS;
-  // segments are claimed in batches of SEG_BATCH by an atomic counter (work per segment varies by orders of magnitude)
-  for (unsigned seg = 0, seg_end = 0;; ++seg) {
-    if (seg == seg_end) {
-      if (lane == 0) seg = atomicAdd(claim, SEG_BATCH);
-      seg = __shfl_sync(0xffffffffu, seg, 0);
-      seg_end = seg + SEG_BATCH;
-    }
-    if (seg >= nseg) break;
-    const unsigned seg0 = seg * SEG_WORDS;
-    unsigned cnt[2] = {0, 0}, vb0 = 0;
-    {
-      const unsigned rel = seg0 + lane * 2;
-      if (rel < nwords_emit) {
-        const unsigned gw = word0 + rel;
-        vb0 = wpre[gw].x;
-        const unsigned a1 = wpre[gw + 1].x;
-        cnt[0] = a1 - vb0;
-        if (rel + 1 < nwords_emit) cnt[1] = wpre[gw + 2].x - a1;
-      }
-    }
-    const unsigned both = cnt[0] + cnt[1];
-    const unsigned incl = warp_incl_scan_u32(both);
-    const unsigned excl = incl - both;
-    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) continue;
-    const unsigned vfirst = __shfl_sync(0xffffffffu, vb0, 0);       // ids of a segment's vertices are consecutive
-    __syncwarp();                                                   // previous segment's readers are done with sx
+  for (unsigned base = 0; base < total; base += 32) {
+    const unsigned vtx = base + lane;
+    const bool act = vtx < total;
+    // owner o = last lane whose exclusive prefix <= vtx  (binary search over the warp's prefixes)
+    int o = 0;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      if (!cnt[q]) continue;
-      const unsigned gw = word0 + seg0 + lane * 2 + q;
-      int i, j, w;
-      g.word_coords(gw, i, j, w);
-      const bool near = g.rowflag[(unsigned)i * (unsigned)g.n1 + (unsigned)j] != 0;
-      Planes pl;
-      load_planes(g, g.bits, i, j, w, pl);
-      uint32_t x[7];
-      owner_used(g, near, pl, i, j, w, x);
-      const uint2 dp = wdir[gw];
-      uint32_t* dst = sx[lane * 2 + q];
-#pragma unroll
-      for (int d = 0; d < 7; ++d) dst[d] = x[d];
-      dst[7] = pl.P[0];
-      dst[8] = dp.x;
-      dst[9] = dp.y;
+    for (int step = 16; step > 0; step >>= 1) {
+      const int probe = o + step;
+      const unsigned e = __shfl_sync(0xffffffffu, excl, probe & 31);
+      if (probe < 32 && e <= vtx) o = probe;
     }
-    __syncwarp();
-    for (unsigned base = 0; base < total; base += 32) {
-      const unsigned vtx = base + lane;
-      const int o = warp_find_owner(excl, vtx);
-      const unsigned o_excl = __shfl_sync(0xffffffffu, excl, o);
-      const unsigned o_c0 = __shfl_sync(0xffffffffu, cnt[0], o);
-      const unsigned id = vfirst + vtx;
-      if (vtx >= total || id >= cap_v) continue;
-      unsigned r = vtx - o_excl;
-      const unsigned second = r >= o_c0 ? 1u : 0u;
-      r -= second ? o_c0 : 0u;
-      const unsigned widx = (unsigned)o * 2u + second;
-      const unsigned gw = word0 + seg0 + widx;
-      const uint32_t* sw = sx[widx];
-      const uint2 dp = make_uint2(sw[8], sw[9]);
-      // direction index q = number of prefixes <= r; owner point = (r - dirbase)-th set bit of that direction's word
-      int q = 0;
-      unsigned qb = 0;
+    // owners with zero vertices never appear in the list (cnt >= 1), so prefixes are strictly increasing
+    const unsigned o_excl = __shfl_sync(0xffffffffu, excl, o);
+    const unsigned o_m7 = __shfl_sync(0xffffffffu, m7, o);
+    const unsigned o_lo = __shfl_sync(0xffffffffu, (unsigned)((oid >> 7) & 1u), o);
+    const int oi = __shfl_sync(0xffffffffu, i, o), oj = __shfl_sync(0xffffffffu, j, o), ok = __shfl_sync(0xffffffffu, k, o);
+    const G ofp = shfl_g(fp, o);
+    G ogp[3];
+    if (normals) {
+      ogp[0] = shfl_g(gp[0], o);
+      ogp[1] = shfl_g(gp[1], o);
+      ogp[2] = shfl_g(gp[2], o);
+    }
+    if (!act || (size_t)vfirst + vtx >= cap_v) continue;
+    const int d = (int)__fns(o_m7, 0, (int)(vtx - o_excl) + 1) + 1;   // (n+1)-th set bit -> direction 1..7
+    const bool p_low = o_lo != 0;
+    const size_t id = (size_t)vfirst + vtx;
+    const int di = (d >> 2) & 1, dj = (d >> 1) & 1, dk = d & 1;
+    const G fq = (G)g.f[((long long)(oi + di) * g.n1 + (oj + dj)) * g.n2 + (ok + dk)];
+    // tetrahedral.py:476-487: key oriented (low, high) by value; ratio = (z-flow)/(fhigh-flow), 0.5 if ~0
+    const G flow = p_low ? ofp : fq, fhigh = p_low ? fq : ofp;
+    const G den = fhigh - flow;
+    const G ratio = (fabs((double)den) <= 1e-8) ? (G)0.5 : (v - flow) / den;
+    // x = low + ratio*(high - low); (high-low) is +-1 or 0 per axis so the product is exact
+    const G step = p_low ? ratio : -ratio;
+    const int pl[3] = {p_low ? oi : oi + di, p_low ? oj : oj + dj, p_low ? ok : ok + dk};
+    const int dd[3] = {di, dj, dk};
 #pragma unroll
-      for (int t = 1; t <= 6; ++t) {
-        const unsigned cb = dir_base(dp, t);
-        if (cb <= r) {
-          q = t;
-          qb = cb;
-        }
-      }
-      const int b = nth_set_bit(sw[q], r - qb);
-      const int d = q + 1;
-      int oi, oj, ow;
-      g.word_coords(gw, oi, oj, ow);
-      const int ok = ow * 32 + b;
-      const bool p_low = ((sw[7] >> b) & 1u) != 0;
-      const int di = (d >> 2) & 1, dj = (d >> 1) & 1, dk = d & 1;
-      const T* cp = g.f + ((long long)oi * g.n1 + oj) * g.n2 + ok;
-      const T* cq = cp + (di ? s0 : 0) + (dj ? s1 : 0) + dk;
-      // all samples this vertex needs are requested before the first one is used (one memory latency per round)
-      const bool inner = normals && oi > 0 && oi + di < g.n0 - 1 && oj > 0 && oj + dj < g.n1 - 1 && ok > 0 && ok + dk < g.n2 - 1;
-      T sp[6], sq[6];
-      if (inner) {
-        sp[0] = cp[s0]; sp[1] = cp[-s0]; sp[2] = cp[s1]; sp[3] = cp[-s1]; sp[4] = cp[1]; sp[5] = cp[-1];
-        sq[0] = cq[s0]; sq[1] = cq[-s0]; sq[2] = cq[s1]; sq[3] = cq[-s1]; sq[4] = cq[1]; sq[5] = cq[-1];
-      }
-      const G fp = (G)*cp, fq = (G)*cq;
-      // tetrahedral.py:476-487: key oriented (low, high) by value; ratio = (z-flow)/(fhigh-flow), 0.5 if ~0
-      const G flow = p_low ? fp : fq, fhigh = p_low ? fq : fp;
-      const G den = fhigh - flow;
-      const G ratio = (fabs(den) <= xf.den_tol) ? (G)0.5 : quot(v - flow, den);
-      // x = low + ratio*(high - low); (high-low) is +-1 or 0 per axis so the product is exact
-      const G step = p_low ? ratio : -ratio;
-      const int pl[3] = {p_low ? oi : oi + di, p_low ? oj : oj + dj, p_low ? ok : ok + dk};
-      const int dd[3] = {di, dj, dk};
-      G* vo = verts + (size_t)id * 3;
+    for (int ax = 0; ax < 3; ++ax) {
+      const G b0 = (ax == 0) ? (G)((long long)pl[0] + g.plane_offset) : (G)pl[ax];
+      const G x = dd[ax] ? add_rn(b0, step) : b0;
+      verts[id * 3 + ax] = add_rn(mul_rn(x, (G)xf.delta[ax]), (G)xf.origin[ax]);   // grid_field.py:93
+    }
+    if (normals) {
+      G gq[3];
+      grad_at<T, G>(g, oi + di, oj + dj, ok + dk, gq);
+      G nn[3], len2 = 0;
 #pragma unroll
       for (int ax = 0; ax < 3; ++ax) {
-        const G c0 = (ax == 0) ? (G)((long long)pl[0] + g.plane_offset) : (G)pl[ax];
-        const G xx = dd[ax] ? add_rn(c0, step) : c0;
-        vo[ax] = add_rn(mul_rn(xx, xf.delta[ax]), xf.origin[ax]);   // grid_field.py:93
+        const G gl = p_low ? ogp[ax] : gq[ax], gh = p_low ? gq[ax] : ogp[ax];
+        nn[ax] = add_rn(gl, mul_rn(ratio, gh - gl)) / (G)xf.delta[ax];
+        len2 = add_rn(len2, mul_rn(nn[ax], nn[ax]));
       }
-      if (normals) {
-        G gp[3], gq[3];
-        if (inner) {
+      const G len = sqrt(len2);
+      const G inv = len > (G)0 ? (G)1 / len : (G)0;
 #pragma unroll
-          for (int ax = 0; ax < 3; ++ax) {
-            gp[ax] = ((G)sp[2 * ax] - (G)sp[2 * ax + 1]) * (G)0.5;
-            gq[ax] = ((G)sq[2 * ax] - (G)sq[2 * ax + 1]) * (G)0.5;
-          }
-        } else {
-          grad_at<T, G>(g, cp, oi, oj, ok, s0, s1, gp);
-          grad_at<T, G>(g, cq, oi + di, oj + dj, ok + dk, s0, s1, gq);
-        }
-        G nn[3], len2 = 0;
-#pragma unroll
-        for (int ax = 0; ax < 3; ++ax) {
-          const G gl = p_low ? gp[ax] : gq[ax], gh = p_low ? gq[ax] : gp[ax];
-          nn[ax] = add_rn(gl, mul_rn(ratio, gh - gl)) * xf.inv_delta[ax];
-          len2 = add_rn(len2, mul_rn(nn[ax], nn[ax]));
-        }
-        const G inv = len2 > (G)0 ? inv_sqrt(len2) : (G)0;
-        G* no = normals + (size_t)id * 3;
-#pragma unroll
-        for (int ax = 0; ax < 3; ++ax) no[ax] = nn[ax] * inv;
-      }
-      if (keys) {
-        const long long lin = (((long long)oi + g.plane_offset) * g.n1 + oj) * g.n2 + ok;
-        keys[id] = ((unsigned long long)lin << 3) | (unsigned)d;
-        lowmin[id] = p_low ? 1 : 0;
-      }
+      for (int ax = 0; ax < 3; ++ax) normals[id * 3 + ax] = nn[ax] * inv;
+    }
+    if (keys) {
+      const long long lin = (((long long)oi + g.plane_offset) * g.n1 + oj) * g.n2 + ok;
+      keys[id] = ((unsigned long long)lin << 3) | (unsigned)d;
+      lowmin[id] = p_low ? 1 : 0;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stage 4: triangles.  Same persistent warp-per-64-words expansion, one lane per emitting voxel.  The id of each of
-// the voxel's 19 edges is vbase[owner word] + dirbase + rank of the owner bit in that direction's crossing word, all
-// from the 2x2 rows of bit words the voxel touches.  A 256-entry table turns the 8 corner bits into the voxel's
-// triangle list (6 Kuhn tets, tetrahedral.py:32-39,554-595; wound towards the high side); the triangles of a
-// round are staged in shared memory and written out coalesced.
+// Stage 4: triangles.  One thread per active voxel.  The ids of the voxel's 19 edges come from
+// vbase[word] + rank of the edge among the used edges of its owner's word (popcounts of crossing words).
 // ------------------------------------------------------------------------------------------------
 constexpr int ET_THREADS = 128;
-constexpr int ET_WARPS = ET_THREADS / 32;
-constexpr int ET_BLOCKS_PER_SM = 6;
-__constant__ uint32_t c_tri_packed[6 * 16];    // per tet: n | slot0<<2 | slot1<<7 | ... (6 slots x 5 bits)
+__constant__ uint32_t c_tri_packed[6 * 16];    // n | slot0<<2 | slot1<<7 | ... (6 slots x 5 bits)
 
-// edge slot e (tables.h CTR_EDGE3_*): owner corner s = a*4 + c*2 + dk and direction d, as compile-time constants
-__device__ __forceinline__ constexpr int edge_s(int e) {
-  return e < 7 ? 0 : e < 10 ? 1 : e < 13 ? 2 : e < 14 ? 3 : e < 17 ? 4 : e < 18 ? 5 : 6;
-}
-__device__ __forceinline__ constexpr int edge_d(int e) {
-  return e < 7 ? e + 1 : e == 7 ? 2 : e == 8 ? 4 : e == 9 ? 6 : e == 10 ? 1 : e == 11 ? 4 : e == 12 ? 5 : e == 13 ? 4
-         : e == 14 ? 1 : e == 15 ? 2 : e == 16 ? 3 : e == 17 ? 2 : 1;
-}
-
-// emitting-voxel word of (i, j, w) and the bit-sliced per-voxel triangle counts
+// exact (allclose-aware) owner ids of a voxel: the rare path, kept out of line
 template <typename T>
-__device__ __forceinline__ uint32_t emit_word(const Grid<T>& g, bool near, int i, int j, int w, uint32_t* s4) {
-  Planes pl;
-  load_planes(g, g.bits, i, j, w, pl);
-  if (!(pl.has_i1 && pl.has_j1 && i < g.i_hi)) {
-    if (s4) s4[0] = s4[1] = s4[2] = s4[3] = 0;
-    return 0;
-  }
-  uint32_t odd[6], two[6], cand;
-  tet_words(pl, nullptr, pl.kp1, odd, two, cand);
-  if (near) word_exact_fix(g, pl, i, j, w, nullptr, odd, two);
-  if (s4) slice_tris(odd, two, s4);
-  return odd[0] | odd[1] | odd[2] | odd[3] | odd[4] | odd[5] | two[0] | two[1] | two[2] | two[3] | two[4] | two[5];
-}
-
-// used-edge words of the voxel's four owner rows when some sample nearby is allclose to the isovalue (rare)
-template <typename T>
-__device__ __noinline__ void rows_used_exact(const Grid<T>& g, int i, int j, int w, uint32_t X[4][7]) {
+__device__ __noinline__ void owner_ids_exact(const Grid<T>& g, const uint32_t* __restrict__ vbase, int i, int j, int w, int b,
+                                             unsigned idb[8], unsigned msk[8]) {
+  const uint32_t below = (1u << b) - 1u;
   for (int ab = 0; ab < 4; ++ab) {
+    const int ii = i + (ab >> 1), jj = j + (ab & 1);
     Planes pl;
-    load_planes(g, g.bits, i + (ab >> 1), j + (ab & 1), w, pl);
-    owner_used(g, true, pl, i + (ab >> 1), j + (ab & 1), w, X[ab]);
+    load_planes(g, g.bits, ii, jj, w, pl);
+    uint32_t u[7];
+    owner_used(g, pl, ii, jj, w, u);
+    const unsigned wi = ((unsigned)ii * (unsigned)g.n1 + (unsigned)jj) * (unsigned)g.W + (unsigned)w;
+    unsigned rank = 0;
+    for (int d = 0; d < 7; ++d) rank += __popc(u[d] & below);
+    const unsigned m0 = gather7(u, b);
+    const unsigned id0 = vbase[wi] + rank;
+    unsigned m1, id1;
+    if (b < 31) {
+      m1 = gather7(u, b + 1);
+      id1 = id0 + __popc(m0);
+    } else {
+      Planes pn;
+      load_planes(g, g.bits, ii, jj, w + 1, pn);
+      uint32_t un[7];
+      owner_used(g, pn, ii, jj, w + 1, un);
+      m1 = gather7(un, 0);
+      id1 = vbase[wi + 1];
+    }
+    idb[ab * 2 + 0] = id0;
+    msk[ab * 2 + 0] = m0;
+    idb[ab * 2 + 1] = id1;
+    msk[ab * 2 + 1] = m1;
   }
 }
 
-// exact emitting-tet mask of a voxel in a near row (rare)
 template <typename T>
-__device__ __noinline__ unsigned cell_emit_near(const Grid<T>& g, int i, int j, int w, int b, unsigned c8, bool* exact) {
-  unsigned emit = 0;
+__global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> gin, const unsigned long long* __restrict__ cell_id,
+                                                          const uint32_t* __restrict__ cell_toff, const Counters* __restrict__ ctr,
+                                                          unsigned cap_cell, unsigned cap_t,
+                                                          const uint32_t* __restrict__ vbase, int* __restrict__ tris) {
+  const unsigned n_cells = min((unsigned)(ctr->total_act >> 31), cap_cell);
+  __shared__ unsigned s_ids[19][ET_THREADS];
+  __shared__ uint32_t s_tab[96];
+  Grid<T> g = gin;
+  if (threadIdx.x < 96) s_tab[threadIdx.x] = c_tri_packed[threadIdx.x];
+  __syncthreads();
+  unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_cells) return;
+  const unsigned long long cid = cell_id[a];
+  const unsigned c8 = (unsigned)cid & 255u, emit = (unsigned)(cid >> 8) & 63u;
+  const int b = (int)((cid >> 14) & 31u);
+  int i, j, w;
+  g.word_coords((unsigned)(cid >> 19), i, j, w);
+  g.any_near = g.rowflag[(size_t)i * g.n1 + j];
+
+  unsigned idb[8], msk[8];   // owner (first vertex id, mask7); index = corner s = a*4 + b*2 + dk
+  if (g.any_near) {
+    owner_ids_exact(g, vbase, i, j, w, b, idb, msk);
+  } else {
+    // rows (i+a, j+c), a,c in 0..2: word w (R) and the word after it (N)
+    uint32_t R[3][3], N[3][3];
+    const bool next_ok = (w + 1 < g.W);
+#pragma unroll
+    for (int ra = 0; ra < 3; ++ra)
+#pragma unroll
+      for (int rc = 0; rc < 3; ++rc) {
+        const bool ok = (i + ra < g.n0) && (j + rc < g.n1);
+        uint32_t r = 0, nx = 0;
+        if (ok) {
+          const uint32_t* p = g.bits + ((size_t)(i + ra) * g.n1 + (j + rc)) * g.W + w;
+          r = p[0];
+          if (next_ok) nx = p[1];
+        }
+        R[ra][rc] = r;
+        N[ra][rc] = nx;
+      }
+    const int rem = g.n2 - w * 32;
+    const uint32_t kpt = low_mask(rem), kp1 = low_mask(rem - 1);
+    const uint32_t below = (1u << b) - 1u;
+    const bool nkpt = (rem - 32) > 0, nkp1 = (rem - 33) > 0;       // validity of bit 0 of the next word
+#pragma unroll
+    for (int ab = 0; ab < 4; ++ab) {
+      const int ra = ab >> 1, rc = ab & 1;
+      const uint32_t vi = (i + ra + 1 < g.n0) ? 0xffffffffu : 0u, vj = (j + rc + 1 < g.n1) ? 0xffffffffu : 0u;
+      const uint32_t A = R[ra][rc];
+      uint32_t u[7];
+#define CTR_S(x, y) ((R[x][y] >> 1) | (N[x][y] << 31))
+      u[0] = (A ^ CTR_S(ra, rc)) & kp1;
+      u[1] = (A ^ R[ra][rc + 1]) & kpt & vj;
+      u[2] = (A ^ CTR_S(ra, rc + 1)) & kp1 & vj;
+      u[3] = (A ^ R[ra + 1][rc]) & kpt & vi;
+      u[4] = (A ^ CTR_S(ra + 1, rc)) & kp1 & vi;
+      u[5] = (A ^ R[ra + 1][rc + 1]) & kpt & vi & vj;
+      u[6] = (A ^ CTR_S(ra + 1, rc + 1)) & kp1 & vi & vj;
+#undef CTR_S
+      const unsigned wi = ((unsigned)(i + ra) * (unsigned)g.n1 + (unsigned)(j + rc)) * (unsigned)g.W + (unsigned)w;
+      unsigned rank = 0;
+#pragma unroll
+      for (int d = 0; d < 7; ++d) rank += __popc(u[d] & below);
+      const unsigned m0 = gather7(u, b);
+      const unsigned id0 = vbase[wi] + rank;
+      unsigned m1, id1;
+      if (b < 31) {
+        m1 = gather7(u, b + 1);
+        id1 = id0 + __popc(m0);
+      } else {
+        // k+1 is bit 0 of the next word (it exists: the voxel is in range); its k+1 neighbour is bit 1
+        const uint32_t A1 = N[ra][rc] & 1u;
+        const uint32_t vi1 = vi & 1u, vj1 = vj & 1u;
+        const uint32_t p1 = nkpt ? 1u : 0u, q1 = nkp1 ? 1u : 0u;
+        m1 = ((A1 ^ ((N[ra][rc] >> 1) & 1u)) & q1) | (((A1 ^ (N[ra][rc + 1] & 1u)) & p1 & vj1) << 1) |
+             (((A1 ^ ((N[ra][rc + 1] >> 1) & 1u)) & q1 & vj1) << 2) | (((A1 ^ (N[ra + 1][rc] & 1u)) & p1 & vi1) << 3) |
+             (((A1 ^ ((N[ra + 1][rc] >> 1) & 1u)) & q1 & vi1) << 4) |
+             (((A1 ^ (N[ra + 1][rc + 1] & 1u)) & p1 & vi1 & vj1) << 5) |
+             (((A1 ^ ((N[ra + 1][rc + 1] >> 1) & 1u)) & q1 & vi1 & vj1) << 6);
+        id1 = vbase[wi + 1];
+      }
+      idb[ab * 2 + 0] = id0;
+      msk[ab * 2 + 0] = m0;
+      idb[ab * 2 + 1] = id1;
+      msk[ab * 2 + 1] = m1;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 19; ++e) {
+    const int s = c_edge_s[e], d = c_edge_d[e];
+    s_ids[e][threadIdx.x] = idb[s] + __popc(msk[s] & ((1u << (d - 1)) - 1u));
+  }
+  size_t o = cell_toff[a];
+#pragma unroll
   for (int t = 0; t < 6; ++t) {
-    const unsigned tm = tet_mask_of(c8, t);
-    if (tm != 0 && tm != 15) emit |= 1u << t;
-  }
-  Planes npl;
-  load_planes(g, g.nbits, i, j, w, npl);
-  unsigned n8 = 0;
-  for (int c = 0; c < 8; ++c) n8 |= ((corner_plane(npl, c) >> b) & 1u) << c;
-  bool cand = false;
-  for (int t = 0; t < 6; ++t) cand = cand || (((emit >> t) & 1u) && tet_mask_of(n8, t) == 15);
-  *exact = cand;
-  if (cand) emit = cell_emit_exact(g, i, j, w * 32 + b, nullptr);
-  return emit;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(ET_THREADS, ET_BLOCKS_PER_SM)
-    k_emit_tris(const __grid_constant__ Grid<T> g, unsigned word0, unsigned nwords_emit, const uint2* __restrict__ wpre,
-                const uint2* __restrict__ wdir, const uint32_t* __restrict__ vox_tab, int* __restrict__ tris, unsigned cap_t,
-                unsigned* claim) {
-  __shared__ unsigned s_ids[ET_WARPS][19][32];
-  __shared__ int s_stage[ET_WARPS][32 * 12 * 3];
-  __shared__ uint32_t s_ew[ET_WARPS][SEG_WORDS][6];   // emitting-voxel word, 4 bit planes of per-voxel triangle counts, tbase
-  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-  uint32_t (*ew)[6] = s_ew[warp];
-  unsigned (*ids)[32] = s_ids[warp];
-  int* stage = s_stage[warp];
-  const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
-  const unsigned uW = (unsigned)g.W;
-  const size_t gcap = (size_t)cap_t * 3;
-  const unsigned nseg = (nwords_emit + SEG_WORDS - 1) / SEG_WORDS;
-  for (unsigned seg = 0, seg_end = 0;; ++seg) {
-    if (seg == seg_end) {
-      if (lane == 0) seg = atomicAdd(claim, SEG_BATCH);
-      seg = __shfl_sync(0xffffffffu, seg, 0);
-      seg_end = seg + SEG_BATCH;
+    if (!((emit >> t) & 1u)) continue;
+    const uint32_t e = s_tab[t * 16 + tet_mask_of(c8, t)];
+    if (o + (e & 3u) > cap_t) break;
+    int* dst = tris + o * 3;
+    dst[0] = (int)s_ids[(e >> 2) & 31u][threadIdx.x];
+    dst[1] = (int)s_ids[(e >> 7) & 31u][threadIdx.x];
+    dst[2] = (int)s_ids[(e >> 12) & 31u][threadIdx.x];
+    if ((e & 3u) == 2u) {
+      dst[3] = (int)s_ids[(e >> 17) & 31u][threadIdx.x];
+      dst[4] = (int)s_ids[(e >> 22) & 31u][threadIdx.x];
+      dst[5] = (int)s_ids[(e >> 27) & 31u][threadIdx.x];
     }
-    if (seg >= nseg) break;
-    const unsigned seg0 = seg * SEG_WORDS;
-    unsigned tcnt[2] = {0, 0}, tb[2] = {0, 0};
-    {
-      const unsigned rel = seg0 + lane * 2;
-      if (rel < nwords_emit) {
-        const unsigned gw = word0 + rel;
-        tb[0] = wpre[gw].y;
-        tb[1] = wpre[gw + 1].y;
-        tcnt[0] = tb[1] - tb[0];
-        if (rel + 1 < nwords_emit) tcnt[1] = wpre[gw + 2].y - tb[1];
-      }
-    }
-    if (!__any_sync(0xffffffffu, (tcnt[0] | tcnt[1]) != 0)) continue;
-    __syncwarp();                                                   // previous segment's readers are done with ew
-    unsigned ccnt[2] = {0, 0};
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      if (!tcnt[q]) continue;
-      const unsigned gw = word0 + seg0 + lane * 2 + q;
-      int i, j, w;
-      g.word_coords(gw, i, j, w);
-      const bool near = g.rowflag[(unsigned)i * (unsigned)g.n1 + (unsigned)j] != 0;
-      uint32_t s4[4];
-      const uint32_t em = emit_word(g, near, i, j, w, s4);
-      uint32_t* dst = ew[lane * 2 + q];
-      dst[0] = em;
-      dst[1] = s4[0];
-      dst[2] = s4[1];
-      dst[3] = s4[2];
-      dst[4] = s4[3];
-      dst[5] = tb[q];
-      ccnt[q] = __popc(em);
-    }
-    __syncwarp();
-    const unsigned both = ccnt[0] + ccnt[1];
-    const unsigned incl = warp_incl_scan_u32(both);
-    const unsigned excl = incl - both;
-    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-    for (unsigned base = 0; base < total; base += 32) {
-      const unsigned slot = base + lane;
-      const bool act = slot < total;
-      const int o = warp_find_owner(excl, slot);
-      const unsigned o_excl = __shfl_sync(0xffffffffu, excl, o);
-      const unsigned o_c0 = __shfl_sync(0xffffffffu, ccnt[0], o);
-      unsigned toff = 0, nt = 0, c8 = 0, emit = 0;
-      bool table_path = true;
-      if (act) {
-        unsigned r = slot - o_excl;
-        const unsigned second = r >= o_c0 ? 1u : 0u;
-        r -= second ? o_c0 : 0u;
-        const unsigned widx = (unsigned)o * 2u + second;
-        const unsigned gw = word0 + seg0 + widx;
-        const uint32_t* e5 = ew[widx];
-        const int b = nth_set_bit(e5[0], r);
-        const uint32_t below = (1u << b) - 1u;
-        toff = e5[5] + __popc(e5[1] & below) + 2u * __popc(e5[2] & below) + 4u * __popc(e5[3] & below) +
-               8u * __popc(e5[4] & below);
-        nt = ((e5[1] >> b) & 1u) | (((e5[2] >> b) & 1u) << 1) | (((e5[3] >> b) & 1u) << 2) | (((e5[4] >> b) & 1u) << 3);
-        const unsigned row = g.divW.div(gw);
-        const unsigned w = gw - row * uW;
-        const bool near = g.rowflag[row] != 0;
-        // the voxel's 2x2 rows: word w (P) and the word after it; S = the same rows shifted by one sample in k
-        const bool next_ok = (w + 1 < uW);
-        const unsigned wi[4] = {gw, gw + uW, gw + plane_words, gw + plane_words + uW};
-        uint32_t P[4], S[4];
-#pragma unroll
-        for (int ab = 0; ab < 4; ++ab) {
-          P[ab] = g.bits[wi[ab]];
-          const uint32_t nx = next_ok ? g.bits[wi[ab] + 1] : 0u;
-          S[ab] = __funnelshift_r(P[ab], nx, 1);
-          c8 |= (__funnelshift_r(P[ab], nx, b) & 3u) << (ab * 2);    // bits b, b+1 of the row = corners (ab, dk)
-        }
-        unsigned vb[4], vb1[4];
-        uint2 dp[4], dp1[4];
-#pragma unroll
-        for (int ab = 0; ab < 4; ++ab) {
-          vb[ab] = wpre[wi[ab]].x;
-          dp[ab] = wdir[wi[ab]];
-        }
-        // used-edge words per owner row (index ab) and direction (index d-1); only the 14 that voxel edges use
-        uint32_t X[4][7];
-        if (near) {
-          const unsigned i = g.divN1.div(row);
-          rows_used_exact(g, (int)i, (int)(row - i * (unsigned)g.n1), (int)w, X);
-        } else {
-          X[0][0] = P[0] ^ S[0]; X[0][1] = P[0] ^ P[1]; X[0][2] = P[0] ^ S[1]; X[0][3] = P[0] ^ P[2];
-          X[0][4] = P[0] ^ S[2]; X[0][5] = P[0] ^ P[3]; X[0][6] = P[0] ^ S[3];
-          X[1][0] = P[1] ^ S[1]; X[1][3] = P[1] ^ P[3]; X[1][4] = P[1] ^ S[3];
-          X[2][0] = P[2] ^ S[2]; X[2][1] = P[2] ^ P[3]; X[2][2] = P[2] ^ S[3];
-          X[3][0] = P[3] ^ S[3];
-        }
-        // owner points at k+1: bit b+1 of the same word, or (b == 31) bit 0 of the next word with rank 0
-        uint32_t below1 = below | (1u << b);
-        if (b == 31) {
-          below1 = 0u;
-#pragma unroll
-          for (int ab = 0; ab < 3; ++ab) {
-            vb1[ab] = wpre[wi[ab] + 1].x;
-            dp1[ab] = wdir[wi[ab] + 1];
-          }
-        } else {
-#pragma unroll
-          for (int ab = 0; ab < 3; ++ab) {
-            vb1[ab] = vb[ab];
-            dp1[ab] = dp[ab];
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < 19; ++e) {
-          const int s = edge_s(e), d = edge_d(e);
-          const int ab = s >> 1;
-          unsigned id;
-          if (s & 1) id = vb1[ab] + dir_base(dp1[ab], d - 1) + __popc(X[ab][d - 1] & below1);
-          else id = vb[ab] + dir_base(dp[ab], d - 1) + __popc(X[ab][d - 1] & below);
-          ids[e][lane] = id;
-        }
-        if (near) {
-          const unsigned i = g.divN1.div(row);
-          bool exact;
-          emit = cell_emit_near(g, (int)i, (int)(row - i * (unsigned)g.n1), (int)w, b, c8, &exact);
-          table_path = !exact;
-        }
-      }
-      // stage this round's triangles (contiguous in the output: voxels are in word/bit order) and write them coalesced
-      const unsigned nact = min(32u, total - base);
-      const unsigned first = __shfl_sync(0xffffffffu, toff, 0);
-      const unsigned end = __shfl_sync(0xffffffffu, toff + nt, (int)nact - 1);
-      if (act) {
-        int* dst = stage + (toff - first) * 3u;
-        if (table_path) {
-          const uint32_t* tab = vox_tab + c8 * 12;
-          for (unsigned t = 0; t < nt; ++t) {
-            const uint32_t e = __ldg(tab + t);          // three byte offsets into this lane's column of ids
-            const char* col = (const char*)&ids[0][lane];
-            dst[0] = *(const int*)(col + (e & 0xfffu));
-            dst[1] = *(const int*)(col + ((e >> 12) & 0xfffu));
-            dst[2] = *(const int*)(col + (e >> 24 << 4));
-            dst += 3;
-          }
-        } else {
-          for (int t = 0; t < 6; ++t) {
-            if (!((emit >> t) & 1u)) continue;
-            const uint32_t e = c_tri_packed[t * 16 + tet_mask_of(c8, t)];
-            dst[0] = (int)ids[(e >> 2) & 31u][lane];
-            dst[1] = (int)ids[(e >> 7) & 31u][lane];
-            dst[2] = (int)ids[(e >> 12) & 31u][lane];
-            if ((e & 3u) == 2u) {
-              dst[3] = (int)ids[(e >> 17) & 31u][lane];
-              dst[4] = (int)ids[(e >> 22) & 31u][lane];
-              dst[5] = (int)ids[(e >> 27) & 31u][lane];
-            }
-            dst += (e & 3u) * 3;
-          }
-        }
-      }
-      __syncwarp();
-      {
-        const size_t gbase = (size_t)first * 3;
-        unsigned nint = (end - first) * 3u;
-        if (gbase + nint > gcap) nint = gbase < gcap ? (unsigned)(gcap - gbase) : 0u;
-        int* out = tris + gbase;
-        for (unsigned q = lane; q < nint; q += 32) out[q] = stage[q];
-      }
-      __syncwarp();
-    }
+    o += e & 3u;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Parity output: (voxel, case code) of emitting voxels, recomputed from the samples in fp64
-// (independent of the bit logic above).  Unordered (slots are handed out per warp by an atomic counter).
+// (independent of the bit logic above).  Same order as the voxel list.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) k_codes(const __grid_constant__ Grid<T> g, unsigned word0, unsigned nwords_emit,
-                                               const uint2* __restrict__ wpre, Counters* ctr, unsigned cap,
+__global__ void __launch_bounds__(256) k_codes(Grid<T> g, const unsigned long long* __restrict__ cell_id, unsigned n_cells,
                                                long long* __restrict__ cells, uint32_t* __restrict__ codes) {
-  const unsigned lane = lane_id();
-  const unsigned seg0 = (blockIdx.x * 8u + (threadIdx.x >> 5)) * 32u;
-  if (seg0 >= nwords_emit) return;
-  const bool have = seg0 + lane < nwords_emit;
-  const unsigned gw = word0 + seg0 + (have ? lane : 0u);
-  uint32_t em = 0;
-  if (have && wpre[gw + 1].y != wpre[gw].y) {
-    int i, j, w;
-    g.word_coords(gw, i, j, w);
-    em = emit_word(g, g.rowflag[(size_t)i * g.n1 + j] != 0, i, j, w, nullptr);
-  }
-  const unsigned ccnt = __popc(em);
-  const unsigned incl = warp_incl_scan_u32(ccnt);
-  const unsigned excl = incl - ccnt;
-  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-  if (total == 0) return;
-  unsigned out0 = 0;
-  if (lane == 0) out0 = atomicAdd(&ctr->n_codes, total);
-  out0 = __shfl_sync(0xffffffffu, out0, 0);
-  for (unsigned base = 0; base < total; base += 32) {
-    const unsigned slot = base + lane;
-    const int o = warp_find_owner(excl, slot);
-    const unsigned o_excl = __shfl_sync(0xffffffffu, excl, o);
-    const unsigned o_gw = __shfl_sync(0xffffffffu, gw, o);
-    const uint32_t o_em = __shfl_sync(0xffffffffu, em, o);
-    if (slot >= total || out0 + slot >= cap) continue;
-    const int b = nth_set_bit(o_em, slot - o_excl);
-    int i, j, w;
-    g.word_coords(o_gw, i, j, w);
-    const int k = w * 32 + b;
-    unsigned code = 0;
-    const unsigned e = cell_emit_exact(g, i, j, k, &code);
-    cells[out0 + slot] = e ? (((long long)i + g.plane_offset) * (g.n1 - 1) + j) * (long long)(g.n2 - 1) + k : -1;
-    codes[out0 + slot] = code;
-  }
+  unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_cells) return;
+  const unsigned long long cid = cell_id[a];
+  const int b = (int)((cid >> 14) & 31u);
+  const unsigned gw = (unsigned)(cid >> 19);
+  const unsigned row = gw / (unsigned)g.W;
+  const int w = (int)(gw - row * (unsigned)g.W);
+  const int i = (int)(row / (unsigned)g.n1), j = (int)(row - (unsigned)i * (unsigned)g.n1);
+  const int k = w * 32 + b;
+  unsigned code = 0;
+  unsigned e = cell_emit_exact(g, i, j, k, &code);
+  cells[a] = e ? (((long long)i + g.plane_offset) * (g.n1 - 1) + j) * (long long)(g.n2 - 1) + k : -1;
+  codes[a] = code;
 }
 
 // one launch instead of four memsets / copies in front of every run
@@ -1152,169 +945,140 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   g.plane_offset = p->plane_offset;
   g.v = p->isovalue;
   g.tolv = 1e-8 + 1e-5 * fabs(p->isovalue);
+  g.any_near = 0;
   g.divW.init((unsigned)W);
   g.divN1.init((unsigned)n1);
   const long long plane_words = (long long)n1 * W;
   const unsigned word0 = (unsigned)((long long)g.i_lo * plane_words);
   const unsigned nscan = (unsigned)((long long)(g.i_hiv - g.i_lo) * plane_words);
-  const unsigned nemit = (unsigned)((long long)(g.i_hi - g.i_lo) * plane_words);
-  unsigned chunk = (nscan + 3u * (unsigned)ctx->sm_count - 1u) / (3u * (unsigned)ctx->sm_count);
-  chunk = std::min<unsigned>(std::max<unsigned>((chunk + CS_SUB - 1) / CS_SUB * CS_SUB, CS_SUB), CS_MAX_CHUNK);
-  const int ntiles = (int)((nscan + chunk - 1) / chunk);
+  const int ntiles = (int)((nscan + CS_TILE - 1) / CS_TILE);
 
   if ((rc = ctr_ensure(ctx, ctx->bits, (size_t)(nwords + 4) * 4))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->nbits, (size_t)(nwords + 4) * 4))) return rc;
-  if ((rc = ctr_ensure(ctx, ctx->vbase, (size_t)(nwords + 4) * 8))) return rc;     // wpre: (vbase, tbase) per word
-  if ((rc = ctr_ensure(ctx, ctx->tbase, (size_t)(nwords + 4) * 8))) return rc;     // wdir: dirpack per word
-  if (!ctx->vox_tab.p) {
-    // corner bits -> triangle list of the whole voxel (tet order, then triangle order; one triangle per word)
-    static uint32_t tab[256 * 12];
-    const int xs[6] = {1, 3, 2, 6, 4, 5}, ys[6] = {3, 2, 6, 4, 5, 1};
-    for (unsigned c8 = 0; c8 < 256; ++c8) {
-      uint32_t* e = tab + c8 * 12;
-      for (int q = 0; q < 12; ++q) e[q] = 0;
-      int k = 0;
-      for (int t = 0; t < 6; ++t) {
-        const unsigned m = (c8 & 1u) | (((c8 >> 7) & 1u) << 1) | (((c8 >> xs[t]) & 1u) << 2) | (((c8 >> ys[t]) & 1u) << 3);
-        for (int tri = 0; tri < CTR_TRI3_N_H[t][m]; ++tri, ++k) {
-          // byte offsets of the three edge slots in a lane's column of s_ids[19][32]: slot * 128
-          const uint32_t a = CTR_TRI3_E_H[t][m][tri * 3 + 0], b = CTR_TRI3_E_H[t][m][tri * 3 + 1], c = CTR_TRI3_E_H[t][m][tri * 3 + 2];
-          e[k] = (a * 128u) | ((b * 128u) << 12) | ((c * 8u) << 24);
-        }
-      }
-    }
-    if ((rc = ctr_ensure(ctx, ctx->vox_tab, sizeof tab, true))) return rc;
-    CTR_CUDA(ctx, cudaMemcpyAsync(ctx->vox_tab.p, tab, sizeof tab, cudaMemcpyHostToDevice, st));
-    CTR_CUDA(ctx, cudaStreamSynchronize(st));
-  }
+  if ((rc = ctr_ensure(ctx, ctx->vbase, (size_t)(nwords + 4) * 4))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->counters, sizeof(Counters)))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->aux[4], (size_t)nrows + 32))) return rc;
-  if ((rc = ctr_ensure(ctx, ctx->tile_state, (size_t)ntiles * 8 + 16))) return rc;
+  if ((rc = ctr_ensure(ctx, ctx->tile_state, (size_t)ntiles * 16 + 16))) return rc;
   if (!ctx->counters_host) CTR_CUDA(ctx, cudaMallocHost(&ctx->counters_host, 256));
   g.bits = (const uint32_t*)ctx->bits.p;
   g.nbits = (const uint32_t*)ctx->nbits.p;
   g.rowflag = (const uint8_t*)ctx->aux[4].p;
   Counters* dctr = (Counters*)ctx->counters.p;
-
-  k_reset3<<<64, 256, 0, st>>>(dctr, (uint4*)ctx->aux[4].p, (size_t)(nrows + 15) / 16, (unsigned long long*)ctx->tile_state.p,
-                               (size_t)ntiles);
-  ctx->launches++;
-  CTR_DBG(ctx, "k_reset3");
-  if (p->flags & CTR_WANT_MINMAX)
-    rc = launch_bitplane<T, true>(ctx, dfield, (unsigned)nrows, n2, W, n0, n1, p->isovalue, (uint32_t*)ctx->bits.p,
-                                  (uint32_t*)ctx->nbits.p, (uint8_t*)ctx->aux[4].p, (MinMaxKeys*)dctr, false);
-  else
-    rc = launch_bitplane<T, false>(ctx, dfield, (unsigned)nrows, n2, W, n0, n1, p->isovalue, (uint32_t*)ctx->bits.p,
-                                   (uint32_t*)ctx->nbits.p, (uint8_t*)ctx->aux[4].p, (MinMaxKeys*)dctr, false);
-  if (rc) return rc;
-  CTR_DBG(ctx, "k_bitplane");
-  ctr_stage_mark(ctx, 2);
-
-  if (ntiles > 0) {
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[sizeof(T) == 4 ? 0 : 1]) {
-      CTR_CUDA(ctx, cudaFuncSetAttribute(k_count_scan<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_MAX_CHUNK * 4));
-      attr_set[sizeof(T) == 4 ? 0 : 1] = true;
-    }
-    k_count_scan<T><<<ntiles, CS_THREADS, (size_t)chunk * 4, st>>>(g, word0, nscan, chunk, (uint2*)ctx->vbase.p,
-                                                                   (uint2*)ctx->tbase.p,
-                                                                   (unsigned long long*)ctx->tile_state.p, dctr, ntiles);
-    ctx->launches++;
-    CTR_DBG(ctx, "k_count_scan");
-  }
-  CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-  ctr_stage_mark(ctx, 3);
+  unsigned long long* st_vt = (unsigned long long*)ctx->tile_state.p;
+  unsigned long long* st_act = st_vt + ntiles;
 
   const bool geom = !(p->flags & CTR_NO_GEOMETRY);
   const bool f64 = (p->flags & CTR_GEOM_F64) != 0;
   const size_t gsz = f64 ? 8 : 4;
   const bool want_n = (p->flags & CTR_WANT_NORMALS) != 0, want_k = (p->flags & CTR_WANT_KEYS) != 0;
-  Xform<double> xd;
-  Xform<float> xs;
+  Xform xf;
   for (int a = 0; a < 3; ++a) {
-    xd.origin[a] = p->origin[a];
-    xd.delta[a] = p->delta[a];
-    xd.inv_delta[a] = 1.0 / p->delta[a];
-    xs.origin[a] = (float)p->origin[a];
-    xs.delta[a] = (float)p->delta[a];
-    xs.inv_delta[a] = (float)(1.0 / p->delta[a]);
+    xf.origin[a] = p->origin[a];
+    xf.delta[a] = p->delta[a];
   }
-  xd.den_tol = 1e-8;
-  xs.den_tol = 1e-8f;
-  if ((double)xs.den_tol > 1e-8) xs.den_tol = nextafterf(xs.den_tol, 0.f);
-  // Output pools are grow-only.  When a previous run left capacities behind, stages 3-4 are enqueued right away
-  // against those capacities (kernels never write past them) and the counts are checked after the single
-  // synchronisation at the end; otherwise (first run, or the guess was too small) the counts are read first.
-  auto ensure_outputs = [&](size_t cv, size_t ct) -> int {
-    int r;
-    if ((r = ctr_ensure(ctx, ctx->verts, cv * 3 * gsz, true))) return r;
-    if (want_n && (r = ctr_ensure(ctx, ctx->normals, cv * 3 * gsz, true))) return r;
-    if (want_k && (r = ctr_ensure(ctx, ctx->keys, cv * 8, true))) return r;
-    if (want_k && (r = ctr_ensure(ctx, ctx->lowmin, cv, true))) return r;
-    if ((r = ctr_ensure(ctx, ctx->tris, ct * 12, true))) return r;
-    return 0;
-  };
-  auto launch_emit = [&](size_t cv, size_t ct, bool again) -> int {
-    if (again) CTR_CUDA(ctx, cudaMemsetAsync(&dctr->claim_v, 0, 2 * sizeof(unsigned), st));
-    const unsigned capv = (unsigned)std::min<size_t>(cv, 0x7fffffffu), capt = (unsigned)std::min<size_t>(ct, 0x7fffffffu);
-    unsigned long long* dkeys = want_k ? (unsigned long long*)ctx->keys.p : nullptr;
-    uint8_t* dlow = want_k ? (uint8_t*)ctx->lowmin.p : nullptr;
-    if (nemit) {
-      const unsigned segs = (nemit + SEG_WORDS - 1) / SEG_WORDS;
-      const unsigned vb = std::min<unsigned>((segs + EV_WARPS - 1) / EV_WARPS, (unsigned)ctx->sm_count * EV_BLOCKS_PER_SM);
-      const uint2* wpre = (const uint2*)ctx->vbase.p;
-      const uint2* wdir = (const uint2*)ctx->tbase.p;
+  // Work lists and output pools are grow-only.  Their capacities come from earlier runs (or a guess on the first one):
+  // every stage is enqueued against them without waiting for the counts -- kernels read the list lengths from the
+  // device counters and never write past a capacity -- and the counts are checked after the single synchronisation
+  // at the end.  Only when a capacity turns out too small are the buffers grown and the affected stages redone.
+  DevBuf& b_own_id = ctx->aux[0];
+  DevBuf& b_own_voff = ctx->aux[1];
+  DevBuf& b_cell_id = ctx->aux[2];
+  DevBuf& b_cell_toff = ctx->aux[3];
+  if (!ctx->spec_own) ctx->spec_own = std::max<size_t>((size_t)nwords / 2, 1 << 14);
+  if (!ctx->spec_cell) ctx->spec_cell = ctx->spec_own;
+  if (!ctx->spec_v) ctx->spec_v = ctx->spec_own * 2;
+  if (!ctx->spec_t) ctx->spec_t = ctx->spec_cell * 4;
+  Counters h;
+  unsigned long long totV = 0, totT = 0, nOwn = 0, nCell = 0, nV = 0;
+  for (int attempt = 0;; ++attempt) {
+    if ((rc = ctr_ensure(ctx, b_own_id, ctx->spec_own * 8, true))) return rc;
+    if ((rc = ctr_ensure(ctx, b_own_voff, ctx->spec_own * 4, true))) return rc;
+    if ((rc = ctr_ensure(ctx, b_cell_id, ctx->spec_cell * 8, true))) return rc;
+    if ((rc = ctr_ensure(ctx, b_cell_toff, ctx->spec_cell * 4, true))) return rc;
+    if (geom) {
+      if ((rc = ctr_ensure(ctx, ctx->verts, ctx->spec_v * 3 * gsz, true))) return rc;
+      if (want_n && (rc = ctr_ensure(ctx, ctx->normals, ctx->spec_v * 3 * gsz, true))) return rc;
+      if (want_k && (rc = ctr_ensure(ctx, ctx->keys, ctx->spec_v * 8, true))) return rc;
+      if (want_k && (rc = ctr_ensure(ctx, ctx->lowmin, ctx->spec_v, true))) return rc;
+      if ((rc = ctr_ensure(ctx, ctx->tris, ctx->spec_t * 12, true))) return rc;
+    }
+    const unsigned cap_own = (unsigned)std::min<size_t>(ctx->spec_own, 0x7fffffffu);
+    const unsigned cap_cell = (unsigned)std::min<size_t>(ctx->spec_cell, 0x7fffffffu);
+    const unsigned cap_v = (unsigned)std::min<size_t>(ctx->spec_v, 0x7fffffffu);
+    const unsigned cap_t = (unsigned)std::min<size_t>(ctx->spec_t, 0x7fffffffu);
+
+    k_reset3<<<64, 256, 0, st>>>(dctr, (uint4*)ctx->aux[4].p, (size_t)(nrows + 15) / 16, st_vt, (size_t)ntiles * 2);
+    ctx->launches++;
+    CTR_DBG(ctx, "k_reset3");
+    if (p->flags & CTR_WANT_MINMAX)
+      rc = launch_bitplane<T, true>(ctx, dfield, (unsigned)nrows, n2, W, n0, n1, p->isovalue, (uint32_t*)ctx->bits.p,
+                                    (uint32_t*)ctx->nbits.p, (uint8_t*)ctx->aux[4].p, (MinMaxKeys*)dctr, false);
+    else
+      rc = launch_bitplane<T, false>(ctx, dfield, (unsigned)nrows, n2, W, n0, n1, p->isovalue, (uint32_t*)ctx->bits.p,
+                                     (uint32_t*)ctx->nbits.p, (uint8_t*)ctx->aux[4].p, (MinMaxKeys*)dctr, false);
+    if (rc) return rc;
+    CTR_DBG(ctx, "k_bitplane");
+    ctr_stage_mark(ctx, 2);
+    if (ntiles > 0) {
+      k_count_scan<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (uint32_t*)ctx->vbase.p,
+                                                     (unsigned long long*)b_own_id.p, (uint32_t*)b_own_voff.p,
+                                                     (unsigned long long*)b_cell_id.p, (uint32_t*)b_cell_toff.p, cap_own,
+                                                     cap_cell, st_vt, st_act, dctr, ntiles);
+      ctx->launches++;
+      CTR_DBG(ctx, "k_count_scan");
+    }
+    CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    ctr_stage_mark(ctx, 3);
+    if (geom && ntiles > 0) {
+      unsigned long long* dkeys = want_k ? (unsigned long long*)ctx->keys.p : nullptr;
+      uint8_t* dlow = want_k ? (uint8_t*)ctx->lowmin.p : nullptr;
+      // grids cover the expected list lengths (last run's, with head-room); blocks past the real length return at once
+      const unsigned vb = (unsigned)((std::min<size_t>(cap_own, ctx->last_own + ctx->last_own / 8 + 4096) + 255) / 256);
+      const unsigned long long* oid = (const unsigned long long*)b_own_id.p;
+      const uint32_t* ovo = (const uint32_t*)b_own_voff.p;
       if (f64)
-        k_emit_verts<T, double><<<vb, EV_THREADS, 0, st>>>(g, word0, nemit, wpre, wdir, xd, (double*)ctx->verts.p,
-                                                            want_n ? (double*)ctx->normals.p : nullptr, dkeys, dlow, capv, &dctr->claim_v);
+        k_emit_verts<T, double><<<vb, 256, 0, st>>>(g, oid, ovo, dctr, vb * 256u, cap_v, xf, (double*)ctx->verts.p,
+                                                    want_n ? (double*)ctx->normals.p : nullptr, dkeys, dlow);
       else
-        k_emit_verts<T, float><<<vb, EV_THREADS, 0, st>>>(g, word0, nemit, wpre, wdir, xs, (float*)ctx->verts.p,
-                                                           want_n ? (float*)ctx->normals.p : nullptr, dkeys, dlow, capv, &dctr->claim_v);
+        k_emit_verts<T, float><<<vb, 256, 0, st>>>(g, oid, ovo, dctr, vb * 256u, cap_v, xf, (float*)ctx->verts.p,
+                                                   want_n ? (float*)ctx->normals.p : nullptr, dkeys, dlow);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_verts");
       ctr_stage_mark(ctx, 4);
-      const unsigned tb = std::min<unsigned>((segs + ET_WARPS - 1) / ET_WARPS, (unsigned)ctx->sm_count * ET_BLOCKS_PER_SM);
-      k_emit_tris<T><<<tb, ET_THREADS, 0, st>>>(g, word0, nemit, wpre, wdir, (const uint32_t*)ctx->vox_tab.p,
-                                                (int*)ctx->tris.p, capt, &dctr->claim_t);
+      const unsigned tb = (unsigned)((std::min<size_t>(cap_cell, ctx->last_cell + ctx->last_cell / 8 + 4096) + ET_THREADS - 1) / ET_THREADS);
+      k_emit_tris<T><<<tb, ET_THREADS, 0, st>>>(g, (const unsigned long long*)b_cell_id.p, (const uint32_t*)b_cell_toff.p, dctr,
+                                                tb * (unsigned)ET_THREADS, cap_t, (const uint32_t*)ctx->vbase.p, (int*)ctx->tris.p);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_tris");
+      ctr_stage_mark(ctx, 5);
+      // what the launches above could cover
+      ctx->cover_own = (size_t)vb * 256u;
+      ctx->cover_cell = (size_t)tb * ET_THREADS;
     } else {
       ctr_stage_mark(ctx, 4);
+      ctr_stage_mark(ctx, 5);
+      ctx->cover_own = ctx->cover_cell = (size_t)-1;
     }
-    ctr_stage_mark(ctx, 5);
     CTR_CUDA(ctx, cudaGetLastError());
-    return 0;
-  };
-  Counters h;
-  unsigned long long totV = 0, totT = 0, nV = 0;
-  auto read_counts = [&]() -> int {
     CTR_CUDA(ctx, cudaStreamSynchronize(st));
     memcpy(&h, ctx->counters_host, sizeof h);
     totV = h.total_vt & 0x7fffffffull;
     totT = h.total_vt >> 31;
+    nOwn = h.total_act & 0x7fffffffull;
+    nCell = h.total_act >> 31;
     nV = (g.i_hiv > g.i_hi) ? h.v_emit : totV;
-    return 0;
-  };
-  bool emitted = false;
-  const bool speculate = geom && ctx->spec_v > 0 && ctx->spec_t > 0 && !(p->flags & CTR_WANT_CODES);
-  if (speculate) {
-    if ((rc = ensure_outputs(ctx->spec_v, ctx->spec_t))) return rc;
-    if ((rc = launch_emit(ctx->spec_v, ctx->spec_t, false))) return rc;
-    if ((rc = read_counts())) return rc;
-    emitted = nV <= ctx->spec_v && totT <= ctx->spec_t;
-  } else {
-    if ((rc = read_counts())) return rc;
-  }
-  if (totV >= 0x7ffffff0ull || totT >= 0x7ffffff0ull)
-    return ctr_fail(ctx, CTR_ERR_OVERFLOW, "more than 2^31 vertices or triangles in one call; shard the volume");
-  if (geom && !emitted) {
+    if (totV >= 0x7ffffff0ull || totT >= 0x7ffffff0ull)
+      return ctr_fail(ctx, CTR_ERR_OVERFLOW, "more than 2^31 vertices or triangles in one call; shard the volume");
+    ctx->last_own = (size_t)nOwn;
+    ctx->last_cell = (size_t)nCell;
+    const bool ok = nOwn <= cap_own && nCell <= cap_cell && (!geom || (nV <= cap_v && totT <= cap_t && nOwn <= ctx->cover_own &&
+                                                                       nCell <= ctx->cover_cell));
+    if (ok) break;
+    if (attempt == 2) return ctr_fail(ctx, CTR_ERR_STATE, "capacities did not converge");
+    ctx->spec_own = std::max<size_t>(ctx->spec_own, (size_t)nOwn + (size_t)nOwn / 4 + 1024);
+    ctx->spec_cell = std::max<size_t>(ctx->spec_cell, (size_t)nCell + (size_t)nCell / 4 + 1024);
     ctx->spec_v = std::max<size_t>(ctx->spec_v, (size_t)nV + (size_t)nV / 4 + 1024);
     ctx->spec_t = std::max<size_t>(ctx->spec_t, (size_t)totT + (size_t)totT / 4 + 1024);
-    if ((rc = ensure_outputs(ctx->spec_v, ctx->spec_t))) return rc;
-    if ((rc = launch_emit(ctx->spec_v, ctx->spec_t, speculate))) return rc;
-  } else if (!geom) {
-    ctr_stage_mark(ctx, 4);
-    ctr_stage_mark(ctx, 5);
   }
 
   out->n_verts = (int64_t)nV;
@@ -1327,21 +1091,20 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   out->fmax = mm ? key_to_double(h.max_key) : NAN;
 
   if (p->flags & CTR_WANT_CODES) {
-    const size_t nCell = (size_t)h.n_cells;
-    if ((rc = ctr_ensure(ctx, ctx->cells, nCell * 8 + 8))) return rc;
-    if ((rc = ctr_ensure(ctx, ctx->codes, nCell * 4 + 4))) return rc;
-    if (nCell && nemit) {
-      const unsigned segs = (nemit + 31) / 32;
-      k_codes<T><<<(segs + 7) / 8, 256, 0, st>>>(g, word0, nemit, (const uint2*)ctx->vbase.p, dctr, (unsigned)nCell,
-                                                 (long long*)ctx->cells.p, (uint32_t*)ctx->codes.p);
+    if ((rc = ctr_ensure(ctx, ctx->cells, (size_t)nCell * 8 + 8))) return rc;
+    if ((rc = ctr_ensure(ctx, ctx->codes, (size_t)nCell * 4 + 4))) return rc;
+    if (nCell) {
+      k_codes<T><<<(unsigned)((nCell + 255) / 256), 256, 0, st>>>(g, (const unsigned long long*)b_cell_id.p, (unsigned)nCell,
+                                                                   (long long*)ctx->cells.p, (uint32_t*)ctx->codes.p);
       ctx->launches++;
     }
     out->n_codes = (int64_t)nCell;
+    CTR_CUDA(ctx, cudaGetLastError());
+    CTR_CUDA(ctx, cudaStreamSynchronize(st));
   }
   ctr_stage_mark(ctx, 6);
-  CTR_CUDA(ctx, cudaGetLastError());
-  CTR_CUDA(ctx, cudaStreamSynchronize(st));
   if (ctx->timing) {
+    CTR_CUDA(ctx, cudaStreamSynchronize(st));
     for (int s = 0; s < 6; ++s) {
       ctx->stage_ms[s] = 0.f;
       if (ctx->ev_set[s] && ctx->ev_set[s + 1]) cudaEventElapsedTime(&ctx->stage_ms[s], ctx->ev[s], ctx->ev[s + 1]);

@@ -73,6 +73,10 @@ def load_library():
     lib.ctr_mt3d_fetch.restype = i32
     lib.ctr_mt3d_device_ptrs.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
     lib.ctr_mt3d_device_ptrs.restype = i32
+    lib.ctr_host_alloc.argtypes = [vp, ctypes.c_uint64, ctypes.POINTER(vp)]
+    lib.ctr_host_alloc.restype = i32
+    lib.ctr_host_free.argtypes = [vp, vp]
+    lib.ctr_host_free.restype = i32
     _bind_optional(lib)
     _lib = lib
     return lib
@@ -103,8 +107,29 @@ class Engine(object):
 
     def close(self):
         if getattr(self, "h", None):
+            for ptr, _ in getattr(self, "_pinned", {}).values():
+                self.lib.ctr_host_free(self.h, ptr)
+            self._pinned = {}
             self.lib.ctr_destroy(self.h)
             self.h = None
+
+    def pinned_empty(self, name, shape, dtype):
+        """numpy array over page-locked host memory from a grow-only pool keyed by `name` (valid until the next
+        request under the same name): device <-> host copies of it run at full PCIe rate."""
+        pool = self.__dict__.setdefault("_pinned", {})
+        dtype = np.dtype(dtype)
+        need = int(np.prod(shape)) * dtype.itemsize
+        ptr, cap = pool.get(name, (None, 0))
+        if cap < max(need, 1):
+            if ptr:
+                self._check(self.lib.ctr_host_free(self.h, ptr), "ctr_host_free")
+            cap = max(need + need // 4, 4096)
+            p = ctypes.c_void_p()
+            self._check(self.lib.ctr_host_alloc(self.h, cap, ctypes.byref(p)), "ctr_host_alloc")
+            ptr = p.value
+            pool[name] = (ptr, cap)
+        buf = (ctypes.c_char * max(need, 1)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def __del__(self):
         try:
@@ -168,8 +193,11 @@ class Engine(object):
         self._last3 = (flags, c)
         return c
 
-    def mt3d_fetch(self, verts=True, normals=None, tris=True, keys=None, codes=None):
+    def mt3d_fetch(self, verts=True, normals=None, tris=True, keys=None, codes=None, pinned=False):
+        """Copy the last run's outputs to host arrays.  pinned=True: the arrays live in the engine's page-locked pool
+        (fast copies) and are overwritten by the next pinned fetch."""
         flags, c = self._last3
+        empty = (lambda n, shape, dt: self.pinned_empty("mt3d_" + n, shape, dt)) if pinned else (lambda n, shape, dt: np.empty(shape, dtype=dt))
         gd = np.float64 if flags & GEOM_F64 else np.float32
         geom = not (flags & NO_GEOMETRY)
         out = {}
@@ -180,13 +208,13 @@ class Engine(object):
         if codes is None:
             codes = bool(flags & WANT_CODES)
         V, T, C = int(c.n_verts), int(c.n_tris), int(c.n_codes)
-        a_v = np.empty((V, 3), dtype=gd) if (verts and geom) else None
-        a_n = np.empty((V, 3), dtype=gd) if (normals and geom) else None
-        a_t = np.empty((T, 3), dtype=np.int32) if (tris and geom) else None
-        a_k = np.empty((V,), dtype=np.uint64) if (keys and geom) else None
-        a_l = np.empty((V,), dtype=np.uint8) if (keys and geom) else None
-        a_c = np.empty((C,), dtype=np.int64) if codes else None
-        a_d = np.empty((C,), dtype=np.uint32) if codes else None
+        a_v = empty("v", (V, 3), gd) if (verts and geom) else None
+        a_n = empty("n", (V, 3), gd) if (normals and geom) else None
+        a_t = empty("t", (T, 3), np.int32) if (tris and geom) else None
+        a_k = empty("k", (V,), np.uint64) if (keys and geom) else None
+        a_l = empty("l", (V,), np.uint8) if (keys and geom) else None
+        a_c = empty("c", (C,), np.int64) if codes else None
+        a_d = empty("d", (C,), np.uint32) if codes else None
         self._check(self.lib.ctr_mt3d_fetch(self.h, _ptr(a_v), _ptr(a_n), _ptr(a_t), _ptr(a_k), _ptr(a_l),
                                             _ptr(a_c), _ptr(a_d)), "ctr_mt3d_fetch")
         out.update(verts=a_v, normals=a_n, tris=a_t, keys=a_k, lowmin=a_l, cells=a_c, codes=a_d)

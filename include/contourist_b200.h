@@ -74,6 +74,11 @@ CTR_API int ctr_stage_times(ctr_ctx* ctx, float* ms, int n);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
 CTR_API int64_t ctr_kernel_launches(const ctr_ctx* ctx);
 
+/* Page-locked host memory for the caller's input / output arrays: cudaMemcpyAsync to or from it runs at full PCIe
+ * rate (pageable memory is staged through a bounce buffer, ~3x slower for the 0.2-0.5 GB arrays of a 512^3 run). */
+CTR_API int ctr_host_alloc(ctr_ctx* ctx, uint64_t bytes, void** out);
+CTR_API int ctr_host_free(ctr_ctx* ctx, void* p);
+
 /* ---- 3D marching tetrahedra ---------------------------------------------------------------------
  * Replaces, for an array-backed field, the reference's
  *   grid_field.py:64-84     FunctionGrid.find_contour_crossing_grid_segments  (n_crossings, fmin, fmax)
