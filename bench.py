@@ -24,6 +24,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ISOVALUE = 0.5
+# dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one extraction, from profiles/ (ncu --set full);
+TRAFFIC_BYTES = 876.7e6      # profiles/r1i_ncu_full_summary.txt: 574.3 + 63.0 + 132.7 + 106.7 MB (algorithmic: 725.9 MB)
 METRIC = "Gvoxels/s, 512^3 fp32 marching-tetrahedra extraction (indexed mesh + normals)"
 
 
@@ -271,14 +273,13 @@ def run_ours(args):
     stages = {"k_bitplane_tma (stage 1: field -> low/near bitplanes, the only full-field pass)": (st[1], field_bytes),
               "k_emit_verts (stage 3: positions + normals)": (st[3], c.n_verts * 24.0),
               "k_emit_tris (stage 4: indexed triangles)": (st[4], c.n_tris * 12.0)}
-    dom = max(stages, key=lambda k: stages[k][0])     # dominant = the kernel with the largest share of the step
-    dom_ms, dom_bytes = stages[dom]
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
     per_stage = {k.split(" ")[0]: {"ms": v[0], "algorithmic_bytes": v[1],
                                    "gbs": (v[1] / (v[0] * 1e-3) / 1e9) if v[0] > 0 else None,
                                    "frac": (v[1] / (v[0] * 1e-3) / 1e9 / peak) if v[0] > 0 else None}
                  for k, v in stages.items()}
     per_stage["k_count_scan"] = {"ms": st[2], "algorithmic_bytes": 0.0, "gbs": 0.0, "frac": 0.0}
+    kern_ms = float(st[1] + st[2] + st[3] + st[4])    # the four kernels of one extraction, from CUDA events on their stream
+    dom = max(per_stage, key=lambda k: per_stage[k]["ms"])
     alg_total = float(n) ** 3 * 4 + c.n_verts * 24 + c.n_tris * 12        # field + V*(3p+3p) + T*12
     pipe_gbs = alg_total / (ms_step * 1e-3) / 1e9
     # CPU baseline: oracle port, 1 core, bounded sample of the same field family
@@ -296,10 +297,13 @@ def run_ours(args):
         "mtris_per_s": n_tris_all / (ms_step * 1e-3) / 1e6, "n_tris": n_tris_all, "n_verts": n_verts_all,
         "stage_ms": {"bitplane": st[1], "count_scan": st[2], "emit_verts": st[3], "emit_tris": st[4],
                      "wall_ms_per_step": wall / args.steps * 1e3},
-        "roofline": {"bound": "hbm", "kernel": dom,
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": dom_bytes, "per_stage": per_stage},
+        # one extraction = one launch each of four kernels; SURVEY 8(d) defines the algorithmic bytes per extraction, so the
+        # roofline is taken over the four launches together (the scan kernel moves no algorithmic bytes of its own)
+        "roofline": {"bound": "hbm", "kernel": "mt3d extraction = k_bitplane_tma + k_count_scan + k_emit_verts + k_emit_tris "
+                                                "(largest share: %s, %.0f%% of the kernel time)" % (dom, 100.0 * per_stage[dom]["ms"] / kern_ms),
+                     "achieved": alg_total / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg_total / (kern_ms * 1e-3) / 1e9 / peak, "traffic": TRAFFIC_BYTES, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_total, "kernel_ms": kern_ms, "per_stage": per_stage},
         "pipeline_roofline": {"algorithmic_bytes": alg_total, "achieved": pipe_gbs, "frac": pipe_gbs / peak,
                               "note": "whole step: (field + V*24 + T*12) / device time of the step"},
         "cpu_baseline": {"value": cpu_val, "unit": "Gvoxels/s", "cores": 1, "kind": "port",

@@ -181,4 +181,76 @@ __device__ __forceinline__ unsigned long long lb_lookback(unsigned long long* st
   return excl;
 }
 
+// Block-wide look-back over two status arrays at once.  Every thread of the block polls one predecessor, so a window
+// of THREADS tiles is resolved per iteration -- with a few hundred tiles in flight the warp version above needs ~10
+// serial L2 round trips while the rest of the block idles at a barrier; this one needs one or two.
+// Called by all threads; returns the exclusive prefixes of `tile` and publishes the inclusive ones.
+template <int THREADS>
+__device__ __forceinline__ void lb_lookback2_block(unsigned long long* st_a, unsigned long long* st_b, int tile,
+                                                   unsigned long long agg_a, unsigned long long agg_b,
+                                                   unsigned long long& excl_a, unsigned long long& excl_b) {
+  constexpr int NW = THREADS / 32;
+  __shared__ int s_first[2][NW];
+  __shared__ unsigned long long s_sum[2][NW];
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  excl_a = excl_b = 0ull;
+  if (tile == 0) {                                   // block-uniform
+    if (tid == 0) {
+      lb_store(&st_a[0], CTR_LB_INC | agg_a);
+      lb_store(&st_b[0], CTR_LB_INC | agg_b);
+    }
+    return;
+  }
+  if (tid == 0) {
+    lb_store(&st_a[tile], CTR_LB_AGG | agg_a);
+    lb_store(&st_b[tile], CTR_LB_AGG | agg_b);
+  }
+  bool done_a = false, done_b = false;
+  for (int idx = tile - 1;; idx -= THREADS) {
+    const int my = idx - tid;
+    unsigned long long sa = CTR_LB_INC, sb = CTR_LB_INC;   // virtual tiles before the first: inclusive prefix 0
+    if (my >= 0) {
+      if (!done_a) do { sa = lb_load(&st_a[my]); } while ((sa >> 62) == 0ull);
+      if (!done_b) do { sb = lb_load(&st_b[my]); } while ((sb >> 62) == 0ull);
+    }
+    const unsigned ia = __ballot_sync(0xffffffffu, (sa >> 62) == 2ull), ib = __ballot_sync(0xffffffffu, (sb >> 62) == 2ull);
+    if (lane == 0) {
+      s_first[0][warp] = ia ? warp * 32 + (__ffs(ia) - 1) : THREADS;
+      s_first[1][warp] = ib ? warp * 32 + (__ffs(ib) - 1) : THREADS;
+    }
+    __syncthreads();
+    int fa = THREADS, fb = THREADS;                  // nearest inclusive predecessor in this window (thread index)
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+      fa = min(fa, s_first[0][q]);
+      fb = min(fb, s_first[1][q]);
+    }
+    unsigned long long va = (!done_a && tid <= fa) ? (sa & CTR_LB_VAL) : 0ull;
+    unsigned long long vb = (!done_b && tid <= fb) ? (sb & CTR_LB_VAL) : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      va += __shfl_xor_sync(0xffffffffu, va, o);
+      vb += __shfl_xor_sync(0xffffffffu, vb, o);
+    }
+    if (lane == 0) {
+      s_sum[0][warp] = va;
+      s_sum[1][warp] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+      excl_a += s_sum[0][q];
+      excl_b += s_sum[1][q];
+    }
+    done_a = done_a || fa < THREADS;
+    done_b = done_b || fb < THREADS;
+    __syncthreads();                                 // s_first / s_sum are rewritten by the next iteration
+    if (done_a && done_b) break;
+  }
+  if (tid == 0) {
+    lb_store(&st_a[tile], CTR_LB_INC | (excl_a + agg_a));
+    lb_store(&st_b[tile], CTR_LB_INC | (excl_b + agg_b));
+  }
+}
+
 #endif  // __CUDACC__

@@ -453,12 +453,13 @@ __global__ void __launch_bounds__(CS_THREADS, 3) k_count_scan(Grid<T> gin, unsig
     blk_vt += sh.warp_vt[q];
     blk_act += sh.warp_act[q];
   }
-  if (warp == 0) {
-    unsigned long long e = lb_lookback(status_vt, tile, blk_vt);
-    if (lane == 0) sh.excl_vt = e;
-  } else if (warp == 1) {
-    unsigned long long e = lb_lookback(status_act, tile, blk_act);
-    if (lane == 0) sh.excl_act = e;
+  {
+    unsigned long long ea, eb;
+    lb_lookback2_block<CS_THREADS>(status_vt, status_act, tile, blk_vt, blk_act, ea, eb);
+    if (threadIdx.x == 0) {
+      sh.excl_vt = ea;
+      sh.excl_act = eb;
+    }
   }
   __syncthreads();
   unsigned long long run_vt = sh.excl_vt + woff_vt + inc_vt - loc_vt;

@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Measured numbers for the other two hot-path rows: BASELINE configs[1] (2D, 16384^2 fp32,
+16 levels) and configs[3] (4D, 128^3 x 64 fp32 morph field).  bench.py stays the single headline line (configs[2]);
+this prints one JSON line per path with the same roofline conventions.
+
+    python tools/bench_paths.py [--steps 10] [--warmup 3] [--n2d 16384] [--n4d 128 --nt 64]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def timed(fn, steps, warmup, stream, acc):
+    import torch
+    for _ in range(max(warmup, 3)):
+        c = fn()
+    torch.cuda.synchronize()
+    acc[:] = 0                                       # stage times of the timed steps only
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        c = fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return c, e0.elapsed_time(e1) / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n2d", type=int, default=16384)
+    ap.add_argument("--n4d", type=int, default=128)
+    ap.add_argument("--nt", type=int, default=64)
+    args = ap.parse_args()
+    import torch
+    from contourist_b200 import engine as E
+    from contourist_b200 import synthetic
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    eng = E.Engine(0)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_timing(True)
+    pk, src = peak()
+
+    # ---- 2D: configs[1]
+    n = args.n2d
+    f = synthetic.field2d(n, device=dev)
+    mn, mx = float(f.min()), float(f.max())
+    levels = [(mx - mn) / 17 * i for i in range(1, 17)]          # Linear2DContour rule, multiple_2d_contour.py:102-107
+    acc = np.zeros(8)
+
+    def step2():
+        c = eng.mt2d_run(f.data_ptr(), levels, shape=(n, n), dtype=np.float32)
+        acc[:] += np.array(eng.stage_times(8))
+        return c
+    c, ms = timed(step2, args.steps, args.warmup, stream, acc)
+    st = acc / args.steps
+    S = int(c.n_segments)
+    alg = n * n * 4.0 + S * (1 + 16 + 16)                        # field once for all levels + level tag, 2 keys, 2 fp32 points
+    print(json.dumps({"path": "2D marching triangles (BASELINE configs[1])", "metric": "Gsamples/s", "value": n * n / ms / 1e6,
+                      "msegments_per_s": S / ms / 1e3, "ms_per_step": ms, "n_segments": S, "levels": 16, "dtype": "f32",
+                      "stage_ms": {"count_scan": float(st[1]), "emit": float(st[2])},
+                      "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": pk, "unit": "GB/s",
+                                   "frac": alg / ms / 1e6 / pk, "algorithmic_bytes": alg, "peak_source": src}}))
+    del f
+    torch.cuda.empty_cache()
+
+    # ---- 4D: configs[3]
+    f = synthetic.morph4d(args.n4d, args.nt, device=dev)
+    shape = tuple(f.shape)
+    acc[:] = 0
+
+    def step4():
+        c = eng.mp4d_run(f.data_ptr(), 1.2, shape=shape, dtype=np.float32, flags=E.MORPH)
+        acc[:] += np.array(eng.stage_times(8))
+        return c
+    c, ms = timed(step4, args.steps, args.warmup, stream, acc)
+    st = acc / args.steps
+    V, T, M = int(c.n_verts), int(c.n_tets), int(c.n_morph_tris)
+    nsamp = float(np.prod(shape))
+    alg = nsamp * 4 + V * 16 + T * 16 + M * 24                   # field + 4D points + tetrahedra + morph triangles (3 segments x 2 ids)
+    print(json.dumps({"path": "4D marching pentatopes + morph triangles (BASELINE configs[3])", "metric": "Gsamples/s",
+                      "value": nsamp / ms / 1e6, "mtets_per_s": T / ms / 1e3, "ms_per_step": ms, "shape": list(shape),
+                      "n_verts": V, "n_tets": T, "n_morph_tris": M, "dtype": "f32",
+                      "stage_ms": {"bitplane": float(st[1]), "count_scan": float(st[2]), "emit_verts": float(st[3]),
+                                   "emit_tets": float(st[4]), "morph": float(st[5])},
+                      "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": pk, "unit": "GB/s",
+                                   "frac": alg / ms / 1e6 / pk, "algorithmic_bytes": alg, "peak_source": src}}))
+
+
+if __name__ == "__main__":
+    main()
