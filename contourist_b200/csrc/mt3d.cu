@@ -308,34 +308,38 @@ constexpr int CS_THREADS = 256;
 constexpr int CS_ITEMS = 4;
 constexpr int CS_TILE = CS_THREADS * CS_ITEMS;
 
-struct CsShared {
+struct CountShared {
   uint32_t own[CS_TILE], emit[CS_TILE];
-  uint32_t pv[CS_TILE], pt[CS_TILE], po[CS_TILE], pc[CS_TILE];
   unsigned short cv[CS_TILE], ct[CS_TILE];
   unsigned short list[CS_TILE];
   unsigned long long warp_vt[CS_THREADS / 32], warp_act[CS_THREADS / 32];
-  unsigned long long excl_vt, excl_act;
-  unsigned tile, nint;
+  unsigned nint, last;
 };
 
+// per-word record of the scan: vertices | triangles << 8 | active owners << 17 | emitting voxels << 23
+__device__ __forceinline__ uint32_t pack_rec(unsigned v, unsigned t, unsigned no, unsigned nc) {
+  return v | (t << 8) | (no << 17) | (nc << 23);
+}
+__device__ __forceinline__ unsigned long long rec_vt(uint32_t r) {
+  return ((unsigned long long)((r >> 8) & 511u) << 31) | (r & 255u);
+}
+__device__ __forceinline__ unsigned long long rec_act(uint32_t r) {
+  return ((unsigned long long)(r >> 23) << 31) | ((r >> 17) & 63u);
+}
+
+// Stage 2a: counts.  Tiles of 1024 words in any order, no inter-tile dependency: per-word records, the masks of the
+// interesting words, one aggregate per tile; the block that finishes last turns the aggregates into exclusive prefixes.
 template <typename T>
-__global__ void __launch_bounds__(CS_THREADS, 3) k_count_scan(Grid<T> gin, unsigned word0, unsigned nwords_scan,
-                                                           uint32_t* __restrict__ vbase,
-                                                           unsigned long long* __restrict__ own_id,
-                                                           uint32_t* __restrict__ own_voff,
-                                                           unsigned long long* __restrict__ cell_id,
-                                                           uint32_t* __restrict__ cell_toff, unsigned cap_own,
-                                                           unsigned cap_cell, unsigned long long* status_vt,
-                                                           unsigned long long* status_act, Counters* ctr, int ntiles) {
-  __shared__ CsShared sh;
+__global__ void __launch_bounds__(CS_THREADS, 4) k_count(Grid<T> gin, unsigned word0, unsigned nwords_scan,
+                                                      uint32_t* __restrict__ rec, uint2* __restrict__ wmask,
+                                                      unsigned long long* __restrict__ tile_vt,
+                                                      unsigned long long* __restrict__ tile_act, Counters* ctr, int ntiles) {
+  __shared__ CountShared sh;
   Grid<T> g = gin;
   g.any_near = 0;
-  if (threadIdx.x == 0) {
-    sh.tile = atomicAdd(&ctr->ticket, 1u);
-    sh.nint = 0;
-  }
+  if (threadIdx.x == 0) sh.nint = 0;
   __syncthreads();
-  const int tile = (int)sh.tile;
+  const int tile = (int)blockIdx.x;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
   const unsigned emit_end = (unsigned)g.i_hi * plane_words;      // words below this are emitted
@@ -415,6 +419,7 @@ __global__ void __launch_bounds__(CS_THREADS, 3) k_count_scan(Grid<T> gin, unsig
     sh.ct[wl] = (unsigned short)t;
     sh.own[wl] = gw < emit_end ? any : 0u;
     sh.emit[wl] = em;
+    wmask[gw] = make_uint2(gw < emit_end ? any : 0u, em);
     ncells += __popc(em);
   }
   unsigned long long cc = ((unsigned long long)ncross << 32) | ncells;
@@ -426,78 +431,197 @@ __global__ void __launch_bounds__(CS_THREADS, 3) k_count_scan(Grid<T> gin, unsig
   }
   __syncthreads();
 
-  // ---- C: scan.  Thread t owns the 4 consecutive words 4t..4t+3 (linear order)
+  // ---- records (thread t owns the 4 consecutive words 4t..4t+3) and the tile aggregate
   unsigned long long loc_vt = 0, loc_act = 0;
-  unsigned long long item_vt[CS_ITEMS], item_act[CS_ITEMS];
+  uint32_t r4[CS_ITEMS];
 #pragma unroll
   for (int it = 0; it < CS_ITEMS; ++it) {
     const unsigned wl = threadIdx.x * CS_ITEMS + it;
-    item_vt[it] = ((unsigned long long)sh.ct[wl] << 31) | sh.cv[wl];
-    item_act[it] = ((unsigned long long)__popc(sh.emit[wl]) << 31) | (unsigned)__popc(sh.own[wl]);
+    r4[it] = pack_rec(sh.cv[wl], sh.ct[wl], __popc(sh.own[wl]), __popc(sh.emit[wl]));
+    loc_vt += rec_vt(r4[it]);
+    loc_act += rec_act(r4[it]);
+  }
+  {
+    const unsigned rel0 = tile0 + threadIdx.x * CS_ITEMS;
+#pragma unroll
+    for (int it = 0; it < CS_ITEMS; ++it)
+      if (rel0 + it < nwords_scan) rec[word0 + rel0 + it] = r4[it];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    loc_vt += __shfl_xor_sync(0xffffffffu, loc_vt, o);
+    loc_act += __shfl_xor_sync(0xffffffffu, loc_act, o);
+  }
+  if (lane == 0) {
+    sh.warp_vt[warp] = loc_vt;
+    sh.warp_act[warp] = loc_act;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long a = 0, b = 0;
+#pragma unroll
+    for (int q = 0; q < CS_THREADS / 32; ++q) {
+      a += sh.warp_vt[q];
+      b += sh.warp_act[q];
+    }
+    tile_vt[tile] = a;
+    tile_act[tile] = b;
+    __threadfence();
+    sh.last = (atomicAdd(&ctr->ticket, 1u) == (unsigned)ntiles - 1u) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!sh.last) return;
+  // ---- last block: exclusive scan of the tile aggregates in place (a few thousand entries)
+  __threadfence();
+  unsigned long long carry_vt = 0, carry_act = 0;
+  for (int base = 0; base < ntiles; base += CS_THREADS) {
+    const int q = base + (int)threadIdx.x;
+    unsigned long long a = 0, b = 0;
+    if (q < ntiles) {
+      a = lb_load(&tile_vt[q]);
+      b = lb_load(&tile_act[q]);
+    }
+    const unsigned long long ia = warp_incl_scan_u64(a), ib = warp_incl_scan_u64(b);
+    __syncthreads();
+    if (lane == 31) {
+      sh.warp_vt[warp] = ia;
+      sh.warp_act[warp] = ib;
+    }
+    __syncthreads();
+    unsigned long long wa = 0, wb = 0, ta = 0, tb = 0;
+#pragma unroll
+    for (int w8 = 0; w8 < CS_THREADS / 32; ++w8) {
+      if (w8 < (int)warp) {
+        wa += sh.warp_vt[w8];
+        wb += sh.warp_act[w8];
+      }
+      ta += sh.warp_vt[w8];
+      tb += sh.warp_act[w8];
+    }
+    if (q < ntiles) {
+      tile_vt[q] = carry_vt + wa + ia - a;
+      tile_act[q] = carry_act + wb + ib - b;
+    }
+    carry_vt += ta;
+    carry_act += tb;
+  }
+  if (threadIdx.x == 0) {
+    ctr->total_vt = carry_vt;
+    ctr->total_act = carry_act;
+  }
+}
+
+struct ExpandShared {
+  uint32_t pv[CS_TILE], pt[CS_TILE], po[CS_TILE], pc[CS_TILE];
+  unsigned short list[CS_TILE];
+  unsigned short vox[256];           // corner bits -> emitting tets (6 bits) | triangle count << 8
+  unsigned long long warp_vt[CS_THREADS / 32], warp_act[CS_THREADS / 32];
+  unsigned nint;
+};
+
+// Stage 2b: offsets and work lists.  Every tile knows its exclusive prefix (k_count's last block): block scan of the
+// records -> vbase[word]; the interesting words are dealt out evenly and write the compacted, ordered lists of
+//   active owners (own_id = word<<13 | bit<<8 | p_low<<7 | mask7, own_voff = first vertex id)
+//   active voxels (cell_id = word<<19 | bit<<14 | emit6<<8 | corner8, cell_toff = first triangle).
+template <typename T>
+__global__ void __launch_bounds__(CS_THREADS, 4) k_expand(Grid<T> gin, unsigned word0, unsigned nwords_scan,
+                                                       const uint32_t* __restrict__ rec, const uint2* __restrict__ wmask,
+                                                       const unsigned long long* __restrict__ tile_vt,
+                                                       const unsigned long long* __restrict__ tile_act,
+                                                       uint32_t* __restrict__ vbase, unsigned long long* __restrict__ own_id,
+                                                       uint32_t* __restrict__ own_voff, unsigned long long* __restrict__ cell_id,
+                                                       uint32_t* __restrict__ cell_toff, unsigned cap_own, unsigned cap_cell,
+                                                       Counters* ctr) {
+  __shared__ ExpandShared sh;
+  Grid<T> g = gin;
+  g.any_near = 0;
+  if (threadIdx.x == 0) sh.nint = 0;
+  {
+    const unsigned c8 = threadIdx.x;                 // CS_THREADS == 256: one table entry per thread
+    unsigned emit = 0, nt = 0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+      const unsigned tm = tet_mask_of(c8, t);
+      if (tm != 0 && tm != 15) {
+        emit |= 1u << t;
+        nt += (__popc(tm) == 2) ? 2u : 1u;
+      }
+    }
+    sh.vox[c8] = (unsigned short)(emit | (nt << 8));
+  }
+  __syncthreads();
+  const int tile = (int)blockIdx.x;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
+  const unsigned emit_end = (unsigned)g.i_hi * plane_words;
+  const unsigned tile0 = (unsigned)tile * CS_TILE;
+
+  // ---- scan: thread t owns the 4 consecutive words 4t..4t+3 (linear order)
+  unsigned long long loc_vt = 0, loc_act = 0;
+  unsigned long long item_vt[CS_ITEMS], item_act[CS_ITEMS];
+  const unsigned rel0 = tile0 + threadIdx.x * CS_ITEMS;
+  unsigned mine = 0;                                 // which of my words are interesting
+#pragma unroll
+  for (int it = 0; it < CS_ITEMS; ++it) {
+    const uint32_t r = (rel0 + it < nwords_scan) ? rec[word0 + rel0 + it] : 0u;
+    item_vt[it] = rec_vt(r);
+    item_act[it] = rec_act(r);
     loc_vt += item_vt[it];
     loc_act += item_act[it];
+    if (r >> 17) mine |= 1u << it;                   // has active owners or emitting voxels
   }
-  unsigned long long inc_vt = warp_incl_scan_u64(loc_vt), inc_act = warp_incl_scan_u64(loc_act);
+  {
+    // compact the interesting words of the tile (ordered by word)
+    const unsigned cnt = __popc(mine);
+    const unsigned inc = warp_incl_scan_u32(cnt);
+    unsigned base = 0;
+    if (lane == 31 && inc) base = atomicAdd(&sh.nint, inc);
+    base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+#pragma unroll
+    for (int it = 0; it < CS_ITEMS; ++it)
+      if ((mine >> it) & 1u) sh.list[base++] = (unsigned short)(threadIdx.x * CS_ITEMS + it);
+  }
+  const unsigned long long inc_vt = warp_incl_scan_u64(loc_vt), inc_act = warp_incl_scan_u64(loc_act);
   if (lane == 31) {
     sh.warp_vt[warp] = inc_vt;
     sh.warp_act[warp] = inc_act;
   }
   __syncthreads();
-  unsigned long long woff_vt = 0, woff_act = 0, blk_vt = 0, blk_act = 0;
+  unsigned long long woff_vt = 0, woff_act = 0;
 #pragma unroll
   for (int q = 0; q < CS_THREADS / 32; ++q) {
     if (q < (int)warp) {
       woff_vt += sh.warp_vt[q];
       woff_act += sh.warp_act[q];
     }
-    blk_vt += sh.warp_vt[q];
-    blk_act += sh.warp_act[q];
   }
-  {
-    unsigned long long ea, eb;
-    lb_lookback2_block<CS_THREADS>(status_vt, status_act, tile, blk_vt, blk_act, ea, eb);
-    if (threadIdx.x == 0) {
-      sh.excl_vt = ea;
-      sh.excl_act = eb;
+  unsigned long long run_vt = tile_vt[tile] + woff_vt + inc_vt - loc_vt;
+  unsigned long long run_act = tile_act[tile] + woff_act + inc_act - loc_act;
+#pragma unroll
+  for (int it = 0; it < CS_ITEMS; ++it) {
+    const unsigned wl = threadIdx.x * CS_ITEMS + it;
+    const uint32_t vb = (uint32_t)(run_vt & 0x7fffffffull);
+    sh.pv[wl] = vb;
+    sh.pt[wl] = (uint32_t)(run_vt >> 31);
+    sh.po[wl] = (uint32_t)(run_act & 0x7fffffffull);
+    sh.pc[wl] = (uint32_t)(run_act >> 31);
+    if (rel0 + it < nwords_scan) {
+      vbase[word0 + rel0 + it] = vb;
+      if (g.i_hiv > g.i_hi && word0 + rel0 + it == emit_end) ctr->v_emit = vb;
     }
+    run_vt += item_vt[it];
+    run_act += item_act[it];
   }
   __syncthreads();
-  unsigned long long run_vt = sh.excl_vt + woff_vt + inc_vt - loc_vt;
-  unsigned long long run_act = sh.excl_act + woff_act + inc_act - loc_act;
-  {
-    uint32_t vb[CS_ITEMS];
-#pragma unroll
-    for (int it = 0; it < CS_ITEMS; ++it) {
-      const unsigned wl = threadIdx.x * CS_ITEMS + it;
-      vb[it] = (uint32_t)(run_vt & 0x7fffffffull);
-      sh.pv[wl] = vb[it];
-      sh.pt[wl] = (uint32_t)(run_vt >> 31);
-      sh.po[wl] = (uint32_t)(run_act & 0x7fffffffull);
-      sh.pc[wl] = (uint32_t)(run_act >> 31);
-      run_vt += item_vt[it];
-      run_act += item_act[it];
-    }
-    const unsigned rel0 = tile0 + threadIdx.x * CS_ITEMS;
-#pragma unroll
-    for (int it = 0; it < CS_ITEMS; ++it) {
-      if (rel0 + it < nwords_scan) {
-        vbase[word0 + rel0 + it] = vb[it];
-        if (g.i_hiv > g.i_hi && word0 + rel0 + it == emit_end) ctr->v_emit = vb[it];
-      }
-    }
-  }
-  if (tile == ntiles - 1 && threadIdx.x == 0) {
-    ctr->total_vt = sh.excl_vt + blk_vt;
-    ctr->total_act = sh.excl_act + blk_act;
-  }
-  __syncthreads();
+  const unsigned nint = sh.nint;
 
   // ---- D: compacted owner / voxel lists
   for (unsigned idx = threadIdx.x; idx < nint; idx += CS_THREADS) {
     const unsigned wl = sh.list[idx];
-    uint32_t mo = sh.own[wl], me = sh.emit[wl];
-    if (!(mo | me)) continue;
     const unsigned gw = word0 + tile0 + wl;
+    const uint2 msk = wmask[gw];
+    uint32_t mo = msk.x, me = msk.y;
+    if (!(mo | me)) continue;
     int i, j, w;
     g.word_coords(gw, i, j, w);
     g.any_near = g.rowflag[(size_t)i * g.n1 + j];
@@ -528,13 +652,11 @@ __global__ void __launch_bounds__(CS_THREADS, 3) k_count_scan(Grid<T> gin, unsig
         me &= me - 1;
         unsigned c8 = 0;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) c8 |= ((corner_plane(pl, c) >> b) & 1u) << c;
-        unsigned emit = 0;
-#pragma unroll
-        for (int t = 0; t < 6; ++t) {
-          const unsigned tm = tet_mask_of(c8, t);
-          if (tm != 0 && tm != 15) emit |= 1u << t;
-        }
+        for (int ab = 0; ab < 4; ++ab)                      // corners (ab, dk): bit b of the row and of the row shifted in k
+          c8 |= (((pl.P[ab] >> b) & 1u) | (((pl.S[ab] >> b) & 1u) << 1)) << (2 * ab);
+        // emitting tets (all the mixed ones) and their triangle count from a 256-entry table of the corner bits
+        const unsigned en = sh.vox[c8];
+        unsigned emit = en & 63u, nt = en >> 8;
         if (g.any_near) {
           unsigned n8 = 0;
 #pragma unroll
@@ -542,12 +664,14 @@ __global__ void __launch_bounds__(CS_THREADS, 3) k_count_scan(Grid<T> gin, unsig
           bool cand = false;
 #pragma unroll
           for (int t = 0; t < 6; ++t) cand = cand || (((emit >> t) & 1u) && tet_mask_of(n8, t) == 15);
-          if (cand) emit = cell_emit_exact(g, i, j, w * 32 + b, nullptr);
-        }
-        unsigned nt = 0;
+          if (cand) {
+            emit = cell_emit_exact(g, i, j, w * 32 + b, nullptr);
+            nt = 0;
 #pragma unroll
-        for (int t = 0; t < 6; ++t)
-          if ((emit >> t) & 1u) nt += (__popc(tet_mask_of(c8, t)) == 2) ? 2u : 1u;
+            for (int t = 0; t < 6; ++t)
+              if ((emit >> t) & 1u) nt += (__popc(tet_mask_of(c8, t)) == 2) ? 2u : 1u;
+          }
+        }
         if (crun < cap_cell) {
           cell_id[crun] = ((unsigned long long)gw << 19) | ((unsigned)b << 14) | (emit << 8) | c8;
           cell_toff[crun] = trun;
@@ -957,6 +1081,8 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   if ((rc = ctr_ensure(ctx, ctx->bits, (size_t)(nwords + 4) * 4))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->nbits, (size_t)(nwords + 4) * 4))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->vbase, (size_t)(nwords + 4) * 4))) return rc;
+  if ((rc = ctr_ensure(ctx, ctx->tbase, (size_t)(nwords + 4) * 4))) return rc;     // per-word scan records
+  if ((rc = ctr_ensure(ctx, ctx->wmask, (size_t)(nwords + 4) * 8))) return rc;     // (owner, voxel) masks of interesting words
   if ((rc = ctr_ensure(ctx, ctx->counters, sizeof(Counters)))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->aux[4], (size_t)nrows + 32))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->tile_state, (size_t)ntiles * 16 + 16))) return rc;
@@ -1021,12 +1147,16 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
     CTR_DBG(ctx, "k_bitplane");
     ctr_stage_mark(ctx, 2);
     if (ntiles > 0) {
-      k_count_scan<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (uint32_t*)ctx->vbase.p,
-                                                     (unsigned long long*)b_own_id.p, (uint32_t*)b_own_voff.p,
-                                                     (unsigned long long*)b_cell_id.p, (uint32_t*)b_cell_toff.p, cap_own,
-                                                     cap_cell, st_vt, st_act, dctr, ntiles);
+      k_count<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (uint32_t*)ctx->tbase.p, (uint2*)ctx->wmask.p, st_vt, st_act,
+                                                dctr, ntiles);
       ctx->launches++;
-      CTR_DBG(ctx, "k_count_scan");
+      CTR_DBG(ctx, "k_count");
+      k_expand<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (const uint32_t*)ctx->tbase.p, (const uint2*)ctx->wmask.p,
+                                                 st_vt, st_act, (uint32_t*)ctx->vbase.p, (unsigned long long*)b_own_id.p,
+                                                 (uint32_t*)b_own_voff.p, (unsigned long long*)b_cell_id.p,
+                                                 (uint32_t*)b_cell_toff.p, cap_own, cap_cell, dctr);
+      ctx->launches++;
+      CTR_DBG(ctx, "k_expand");
     }
     CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     ctr_stage_mark(ctx, 3);
