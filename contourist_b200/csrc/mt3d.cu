@@ -165,7 +165,7 @@ __device__ __forceinline__ void load_planes(const Grid<T>& g, const uint32_t* __
       bool ok = (a == 0 || pl.has_i1) && (b == 0 || pl.has_j1);
       uint32_t p = 0, nx = 0;
       if (ok) {
-        long long base = ((long long)(i + a) * g.n1 + (j + b)) * g.W + w;
+        const unsigned base = ((unsigned)(i + a) * (unsigned)g.n1 + (unsigned)(j + b)) * (unsigned)g.W + (unsigned)w;
         p = plane[base];
         if (w + 1 < g.W) nx = plane[base + 1];
       }
@@ -308,6 +308,52 @@ constexpr int CS_THREADS = 256;
 constexpr int CS_ITEMS = 4;
 constexpr int CS_TILE = CS_THREADS * CS_ITEMS;
 
+// Quick test of 4 consecutive words of one row (W % 4 == 0, gw % 4 == 0): does any of their 7 x 32 owned edges cross?
+// 128-bit loads of the four rows the words touch; returns a 4-bit mask.
+template <typename T>
+__device__ __forceinline__ unsigned words4_interesting(const Grid<T>& g, unsigned gw, unsigned plane_words) {
+  const unsigned row = g.divW.div(gw);
+  const unsigned w = gw - row * (unsigned)g.W;
+  const unsigned i = g.divN1.div(row);
+  const unsigned j = row - i * (unsigned)g.n1;
+  const bool hi = (int)i + 1 < g.n0, hj = (int)j + 1 < g.n1, hw = (int)w + 4 < g.W;
+  const uint32_t* p = g.bits + gw;
+  uint32_t a[5], b[5] = {0, 0, 0, 0, 0}, c[5] = {0, 0, 0, 0, 0}, d[5] = {0, 0, 0, 0, 0};
+  {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+    a[4] = hw ? p[4] : 0u;
+  }
+  if (hj) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p + g.W);
+    b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+    b[4] = hw ? p[g.W + 4] : 0u;
+  }
+  if (hi) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p + plane_words);
+    c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    c[4] = hw ? p[plane_words + 4] : 0u;
+    if (hj) {
+      const uint4 u = *reinterpret_cast<const uint4*>(p + plane_words + g.W);
+      d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+      d[4] = hw ? p[plane_words + g.W + 4] : 0u;
+    }
+  }
+  const uint32_t mj = hj ? 0xffffffffu : 0u, mi = hi ? 0xffffffffu : 0u, mij = mi & mj;
+  unsigned out = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int rem = g.n2 - (int)(w + q) * 32;
+    const uint32_t kpt = low_mask(rem), kp1 = low_mask(rem - 1);
+    const uint32_t A = a[q];
+    const uint32_t t = ((A ^ b[q]) & mj) | ((A ^ c[q]) & mi) | ((A ^ d[q]) & mij);
+    const uint32_t u = (A ^ __funnelshift_r(a[q], a[q + 1], 1)) | ((A ^ __funnelshift_r(b[q], b[q + 1], 1)) & mj) |
+                       ((A ^ __funnelshift_r(c[q], c[q + 1], 1)) & mi) | ((A ^ __funnelshift_r(d[q], d[q + 1], 1)) & mij);
+    if (((t & kpt) | (u & kp1)) != 0) out |= 1u << q;
+  }
+  return out;
+}
+
 struct CountShared {
   uint32_t own[CS_TILE], emit[CS_TILE];
   unsigned short cv[CS_TILE], ct[CS_TILE];
@@ -345,30 +391,53 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_count(Grid<T> gin, unsigned w
   const unsigned emit_end = (unsigned)g.i_hi * plane_words;      // words below this are emitted
   const unsigned tile0 = (unsigned)tile * CS_TILE;
 
-  // ---- A: dense quick test, 4 strided words per thread
+  // ---- A: dense quick test.  Rows of a multiple of 4 words: thread t takes the 4 consecutive words 4t..4t+3 with
+  // 128-bit loads; otherwise 4 strided words per thread.
+  if ((g.W & 3) == 0) {
+    const unsigned wl0 = threadIdx.x * CS_ITEMS;
+    const unsigned rel = tile0 + wl0;
+    unsigned m4 = 0;
+    if (rel < nwords_scan) m4 = words4_interesting(g, word0 + rel, plane_words);     // nwords_scan is a multiple of W
 #pragma unroll
-  for (int q = 0; q < CS_ITEMS; ++q) {
-    const unsigned wl = (unsigned)q * CS_THREADS + threadIdx.x;
-    const unsigned rel = tile0 + wl;
-    bool interesting = false;
-    if (rel < nwords_scan) {
-      int i, j, w;
-      g.word_coords(word0 + rel, i, j, w);
-      Planes pl;
-      load_planes(g, g.bits, i, j, w, pl);
-      uint32_t x[7];
-      cross_words(pl, x);
-      interesting = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6]) != 0;
+    for (int q = 0; q < CS_ITEMS; ++q) {
+      sh.cv[wl0 + q] = 0;
+      sh.ct[wl0 + q] = 0;
+      sh.own[wl0 + q] = 0;
+      sh.emit[wl0 + q] = 0;
     }
-    sh.cv[wl] = 0;
-    sh.ct[wl] = 0;
-    sh.own[wl] = 0;
-    sh.emit[wl] = 0;
-    const unsigned m = __ballot_sync(0xffffffffu, interesting);
+    const unsigned cnt = __popc(m4);
+    const unsigned inc = warp_incl_scan_u32(cnt);
     unsigned base = 0;
-    if (lane == 0 && m) base = atomicAdd(&sh.nint, (unsigned)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (interesting) sh.list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)wl;
+    if (lane == 31 && inc) base = atomicAdd(&sh.nint, inc);
+    base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+#pragma unroll
+    for (int q = 0; q < CS_ITEMS; ++q)
+      if ((m4 >> q) & 1u) sh.list[base++] = (unsigned short)(wl0 + q);
+  } else {
+#pragma unroll
+    for (int q = 0; q < CS_ITEMS; ++q) {
+      const unsigned wl = (unsigned)q * CS_THREADS + threadIdx.x;
+      const unsigned rel = tile0 + wl;
+      bool interesting = false;
+      if (rel < nwords_scan) {
+        int i, j, w;
+        g.word_coords(word0 + rel, i, j, w);
+        Planes pl;
+        load_planes(g, g.bits, i, j, w, pl);
+        uint32_t x[7];
+        cross_words(pl, x);
+        interesting = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6]) != 0;
+      }
+      sh.cv[wl] = 0;
+      sh.ct[wl] = 0;
+      sh.own[wl] = 0;
+      sh.emit[wl] = 0;
+      const unsigned m = __ballot_sync(0xffffffffu, interesting);
+      unsigned base = 0;
+      if (lane == 0 && m) base = atomicAdd(&sh.nint, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (interesting) sh.list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)wl;
+    }
   }
   __syncthreads();
   const unsigned nint = sh.nint;
