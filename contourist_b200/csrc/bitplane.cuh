@@ -239,7 +239,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigne
                : "memory");
 }
 
-constexpr int TMA_STAGES = 6;
+constexpr int TMA_STAGES_DEFAULT = 3;              // x 16 KiB per CTA; 3 CTAs per SM (measured best of 1..6 x 2..6)
 constexpr int TMA_CHUNK = 16384;                 // bytes per stage
 constexpr int TMA_CONSUMER_WARPS = 8;
 
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__((TMA_CONSUMER_WARPS + 1) * 32) k_bitplane_tma(
                                                                                   T thr, T near_lo, T near_hi,
                                                                                   uint32_t* __restrict__ bits,
                                                                                   uint32_t* __restrict__ nbits, RowGeom rg,
-                                                                                  MinMaxKeys* ctr) {
+                                                                                  MinMaxKeys* ctr, int TMA_STAGES) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)TMA_STAGES * TMA_CHUNK);
   uint64_t* empty = full + TMA_STAGES;
@@ -403,16 +403,18 @@ int launch_bitplane(ctr_ctx* ctx, const T* dfield, unsigned nrows, int n2, int W
   if (clear_rowflag) CTR_CUDA(ctx, cudaMemsetAsync(rg.rowflag, 0, (size_t)nrows, st));
   if (kind == BP_TMA) {
     static bool attr_set[4] = {false, false, false, false};
+    static const int TMA_STAGES = getenv("CTR_BP_STAGES") ? atoi(getenv("CTR_BP_STAGES")) : TMA_STAGES_DEFAULT;
+    static const int ctas_per_sm = getenv("CTR_BP_CTAS") ? atoi(getenv("CTR_BP_CTAS")) : 3;
     const int smem = TMA_STAGES * TMA_CHUNK + 2 * TMA_STAGES * 8 + TMA_CONSUMER_WARPS * 32 * 4 + 64;
     const int ti = (sizeof(T) == 4 ? 0 : 1) + (MINMAX ? 2 : 0);
     if (!attr_set[ti]) {
-      CTR_CUDA(ctx, cudaFuncSetAttribute(k_bitplane_tma<T, MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CTR_CUDA(ctx, cudaFuncSetAttribute(k_bitplane_tma<T, MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * TMA_CHUNK + 1024));
       attr_set[ti] = true;
     }
     const size_t nbytes = nsamp * sizeof(T);
     const size_t nchunks = (nbytes + TMA_CHUNK - 1) / TMA_CHUNK;
-    int blocks = (int)std::min<size_t>(nchunks, (size_t)ctx->sm_count * 2);
-    k_bitplane_tma<T, MINMAX><<<blocks, (TMA_CONSUMER_WARPS + 1) * 32, smem, st>>>(dfield, nbytes, thr, nlo, nhi, bits, nbits, rg, dctr);
+    int blocks = (int)std::min<size_t>(nchunks, (size_t)ctx->sm_count * ctas_per_sm);
+    k_bitplane_tma<T, MINMAX><<<blocks, (TMA_CONSUMER_WARPS + 1) * 32, smem, st>>>(dfield, nbytes, thr, nlo, nhi, bits, nbits, rg, dctr, TMA_STAGES);
   } else if (kind == BP_VEC) {
     const size_t nchunks = (nsamp + 32 * Vec16<T>::VEC - 1) / (32 * Vec16<T>::VEC);
     size_t need = (nchunks + 8 * 4 - 1) / (8 * 4);

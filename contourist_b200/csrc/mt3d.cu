@@ -953,6 +953,7 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> gin, const uns
     // rows (i+a, j+c), a,c in 0..2: word w (R) and the word after it (N)
     uint32_t R[3][3], N[3][3];
     const bool next_ok = (w + 1 < g.W);
+    const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W, gw0 = (unsigned)(cid >> 19);
 #pragma unroll
     for (int ra = 0; ra < 3; ++ra)
 #pragma unroll
@@ -960,7 +961,7 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> gin, const uns
         const bool ok = (i + ra < g.n0) && (j + rc < g.n1);
         uint32_t r = 0, nx = 0;
         if (ok) {
-          const uint32_t* p = g.bits + ((size_t)(i + ra) * g.n1 + (j + rc)) * g.W + w;
+          const uint32_t* p = g.bits + (gw0 + (unsigned)ra * plane_words + (unsigned)rc * (unsigned)g.W);   // 32-bit word index
           r = p[0];
           if (next_ok) nx = p[1];
         }
@@ -986,7 +987,7 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> gin, const uns
       u[5] = (A ^ R[ra + 1][rc + 1]) & kpt & vi & vj;
       u[6] = (A ^ CTR_S(ra + 1, rc + 1)) & kp1 & vi & vj;
 #undef CTR_S
-      const unsigned wi = ((unsigned)(i + ra) * (unsigned)g.n1 + (unsigned)(j + rc)) * (unsigned)g.W + (unsigned)w;
+      const unsigned wi = gw0 + (unsigned)ra * plane_words + (unsigned)rc * (unsigned)g.W;
       unsigned rank = 0;
 #pragma unroll
       for (int d = 0; d < 7; ++d) rank += __popc(u[d] & below);
