@@ -254,4 +254,61 @@ __device__ __forceinline__ void lb_lookback2_block(unsigned long long* st_a, uns
   }
 }
 
+// Single-array wide look-back: warp 0 polls THREADS predecessors per iteration (THREADS/32 loads in flight per lane),
+// the other warps park at the barrier instead of spinning.  Called by all threads.
+template <int THREADS>
+__device__ __forceinline__ unsigned long long lb_lookback_block(unsigned long long* st, int tile, unsigned long long agg) {
+  constexpr int PER = THREADS / 32;
+  __shared__ unsigned long long s_excl;
+  const int tid = (int)threadIdx.x, lane = tid & 31;
+  if (tile == 0) {                                   // block-uniform
+    if (tid == 0) lb_store(&st[0], CTR_LB_INC | agg);
+    return 0ull;
+  }
+  if (tid < 32) {
+    if (lane == 0) lb_store(&st[tile], CTR_LB_AGG | agg);
+    unsigned long long excl = 0ull;
+    for (int idx = tile - 1;; idx -= THREADS) {
+      // lane l looks at predecessors idx - (l*PER + q), q = 0..PER-1 (nearest first)
+      unsigned long long v[PER];
+      bool all_valid;
+      do {
+        all_valid = true;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+          const int my = idx - (lane * PER + q);
+          v[q] = my >= 0 ? lb_load(&st[my]) : CTR_LB_INC;
+          all_valid = all_valid && (v[q] >> 62) != 0ull;
+        }
+        if (!all_valid) __nanosleep(64);
+      } while (!all_valid);
+      // sum up to and including the nearest inclusive entry
+      unsigned long long sum = 0ull;
+      bool found = false;
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        if (!found) sum += v[q] & CTR_LB_VAL;
+        found = found || (v[q] >> 62) == 2ull;
+      }
+      const unsigned fm = __ballot_sync(0xffffffffu, found);
+      if (fm) {
+        const int first = __ffs(fm) - 1;
+        if (lane > first) sum = 0ull;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      excl += sum;
+      if (fm) break;
+    }
+    if (lane == 0) {
+      lb_store(&st[tile], CTR_LB_INC | (excl + agg));
+      s_excl = excl;
+    }
+  }
+  __syncthreads();
+  const unsigned long long e = s_excl;
+  __syncthreads();
+  return e;
+}
+
 #endif  // __CUDACC__

@@ -15,6 +15,7 @@
 // :66-77 + :295-305 (two keys are joined iff they are adjacent_pairs of each other = share their low or
 // their high end inside one grid triangle), multiple_2d_contour.py:50-75 (level classification of edges).
 #include <math.h>
+#include <cmath>
 #include <string.h>
 
 #include <algorithm>
@@ -33,6 +34,7 @@ struct Levels2D {
   T eqv[MAXL];     // level l as a T when exactly representable, else NaN
   double z[MAXL];
   int n;
+  T g0, ginv;      // first guess of the class of f: (f - g0) * ginv + 1 (exact for evenly spaced levels; fixed up otherwise)
 };
 
 struct Counters2D {
@@ -46,17 +48,23 @@ __device__ __forceinline__ unsigned long long order_key2(double x) {
   return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 
+// lt = number of levels strictly below f, eq = f equals level lt.  The thresholds live in shared memory (dynamic
+// indexing of kernel parameters serialises in the constant cache); the class is guessed from the level spacing and
+// then corrected against the true thresholds, so the result is exact for any strictly increasing level list.
 template <typename T>
-__device__ __forceinline__ unsigned classify(const Levels2D<T>& lv, T f) {
-  // lt = number of levels strictly below f (binary search over up[]), eq = f equals level lt
-  int lo = 0, hi = lv.n;
-#pragma unroll 1
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (f >= lv.up[mid]) lo = mid + 1; else hi = mid;
+__device__ __forceinline__ unsigned classify(const T* __restrict__ up, const T* __restrict__ eqv, int n, T g0, T ginv, T f) {
+  const T q = fmin((f - g0) * ginv, (T)n);           // NaN -> n (fmin returns the non-NaN operand); corrected below
+  int k = f < g0 ? 0 : min(n, (int)q + 1);
+  // the guess is right unless f sits within rounding of a threshold (or the levels are unevenly spaced): verify it
+  // with two comparisons, walk only when that fails
+  const bool too_low = k < n && f >= up[min(k, n - 1)];
+  const bool too_high = k > 0 && !(f >= up[max(k - 1, 0)]);
+  if (too_low | too_high) {
+    while (k < n && f >= up[k]) ++k;
+    while (k > 0 && !(f >= up[k - 1])) --k;
   }
-  unsigned eq = (lo < lv.n && f == lv.eqv[lo]) ? 1u : 0u;
-  return (unsigned)lo | (eq << 7);
+  const unsigned eq = (k < n && f == eqv[k]) ? 1u : 0u;
+  return (unsigned)k | (eq << 7);
 }
 
 __device__ __forceinline__ int tri_count(unsigned a, unsigned b, unsigned c) {
@@ -85,24 +93,38 @@ __global__ void __launch_bounds__(T2_COLS) k2d_count(const T* __restrict__ f, in
                                                      uint32_t* __restrict__ sq_cls, unsigned cap,
                                                      unsigned long long* status, Counters2D* ctr) {
   __shared__ Shared2D sh;
+  __shared__ T s_up[MAXL], s_eq[MAXL];
   if (threadIdx.x == 0) sh.tile = atomicAdd(&ctr->ticket, 1u);
+  if (threadIdx.x < MAXL) {
+    s_up[threadIdx.x] = lv.up[threadIdx.x < lv.n ? threadIdx.x : 0];
+    s_eq[threadIdx.x] = lv.eqv[threadIdx.x < lv.n ? threadIdx.x : 0];
+  }
   __syncthreads();
   const int tile = (int)sh.tile;
   const int ti = tile / tiles_j, tj = tile - ti * tiles_j;
   const int i0 = i_lo + ti * T2_ROWS, j0 = tj * T2_COLS;
   const int t = threadIdx.x;
   const unsigned lane = lane_id(), warp = t >> 5;
-  // ---- classify 33 x 257 samples (column t, plus the halo column by thread 0)
-  for (int r = 0; r <= T2_ROWS; ++r) {
-    const int i = i0 + r;
-    unsigned c = 0;
-    if (i < n0 && j0 + t < n1) c = classify(lv, f[(size_t)i * n1 + j0 + t]);
-    sh.cls[r][t] = (unsigned char)c;
-    if (t == 0) {
-      unsigned ch = 0;
-      if (i < n0 && j0 + T2_COLS < n1) ch = classify(lv, f[(size_t)i * n1 + j0 + T2_COLS]);
-      sh.cls[r][T2_COLS] = (unsigned char)ch;
+  // ---- classify 33 x 257 samples (column t, plus the halo column by thread 0); the loads of 11 rows are in flight together
+  constexpr int RB = 11;
+  static_assert((T2_ROWS + 1) % RB == 0, "row batches");
+  const bool col_ok = j0 + t < n1;
+  const T* colp = f + (size_t)i0 * n1 + j0 + t;
+  for (int r0 = 0; r0 <= T2_ROWS; r0 += RB) {
+    T v[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) v[q] = (col_ok && i0 + r0 + q < n0) ? colp[(size_t)(r0 + q) * n1] : (T)NAN;
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      unsigned c = 0;
+      if (col_ok && i0 + r0 + q < n0) c = classify(s_up, s_eq, lv.n, lv.g0, lv.ginv, v[q]);
+      sh.cls[r0 + q][t] = (unsigned char)c;
     }
+  }
+  if (t <= T2_ROWS) {                                  // halo column j0 + 256: one row per thread
+    unsigned ch = 0;
+    if (i0 + t < n0 && j0 + T2_COLS < n1) ch = classify(s_up, s_eq, lv.n, lv.g0, lv.ginv, f[(size_t)(i0 + t) * n1 + j0 + T2_COLS]);
+    sh.cls[t][T2_COLS] = (unsigned char)ch;
   }
   __syncthreads();
   // ---- segments per square (r, t)
@@ -132,9 +154,9 @@ __global__ void __launch_bounds__(T2_COLS) k2d_count(const T* __restrict__ f, in
     if (q < (int)warp) woff += sh.warp_sum[q];
     blk += sh.warp_sum[q];
   }
-  if (warp == 0) {
-    unsigned long long e = lb_lookback(status, tile, blk);
-    if (lane == 0) sh.excl = e;
+  {
+    const unsigned long long e = lb_lookback_block<T2_COLS>(status, tile, blk);
+    if (t == 0) sh.excl = e;
   }
   __syncthreads();
   unsigned long long run = sh.excl + woff + inc - loc;
@@ -296,6 +318,13 @@ void make_levels<float>(const double* z, int n, Levels2D<float>& lv) {
 }
 
 template <typename T>
+void make_guess(Levels2D<T>& lv) {
+  lv.g0 = lv.up[0];
+  const double span = (double)lv.up[lv.n - 1] - (double)lv.up[0];
+  lv.ginv = (lv.n > 1 && span > 0 && std::isfinite(span)) ? (T)((lv.n - 1) / span) : (T)0;
+}
+
+template <typename T>
 int run2d(ctr_ctx* ctx, const ctr_mt2d_params* p, ctr_mt2d_counts* out) {
   const int n0 = (int)p->n0, n1 = (int)p->n1;
   const size_t nsamp = (size_t)n0 * n1;
@@ -313,6 +342,7 @@ int run2d(ctr_ctx* ctx, const ctr_mt2d_params* p, ctr_mt2d_counts* out) {
   ctr_stage_mark(ctx, 1);
   Levels2D<T> lv;
   make_levels<T>(p->levels, p->nlevels, lv);
+  make_guess<T>(lv);
   const int i_lo = (int)p->i_lo, i_hi = (int)std::min<int64_t>(p->i_hi, n0 - 1);
   const int rows = std::max(i_hi - i_lo, 0);
   const int tiles_i = (rows + T2_ROWS - 1) / T2_ROWS, tiles_j = (n1 - 1 + T2_COLS - 1) / T2_COLS;
