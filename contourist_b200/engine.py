@@ -345,9 +345,9 @@ class Engine(object):
 def canonical_mesh(out):
     """Key-sorted copy of an mt3d_fetch() result (needs WANT_KEYS).
 
-    The engine numbers vertices word-major (32 samples along k), then by edge direction, then by k -- deterministic,
-    but not the lexicographic order of the edge keys.  Parity checks (and anyone who wants ids = rank of the key)
-    sort here: vertices / normals / keys / lowmin reordered by key, triangle ids remapped, triangle order kept."""
+    Vertex ids are an engine choice (deterministic, word-major; in this build they are the rank of the edge key).
+    Parity checks must not depend on that choice: they sort here -- vertices / normals / keys / lowmin reordered
+    by key, triangle ids remapped, triangle order kept."""
     keys = out["keys"]
     perm = np.argsort(keys, kind="stable")
     inv = np.empty(len(perm), dtype=np.int64)

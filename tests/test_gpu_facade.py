@@ -43,7 +43,7 @@ def test_isosurface_facade_equals_oracle_world_coords(engine):
     arr = S.grid.samples(1)
     assert arr.shape == (18, 18, 18)
     r = mt3d.extract(arr, 0.5)
-    # canonical form (the engine's vertex order is word / direction / k, the oracle's is by edge key): each triangle
+    # canonical form (vertex numbering is an engine choice; the oracle's is by edge key): each triangle
     # as the sorted tuple of its three world positions, the mesh as the sorted list of those
     world = r["pos"] * 0.125 + (-1.0)
     assert len(pts) == len(world) and len(tris) == len(r["tris"])
