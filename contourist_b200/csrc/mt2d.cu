@@ -1,6 +1,6 @@
 // 2D marching triangles, all levels fused in one pass over the field (sm_100a).
 //
-//   k2d_count : dense pass.  A CTA owns a tile of 32 x 256 squares: it reads the 33 x 257 samples ONCE
+//   k2d_count : dense pass.  A CTA owns a tile of 32 x 1024 squares: it reads the 33 x 1025 samples ONCE
 //               (the field is never re-read densely, whatever the number of levels), classifies each sample
 //               against the sorted level list (lt = #levels < f, eq = f equals a level), counts the contour
 //               segments of every square for all levels from the four corner classes, and joins a
@@ -25,7 +25,8 @@
 namespace {
 
 constexpr int MAXL = 64;
-constexpr int T2_COLS = 256;
+constexpr int T2_COLS = 1024;                       // squares per tile row: 4 consecutive columns per thread
+constexpr int T2_THREADS = 256;
 constexpr int T2_ROWS = 32;
 
 template <typename T>
@@ -48,23 +49,28 @@ __device__ __forceinline__ unsigned long long order_key2(double x) {
   return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 
-// lt = number of levels strictly below f, eq = f equals level lt.  The thresholds live in shared memory (dynamic
-// indexing of kernel parameters serialises in the constant cache); the class is guessed from the level spacing and
-// then corrected against the true thresholds, so the result is exact for any strictly increasing level list.
+// lt = number of levels strictly below f, eq = f equals level lt.  The thresholds live in shared memory, padded:
+// upp[0] = -inf, upp[1..n] = up[0..n-1], upp[n+1] = NaN (never reached), eqp[n] = NaN, so class k is right iff
+// f >= upp[k] and not f >= upp[k+1]
+// and no index needs a bound check.  A guess (from the level spacing, or the neighbour's class: fields are smooth) is
+// verified with two comparisons and only walked when wrong, so the result is exact for any increasing level list.
 template <typename T>
-__device__ __forceinline__ unsigned classify(const T* __restrict__ up, const T* __restrict__ eqv, int n, T g0, T ginv, T f) {
-  const T q = fmin((f - g0) * ginv, (T)n);           // NaN -> n (fmin returns the non-NaN operand); corrected below
-  int k = f < g0 ? 0 : min(n, (int)q + 1);
-  // the guess is right unless f sits within rounding of a threshold (or the levels are unevenly spaced): verify it
-  // with two comparisons, walk only when that fails
-  const bool too_low = k < n && f >= up[min(k, n - 1)];
-  const bool too_high = k > 0 && !(f >= up[max(k - 1, 0)]);
-  if (too_low | too_high) {
-    while (k < n && f >= up[k]) ++k;
-    while (k > 0 && !(f >= up[k - 1])) --k;
+__device__ __forceinline__ int class_fix(const T* __restrict__ upp, T f, int k) {
+  if (!((f >= upp[k]) && !(f >= upp[k + 1]))) {
+    if (f != f) return 0;                            // NaN: below every level, equal to none
+    while (f >= upp[k + 1]) ++k;
+    while (!(f >= upp[k])) --k;
   }
-  const unsigned eq = (k < n && f == eqv[k]) ? 1u : 0u;
-  return (unsigned)k | (eq << 7);
+  return k;
+}
+template <typename T>
+__device__ __forceinline__ int class_guess(int n, T g0, T ginv, T f) {
+  const T q = fmin((f - g0) * ginv, (T)n);           // NaN -> n
+  return f < g0 ? 0 : min(n, (int)q + 1);
+}
+template <typename T>
+__device__ __forceinline__ unsigned class_byte(const T* __restrict__ eqp, T f, int k) {
+  return (unsigned)k | ((f == eqp[k]) ? 128u : 0u);
 }
 
 __device__ __forceinline__ int tri_count(unsigned a, unsigned b, unsigned c) {
@@ -79,97 +85,151 @@ __device__ __forceinline__ int tri_count(unsigned a, unsigned b, unsigned c) {
 }
 
 struct Shared2D {
-  unsigned char cls[T2_ROWS + 1][T2_COLS + 4];
-  unsigned short nseg[T2_ROWS][T2_COLS];
-  unsigned long long warp_sum[T2_COLS / 32];
+  uint32_t cls[T2_ROWS + 1][T2_THREADS + 1];         // 4 class bytes per word (columns 4t..4t+3); word 256 = halo column
+  uint32_t act[T2_ROWS * (T2_COLS / 32)];            // bitmap of the squares that may emit, row-major
+  unsigned long long warp_sum[T2_THREADS / 32];
   unsigned long long excl;
   unsigned tile;
 };
 
+__device__ __forceinline__ unsigned cls_at(const Shared2D& sh, int r, int c) {   // class byte of sample (r, c) of the tile
+  return (sh.cls[r][c >> 2] >> (8 * (c & 3))) & 255u;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(T2_COLS) k2d_count(const T* __restrict__ f, int n0, int n1, int i_lo, int i_hi,
-                                                     Levels2D<T> lv, int tiles_j, int ntiles,
-                                                     uint32_t* __restrict__ sq_lin, uint32_t* __restrict__ sq_base,
-                                                     uint32_t* __restrict__ sq_cls, unsigned cap,
-                                                     unsigned long long* status, Counters2D* ctr) {
+__global__ void __launch_bounds__(T2_THREADS) k2d_count(const T* __restrict__ f, int n0, int n1, int i_lo, int i_hi,
+                                                        Levels2D<T> lv, int tiles_j, int ntiles, int vec_ok,
+                                                        uint32_t* __restrict__ sq_lin, uint32_t* __restrict__ sq_base,
+                                                        uint32_t* __restrict__ sq_cls, unsigned cap,
+                                                        unsigned long long* status, Counters2D* ctr) {
   __shared__ Shared2D sh;
-  __shared__ T s_up[MAXL], s_eq[MAXL];
+  __shared__ T s_upp[MAXL + 2], s_eqp[MAXL + 1];
   if (threadIdx.x == 0) sh.tile = atomicAdd(&ctr->ticket, 1u);
-  if (threadIdx.x < MAXL) {
-    s_up[threadIdx.x] = lv.up[threadIdx.x < lv.n ? threadIdx.x : 0];
-    s_eq[threadIdx.x] = lv.eqv[threadIdx.x < lv.n ? threadIdx.x : 0];
-  }
+  const int nl = lv.n;
+  if ((int)threadIdx.x <= nl + 1) s_upp[threadIdx.x] = threadIdx.x == 0 ? (T)-INFINITY : ((int)threadIdx.x <= nl ? lv.up[threadIdx.x - 1] : (T)NAN);
+  if ((int)threadIdx.x <= nl) s_eqp[threadIdx.x] = (int)threadIdx.x < nl ? lv.eqv[threadIdx.x] : (T)NAN;
   __syncthreads();
   const int tile = (int)sh.tile;
   const int ti = tile / tiles_j, tj = tile - ti * tiles_j;
   const int i0 = i_lo + ti * T2_ROWS, j0 = tj * T2_COLS;
   const int t = threadIdx.x;
   const unsigned lane = lane_id(), warp = t >> 5;
-  // ---- classify 33 x 257 samples (column t, plus the halo column by thread 0); the loads of 11 rows are in flight together
-  constexpr int RB = 11;
+  const int jc = j0 + 4 * t;                         // first of this thread's 4 columns
+
+  // ---- classify 33 x 1025 samples: 4 consecutive columns per thread (one 128-bit load per row), 3 rows in flight
+  constexpr int RB = 3;
   static_assert((T2_ROWS + 1) % RB == 0, "row batches");
-  const bool col_ok = j0 + t < n1;
-  const T* colp = f + (size_t)i0 * n1 + j0 + t;
+  int kprev = 0;
   for (int r0 = 0; r0 <= T2_ROWS; r0 += RB) {
-    T v[RB];
-#pragma unroll
-    for (int q = 0; q < RB; ++q) v[q] = (col_ok && i0 + r0 + q < n0) ? colp[(size_t)(r0 + q) * n1] : (T)NAN;
+    T v[RB][4];
 #pragma unroll
     for (int q = 0; q < RB; ++q) {
-      unsigned c = 0;
-      if (col_ok && i0 + r0 + q < n0) c = classify(s_up, s_eq, lv.n, lv.g0, lv.ginv, v[q]);
-      sh.cls[r0 + q][t] = (unsigned char)c;
+      const int i = i0 + r0 + q;
+      const T* p = f + (size_t)i * n1 + jc;
+      if (i < n0 && vec_ok && jc + 3 < n1) {
+        if (sizeof(T) == 4) {
+          const float4 x = *reinterpret_cast<const float4*>(p);
+          v[q][0] = (T)x.x; v[q][1] = (T)x.y; v[q][2] = (T)x.z; v[q][3] = (T)x.w;
+        } else {
+          const double2 x = *reinterpret_cast<const double2*>(p), y = *reinterpret_cast<const double2*>(p + 2);
+          v[q][0] = (T)x.x; v[q][1] = (T)x.y; v[q][2] = (T)y.x; v[q][3] = (T)y.y;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[q][u] = (i < n0 && jc + u < n1) ? p[u] : (T)NAN;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      uint32_t word = 0;
+      int k = (r0 + q == 0) ? class_guess(nl, lv.g0, lv.ginv, v[q][0]) : kprev;      // the row above, else arithmetic
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        k = class_fix(s_upp, v[q][u], k);
+        word |= class_byte(s_eqp, v[q][u], k) << (8 * u);
+        if (u == 0) kprev = k;
+      }
+      sh.cls[r0 + q][t] = word;
     }
   }
-  if (t <= T2_ROWS) {                                  // halo column j0 + 256: one row per thread
-    unsigned ch = 0;
-    if (i0 + t < n0 && j0 + T2_COLS < n1) ch = classify(s_up, s_eq, lv.n, lv.g0, lv.ginv, f[(size_t)(i0 + t) * n1 + j0 + T2_COLS]);
-    sh.cls[t][T2_COLS] = (unsigned char)ch;
+  if (t <= T2_ROWS) {                                  // halo column j0 + 1024: one row per thread
+    uint32_t ch = 0;
+    if (i0 + t < n0 && j0 + T2_COLS < n1) {
+      const T x = f[(size_t)(i0 + t) * n1 + j0 + T2_COLS];
+      ch = class_byte(s_eqp, x, class_fix(s_upp, x, class_guess(nl, lv.g0, lv.ginv, x)));
+    }
+    sh.cls[t][T2_THREADS] = ch;
   }
   __syncthreads();
-  // ---- segments per square (r, t)
+
+  // ---- squares that may emit: 4 per thread and row, decided on packed class bytes (A = B = C = D without an
+  // equality flag <=> no level touches the square); 8 lanes make one bitmap word
   for (int r = 0; r < T2_ROWS; ++r) {
-    const int i = i0 + r, j = j0 + t;
-    int n = 0;
-    if (i + 1 < n0 && i < i_hi && j + 1 < n1) {
-      const unsigned A = sh.cls[r][t], B = sh.cls[r][t + 1], C = sh.cls[r + 1][t], D = sh.cls[r + 1][t + 1];
-      if (!(A == B && A == C && A == D && !(A & 128u))) n = tri_count(A, C, D) + tri_count(A, B, D);
+    const int i = i0 + r;
+    const uint32_t W0 = sh.cls[r][t], W1 = sh.cls[r][t + 1], X0 = sh.cls[r + 1][t], X1 = sh.cls[r + 1][t + 1];
+    const uint32_t B = __funnelshift_r(W0, W1, 8), D = __funnelshift_r(X0, X1, 8);
+    const uint32_t m = (W0 ^ B) | (W0 ^ X0) | (W0 ^ D) | (W0 & 0x80808080u);
+    uint32_t nib = 0;
+    if (m && i + 1 < n0 && i < i_hi) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (((m >> (8 * u)) & 255u) && jc + u + 1 < n1) nib |= 1u << u;
     }
-    sh.nseg[r][t] = (unsigned short)n;
+    uint32_t wbits = nib << (4 * (lane & 7u));
+    wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
+    wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
+    wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);
+    if ((lane & 7u) == 0) sh.act[r * (T2_COLS / 32) + (t >> 3)] = wbits;
   }
   __syncthreads();
-  // ---- scan in (r, col) order: thread t owns 32 consecutive squares of row t/8
-  const int rr = t >> 3, c0 = (t & 7) * 32;
+
+  // ---- count: thread t owns bitmap words 4t..4t+3 (row-major order of the tile's squares)
   unsigned long long loc = 0;
-  for (int q = 0; q < 32; ++q) {
-    const unsigned n = sh.nseg[rr][c0 + q];
-    loc += ((unsigned long long)n << 31) | (n ? 1u : 0u);
+#pragma unroll 1
+  for (int u = 0; u < 4; ++u) {
+    const int q = 4 * t + u;
+    uint32_t bits = sh.act[q];
+    const int r = q / (T2_COLS / 32), c0 = (q % (T2_COLS / 32)) * 32;
+    while (bits) {
+      const int c = c0 + __ffs(bits) - 1;
+      bits &= bits - 1;
+      const unsigned A = cls_at(sh, r, c), Bc = cls_at(sh, r, c + 1), C = cls_at(sh, r + 1, c), Dc = cls_at(sh, r + 1, c + 1);
+      const unsigned n = (unsigned)(tri_count(A, C, Dc) + tri_count(A, Bc, Dc));
+      if (n) loc += ((unsigned long long)n << 31) | 1u;
+    }
   }
   const unsigned long long inc = warp_incl_scan_u64(loc);
   if (lane == 31) sh.warp_sum[warp] = inc;
   __syncthreads();
   unsigned long long woff = 0, blk = 0;
 #pragma unroll
-  for (int q = 0; q < T2_COLS / 32; ++q) {
+  for (int q = 0; q < T2_THREADS / 32; ++q) {
     if (q < (int)warp) woff += sh.warp_sum[q];
     blk += sh.warp_sum[q];
   }
   {
-    const unsigned long long e = lb_lookback_block<T2_COLS>(status, tile, blk);
+    const unsigned long long e = lb_lookback_block<T2_THREADS>(status, tile, blk);
     if (t == 0) sh.excl = e;
   }
   __syncthreads();
   unsigned long long run = sh.excl + woff + inc - loc;
-  for (int q = 0; q < 32; ++q) {
-    const unsigned n = sh.nseg[rr][c0 + q];
-    if (n) {
+  // ---- compact, ordered list of active squares with their segment offsets
+#pragma unroll 1
+  for (int u = 0; u < 4; ++u) {
+    const int q = 4 * t + u;
+    uint32_t bits = sh.act[q];
+    const int r = q / (T2_COLS / 32), c0 = (q % (T2_COLS / 32)) * 32;
+    while (bits) {
+      const int c = c0 + __ffs(bits) - 1;
+      bits &= bits - 1;
+      const unsigned A = cls_at(sh, r, c), Bc = cls_at(sh, r, c + 1), C = cls_at(sh, r + 1, c), Dc = cls_at(sh, r + 1, c + 1);
+      const unsigned n = (unsigned)(tri_count(A, C, Dc) + tri_count(A, Bc, Dc));
+      if (!n) continue;
       const unsigned slot = (unsigned)(run & 0x7fffffffull);
       if (slot < cap) {
-        const int i = i0 + rr, j = j0 + c0 + q;
-        sq_lin[slot] = (uint32_t)((size_t)i * n1 + j);
+        sq_lin[slot] = (uint32_t)((size_t)(i0 + r) * n1 + (j0 + c));
         sq_base[slot] = (uint32_t)(run >> 31);
-        sq_cls[slot] = (uint32_t)sh.cls[rr][c0 + q] | ((uint32_t)sh.cls[rr][c0 + q + 1] << 8) |
-                       ((uint32_t)sh.cls[rr + 1][c0 + q] << 16) | ((uint32_t)sh.cls[rr + 1][c0 + q + 1] << 24);
+        sq_cls[slot] = A | (Bc << 8) | (C << 16) | (Dc << 24);
       }
       run += ((unsigned long long)n << 31) | 1u;
     }
@@ -347,6 +407,7 @@ int run2d(ctr_ctx* ctx, const ctr_mt2d_params* p, ctr_mt2d_counts* out) {
   const int rows = std::max(i_hi - i_lo, 0);
   const int tiles_i = (rows + T2_ROWS - 1) / T2_ROWS, tiles_j = (n1 - 1 + T2_COLS - 1) / T2_COLS;
   const int ntiles = tiles_i * tiles_j;
+  const int vec_ok = ((n1 & 3) == 0 && (((uintptr_t)df) & 15) == 0) ? 1 : 0;      // rows start 16-byte aligned
   if ((rc = ctr_ensure(ctx, ctx->counters, 256))) return rc;
   if (!ctx->counters_host) CTR_CUDA(ctx, cudaMallocHost(&ctx->counters_host, 256));
   if ((rc = ctr_ensure(ctx, ctx->tile_state, (size_t)ntiles * 8 + 16))) return rc;
@@ -369,7 +430,7 @@ int run2d(ctr_ctx* ctx, const ctr_mt2d_params* p, ctr_mt2d_counts* out) {
     CTR_CUDA(ctx, cudaMemcpyAsync(dctr, ctx->counters_host, sizeof init, cudaMemcpyHostToDevice, st));
     CTR_CUDA(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, (size_t)ntiles * 8 + 8, st));
     if (ntiles > 0) {
-      k2d_count<T><<<ntiles, T2_COLS, 0, st>>>(df, n0, n1, i_lo, i_hi, lv, tiles_j, ntiles, (uint32_t*)b_lin.p,
+      k2d_count<T><<<ntiles, T2_THREADS, 0, st>>>(df, n0, n1, i_lo, i_hi, lv, tiles_j, ntiles, vec_ok, (uint32_t*)b_lin.p,
                                                (uint32_t*)b_base.p, (uint32_t*)b_cls.p, cap,
                                                (unsigned long long*)ctx->tile_state.p, dctr);
       ctx->launches++;
