@@ -103,11 +103,15 @@ __global__ void __launch_bounds__(T2_THREADS) k2d_count(const T* __restrict__ f,
                                                         uint32_t* __restrict__ sq_cls, unsigned cap,
                                                         unsigned long long* status, Counters2D* ctr) {
   __shared__ Shared2D sh;
-  __shared__ T s_upp[MAXL + 2], s_eqp[MAXL + 1];
+  __shared__ T s_upp[MAXL + 2], s_eqp[MAXL + 1], s_lim[MAXL + 1];   // s_lim[k]: samples of class k below it carry no equality flag
   if (threadIdx.x == 0) sh.tile = atomicAdd(&ctr->ticket, 1u);
   const int nl = lv.n;
   if ((int)threadIdx.x <= nl + 1) s_upp[threadIdx.x] = threadIdx.x == 0 ? (T)-INFINITY : ((int)threadIdx.x <= nl ? lv.up[threadIdx.x - 1] : (T)NAN);
-  if ((int)threadIdx.x <= nl) s_eqp[threadIdx.x] = (int)threadIdx.x < nl ? lv.eqv[threadIdx.x] : (T)NAN;
+  if ((int)threadIdx.x <= nl) {
+    const T e = (int)threadIdx.x < nl ? lv.eqv[threadIdx.x] : (T)NAN;
+    s_eqp[threadIdx.x] = e;
+    s_lim[threadIdx.x] = (int)threadIdx.x < nl ? (e == e ? e : lv.up[threadIdx.x]) : (T)INFINITY;
+  }
   __syncthreads();
   const int tile = (int)sh.tile;
   const int ti = tile / tiles_j, tj = tile - ti * tiles_j;
@@ -141,13 +145,22 @@ __global__ void __launch_bounds__(T2_THREADS) k2d_count(const T* __restrict__ f,
     }
 #pragma unroll
     for (int q = 0; q < RB; ++q) {
-      uint32_t word = 0;
-      int k = (r0 + q == 0) ? class_guess(nl, lv.g0, lv.ginv, v[q][0]) : kprev;      // the row above, else arithmetic
+      uint32_t word;
+      int k = (r0 + q == 0) ? class_fix(s_upp, v[q][0], class_guess(nl, lv.g0, lv.ginv, v[q][0])) : kprev;
+      // fast path: all four samples strictly inside class k (fields are smooth: almost always) -> 2 comparisons for 4 samples
+      const T lo4 = fmin(fmin(v[q][0], v[q][1]), fmin(v[q][2], v[q][3]));
+      const T hi4 = fmax(fmax(v[q][0], v[q][1]), fmax(v[q][2], v[q][3]));
+      const bool nan4 = (v[q][0] != v[q][0]) | (v[q][1] != v[q][1]) | (v[q][2] != v[q][2]) | (v[q][3] != v[q][3]);
+      if (lo4 >= s_upp[k] && hi4 < s_lim[k] && !nan4) {
+        word = (uint32_t)k * 0x01010101u;
+      } else {
+        word = 0;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        k = class_fix(s_upp, v[q][u], k);
-        word |= class_byte(s_eqp, v[q][u], k) << (8 * u);
-        if (u == 0) kprev = k;
+        for (int u = 0; u < 4; ++u) {
+          k = class_fix(s_upp, v[q][u], k);
+          word |= class_byte(s_eqp, v[q][u], k) << (8 * u);
+          if (u == 0) kprev = k;
+        }
       }
       sh.cls[r0 + q][t] = word;
     }
