@@ -656,91 +656,79 @@ __global__ void k4_tet_filter(const double* __restrict__ verts, const int* __res
 // slices of one tetrahedron: returns the number of morph triangles; if out != nullptr writes them as
 // 3 segments x (low id, high id) with the deterministic 4-edge split (first edge in (ab,ac,ad,bc,bd,cd) order
 // of the id-sorted vertices + the edge disjoint from it are the shared pair).
-__device__ __forceinline__ int slice_tet(const double* __restrict__ verts, const int* __restrict__ tet, const MorphParams& mp,
-                                         int* __restrict__ out) {
-  int v[4] = {tet[0], tet[1], tet[2], tet[3]};
-#pragma unroll
-  for (int x = 0; x < 3; ++x)
-#pragma unroll
-    for (int y = 0; y < 3 - x; ++y)
-      if (v[y] > v[y + 1]) {
-        const int tmp = v[y];
-        v[y] = v[y + 1];
-        v[y + 1] = tmp;
+// Slicing of one tetrahedron at the midpoints of its t-gaps (morph_geometry.py:145-237), done ONCE per tetrahedron:
+// the result is a 64-bit code (up to 6 morph triangles x 3 tetrahedron edges x 3 bits) that the emit step only decodes.
+// Edge e joins corners EA(e), EB(e) of the id-sorted tetrahedron; opposite edges are e and 5 - e.
+__device__ __forceinline__ constexpr int EA(int e) { return e < 3 ? 0 : e < 5 ? 1 : 2; }
+__device__ __forceinline__ constexpr int EB(int e) { return e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 3 : e == 3 ? 2 : 3; }
+
+// per 6-bit mask of the edges cut by a slice: triangle count | (e0 | e1<<3 | e2<<6) << 2 | second triangle << 11
+__device__ __forceinline__ unsigned slice_entry(unsigned mask) {
+  int inter[6], ni = 0;
+  for (int e = 0; e < 6; ++e)
+    if ((mask >> e) & 1u) inter[ni++] = e;
+  if (ni == 3) return 1u | ((unsigned)(inter[0] | (inter[1] << 3) | (inter[2] << 6)) << 2);
+  if (ni == 4) {                                                   // morph_geometry.py:176-186
+    const int p1 = inter[0], p2 = 5 - p1;                          // the edge sharing no corner with p1
+    if (!((mask >> p2) & 1u)) return 0u;
+    unsigned out = 0, ntri = 0;
+    for (int q = 1; q < 4; ++q)
+      if (inter[q] != p2) {
+        out |= (unsigned)(p1 | (p2 << 3) | (inter[q] << 6)) << (2 + 9 * ntri);
+        ++ntri;
       }
-  if (v[0] == v[1] || v[1] == v[2] || v[2] == v[3]) return 0;
-  double tv[4], ts[4];
+    return out | ntri;
+  }
+  return 0u;
+}
+
+constexpr int SL_THREADS = 256;
+
+__device__ __forceinline__ int pick4(const int v[4], int i) { return i == 0 ? v[0] : i == 1 ? v[1] : i == 2 ? v[2] : v[3]; }
+
+// returns the number of morph triangles of the tetrahedron and their code; v = corner ids sorted, tv = their t
+__device__ __forceinline__ int slice_code(const double tv[4], const MorphParams& mp, const unsigned* __restrict__ s_tab,
+                                          unsigned long long& code) {
+  double ts[4] = {tv[0], tv[1], tv[2], tv[3]};
+#define CTR_CSWAP(a, b)            \
+  {                                \
+    const double lo = fmin(a, b);  \
+    b = fmax(a, b);                \
+    a = lo;                        \
+  }
+  CTR_CSWAP(ts[0], ts[1]) CTR_CSWAP(ts[2], ts[3]) CTR_CSWAP(ts[0], ts[2]) CTR_CSWAP(ts[1], ts[3]) CTR_CSWAP(ts[1], ts[2])
+#undef CTR_CSWAP
+  // edges whose two ends are (nearly) simultaneous: a morph triangle using one is dropped (pentatopes.py:339-348)
+  unsigned killmask = 0;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) ts[r] = tv[r] = verts[(size_t)v[r] * 4 + 3];
-#pragma unroll
-  for (int x = 0; x < 3; ++x)
-#pragma unroll
-    for (int y = 0; y < 3 - x; ++y)
-      if (ts[y] > ts[y + 1]) {
-        const double tmp = ts[y];
-        ts[y] = ts[y + 1];
-        ts[y + 1] = tmp;
-      }
-  const int ea[6] = {0, 0, 0, 1, 1, 2}, eb[6] = {1, 2, 3, 2, 3, 3};
+  for (int e = 0; e < 6; ++e)
+    if (fabs(tv[EA(e)] - tv[EB(e)]) <= mp.t_eps) killmask |= 1u << e;
   int n = 0;
-#pragma unroll 1
+  code = 0ull;
+#pragma unroll
   for (int gap = 0; gap < 3; ++gap) {
     if (!((ts[gap + 1] - ts[gap]) > mp.eps_gap)) continue;
     const double mid = 0.5 * (ts[gap + 1] + ts[gap]);
-    int inter[6], ni = 0;
+    unsigned mask = 0;
 #pragma unroll
     for (int e = 0; e < 6; ++e) {
-      double v1 = tv[ea[e]], v2 = tv[eb[e]];
-      if (v1 > v2) {
-        const double tmp = v1;
-        v1 = v2;
-        v2 = tmp;
-      }
-      if (mid + mp.eps_in < v1 || mid - mp.eps_in > v2) continue;     // morph_geometry.py:218
-      inter[ni++] = e;
+      const double v1 = fmin(tv[EA(e)], tv[EB(e)]), v2 = fmax(tv[EA(e)], tv[EB(e)]);
+      if (!(mid + mp.eps_in < v1 || mid - mp.eps_in > v2)) mask |= 1u << e;     // morph_geometry.py:218
     }
-    int ntri = 0, tri[2][3];
-    if (ni == 3) {
-      tri[0][0] = inter[0]; tri[0][1] = inter[1]; tri[0][2] = inter[2];
-      ntri = 1;
-    } else if (ni == 4) {                                            // morph_geometry.py:176-186
-      const int p1 = inter[0];
-      int p2 = -1;
-      for (int q = 1; q < 4; ++q) {
-        const int e = inter[q];
-        if (ea[e] != ea[p1] && ea[e] != eb[p1] && eb[e] != ea[p1] && eb[e] != eb[p1]) p2 = e;
-      }
-      if (p2 >= 0) {
-        for (int q = 1; q < 4; ++q)
-          if (inter[q] != p2) {
-            tri[ntri][0] = p1; tri[ntri][1] = p2; tri[ntri][2] = inter[q];
-            ++ntri;
-          }
-      }
-    }
-    for (int q = 0; q < ntri; ++q) {
-      bool kill = false;                                             // pentatopes.py:339-348
-      for (int r = 0; r < 3; ++r) {
-        const int e = tri[q][r];
-        if (fabs(tv[ea[e]] - tv[eb[e]]) <= mp.t_eps) kill = true;
-      }
-      if (kill) continue;
-      if (out) {
-        for (int r = 0; r < 3; ++r) {
-          const int e = tri[q][r];
-          const int i0 = v[ea[e]], i1 = v[eb[e]];
-          const bool swap = tv[ea[e]] > tv[eb[e]];           // morph_geometry.py:13-17: low t first
-          out[(size_t)n * 6 + r * 2 + 0] = swap ? i1 : i0;
-          out[(size_t)n * 6 + r * 2 + 1] = swap ? i0 : i1;
-        }
-      }
+    unsigned ent = s_tab[mask];
+    const unsigned ntri = ent & 3u;
+    ent >>= 2;
+    for (unsigned q = 0; q < ntri; ++q, ent >>= 9) {
+      const unsigned t9 = ent & 511u;
+      const unsigned em = (1u << (t9 & 7u)) | (1u << ((t9 >> 3) & 7u)) | (1u << (t9 >> 6));
+      if (em & killmask) continue;
+      code |= (unsigned long long)t9 << (9 * n);
       ++n;
     }
   }
   return n;
 }
 
-constexpr int SL_THREADS = 256;
 struct SlCounters {
   unsigned long long total;
   unsigned int ticket, pad;
@@ -751,14 +739,35 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
                                                        unsigned long long* status, SlCounters* ctr, int ntiles,
                                                        int* __restrict__ out, unsigned cap) {
   __shared__ unsigned s_tile;
+  __shared__ unsigned s_tab[64];
   __shared__ unsigned long long s_warp[SL_THREADS / 32], s_excl;
   if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket, 1u);
+  if (threadIdx.x < 64) s_tab[threadIdx.x] = slice_entry(threadIdx.x);
   __syncthreads();
   const int tile = (int)s_tile;
   const unsigned a = (unsigned)tile * SL_THREADS + threadIdx.x;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   int n = 0;
-  if (a < nt && keep[a]) n = slice_tet(verts, tets + (size_t)a * 4, mp, nullptr);
+  int v[4] = {0, 0, 0, 0};
+  double tv[4] = {0, 0, 0, 0};
+  unsigned long long code = 0ull;
+  if (a < nt && keep[a]) {
+    const int4 t4 = *reinterpret_cast<const int4*>(tets + (size_t)a * 4);
+    v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
+#define CTR_ISWAP(a, b)          \
+  {                              \
+    const int lo = min(a, b);    \
+    b = max(a, b);               \
+    a = lo;                      \
+  }
+    CTR_ISWAP(v[0], v[1]) CTR_ISWAP(v[2], v[3]) CTR_ISWAP(v[0], v[2]) CTR_ISWAP(v[1], v[3]) CTR_ISWAP(v[1], v[2])
+#undef CTR_ISWAP
+    if (!(v[0] == v[1] || v[1] == v[2] || v[2] == v[3])) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) tv[r] = verts[(size_t)v[r] * 4 + 3];
+      n = slice_code(tv, mp, s_tab, code);
+    }
+  }
   const unsigned long long inc = warp_incl_scan_u64((unsigned long long)n);
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
@@ -774,7 +783,21 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
   }
   __syncthreads();
   const unsigned long long off = s_excl + woff + inc - (unsigned long long)n;
-  if (n && off + n <= cap) slice_tet(verts, tets + (size_t)a * 4, mp, out + off * 6);
+  if (n && off + n <= cap) {
+    int* o = out + off * 6;
+    for (int q = 0; q < n; ++q, code >>= 9, o += 6) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int e = (int)((code >> (3 * r)) & 7ull);
+        const int ca = e < 3 ? 0 : e < 5 ? 1 : 2, cb = e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 3 : e == 3 ? 2 : 3;
+        const int i0 = pick4(v, ca), i1 = pick4(v, cb);
+        const double t0 = ca == 0 ? tv[0] : ca == 1 ? tv[1] : tv[2], t1 = cb == 1 ? tv[1] : cb == 2 ? tv[2] : tv[3];
+        const bool swap = t0 > t1;                                   // morph_geometry.py:13-17: low t first
+        o[r * 2 + 0] = swap ? i1 : i0;
+        o[r * 2 + 1] = swap ? i0 : i1;
+      }
+    }
+  }
   if (tile == ntiles - 1 && threadIdx.x == 0) ctr->total = s_excl + blk;
 }
 
