@@ -734,10 +734,33 @@ struct SlCounters {
   unsigned int ticket, pad;
 };
 
+constexpr int SL_PER = 4;                            // consecutive tetrahedra per thread (10^5 tiles of 256 would
+constexpr int SL_TILE = SL_THREADS * SL_PER;         // serialise on the ticket atomic and on the look-back)
+constexpr int SL_STAGE = 2048;                       // triangles staged in shared memory per tile (48 KB)
+
+__device__ __forceinline__ bool slice_load(const double* __restrict__ verts, const int* __restrict__ tets, unsigned a,
+                                           int v[4], double tv[4]) {
+  const int4 t4 = *reinterpret_cast<const int4*>(tets + (size_t)a * 4);
+  v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
+#define CTR_ISWAP(a, b)          \
+  {                              \
+    const int lo = min(a, b);    \
+    b = max(a, b);               \
+    a = lo;                      \
+  }
+  CTR_ISWAP(v[0], v[1]) CTR_ISWAP(v[2], v[3]) CTR_ISWAP(v[0], v[2]) CTR_ISWAP(v[1], v[3]) CTR_ISWAP(v[1], v[2])
+#undef CTR_ISWAP
+  if (v[0] == v[1] || v[1] == v[2] || v[2] == v[3]) return false;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) tv[r] = verts[(size_t)v[r] * 4 + 3];
+  return true;
+}
+
 __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict__ verts, const int* __restrict__ tets,
                                                        const uint8_t* __restrict__ keep, unsigned nt, MorphParams mp,
                                                        unsigned long long* status, SlCounters* ctr, int ntiles,
                                                        int* __restrict__ out, unsigned cap) {
+  extern __shared__ int s_out[];                     // SL_STAGE * 6 ints
   __shared__ unsigned s_tile;
   __shared__ unsigned s_tab[64];
   __shared__ unsigned long long s_warp[SL_THREADS / 32], s_excl;
@@ -745,28 +768,21 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
   if (threadIdx.x < 64) s_tab[threadIdx.x] = slice_entry(threadIdx.x);
   __syncthreads();
   const int tile = (int)s_tile;
-  const unsigned a = (unsigned)tile * SL_THREADS + threadIdx.x;
+  const unsigned a0 = (unsigned)tile * SL_TILE + threadIdx.x * SL_PER;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-  int n = 0;
-  int v[4] = {0, 0, 0, 0};
-  double tv[4] = {0, 0, 0, 0};
-  unsigned long long code = 0ull;
-  if (a < nt && keep[a]) {
-    const int4 t4 = *reinterpret_cast<const int4*>(tets + (size_t)a * 4);
-    v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
-#define CTR_ISWAP(a, b)          \
-  {                              \
-    const int lo = min(a, b);    \
-    b = max(a, b);               \
-    a = lo;                      \
-  }
-    CTR_ISWAP(v[0], v[1]) CTR_ISWAP(v[2], v[3]) CTR_ISWAP(v[0], v[2]) CTR_ISWAP(v[1], v[3]) CTR_ISWAP(v[1], v[2])
-#undef CTR_ISWAP
-    if (!(v[0] == v[1] || v[1] == v[2] || v[2] == v[3])) {
+  unsigned long long code[SL_PER];
+  int cnt[SL_PER], n = 0;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) tv[r] = verts[(size_t)v[r] * 4 + 3];
-      n = slice_code(tv, mp, s_tab, code);
+  for (int u = 0; u < SL_PER; ++u) {
+    cnt[u] = 0;
+    code[u] = 0ull;
+    const unsigned a = a0 + u;
+    if (a < nt && keep[a]) {
+      int v[4];
+      double tv[4];
+      if (slice_load(verts, tets, a, v, tv)) cnt[u] = slice_code(tv, mp, s_tab, code[u]);
     }
+    n += cnt[u];
   }
   const unsigned long long inc = warp_incl_scan_u64((unsigned long long)n);
   if (lane == 31) s_warp[warp] = inc;
@@ -782,13 +798,24 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
     if (lane == 0) s_excl = e;
   }
   __syncthreads();
-  const unsigned long long off = s_excl + woff + inc - (unsigned long long)n;
-  if (n && off + n <= cap) {
-    int* o = out + off * 6;
-    for (int q = 0; q < n; ++q, code >>= 9, o += 6) {
+  const unsigned long long base = s_excl;
+  // the tile's triangles are contiguous in the output (tetrahedron order): staged in shared memory and written out
+  // coalesced when they fit, else written directly
+  const bool staged = blk <= (unsigned long long)SL_STAGE;
+  unsigned loc = (unsigned)(woff + inc - (unsigned long long)n);           // first triangle of this thread in the tile
+#pragma unroll
+  for (int u = 0; u < SL_PER; ++u) {
+    if (!cnt[u]) continue;
+    int v[4];
+    double tv[4];
+    slice_load(verts, tets, a0 + u, v, tv);
+    unsigned long long c = code[u];
+    for (int q = 0; q < cnt[u]; ++q, c >>= 9, ++loc) {
+      if (!staged && base + loc >= cap) continue;
+      int* o = staged ? s_out + loc * 6 : out + (base + loc) * 6;
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
-        const int e = (int)((code >> (3 * r)) & 7ull);
+        const int e = (int)((c >> (3 * r)) & 7ull);
         const int ca = e < 3 ? 0 : e < 5 ? 1 : 2, cb = e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 3 : e == 3 ? 2 : 3;
         const int i0 = pick4(v, ca), i1 = pick4(v, cb);
         const double t0 = ca == 0 ? tv[0] : ca == 1 ? tv[1] : tv[2], t1 = cb == 1 ? tv[1] : cb == 2 ? tv[2] : tv[3];
@@ -797,6 +824,14 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
         o[r * 2 + 1] = swap ? i0 : i1;
       }
     }
+  }
+  if (staged) {
+    __syncthreads();
+    unsigned long long nb = blk;
+    if (base + nb > cap) nb = base < cap ? cap - base : 0ull;
+    const unsigned nint = (unsigned)nb * 6u;
+    int* dst = out + base * 6;
+    for (unsigned q = threadIdx.x; q < nint; q += SL_THREADS) dst[q] = s_out[q];
   }
   if (tile == ntiles - 1 && threadIdx.x == 0) ctr->total = s_excl + blk;
 }
@@ -1020,16 +1055,21 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
       k4_tet_filter<<<(int)((totT + 255) / 256), 256, 0, st>>>((const double*)B.mverts.p, (const int*)B.tets.p, (unsigned)totT,
                                                                mp, (uint8_t*)B.keep.p);
       ctx->launches += 4;
-      const int sl_tiles = (int)((totT + SL_THREADS - 1) / SL_THREADS);
+      const int sl_tiles = (int)((totT + SL_TILE - 1) / SL_TILE);
       if ((rc = ctr_ensure(ctx, B.slstate, (size_t)sl_tiles * 8 + 64))) return rc;
       size_t want = std::max<size_t>((size_t)totT * 2, 1 << 14);
       unsigned long long nmt = 0;
       for (int attempt = 0; attempt < 3; ++attempt) {
         if ((rc = ctr_ensure(ctx, B.mtris, want * 24))) return rc;
         const unsigned cap = (unsigned)std::min<size_t>(B.mtris.cap / 24, 0x7fffffffu);
+        static bool sl_attr = false;
+        if (!sl_attr) {
+          CTR_CUDA(ctx, cudaFuncSetAttribute(k4_slice, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_STAGE * 6 * sizeof(int))));
+          sl_attr = true;
+        }
         SlCounters* slc = (SlCounters*)((char*)B.slstate.p + (size_t)sl_tiles * 8);
         CTR_CUDA(ctx, cudaMemsetAsync(B.slstate.p, 0, (size_t)sl_tiles * 8 + 32, st));
-        k4_slice<<<sl_tiles, SL_THREADS, 0, st>>>((const double*)B.mverts.p, (const int*)B.tets.p, (const uint8_t*)B.keep.p,
+        k4_slice<<<sl_tiles, SL_THREADS, SL_STAGE * 6 * sizeof(int), st>>>((const double*)B.mverts.p, (const int*)B.tets.p, (const uint8_t*)B.keep.p,
                                                   (unsigned)totT, mp, (unsigned long long*)B.slstate.p, slc, sl_tiles,
                                                   (int*)B.mtris.p, cap);
         ctx->launches++;
