@@ -760,6 +760,12 @@ template <typename T, typename G>
 __device__ __forceinline__ void grad_at(const Grid<T>& g, int i, int j, int k, G out[3]) {
   const long long s1 = g.n2, s0 = (long long)g.n1 * g.n2;
   const T* c = g.f + ((long long)i * g.n1 + j) * g.n2 + k;
+  if (i > 0 && i < g.n0 - 1 && j > 0 && j < g.n1 - 1 && k > 0 && k < g.n2 - 1) {   // interior: plain central differences
+    out[0] = ((G)c[s0] - (G)c[-s0]) * (G)0.5;
+    out[1] = ((G)c[s1] - (G)c[-s1]) * (G)0.5;
+    out[2] = ((G)c[1] - (G)c[-1]) * (G)0.5;
+    return;
+  }
   {
     const bool lo = i > 0, hi = i < g.n0 - 1;
     G a = (G)c[hi ? s0 : 0], b = (G)c[lo ? -s0 : 0];
@@ -785,8 +791,22 @@ __device__ __forceinline__ double shfl_g(double v, int src) { return __shfl_sync
 __device__ __forceinline__ float shfl_g(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 struct Xform {
-  double origin[3], delta[3];
+  double origin[3], delta[3], inv_delta[3];
 };
+
+// geometry-mode arithmetic: IEEE in fp64 mode (positions bit-exact vs the oracle); fast approximations in fp32 mode (1e-4 rel)
+__device__ __forceinline__ double quot(double a, double b) { return a / b; }
+__device__ __forceinline__ float quot(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double inv_sqrt(double a) { return 1.0 / sqrt(a); }
+__device__ __forceinline__ float inv_sqrt(float a) { return rsqrtf(a); }
+// n-th (0-based) set bit of a 7-bit mask (__fns costs ~50 instructions)
+__device__ __forceinline__ int nth_set_bit7(unsigned m, unsigned n) {
+  int b = 0;
+  if ((unsigned)__popc(m & 0xfu) <= n) b = 4;
+  if ((unsigned)__popc(m & ((1u << (b + 2)) - 1u)) <= n) b += 2;
+  if ((unsigned)__popc(m & ((1u << (b + 1)) - 1u)) <= n) b += 1;
+  return b;
+}
 
 template <typename T, typename G>
 __global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned long long* __restrict__ own_id,
@@ -842,7 +862,7 @@ __global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned lo
       ogp[2] = shfl_g(gp[2], o);
     }
     if (!act || (size_t)vfirst + vtx >= cap_v) continue;
-    const int d = (int)__fns(o_m7, 0, (int)(vtx - o_excl) + 1) + 1;   // (n+1)-th set bit -> direction 1..7
+    const int d = nth_set_bit7(o_m7, vtx - o_excl) + 1;               // (n+1)-th set bit -> direction 1..7
     const bool p_low = o_lo != 0;
     const size_t id = (size_t)vfirst + vtx;
     const int di = (d >> 2) & 1, dj = (d >> 1) & 1, dk = d & 1;
@@ -850,7 +870,7 @@ __global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned lo
     // tetrahedral.py:476-487: key oriented (low, high) by value; ratio = (z-flow)/(fhigh-flow), 0.5 if ~0
     const G flow = p_low ? ofp : fq, fhigh = p_low ? fq : ofp;
     const G den = fhigh - flow;
-    const G ratio = (fabs((double)den) <= 1e-8) ? (G)0.5 : (v - flow) / den;
+    const G ratio = (fabs((double)den) <= 1e-8) ? (G)0.5 : quot(v - flow, den);
     // x = low + ratio*(high - low); (high-low) is +-1 or 0 per axis so the product is exact
     const G step = p_low ? ratio : -ratio;
     const int pl[3] = {p_low ? oi : oi + di, p_low ? oj : oj + dj, p_low ? ok : ok + dk};
@@ -868,11 +888,10 @@ __global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned lo
 #pragma unroll
       for (int ax = 0; ax < 3; ++ax) {
         const G gl = p_low ? ogp[ax] : gq[ax], gh = p_low ? gq[ax] : ogp[ax];
-        nn[ax] = add_rn(gl, mul_rn(ratio, gh - gl)) / (G)xf.delta[ax];
+        nn[ax] = add_rn(gl, mul_rn(ratio, gh - gl)) * (G)xf.inv_delta[ax];
         len2 = add_rn(len2, mul_rn(nn[ax], nn[ax]));
       }
-      const G len = sqrt(len2);
-      const G inv = len > (G)0 ? (G)1 / len : (G)0;
+      const G inv = len2 > (G)0 ? inv_sqrt(len2) : (G)0;
 #pragma unroll
       for (int ax = 0; ax < 3; ++ax) normals[id * 3 + ax] = nn[ax] * inv;
     }
@@ -991,11 +1010,17 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> gin, const uns
       unsigned rank = 0;
 #pragma unroll
       for (int d = 0; d < 7; ++d) rank += __popc(u[d] & below);
-      const unsigned m0 = gather7(u, b);
+      // direction masks are only needed where a voxel edge ranks behind another direction of the same point:
+      // corner (ab, 0) needs all of its 7 bits for ab < 3 (and for the id of the point at k+1), corner 6 (ab = 3) none;
+      // corners 1, 3, 5 at k+1 need the directions below 6, 4, 2; corner 7 owns no voxel edge
+      const unsigned m0 = (ab < 3) ? gather7(u, b) : 0u;
       const unsigned id0 = vbase[wi] + rank;
-      unsigned m1, id1;
-      if (b < 31) {
-        m1 = gather7(u, b + 1);
+      unsigned m1 = 0, id1 = 0;
+      if (ab == 3) {
+      } else if (b < 31) {
+        const int need = ab == 0 ? 5 : ab == 1 ? 3 : 1;
+#pragma unroll
+        for (int d = 0; d < need; ++d) m1 |= ((u[d] >> (b + 1)) & 1u) << d;
         id1 = id0 + __popc(m0);
       } else {
         // k+1 is bit 0 of the next word (it exists: the voxel is in range); its k+1 neighbour is bit 1
@@ -1172,6 +1197,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   for (int a = 0; a < 3; ++a) {
     xf.origin[a] = p->origin[a];
     xf.delta[a] = p->delta[a];
+    xf.inv_delta[a] = 1.0 / p->delta[a];
   }
   // Work lists and output pools are grow-only.  Their capacities come from earlier runs (or a guess on the first one):
   // every stage is enqueued against them without waiting for the counts -- kernels read the list lengths from the
