@@ -34,6 +34,7 @@ __constant__ uint8_t c_edge_s[19];
 __constant__ uint8_t c_edge_d[19];
 __constant__ uint8_t c_tetmask[8][8];
 __constant__ uint8_t c_tet[6][4];
+__constant__ unsigned short c_vox[256];   // corner bits -> emitting tets (6 bits) | triangle count << 8
 
 struct Counters {                    // device counter block (mirrored to pinned host memory)
   // stage 1 (bitplane)
@@ -605,19 +606,7 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_expand(Grid<T> gin, unsigned 
   Grid<T> g = gin;
   g.any_near = 0;
   if (threadIdx.x == 0) sh.nint = 0;
-  {
-    const unsigned c8 = threadIdx.x;                 // CS_THREADS == 256: one table entry per thread
-    unsigned emit = 0, nt = 0;
-#pragma unroll
-    for (int t = 0; t < 6; ++t) {
-      const unsigned tm = tet_mask_of(c8, t);
-      if (tm != 0 && tm != 15) {
-        emit |= 1u << t;
-        nt += (__popc(tm) == 2) ? 2u : 1u;
-      }
-    }
-    sh.vox[c8] = (unsigned short)(emit | (nt << 8));
-  }
+  sh.vox[threadIdx.x] = c_vox[threadIdx.x];          // CS_THREADS == 256: one table entry per thread
   __syncthreads();
   const int tile = (int)blockIdx.x;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -1120,6 +1109,22 @@ int load_tables(ctr_ctx* ctx) {
       packed[t * 16 + m] = e;
     }
   CTR_CUDA(ctx, cudaMemcpyToSymbol(c_tri_packed, packed, sizeof(packed)));
+  unsigned short vox[256];
+  {
+    const int xs[6] = {1, 3, 2, 6, 4, 5}, ys[6] = {3, 2, 6, 4, 5, 1};
+    for (unsigned c8 = 0; c8 < 256; ++c8) {
+      unsigned emit = 0, nt = 0;
+      for (int t = 0; t < 6; ++t) {
+        const unsigned tm = (c8 & 1u) | (((c8 >> 7) & 1u) << 1) | (((c8 >> xs[t]) & 1u) << 2) | (((c8 >> ys[t]) & 1u) << 3);
+        if (tm != 0 && tm != 15) {
+          emit |= 1u << t;
+          nt += CTR_TRI3_N_H[t][tm];
+        }
+      }
+      vox[c8] = (unsigned short)(emit | (nt << 8));
+    }
+  }
+  CTR_CUDA(ctx, cudaMemcpyToSymbol(c_vox, vox, sizeof(vox)));
   if (ctx->device < 64) g_tables_loaded[ctx->device] = true;
   return 0;
 }
