@@ -37,6 +37,7 @@ struct ctr_ctx {
   DevBuf tile_state;         // decoupled-lookback status words
   DevBuf counters;           // small block of device counters (see each path)
   DevBuf wmask;              // 3D: per-word (active-owner, emitting-voxel) masks
+  DevBuf wdir;               // 3D: per-word direction prefix (dirpack) of the vertex numbering
   DevBuf vox_tab;            // 3D: corner bits -> triangle list of a voxel (256 x 12 words)
   void* counters_host = nullptr;  // pinned mirror
 

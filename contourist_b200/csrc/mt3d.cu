@@ -309,6 +309,24 @@ constexpr int CS_THREADS = 256;
 constexpr int CS_ITEMS = 4;
 constexpr int CS_TILE = CS_THREADS * CS_ITEMS;
 
+// Vertex order inside a word: direction-major, then bit (k).  dirpack byte q-1 (q = 1..6) = number of used edges of
+// the word in the directions before direction index q (index = d-1); id = vbase[word] + dirbase(q) + rank of the bit
+// among the used edges of that direction.  Kept as two 32-bit halves so that every extraction is a 32-bit shift.
+__device__ __forceinline__ uint2 dir_pack(const uint32_t x[7]) {
+  unsigned c = 0;
+  uint2 dp = make_uint2(0u, 0u);
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    c += __popc(x[q]);
+    if (q < 4) dp.x |= c << (8 * q);
+    else dp.y |= c << (8 * (q - 4));
+  }
+  return dp;
+}
+__device__ __forceinline__ unsigned dir_base(uint2 dp, int q) {   // q = d-1 in 0..6, compile-time constant when unrolled
+  return q == 0 ? 0u : q <= 4 ? (dp.x >> (8 * (q - 1))) & 255u : (dp.y >> (8 * (q - 5))) & 255u;
+}
+
 // Quick test of 4 consecutive words of one row (W % 4 == 0, gw % 4 == 0): does any of their 7 x 32 owned edges cross?
 // 128-bit loads of the four rows the words touch; returns a 4-bit mask.
 template <typename T>
@@ -379,7 +397,7 @@ __device__ __forceinline__ unsigned long long rec_act(uint32_t r) {
 template <typename T>
 __global__ void __launch_bounds__(CS_THREADS, 4) k_count(Grid<T> gin, unsigned word0, unsigned nwords_scan,
                                                       uint32_t* __restrict__ rec, uint2* __restrict__ wmask,
-                                                      unsigned long long* __restrict__ tile_vt,
+                                                      uint2* __restrict__ wdir, unsigned long long* __restrict__ tile_vt,
                                                       unsigned long long* __restrict__ tile_act, Counters* ctr, int ntiles) {
   __shared__ CountShared sh;
   Grid<T> g = gin;
@@ -490,6 +508,7 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_count(Grid<T> gin, unsigned w
     sh.own[wl] = gw < emit_end ? any : 0u;
     sh.emit[wl] = em;
     wmask[gw] = make_uint2(gw < emit_end ? any : 0u, em);
+    if (v) wdir[gw] = dir_pack(x);
     ncells += __popc(em);
   }
   unsigned long long cc = ((unsigned long long)ncross << 32) | ncells;
@@ -591,7 +610,7 @@ struct ExpandShared {
 
 // Stage 2b: offsets and work lists.  Every tile knows its exclusive prefix (k_count's last block): block scan of the
 // records -> vbase[word]; the interesting words are dealt out evenly and write the compacted, ordered lists of
-//   active owners (own_id = word<<13 | bit<<8 | p_low<<7 | mask7, own_voff = first vertex id)
+//   active owners (own_id = word<<13 | bit<<8 | p_low<<7 | mask7, own_rk = 7 x 5-bit ranks within the directions)
 //   active voxels (cell_id = word<<19 | bit<<14 | emit6<<8 | corner8, cell_toff = first triangle).
 template <typename T>
 __global__ void __launch_bounds__(CS_THREADS, 4) k_expand(Grid<T> gin, unsigned word0, unsigned nwords_scan,
@@ -599,7 +618,7 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_expand(Grid<T> gin, unsigned 
                                                        const unsigned long long* __restrict__ tile_vt,
                                                        const unsigned long long* __restrict__ tile_act,
                                                        uint32_t* __restrict__ vbase, unsigned long long* __restrict__ own_id,
-                                                       uint32_t* __restrict__ own_voff, unsigned long long* __restrict__ cell_id,
+                                                       unsigned long long* __restrict__ own_rk, unsigned long long* __restrict__ cell_id,
                                                        uint32_t* __restrict__ cell_toff, unsigned cap_own, unsigned cap_cell,
                                                        Counters* ctr) {
   __shared__ ExpandShared sh;
@@ -688,17 +707,22 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_expand(Grid<T> gin, unsigned 
     if (mo) {
       uint32_t x[7];
       owner_used(g, pl, i, j, w, x);
-      unsigned vrun = sh.pv[wl], orun = sh.po[wl];
+      unsigned orun = sh.po[wl];
       while (mo) {
         const int b = __ffs(mo) - 1;
         mo &= mo - 1;
         const unsigned m7 = gather7(x, b);
         if (orun < cap_own) {
+          // rank of the point among the used edges of each direction (5 bits x 7): with the word's vbase and dirpack
+          // this gives the vertex id of every edge the point owns
+          const uint32_t below = (1u << b) - 1u;
+          unsigned long long rk = 0;
+#pragma unroll
+          for (int d = 0; d < 7; ++d) rk |= (unsigned long long)__popc(x[d] & below) << (5 * d);
           own_id[orun] = ((unsigned long long)gw << 13) | ((unsigned)b << 8) | (((pl.P[0] >> b) & 1u) << 7) | m7;
-          own_voff[orun] = vrun;
+          own_rk[orun] = rk;
         }
         ++orun;
-        vrun += __popc(m7);
       }
     }
     if (me) {
@@ -799,8 +823,9 @@ __device__ __forceinline__ int nth_set_bit7(unsigned m, unsigned n) {
 
 template <typename T, typename G>
 __global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned long long* __restrict__ own_id,
-                                                    const uint32_t* __restrict__ own_voff, const Counters* __restrict__ ctr,
-                                                    unsigned cap_own, unsigned cap_v, Xform xf,
+                                                    const unsigned long long* __restrict__ own_rk,
+                                                    const uint32_t* __restrict__ vbase, const uint2* __restrict__ wdir,
+                                                    const Counters* __restrict__ ctr, unsigned cap_own, unsigned cap_v, Xform xf,
                                                     G* __restrict__ verts, G* __restrict__ normals,
                                                     unsigned long long* __restrict__ keys, uint8_t* __restrict__ lowmin) {
   // the list length comes from the device counters: the launch may precede the host's read of the counts
@@ -811,10 +836,14 @@ __global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned lo
   if (warp_first >= n_own) return;
   const bool have = a < n_own;
   const unsigned long long oid = have ? own_id[a] : 0ull;
-  const unsigned voff = have ? own_voff[a] : 0u;
+  const unsigned long long ork = have ? own_rk[a] : 0ull;
+  const unsigned ogw = (unsigned)(oid >> 13);
+  const unsigned vb = have ? vbase[ogw] : 0u;
+  const uint2 odp = have ? wdir[ogw] : make_uint2(0u, 0u);
+  const unsigned long long dp64 = ((unsigned long long)odp.y << 32) | odp.x;
   const unsigned m7 = (unsigned)oid & 127u;
   int i = 0, j = 0, w = 0;
-  g.word_coords((unsigned)(oid >> 13), i, j, w);
+  g.word_coords(ogw, i, j, w);
   const int k = w * 32 + (int)((oid >> 8) & 31u);
   G fp = (G)0, gp[3] = {(G)0, (G)0, (G)0};
   if (have) {
@@ -825,7 +854,6 @@ __global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned lo
   const unsigned incl = warp_incl_scan_u32(cnt);
   const unsigned excl = incl - cnt;
   const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-  const unsigned vfirst = __shfl_sync(0xffffffffu, voff, 0);        // ids of a warp's vertices are consecutive
   const G v = (G)g.v;
   for (unsigned base = 0; base < total; base += 32) {
     const unsigned vtx = base + lane;
@@ -850,10 +878,14 @@ __global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned lo
       ogp[1] = shfl_g(gp[1], o);
       ogp[2] = shfl_g(gp[2], o);
     }
-    if (!act || (size_t)vfirst + vtx >= cap_v) continue;
+    const unsigned o_vb = __shfl_sync(0xffffffffu, vb, o);
+    const unsigned long long o_dp = __shfl_sync(0xffffffffu, dp64, o), o_rk = __shfl_sync(0xffffffffu, ork, o);
+    if (!act) continue;
     const int d = nth_set_bit7(o_m7, vtx - o_excl) + 1;               // (n+1)-th set bit -> direction 1..7
     const bool p_low = o_lo != 0;
-    const size_t id = (size_t)vfirst + vtx;
+    // id = word base + edges of the word in earlier directions + rank of the point in this direction
+    const size_t id = (size_t)o_vb + (d == 1 ? 0u : (unsigned)(o_dp >> (8 * (d - 2))) & 255u) + ((unsigned)(o_rk >> (5 * (d - 1))) & 31u);
+    if (id >= cap_v) continue;
     const int di = (d >> 2) & 1, dj = (d >> 1) & 1, dk = d & 1;
     const G fq = (G)g.f[((long long)(oi + di) * g.n1 + (oj + dj)) * g.n2 + (ok + dk)];
     // tetrahedral.py:476-487: key oriented (low, high) by value; ratio = (z-flow)/(fhigh-flow), 0.5 if ~0
@@ -899,50 +931,39 @@ __global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned lo
 constexpr int ET_THREADS = 128;
 __constant__ uint32_t c_tri_packed[6 * 16];    // n | slot0<<2 | slot1<<7 | ... (6 slots x 5 bits)
 
-// exact (allclose-aware) owner ids of a voxel: the rare path, kept out of line
+// edge slot e (tables.h CTR_EDGE3_*): owner corner s = a*4 + c*2 + dk and direction d, as compile-time constants
+__device__ __forceinline__ constexpr int edge_s(int e) {
+  return e < 7 ? 0 : e < 10 ? 1 : e < 13 ? 2 : e < 14 ? 3 : e < 17 ? 4 : e < 18 ? 5 : 6;
+}
+__device__ __forceinline__ constexpr int edge_d(int e) {
+  return e < 7 ? e + 1 : e == 7 ? 2 : e == 8 ? 4 : e == 9 ? 6 : e == 10 ? 1 : e == 11 ? 4 : e == 12 ? 5 : e == 13 ? 4
+         : e == 14 ? 1 : e == 15 ? 2 : e == 16 ? 3 : e == 17 ? 2 : 1;
+}
+
+// used-edge words of the voxel's four owner rows when some sample nearby is allclose to the isovalue (rare)
 template <typename T>
-__device__ __noinline__ void owner_ids_exact(const Grid<T>& g, const uint32_t* __restrict__ vbase, int i, int j, int w, int b,
-                                             unsigned idb[8], unsigned msk[8]) {
-  const uint32_t below = (1u << b) - 1u;
+__device__ __noinline__ void rows_used_exact(const Grid<T>& gin, int i, int j, int w, uint32_t X[4][7]) {
+  Grid<T> g = gin;
+  g.any_near = 1;
   for (int ab = 0; ab < 4; ++ab) {
-    const int ii = i + (ab >> 1), jj = j + (ab & 1);
     Planes pl;
-    load_planes(g, g.bits, ii, jj, w, pl);
-    uint32_t u[7];
-    owner_used(g, pl, ii, jj, w, u);
-    const unsigned wi = ((unsigned)ii * (unsigned)g.n1 + (unsigned)jj) * (unsigned)g.W + (unsigned)w;
-    unsigned rank = 0;
-    for (int d = 0; d < 7; ++d) rank += __popc(u[d] & below);
-    const unsigned m0 = gather7(u, b);
-    const unsigned id0 = vbase[wi] + rank;
-    unsigned m1, id1;
-    if (b < 31) {
-      m1 = gather7(u, b + 1);
-      id1 = id0 + __popc(m0);
-    } else {
-      Planes pn;
-      load_planes(g, g.bits, ii, jj, w + 1, pn);
-      uint32_t un[7];
-      owner_used(g, pn, ii, jj, w + 1, un);
-      m1 = gather7(un, 0);
-      id1 = vbase[wi + 1];
-    }
-    idb[ab * 2 + 0] = id0;
-    msk[ab * 2 + 0] = m0;
-    idb[ab * 2 + 1] = id1;
-    msk[ab * 2 + 1] = m1;
+    load_planes(g, g.bits, i + (ab >> 1), j + (ab & 1), w, pl);
+    owner_used(g, pl, i + (ab >> 1), j + (ab & 1), w, X[ab]);
   }
 }
 
+// One thread per emitting voxel.  The id of each of the voxel's 19 edges is vbase[owner word] + dirbase + rank of the
+// owner bit in that direction's used-edge word -- all from the 2x2 rows of bit words the voxel touches (8 loads) and
+// the (vbase, dirpack) records of those rows.
 template <typename T>
-__global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> gin, const unsigned long long* __restrict__ cell_id,
+__global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsigned long long* __restrict__ cell_id,
                                                           const uint32_t* __restrict__ cell_toff, const Counters* __restrict__ ctr,
                                                           unsigned cap_cell, unsigned cap_t,
-                                                          const uint32_t* __restrict__ vbase, int* __restrict__ tris) {
+                                                          const uint32_t* __restrict__ vbase, const uint2* __restrict__ wdir,
+                                                          int* __restrict__ tris) {
   const unsigned n_cells = min((unsigned)(ctr->total_act >> 31), cap_cell);
   __shared__ unsigned s_ids[19][ET_THREADS];
   __shared__ uint32_t s_tab[96];
-  Grid<T> g = gin;
   if (threadIdx.x < 96) s_tab[threadIdx.x] = c_tri_packed[threadIdx.x];
   __syncthreads();
   unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -950,89 +971,63 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> gin, const uns
   const unsigned long long cid = cell_id[a];
   const unsigned c8 = (unsigned)cid & 255u, emit = (unsigned)(cid >> 8) & 63u;
   const int b = (int)((cid >> 14) & 31u);
-  int i, j, w;
-  g.word_coords((unsigned)(cid >> 19), i, j, w);
-  g.any_near = g.rowflag[(size_t)i * g.n1 + j];
-
-  unsigned idb[8], msk[8];   // owner (first vertex id, mask7); index = corner s = a*4 + b*2 + dk
-  if (g.any_near) {
-    owner_ids_exact(g, vbase, i, j, w, b, idb, msk);
+  const unsigned gw0 = (unsigned)(cid >> 19);
+  const unsigned uW = (unsigned)g.W, plane_words = (unsigned)g.n1 * uW;
+  const unsigned row = g.divW.div(gw0);
+  const unsigned w = gw0 - row * uW;
+  const bool near = g.rowflag[row] != 0;
+  // the voxel's 2x2 rows: word w (P) and the same rows shifted by one sample in k (S)
+  const bool next_ok = (w + 1 < uW);
+  const unsigned wi[4] = {gw0, gw0 + uW, gw0 + plane_words, gw0 + plane_words + uW};
+  uint32_t P[4], S[4];
+  unsigned vb[4], vb1[4];
+  uint2 dp[4], dp1[4];
+#pragma unroll
+  for (int ab = 0; ab < 4; ++ab) {
+    P[ab] = g.bits[wi[ab]];
+    const uint32_t nx = next_ok ? g.bits[wi[ab] + 1] : 0u;
+    S[ab] = __funnelshift_r(P[ab], nx, 1);
+    vb[ab] = vbase[wi[ab]];
+    dp[ab] = wdir[wi[ab]];
+  }
+  // used-edge words per owner row (index ab) and direction (index d-1); only the 14 that voxel edges use.  No masks:
+  // bits below a valid edge's bit are valid edges of the same direction
+  uint32_t X[4][7];
+  if (near) {
+    const unsigned i = g.divN1.div(row);
+    rows_used_exact(g, (int)i, (int)(row - i * (unsigned)g.n1), (int)w, X);
   } else {
-    // rows (i+a, j+c), a,c in 0..2: word w (R) and the word after it (N)
-    uint32_t R[3][3], N[3][3];
-    const bool next_ok = (w + 1 < g.W);
-    const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W, gw0 = (unsigned)(cid >> 19);
+    X[0][0] = P[0] ^ S[0]; X[0][1] = P[0] ^ P[1]; X[0][2] = P[0] ^ S[1]; X[0][3] = P[0] ^ P[2];
+    X[0][4] = P[0] ^ S[2]; X[0][5] = P[0] ^ P[3]; X[0][6] = P[0] ^ S[3];
+    X[1][0] = P[1] ^ S[1]; X[1][3] = P[1] ^ P[3]; X[1][4] = P[1] ^ S[3];
+    X[2][0] = P[2] ^ S[2]; X[2][1] = P[2] ^ P[3]; X[2][2] = P[2] ^ S[3];
+    X[3][0] = P[3] ^ S[3];
+  }
+  // owner points at k+1: bit b+1 of the same word, or (b == 31) bit 0 of the next word, which has rank 0
+  const uint32_t below = (1u << b) - 1u;
+  uint32_t below1 = below | (1u << b);
+  if (b == 31) {
+    below1 = 0u;
 #pragma unroll
-    for (int ra = 0; ra < 3; ++ra)
+    for (int ab = 0; ab < 3; ++ab) {
+      vb1[ab] = vbase[wi[ab] + 1];
+      dp1[ab] = wdir[wi[ab] + 1];
+    }
+  } else {
 #pragma unroll
-      for (int rc = 0; rc < 3; ++rc) {
-        const bool ok = (i + ra < g.n0) && (j + rc < g.n1);
-        uint32_t r = 0, nx = 0;
-        if (ok) {
-          const uint32_t* p = g.bits + (gw0 + (unsigned)ra * plane_words + (unsigned)rc * (unsigned)g.W);   // 32-bit word index
-          r = p[0];
-          if (next_ok) nx = p[1];
-        }
-        R[ra][rc] = r;
-        N[ra][rc] = nx;
-      }
-    const int rem = g.n2 - w * 32;
-    const uint32_t kpt = low_mask(rem), kp1 = low_mask(rem - 1);
-    const uint32_t below = (1u << b) - 1u;
-    const bool nkpt = (rem - 32) > 0, nkp1 = (rem - 33) > 0;       // validity of bit 0 of the next word
-#pragma unroll
-    for (int ab = 0; ab < 4; ++ab) {
-      const int ra = ab >> 1, rc = ab & 1;
-      const uint32_t vi = (i + ra + 1 < g.n0) ? 0xffffffffu : 0u, vj = (j + rc + 1 < g.n1) ? 0xffffffffu : 0u;
-      const uint32_t A = R[ra][rc];
-      uint32_t u[7];
-#define CTR_S(x, y) ((R[x][y] >> 1) | (N[x][y] << 31))
-      u[0] = (A ^ CTR_S(ra, rc)) & kp1;
-      u[1] = (A ^ R[ra][rc + 1]) & kpt & vj;
-      u[2] = (A ^ CTR_S(ra, rc + 1)) & kp1 & vj;
-      u[3] = (A ^ R[ra + 1][rc]) & kpt & vi;
-      u[4] = (A ^ CTR_S(ra + 1, rc)) & kp1 & vi;
-      u[5] = (A ^ R[ra + 1][rc + 1]) & kpt & vi & vj;
-      u[6] = (A ^ CTR_S(ra + 1, rc + 1)) & kp1 & vi & vj;
-#undef CTR_S
-      const unsigned wi = gw0 + (unsigned)ra * plane_words + (unsigned)rc * (unsigned)g.W;
-      unsigned rank = 0;
-#pragma unroll
-      for (int d = 0; d < 7; ++d) rank += __popc(u[d] & below);
-      // direction masks are only needed where a voxel edge ranks behind another direction of the same point:
-      // corner (ab, 0) needs all of its 7 bits for ab < 3 (and for the id of the point at k+1), corner 6 (ab = 3) none;
-      // corners 1, 3, 5 at k+1 need the directions below 6, 4, 2; corner 7 owns no voxel edge
-      const unsigned m0 = (ab < 3) ? gather7(u, b) : 0u;
-      const unsigned id0 = vbase[wi] + rank;
-      unsigned m1 = 0, id1 = 0;
-      if (ab == 3) {
-      } else if (b < 31) {
-        const int need = ab == 0 ? 5 : ab == 1 ? 3 : 1;
-#pragma unroll
-        for (int d = 0; d < need; ++d) m1 |= ((u[d] >> (b + 1)) & 1u) << d;
-        id1 = id0 + __popc(m0);
-      } else {
-        // k+1 is bit 0 of the next word (it exists: the voxel is in range); its k+1 neighbour is bit 1
-        const uint32_t A1 = N[ra][rc] & 1u;
-        const uint32_t vi1 = vi & 1u, vj1 = vj & 1u;
-        const uint32_t p1 = nkpt ? 1u : 0u, q1 = nkp1 ? 1u : 0u;
-        m1 = ((A1 ^ ((N[ra][rc] >> 1) & 1u)) & q1) | (((A1 ^ (N[ra][rc + 1] & 1u)) & p1 & vj1) << 1) |
-             (((A1 ^ ((N[ra][rc + 1] >> 1) & 1u)) & q1 & vj1) << 2) | (((A1 ^ (N[ra + 1][rc] & 1u)) & p1 & vi1) << 3) |
-             (((A1 ^ ((N[ra + 1][rc] >> 1) & 1u)) & q1 & vi1) << 4) |
-             (((A1 ^ (N[ra + 1][rc + 1] & 1u)) & p1 & vi1 & vj1) << 5) |
-             (((A1 ^ ((N[ra + 1][rc + 1] >> 1) & 1u)) & q1 & vi1 & vj1) << 6);
-        id1 = vbase[wi + 1];
-      }
-      idb[ab * 2 + 0] = id0;
-      msk[ab * 2 + 0] = m0;
-      idb[ab * 2 + 1] = id1;
-      msk[ab * 2 + 1] = m1;
+    for (int ab = 0; ab < 3; ++ab) {
+      vb1[ab] = vb[ab];
+      dp1[ab] = dp[ab];
     }
   }
 #pragma unroll
   for (int e = 0; e < 19; ++e) {
-    const int s = c_edge_s[e], d = c_edge_d[e];
-    s_ids[e][threadIdx.x] = idb[s] + __popc(msk[s] & ((1u << (d - 1)) - 1u));
+    const int s = edge_s(e), d = edge_d(e);
+    const int ab = s >> 1;
+    unsigned id;
+    if (s & 1) id = vb1[ab] + dir_base(dp1[ab], d - 1) + __popc(X[ab][d - 1] & below1);
+    else id = vb[ab] + dir_base(dp[ab], d - 1) + __popc(X[ab][d - 1] & below);
+    s_ids[e][threadIdx.x] = id;
   }
   size_t o = cell_toff[a];
 #pragma unroll
@@ -1183,6 +1178,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   if ((rc = ctr_ensure(ctx, ctx->vbase, (size_t)(nwords + 4) * 4))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->tbase, (size_t)(nwords + 4) * 4))) return rc;     // per-word scan records
   if ((rc = ctr_ensure(ctx, ctx->wmask, (size_t)(nwords + 4) * 8))) return rc;     // (owner, voxel) masks of interesting words
+  if ((rc = ctr_ensure(ctx, ctx->wdir, (size_t)(nwords + 4) * 8))) return rc;      // per-direction vertex prefix of interesting words
   if ((rc = ctr_ensure(ctx, ctx->counters, sizeof(Counters)))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->aux[4], (size_t)nrows + 32))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->tile_state, (size_t)ntiles * 16 + 16))) return rc;
@@ -1220,7 +1216,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   unsigned long long totV = 0, totT = 0, nOwn = 0, nCell = 0, nV = 0;
   for (int attempt = 0;; ++attempt) {
     if ((rc = ctr_ensure(ctx, b_own_id, ctx->spec_own * 8, true))) return rc;
-    if ((rc = ctr_ensure(ctx, b_own_voff, ctx->spec_own * 4, true))) return rc;
+    if ((rc = ctr_ensure(ctx, b_own_voff, ctx->spec_own * 8, true))) return rc;      // own_rk
     if ((rc = ctr_ensure(ctx, b_cell_id, ctx->spec_cell * 8, true))) return rc;
     if ((rc = ctr_ensure(ctx, b_cell_toff, ctx->spec_cell * 4, true))) return rc;
     if (geom) {
@@ -1248,13 +1244,13 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
     CTR_DBG(ctx, "k_bitplane");
     ctr_stage_mark(ctx, 2);
     if (ntiles > 0) {
-      k_count<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (uint32_t*)ctx->tbase.p, (uint2*)ctx->wmask.p, st_vt, st_act,
+      k_count<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (uint32_t*)ctx->tbase.p, (uint2*)ctx->wmask.p, (uint2*)ctx->wdir.p, st_vt, st_act,
                                                 dctr, ntiles);
       ctx->launches++;
       CTR_DBG(ctx, "k_count");
       k_expand<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (const uint32_t*)ctx->tbase.p, (const uint2*)ctx->wmask.p,
                                                  st_vt, st_act, (uint32_t*)ctx->vbase.p, (unsigned long long*)b_own_id.p,
-                                                 (uint32_t*)b_own_voff.p, (unsigned long long*)b_cell_id.p,
+                                                 (unsigned long long*)b_own_voff.p, (unsigned long long*)b_cell_id.p,
                                                  (uint32_t*)b_cell_toff.p, cap_own, cap_cell, dctr);
       ctx->launches++;
       CTR_DBG(ctx, "k_expand");
@@ -1267,19 +1263,21 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
       // grids cover the expected list lengths (last run's, with head-room); blocks past the real length return at once
       const unsigned vb = (unsigned)((std::min<size_t>(cap_own, ctx->last_own + ctx->last_own / 8 + 4096) + 255) / 256);
       const unsigned long long* oid = (const unsigned long long*)b_own_id.p;
-      const uint32_t* ovo = (const uint32_t*)b_own_voff.p;
+      const unsigned long long* ovo = (const unsigned long long*)b_own_voff.p;
+      const uint32_t* dvb = (const uint32_t*)ctx->vbase.p;
+      const uint2* dwd = (const uint2*)ctx->wdir.p;
       if (f64)
-        k_emit_verts<T, double><<<vb, 256, 0, st>>>(g, oid, ovo, dctr, vb * 256u, cap_v, xf, (double*)ctx->verts.p,
+        k_emit_verts<T, double><<<vb, 256, 0, st>>>(g, oid, ovo, dvb, dwd, dctr, vb * 256u, cap_v, xf, (double*)ctx->verts.p,
                                                     want_n ? (double*)ctx->normals.p : nullptr, dkeys, dlow);
       else
-        k_emit_verts<T, float><<<vb, 256, 0, st>>>(g, oid, ovo, dctr, vb * 256u, cap_v, xf, (float*)ctx->verts.p,
+        k_emit_verts<T, float><<<vb, 256, 0, st>>>(g, oid, ovo, dvb, dwd, dctr, vb * 256u, cap_v, xf, (float*)ctx->verts.p,
                                                    want_n ? (float*)ctx->normals.p : nullptr, dkeys, dlow);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_verts");
       ctr_stage_mark(ctx, 4);
       const unsigned tb = (unsigned)((std::min<size_t>(cap_cell, ctx->last_cell + ctx->last_cell / 8 + 4096) + ET_THREADS - 1) / ET_THREADS);
       k_emit_tris<T><<<tb, ET_THREADS, 0, st>>>(g, (const unsigned long long*)b_cell_id.p, (const uint32_t*)b_cell_toff.p, dctr,
-                                                tb * (unsigned)ET_THREADS, cap_t, (const uint32_t*)ctx->vbase.p, (int*)ctx->tris.p);
+                                                tb * (unsigned)ET_THREADS, cap_t, (const uint32_t*)ctx->vbase.p, (const uint2*)ctx->wdir.p, (int*)ctx->tris.p);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_tris");
       ctr_stage_mark(ctx, 5);
