@@ -964,11 +964,14 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsig
   const unsigned n_cells = min((unsigned)(ctr->total_act >> 31), cap_cell);
   __shared__ unsigned s_ids[19][ET_THREADS];
   __shared__ uint32_t s_tab[96];
+  __shared__ int s_stage[ET_THREADS / 32][32 * 12 * 3];   // a warp's triangles (contiguous in the output), written out coalesced
   if (threadIdx.x < 96) s_tab[threadIdx.x] = c_tri_packed[threadIdx.x];
   __syncthreads();
   unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_cells) return;
-  const unsigned long long cid = cell_id[a];
+  const unsigned warp_first = a - (threadIdx.x & 31u);
+  if (warp_first >= n_cells) return;                  // warp-uniform
+  const bool valid = a < n_cells;
+  const unsigned long long cid = valid ? cell_id[a] : 0ull;   // lanes past the end run voxel 0 with nothing to emit
   const unsigned c8 = (unsigned)cid & 255u, emit = (unsigned)(cid >> 8) & 63u;
   const int b = (int)((cid >> 14) & 31u);
   const unsigned gw0 = (unsigned)(cid >> 19);
@@ -1029,22 +1032,40 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsig
     else id = vb[ab] + dir_base(dp[ab], d - 1) + __popc(X[ab][d - 1] & below);
     s_ids[e][threadIdx.x] = id;
   }
-  size_t o = cell_toff[a];
+  // 4-byte stores of a lane's own triangles would each be a partial-sector write (16 sectors per store instruction):
+  // the warp's triangles are contiguous in the output, so they are staged in shared memory and written out coalesced
+  const unsigned o = valid ? cell_toff[a] : 0u;
+  const unsigned lane = threadIdx.x & 31u;
+  int* stage = s_stage[threadIdx.x >> 5];
+  const unsigned first = __shfl_sync(0xffffffffu, o, 0);
+  unsigned nt = 0;
+  {
+    int* dst = stage + (size_t)(o - first) * 3;
 #pragma unroll
-  for (int t = 0; t < 6; ++t) {
-    if (!((emit >> t) & 1u)) continue;
-    const uint32_t e = s_tab[t * 16 + tet_mask_of(c8, t)];
-    if (o + (e & 3u) > cap_t) break;
-    int* dst = tris + o * 3;
-    dst[0] = (int)s_ids[(e >> 2) & 31u][threadIdx.x];
-    dst[1] = (int)s_ids[(e >> 7) & 31u][threadIdx.x];
-    dst[2] = (int)s_ids[(e >> 12) & 31u][threadIdx.x];
-    if ((e & 3u) == 2u) {
-      dst[3] = (int)s_ids[(e >> 17) & 31u][threadIdx.x];
-      dst[4] = (int)s_ids[(e >> 22) & 31u][threadIdx.x];
-      dst[5] = (int)s_ids[(e >> 27) & 31u][threadIdx.x];
+    for (int t = 0; t < 6; ++t) {
+      if (!((emit >> t) & 1u)) continue;
+      const uint32_t e = s_tab[t * 16 + tet_mask_of(c8, t)];
+      dst[0] = (int)s_ids[(e >> 2) & 31u][threadIdx.x];
+      dst[1] = (int)s_ids[(e >> 7) & 31u][threadIdx.x];
+      dst[2] = (int)s_ids[(e >> 12) & 31u][threadIdx.x];
+      if ((e & 3u) == 2u) {
+        dst[3] = (int)s_ids[(e >> 17) & 31u][threadIdx.x];
+        dst[4] = (int)s_ids[(e >> 22) & 31u][threadIdx.x];
+        dst[5] = (int)s_ids[(e >> 27) & 31u][threadIdx.x];
+      }
+      dst += (e & 3u) * 3;
+      nt += e & 3u;
     }
-    o += e & 3u;
+  }
+  const unsigned last = min(31u, n_cells - 1u - warp_first);
+  const unsigned end = __shfl_sync(0xffffffffu, o + nt, (int)last);
+  __syncwarp();
+  {
+    const size_t gbase = (size_t)first * 3, gcap = (size_t)cap_t * 3;
+    unsigned nint = (end - first) * 3u;
+    if (gbase + nint > gcap) nint = gbase < gcap ? (unsigned)(gcap - gbase) : 0u;
+    int* out = tris + gbase;
+    for (unsigned q = lane; q < nint; q += 32) out[q] = stage[q];
   }
 }
 
