@@ -960,13 +960,10 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsig
                                                           const uint32_t* __restrict__ cell_toff, const Counters* __restrict__ ctr,
                                                           unsigned cap_cell, unsigned cap_t,
                                                           const uint32_t* __restrict__ vbase, const uint2* __restrict__ wdir,
-                                                          int* __restrict__ tris) {
+                                                          const uint32_t* __restrict__ vox_tab, int* __restrict__ tris) {
   const unsigned n_cells = min((unsigned)(ctr->total_act >> 31), cap_cell);
   __shared__ unsigned s_ids[19][ET_THREADS];
-  __shared__ uint32_t s_tab[96];
   __shared__ int s_stage[ET_THREADS / 32][32 * 12 * 3];   // a warp's triangles (contiguous in the output), written out coalesced
-  if (threadIdx.x < 96) s_tab[threadIdx.x] = c_tri_packed[threadIdx.x];
-  __syncthreads();
   unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned warp_first = a - (threadIdx.x & 31u);
   if (warp_first >= n_cells) return;                  // warp-uniform
@@ -1040,21 +1037,34 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsig
   const unsigned first = __shfl_sync(0xffffffffu, o, 0);
   unsigned nt = 0;
   {
+    // vox_tab[c8]: 12 triangles (3 edge slots x 5 bits each) of the voxel with ALL its mixed tets emitting, then
+    // (that tet mask | triangle count << 8); a voxel that lost tets to the allclose rule takes the per-tet table
     int* dst = stage + (size_t)(o - first) * 3;
-#pragma unroll
-    for (int t = 0; t < 6; ++t) {
-      if (!((emit >> t) & 1u)) continue;
-      const uint32_t e = s_tab[t * 16 + tet_mask_of(c8, t)];
-      dst[0] = (int)s_ids[(e >> 2) & 31u][threadIdx.x];
-      dst[1] = (int)s_ids[(e >> 7) & 31u][threadIdx.x];
-      dst[2] = (int)s_ids[(e >> 12) & 31u][threadIdx.x];
-      if ((e & 3u) == 2u) {
-        dst[3] = (int)s_ids[(e >> 17) & 31u][threadIdx.x];
-        dst[4] = (int)s_ids[(e >> 22) & 31u][threadIdx.x];
-        dst[5] = (int)s_ids[(e >> 27) & 31u][threadIdx.x];
+    const uint32_t* tab = vox_tab + c8 * 13;
+    const uint32_t full = __ldg(tab + 12);
+    if (emit == (full & 63u)) {
+      nt = full >> 8;
+      for (unsigned t = 0; t < nt; ++t, dst += 3) {
+        const uint32_t e = __ldg(tab + t);
+        dst[0] = (int)s_ids[e & 31u][threadIdx.x];
+        dst[1] = (int)s_ids[(e >> 5) & 31u][threadIdx.x];
+        dst[2] = (int)s_ids[(e >> 10) & 31u][threadIdx.x];
       }
-      dst += (e & 3u) * 3;
-      nt += e & 3u;
+    } else {
+      for (int t = 0; t < 6; ++t) {
+        if (!((emit >> t) & 1u)) continue;
+        const uint32_t e = c_tri_packed[t * 16 + tet_mask_of(c8, t)];
+        dst[0] = (int)s_ids[(e >> 2) & 31u][threadIdx.x];
+        dst[1] = (int)s_ids[(e >> 7) & 31u][threadIdx.x];
+        dst[2] = (int)s_ids[(e >> 12) & 31u][threadIdx.x];
+        if ((e & 3u) == 2u) {
+          dst[3] = (int)s_ids[(e >> 17) & 31u][threadIdx.x];
+          dst[4] = (int)s_ids[(e >> 22) & 31u][threadIdx.x];
+          dst[5] = (int)s_ids[(e >> 27) & 31u][threadIdx.x];
+        }
+        dst += (e & 3u) * 3;
+        nt += e & 3u;
+      }
     }
   }
   const unsigned last = min(31u, n_cells - 1u - warp_first);
@@ -1200,6 +1210,27 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   if ((rc = ctr_ensure(ctx, ctx->tbase, (size_t)(nwords + 4) * 4))) return rc;     // per-word scan records
   if ((rc = ctr_ensure(ctx, ctx->wmask, (size_t)(nwords + 4) * 8))) return rc;     // (owner, voxel) masks of interesting words
   if ((rc = ctr_ensure(ctx, ctx->wdir, (size_t)(nwords + 4) * 8))) return rc;      // per-direction vertex prefix of interesting words
+  if (!ctx->vox_tab.p) {
+    // corner bits -> triangle list of the whole voxel (tet order, then triangle order), then (tet mask | count << 8)
+    static uint32_t tab[256 * 13];
+    const int xs[6] = {1, 3, 2, 6, 4, 5}, ys[6] = {3, 2, 6, 4, 5, 1};
+    for (unsigned c8 = 0; c8 < 256; ++c8) {
+      uint32_t* e = tab + c8 * 13;
+      for (int q = 0; q < 13; ++q) e[q] = 0;
+      unsigned k = 0, mask = 0;
+      for (int t = 0; t < 6; ++t) {
+        const unsigned m = (c8 & 1u) | (((c8 >> 7) & 1u) << 1) | (((c8 >> xs[t]) & 1u) << 2) | (((c8 >> ys[t]) & 1u) << 3);
+        if (m != 0 && m != 15) mask |= 1u << t;
+        for (int tri = 0; tri < CTR_TRI3_N_H[t][m]; ++tri, ++k)
+          e[k] = (uint32_t)(CTR_TRI3_E_H[t][m][tri * 3] & 31u) | ((uint32_t)(CTR_TRI3_E_H[t][m][tri * 3 + 1] & 31u) << 5) |
+                 ((uint32_t)(CTR_TRI3_E_H[t][m][tri * 3 + 2] & 31u) << 10);
+      }
+      e[12] = mask | (k << 8);
+    }
+    if ((rc = ctr_ensure(ctx, ctx->vox_tab, sizeof tab, true))) return rc;
+    CTR_CUDA(ctx, cudaMemcpyAsync(ctx->vox_tab.p, tab, sizeof tab, cudaMemcpyHostToDevice, st));
+    CTR_CUDA(ctx, cudaStreamSynchronize(st));
+  }
   if ((rc = ctr_ensure(ctx, ctx->counters, sizeof(Counters)))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->aux[4], (size_t)nrows + 32))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->tile_state, (size_t)ntiles * 16 + 16))) return rc;
@@ -1298,7 +1329,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
       ctr_stage_mark(ctx, 4);
       const unsigned tb = (unsigned)((std::min<size_t>(cap_cell, ctx->last_cell + ctx->last_cell / 8 + 4096) + ET_THREADS - 1) / ET_THREADS);
       k_emit_tris<T><<<tb, ET_THREADS, 0, st>>>(g, (const unsigned long long*)b_cell_id.p, (const uint32_t*)b_cell_toff.p, dctr,
-                                                tb * (unsigned)ET_THREADS, cap_t, (const uint32_t*)ctx->vbase.p, (const uint2*)ctx->wdir.p, (int*)ctx->tris.p);
+                                                tb * (unsigned)ET_THREADS, cap_t, (const uint32_t*)ctx->vbase.p, (const uint2*)ctx->wdir.p, (const uint32_t*)ctx->vox_tab.p, (int*)ctx->tris.p);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_tris");
       ctr_stage_mark(ctx, 5);
