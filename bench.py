@@ -194,13 +194,16 @@ def run_ours(args):
     eng.set_timing(True)
     flags = E.WANT_NORMALS if not os.environ.get("CTR_BENCH_NO_NORMALS") else 0   # (diagnostic switch; the metric needs normals)
     counts_dev = torch.zeros(2, dtype=torch.int64, device=dev)
+    counts_pin = torch.zeros(2, dtype=torch.int64, pin_memory=True)
     gathered = torch.zeros(2 * world, dtype=torch.int64, device=dev)
 
     def step():
         c = eng.mt3d_run(field.data_ptr(), ISOVALUE, shape=shape, dtype=np.float32, flags=flags,
                          i_lo=a - lo, i_hi=b - lo, plane_offset=lo)
         if world > 1:
-            counts_dev.copy_(torch.tensor([c.n_verts, c.n_tris], dtype=torch.int64), non_blocking=True)
+            counts_pin[0] = int(c.n_verts)
+            counts_pin[1] = int(c.n_tris)
+            counts_dev.copy_(counts_pin, non_blocking=True)
             dist.all_gather_into_tensor(gathered, counts_dev)     # -> exclusive scan = global vertex offsets
         return c
 
