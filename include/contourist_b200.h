@@ -85,7 +85,8 @@ CTR_API int ctr_host_free(ctr_ctx* ctx, void* p);
  *   tetrahedral.py:383-469  border_voxel / find_initial_voxels / expand_voxels (full scan instead of flood fill)
  *   tetrahedral.py:554-595  enumerate_voxel_triangles / enumerate_tetrahedron_triangles (case codes, triangles)
  *   tetrahedral.py:176-188,471-512  add_simplex / interpolate_pair / contour_pair_interpolation (keys, positions)
- *   tetrahedral.py:604-614  extract_surface_geometry vertex numbering (ids = rank of the key)
+ *   tetrahedral.py:604-614  extract_surface_geometry vertex numbering (deterministic: by 32-sample word of the owner
+ *                           point, then edge direction, then k; sort by key for the canonical order)
  *   tetrahedral.py:83-87 + grid_field.py:89-93  grid -> world coordinates
  */
 typedef struct {
@@ -114,7 +115,8 @@ typedef struct {
 
 CTR_API int ctr_mt3d_run(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out);
 /* verts/normals: [n_verts][3] float or double (CTR_GEOM_F64); tris: [n_tris][3] vertex ids, local to
- * this call (0 = first emitted vertex; ids >= n_verts refer to the next shard's vertices);
+ * this call (0 = first emitted vertex; ids >= n_verts refer to the next shard's vertices; vertices are numbered
+ * by owner word (plane-major), then edge direction, then k -- not by key);
  * keys/lowmin: [n_verts]; cells/codes: [n_codes] linear voxel index ((i*(n1-1)+j)*(n2-1)+k, i global)
  * and 30-bit case code (6 tets x (4-bit low mask | 16 if skipped by allclose)), unordered.            */
 CTR_API int ctr_mt3d_fetch(ctr_ctx* ctx, void* verts, void* normals, int32_t* tris, uint64_t* keys,
