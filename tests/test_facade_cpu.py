@@ -111,3 +111,19 @@ def test_engine_import_fails_loudly_without_library(monkeypatch, tmp_path):
     monkeypatch.setattr(engine, "LIB_PATH", str(tmp_path / "missing.so"))
     with pytest.raises(engine.EngineError):
         engine.load_library()
+
+
+def test_canonical_mesh_sorts_by_key_and_remaps_triangles():
+    """engine.canonical_mesh: vertices by edge key, triangle ids remapped, ids of the next shard left alone."""
+    from contourist_b200 import engine as E
+    keys = np.array([40, 8, 24, 16], dtype=np.uint64)
+    out = dict(keys=keys, lowmin=np.array([1, 0, 1, 0], dtype=np.uint8),
+               verts=np.arange(12, dtype=np.float64).reshape(4, 3), normals=None,
+               tris=np.array([[0, 1, 2], [3, 2, 5]], dtype=np.int32))
+    c = E.canonical_mesh(out)
+    assert c["keys"].tolist() == [8, 16, 24, 40]
+    assert c["lowmin"].tolist() == [0, 0, 1, 1]
+    assert np.array_equal(c["verts"], out["verts"][[1, 3, 2, 0]])
+    # old id -> new id: 0->3, 1->0, 2->2, 3->1; id 5 >= n_verts belongs to the next shard and stays
+    assert c["tris"].tolist() == [[3, 0, 2], [1, 2, 5]]
+    assert out["tris"].tolist() == [[0, 1, 2], [3, 2, 5]]          # input untouched
