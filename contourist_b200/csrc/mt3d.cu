@@ -46,10 +46,10 @@ struct Counters {                    // device counter block (mirrored to pinned
   unsigned long long n_cells;        // emitting voxels
   unsigned long long n_cross;        // strict crossings
   unsigned long long total_vt;       // packed totals over the scanned range: T << 31 | V
-  unsigned long long total_act;      // packed list lengths: voxels << 31 | owners
   unsigned long long v_emit;         // vertex count at the start of plane i_hi (vertices this call emits)
   unsigned int ticket;
   unsigned int pad1;
+  unsigned int n_own, n_cell;        // slots handed out in the owner / voxel work lists (their lengths at the end)
 };
 
 
@@ -374,35 +374,44 @@ __device__ __forceinline__ unsigned words4_interesting(const Grid<T>& g, unsigne
 }
 
 struct CountShared {
-  uint32_t own[CS_TILE], emit[CS_TILE];
   unsigned short cv[CS_TILE], ct[CS_TILE];
   unsigned short list[CS_TILE];
+  unsigned short vox[256];           // corner bits -> emitting tets (6 bits) | triangle count << 8
   unsigned long long warp_vt[CS_THREADS / 32], warp_act[CS_THREADS / 32];
+  unsigned warp_items[CS_THREADS / 32];
+  unsigned base_own, base_cell;
   unsigned nint, last;
 };
 
-// per-word record of the scan: vertices | triangles << 8 | active owners << 17 | emitting voxels << 23
-__device__ __forceinline__ uint32_t pack_rec(unsigned v, unsigned t, unsigned no, unsigned nc) {
-  return v | (t << 8) | (no << 17) | (nc << 23);
-}
+// per-word record of the scan: vertices | triangles << 8
 __device__ __forceinline__ unsigned long long rec_vt(uint32_t r) {
-  return ((unsigned long long)((r >> 8) & 511u) << 31) | (r & 255u);
-}
-__device__ __forceinline__ unsigned long long rec_act(uint32_t r) {
-  return ((unsigned long long)(r >> 23) << 31) | ((r >> 17) & 63u);
+  return ((unsigned long long)(r >> 8) << 31) | (r & 255u);
 }
 
-// Stage 2a: counts.  Tiles of 1024 words in any order, no inter-tile dependency: per-word records, the masks of the
-// interesting words, one aggregate per tile; the block that finishes last turns the aggregates into exclusive prefixes.
+// Stage 2a: counts and work lists in ONE visit of every interesting word.  Tiles of 1024 words in any order, no
+// inter-tile dependency:
+//   A  128-bit quick test (does any of the word's 7 x 32 owned edges cross?), interesting words compacted in smem;
+//   B  dealt out one per thread and round: used-edge words, per-tet words -> vertex / triangle counts (the per-word
+//      record of the scan), dirpack; the round's owner and voxel entries get slots from two atomic counters (one
+//      atomicAdd per round and list) and are written while the bit planes are still in registers:
+//        owner  (own_id = word<<13 | bit<<8 | p_low<<7 | mask7, own_rk = 7 x 5-bit ranks within the directions)
+//        voxel  (cell_id = word<<19 | bit<<14 | emit6<<8 | corner8, cell_toff = first triangle RELATIVE to tbase[word]).
+//      Neither needs the scan: vertex ids are vbase[word] + dirbase + rank, triangle offsets tbase[word] + relative.
+//   C  tile aggregate; the block that finishes last turns the aggregates into exclusive tile prefixes.
+// The lists are ordered inside a round and unordered across rounds / tiles; the mesh does not depend on their order.
 template <typename T>
 __global__ void __launch_bounds__(CS_THREADS, 4) k_count(Grid<T> gin, unsigned word0, unsigned nwords_scan,
-                                                      uint32_t* __restrict__ rec, uint2* __restrict__ wmask,
-                                                      uint2* __restrict__ wdir, unsigned long long* __restrict__ tile_vt,
-                                                      unsigned long long* __restrict__ tile_act, Counters* ctr, int ntiles) {
+                                                      uint32_t* __restrict__ rec, uint2* __restrict__ wdir,
+                                                      unsigned long long* __restrict__ own_id,
+                                                      unsigned long long* __restrict__ own_rk,
+                                                      unsigned long long* __restrict__ cell_id,
+                                                      uint32_t* __restrict__ cell_toff, unsigned cap_own, unsigned cap_cell,
+                                                      unsigned long long* __restrict__ tile_vt, Counters* ctr, int ntiles) {
   __shared__ CountShared sh;
   Grid<T> g = gin;
   g.any_near = 0;
   if (threadIdx.x == 0) sh.nint = 0;
+  sh.vox[threadIdx.x] = c_vox[threadIdx.x];          // CS_THREADS == 256: one table entry per thread
   __syncthreads();
   const int tile = (int)blockIdx.x;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -421,8 +430,6 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_count(Grid<T> gin, unsigned w
     for (int q = 0; q < CS_ITEMS; ++q) {
       sh.cv[wl0 + q] = 0;
       sh.ct[wl0 + q] = 0;
-      sh.own[wl0 + q] = 0;
-      sh.emit[wl0 + q] = 0;
     }
     const unsigned cnt = __popc(m4);
     const unsigned inc = warp_incl_scan_u32(cnt);
@@ -449,8 +456,6 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_count(Grid<T> gin, unsigned w
       }
       sh.cv[wl] = 0;
       sh.ct[wl] = 0;
-      sh.own[wl] = 0;
-      sh.emit[wl] = 0;
       const unsigned m = __ballot_sync(0xffffffffu, interesting);
       unsigned base = 0;
       if (lane == 0 && m) base = atomicAdd(&sh.nint, (unsigned)__popc(m));
@@ -461,257 +466,81 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_count(Grid<T> gin, unsigned w
   __syncthreads();
   const unsigned nint = sh.nint;
 
-  // ---- B: counts of the interesting words, one word per thread per round
+  // ---- B: the interesting words, one per thread and round
   unsigned ncross = 0, ncells = 0;
-  for (unsigned idx = threadIdx.x; idx < nint; idx += CS_THREADS) {
-    const unsigned wl = sh.list[idx];
-    const unsigned gw = word0 + tile0 + wl;
-    int i, j, w;
-    g.word_coords(gw, i, j, w);
-    g.any_near = g.rowflag[(size_t)i * g.n1 + j];
+  for (unsigned r0 = 0; r0 < nint; r0 += CS_THREADS) {
+    const unsigned idx = r0 + threadIdx.x;
+    const bool have = idx < nint;
+    unsigned gw = 0, wl = 0;
+    int i = 0, j = 0, w = 0;
     Planes pl;
-    load_planes(g, g.bits, i, j, w, pl);
-    uint32_t x[7];
-    owner_used(g, pl, i, j, w, x);
-    unsigned v = 0;
-    uint32_t any = 0;
+    uint32_t x[7] = {0, 0, 0, 0, 0, 0, 0};
+    uint32_t any = 0, em = 0;
+    if (have) {
+      wl = sh.list[idx];
+      gw = word0 + tile0 + wl;
+      g.word_coords(gw, i, j, w);
+      g.any_near = g.rowflag[(size_t)i * g.n1 + j];
+      load_planes(g, g.bits, i, j, w, pl);
+      owner_used(g, pl, i, j, w, x);
+      unsigned v = 0;
 #pragma unroll
-    for (int d = 0; d < 7; ++d) {
-      v += __popc(x[d]);
-      any |= x[d];
-    }
-    const bool cells_ok = pl.has_i1 && pl.has_j1 && i < g.i_hi;
-    unsigned t = 0;
-    uint32_t em = 0;
-    if (cells_ok) {
-      // strict crossings for owners inside the voxel range (grid_field.py:64-84)
-      if (!g.any_near) {
-#pragma unroll
-        for (int d = 0; d < 7; ++d) ncross += __popc(x[d] & pl.kp1);
-      } else {
-        uint32_t xs[7];
-        cross_words(pl, xs);
-#pragma unroll
-        for (int d = 0; d < 7; ++d) ncross += __popc(xs[d] & pl.kp1);
+      for (int d = 0; d < 7; ++d) {
+        v += __popc(x[d]);
+        any |= x[d];
       }
-      uint32_t odd[6], two[6], cand;
-      tet_words(pl, nullptr, pl.kp1, odd, two, cand);
+      const bool cells_ok = pl.has_i1 && pl.has_j1 && i < g.i_hi;
+      unsigned t = 0;
+      if (cells_ok) {
+        // strict crossings for owners inside the voxel range (grid_field.py:64-84)
+        if (!g.any_near) {
 #pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        t += __popc(odd[q]) + 2 * __popc(two[q]);
-        em |= odd[q] | two[q];
+          for (int d = 0; d < 7; ++d) ncross += __popc(x[d] & pl.kp1);
+        } else {
+          uint32_t xs[7];
+          cross_words(pl, xs);
+#pragma unroll
+          for (int d = 0; d < 7; ++d) ncross += __popc(xs[d] & pl.kp1);
+        }
+        uint32_t odd[6], two[6], cand;
+        tet_words(pl, nullptr, pl.kp1, odd, two, cand);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          t += __popc(odd[q]) + 2 * __popc(two[q]);
+          em |= odd[q] | two[q];
+        }
       }
+      if (g.any_near) count_word_exact(g, pl, i, j, w, cells_ok, ncross, t, em);
+      sh.cv[wl] = (unsigned short)v;
+      sh.ct[wl] = (unsigned short)t;
+      if (v) wdir[gw] = dir_pack(x);
+      if (gw >= emit_end) any = 0u;
+      ncells += __popc(em);
     }
-    if (g.any_near) count_word_exact(g, pl, i, j, w, cells_ok, ncross, t, em);
-    sh.cv[wl] = (unsigned short)v;
-    sh.ct[wl] = (unsigned short)t;
-    sh.own[wl] = gw < emit_end ? any : 0u;
-    sh.emit[wl] = em;
-    wmask[gw] = make_uint2(gw < emit_end ? any : 0u, em);
-    if (v) wdir[gw] = dir_pack(x);
-    ncells += __popc(em);
-  }
-  unsigned long long cc = ((unsigned long long)ncross << 32) | ncells;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cc += __shfl_xor_sync(0xffffffffu, cc, o);
-  if (lane == 0 && cc) {
-    if (cc & 0xffffffffull) atomicAdd(&ctr->n_cells, cc & 0xffffffffull);
-    if (cc >> 32) atomicAdd(&ctr->n_cross, cc >> 32);
-  }
-  __syncthreads();
-
-  // ---- records (thread t owns the 4 consecutive words 4t..4t+3) and the tile aggregate
-  unsigned long long loc_vt = 0, loc_act = 0;
-  uint32_t r4[CS_ITEMS];
-#pragma unroll
-  for (int it = 0; it < CS_ITEMS; ++it) {
-    const unsigned wl = threadIdx.x * CS_ITEMS + it;
-    r4[it] = pack_rec(sh.cv[wl], sh.ct[wl], __popc(sh.own[wl]), __popc(sh.emit[wl]));
-    loc_vt += rec_vt(r4[it]);
-    loc_act += rec_act(r4[it]);
-  }
-  {
-    const unsigned rel0 = tile0 + threadIdx.x * CS_ITEMS;
-#pragma unroll
-    for (int it = 0; it < CS_ITEMS; ++it)
-      if (rel0 + it < nwords_scan) rec[word0 + rel0 + it] = r4[it];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    loc_vt += __shfl_xor_sync(0xffffffffu, loc_vt, o);
-    loc_act += __shfl_xor_sync(0xffffffffu, loc_act, o);
-  }
-  if (lane == 0) {
-    sh.warp_vt[warp] = loc_vt;
-    sh.warp_act[warp] = loc_act;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long a = 0, b = 0;
+    // slots of this round's entries: block scan of (owners | voxels << 16), one atomicAdd per list
+    const unsigned items = (unsigned)__popc(any) | ((unsigned)__popc(em) << 16);
+    const unsigned inc = warp_incl_scan_u32(items);
+    __syncthreads();                                  // warp_items / base_* of the previous round are consumed
+    if (lane == 31) sh.warp_items[warp] = inc;
+    __syncthreads();
+    unsigned woff = 0, tot = 0;
 #pragma unroll
     for (int q = 0; q < CS_THREADS / 32; ++q) {
-      a += sh.warp_vt[q];
-      b += sh.warp_act[q];
+      if (q < (int)warp) woff += sh.warp_items[q];
+      tot += sh.warp_items[q];
     }
-    tile_vt[tile] = a;
-    tile_act[tile] = b;
-    __threadfence();
-    sh.last = (atomicAdd(&ctr->ticket, 1u) == (unsigned)ntiles - 1u) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (!sh.last) return;
-  // ---- last block: exclusive scan of the tile aggregates in place (a few thousand entries)
-  __threadfence();
-  unsigned long long carry_vt = 0, carry_act = 0;
-  for (int base = 0; base < ntiles; base += CS_THREADS) {
-    const int q = base + (int)threadIdx.x;
-    unsigned long long a = 0, b = 0;
-    if (q < ntiles) {
-      a = lb_load(&tile_vt[q]);
-      b = lb_load(&tile_act[q]);
-    }
-    const unsigned long long ia = warp_incl_scan_u64(a), ib = warp_incl_scan_u64(b);
-    __syncthreads();
-    if (lane == 31) {
-      sh.warp_vt[warp] = ia;
-      sh.warp_act[warp] = ib;
+    if (threadIdx.x == 0) {
+      sh.base_own = (tot & 0xffffu) ? atomicAdd(&ctr->n_own, tot & 0xffffu) : 0u;
+      sh.base_cell = (tot >> 16) ? atomicAdd(&ctr->n_cell, tot >> 16) : 0u;
     }
     __syncthreads();
-    unsigned long long wa = 0, wb = 0, ta = 0, tb = 0;
-#pragma unroll
-    for (int w8 = 0; w8 < CS_THREADS / 32; ++w8) {
-      if (w8 < (int)warp) {
-        wa += sh.warp_vt[w8];
-        wb += sh.warp_act[w8];
-      }
-      ta += sh.warp_vt[w8];
-      tb += sh.warp_act[w8];
-    }
-    if (q < ntiles) {
-      tile_vt[q] = carry_vt + wa + ia - a;
-      tile_act[q] = carry_act + wb + ib - b;
-    }
-    carry_vt += ta;
-    carry_act += tb;
-  }
-  if (threadIdx.x == 0) {
-    ctr->total_vt = carry_vt;
-    ctr->total_act = carry_act;
-  }
-}
-
-struct ExpandShared {
-  uint32_t pv[CS_TILE], pt[CS_TILE], po[CS_TILE], pc[CS_TILE];
-  unsigned short list[CS_TILE];
-  unsigned short vox[256];           // corner bits -> emitting tets (6 bits) | triangle count << 8
-  unsigned long long warp_vt[CS_THREADS / 32], warp_act[CS_THREADS / 32];
-  unsigned nint;
-};
-
-// Stage 2b: offsets and work lists.  Every tile knows its exclusive prefix (k_count's last block): block scan of the
-// records -> vbase[word]; the interesting words are dealt out evenly and write the compacted, ordered lists of
-//   active owners (own_id = word<<13 | bit<<8 | p_low<<7 | mask7, own_rk = 7 x 5-bit ranks within the directions)
-//   active voxels (cell_id = word<<19 | bit<<14 | emit6<<8 | corner8, cell_toff = first triangle).
-template <typename T>
-__global__ void __launch_bounds__(CS_THREADS, 4) k_expand(Grid<T> gin, unsigned word0, unsigned nwords_scan,
-                                                       const uint32_t* __restrict__ rec, const uint2* __restrict__ wmask,
-                                                       const unsigned long long* __restrict__ tile_vt,
-                                                       const unsigned long long* __restrict__ tile_act,
-                                                       uint32_t* __restrict__ vbase, unsigned long long* __restrict__ own_id,
-                                                       unsigned long long* __restrict__ own_rk, unsigned long long* __restrict__ cell_id,
-                                                       uint32_t* __restrict__ cell_toff, unsigned cap_own, unsigned cap_cell,
-                                                       Counters* ctr) {
-  __shared__ ExpandShared sh;
-  Grid<T> g = gin;
-  g.any_near = 0;
-  if (threadIdx.x == 0) sh.nint = 0;
-  sh.vox[threadIdx.x] = c_vox[threadIdx.x];          // CS_THREADS == 256: one table entry per thread
-  __syncthreads();
-  const int tile = (int)blockIdx.x;
-  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-  const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
-  const unsigned emit_end = (unsigned)g.i_hi * plane_words;
-  const unsigned tile0 = (unsigned)tile * CS_TILE;
-
-  // ---- scan: thread t owns the 4 consecutive words 4t..4t+3 (linear order)
-  unsigned long long loc_vt = 0, loc_act = 0;
-  unsigned long long item_vt[CS_ITEMS], item_act[CS_ITEMS];
-  const unsigned rel0 = tile0 + threadIdx.x * CS_ITEMS;
-  unsigned mine = 0;                                 // which of my words are interesting
-#pragma unroll
-  for (int it = 0; it < CS_ITEMS; ++it) {
-    const uint32_t r = (rel0 + it < nwords_scan) ? rec[word0 + rel0 + it] : 0u;
-    item_vt[it] = rec_vt(r);
-    item_act[it] = rec_act(r);
-    loc_vt += item_vt[it];
-    loc_act += item_act[it];
-    if (r >> 17) mine |= 1u << it;                   // has active owners or emitting voxels
-  }
-  {
-    // compact the interesting words of the tile (ordered by word)
-    const unsigned cnt = __popc(mine);
-    const unsigned inc = warp_incl_scan_u32(cnt);
-    unsigned base = 0;
-    if (lane == 31 && inc) base = atomicAdd(&sh.nint, inc);
-    base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
-#pragma unroll
-    for (int it = 0; it < CS_ITEMS; ++it)
-      if ((mine >> it) & 1u) sh.list[base++] = (unsigned short)(threadIdx.x * CS_ITEMS + it);
-  }
-  const unsigned long long inc_vt = warp_incl_scan_u64(loc_vt), inc_act = warp_incl_scan_u64(loc_act);
-  if (lane == 31) {
-    sh.warp_vt[warp] = inc_vt;
-    sh.warp_act[warp] = inc_act;
-  }
-  __syncthreads();
-  unsigned long long woff_vt = 0, woff_act = 0;
-#pragma unroll
-  for (int q = 0; q < CS_THREADS / 32; ++q) {
-    if (q < (int)warp) {
-      woff_vt += sh.warp_vt[q];
-      woff_act += sh.warp_act[q];
-    }
-  }
-  unsigned long long run_vt = tile_vt[tile] + woff_vt + inc_vt - loc_vt;
-  unsigned long long run_act = tile_act[tile] + woff_act + inc_act - loc_act;
-#pragma unroll
-  for (int it = 0; it < CS_ITEMS; ++it) {
-    const unsigned wl = threadIdx.x * CS_ITEMS + it;
-    const uint32_t vb = (uint32_t)(run_vt & 0x7fffffffull);
-    sh.pv[wl] = vb;
-    sh.pt[wl] = (uint32_t)(run_vt >> 31);
-    sh.po[wl] = (uint32_t)(run_act & 0x7fffffffull);
-    sh.pc[wl] = (uint32_t)(run_act >> 31);
-    if (rel0 + it < nwords_scan) {
-      vbase[word0 + rel0 + it] = vb;
-      if (g.i_hiv > g.i_hi && word0 + rel0 + it == emit_end) ctr->v_emit = vb;
-    }
-    run_vt += item_vt[it];
-    run_act += item_act[it];
-  }
-  __syncthreads();
-  const unsigned nint = sh.nint;
-
-  // ---- D: compacted owner / voxel lists
-  for (unsigned idx = threadIdx.x; idx < nint; idx += CS_THREADS) {
-    const unsigned wl = sh.list[idx];
-    const unsigned gw = word0 + tile0 + wl;
-    const uint2 msk = wmask[gw];
-    uint32_t mo = msk.x, me = msk.y;
-    if (!(mo | me)) continue;
-    int i, j, w;
-    g.word_coords(gw, i, j, w);
-    g.any_near = g.rowflag[(size_t)i * g.n1 + j];
-    Planes pl;
-    load_planes(g, g.bits, i, j, w, pl);
-    if (mo) {
-      uint32_t x[7];
-      owner_used(g, pl, i, j, w, x);
-      unsigned orun = sh.po[wl];
+    const unsigned excl = woff + inc - items;
+    unsigned orun = sh.base_own + (excl & 0xffffu), crun = sh.base_cell + (excl >> 16);
+    if (any) {
+      uint32_t mo = any;
       while (mo) {
         const int b = __ffs(mo) - 1;
         mo &= mo - 1;
-        const unsigned m7 = gather7(x, b);
         if (orun < cap_own) {
           // rank of the point among the used edges of each direction (5 bits x 7): with the word's vbase and dirpack
           // this gives the vertex id of every edge the point owns
@@ -719,14 +548,15 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_expand(Grid<T> gin, unsigned 
           unsigned long long rk = 0;
 #pragma unroll
           for (int d = 0; d < 7; ++d) rk |= (unsigned long long)__popc(x[d] & below) << (5 * d);
-          own_id[orun] = ((unsigned long long)gw << 13) | ((unsigned)b << 8) | (((pl.P[0] >> b) & 1u) << 7) | m7;
+          own_id[orun] = ((unsigned long long)gw << 13) | ((unsigned)b << 8) | (((pl.P[0] >> b) & 1u) << 7) | gather7(x, b);
           own_rk[orun] = rk;
         }
         ++orun;
       }
     }
-    if (me) {
-      unsigned trun = sh.pt[wl], crun = sh.pc[wl];
+    if (em) {
+      uint32_t me = em;
+      unsigned trun = 0;
       Planes npl;
       if (g.any_near) load_planes(g, g.nbits, i, j, w, npl);
       while (me) {
@@ -756,12 +586,137 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_expand(Grid<T> gin, unsigned 
         }
         if (crun < cap_cell) {
           cell_id[crun] = ((unsigned long long)gw << 19) | ((unsigned)b << 14) | (emit << 8) | c8;
-          cell_toff[crun] = trun;
+          cell_toff[crun] = trun;                           // relative to tbase[word]
         }
         ++crun;
         trun += nt;
       }
     }
+  }
+  unsigned long long cc = ((unsigned long long)ncross << 32) | ncells;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cc += __shfl_xor_sync(0xffffffffu, cc, o);
+  if (lane == 0 && cc) {
+    if (cc & 0xffffffffull) atomicAdd(&ctr->n_cells, cc & 0xffffffffull);
+    if (cc >> 32) atomicAdd(&ctr->n_cross, cc >> 32);
+  }
+  __syncthreads();
+
+  // ---- records (thread t owns the 4 consecutive words 4t..4t+3) and the tile aggregate
+  unsigned long long loc_vt = 0, loc_act = 0;
+  uint32_t r4[CS_ITEMS];
+#pragma unroll
+  for (int it = 0; it < CS_ITEMS; ++it) {
+    const unsigned wl = threadIdx.x * CS_ITEMS + it;
+    r4[it] = (uint32_t)sh.cv[wl] | ((uint32_t)sh.ct[wl] << 8);
+    loc_vt += rec_vt(r4[it]);
+  }
+  {
+    const unsigned rel0 = tile0 + threadIdx.x * CS_ITEMS;
+#pragma unroll
+    for (int it = 0; it < CS_ITEMS; ++it)
+      if (rel0 + it < nwords_scan) rec[word0 + rel0 + it] = r4[it];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    loc_vt += __shfl_xor_sync(0xffffffffu, loc_vt, o);
+    loc_act += __shfl_xor_sync(0xffffffffu, loc_act, o);
+  }
+  if (lane == 0) {
+    sh.warp_vt[warp] = loc_vt;
+    sh.warp_act[warp] = loc_act;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long a = 0, b = 0;
+#pragma unroll
+    for (int q = 0; q < CS_THREADS / 32; ++q) {
+      a += sh.warp_vt[q];
+      b += sh.warp_act[q];
+    }
+    tile_vt[tile] = a;
+    __threadfence();
+    sh.last = (atomicAdd(&ctr->ticket, 1u) == (unsigned)ntiles - 1u) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!sh.last) return;
+  // ---- last block: exclusive scan of the tile aggregates in place (a few thousand entries)
+  __threadfence();
+  unsigned long long carry_vt = 0, carry_act = 0;
+  for (int base = 0; base < ntiles; base += CS_THREADS) {
+    const int q = base + (int)threadIdx.x;
+    unsigned long long a = 0, b = 0;
+    if (q < ntiles) {
+      a = lb_load(&tile_vt[q]);
+    }
+    const unsigned long long ia = warp_incl_scan_u64(a), ib = warp_incl_scan_u64(b);
+    __syncthreads();
+    if (lane == 31) {
+      sh.warp_vt[warp] = ia;
+      sh.warp_act[warp] = ib;
+    }
+    __syncthreads();
+    unsigned long long wa = 0, wb = 0, ta = 0, tb = 0;
+#pragma unroll
+    for (int w8 = 0; w8 < CS_THREADS / 32; ++w8) {
+      if (w8 < (int)warp) {
+        wa += sh.warp_vt[w8];
+        wb += sh.warp_act[w8];
+      }
+      ta += sh.warp_vt[w8];
+      tb += sh.warp_act[w8];
+    }
+    if (q < ntiles) {
+      tile_vt[q] = carry_vt + wa + ia - a;
+    }
+    carry_vt += ta;
+    carry_act += tb;
+  }
+  if (threadIdx.x == 0) {
+    ctr->total_vt = carry_vt;
+  }
+}
+
+// Stage 2b: offsets.  Every tile knows its exclusive prefix (k_count's last block): block scan of the per-word records
+// -> vbase[word] (first vertex id of the word), tbase[word] (first triangle of the word).
+template <typename T>
+__global__ void __launch_bounds__(CS_THREADS) k_scan(Grid<T> g, unsigned word0, unsigned nwords_scan,
+                                                  const uint32_t* __restrict__ rec,
+                                                  const unsigned long long* __restrict__ tile_vt,
+                                                  uint32_t* __restrict__ vbase, uint32_t* __restrict__ tbase, Counters* ctr) {
+  __shared__ unsigned long long s_warp[CS_THREADS / 32];
+  const int tile = (int)blockIdx.x;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
+  const unsigned emit_end = (unsigned)g.i_hi * plane_words;
+  const unsigned rel0 = (unsigned)tile * CS_TILE + threadIdx.x * CS_ITEMS;    // thread t owns 4 consecutive words
+  unsigned long long item[CS_ITEMS], loc = 0;
+  if (rel0 + CS_ITEMS <= nwords_scan && ((word0 + rel0) & 3u) == 0) {
+    const uint4 r = *reinterpret_cast<const uint4*>(rec + word0 + rel0);
+    item[0] = rec_vt(r.x); item[1] = rec_vt(r.y); item[2] = rec_vt(r.z); item[3] = rec_vt(r.w);
+  } else {
+#pragma unroll
+    for (int it = 0; it < CS_ITEMS; ++it) item[it] = (rel0 + it < nwords_scan) ? rec_vt(rec[word0 + rel0 + it]) : 0ull;
+  }
+#pragma unroll
+  for (int it = 0; it < CS_ITEMS; ++it) loc += item[it];
+  const unsigned long long inc = warp_incl_scan_u64(loc);
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  unsigned long long woff = 0;
+#pragma unroll
+  for (int q = 0; q < CS_THREADS / 32; ++q)
+    if (q < (int)warp) woff += s_warp[q];
+  unsigned long long run = tile_vt[tile] + woff + inc - loc;
+#pragma unroll
+  for (int it = 0; it < CS_ITEMS; ++it) {
+    if (rel0 + it < nwords_scan) {
+      const uint32_t vb = (uint32_t)(run & 0x7fffffffull);
+      vbase[word0 + rel0 + it] = vb;
+      tbase[word0 + rel0 + it] = (uint32_t)(run >> 31);
+      if (g.i_hiv > g.i_hi && word0 + rel0 + it == emit_end) ctr->v_emit = vb;
+    }
+    run += item[it];
   }
 }
 
@@ -829,7 +784,7 @@ __global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned lo
                                                     G* __restrict__ verts, G* __restrict__ normals,
                                                     unsigned long long* __restrict__ keys, uint8_t* __restrict__ lowmin) {
   // the list length comes from the device counters: the launch may precede the host's read of the counts
-  const unsigned n_own = min((unsigned)(ctr->total_act & 0x7fffffffull), cap_own);
+  const unsigned n_own = min(ctr->n_own, cap_own);
   const unsigned lane = lane_id();
   const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;          // owner index of this lane
   const unsigned warp_first = a - lane;
@@ -959,9 +914,10 @@ template <typename T>
 __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsigned long long* __restrict__ cell_id,
                                                           const uint32_t* __restrict__ cell_toff, const Counters* __restrict__ ctr,
                                                           unsigned cap_cell, unsigned cap_t,
-                                                          const uint32_t* __restrict__ vbase, const uint2* __restrict__ wdir,
-                                                          const uint32_t* __restrict__ vox_tab, int* __restrict__ tris) {
-  const unsigned n_cells = min((unsigned)(ctr->total_act >> 31), cap_cell);
+                                                          const uint32_t* __restrict__ vbase, const uint32_t* __restrict__ tbase,
+                                                          const uint2* __restrict__ wdir, const uint32_t* __restrict__ vox_tab,
+                                                          int* __restrict__ tris) {
+  const unsigned n_cells = min(ctr->n_cell, cap_cell);
   __shared__ unsigned s_ids[19][ET_THREADS];
   __shared__ int s_stage[ET_THREADS / 32][32 * 12 * 3];   // a warp's triangles (contiguous in the output), written out coalesced
   unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1031,46 +987,59 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsig
   }
   // 4-byte stores of a lane's own triangles would each be a partial-sector write (16 sectors per store instruction):
   // the warp's triangles are contiguous in the output, so they are staged in shared memory and written out coalesced
-  const unsigned o = valid ? cell_toff[a] : 0u;
+  const unsigned o = valid ? tbase[gw0] + cell_toff[a] : 0u;       // cell_toff is relative to the word's first triangle
   const unsigned lane = threadIdx.x & 31u;
   int* stage = s_stage[threadIdx.x >> 5];
-  const unsigned first = __shfl_sync(0xffffffffu, o, 0);
+  // vox_tab[c8]: 12 triangles (3 edge slots x 5 bits each) of the voxel with ALL its mixed tets emitting, then
+  // (that tet mask | triangle count << 8); a voxel that lost tets to the allclose rule takes the per-tet table
+  const uint32_t* tab = vox_tab + c8 * 13;
+  const uint32_t full = __ldg(tab + 12);
+  const bool table_path = emit == (full & 63u);
   unsigned nt = 0;
-  {
-    // vox_tab[c8]: 12 triangles (3 edge slots x 5 bits each) of the voxel with ALL its mixed tets emitting, then
-    // (that tet mask | triangle count << 8); a voxel that lost tets to the allclose rule takes the per-tet table
-    int* dst = stage + (size_t)(o - first) * 3;
-    const uint32_t* tab = vox_tab + c8 * 13;
-    const uint32_t full = __ldg(tab + 12);
-    if (emit == (full & 63u)) {
-      nt = full >> 8;
-      for (unsigned t = 0; t < nt; ++t, dst += 3) {
-        const uint32_t e = __ldg(tab + t);
-        dst[0] = (int)s_ids[e & 31u][threadIdx.x];
-        dst[1] = (int)s_ids[(e >> 5) & 31u][threadIdx.x];
-        dst[2] = (int)s_ids[(e >> 10) & 31u][threadIdx.x];
-      }
-    } else {
-      for (int t = 0; t < 6; ++t) {
-        if (!((emit >> t) & 1u)) continue;
-        const uint32_t e = c_tri_packed[t * 16 + tet_mask_of(c8, t)];
-        dst[0] = (int)s_ids[(e >> 2) & 31u][threadIdx.x];
-        dst[1] = (int)s_ids[(e >> 7) & 31u][threadIdx.x];
-        dst[2] = (int)s_ids[(e >> 12) & 31u][threadIdx.x];
-        if ((e & 3u) == 2u) {
-          dst[3] = (int)s_ids[(e >> 17) & 31u][threadIdx.x];
-          dst[4] = (int)s_ids[(e >> 22) & 31u][threadIdx.x];
-          dst[5] = (int)s_ids[(e >> 27) & 31u][threadIdx.x];
+  if (table_path) {
+    nt = full >> 8;
+  } else {
+    for (int t = 0; t < 6; ++t)
+      if ((emit >> t) & 1u) nt += c_tri_packed[t * 16 + tet_mask_of(c8, t)] & 3u;
+  }
+  // 4-byte stores of a lane's own triangles would each be a partial-sector write (16 sectors per store instruction).
+  // Entries of one list round are in voxel order, so a warp's triangles are usually contiguous in the output: then
+  // they are staged in shared memory and written out coalesced; a warp that straddles two rounds writes directly.
+  const unsigned last = min(31u, n_cells - 1u - warp_first);
+  const unsigned prev_end = __shfl_up_sync(0xffffffffu, o + nt, 1);
+  const bool contiguous = __all_sync(0xffffffffu, lane == 0 || lane > last || prev_end == o);
+  const unsigned first = __shfl_sync(0xffffffffu, o, 0);
+  const unsigned end = __shfl_sync(0xffffffffu, o + nt, (int)last);
+  if (valid && nt) {
+    int* dst = contiguous ? stage + (size_t)(o - first) * 3 : tris + (size_t)o * 3;
+    const bool fits = contiguous || (size_t)o + nt <= (size_t)cap_t;
+    if (fits) {
+      if (table_path) {
+        for (unsigned t = 0; t < nt; ++t, dst += 3) {
+          const uint32_t e = __ldg(tab + t);
+          dst[0] = (int)s_ids[e & 31u][threadIdx.x];
+          dst[1] = (int)s_ids[(e >> 5) & 31u][threadIdx.x];
+          dst[2] = (int)s_ids[(e >> 10) & 31u][threadIdx.x];
         }
-        dst += (e & 3u) * 3;
-        nt += e & 3u;
+      } else {
+        for (int t = 0; t < 6; ++t) {
+          if (!((emit >> t) & 1u)) continue;
+          const uint32_t e = c_tri_packed[t * 16 + tet_mask_of(c8, t)];
+          dst[0] = (int)s_ids[(e >> 2) & 31u][threadIdx.x];
+          dst[1] = (int)s_ids[(e >> 7) & 31u][threadIdx.x];
+          dst[2] = (int)s_ids[(e >> 12) & 31u][threadIdx.x];
+          if ((e & 3u) == 2u) {
+            dst[3] = (int)s_ids[(e >> 17) & 31u][threadIdx.x];
+            dst[4] = (int)s_ids[(e >> 22) & 31u][threadIdx.x];
+            dst[5] = (int)s_ids[(e >> 27) & 31u][threadIdx.x];
+          }
+          dst += (e & 3u) * 3;
+        }
       }
     }
   }
-  const unsigned last = min(31u, n_cells - 1u - warp_first);
-  const unsigned end = __shfl_sync(0xffffffffu, o + nt, (int)last);
-  __syncwarp();
-  {
+  if (contiguous) {
+    __syncwarp();
     const size_t gbase = (size_t)first * 3, gcap = (size_t)cap_t * 3;
     unsigned nint = (end - first) * 3u;
     if (gbase + nint > gcap) nint = gbase < gcap ? (unsigned)(gcap - gbase) : 0u;
@@ -1208,7 +1177,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   if ((rc = ctr_ensure(ctx, ctx->nbits, (size_t)(nwords + 4) * 4))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->vbase, (size_t)(nwords + 4) * 4))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->tbase, (size_t)(nwords + 4) * 4))) return rc;     // per-word scan records
-  if ((rc = ctr_ensure(ctx, ctx->wmask, (size_t)(nwords + 4) * 8))) return rc;     // (owner, voxel) masks of interesting words
+  if ((rc = ctr_ensure(ctx, ctx->wmask, (size_t)(nwords + 4) * 4))) return rc;     // tbase: first triangle of each word
   if ((rc = ctr_ensure(ctx, ctx->wdir, (size_t)(nwords + 4) * 8))) return rc;      // per-direction vertex prefix of interesting words
   if (!ctx->vox_tab.p) {
     // corner bits -> triangle list of the whole voxel (tet order, then triangle order), then (tet mask | count << 8)
@@ -1240,7 +1209,6 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   g.rowflag = (const uint8_t*)ctx->aux[4].p;
   Counters* dctr = (Counters*)ctx->counters.p;
   unsigned long long* st_vt = (unsigned long long*)ctx->tile_state.p;
-  unsigned long long* st_act = st_vt + ntiles;
 
   const bool geom = !(p->flags & CTR_NO_GEOMETRY);
   const bool f64 = (p->flags & CTR_GEOM_F64) != 0;
@@ -1283,7 +1251,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
     const unsigned cap_v = (unsigned)std::min<size_t>(ctx->spec_v, 0x7fffffffu);
     const unsigned cap_t = (unsigned)std::min<size_t>(ctx->spec_t, 0x7fffffffu);
 
-    k_reset3<<<64, 256, 0, st>>>(dctr, (uint4*)ctx->aux[4].p, (size_t)(nrows + 15) / 16, st_vt, (size_t)ntiles * 2);
+    k_reset3<<<64, 256, 0, st>>>(dctr, (uint4*)ctx->aux[4].p, (size_t)(nrows + 15) / 16, st_vt, (size_t)ntiles);
     ctx->launches++;
     CTR_DBG(ctx, "k_reset3");
     if (p->flags & CTR_WANT_MINMAX)
@@ -1296,16 +1264,16 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
     CTR_DBG(ctx, "k_bitplane");
     ctr_stage_mark(ctx, 2);
     if (ntiles > 0) {
-      k_count<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (uint32_t*)ctx->tbase.p, (uint2*)ctx->wmask.p, (uint2*)ctx->wdir.p, st_vt, st_act,
-                                                dctr, ntiles);
+      k_count<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (uint32_t*)ctx->tbase.p, (uint2*)ctx->wdir.p,
+                                                (unsigned long long*)b_own_id.p, (unsigned long long*)b_own_voff.p,
+                                                (unsigned long long*)b_cell_id.p, (uint32_t*)b_cell_toff.p, cap_own, cap_cell,
+                                                st_vt, dctr, ntiles);
       ctx->launches++;
       CTR_DBG(ctx, "k_count");
-      k_expand<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (const uint32_t*)ctx->tbase.p, (const uint2*)ctx->wmask.p,
-                                                 st_vt, st_act, (uint32_t*)ctx->vbase.p, (unsigned long long*)b_own_id.p,
-                                                 (unsigned long long*)b_own_voff.p, (unsigned long long*)b_cell_id.p,
-                                                 (uint32_t*)b_cell_toff.p, cap_own, cap_cell, dctr);
+      k_scan<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (const uint32_t*)ctx->tbase.p, st_vt, (uint32_t*)ctx->vbase.p,
+                                               (uint32_t*)ctx->wmask.p, dctr);
       ctx->launches++;
-      CTR_DBG(ctx, "k_expand");
+      CTR_DBG(ctx, "k_scan");
     }
     CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     ctr_stage_mark(ctx, 3);
@@ -1329,7 +1297,8 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
       ctr_stage_mark(ctx, 4);
       const unsigned tb = (unsigned)((std::min<size_t>(cap_cell, ctx->last_cell + ctx->last_cell / 8 + 4096) + ET_THREADS - 1) / ET_THREADS);
       k_emit_tris<T><<<tb, ET_THREADS, 0, st>>>(g, (const unsigned long long*)b_cell_id.p, (const uint32_t*)b_cell_toff.p, dctr,
-                                                tb * (unsigned)ET_THREADS, cap_t, (const uint32_t*)ctx->vbase.p, (const uint2*)ctx->wdir.p, (const uint32_t*)ctx->vox_tab.p, (int*)ctx->tris.p);
+                                                tb * (unsigned)ET_THREADS, cap_t, (const uint32_t*)ctx->vbase.p, (const uint32_t*)ctx->wmask.p, (const uint2*)ctx->wdir.p,
+                                                (const uint32_t*)ctx->vox_tab.p, (int*)ctx->tris.p);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_tris");
       ctr_stage_mark(ctx, 5);
@@ -1346,8 +1315,8 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
     memcpy(&h, ctx->counters_host, sizeof h);
     totV = h.total_vt & 0x7fffffffull;
     totT = h.total_vt >> 31;
-    nOwn = h.total_act & 0x7fffffffull;
-    nCell = h.total_act >> 31;
+    nOwn = h.n_own;
+    nCell = h.n_cell;
     nV = (g.i_hiv > g.i_hi) ? h.v_emit : totV;
     if (totV >= 0x7ffffff0ull || totT >= 0x7ffffff0ull)
       return ctr_fail(ctx, CTR_ERR_OVERFLOW, "more than 2^31 vertices or triangles in one call; shard the volume");
