@@ -703,18 +703,24 @@ __device__ __forceinline__ int slice_code(const double tv[4], const MorphParams&
 #pragma unroll
   for (int e = 0; e < 6; ++e)
     if (fabs(tv[EA(e)] - tv[EB(e)]) <= mp.t_eps) killmask |= 1u << e;
+  // t-extent of every edge, once (the three slices test the same six intervals)
+  double e_lo[6], e_hi[6];
+#pragma unroll
+  for (int e = 0; e < 6; ++e) {
+    e_lo[e] = fmin(tv[EA(e)], tv[EB(e)]);
+    e_hi[e] = fmax(tv[EA(e)], tv[EB(e)]);
+  }
   int n = 0;
   code = 0ull;
 #pragma unroll
   for (int gap = 0; gap < 3; ++gap) {
     if (!((ts[gap + 1] - ts[gap]) > mp.eps_gap)) continue;
     const double mid = 0.5 * (ts[gap + 1] + ts[gap]);
+    const double mid_hi = mid + mp.eps_in, mid_lo = mid - mp.eps_in;
     unsigned mask = 0;
 #pragma unroll
-    for (int e = 0; e < 6; ++e) {
-      const double v1 = fmin(tv[EA(e)], tv[EB(e)]), v2 = fmax(tv[EA(e)], tv[EB(e)]);
-      if (!(mid + mp.eps_in < v1 || mid - mp.eps_in > v2)) mask |= 1u << e;     // morph_geometry.py:218
-    }
+    for (int e = 0; e < 6; ++e)
+      if (!(mid_hi < e_lo[e] || mid_lo > e_hi[e])) mask |= 1u << e;     // morph_geometry.py:218
     unsigned ent = s_tab[mask];
     const unsigned ntri = ent & 3u;
     ent >>= 2;
@@ -810,16 +816,21 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
     double tv[4];
     slice_load(verts, tets, a0 + u, v, tv);
     unsigned long long c = code[u];
+    // low-t end first (morph_geometry.py:13-17): one bit per edge, then only 32-bit selects per triangle corner
+    unsigned swapmask = 0;
+#pragma unroll
+    for (int e = 0; e < 6; ++e)
+      if (tv[EA(e)] > tv[EB(e)]) swapmask |= 1u << e;
     for (int q = 0; q < cnt[u]; ++q, c >>= 9, ++loc) {
       if (!staged && base + loc >= cap) continue;
       int* o = staged ? s_out + loc * 6 : out + (base + loc) * 6;
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const int e = (int)((c >> (3 * r)) & 7ull);
-        const int ca = e < 3 ? 0 : e < 5 ? 1 : 2, cb = e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 3 : e == 3 ? 2 : 3;
+        // corners of edge e: EA = {0,0,0,1,1,2}, EB = {1,2,3,2,3,3} as 2-bit fields
+        const int ca = (0x940 >> (2 * e)) & 3, cb = (0xfb9 >> (2 * e)) & 3;
         const int i0 = pick4(v, ca), i1 = pick4(v, cb);
-        const double t0 = ca == 0 ? tv[0] : ca == 1 ? tv[1] : tv[2], t1 = cb == 1 ? tv[1] : cb == 2 ? tv[2] : tv[3];
-        const bool swap = t0 > t1;                                   // morph_geometry.py:13-17: low t first
+        const bool swap = (swapmask >> e) & 1u;
         o[r * 2 + 0] = swap ? i1 : i0;
         o[r * 2 + 1] = swap ? i0 : i1;
       }
