@@ -61,6 +61,7 @@ struct Grid {
   int n0, n1, n2, W;
   int i_lo, i_hi, i_hiv;             // emit planes [i_lo, i_hi); scanned owner planes [i_lo, i_hiv)
   long long plane_offset;
+  unsigned id_base;                  // added to every vertex id written into the triangles
   double v;                          // isovalue
   double tolv;                       // 1e-8 + 1e-5*|v|
   // allclose handling is local: rowflag[i*n1+j] != 0 iff some sample of rows (i..i+2, j..j+2) lies inside the
@@ -943,7 +944,7 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsig
     P[ab] = g.bits[wi[ab]];
     const uint32_t nx = next_ok ? g.bits[wi[ab] + 1] : 0u;
     S[ab] = __funnelshift_r(P[ab], nx, 1);
-    vb[ab] = vbase[wi[ab]];
+    vb[ab] = vbase[wi[ab]] + g.id_base;
     dp[ab] = wdir[wi[ab]];
   }
   // used-edge words per owner row (index ab) and direction (index d-1); only the 14 that voxel edges use.  No masks:
@@ -966,7 +967,7 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsig
     below1 = 0u;
 #pragma unroll
     for (int ab = 0; ab < 3; ++ab) {
-      vb1[ab] = vbase[wi[ab] + 1];
+      vb1[ab] = vbase[wi[ab] + 1] + g.id_base;
       dp1[ab] = wdir[wi[ab] + 1];
     }
   } else {
@@ -1163,6 +1164,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   g.i_hi = (int)p->i_hi;
   g.i_hiv = std::min(g.i_hi + 1, n0);
   g.plane_offset = p->plane_offset;
+  g.id_base = (unsigned)p->vert_id_base;
   g.v = p->isovalue;
   g.tolv = 1e-8 + 1e-5 * fabs(p->isovalue);
   g.any_near = 0;
@@ -1377,6 +1379,7 @@ extern "C" int ctr_mt3d_run(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_cou
   if (p->n0 < 2 || p->n1 < 2 || p->n2 < 2) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "grid must have at least 2 samples per axis");
   if (p->n0 > 0x7ffffff0ll || p->n1 > 0x7ffffff0ll || p->n2 > 0x7ffffff0ll) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "axis too long");
   if (p->i_lo < 0 || p->i_hi > p->n0 || p->i_lo >= p->i_hi) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "bad slab range [i_lo, i_hi)");
+  if (p->vert_id_base < 0 || p->vert_id_base > 0x7fffffffll) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "vert_id_base out of range");
   if (!(p->isovalue == p->isovalue)) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "isovalue is NaN");
   for (int a = 0; a < 3; ++a)
     if (p->delta[a] == 0.0) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "delta must be non-zero");

@@ -30,7 +30,8 @@ class Mt3dParams(ctypes.Structure):
     _fields_ = [("field", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("flags", ctypes.c_uint32),
                 ("n0", ctypes.c_int64), ("n1", ctypes.c_int64), ("n2", ctypes.c_int64),
                 ("isovalue", ctypes.c_double), ("origin", ctypes.c_double * 3), ("delta", ctypes.c_double * 3),
-                ("i_lo", ctypes.c_int64), ("i_hi", ctypes.c_int64), ("plane_offset", ctypes.c_int64)]
+                ("i_lo", ctypes.c_int64), ("i_hi", ctypes.c_int64), ("plane_offset", ctypes.c_int64),
+                ("vert_id_base", ctypes.c_int64)]
 
 
 class Mt3dCounts(ctypes.Structure):
@@ -107,6 +108,12 @@ class Engine(object):
 
     def close(self):
         if getattr(self, "h", None):
+            if self.__dict__.get("_xpool") is not None:
+                self._xpool.shutdown(wait=True)
+                self._xpool = None
+            if self.__dict__.get("_twin") is not None:
+                self._twin.close()
+                self._twin = None
             for ptr, _ in getattr(self, "_pinned", {}).values():
                 self.lib.ctr_host_free(self.h, ptr)
             self._pinned = {}
@@ -160,7 +167,7 @@ class Engine(object):
 
     # ------------------------------------------------------------------ 3D
     def mt3d_run(self, field, value, origin=(0.0, 0.0, 0.0), delta=(1.0, 1.0, 1.0), flags=0,
-                 i_lo=0, i_hi=None, plane_offset=0, shape=None, dtype=None):
+                 i_lo=0, i_hi=None, plane_offset=0, shape=None, dtype=None, vert_id_base=0):
         """field: C-contiguous numpy array [n0,n1,n2] float32/float64, or an integer device pointer
         (then pass shape, dtype and FIELD_ON_DEVICE).  Returns Mt3dCounts."""
         p = Mt3dParams()
@@ -188,6 +195,7 @@ class Engine(object):
         p.i_lo = int(i_lo)
         p.i_hi = int(p.n0 if i_hi is None else i_hi)
         p.plane_offset = int(plane_offset)
+        p.vert_id_base = int(vert_id_base)
         c = Mt3dCounts()
         self._check(self.lib.ctr_mt3d_run(self.h, ctypes.byref(p), ctypes.byref(c)), "ctr_mt3d_run")
         self._last3 = (flags, c)
@@ -219,6 +227,90 @@ class Engine(object):
                                             _ptr(a_c), _ptr(a_d)), "ctr_mt3d_fetch")
         out.update(verts=a_v, normals=a_n, tris=a_t, keys=a_k, lowmin=a_l, cells=a_c, codes=a_d)
         return out
+
+    def mt3d_extract_host(self, field, value, origin=(0.0, 0.0, 0.0), delta=(1.0, 1.0, 1.0), flags=0, nslabs=4):
+        """Host array in, host mesh out, with the PCIe traffic of the two directions overlapped.
+
+        The volume is cut into `nslabs` z-slabs (sharding.slab_with_halo, the multi-GPU decomposition); slab s is
+        uploaded and extracted on one of two alternating contexts while a worker thread downloads the mesh of slab
+        s-1 from the other (PCIe is full duplex; ctypes releases the GIL).  Triangle ids are global: each slab's run
+        gets the vertex count of the slabs before it as `vert_id_base`.  `field` should be page-locked
+        (Engine.pinned_empty) for full transfer rate.  Returns (totals dict, arrays dict); the arrays live in the
+        engine's page-locked pool and are overwritten by the next call."""
+        from concurrent.futures import ThreadPoolExecutor
+        from . import sharding
+        if not (isinstance(field, np.ndarray) and field.ndim == 3 and field.flags["C_CONTIGUOUS"]):
+            raise ValueError("mt3d_extract_host needs a C-contiguous 3D numpy array")
+        if field.dtype not in (np.float32, np.float64):
+            raise ValueError("float32 / float64 samples expected")
+        flags &= ~(FIELD_ON_DEVICE | WANT_CODES | NO_GEOMETRY)
+        n0 = field.shape[0]
+        nslabs = max(1, min(int(nslabs), n0 - 1))
+        twin = self.__dict__.get("_twin")
+        if twin is None or twin.h is None:
+            twin = self._twin = Engine(self.device)
+        engines = (self, twin)
+        pool = self.__dict__.setdefault("_xpool", ThreadPoolExecutor(max_workers=1))
+        gd = np.float64 if flags & GEOM_F64 else np.float32
+        gsz = np.dtype(gd).itemsize
+        want_n, want_k = bool(flags & WANT_NORMALS), bool(flags & WANT_KEYS)
+        cap_v, cap_t = self.__dict__.get("_xcap", (0, 0))
+        bufs = {}
+
+        def alloc(cv, ct):
+            bufs["verts"] = self.pinned_empty("x_v", (cv, 3), gd)
+            bufs["normals"] = self.pinned_empty("x_n", (cv, 3), gd) if want_n else None
+            bufs["tris"] = self.pinned_empty("x_t", (ct, 3), np.int32)
+            bufs["keys"] = self.pinned_empty("x_k", (cv,), np.uint64) if want_k else None
+            bufs["lowmin"] = self.pinned_empty("x_l", (cv,), np.uint8) if want_k else None
+
+        def fetch(eng, voff, toff, nv, nt):
+            def at(a, off, item):
+                return None if a is None else ctypes.c_void_p(a.ctypes.data + off * item)
+            eng._check(eng.lib.ctr_mt3d_fetch(eng.h, at(bufs["verts"], voff, 3 * gsz), at(bufs["normals"], voff, 3 * gsz),
+                                              at(bufs["tris"], toff, 12), at(bufs["keys"], voff, 8),
+                                              at(bufs["lowmin"], voff, 1), None, None), "ctr_mt3d_fetch")
+
+        for attempt in range(2):
+            if cap_v and cap_t:
+                alloc(cap_v, cap_t)
+            pending = [None, None]
+            vsum = tsum = 0
+            totals = dict(n_active_cells=0, n_crossings=0)
+            sizes = []
+            overflow = False
+            for s_i, (a, b) in enumerate(sharding.slab_bounds(n0, nslabs)):
+                if b <= a:
+                    continue
+                lo, hi, kw = sharding.slab_with_halo(a, b, n0)
+                eng = engines[s_i & 1]
+                if pending[s_i & 1] is not None:
+                    pending[s_i & 1].result()                 # its previous slab has been downloaded
+                    pending[s_i & 1] = None
+                c = eng.mt3d_run(field[lo:hi], value, origin=origin, delta=delta, flags=flags, vert_id_base=vsum, **kw)
+                nv, nt = int(c.n_verts), int(c.n_tris)
+                sizes.append((nv, nt))
+                totals["n_active_cells"] += int(c.n_active_cells)
+                totals["n_crossings"] += int(c.n_crossings)
+                if not overflow and vsum + nv <= cap_v and tsum + nt <= cap_t:
+                    pending[s_i & 1] = pool.submit(fetch, eng, vsum, tsum, nv, nt)
+                else:
+                    overflow = True                           # first call (sizes unknown) or a larger mesh than before
+                vsum += nv
+                tsum += nt
+            for f in pending:
+                if f is not None:
+                    f.result()
+            cap_v = max(cap_v, vsum + vsum // 4 + 1024)
+            cap_t = max(cap_t, tsum + tsum // 4 + 1024)
+            self._xcap = (cap_v, cap_t)
+            if not overflow:
+                break
+        totals.update(n_verts=vsum, n_tris=tsum, slabs=sizes)
+        out = dict(verts=bufs["verts"][:vsum], normals=None if bufs["normals"] is None else bufs["normals"][:vsum],
+                   tris=bufs["tris"][:tsum], keys=None if bufs["keys"] is None else bufs["keys"][:vsum],
+                   lowmin=None if bufs["lowmin"] is None else bufs["lowmin"][:vsum], cells=None, codes=None)
+        return totals, out
 
     # ------------------------------------------------------------------ 2D
     def mt2d_run(self, field, levels, origin=(0.0, 0.0), delta=(1.0, 1.0), flags=0, i_lo=0, i_hi=None,

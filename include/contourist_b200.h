@@ -102,6 +102,9 @@ typedef struct {
    * 1 below for normals, 2 above for the ids of the next shard's first plane).  plane_offset is the
    * global index of array plane 0; keys and positions are global.                                   */
   int64_t i_lo, i_hi, plane_offset;
+  /* added to every vertex id written into the triangles: the number of vertices of the shards before this one, when
+   * the caller already knows it (slab-by-slab runs on one device: contourist_b200/engine.py mt3d_extract_host).     */
+  int64_t vert_id_base;
 } ctr_mt3d_params;
 
 typedef struct {

@@ -161,6 +161,26 @@ def test_slab_sharding_matches_single_run(engine):
         assert np.array_equal(np.concatenate(tris), ref["tris"].astype(np.int64))
 
 
+def test_pipelined_host_extraction_equals_single_run(engine):
+    """engine.mt3d_extract_host (slab-by-slab upload / extract / download on two contexts, global triangle ids via
+    vert_id_base) returns exactly the mesh of one ctr_mt3d_run + ctr_mt3d_fetch."""
+    from contourist_b200 import engine as E
+    rng = np.random.default_rng(5)
+    g = np.linspace(-1, 1, 61)
+    X, Y, Z = np.meshgrid(g, g[:40], g[:70], indexing="ij")
+    f = (np.sin(5 * X) * np.cos(3 * Y) + Z * Z + 0.05 * rng.standard_normal(X.shape)).astype(np.float32)
+    flags = E.WANT_KEYS | E.WANT_NORMALS
+    c = engine.mt3d_run(f, 0.2, origin=(1, 2, 3), delta=(0.5, 0.25, 2), flags=flags)
+    ref = engine.mt3d_fetch()
+    for nslabs in (1, 3, 4):
+        for rep in range(2):                             # first call sizes its pools, the second runs overlapped
+            tot, out = engine.mt3d_extract_host(f, 0.2, origin=(1, 2, 3), delta=(0.5, 0.25, 2), flags=flags, nslabs=nslabs)
+            assert tot["n_verts"] == c.n_verts and tot["n_tris"] == c.n_tris
+            assert tot["n_active_cells"] == c.n_active_cells and tot["n_crossings"] == c.n_crossings
+            for name in ("keys", "lowmin", "verts", "normals", "tris"):
+                assert np.array_equal(out[name], ref[name]), (name, nslabs, rep)
+
+
 def test_full_size_properties_512(engine):
     """BASELINE config 3 size: 512^3 fp32 CT-like volume.  Size-independent properties: the mesh is a closed
     2-manifold away from the domain boundary (every interior edge shared by exactly 2 triangles with opposite
