@@ -47,6 +47,9 @@ struct ctr_ctx {
   int last_kind = 0;         // 0 none, 3 = mt3d, 2 = mt2d, 4 = mp4d
   uint32_t last_flags = 0;
   int64_t last_counts[8] = {};
+  // 3D: an extraction enqueued by ctr_mt3d_enqueue and not yet finished
+  bool pending3 = false;
+  alignas(8) unsigned char pending3_params[160] = {};
   // 3D: capacities of the output pools / work lists kept from earlier runs, last list lengths, launch coverage
   size_t spec_v = 0, spec_t = 0, spec_own = 0, spec_cell = 0, last_own = 0, last_cell = 0, cover_own = 0, cover_cell = 0;
 

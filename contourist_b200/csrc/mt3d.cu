@@ -1135,8 +1135,10 @@ int load_tables(ctr_ctx* ctx) {
     }                                                                                            \
   } while (0)
 
+// phase 0: enqueue and wait (ctr_mt3d_run); 1: enqueue only (ctr_mt3d_enqueue); 2: wait for what phase 1 enqueued,
+// check the counts, redo synchronously only if a capacity was too small (ctr_mt3d_finish)
 template <typename T>
-int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
+int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int phase) {
   const int n0 = (int)p->n0, n1 = (int)p->n1, n2 = (int)p->n2;
   const int W = (n2 + 31) / 32;
   const long long nrows = (long long)n0 * n1;
@@ -1146,16 +1148,16 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
   if (nwords >= (1ll << 31) - 64) return ctr_fail(ctx, CTR_ERR_UNSUPPORTED, "volume too large for 32-bit word indices");
   int rc;
   if ((rc = load_tables(ctx))) return rc;
-  ctr_stage_mark(ctx, 0);
+  if (phase != 2) ctr_stage_mark(ctx, 0);
   const T* dfield;
   if (p->flags & CTR_FIELD_ON_DEVICE) {
     dfield = (const T*)p->field;
   } else {
     if ((rc = ctr_ensure(ctx, ctx->field, nsamp * sizeof(T)))) return rc;
-    CTR_CUDA(ctx, cudaMemcpyAsync(ctx->field.p, p->field, nsamp * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (phase != 2) CTR_CUDA(ctx, cudaMemcpyAsync(ctx->field.p, p->field, nsamp * sizeof(T), cudaMemcpyHostToDevice, st));
     dfield = (const T*)ctx->field.p;
   }
-  ctr_stage_mark(ctx, 1);
+  if (phase != 2) ctr_stage_mark(ctx, 1);
 
   Grid<T> g;
   g.f = dfield;
@@ -1253,6 +1255,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
     const unsigned cap_v = (unsigned)std::min<size_t>(ctx->spec_v, 0x7fffffffu);
     const unsigned cap_t = (unsigned)std::min<size_t>(ctx->spec_t, 0x7fffffffu);
 
+    if (!(phase == 2 && attempt == 0)) {                 // phase 2: attempt 0 was enqueued by phase 1
     k_reset3<<<64, 256, 0, st>>>(dctr, (uint4*)ctx->aux[4].p, (size_t)(nrows + 15) / 16, st_vt, (size_t)ntiles);
     ctx->launches++;
     CTR_DBG(ctx, "k_reset3");
@@ -1311,6 +1314,11 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
       ctr_stage_mark(ctx, 4);
       ctr_stage_mark(ctx, 5);
       ctx->cover_own = ctx->cover_cell = (size_t)-1;
+    }
+    }
+    if (phase == 1) {
+      CTR_CUDA(ctx, cudaGetLastError());
+      return 0;                                          // ctr_mt3d_finish picks up from here
     }
     CTR_CUDA(ctx, cudaGetLastError());
     CTR_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1373,9 +1381,10 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
 
 }  // namespace
 
-extern "C" int ctr_mt3d_run(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
-  if (!ctx) return CTR_ERR_BAD_ARG;
-  if (!p || !out || !p->field) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "null argument");
+static_assert(sizeof(ctr_mt3d_params) <= sizeof(((ctr_ctx*)nullptr)->pending3_params), "pending3_params too small");
+
+static int mt3d_check(ctr_ctx* ctx, const ctr_mt3d_params* p) {
+  if (!p || !p->field) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "null argument");
   if (p->n0 < 2 || p->n1 < 2 || p->n2 < 2) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "grid must have at least 2 samples per axis");
   if (p->n0 > 0x7ffffff0ll || p->n1 > 0x7ffffff0ll || p->n2 > 0x7ffffff0ll) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "axis too long");
   if (p->i_lo < 0 || p->i_hi > p->n0 || p->i_lo >= p->i_hi) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "bad slab range [i_lo, i_hi)");
@@ -1383,12 +1392,45 @@ extern "C" int ctr_mt3d_run(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_cou
   if (!(p->isovalue == p->isovalue)) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "isovalue is NaN");
   for (int a = 0; a < 3; ++a)
     if (p->delta[a] == 0.0) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "delta must be non-zero");
+  if (p->dtype != CTR_F32 && p->dtype != CTR_F64) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "dtype must be CTR_F32 or CTR_F64");
+  return 0;
+}
+
+static int mt3d_dispatch(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int phase) {
   CTR_CUDA(ctx, cudaSetDevice(ctx->device));
-  memset(out, 0, sizeof *out);
+  if (out) memset(out, 0, sizeof *out);
   ctx->last_kind = 0;
-  if (p->dtype == CTR_F32) return run_typed<float>(ctx, p, out);
-  if (p->dtype == CTR_F64) return run_typed<double>(ctx, p, out);
-  return ctr_fail(ctx, CTR_ERR_BAD_ARG, "dtype must be CTR_F32 or CTR_F64");
+  if (p->dtype == CTR_F32) return run_typed<float>(ctx, p, out, phase);
+  return run_typed<double>(ctx, p, out, phase);
+}
+
+extern "C" int ctr_mt3d_run(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out) {
+  if (!ctx) return CTR_ERR_BAD_ARG;
+  if (!out) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "null argument");
+  ctx->pending3 = false;
+  int rc = mt3d_check(ctx, p);
+  if (rc) return rc;
+  return mt3d_dispatch(ctx, p, out, 0);
+}
+
+extern "C" int ctr_mt3d_enqueue(ctr_ctx* ctx, const ctr_mt3d_params* p) {
+  if (!ctx) return CTR_ERR_BAD_ARG;
+  ctx->pending3 = false;
+  int rc = mt3d_check(ctx, p);
+  if (rc) return rc;
+  if (p->flags & CTR_WANT_CODES) return ctr_fail(ctx, CTR_ERR_UNSUPPORTED, "CTR_WANT_CODES needs the synchronous ctr_mt3d_run");
+  memcpy(ctx->pending3_params, p, sizeof *p);
+  rc = mt3d_dispatch(ctx, p, nullptr, 1);
+  ctx->pending3 = rc == 0;
+  return rc;
+}
+
+extern "C" int ctr_mt3d_finish(ctr_ctx* ctx, ctr_mt3d_counts* out) {
+  if (!ctx) return CTR_ERR_BAD_ARG;
+  if (!out) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "null argument");
+  if (!ctx->pending3) return ctr_fail(ctx, CTR_ERR_STATE, "no ctr_mt3d_enqueue to finish");
+  ctx->pending3 = false;
+  return mt3d_dispatch(ctx, (const ctr_mt3d_params*)ctx->pending3_params, out, 2);
 }
 
 extern "C" int ctr_mt3d_fetch(ctr_ctx* ctx, void* verts, void* normals, int32_t* tris, uint64_t* keys,

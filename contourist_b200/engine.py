@@ -70,6 +70,10 @@ def load_library():
     lib.ctr_kernel_launches.restype = i64
     lib.ctr_mt3d_run.argtypes = [vp, ctypes.POINTER(Mt3dParams), ctypes.POINTER(Mt3dCounts)]
     lib.ctr_mt3d_run.restype = i32
+    lib.ctr_mt3d_enqueue.argtypes = [vp, ctypes.POINTER(Mt3dParams)]
+    lib.ctr_mt3d_enqueue.restype = i32
+    lib.ctr_mt3d_finish.argtypes = [vp, ctypes.POINTER(Mt3dCounts)]
+    lib.ctr_mt3d_finish.restype = i32
     lib.ctr_mt3d_fetch.argtypes = [vp] + [vp] * 7
     lib.ctr_mt3d_fetch.restype = i32
     lib.ctr_mt3d_device_ptrs.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
@@ -166,10 +170,7 @@ class Engine(object):
         return int(self.lib.ctr_kernel_launches(self.h))
 
     # ------------------------------------------------------------------ 3D
-    def mt3d_run(self, field, value, origin=(0.0, 0.0, 0.0), delta=(1.0, 1.0, 1.0), flags=0,
-                 i_lo=0, i_hi=None, plane_offset=0, shape=None, dtype=None, vert_id_base=0):
-        """field: C-contiguous numpy array [n0,n1,n2] float32/float64, or an integer device pointer
-        (then pass shape, dtype and FIELD_ON_DEVICE).  Returns Mt3dCounts."""
+    def _mt3d_params(self, field, value, origin, delta, flags, i_lo, i_hi, plane_offset, shape, dtype, vert_id_base):
         p = Mt3dParams()
         if isinstance(field, np.ndarray):
             if field.dtype not in (np.float32, np.float64):
@@ -196,9 +197,29 @@ class Engine(object):
         p.i_hi = int(p.n0 if i_hi is None else i_hi)
         p.plane_offset = int(plane_offset)
         p.vert_id_base = int(vert_id_base)
+        return p, flags
+
+    def mt3d_run(self, field, value, origin=(0.0, 0.0, 0.0), delta=(1.0, 1.0, 1.0), flags=0,
+                 i_lo=0, i_hi=None, plane_offset=0, shape=None, dtype=None, vert_id_base=0):
+        """field: C-contiguous numpy array [n0,n1,n2] float32/float64, or an integer device pointer
+        (then pass shape, dtype and FIELD_ON_DEVICE).  Returns Mt3dCounts."""
+        p, flags = self._mt3d_params(field, value, origin, delta, flags, i_lo, i_hi, plane_offset, shape, dtype, vert_id_base)
         c = Mt3dCounts()
         self._check(self.lib.ctr_mt3d_run(self.h, ctypes.byref(p), ctypes.byref(c)), "ctr_mt3d_run")
         self._last3 = (flags, c)
+        return c
+
+    def mt3d_enqueue(self, field, value, origin=(0.0, 0.0, 0.0), delta=(1.0, 1.0, 1.0), flags=0,
+                     i_lo=0, i_hi=None, plane_offset=0, shape=None, dtype=None, vert_id_base=0):
+        """Queue an extraction on the stream and return at once; mt3d_finish() waits for it and returns the counts."""
+        p, flags = self._mt3d_params(field, value, origin, delta, flags, i_lo, i_hi, plane_offset, shape, dtype, vert_id_base)
+        self._check(self.lib.ctr_mt3d_enqueue(self.h, ctypes.byref(p)), "ctr_mt3d_enqueue")
+        self._pending3 = flags
+
+    def mt3d_finish(self):
+        c = Mt3dCounts()
+        self._check(self.lib.ctr_mt3d_finish(self.h, ctypes.byref(c)), "ctr_mt3d_finish")
+        self._last3 = (self._pending3, c)
         return c
 
     def mt3d_fetch(self, verts=True, normals=None, tris=True, keys=None, codes=None, pinned=False):

@@ -117,6 +117,11 @@ typedef struct {
 } ctr_mt3d_counts;
 
 CTR_API int ctr_mt3d_run(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out);
+/* The same extraction split in two: _enqueue returns as soon as every stage is queued on the stream (the field must
+ * stay valid), _finish waits for it and reports the counts.  The host can work in between -- e.g. all-gather the
+ * counts of the previous volume (bench.py, N > 1).  Not with CTR_WANT_CODES.                                         */
+CTR_API int ctr_mt3d_enqueue(ctr_ctx* ctx, const ctr_mt3d_params* p);
+CTR_API int ctr_mt3d_finish(ctr_ctx* ctx, ctr_mt3d_counts* out);
 /* verts/normals: [n_verts][3] float or double (CTR_GEOM_F64); tris: [n_tris][3] vertex ids, local to
  * this call (0 = first emitted vertex; ids >= n_verts refer to the next shard's vertices; vertices are numbered
  * by owner word (plane-major), then edge direction, then k -- not by key);

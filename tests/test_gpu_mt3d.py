@@ -161,6 +161,36 @@ def test_slab_sharding_matches_single_run(engine):
         assert np.array_equal(np.concatenate(tris), ref["tris"].astype(np.int64))
 
 
+def test_enqueue_finish_equals_run(engine):
+    """ctr_mt3d_enqueue + ctr_mt3d_finish is ctr_mt3d_run split at the wait (also when the pools have to grow)."""
+    from contourist_b200 import engine as E
+    rng = np.random.default_rng(21)
+    flags = E.WANT_KEYS | E.WANT_NORMALS | E.GEOM_F64
+    for shape in ((20, 33, 40), (70, 64, 96)):           # the second is larger than anything this context has seen
+        f = rng.standard_normal(shape)
+        c0 = engine.mt3d_run(f, 0.1, flags=flags)
+        ref = engine.mt3d_fetch()
+        engine.mt3d_enqueue(f, 0.1, flags=flags)
+        c1 = engine.mt3d_finish()
+        out = engine.mt3d_fetch()
+        assert (c1.n_verts, c1.n_tris, c1.n_active_cells, c1.n_crossings) == (c0.n_verts, c0.n_tris, c0.n_active_cells, c0.n_crossings)
+        for name in ("keys", "lowmin", "verts", "normals", "tris"):
+            assert np.array_equal(out[name], ref[name]), name
+    big = rng.standard_normal((90, 80, 128))
+    fresh = E.Engine(0)                                  # first call of a context: pools are guesses, finish() must redo
+    fresh.mt3d_enqueue(big, 0.0, flags=flags)
+    c2 = fresh.mt3d_finish()
+    o2 = E.canonical_mesh(fresh.mt3d_fetch())
+    c3 = engine.mt3d_run(big, 0.0, flags=flags)
+    o3 = E.canonical_mesh(engine.mt3d_fetch())
+    assert c2.n_verts == c3.n_verts and c2.n_tris == c3.n_tris
+    for name in ("keys", "verts", "tris"):
+        assert np.array_equal(o2[name], o3[name]), name
+    with pytest.raises(E.EngineError):
+        fresh.mt3d_finish()                              # nothing pending
+    fresh.close()
+
+
 def test_pipelined_host_extraction_equals_single_run(engine):
     """engine.mt3d_extract_host (slab-by-slab upload / extract / download on two contexts, global triangle ids via
     vert_id_base) returns exactly the mesh of one ctr_mt3d_run + ctr_mt3d_fetch."""
