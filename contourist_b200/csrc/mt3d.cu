@@ -1,16 +1,21 @@
-// 3D marching tetrahedra on sm_100a -- bitplane-first design.
+// 3D marching tetrahedra on sm_100a -- bitplane-first design (DESIGN.md sections 3-4).
 //
-//   k_bitplane   : stream the scalar field ONCE (the only pass that touches all of it), write two bitplanes
-//                  (1 bit/sample each): low = f < v (tetrahedral.py:572) and near = conservative hull of the
-//                  two np.allclose tests (tetrahedral.py:391,576); min/max (grid_field.py:79-80).
-//   k_count_scan : from the bitplanes (L2 resident), per 32-voxel word: triangle count, distinct-edge
-//                  (vertex) count, crossing count; fused single-pass decoupled-lookback exclusive scan
-//                  -> per-word output offsets + compacted active-word lists.
-//   k_emit_verts : per active owner word: interpolate edge crossings (tetrahedral.py:471-487), gradient
-//                  normals, world transform (grid_field.py:89-93); vertex id = rank of the edge key
-//                  (the reference's dict dedup, tetrahedral.py:184-188, as a perfect hash).
-//   k_emit_tris  : per active voxel word: 6 Kuhn tets per voxel (tetrahedral.py:32-39,554-595) ->
-//                  triangles of vertex ids, wound so the normal points to the high side.
+//   k_reset3     : counters, row flags, tile aggregates.
+//   k_bitplane   : stream the scalar field ONCE (the only pass that touches all of it; TMA bulk copies into a shared
+//                  memory ring, bitplane.cuh), write two bitplanes (1 bit/sample each): low = f < v
+//                  (tetrahedral.py:572) and near = conservative hull of the two np.allclose tests
+//                  (tetrahedral.py:391,576); min/max (grid_field.py:79-80).
+//   k_count      : from the bitplanes (L2 resident), per 32-sample word: used-edge words of the 7 Kuhn directions,
+//                  per-tet words, vertex / triangle counts (the scan records), per-direction vertex prefix (dirpack),
+//                  strict crossings (grid_field.py:81) -- and, in the same visit, the work lists of stages 3 / 4
+//                  (owner points, emitting voxels) into slots handed out by atomic counters; tile aggregates, scanned
+//                  by the last block.
+//   k_scan       : records -> vbase[word] (first vertex id), tbase[word] (first triangle).
+//   k_emit_verts : thread per owner point, its 1..7 edges dealt out over the warp: crossings
+//                  (tetrahedral.py:471-487), gradient normals, world transform (grid_field.py:89-93); vertex id =
+//                  vbase[word] + dirbase + rank (the reference's dict dedup, tetrahedral.py:184-188, as a perfect hash).
+//   k_emit_tris  : thread per emitting voxel: 6 Kuhn tets (tetrahedral.py:32-39,554-595) -> triangles of vertex ids,
+//                  wound so the normal points to the high side.
 //   k_codes      : optional parity output: (voxel, 30-bit case code) recomputed from the raw samples.
 //
 // Exactness: voxels / tets / edges whose outcome could depend on an np.allclose test are detected from the
@@ -28,10 +33,6 @@
 
 namespace {
 
-__constant__ uint8_t c_tri_n[6][16];
-__constant__ uint8_t c_tri_e[6][16][6];
-__constant__ uint8_t c_edge_s[19];
-__constant__ uint8_t c_edge_d[19];
 __constant__ uint8_t c_tetmask[8][8];
 __constant__ uint8_t c_tet[6][4];
 __constant__ unsigned short c_vox[256];   // corner bits -> emitting tets (6 bits) | triangle count << 8
@@ -1091,10 +1092,6 @@ bool g_tables_loaded[64] = {};
 
 int load_tables(ctr_ctx* ctx) {
   if (ctx->device < 64 && g_tables_loaded[ctx->device]) return 0;
-  CTR_CUDA(ctx, cudaMemcpyToSymbol(c_tri_n, CTR_TRI3_N_H, sizeof(CTR_TRI3_N_H)));
-  CTR_CUDA(ctx, cudaMemcpyToSymbol(c_tri_e, CTR_TRI3_E_H, sizeof(CTR_TRI3_E_H)));
-  CTR_CUDA(ctx, cudaMemcpyToSymbol(c_edge_s, CTR_EDGE3_S_H, sizeof(CTR_EDGE3_S_H)));
-  CTR_CUDA(ctx, cudaMemcpyToSymbol(c_edge_d, CTR_EDGE3_D_H, sizeof(CTR_EDGE3_D_H)));
   CTR_CUDA(ctx, cudaMemcpyToSymbol(c_tetmask, CTR_TETMASK3_H, sizeof(CTR_TETMASK3_H)));
   CTR_CUDA(ctx, cudaMemcpyToSymbol(c_tet, CTR_TET3_H, sizeof(CTR_TET3_H)));
   uint32_t packed[96];
