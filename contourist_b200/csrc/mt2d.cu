@@ -154,12 +154,33 @@ __global__ void __launch_bounds__(T2_THREADS) k2d_count(const T* __restrict__ f,
       if (lo4 >= s_upp[k] && hi4 < s_lim[k] && !nan4) {
         word = (uint32_t)k * 0x01010101u;
       } else {
+        // second path, branch-free per sample: every sample within one class of k (smooth fields: nearly always when
+        // the first test fails) -- the four thresholds and three level values around k are loaded once for the group
+        const T t_lo = s_upp[max(k - 1, 0)], t_a = s_upp[k], t_b = s_upp[k + 1], t_c = s_upp[min(k + 2, nl + 1)];
+        const T e_m = s_eqp[max(k - 1, 0)], e_0 = s_eqp[k], e_p = s_eqp[min(k + 1, nl)];
+        bool all_ok = true;
         word = 0;
+        int k0 = k;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          k = class_fix(s_upp, v[q][u], k);
-          word |= class_byte(s_eqp, v[q][u], k) << (8 * u);
-          if (u == 0) kprev = k;
+          const T f = v[q][u];
+          const bool up = f >= t_b, dn = !(f >= t_a);
+          const int ku = k + (up ? 1 : 0) - (dn ? 1 : 0);
+          all_ok = all_ok && (up ? !(f >= t_c) : (dn ? (k > 0 && f >= t_lo) : true));
+          const T ev = up ? e_p : (dn ? e_m : e_0);
+          word |= ((uint32_t)ku | (f == ev ? 128u : 0u)) << (8 * u);
+          if (u == 0) k0 = ku;
+        }
+        if (all_ok) {
+          kprev = k0;
+        } else {
+          word = 0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            k = class_fix(s_upp, v[q][u], k);
+            word |= class_byte(s_eqp, v[q][u], k) << (8 * u);
+            if (u == 0) kprev = k;
+          }
         }
       }
       sh.cls[r0 + q][t] = word;
