@@ -19,7 +19,7 @@ __constant__ uint8_t c4_edge_s[CTR_NEDGE4];
 __constant__ uint8_t c4_edge_d[CTR_NEDGE4];
 __constant__ uint32_t c4_pentmask[16][16];
 __device__ uint8_t d4_tet_n[24][32];
-__device__ uint8_t d4_tet_e[24][32][12];
+__device__ __align__(4) uint8_t d4_tet_e[24][32][12];
 
 struct Counters4 {
   unsigned long long min_key, max_key;
@@ -606,9 +606,14 @@ __global__ void __launch_bounds__(E4_THREADS) k4_emit_tets(Grid4<T> gin, const u
     if (m == 0 || m == 31 || !((emit >> p) & 1u)) continue;
     const int n = d4_tet_n[p][m];
     for (int q = 0; q < n; ++q) {
-      int* dst = tets + o * 4;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) dst[r] = (int)s_ids[d4_tet_e[p][m][q * 4 + r]][threadIdx.x];
+      // the four edge slots of the tetrahedron in one 32-bit load, its four vertex ids in one 128-bit store
+      const uint32_t e4 = *reinterpret_cast<const uint32_t*>(&d4_tet_e[p][m][q * 4]);
+      int4 t4;
+      t4.x = (int)s_ids[e4 & 255u][threadIdx.x];
+      t4.y = (int)s_ids[(e4 >> 8) & 255u][threadIdx.x];
+      t4.z = (int)s_ids[(e4 >> 16) & 255u][threadIdx.x];
+      t4.w = (int)s_ids[e4 >> 24][threadIdx.x];
+      *reinterpret_cast<int4*>(tets + o * 4) = t4;
       ++o;
     }
   }
