@@ -640,14 +640,17 @@ __global__ void k4_tet_filter(const double* __restrict__ verts, const int* __res
   const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nt) return;
   double mn[4], mx[4];
+  const int4 t4 = *reinterpret_cast<const int4*>(tets + (size_t)a * 4);       // 128-bit loads: ids, then 2 per vertex
+  const int tv[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const double* p = verts + (size_t)tets[(size_t)a * 4 + r] * 4;
+    const double2* p = reinterpret_cast<const double2*>(verts + (size_t)tv[r] * 4);
+    const double2 xy = p[0], zt = p[1];
+    const double x[4] = {xy.x, xy.y, zt.x, zt.y};
 #pragma unroll
     for (int ax = 0; ax < 4; ++ax) {
-      const double x = p[ax];
-      mn[ax] = r == 0 ? x : fmin(mn[ax], x);
-      mx[ax] = r == 0 ? x : fmax(mx[ax], x);
+      mn[ax] = r == 0 ? x[ax] : fmin(mn[ax], x[ax]);
+      mx[ax] = r == 0 ? x[ax] : fmax(mx[ax], x[ax]);
     }
   }
   const bool instant = (mx[3] - mn[3]) < mp.eps_instant;
