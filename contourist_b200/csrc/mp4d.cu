@@ -622,11 +622,13 @@ __global__ void __launch_bounds__(E4_THREADS) k4_emit_tets(Grid4<T> gin, const u
 // ------------------------------------------------------------------------------------------------
 // morph stage (grid coordinates, fp64): pentatopes.py:162-189, tetrahedral.py:353-375, morph_geometry.py:145-237
 // ------------------------------------------------------------------------------------------------
-__global__ void k4_bin(double* __restrict__ verts, unsigned nv, double min_interval) {
+__global__ void k4_bin(double* __restrict__ verts, int* __restrict__ tbin, unsigned nv, double min_interval) {
   const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nv) return;
   const double t = verts[(size_t)a * 4 + 3];
-  verts[(size_t)a * 4 + 3] = __dmul_rn(trunc(t / min_interval), min_interval);      // pentatopes.py:168-169
+  const double b = trunc(t / min_interval);
+  verts[(size_t)a * 4 + 3] = __dmul_rn(b, min_interval);                            // pentatopes.py:168-169
+  tbin[a] = (int)fmax(fmin(b, 1.0e9), -1.0e9);       // the bin itself: binned times compare like these integers
 }
 
 struct MorphParams {
@@ -694,14 +696,47 @@ constexpr int SL_THREADS = 256;
 
 __device__ __forceinline__ int pick4(const int v[4], int i) { return i == 0 ? v[0] : i == 1 ? v[1] : i == 2 ? v[2] : v[3]; }
 
+// The time comparisons of the slicing, on the binned times themselves (fp64, the reference's tolerances) or -- when
+// the bin width dwarfs every tolerance, i.e. always in practice -- on the integer bins: binned times are bin * width, so
+// "gap > 1e-4" is "bins differ", "mid +- 1e-5 inside [lo, hi]" is "2 lo < a + b < 2 hi" (a slice midpoint never
+// coincides with a corner time: the two sorted times it lies between are adjacent), "|dt| <= 1e-7 range" is "bins equal".
+template <typename TT>
+struct TimeOps;
+template <>
+struct TimeOps<double> {
+  static __device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
+  static __device__ __forceinline__ double mx(double a, double b) { return fmax(a, b); }
+  static __device__ __forceinline__ bool gap(double a, double b, const MorphParams& mp) { return (b - a) > mp.eps_gap; }
+  static __device__ __forceinline__ bool cut(double lo, double hi, double a, double b, const MorphParams& mp) {
+    const double mid = 0.5 * (b + a);
+    return !(mid + mp.eps_in < lo || mid - mp.eps_in > hi);                         // morph_geometry.py:218
+  }
+  static __device__ __forceinline__ bool same(double a, double b, const MorphParams& mp) { return fabs(a - b) <= mp.t_eps; }
+  static __device__ __forceinline__ double load(const double* verts, const int*, int v) { return verts[(size_t)v * 4 + 3]; }
+};
+template <>
+struct TimeOps<int> {
+  static __device__ __forceinline__ int mn(int a, int b) { return min(a, b); }
+  static __device__ __forceinline__ int mx(int a, int b) { return max(a, b); }
+  static __device__ __forceinline__ bool gap(int a, int b, const MorphParams&) { return b > a; }
+  static __device__ __forceinline__ bool cut(int lo, int hi, int a, int b, const MorphParams&) {
+    const int s2 = a + b;
+    return !(s2 < 2 * lo || s2 > 2 * hi);
+  }
+  static __device__ __forceinline__ bool same(int a, int b, const MorphParams&) { return a == b; }
+  static __device__ __forceinline__ int load(const double*, const int* tbin, int v) { return tbin[v]; }
+};
+
 // returns the number of morph triangles of the tetrahedron and their code; v = corner ids sorted, tv = their t
-__device__ __forceinline__ int slice_code(const double tv[4], const MorphParams& mp, const unsigned* __restrict__ s_tab,
+template <typename TT>
+__device__ __forceinline__ int slice_code(const TT tv[4], const MorphParams& mp, const unsigned* __restrict__ s_tab,
                                           unsigned long long& code) {
-  double ts[4] = {tv[0], tv[1], tv[2], tv[3]};
+  typedef TimeOps<TT> Op;
+  TT ts[4] = {tv[0], tv[1], tv[2], tv[3]};
 #define CTR_CSWAP(a, b)            \
   {                                \
-    const double lo = fmin(a, b);  \
-    b = fmax(a, b);                \
+    const TT lo = Op::mn(a, b);    \
+    b = Op::mx(a, b);              \
     a = lo;                        \
   }
   CTR_CSWAP(ts[0], ts[1]) CTR_CSWAP(ts[2], ts[3]) CTR_CSWAP(ts[0], ts[2]) CTR_CSWAP(ts[1], ts[3]) CTR_CSWAP(ts[1], ts[2])
@@ -710,25 +745,23 @@ __device__ __forceinline__ int slice_code(const double tv[4], const MorphParams&
   unsigned killmask = 0;
 #pragma unroll
   for (int e = 0; e < 6; ++e)
-    if (fabs(tv[EA(e)] - tv[EB(e)]) <= mp.t_eps) killmask |= 1u << e;
+    if (Op::same(tv[EA(e)], tv[EB(e)], mp)) killmask |= 1u << e;
   // t-extent of every edge, once (the three slices test the same six intervals)
-  double e_lo[6], e_hi[6];
+  TT e_lo[6], e_hi[6];
 #pragma unroll
   for (int e = 0; e < 6; ++e) {
-    e_lo[e] = fmin(tv[EA(e)], tv[EB(e)]);
-    e_hi[e] = fmax(tv[EA(e)], tv[EB(e)]);
+    e_lo[e] = Op::mn(tv[EA(e)], tv[EB(e)]);
+    e_hi[e] = Op::mx(tv[EA(e)], tv[EB(e)]);
   }
   int n = 0;
   code = 0ull;
 #pragma unroll
   for (int gap = 0; gap < 3; ++gap) {
-    if (!((ts[gap + 1] - ts[gap]) > mp.eps_gap)) continue;
-    const double mid = 0.5 * (ts[gap + 1] + ts[gap]);
-    const double mid_hi = mid + mp.eps_in, mid_lo = mid - mp.eps_in;
+    if (!Op::gap(ts[gap], ts[gap + 1], mp)) continue;
     unsigned mask = 0;
 #pragma unroll
     for (int e = 0; e < 6; ++e)
-      if (!(mid_hi < e_lo[e] || mid_lo > e_hi[e])) mask |= 1u << e;     // morph_geometry.py:218
+      if (Op::cut(e_lo[e], e_hi[e], ts[gap], ts[gap + 1], mp)) mask |= 1u << e;
     unsigned ent = s_tab[mask];
     const unsigned ntri = ent & 3u;
     ent >>= 2;
@@ -752,8 +785,9 @@ constexpr int SL_PER = 4;                            // consecutive tetrahedra p
 constexpr int SL_TILE = SL_THREADS * SL_PER;         // serialise on the ticket atomic and on the look-back)
 constexpr int SL_STAGE = 2048;                       // triangles staged in shared memory per tile (48 KB)
 
-__device__ __forceinline__ bool slice_load(const double* __restrict__ verts, const int* __restrict__ tets, unsigned a,
-                                           int v[4], double tv[4]) {
+template <typename TT>
+__device__ __forceinline__ bool slice_load(const double* __restrict__ verts, const int* __restrict__ tbin,
+                                           const int* __restrict__ tets, unsigned a, int v[4], TT tv[4]) {
   const int4 t4 = *reinterpret_cast<const int4*>(tets + (size_t)a * 4);
   v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
 #define CTR_ISWAP(a, b)          \
@@ -766,11 +800,13 @@ __device__ __forceinline__ bool slice_load(const double* __restrict__ verts, con
 #undef CTR_ISWAP
   if (v[0] == v[1] || v[1] == v[2] || v[2] == v[3]) return false;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) tv[r] = verts[(size_t)v[r] * 4 + 3];
+  for (int r = 0; r < 4; ++r) tv[r] = TimeOps<TT>::load(verts, tbin, v[r]);
   return true;
 }
 
-__global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict__ verts, const int* __restrict__ tets,
+template <typename TT>
+__global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict__ verts, const int* __restrict__ tbin,
+                                                       const int* __restrict__ tets,
                                                        const uint8_t* __restrict__ keep, unsigned nt, MorphParams mp,
                                                        unsigned long long* status, SlCounters* ctr, int ntiles,
                                                        int* __restrict__ out, unsigned cap) {
@@ -793,8 +829,8 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
     const unsigned a = a0 + u;
     if (a < nt && keep[a]) {
       int v[4];
-      double tv[4];
-      if (slice_load(verts, tets, a, v, tv)) cnt[u] = slice_code(tv, mp, s_tab, code[u]);
+      TT tv[4];
+      if (slice_load<TT>(verts, tbin, tets, a, v, tv)) cnt[u] = slice_code<TT>(tv, mp, s_tab, code[u]);
     }
     n += cnt[u];
   }
@@ -821,8 +857,8 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
   for (int u = 0; u < SL_PER; ++u) {
     if (!cnt[u]) continue;
     int v[4];
-    double tv[4];
-    slice_load(verts, tets, a0 + u, v, tv);
+    TT tv[4];
+    slice_load<TT>(verts, tbin, tets, a0 + u, v, tv);
     unsigned long long c = code[u];
     // low-t end first (morph_geometry.py:13-17): one bit per edge, then only 32-bit selects per triangle corner
     unsigned swapmask = 0;
@@ -893,11 +929,11 @@ int load_tables4(ctr_ctx* ctx) {
 // buffers of the 4D path: generic slots 12.. of the context
 struct Bufs4 {
   DevBuf &own_id, &own_voff, &cell_id, &cell_toff, &rowflag, &verts, &keys, &lowmin, &tets, &codes, &keep, &mverts, &mtris,
-      &slstate;
+      &slstate, &tbin;
   explicit Bufs4(ctr_ctx* c)
       : own_id(c->aux[12]), own_voff(c->aux[13]), cell_id(c->aux[14]), cell_toff(c->aux[15]), rowflag(c->aux[16]),
         verts(c->aux[17]), keys(c->aux[18]), lowmin(c->aux[19]), tets(c->aux[20]), codes(c->aux[21]), keep(c->aux[22]),
-        mverts(c->aux[23]), mtris(c->aux[24]), slstate(c->aux[25]) {}
+        mverts(c->aux[23]), mtris(c->aux[24]), slstate(c->aux[25]), tbin(c->aux[26]) {}
 };
 
 template <typename T>
@@ -1039,6 +1075,7 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
     // ---- morph stage: always in grid coordinates and fp64 (its thresholds are defined there)
     if ((p->flags & CTR_MORPH) && totV && totT) {
       if ((rc = ctr_ensure(ctx, B.mverts, (size_t)totV * 32 + 16))) return rc;
+      if ((rc = ctr_ensure(ctx, B.tbin, (size_t)totV * 4 + 16))) return rc;
       if ((rc = ctr_ensure(ctx, B.keep, (size_t)totT + 16))) return rc;
       Xform4 unit;
       for (int a = 0; a < 4; ++a) {
@@ -1049,7 +1086,8 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
                                                                           (const uint32_t*)B.own_voff.p, (unsigned)nOwn, unit,
                                                                           (double*)B.mverts.p, nullptr, nullptr);
       const double corner_t = (double)(n3 - 1);
-      k4_bin<<<(int)((totV + 255) / 256), 256, 0, st>>>((double*)B.mverts.p, (unsigned)totV, corner_t * (1.0 / p->nbins));
+      const double bin_width = corner_t * (1.0 / p->nbins);
+      k4_bin<<<(int)((totV + 255) / 256), 256, 0, st>>>((double*)B.mverts.p, (int*)B.tbin.p, (unsigned)totV, bin_width);
       // t range of the binned vertices (for the zero-duration threshold, pentatopes.py:336-337)
       MinMaxKeys mk;
       mk.min_key = ~0ull;
@@ -1083,14 +1121,23 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
         const unsigned cap = (unsigned)std::min<size_t>(B.mtris.cap / 24, 0x7fffffffu);
         static bool sl_attr = false;
         if (!sl_attr) {
-          CTR_CUDA(ctx, cudaFuncSetAttribute(k4_slice, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_STAGE * 6 * sizeof(int))));
+          CTR_CUDA(ctx, cudaFuncSetAttribute(k4_slice<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_STAGE * 6 * sizeof(int))));
+          CTR_CUDA(ctx, cudaFuncSetAttribute(k4_slice<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_STAGE * 6 * sizeof(int))));
           sl_attr = true;
         }
+        // integer bins decide exactly like the fp64 tolerances when the bin width dwarfs them (CTR_SLICE_FP64=1: never)
+        const bool int_times = bin_width > 100.0 * std::max(mp.eps_gap, std::max(mp.eps_in, mp.t_eps)) &&
+                               fabs(tmax) < 1.0e9 * bin_width && fabs(tmin) < 1.0e9 * bin_width && !getenv("CTR_SLICE_FP64");
         SlCounters* slc = (SlCounters*)((char*)B.slstate.p + (size_t)sl_tiles * 8);
         CTR_CUDA(ctx, cudaMemsetAsync(B.slstate.p, 0, (size_t)sl_tiles * 8 + 32, st));
-        k4_slice<<<sl_tiles, SL_THREADS, SL_STAGE * 6 * sizeof(int), st>>>((const double*)B.mverts.p, (const int*)B.tets.p, (const uint8_t*)B.keep.p,
-                                                  (unsigned)totT, mp, (unsigned long long*)B.slstate.p, slc, sl_tiles,
-                                                  (int*)B.mtris.p, cap);
+        if (int_times)
+          k4_slice<int><<<sl_tiles, SL_THREADS, SL_STAGE * 6 * sizeof(int), st>>>(
+              (const double*)B.mverts.p, (const int*)B.tbin.p, (const int*)B.tets.p, (const uint8_t*)B.keep.p, (unsigned)totT, mp,
+              (unsigned long long*)B.slstate.p, slc, sl_tiles, (int*)B.mtris.p, cap);
+        else
+          k4_slice<double><<<sl_tiles, SL_THREADS, SL_STAGE * 6 * sizeof(int), st>>>(
+              (const double*)B.mverts.p, (const int*)B.tbin.p, (const int*)B.tets.p, (const uint8_t*)B.keep.p, (unsigned)totT, mp,
+              (unsigned long long*)B.slstate.p, slc, sl_tiles, (int*)B.mtris.p, cap);
         ctx->launches++;
         CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, slc, sizeof(SlCounters), cudaMemcpyDeviceToHost, st));
         CTR_CUDA(ctx, cudaStreamSynchronize(st));
