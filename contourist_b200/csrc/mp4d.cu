@@ -822,15 +822,23 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   unsigned long long code[SL_PER];
   int cnt[SL_PER], n = 0;
+  int vv[SL_PER][4];                                  // id-sorted corners and low-t-first flags, kept for the write phase
+  unsigned swapm[SL_PER];
 #pragma unroll
   for (int u = 0; u < SL_PER; ++u) {
     cnt[u] = 0;
     code[u] = 0ull;
+    swapm[u] = 0;
+    vv[u][0] = vv[u][1] = vv[u][2] = vv[u][3] = 0;
     const unsigned a = a0 + u;
     if (a < nt && keep[a]) {
-      int v[4];
       TT tv[4];
-      if (slice_load<TT>(verts, tbin, tets, a, v, tv)) cnt[u] = slice_code<TT>(tv, mp, s_tab, code[u]);
+      if (slice_load<TT>(verts, tbin, tets, a, vv[u], tv)) {
+        cnt[u] = slice_code<TT>(tv, mp, s_tab, code[u]);
+#pragma unroll
+        for (int e = 0; e < 6; ++e)
+          if (tv[EA(e)] > tv[EB(e)]) swapm[u] |= 1u << e;           // morph_geometry.py:13-17: low t first
+      }
     }
     n += cnt[u];
   }
@@ -856,15 +864,9 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
 #pragma unroll
   for (int u = 0; u < SL_PER; ++u) {
     if (!cnt[u]) continue;
-    int v[4];
-    TT tv[4];
-    slice_load<TT>(verts, tbin, tets, a0 + u, v, tv);
+    const int* v = vv[u];
+    const unsigned swapmask = swapm[u];
     unsigned long long c = code[u];
-    // low-t end first (morph_geometry.py:13-17): one bit per edge, then only 32-bit selects per triangle corner
-    unsigned swapmask = 0;
-#pragma unroll
-    for (int e = 0; e < 6; ++e)
-      if (tv[EA(e)] > tv[EB(e)]) swapmask |= 1u << e;
     for (int q = 0; q < cnt[u]; ++q, c >>= 9, ++loc) {
       if (!staged && base + loc >= cap) continue;
       int* o = staged ? s_out + loc * 6 : out + (base + loc) * 6;
