@@ -78,6 +78,8 @@ def load_library():
     lib.ctr_mt3d_fetch.restype = i32
     lib.ctr_mt3d_device_ptrs.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
     lib.ctr_mt3d_device_ptrs.restype = i32
+    lib.ctr_mt3d_orient_reference.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.ctr_mt3d_orient_reference.restype = i32
     lib.ctr_host_alloc.argtypes = [vp, ctypes.c_uint64, ctypes.POINTER(vp)]
     lib.ctr_host_alloc.restype = i32
     lib.ctr_host_free.argtypes = [vp, vp]
@@ -221,6 +223,13 @@ class Engine(object):
         self._check(self.lib.ctr_mt3d_finish(self.h, ctypes.byref(c)), "ctr_mt3d_finish")
         self._last3 = (self._pending3, c)
         return c
+
+    def mt3d_orient_reference(self):
+        """Rewind the last run's device triangles with the reference's outward rule (surface_geometry.py:52-140);
+        returns (components, triangles reversed).  Fetch afterwards."""
+        nc, nf = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self.lib.ctr_mt3d_orient_reference(self.h, ctypes.byref(nc), ctypes.byref(nf)), "ctr_mt3d_orient_reference")
+        return int(nc.value), int(nf.value)
 
     def mt3d_fetch(self, verts=True, normals=None, tris=True, keys=None, codes=None, pinned=False):
         """Copy the last run's outputs to host arrays.  pinned=True: the arrays live in the engine's page-locked pool

@@ -79,12 +79,12 @@ class GridContour3d(object):
         eng = E.default_engine()
         flags = (E.GEOM_F64 if np.dtype(self.geometry_dtype) == np.float64 else 0) | (E.WANT_NORMALS if self.want_normals else 0)
         self.counts = eng.mt3d_run(self._field(), self.value, origin=self.origin, delta=self.delta, flags=flags)
+        if self.reference_orientation:
+            # surface_geometry.py:52-140 on the device mesh: one keep / reverse decision per edge-connected component
+            self.components, self.flipped = eng.mt3d_orient_reference()
         out = eng.mt3d_fetch()
         self.normals = out["normals"]
         points, triangles = out["verts"], out["tris"]
-        if self.reference_orientation:
-            geometry = surface_geometry.SurfaceGeometry(points, triangles)
-            triangles = np.array(geometry.orient_triangles(), dtype=np.int32).reshape(-1, 3)
         if self.callback:
             self.callback(self)
         return (points, triangles)

@@ -132,6 +132,13 @@ CTR_API int ctr_mt3d_fetch(ctr_ctx* ctx, void* verts, void* normals, int32_t* tr
 /* Device pointers of the last run's outputs (valid until the next *_run on this context).          */
 CTR_API int ctr_mt3d_device_ptrs(ctr_ctx* ctx, void** verts, void** normals, int32_t** tris);
 
+/* Stage 4b, orientation: rewinds the LAST run's device triangles like the reference's
+ *   surface_geometry.py:52-140  SurfaceGeometry.orient_triangles
+ * does: per edge-connected component, the triangle with the largest |cross.x| at the component's max-x vertex faces +x
+ * ("outward" for closed sheets).  The engine's triangles are wound towards the high side of the field, so this is one
+ * keep / reverse decision per component.  Fetch afterwards to get the rewound triangles.                            */
+CTR_API int ctr_mt3d_orient_reference(ctr_ctx* ctx, int64_t* n_components, int64_t* n_flipped);
+
 /* ---- 2D marching triangles, all levels in one pass ------------------------------------------------
  * Replaces, for an array-backed field, the reference's
  *   multiple_2d_contour.py:63-75 + :50-61  search_grid_for_crossings / classify_endpoint_values

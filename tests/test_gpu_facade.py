@@ -85,6 +85,74 @@ def test_reference_orientation_matches_reference_on_golden_sphere(engine):
     assert all(mine[k] == ref[k] == 1 for k in common)
 
 
+@pytest.mark.parametrize("geom64", [True, False])
+def test_device_orientation_equals_surface_geometry(engine, geom64):
+    """ctr_mt3d_orient_reference against the host restatement of surface_geometry.py:52-140 (SurfaceGeometry
+    .orient_triangles) on a field with many components: blobs whose high side is inside (kept), blobs whose high side
+    is outside (reversed), sheets cut by the volume boundary."""
+    from contourist_b200 import engine as E
+    from contourist_b200 import surface_geometry
+    n = 48
+    x, y, z = np.meshgrid(*(np.arange(n, dtype=np.float64),) * 3, indexing="ij")
+    rng = np.random.default_rng(5)
+    f = np.zeros((n, n, n))
+    for _ in range(14):
+        c = rng.uniform(4, n - 4, 3)
+        r = rng.uniform(2.5, 6.0)
+        sgn = rng.choice([-1.0, 1.0])
+        f += sgn * np.exp(-((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2) / (r * r))
+    f += 0.02 * (x - n / 2)                                     # an open sheet through the box as well
+    flags = E.GEOM_F64 if geom64 else 0
+    engine.mt3d_run(f, 0.35, flags=flags)
+    raw = engine.mt3d_fetch()
+    ncomp, nflip = engine.mt3d_orient_reference()
+    got = engine.mt3d_fetch()
+    assert np.array_equal(got["verts"], raw["verts"])
+    geometry = surface_geometry.SurfaceGeometry(raw["verts"], raw["tris"])
+    want = geometry.orient_triangles()
+    assert sorted(map(tuple, got["tris"].tolist())) == want
+    changed = np.any(got["tris"] != raw["tris"], axis=1)
+    assert int(changed.sum()) == nflip and 0 < nflip < len(raw["tris"])
+    assert ncomp >= 3
+    # a second call finds everything oriented already
+    ncomp2, nflip2 = engine.mt3d_orient_reference()
+    assert (ncomp2, nflip2) == (ncomp, 0)
+
+
+def test_device_orientation_equals_oracle_dfs(engine):
+    """... and against the oracle's restatement of the reference DFS itself (oracle/mt3d.py orient, pinned to the
+    reference's final sphere mesh in tests/test_oracle_mt3d.py) on closed blobs of both signs.  Triangles compared up to
+    rotation (the DFS starts every triangle at the shared edge)."""
+    from contourist_b200 import engine as E
+    n = 30
+    x, y, z = np.meshgrid(*(np.arange(n, dtype=np.float64),) * 3, indexing="ij")
+    rng = np.random.default_rng(11)
+    f = np.zeros((n, n, n))
+    for c, sgn in zip(([8.3, 8.1, 8.7], [21.2, 9.4, 8.9], [8.8, 21.6, 20.9], [20.7, 20.3, 21.1]), (1, -1, -1, 1)):
+        r = rng.uniform(3.0, 4.5)
+        f += sgn * np.exp(-((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2) / (r * r))
+    for value in (0.4, -0.4):
+        engine.mt3d_run(f, value, flags=E.GEOM_F64)
+        raw = engine.mt3d_fetch()
+        ncomp, nflip = engine.mt3d_orient_reference()
+        got = engine.mt3d_fetch()["tris"]
+        assert ncomp == 2 and nflip == (len(got) if value > 0 else 0)     # high side inside: engine winds inward
+
+        def rot(t):
+            t = tuple(int(i) for i in t)
+            k = t.index(min(t))
+            return t[k:] + t[:k]
+        assert sorted(rot(t) for t in got) == sorted(rot(t) for t in mt3d.orient(raw["verts"], raw["tris"]))
+
+
+def test_device_orientation_needs_a_run(engine):
+    from contourist_b200 import engine as E
+    e2 = E.Engine(0)
+    with pytest.raises(E.EngineError):
+        e2.mt3d_orient_reference()
+    e2.close()
+
+
 def test_grid2d_line_and_dot(engine):
     """test_triangulated.py:79-106."""
     from contourist_b200 import triangulated
