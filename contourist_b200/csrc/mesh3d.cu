@@ -34,28 +34,31 @@ __device__ __forceinline__ unsigned long long edge_key(int a, int b) {
   return ((unsigned long long)hi << 32) | lo;
 }
 
-// slot of `key` in the table (inserting it if `insert`); the table is never more than half full
-__device__ __forceinline__ size_t edge_slot(unsigned long long* keys, size_t mask, unsigned long long key, bool insert) {
+struct __align__(16) EdgeSlot {                       // key and value in one 16-byte slot: one sector per probe
+  unsigned long long key;
+  int tri;                                            // smallest id of the triangles on this edge
+  int pad;
+};
+
+// slot of `key` in the table (inserting it if `insert`); linear probing, the table always keeps free slots
+__device__ __forceinline__ EdgeSlot* edge_slot(EdgeSlot* tab, size_t mask, unsigned long long key, bool insert) {
   size_t s = (size_t)mix64(key) & mask;
   while (true) {
-    unsigned long long k = keys[s];
-    if (k == key) return s;
+    unsigned long long k = tab[s].key;
+    if (k == key) return tab + s;
     if (k == EMPTY) {
-      if (!insert) return s;
-      k = atomicCAS(&keys[s], EMPTY, key);
-      if (k == EMPTY || k == key) return s;
+      if (!insert) return tab + s;
+      k = atomicCAS(&tab[s].key, EMPTY, key);
+      if (k == EMPTY || k == key) return tab + s;
     }
     s = (s + 1) & mask;
   }
 }
 
-__global__ void k_o_init(unsigned long long* keys, int* vals, size_t nslots, int* parent, unsigned nt,
-                         unsigned long long* comp_key, unsigned long long* comp_best) {
+__global__ void k_o_init(EdgeSlot* tab, size_t nslots, int* parent, unsigned nt, unsigned long long* comp_key,
+                         unsigned long long* comp_best) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)gridDim.x * blockDim.x;
-  for (size_t q = t; q < nslots; q += n) {
-    keys[q] = EMPTY;
-    vals[q] = 0x7fffffff;
-  }
+  for (size_t q = t; q < nslots; q += n) reinterpret_cast<int4*>(tab)[q] = make_int4(-1, -1, 0x7fffffff, 0);
   for (size_t q = t; q < nt; q += n) {
     parent[q] = (int)q;
     comp_key[q] = 0ull;
@@ -63,13 +66,13 @@ __global__ void k_o_init(unsigned long long* keys, int* vals, size_t nslots, int
   }
 }
 
-__global__ void k_o_edges(const int* __restrict__ tris, unsigned nt, unsigned long long* keys, int* vals, size_t mask) {
+__global__ void k_o_edges(const int* __restrict__ tris, unsigned nt, EdgeSlot* tab, size_t mask) {
   const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nt) return;
   const int a = tris[(size_t)t * 3], b = tris[(size_t)t * 3 + 1], c = tris[(size_t)t * 3 + 2];
-  atomicMin(&vals[edge_slot(keys, mask, edge_key(a, b), true)], (int)t);
-  atomicMin(&vals[edge_slot(keys, mask, edge_key(b, c), true)], (int)t);
-  atomicMin(&vals[edge_slot(keys, mask, edge_key(c, a), true)], (int)t);
+  atomicMin(&edge_slot(tab, mask, edge_key(a, b), true)->tri, (int)t);
+  atomicMin(&edge_slot(tab, mask, edge_key(b, c), true)->tri, (int)t);
+  atomicMin(&edge_slot(tab, mask, edge_key(c, a), true)->tri, (int)t);
 }
 
 __device__ __forceinline__ int uf_find(int* parent, int x) {
@@ -96,14 +99,13 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   }
 }
 
-__global__ void k_o_union(const int* __restrict__ tris, unsigned nt, const unsigned long long* __restrict__ keys,
-                          const int* __restrict__ vals, size_t mask, int* parent) {
+__global__ void k_o_union(const int* __restrict__ tris, unsigned nt, EdgeSlot* tab, size_t mask, int* parent) {
   const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nt) return;
   const int v[3] = {tris[(size_t)t * 3], tris[(size_t)t * 3 + 1], tris[(size_t)t * 3 + 2]};
 #pragma unroll
   for (int e = 0; e < 3; ++e) {
-    const int m = vals[edge_slot(const_cast<unsigned long long*>(keys), mask, edge_key(v[e], v[(e + 1) % 3]), false)];
+    const int m = edge_slot(tab, mask, edge_key(v[e], v[(e + 1) % 3]), false)->tri;
     if (m != (int)t) uf_union(parent, (int)t, m);
   }
 }
@@ -125,16 +127,38 @@ __device__ __forceinline__ void tri_stats(const G* __restrict__ verts, const int
   cross_x = __dsub_rn(__dmul_rn(ay - by, az - cz), __dmul_rn(az - bz, ay - cy));
 }
 
+// atomicMax(&slot[r], k) for a whole warp: lanes with the same root combine first, and a slot that already holds at
+// least k is left alone (the target only grows, so a stale read can only under-estimate it).  Without both, every
+// triangle of a large component hits one address.
+__device__ __forceinline__ void warp_max_to_root(unsigned long long* slot, int r, unsigned long long k, bool valid) {
+  const unsigned act = __ballot_sync(0xffffffffu, valid);
+  if (!valid) return;
+  const unsigned peers = __match_any_sync(act, r);
+  unsigned long long best = k;
+  for (unsigned m = peers & (peers - 1) ? peers : 0u; m; m &= m - 1) {      // (skipped when alone in the group)
+    const unsigned long long o = __shfl_sync(peers, k, __ffs(m) - 1);
+    best = o > best ? o : best;
+  }
+  if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31) && *(volatile unsigned long long*)&slot[r] < best) atomicMax(&slot[r], best);
+}
+
 template <typename G>
 __global__ void k_o_maxx(const G* __restrict__ verts, const int* __restrict__ tris, unsigned nt, int* parent, int* root,
                          unsigned long long* comp_key) {
-  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nt) return;
-  const int r = uf_find(parent, (int)t);
-  root[t] = r;                                        // a separate array: path halving by other threads still writes parent[]
-  double maxx, cx;
-  tri_stats(verts, tris, t, maxx, cx);
-  if (maxx == maxx) atomicMax(&comp_key[r], okey(maxx));
+  // blocks walk the triangle list from its end: the engine emits triangles by ascending x, so the running maximum is
+  // found by the first wave and the remaining blocks only read it
+  const unsigned t = (gridDim.x - 1 - blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool in = t < nt;
+  int r = 0;
+  double maxx = 0, cx;
+  if (in) {
+    r = (int)t;                                       // no unions any more: walk read-only, then one compressing write
+    for (int q = parent[r]; q != r; q = parent[r]) r = q;
+    if (r != (int)t) parent[t] = r;
+    root[t] = r;                                      // a separate array: parent[] may still be rewritten by other walkers
+    tri_stats(verts, tris, t, maxx, cx);
+  }
+  warp_max_to_root(comp_key, r, okey(maxx), in && maxx == maxx);
 }
 
 // largest |cross.x| among the triangles that reach the component's max x
@@ -147,7 +171,8 @@ __global__ void k_o_best(const G* __restrict__ verts, const int* __restrict__ tr
   double maxx, cx;
   tri_stats(verts, tris, t, maxx, cx);
   if (!(maxx == maxx) || okey(maxx) != comp_key[r]) return;
-  atomicMax(&comp_best[r], okey(fabs(cx)));
+  const unsigned long long k = okey(fabs(cx));
+  if (*(volatile unsigned long long*)&comp_best[r] < k) atomicMax(&comp_best[r], k);
 }
 
 // ... and the smallest index among those that attain it: the component's seed
@@ -201,18 +226,15 @@ int orient_typed(ctr_ctx* ctx, int64_t* n_components, int64_t* n_flipped) {
   if (n_flipped) *n_flipped = 0;
   if (nt == 0) return 0;
   size_t nslots = 1;
-  while (nslots < (size_t)nt * 3 * 2) nslots <<= 1;   // <= 1.5 nt distinct edges: load factor <= 1/4 .. 1/2
+  while (nslots < (size_t)nt * 4) nslots <<= 1;       // 1.5 nt distinct edges on closed sheets (3 nt at worst): load <= 3/8 (3/4)
   int rc;
-  DevBuf& b_keys = ctx->aux[27];
-  DevBuf& b_vals = ctx->aux[28];
+  DevBuf& b_tab = ctx->aux[27];
   DevBuf& b_par = ctx->aux[29];
   DevBuf& b_comp = ctx->aux[30];
-  if ((rc = ctr_ensure(ctx, b_keys, nslots * 8))) return rc;
-  if ((rc = ctr_ensure(ctx, b_vals, nslots * 4))) return rc;
+  if ((rc = ctr_ensure(ctx, b_tab, nslots * sizeof(EdgeSlot)))) return rc;
   if ((rc = ctr_ensure(ctx, b_par, (size_t)nt * 8))) return rc;
   if ((rc = ctr_ensure(ctx, b_comp, (size_t)nt * (8 + 8 + 4) + 64))) return rc;
-  unsigned long long* keys = (unsigned long long*)b_keys.p;
-  int* vals = (int*)b_vals.p;
+  EdgeSlot* tab = (EdgeSlot*)b_tab.p;
   int* parent = (int*)b_par.p;
   int* root = parent + nt;
   unsigned long long* comp_key = (unsigned long long*)b_comp.p;
@@ -222,11 +244,11 @@ int orient_typed(ctr_ctx* ctx, int64_t* n_components, int64_t* n_flipped) {
   const G* verts = (const G*)ctx->verts.p;
   int* tris = (int*)ctx->tris.p;
   const unsigned blocks = (nt + 255) / 256;
-  k_o_init<<<ctx->sm_count * 8, 256, 0, st>>>(keys, vals, nslots, parent, nt, comp_key, comp_best);
+  k_o_init<<<ctx->sm_count * 8, 256, 0, st>>>(tab, nslots, parent, nt, comp_key, comp_best);
   CTR_CUDA(ctx, cudaMemsetAsync(comp_tri, 0x7f, (size_t)nt * 4, st));
   CTR_CUDA(ctx, cudaMemsetAsync(counters, 0, 8, st));
-  k_o_edges<<<blocks, 256, 0, st>>>(tris, nt, keys, vals, nslots - 1);
-  k_o_union<<<blocks, 256, 0, st>>>(tris, nt, keys, vals, nslots - 1, parent);
+  k_o_edges<<<blocks, 256, 0, st>>>(tris, nt, tab, nslots - 1);
+  k_o_union<<<blocks, 256, 0, st>>>(tris, nt, tab, nslots - 1, parent);
   k_o_maxx<G><<<blocks, 256, 0, st>>>(verts, tris, nt, parent, root, comp_key);
   k_o_best<G><<<blocks, 256, 0, st>>>(verts, tris, nt, root, comp_key, comp_best);
   k_o_pick<G><<<blocks, 256, 0, st>>>(verts, tris, nt, root, comp_key, comp_best, comp_tri);
