@@ -11,28 +11,37 @@ import torch
 
 
 def ct_like(n, i0=0, i1=None, device="cuda", seed=0, n_total=None, chunk=32):
-    """[i1-i0, n, n] fp32 slab of the n_total x n x n CT-like volume (isovalue 0.5)."""
+    """[i1-i0, n, n] fp32 slab of the n_total x n x n CT-like volume (isovalue 0.5).
+
+    n_total > n (a multiple of n) stacks n_total / n CT-like blocks along the first axis: block r has its own 48
+    blobs (rng(seed + 7919 r), block-local coordinates), and the Gaussian tails of the neighbouring blocks are summed
+    in, so the volume is one continuous field and every n-plane slab carries the same amount of surface (weak
+    scaling: per-GPU work fixed).  n_total == n is the single block, C3 itself."""
     n_total = n if n_total is None else n_total
     i1 = n_total if i1 is None else i1
-    rng = np.random.default_rng(seed)
+    assert n_total % n == 0, "the stacked volume is a whole number of n-plane blocks"
+    nblocks = n_total // n
     nb = 48
-    cen = rng.uniform(0.15, 0.85, size=(nb, 3))
-    sig = rng.uniform(0.03, 0.12, size=(nb, 3))
-    amp = rng.uniform(0.5, 1.0, size=nb)
+    blobs = []
+    for r in range(nblocks):
+        rng = np.random.default_rng(seed + 7919 * r)
+        blobs.append((rng.uniform(0.15, 0.85, size=(nb, 3)), rng.uniform(0.03, 0.12, size=(nb, 3)), rng.uniform(0.5, 1.0, size=nb)))
     out = torch.empty((i1 - i0, n, n), dtype=torch.float32, device=device)
     y = (torch.arange(n, device=device, dtype=torch.float32) / (n - 1)).view(1, n, 1)
     z = (torch.arange(n, device=device, dtype=torch.float32) / (n - 1)).view(1, 1, n)
     gen = torch.Generator(device=device)
     for a in range(i0, i1, chunk):
         b = min(a + chunk, i1)
-        # noise needs one extra plane each side for the 3-tap box filter; seeded per global plane block
-        x = (torch.arange(a, b, device=device, dtype=torch.float32) / (n_total - 1)).view(-1, 1, 1)
         acc = torch.zeros((b - a, n, n), dtype=torch.float32, device=device)
-        for q in range(nb):
-            ex = ((x - cen[q, 0]) / sig[q, 0]) ** 2
-            ey = ((y - cen[q, 1]) / sig[q, 1]) ** 2
-            ez = ((z - cen[q, 2]) / sig[q, 2]) ** 2
-            acc += float(amp[q]) * torch.exp(-0.5 * (ex + ey + ez))
+        for r in range(max(a // n - 1, 0), min((b - 1) // n + 1, nblocks - 1) + 1):
+            cen, sig, amp = blobs[r]
+            x = ((torch.arange(a, b, device=device, dtype=torch.float32) - float(r * n)) / (n - 1)).view(-1, 1, 1)
+            for q in range(nb):
+                ex = ((x - cen[q, 0]) / sig[q, 0]) ** 2
+                ey = ((y - cen[q, 1]) / sig[q, 1]) ** 2
+                ez = ((z - cen[q, 2]) / sig[q, 2]) ** 2
+                acc += float(amp[q]) * torch.exp(-0.5 * (ex + ey + ez))
+        # noise needs one extra plane each side for the 3-tap box filter; seeded per global plane
         planes = []
         for gi in range(a - 1, b + 1):
             gen.manual_seed(1_000_003 * (seed + 1) + (gi % (1 << 30)))
