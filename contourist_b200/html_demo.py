@@ -1,7 +1,11 @@
 """three.js emitters -- drop-in for contourist/html_demo.py:118-161 (grid_html_page, emit_three_json).
 
-Only string formatting happens here; the mesh comes from get_points_and_triangles() of the CUDA engine.
+The mesh comes from get_points_and_triangles() of the CUDA engine; the two big number lists are formatted by the
+library's host threads (`ctr_wire_format` via wire.format_rows: the same bytes as the reference's str() joins).
 """
+import numpy as np
+
+from . import wire
 
 load_three = '<script src="https://cdnjs.cloudflare.com/ajax/libs/three.js/r70/three.min.js"></script>'
 
@@ -80,17 +84,15 @@ def grid_html_page(gridcontour, title="3d contour", load_three=load_three, x=-30
     (points, triangles) = gridcontour.get_points_and_triangles()
     D = {"title": title, "target_div": "THREE_OUTPUT", "load_three": load_three,
          "camera_x": x, "camera_y": y, "camera_z": z}
-    D["vertices"] = "[%s]" % (",\n    ".join(str([float(c) for c in p]) for p in points))
-    D["indices"] = "[%s]" % (",\n    ".join(str([int(i) for i in t]) for t in triangles))
+    rows = dict(row_prefix="[", col_sep=", ", row_suffix="]", row_sep=",\n    ")       # str(list(row)) per row
+    D["vertices"] = wire.format_rows(np.asarray(points, dtype=np.float64).reshape(-1, 3), **rows)
+    D["indices"] = wire.format_rows(np.asarray(triangles, dtype=np.int64).reshape(-1, 3), **rows)
     return three_html_fullscreen % D
 
 
 def emit_three_json(grid_contour):
     "THREE Geometry format 3: faces = [0, i, j, k, ...], vertices flat (html_demo.py:133-161)."
     (points, triangles) = grid_contour.get_points_and_triangles()
-    faces = []
-    for triangle in triangles:
-        faces.append("0")
-        faces.extend(str(int(index)) for index in triangle)
-    vertices = [str(float(coordinate)) for point in points for coordinate in point]
-    return json_template % {"faces": "[%s]" % (",\n".join(faces)), "vertices": "[%s]" % (",\n".join(vertices))}
+    faces = wire.format_rows(np.asarray(triangles, dtype=np.int64).reshape(-1, 3), row_prefix="0,\n", col_sep=",\n")
+    vertices = wire.format_rows(np.asarray(points, dtype=np.float64).reshape(-1, 1))
+    return json_template % {"faces": faces, "vertices": vertices}

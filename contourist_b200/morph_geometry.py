@@ -5,7 +5,7 @@ int((p - min) / scale), scale = max(range, epsilon) / maxint) and is what misc/m
 """
 import numpy as np
 
-from . import surface_geometry
+from . import surface_geometry, wire
 
 
 class MorphTriangles(object):
@@ -81,6 +81,5 @@ def flatten_json_list(sequence, fmt=str):
     "[a,b,..,\\nc,d,..]: rows joined by ',\\n', values by ',' (morph_geometry.py:127-128)."
     arr = np.asarray(sequence)
     if arr.ndim == 2 and arr.size and np.issubdtype(arr.dtype, np.integer) and fmt is str:
-        rows = [",".join(map(str, r)) for r in arr.tolist()]
-        return "[%s]" % (",\n".join(rows),)
+        return wire.format_rows(arr)                                  # host threads of the library, same bytes
     return "[%s]" % (",\n".join(",".join(fmt(y) for y in x) for x in sequence),)

@@ -210,6 +210,20 @@ CTR_API int ctr_mp4d_run(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts
 CTR_API int ctr_mp4d_fetch(ctr_ctx* ctx, void* verts, int32_t* tets, uint64_t* keys, uint8_t* lowmin, uint8_t* codes,
                            int64_t* cells, double* morph_verts, uint8_t* keep, int32_t* morph_tris);
 
+/* ---- wire formats: the text the reference's emitters build with Python joins, by host threads
+ *   html_demo.py:118-161       grid_html_page ("[[x, y, z],\n    [..]]"), emit_three_json ("[0,\ni,\nj,\nk,\n0,.."], flat vertices)
+ *   morph_geometry.py:91-128   MorphTriangles.to_json / flatten_json_list ("[a,b,c,d,\ne,f,g,h]")
+ * data [rows][cols] -> "[" row (row_sep row)* "]",  row = row_prefix value (col_sep value)* row_suffix.
+ * Values are formatted exactly like Python's str(): integers in decimal; floats as repr(float) (shortest round-trip
+ * digits, "1e-05" / "0.0001" / "1000000000000000.0" / "1e+16", float32 widened first like float(np.float32(x))).
+ * *out is malloc'ed, NUL-terminated, *out_len bytes without the NUL; release with ctr_wire_free.  Host-only: needs no
+ * context and no device.  n_threads <= 0 = all hardware threads.                                                    */
+typedef enum { CTR_WIRE_I32 = 0, CTR_WIRE_I64 = 1, CTR_WIRE_U32 = 2, CTR_WIRE_F32 = 3, CTR_WIRE_F64 = 4 } ctr_wire_dtype;
+CTR_API int ctr_wire_format(const void* data, int dtype, int64_t rows, int64_t cols, const char* row_prefix,
+                            const char* col_sep, const char* row_suffix, const char* row_sep, int n_threads, char** out,
+                            int64_t* out_len);
+CTR_API void ctr_wire_free(char* p);
+
 #ifdef __cplusplus
 }
 #endif
