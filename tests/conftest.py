@@ -23,3 +23,17 @@ def engine():
 
 def golden_path(name):
     return os.path.join(GOLDEN, name)
+
+
+def c1_golden():
+    """BASELINE configs[0]: the reference's own run of f = x^2+y^2+z^2 on [-1,1]^3, delta 1/32
+    (N = 65 voxels per axis, samples 0..65), value 0.5 -- tests/golden/make_golden.py c1.  The field is not stored:
+    it is this formula."""
+    import numpy as np
+    g = dict(np.load(os.path.join(GOLDEN, "c1_sphere65.npz")))
+    x = -1.0 + np.arange(66) / 32.0
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    g["field"] = X * X + Y * Y + Z * Z
+    for k in ("voxels", "key_low", "key_high", "tris"):
+        g[k] = g[k].astype(np.int64)
+    return g

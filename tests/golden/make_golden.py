@@ -106,8 +106,28 @@ def run3d(arr, value):
                 seconds=np.float64(dt))
 
 
+def c1_field():
+    """BASELINE configs[0]: f = x^2+y^2+z^2 on [-1,1]^3, delta 1/32 -> N = 65 voxels per axis read
+    samples 0..65 (tetrahedral.py:465-469), value 0.5 -- the one config the full reference runs (about a minute)."""
+    g = -1.0 + np.arange(66) / 32.0
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    return X * X + Y * Y + Z * Z, 0.5
+
+
 def main():
     which = sys.argv[1:] or ["3d"]
+    if "c1" in which:
+        arr, value = c1_field()
+        g = run3d(arr, value)
+        g.pop("field")                                 # regenerated by the tests from the formula above (conftest.c1_field)
+        g["n_final_points"] = np.int64(len(g.pop("final_points")))
+        g["n_final_tris"] = np.int64(len(g.pop("final_tris")))
+        for k in ("voxels", "key_low", "key_high"):
+            g[k] = g[k].astype(np.int16)
+        g["tris"] = g["tris"].astype(np.int32)
+        np.savez_compressed(os.path.join(HERE, "c1_sphere65.npz"), **g)
+        print("c1", arr.shape, "voxels", len(g["voxels"]), "leak", int(g["n_leak"]), "keys", len(g["key_low"]),
+              "tris", len(g["tris"]), "final", int(g["n_final_points"]), int(g["n_final_tris"]), "%.1fs" % g["seconds"])
     if "3d" in which:
         for name, (arr, value) in fields3d().items():
             g = run3d(arr, value)

@@ -64,6 +64,26 @@ def test_golden_fields(engine, path, dtype):
         assert len(g["tris"]) == c.n_tris
 
 
+def test_c1_sphere65_against_full_reference_run(engine):
+    """BASELINE configs[0] through the C ABI, straight against the reference's own run (tests/golden/c1_sphere65.npz)."""
+    from conftest import c1_golden
+    g = c1_golden()
+    c, o, r = run_and_compare(engine, g["field"], 0.5)
+    # 9,656 surface voxels in the reference; 24 of them only touch the level set in a corner with f == value exactly
+    # (border_voxel is inclusive, tetrahedral.py:383-394) and emit nothing
+    assert (c.n_active_cells, c.n_verts, c.n_tris) == (9632, 28778, 57552)
+    n1 = n2 = 66
+    pmin = np.minimum(g["key_low"], g["key_high"])
+    d = np.maximum(g["key_low"], g["key_high"]) - pmin
+    gk = ((((pmin[:, 0] * n1 + pmin[:, 1]) * n2 + pmin[:, 2]).astype(np.uint64) << np.uint64(3))
+          | (d[:, 0] * 4 + d[:, 1] * 2 + d[:, 2]).astype(np.uint64))
+    srt = np.argsort(gk)
+    assert np.array_equal(gk[srt], o["keys"])
+    assert np.array_equal(g["key_pos"][srt], o["verts"])                  # 0 ulp in fp64 mode
+    gv = g["voxels"]
+    assert len(gv) == 9656 and np.isin(o["cells"], (gv[:, 0] * 65 + gv[:, 1]) * 65 + gv[:, 2]).all()
+
+
 @pytest.mark.parametrize("shape", [(2, 2, 2), (3, 2, 33), (33, 17, 70), (5, 64, 31), (40, 40, 40), (9, 9, 129)])
 def test_random_fields_ragged_shapes(engine, shape):
     rng = np.random.default_rng(sum(shape))

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, c1_golden
 from oracle import mt3d
 
 FILES = sorted(glob.glob(os.path.join(GOLDEN, "mt3d_*.npz")))
@@ -29,7 +29,21 @@ def test_have_goldens():
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
 def test_raw_extraction_matches_reference(path):
-    g = np.load(path)
+    check_raw_extraction(np.load(path))
+
+
+def test_c1_sphere65_matches_full_reference_run():
+    """BASELINE configs[0]: the one config the whole reference runs; SURVEY.md 8(d) C1 quotes the same counts."""
+    g = c1_golden()
+    assert (len(g["voxels"]), len(g["key_low"]), len(g["tris"])) == (9656, 28778, 57552)
+    assert (int(g["n_final_points"]), int(g["n_final_tris"])) == (28730, 57456)
+    check_raw_extraction(g)
+    r = mt3d.extract(g["field"], 0.5)
+    crossing_tets = sum(int(mt3d.tet_emits((r["codes"] >> np.uint32(5 * k)) & np.uint32(31)).sum()) for k in range(6))
+    assert crossing_tets == 43956
+
+
+def check_raw_extraction(g):
     field, value = g["field"], float(g["value"])
     n0, n1, n2 = field.shape
     r = mt3d.extract(field, value)
