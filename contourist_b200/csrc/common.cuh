@@ -47,6 +47,7 @@ struct ctr_ctx {
   int last_kind = 0;         // 0 none, 3 = mt3d, 2 = mt2d, 4 = mp4d
   uint32_t last_flags = 0;
   int64_t last_counts[8] = {};
+  unsigned char last3_params[160] = {};   // parameters of the last completed ctr_mt3d_run
   // 3D: an extraction enqueued by ctr_mt3d_enqueue and not yet finished
   bool pending3 = false;
   alignas(8) unsigned char pending3_params[160] = {};

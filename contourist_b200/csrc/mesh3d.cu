@@ -15,44 +15,22 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "uf_hash.cuh"
 
 namespace {
 
-constexpr unsigned long long EMPTY = ~0ull;
-
-__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {   // splitmix64 finaliser
-  x ^= x >> 30;
-  x *= 0xbf58476d1ce4e5b9ull;
-  x ^= x >> 27;
-  x *= 0x94d049bb133111ebull;
-  x ^= x >> 31;
-  return x;
-}
+using ufh::EMPTY;
+using ufh::uf_find;
+using ufh::uf_union;
+typedef ufh::Slot EdgeSlot;
 
 __device__ __forceinline__ unsigned long long edge_key(int a, int b) {
   const unsigned lo = (unsigned)min(a, b), hi = (unsigned)max(a, b);
   return ((unsigned long long)hi << 32) | lo;
 }
 
-struct __align__(16) EdgeSlot {                       // key and value in one 16-byte slot: one sector per probe
-  unsigned long long key;
-  int tri;                                            // smallest id of the triangles on this edge
-  int pad;
-};
-
-// slot of `key` in the table (inserting it if `insert`); linear probing, the table always keeps free slots
 __device__ __forceinline__ EdgeSlot* edge_slot(EdgeSlot* tab, size_t mask, unsigned long long key, bool insert) {
-  size_t s = (size_t)mix64(key) & mask;
-  while (true) {
-    unsigned long long k = tab[s].key;
-    if (k == key) return tab + s;
-    if (k == EMPTY) {
-      if (!insert) return tab + s;
-      k = atomicCAS(&tab[s].key, EMPTY, key);
-      if (k == EMPTY || k == key) return tab + s;
-    }
-    s = (s + 1) & mask;
-  }
+  return ufh::hash_slot(tab, mask, key, insert);
 }
 
 __global__ void k_o_init(EdgeSlot* tab, size_t nslots, int* parent, unsigned nt, unsigned long long* comp_key,
@@ -73,30 +51,6 @@ __global__ void k_o_edges(const int* __restrict__ tris, unsigned nt, EdgeSlot* t
   atomicMin(&edge_slot(tab, mask, edge_key(a, b), true)->tri, (int)t);
   atomicMin(&edge_slot(tab, mask, edge_key(b, c), true)->tri, (int)t);
   atomicMin(&edge_slot(tab, mask, edge_key(c, a), true)->tri, (int)t);
-}
-
-__device__ __forceinline__ int uf_find(int* parent, int x) {
-  while (true) {
-    const int p = parent[x];
-    if (p == x) return x;
-    const int gp = parent[p];
-    if (gp != p) parent[x] = gp;                      // path halving (benign race: only ever points nearer the root)
-    x = p;
-  }
-}
-
-__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
-  while (true) {
-    a = uf_find(parent, a);
-    b = uf_find(parent, b);
-    if (a == b) return;
-    if (a < b) {                                      // the larger root goes under the smaller: roots are minima
-      const int tmp = a;
-      a = b;
-      b = tmp;
-    }
-    if (atomicCAS(&parent[a], a, b) == a) return;
-  }
 }
 
 __global__ void k_o_union(const int* __restrict__ tris, unsigned nt, EdgeSlot* tab, size_t mask, int* parent) {

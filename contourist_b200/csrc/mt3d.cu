@@ -30,6 +30,7 @@
 
 #include "bitplane.cuh"
 #include "tables.h"
+#include "uf_hash.cuh"
 
 namespace {
 
@@ -1373,8 +1374,11 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
   ctx->last_counts[0] = (int64_t)nV;
   ctx->last_counts[1] = (int64_t)totT;
   ctx->last_counts[2] = out->n_codes;
+  memcpy(ctx->last3_params, p, sizeof *p);            // ctr_mt3d_select_seeded works on this run
   return 0;
 }
+
+#include "mt3d_select.cuh"
 
 }  // namespace
 
@@ -1473,4 +1477,18 @@ extern "C" int ctr_mt3d_device_ptrs(ctr_ctx* ctx, void** verts, void** normals, 
   if (normals) *normals = (ctx->last_flags & CTR_WANT_NORMALS) ? ctx->normals.p : nullptr;
   if (tris) *tris = (int32_t*)ctx->tris.p;
   return 0;
+}
+
+extern "C" int ctr_mt3d_select_seeded(ctr_ctx* ctx, const int32_t* seed_voxels, int64_t n_seeds, int64_t* n_verts,
+                                      int64_t* n_tris, int64_t* n_voxels) {
+  if (!ctx) return CTR_ERR_BAD_ARG;
+  if (n_seeds < 0 || (n_seeds > 0 && !seed_voxels)) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "bad seed list");
+  if (ctx->last_kind != 3 || (ctx->last_flags & CTR_NO_GEOMETRY))
+    return ctr_fail(ctx, CTR_ERR_STATE, "no completed ctr_mt3d_run with geometry to select from");
+  const ctr_mt3d_params* p = (const ctr_mt3d_params*)ctx->last3_params;
+  if (p->i_lo != 0 || p->i_hi != p->n0)
+    return ctr_fail(ctx, CTR_ERR_UNSUPPORTED, "seeded selection needs a full-volume run (components cross slab faces)");
+  CTR_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (p->dtype == CTR_F32) return select_typed<float>(ctx, p, seed_voxels, n_seeds, n_verts, n_tris, n_voxels);
+  return select_typed<double>(ctx, p, seed_voxels, n_seeds, n_verts, n_tris, n_voxels);
 }

@@ -80,6 +80,8 @@ def load_library():
     lib.ctr_mt3d_device_ptrs.restype = i32
     lib.ctr_mt3d_orient_reference.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.ctr_mt3d_orient_reference.restype = i32
+    lib.ctr_mt3d_select_seeded.argtypes = [vp, vp, i64, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.ctr_mt3d_select_seeded.restype = i32
     lib.ctr_host_alloc.argtypes = [vp, ctypes.c_uint64, ctypes.POINTER(vp)]
     lib.ctr_host_alloc.restype = i32
     lib.ctr_host_free.argtypes = [vp, vp]
@@ -230,6 +232,18 @@ class Engine(object):
         nc, nf = ctypes.c_int64(), ctypes.c_int64()
         self._check(self.lib.ctr_mt3d_orient_reference(self.h, ctypes.byref(nc), ctypes.byref(nf)), "ctr_mt3d_orient_reference")
         return int(nc.value), int(nf.value)
+
+    def mt3d_select_seeded(self, start_voxels):
+        """Keep only what the reference's flood fill reaches from these voxel origins ([n, 3] ints, the output of
+        find_initial_voxels): tetrahedral.py:443-469 on the device mesh of the last full-volume run.
+        Returns (n_verts, n_tris, emitting voxels selected); fetch afterwards."""
+        sv = np.ascontiguousarray(np.asarray(start_voxels, dtype=np.int32).reshape(-1, 3))
+        nv, nt, nc = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        self._check(self.lib.ctr_mt3d_select_seeded(self.h, _ptr(sv) if len(sv) else None, len(sv), ctypes.byref(nv),
+                                                    ctypes.byref(nt), ctypes.byref(nc)), "ctr_mt3d_select_seeded")
+        flags, c = self._last3
+        c.n_verts, c.n_tris = int(nv.value), int(nt.value)             # what mt3d_fetch sizes its arrays from
+        return int(nv.value), int(nt.value), int(nc.value)
 
     def mt3d_fetch(self, verts=True, normals=None, tris=True, keys=None, codes=None, pinned=False):
         """Copy the last run's outputs to host arrays.  pinned=True: the arrays live in the engine's page-locked pool

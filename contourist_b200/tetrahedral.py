@@ -4,8 +4,13 @@ Same public names and signatures as the reference (tetrahedral.py:50-107,514-621
 Delta3DContour, Grid3DContour / GridContour3d with search_for_endpoints(), get_points_and_triangles(),
 extract_surface_geometry().  Differences, all documented in DESIGN.md section 2:
   * `function` may be a numpy array of samples (N+1 per axis for N = grid_dimensions) besides a callable;
-  * extraction is a FULL SCAN on the GPU: segment_endpoints only matter as "non-empty or not" (the reference
-    at HEAD cannot take 3D seeds through this facade either, triangulated.py:96);
+  * extraction is a FULL SCAN on the GPU.  Seeds from search_for_endpoints() (every crossing segment) keep it that
+    way; explicit segment_endpoints at the grid level (Grid3DContour / GridContour3d) restrict the result to what
+    the reference's tracker reaches from them: the start voxels are found on the host as in find_initial_voxels
+    (tetrahedral.py:396-441, a few samples per seed) and the engine keeps the 26-connected components of border
+    voxels that contain one (`ctr_mt3d_select_seeded`; expand_voxels, tetrahedral.py:443-469).  Start voxels outside
+    the array (the reference's out-of-range "leak" voxels, which it can only evaluate through a callable) are
+    ignored;
   * linear_interpolate=False (the callable evaluated off-grid) is not available: NotImplementedError;
   * points / triangles come back as numpy arrays (iterate / index them like the reference's lists);
   * the reference's serial mesh post-processing (quantize, tiny, clean, global orientation) is replaced by the
@@ -28,6 +33,62 @@ G = (1, 1, 0)
 H = (1, 1, 1)
 CUBE = np.array([A, B, C, D, E_, F, G, H], dtype=int)
 TETRAHEDRA = np.array([[A, H, B, D], [A, H, D, C], [A, H, C, G], [A, H, G, E_], [A, H, E_, F], [A, H, F, B]], dtype=int)
+OFFSETS = np.array([(i, j, k) for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1) if i != 0 or j != 0 or k != 0], dtype=int)
+
+
+def initial_voxels(samples, value, end_points):
+    """Start voxels of the reference's tracker for seed segments (tetrahedral.py:396-441 find_initial_voxels), on an
+    array of samples: order low / high by value, integer bisection until the two points are adjacent, then each of
+    them -- or the first of its 26 neighbours in OFFSETS order -- that is a border voxel (tetrahedral.py:383-394),
+    with the reference's `visited` bookkeeping.  Voxels whose 8 samples are not all inside the array are not border
+    voxels here.  Returns an int32 [n, 3] array of voxel origins."""
+    samples = np.asarray(samples)
+    top = np.array(samples.shape) - 2                     # last voxel origin per axis
+
+    def f(p):
+        if np.any(np.asarray(p) < 0) or np.any(np.asarray(p) > top + 1):
+            raise ValueError("seed point %r outside the sample array of shape %r" % (tuple(int(x) for x in p), samples.shape))
+        return float(samples[tuple(int(x) for x in p)])
+
+    def border(p):
+        p = np.asarray(p)
+        if np.any(p < 0) or np.any(p > top):
+            return False
+        v = samples[p[0]:p[0] + 2, p[1]:p[1] + 2, p[2]:p[2] + 2].astype(np.float64).reshape(-1)
+        if np.allclose(value, v):
+            return False
+        return v.min() <= value and v.max() >= value
+
+    visited, found = set(), []
+    for (low_point, high_point) in np.array(end_points, dtype=int).reshape(-1, 2, 3):
+        low_value, high_value = f(low_point), f(high_point)
+        if low_value > value or high_value < value:
+            (low_point, low_value, high_point, high_value) = (high_point, high_value, low_point, low_value)
+        assert low_value <= value and high_value >= value, \
+            "Bad end points " + repr((tuple(low_point), low_value, tuple(high_point), high_value, value))
+        while np.any(np.abs(low_point - high_point) > 1):
+            mid_point = (low_point + high_point) // 2
+            if f(mid_point) < value:
+                low_point = mid_point
+            else:
+                high_point = mid_point
+        for point in (low_point, high_point):
+            tpoint = tuple(int(x) for x in point)
+            if tpoint in visited:
+                continue
+            visited.add(tpoint)
+            if border(point):
+                found.append(tpoint)
+                continue
+            for offset_point in OFFSETS + point.reshape(1, 3):
+                toffset = tuple(int(x) for x in offset_point)
+                if toffset in visited:
+                    continue
+                visited.add(toffset)
+                if border(offset_point):
+                    found.append(toffset)
+                    break
+    return np.array(sorted(set(found)), dtype=np.int32).reshape(-1, 3)
 
 
 class GridContour3d(object):
@@ -40,6 +101,7 @@ class GridContour3d(object):
     geometry_dtype = np.float64
     reference_orientation = False
     want_normals = False
+    full_scan = False                                  # set by search_for_endpoints(): the seeds are every crossing
 
     def __init__(self, corner, function, value, segment_endpoints, linear_interpolate=True, callback=None,
                  origin=(0.0, 0.0, 0.0), delta=(1.0, 1.0, 1.0)):
@@ -78,7 +140,13 @@ class GridContour3d(object):
             raise NotImplementedError("flatten / smooth (LP-based decimation, tetrahedral.py:217-351) are out of scope")
         eng = E.default_engine()
         flags = (E.GEOM_F64 if np.dtype(self.geometry_dtype) == np.float64 else 0) | (E.WANT_NORMALS if self.want_normals else 0)
-        self.counts = eng.mt3d_run(self._field(), self.value, origin=self.origin, delta=self.delta, flags=flags)
+        field = self._field()
+        self.counts = eng.mt3d_run(field, self.value, origin=self.origin, delta=self.delta, flags=flags)
+        if not self.full_scan and self.end_points is not None:
+            # seeded tracking: only what the flood fill reaches from the seeds' start voxels (no seeds: nothing)
+            self.start_voxels = initial_voxels(field, self.value, self.end_points) if len(self.end_points) else \
+                np.zeros((0, 3), np.int32)
+            self.selected = eng.mt3d_select_seeded(self.start_voxels)
         if self.reference_orientation:
             # surface_geometry.py:52-140 on the device mesh: one keep / reverse decision per edge-connected component
             self.components, self.flipped = eng.mt3d_orient_reference()
@@ -128,6 +196,7 @@ class Delta3DContour(object):
                               linear_interpolate=self.linear_interpolate, origin=tuple(grid.mins), delta=tuple(grid.delta))
         maker.flatten = self.flatten
         maker.smooth = self.smooth
+        maker.full_scan = True      # this facade only ever passes the complete seed set (triangulated.py:96 at HEAD)
         return maker
 
     def search_for_endpoints(self, skip=1):

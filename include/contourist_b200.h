@@ -139,6 +139,17 @@ CTR_API int ctr_mt3d_device_ptrs(ctr_ctx* ctx, void** verts, void** normals, int
  * keep / reverse decision per component.  Fetch afterwards to get the rewound triangles.                            */
 CTR_API int ctr_mt3d_orient_reference(ctr_ctx* ctx, int64_t* n_components, int64_t* n_flipped);
 
+/* Seeded extraction: restricts the LAST full-volume run's mesh to what the reference's tracker
+ *   tetrahedral.py:443-469  expand_voxels / in_range  (flood fill over the 26-neighbourhood of border voxels)
+ * reaches from the given start voxels (the output of find_initial_voxels, tetrahedral.py:396-441, which the binding
+ * evaluates on the host: a few samples per seed segment).  seed_voxels [n_seeds][3] voxel origins (i, j, k); origins
+ * outside [0, n-2] are ignored (the reference's out-of-range "leak" voxels).  Triangles, vertices, normals and keys
+ * are compacted in place (order kept, ids renumbered); case codes / cells stay those of the full scan.  Returns the
+ * new counts and the number of emitting voxels selected; fetch afterwards.  With CTR_FIELD_ON_DEVICE the field must
+ * still be resident.                                                                                              */
+CTR_API int ctr_mt3d_select_seeded(ctr_ctx* ctx, const int32_t* seed_voxels, int64_t n_seeds, int64_t* n_verts,
+                                   int64_t* n_tris, int64_t* n_voxels);
+
 /* ---- 2D marching triangles, all levels in one pass ------------------------------------------------
  * Replaces, for an array-backed field, the reference's
  *   multiple_2d_contour.py:63-75 + :50-61  search_grid_for_crossings / classify_endpoint_values

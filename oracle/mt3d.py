@@ -458,3 +458,83 @@ def orient(verts, tris):
                         (i3,) = t2 - e
                         stack.append((t2, (i1, i2, i3)))
     return sorted(orientations.values())
+
+
+# ---------------------------------------------------------------------------------------------------
+# Seeded tracking: what the reference returns for explicit seed segments
+# ---------------------------------------------------------------------------------------------------
+OFFSETS = np.array([(i, j, k) for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1)
+                    if i != 0 or j != 0 or k != 0], dtype=np.int64)       # tetrahedral.py:41-47
+
+
+def initial_voxels(field, value, end_points):
+    """tetrahedral.py:396-441 find_initial_voxels on an array of samples.  A voxel whose 8 samples are not all inside
+    the array cannot be evaluated and counts as "not border" (the reference, through a callable, may call it border:
+    its out-of-range leak voxels).  Returns the set of start voxel origins (tuples)."""
+    field = np.asarray(field)
+    value = float(value)
+    act = active_cells(field, value)
+    visited = set()
+    new_voxels = set()
+
+    def border(p):
+        return bool(all(0 <= int(p[a]) < act.shape[a] for a in range(3)) and act[tuple(int(x) for x in p)])
+
+    for low_point, high_point in np.asarray(end_points, dtype=np.int64).reshape(-1, 2, 3):
+        low_value = float(field[tuple(low_point)])
+        high_value = float(field[tuple(high_point)])
+        if low_value > value or high_value < value:
+            low_point, low_value, high_point, high_value = high_point, high_value, low_point, low_value
+        assert low_value <= value and high_value >= value
+        while np.any(np.abs(low_point - high_point) > 1):
+            mid_point = (low_point + high_point) // 2
+            if float(field[tuple(mid_point)]) < value:
+                low_point = mid_point
+            else:
+                high_point = mid_point
+        for point in (low_point, high_point):
+            tpoint = tuple(int(x) for x in point)
+            if tpoint in visited:
+                continue
+            visited.add(tpoint)
+            if border(point):
+                new_voxels.add(tpoint)
+                continue
+            for offset_point in OFFSETS + point.reshape(1, 3):
+                toffset = tuple(int(x) for x in offset_point)
+                if toffset in visited:
+                    continue
+                visited.add(toffset)
+                if border(offset_point):
+                    new_voxels.add(toffset)
+                    break
+    return new_voxels
+
+
+def flood_fill(field, value, start_voxels):
+    """tetrahedral.py:443-469 expand_voxels / in_range until nothing is new: the border voxels (active_cells) that are
+    26-connected, through border voxels, to a start voxel.  Boolean (n0-1, n1-1, n2-1)."""
+    from scipy import ndimage
+    act = active_cells(np.asarray(field), float(value))
+    lab, _ = ndimage.label(act, structure=np.ones((3, 3, 3), dtype=bool))
+    want = set()
+    for v in start_voxels:
+        if all(0 <= v[a] < act.shape[a] for a in range(3)) and act[tuple(v)]:
+            want.add(int(lab[tuple(v)]))
+    return np.isin(lab, sorted(want)) & act if want else np.zeros_like(act)
+
+
+def extract_seeded(field, value, end_points, geom_dtype=np.float64):
+    """extract() restricted to the voxels the tracker reaches from the seed segments; keys renumbered.
+    Returns the same dict as extract() plus 'voxels' (bool mask of the reached border voxels)."""
+    r = extract(field, value, geom_dtype)
+    mask = flood_fill(field, value, initial_voxels(field, value, end_points))
+    keep_t = mask.reshape(-1)[r["tri_cell"]] if len(r["tri_cell"]) else np.zeros(0, dtype=bool)
+    tris = r["tris"][keep_t]
+    used = np.unique(tris)
+    remap = -np.ones(len(r["keys"]), dtype=np.int64)
+    remap[used] = np.arange(len(used))
+    keep_c = mask.reshape(-1)[r["cells"]]
+    return dict(cells=r["cells"][keep_c], codes=r["codes"][keep_c], keys=r["keys"][used], lowmin=r["lowmin"][used],
+                pos=r["pos"][used], tri_keys=r["tri_keys"][keep_t], tris=remap[tris].astype(np.int32),
+                tri_cell=r["tri_cell"][keep_t], tri_tet=r["tri_tet"][keep_t], voxels=mask)

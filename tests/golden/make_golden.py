@@ -114,8 +114,62 @@ def c1_field():
     return X * X + Y * Y + Z * Z, 0.5
 
 
+def fields_seeded():
+    """Multi-component fields with explicit seed segments: the reference's tracker must return only
+    the components its seeds reach."""
+    out = {}
+    def two_dots(x, y, z):
+        return 1.0 if (x == y == z == -8 or x == y == z == 0) else -1.0
+    arr = np.array([[[two_dots(-8 + 2 * i, -8 + 2 * j, -8 + 2 * k) for k in range(10)] for j in range(10)] for i in range(10)])
+    out["twodots"] = (arr, 0.0, [[(4, 4, 4), (4, 4, 9)]])               # from the dot at the origin (grid 4,4,4) outwards
+    n = 18
+    x, y, z = np.meshgrid(*(np.arange(n, dtype=np.float64),) * 3, indexing="ij")
+    blobs = np.zeros((n, n, n))
+    for c, r in (((4.3, 4.1, 4.6), 2.6), ((12.2, 5.1, 4.9), 2.2), ((5.2, 12.4, 11.8), 2.9), ((12.6, 12.3, 12.1), 2.4)):
+        blobs += np.exp(-((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2) / (r * r))
+    out["blobs_one"] = (blobs, 0.45, [[(4, 4, 4), (4, 4, 9)]])
+    out["blobs_two"] = (blobs, 0.45, [[(12, 5, 5), (12, 9, 5)], [(16, 16, 16), (12, 12, 12)], [(12, 5, 5), (16, 5, 5)]])
+    wave = np.sin(0.9 * x + 0.3) * np.cos(0.7 * y) + 0.05 * (z - 8)
+    out["wave_sheet"] = (wave, 0.1, [[(0, 8, 8), (5, 8, 8)]])
+    return out
+
+
+def run_seeded(arr, value, seeds):
+    T = rh.load("tetrahedral")
+    f = array_callable(arr)
+    corner = [s - 1 for s in arr.shape]
+    G = T.Grid3DContour(corner[0], corner[1], corner[2], f, value, seeds)
+    G.find_initial_voxels()                              # tetrahedral.py:396-441
+    initial = sorted(G.new_surface_voxels)
+    while G.new_surface_voxels:
+        G.expand_voxels()                                # tetrahedral.py:443-463
+    for triple in G.surface_voxels:
+        G.enumerate_voxel_triangles(triple)
+    inr = lambda v: all(0 <= v[a] < corner[a] for a in range(3))
+    vox = np.array(sorted(v for v in G.surface_voxels if inr(v)), dtype=np.int64).reshape(-1, 3)
+    corner_a = np.array(corner)
+    simplices = []
+    for s in G.simplex_sets:
+        pts = np.array([p for pair in s for p in pair])
+        owner = pts.min(axis=0)
+        if np.all(owner >= 0) and np.all(owner < corner_a):
+            simplices.append(sorted(s))
+    used = sorted(set(pair for s in simplices for pair in s))
+    return dict(field=arr, value=np.float64(value), seeds=np.array(seeds, dtype=np.int64).reshape(-1, 2, 3),
+                initial=np.array(initial, dtype=np.int64).reshape(-1, 3), voxels=vox,
+                n_leak=np.int64(len(G.surface_voxels) - len(vox)), n_keys=np.int64(len(used)), n_tris=np.int64(len(simplices)),
+                key_low=np.array([p[0] for p in used], dtype=np.int64).reshape(-1, 3),
+                key_high=np.array([p[1] for p in used], dtype=np.int64).reshape(-1, 3))
+
+
 def main():
     which = sys.argv[1:] or ["3d"]
+    if "seeded" in which:
+        for name, (arr, value, seeds) in fields_seeded().items():
+            g = run_seeded(arr, value, seeds)
+            np.savez_compressed(os.path.join(HERE, "seeded3d_%s.npz" % name), **g)
+            print(name, arr.shape, "initial", g["initial"].tolist(), "voxels", len(g["voxels"]), "leak", int(g["n_leak"]),
+                  "keys", int(g["n_keys"]), "tris", int(g["n_tris"]))
     if "c1" in which:
         arr, value = c1_field()
         g = run3d(arr, value)

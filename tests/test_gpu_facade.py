@@ -67,7 +67,7 @@ def test_reference_orientation_matches_reference_on_golden_sphere(engine):
     with reference_orientation=True, triangle by triangle where both have the triangle."""
     from contourist_b200 import tetrahedral
     g = np.load(os.path.join(GOLDEN, "mt3d_sphere13.npz"))
-    G = tetrahedral.Grid3DContour(12, 12, 12, g["field"], float(g["value"]), [])
+    G = tetrahedral.Grid3DContour(12, 12, 12, g["field"], float(g["value"]), None)      # None: full scan
     G.reference_orientation = True
     pts, tris = G.get_points_and_triangles()
 
