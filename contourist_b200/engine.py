@@ -242,7 +242,9 @@ class Engine(object):
         self._check(self.lib.ctr_mt3d_select_seeded(self.h, _ptr(sv) if len(sv) else None, len(sv), ctypes.byref(nv),
                                                     ctypes.byref(nt), ctypes.byref(nc)), "ctr_mt3d_select_seeded")
         flags, c = self._last3
+        c = type(c).from_buffer_copy(c)                                # the caller keeps the full scan's counts
         c.n_verts, c.n_tris = int(nv.value), int(nt.value)             # what mt3d_fetch sizes its arrays from
+        self._last3 = (flags, c)
         return int(nv.value), int(nt.value), int(nc.value)
 
     def mt3d_fetch(self, verts=True, normals=None, tris=True, keys=None, codes=None, pinned=False):
