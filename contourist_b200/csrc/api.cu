@@ -47,7 +47,7 @@ extern "C" void ctr_destroy(ctr_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->field, &c->bits, &c->nbits, &c->vbase, &c->tbase, &c->list_v, &c->list_t, &c->tile_state,
-                   &c->counters, &c->wmask, &c->wdir, &c->vox_tab, &c->verts, &c->normals, &c->tris, &c->keys, &c->lowmin, &c->cells, &c->codes};
+                   &c->counters, &c->wmask, &c->wdir, &c->wlist, &c->vox_tab, &c->verts, &c->normals, &c->tris, &c->keys, &c->lowmin, &c->cells, &c->codes};
   for (DevBuf* b : all) free_buf(*b);
   for (DevBuf& b : c->aux) free_buf(b);
   if (c->counters_host) cudaFreeHost(c->counters_host);

@@ -53,6 +53,8 @@ struct ctr_ctx {
   alignas(8) unsigned char pending3_params[160] = {};
   // 3D: capacities of the output pools / work lists kept from earlier runs, last list lengths, launch coverage
   size_t spec_v = 0, spec_t = 0, spec_own = 0, spec_cell = 0, last_own = 0, last_cell = 0, cover_own = 0, cover_cell = 0;
+  size_t spec_w = 0, last_w = 0, cover_w = 0;   // interesting-word list of the split stage 2
+  DevBuf wlist;
 
   // 2D / 4D extra outputs are declared in their own translation units via these generic slots
   DevBuf aux[32];

@@ -5,7 +5,7 @@
 //                  memory ring, bitplane.cuh), write two bitplanes (1 bit/sample each): low = f < v
 //                  (tetrahedral.py:572) and near = conservative hull of the two np.allclose tests
 //                  (tetrahedral.py:391,576); min/max (grid_field.py:79-80).
-//   k_count      : from the bitplanes (L2 resident), per 32-sample word: used-edge words of the 7 Kuhn directions,
+//   k_count_a/_b : from the bitplanes (L2 resident), per 32-sample word: used-edge words of the 7 Kuhn directions,
 //                  per-tet words, vertex / triangle counts (the scan records), per-direction vertex prefix (dirpack),
 //                  strict crossings (grid_field.py:81) -- and, in the same visit, the work lists of stages 3 / 4
 //                  (owner points, emitting voxels) into slots handed out by atomic counters; tile aggregates, scanned
@@ -44,13 +44,13 @@ struct Counters {                    // device counter block (mirrored to pinned
   unsigned long long max_key;        // order-preserving encoding of fmax
   unsigned int any_near;
   unsigned int pad0;
-  // stage 2 (count + scan): zeroed before every launch of k_count_scan
+  // stage 2 (count + scan): zeroed before every launch
   unsigned long long n_cells;        // emitting voxels
   unsigned long long n_cross;        // strict crossings
   unsigned long long total_vt;       // packed totals over the scanned range: T << 31 | V
   unsigned long long v_emit;         // vertex count at the start of plane i_hi (vertices this call emits)
   unsigned int ticket;
-  unsigned int pad1;
+  unsigned int n_word;               // interesting words listed by k_count_a
   unsigned int n_own, n_cell;        // slots handed out in the owner / voxel work lists (their lengths at the end)
 };
 
@@ -376,72 +376,53 @@ __device__ __forceinline__ unsigned words4_interesting(const Grid<T>& g, unsigne
   return out;
 }
 
-struct CountShared {
-  unsigned short cv[CS_TILE], ct[CS_TILE];
-  unsigned short list[CS_TILE];
-  unsigned short vox[256];           // corner bits -> emitting tets (6 bits) | triangle count << 8
-  unsigned long long warp_vt[CS_THREADS / 32], warp_act[CS_THREADS / 32];
-  unsigned warp_items[CS_THREADS / 32];
-  unsigned base_own, base_cell;
-  unsigned nint, last;
-};
-
 // per-word record of the scan: vertices | triangles << 8
 __device__ __forceinline__ unsigned long long rec_vt(uint32_t r) {
   return ((unsigned long long)(r >> 8) << 31) | (r & 255u);
 }
 
-// Stage 2a: counts and work lists in ONE visit of every interesting word.  Tiles of 1024 words in any order, no
-// inter-tile dependency:
-//   A  128-bit quick test (does any of the word's 7 x 32 owned edges cross?), interesting words compacted in smem;
-//   B  dealt out one per thread and round: used-edge words, per-tet words -> vertex / triangle counts (the per-word
-//      record of the scan), dirpack; the round's owner and voxel entries get slots from two atomic counters (one
-//      atomicAdd per round and list) and are written while the bit planes are still in registers:
-//        owner  (own_id = word<<13 | bit<<8 | p_low<<7 | mask7, own_rk = 7 x 5-bit ranks within the directions)
-//        voxel  (cell_id = word<<19 | bit<<14 | emit6<<8 | corner8, cell_toff = first triangle RELATIVE to tbase[word]).
-//      Neither needs the scan: vertex ids are vbase[word] + dirbase + rank, triangle offsets tbase[word] + relative.
-//   C  tile aggregate; the block that finishes last turns the aggregates into exclusive tile prefixes.
-// The lists are ordered inside a round and unordered across rounds / tiles; the mesh does not depend on their order.
+// ------------------------------------------------------------------------------------------------
+// Stage 2a: counts and work lists, in two kernels whose threads are all busy.
+//   k_count_a : every word: 128-bit quick test, record zeroed, interesting words appended to a global list (one atomic
+//               per tile; the list is ordered inside a tile's chunk);
+//   k_count_b : one interesting word per thread, dense: counts, dirpack, owner / voxel work lists (slots: one block
+//               scan and one atomicAdd per list and block), record, tile aggregate by atomicAdd; the last block turns
+//               the aggregates into exclusive tile prefixes.
+// (As ONE kernel per tile of 1024 words -- quick test, then the ~70 interesting words of the tile one per thread -- three
+// quarters of every block idled through the second phase and every tile paid the latency chain planes -> counts -> two
+// global atomics -> list writes on its own: 133 us against 17 + 104 us for the pair, measured under ncu.)
+// Owner entries:  own_id = word<<13 | bit<<8 | p_low<<7 | mask7, own_rk = 7 x 5-bit ranks within the directions.
+// Voxel entries:  cell_id = word<<19 | bit<<14 | emit6<<8 | corner8, cell_toff = first triangle RELATIVE to tbase[word].
+// Neither needs the scan: vertex ids are vbase[word] + dirbase + rank, triangle offsets tbase[word] + relative.
+// The lists are ordered inside a block and unordered across blocks; the mesh does not depend on their order.
+// ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(CS_THREADS, 4) k_count(Grid<T> gin, unsigned word0, unsigned nwords_scan,
-                                                      uint32_t* __restrict__ rec, uint2* __restrict__ wdir,
-                                                      unsigned long long* __restrict__ own_id,
-                                                      unsigned long long* __restrict__ own_rk,
-                                                      unsigned long long* __restrict__ cell_id,
-                                                      uint32_t* __restrict__ cell_toff, unsigned cap_own, unsigned cap_cell,
-                                                      unsigned long long* __restrict__ tile_vt, Counters* ctr, int ntiles) {
-  __shared__ CountShared sh;
-  Grid<T> g = gin;
-  g.any_near = 0;
-  if (threadIdx.x == 0) sh.nint = 0;
-  sh.vox[threadIdx.x] = c_vox[threadIdx.x];          // CS_THREADS == 256: one table entry per thread
+__global__ void __launch_bounds__(CS_THREADS) k_count_a(Grid<T> g, unsigned word0, unsigned nwords_scan,
+                                                     uint32_t* __restrict__ rec, uint32_t* __restrict__ wlist,
+                                                     unsigned cap_w, Counters* ctr) {
+  __shared__ unsigned s_n, s_base;
+  __shared__ unsigned short s_list[CS_TILE];
+  if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
-  const int tile = (int)blockIdx.x;
-  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const unsigned lane = lane_id();
   const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
-  const unsigned emit_end = (unsigned)g.i_hi * plane_words;      // words below this are emitted
-  const unsigned tile0 = (unsigned)tile * CS_TILE;
-
-  // ---- A: dense quick test.  Rows of a multiple of 4 words: thread t takes the 4 consecutive words 4t..4t+3 with
-  // 128-bit loads; otherwise 4 strided words per thread.
+  const unsigned tile0 = blockIdx.x * CS_TILE;
   if ((g.W & 3) == 0) {
     const unsigned wl0 = threadIdx.x * CS_ITEMS;
     const unsigned rel = tile0 + wl0;
     unsigned m4 = 0;
-    if (rel < nwords_scan) m4 = words4_interesting(g, word0 + rel, plane_words);     // nwords_scan is a multiple of W
-#pragma unroll
-    for (int q = 0; q < CS_ITEMS; ++q) {
-      sh.cv[wl0 + q] = 0;
-      sh.ct[wl0 + q] = 0;
+    if (rel < nwords_scan) {
+      m4 = words4_interesting(g, word0 + rel, plane_words);
+      *reinterpret_cast<uint4*>(rec + word0 + rel) = make_uint4(0u, 0u, 0u, 0u);
     }
     const unsigned cnt = __popc(m4);
     const unsigned inc = warp_incl_scan_u32(cnt);
     unsigned base = 0;
-    if (lane == 31 && inc) base = atomicAdd(&sh.nint, inc);
+    if (lane == 31 && inc) base = atomicAdd(&s_n, inc);
     base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
 #pragma unroll
     for (int q = 0; q < CS_ITEMS; ++q)
-      if ((m4 >> q) & 1u) sh.list[base++] = (unsigned short)(wl0 + q);
+      if ((m4 >> q) & 1u) s_list[base++] = (unsigned short)(wl0 + q);
   } else {
 #pragma unroll
     for (int q = 0; q < CS_ITEMS; ++q) {
@@ -456,144 +437,169 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_count(Grid<T> gin, unsigned w
         uint32_t x[7];
         cross_words(pl, x);
         interesting = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6]) != 0;
+        rec[word0 + rel] = 0u;
       }
-      sh.cv[wl] = 0;
-      sh.ct[wl] = 0;
       const unsigned m = __ballot_sync(0xffffffffu, interesting);
       unsigned base = 0;
-      if (lane == 0 && m) base = atomicAdd(&sh.nint, (unsigned)__popc(m));
+      if (lane == 0 && m) base = atomicAdd(&s_n, (unsigned)__popc(m));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (interesting) sh.list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)wl;
+      if (interesting) s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)wl;
     }
   }
   __syncthreads();
-  const unsigned nint = sh.nint;
+  const unsigned nint = s_n;
+  if (!nint) return;
+  if (threadIdx.x == 0) s_base = atomicAdd(&ctr->n_word, nint);
+  __syncthreads();
+  const unsigned b0 = s_base;
+  for (unsigned q = threadIdx.x; q < nint; q += CS_THREADS)
+    if (b0 + q < cap_w) wlist[b0 + q] = word0 + tile0 + s_list[q];
+}
 
-  // ---- B: the interesting words, one per thread and round
+constexpr int CB_THREADS = 256;                     // (128: 160 us for stage 2 instead of 153)
+
+struct CountBShared {
+  unsigned short vox[256];
+  unsigned long long warp_vt[CB_THREADS / 32];
+  unsigned warp_items[CB_THREADS / 32];
+  unsigned base_own, base_cell, last;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(CB_THREADS, 4) k_count_b(Grid<T> gin, unsigned word0, const uint32_t* __restrict__ wlist,
+                                                        unsigned cap_w, uint32_t* __restrict__ rec, uint2* __restrict__ wdir,
+                                                        unsigned long long* __restrict__ own_id,
+                                                        unsigned long long* __restrict__ own_rk,
+                                                        unsigned long long* __restrict__ cell_id,
+                                                        uint32_t* __restrict__ cell_toff, unsigned cap_own, unsigned cap_cell,
+                                                        unsigned long long* __restrict__ tile_vt, Counters* ctr, int ntiles) {
+  __shared__ CountBShared sh;
+  Grid<T> g = gin;
+  g.any_near = 0;
+  for (unsigned q = threadIdx.x; q < 256u; q += CB_THREADS) sh.vox[q] = c_vox[q];
+  __syncthreads();
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
+  const unsigned emit_end = (unsigned)g.i_hi * plane_words;
+  const unsigned nint = min(ctr->n_word, cap_w);
+  const unsigned idx = blockIdx.x * CB_THREADS + threadIdx.x;
+  const bool have = idx < nint;
   unsigned ncross = 0, ncells = 0;
-  for (unsigned r0 = 0; r0 < nint; r0 += CS_THREADS) {
-    const unsigned idx = r0 + threadIdx.x;
-    const bool have = idx < nint;
-    unsigned gw = 0, wl = 0;
-    int i = 0, j = 0, w = 0;
-    Planes pl;
-    uint32_t x[7] = {0, 0, 0, 0, 0, 0, 0};
-    uint32_t any = 0, em = 0;
-    if (have) {
-      wl = sh.list[idx];
-      gw = word0 + tile0 + wl;
-      g.word_coords(gw, i, j, w);
-      g.any_near = g.rowflag[(size_t)i * g.n1 + j];
-      load_planes(g, g.bits, i, j, w, pl);
-      owner_used(g, pl, i, j, w, x);
-      unsigned v = 0;
+  unsigned gw = 0;
+  int i = 0, j = 0, w = 0;
+  Planes pl;
+  uint32_t x[7] = {0, 0, 0, 0, 0, 0, 0};
+  uint32_t any = 0, em = 0;
+  if (have) {
+    gw = wlist[idx];
+    g.word_coords(gw, i, j, w);
+    g.any_near = g.rowflag[(size_t)i * g.n1 + j];
+    load_planes(g, g.bits, i, j, w, pl);
+    owner_used(g, pl, i, j, w, x);
+    unsigned v = 0;
 #pragma unroll
-      for (int d = 0; d < 7; ++d) {
-        v += __popc(x[d]);
-        any |= x[d];
+    for (int d = 0; d < 7; ++d) {
+      v += __popc(x[d]);
+      any |= x[d];
+    }
+    const bool cells_ok = pl.has_i1 && pl.has_j1 && i < g.i_hi;
+    unsigned t = 0;
+    if (cells_ok) {
+      if (!g.any_near) {
+#pragma unroll
+        for (int d = 0; d < 7; ++d) ncross += __popc(x[d] & pl.kp1);
+      } else {
+        uint32_t xs[7];
+        cross_words(pl, xs);
+#pragma unroll
+        for (int d = 0; d < 7; ++d) ncross += __popc(xs[d] & pl.kp1);
       }
-      const bool cells_ok = pl.has_i1 && pl.has_j1 && i < g.i_hi;
-      unsigned t = 0;
-      if (cells_ok) {
-        // strict crossings for owners inside the voxel range (grid_field.py:64-84)
-        if (!g.any_near) {
+      uint32_t odd[6], two[6], cand;
+      tet_words(pl, nullptr, pl.kp1, odd, two, cand);
 #pragma unroll
-          for (int d = 0; d < 7; ++d) ncross += __popc(x[d] & pl.kp1);
-        } else {
-          uint32_t xs[7];
-          cross_words(pl, xs);
-#pragma unroll
-          for (int d = 0; d < 7; ++d) ncross += __popc(xs[d] & pl.kp1);
-        }
-        uint32_t odd[6], two[6], cand;
-        tet_words(pl, nullptr, pl.kp1, odd, two, cand);
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          t += __popc(odd[q]) + 2 * __popc(two[q]);
-          em |= odd[q] | two[q];
-        }
-      }
-      if (g.any_near) count_word_exact(g, pl, i, j, w, cells_ok, ncross, t, em);
-      sh.cv[wl] = (unsigned short)v;
-      sh.ct[wl] = (unsigned short)t;
-      if (v) wdir[gw] = dir_pack(x);
-      if (gw >= emit_end) any = 0u;
-      ncells += __popc(em);
-    }
-    // slots of this round's entries: block scan of (owners | voxels << 16), one atomicAdd per list
-    const unsigned items = (unsigned)__popc(any) | ((unsigned)__popc(em) << 16);
-    const unsigned inc = warp_incl_scan_u32(items);
-    __syncthreads();                                  // warp_items / base_* of the previous round are consumed
-    if (lane == 31) sh.warp_items[warp] = inc;
-    __syncthreads();
-    unsigned woff = 0, tot = 0;
-#pragma unroll
-    for (int q = 0; q < CS_THREADS / 32; ++q) {
-      if (q < (int)warp) woff += sh.warp_items[q];
-      tot += sh.warp_items[q];
-    }
-    if (threadIdx.x == 0) {
-      sh.base_own = (tot & 0xffffu) ? atomicAdd(&ctr->n_own, tot & 0xffffu) : 0u;
-      sh.base_cell = (tot >> 16) ? atomicAdd(&ctr->n_cell, tot >> 16) : 0u;
-    }
-    __syncthreads();
-    const unsigned excl = woff + inc - items;
-    unsigned orun = sh.base_own + (excl & 0xffffu), crun = sh.base_cell + (excl >> 16);
-    if (any) {
-      uint32_t mo = any;
-      while (mo) {
-        const int b = __ffs(mo) - 1;
-        mo &= mo - 1;
-        if (orun < cap_own) {
-          // rank of the point among the used edges of each direction (5 bits x 7): with the word's vbase and dirpack
-          // this gives the vertex id of every edge the point owns
-          const uint32_t below = (1u << b) - 1u;
-          unsigned long long rk = 0;
-#pragma unroll
-          for (int d = 0; d < 7; ++d) rk |= (unsigned long long)__popc(x[d] & below) << (5 * d);
-          own_id[orun] = ((unsigned long long)gw << 13) | ((unsigned)b << 8) | (((pl.P[0] >> b) & 1u) << 7) | gather7(x, b);
-          own_rk[orun] = rk;
-        }
-        ++orun;
+      for (int q = 0; q < 6; ++q) {
+        t += __popc(odd[q]) + 2 * __popc(two[q]);
+        em |= odd[q] | two[q];
       }
     }
-    if (em) {
-      uint32_t me = em;
-      unsigned trun = 0;
-      Planes npl;
-      if (g.any_near) load_planes(g, g.nbits, i, j, w, npl);
-      while (me) {
-        const int b = __ffs(me) - 1;
-        me &= me - 1;
-        unsigned c8 = 0;
+    if (g.any_near) count_word_exact(g, pl, i, j, w, cells_ok, ncross, t, em);
+    const uint32_t r = v | (t << 8);
+    if (r) {
+      rec[gw] = r;
+      atomicAdd(&tile_vt[(gw - word0) / CS_TILE], rec_vt(r));
+    }
+    if (v) wdir[gw] = dir_pack(x);
+    if (gw >= emit_end) any = 0u;
+    ncells += __popc(em);
+  }
+  const unsigned items = (unsigned)__popc(any) | ((unsigned)__popc(em) << 16);
+  const unsigned inc = warp_incl_scan_u32(items);
+  if (lane == 31) sh.warp_items[warp] = inc;
+  __syncthreads();
+  unsigned woff = 0, tot = 0;
 #pragma unroll
-        for (int ab = 0; ab < 4; ++ab)                      // corners (ab, dk): bit b of the row and of the row shifted in k
-          c8 |= (((pl.P[ab] >> b) & 1u) | (((pl.S[ab] >> b) & 1u) << 1)) << (2 * ab);
-        // emitting tets (all the mixed ones) and their triangle count from a 256-entry table of the corner bits
-        const unsigned en = sh.vox[c8];
-        unsigned emit = en & 63u, nt = en >> 8;
-        if (g.any_near) {
-          unsigned n8 = 0;
+  for (int q = 0; q < CB_THREADS / 32; ++q) {
+    if (q < (int)warp) woff += sh.warp_items[q];
+    tot += sh.warp_items[q];
+  }
+  if (threadIdx.x == 0) {
+    sh.base_own = (tot & 0xffffu) ? atomicAdd(&ctr->n_own, tot & 0xffffu) : 0u;
+    sh.base_cell = (tot >> 16) ? atomicAdd(&ctr->n_cell, tot >> 16) : 0u;
+  }
+  __syncthreads();
+  const unsigned excl = woff + inc - items;
+  unsigned orun = sh.base_own + (excl & 0xffffu), crun = sh.base_cell + (excl >> 16);
+  if (any) {
+    uint32_t mo = any;
+    while (mo) {
+      const int b = __ffs(mo) - 1;
+      mo &= mo - 1;
+      if (orun < cap_own) {
+        const uint32_t below = (1u << b) - 1u;
+        unsigned long long rk = 0;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) n8 |= ((corner_plane(npl, c) >> b) & 1u) << c;
-          bool cand = false;
-#pragma unroll
-          for (int t = 0; t < 6; ++t) cand = cand || (((emit >> t) & 1u) && tet_mask_of(n8, t) == 15);
-          if (cand) {
-            emit = cell_emit_exact(g, i, j, w * 32 + b, nullptr);
-            nt = 0;
-#pragma unroll
-            for (int t = 0; t < 6; ++t)
-              if ((emit >> t) & 1u) nt += (__popc(tet_mask_of(c8, t)) == 2) ? 2u : 1u;
-          }
-        }
-        if (crun < cap_cell) {
-          cell_id[crun] = ((unsigned long long)gw << 19) | ((unsigned)b << 14) | (emit << 8) | c8;
-          cell_toff[crun] = trun;                           // relative to tbase[word]
-        }
-        ++crun;
-        trun += nt;
+        for (int d = 0; d < 7; ++d) rk |= (unsigned long long)__popc(x[d] & below) << (5 * d);
+        own_id[orun] = ((unsigned long long)gw << 13) | ((unsigned)b << 8) | (((pl.P[0] >> b) & 1u) << 7) | gather7(x, b);
+        own_rk[orun] = rk;
       }
+      ++orun;
+    }
+  }
+  if (em) {
+    uint32_t me = em;
+    unsigned trun = 0;
+    Planes npl;
+    if (g.any_near) load_planes(g, g.nbits, i, j, w, npl);
+    while (me) {
+      const int b = __ffs(me) - 1;
+      me &= me - 1;
+      unsigned c8 = 0;
+#pragma unroll
+      for (int ab = 0; ab < 4; ++ab)
+        c8 |= (((pl.P[ab] >> b) & 1u) | (((pl.S[ab] >> b) & 1u) << 1)) << (2 * ab);
+      const unsigned en = sh.vox[c8];
+      unsigned emit = en & 63u, nt = en >> 8;
+      if (g.any_near) {
+        unsigned n8 = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) n8 |= ((corner_plane(npl, c) >> b) & 1u) << c;
+        bool cand = false;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) cand = cand || (((emit >> t) & 1u) && tet_mask_of(n8, t) == 15);
+        if (cand) {
+          emit = cell_emit_exact(g, i, j, w * 32 + b, nullptr);
+          nt = 0;
+#pragma unroll
+          for (int t = 0; t < 6; ++t)
+            if ((emit >> t) & 1u) nt += (__popc(tet_mask_of(c8, t)) == 2) ? 2u : 1u;
+        }
+      }
+      if (crun < cap_cell) {
+        cell_id[crun] = ((unsigned long long)gw << 19) | ((unsigned)b << 14) | (emit << 8) | c8;
+        cell_toff[crun] = trun;
+      }
+      ++crun;
+      trun += nt;
     }
   }
   unsigned long long cc = ((unsigned long long)ncross << 32) | ncells;
@@ -603,84 +609,36 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_count(Grid<T> gin, unsigned w
     if (cc & 0xffffffffull) atomicAdd(&ctr->n_cells, cc & 0xffffffffull);
     if (cc >> 32) atomicAdd(&ctr->n_cross, cc >> 32);
   }
-  __syncthreads();
-
-  // ---- records (thread t owns the 4 consecutive words 4t..4t+3) and the tile aggregate
-  unsigned long long loc_vt = 0, loc_act = 0;
-  uint32_t r4[CS_ITEMS];
-#pragma unroll
-  for (int it = 0; it < CS_ITEMS; ++it) {
-    const unsigned wl = threadIdx.x * CS_ITEMS + it;
-    r4[it] = (uint32_t)sh.cv[wl] | ((uint32_t)sh.ct[wl] << 8);
-    loc_vt += rec_vt(r4[it]);
-  }
-  {
-    const unsigned rel0 = tile0 + threadIdx.x * CS_ITEMS;
-#pragma unroll
-    for (int it = 0; it < CS_ITEMS; ++it)
-      if (rel0 + it < nwords_scan) rec[word0 + rel0 + it] = r4[it];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    loc_vt += __shfl_xor_sync(0xffffffffu, loc_vt, o);
-    loc_act += __shfl_xor_sync(0xffffffffu, loc_act, o);
-  }
-  if (lane == 0) {
-    sh.warp_vt[warp] = loc_vt;
-    sh.warp_act[warp] = loc_act;
-  }
+  // the block that finishes last turns the tile aggregates into exclusive prefixes
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned long long a = 0, b = 0;
-#pragma unroll
-    for (int q = 0; q < CS_THREADS / 32; ++q) {
-      a += sh.warp_vt[q];
-      b += sh.warp_act[q];
-    }
-    tile_vt[tile] = a;
     __threadfence();
-    sh.last = (atomicAdd(&ctr->ticket, 1u) == (unsigned)ntiles - 1u) ? 1u : 0u;
+    sh.last = (atomicAdd(&ctr->ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
   }
   __syncthreads();
   if (!sh.last) return;
-  // ---- last block: exclusive scan of the tile aggregates in place (a few thousand entries)
   __threadfence();
-  unsigned long long carry_vt = 0, carry_act = 0;
-  for (int base = 0; base < ntiles; base += CS_THREADS) {
+  unsigned long long carry = 0;
+  for (int base = 0; base < ntiles; base += CB_THREADS) {
     const int q = base + (int)threadIdx.x;
-    unsigned long long a = 0, b = 0;
-    if (q < ntiles) {
-      a = lb_load(&tile_vt[q]);
-    }
-    const unsigned long long ia = warp_incl_scan_u64(a), ib = warp_incl_scan_u64(b);
+    const unsigned long long a = q < ntiles ? lb_load(&tile_vt[q]) : 0ull;
+    const unsigned long long ia = warp_incl_scan_u64(a);
     __syncthreads();
-    if (lane == 31) {
-      sh.warp_vt[warp] = ia;
-      sh.warp_act[warp] = ib;
-    }
+    if (lane == 31) sh.warp_vt[warp] = ia;
     __syncthreads();
-    unsigned long long wa = 0, wb = 0, ta = 0, tb = 0;
+    unsigned long long wa = 0, ta = 0;
 #pragma unroll
-    for (int w8 = 0; w8 < CS_THREADS / 32; ++w8) {
-      if (w8 < (int)warp) {
-        wa += sh.warp_vt[w8];
-        wb += sh.warp_act[w8];
-      }
+    for (int w8 = 0; w8 < CB_THREADS / 32; ++w8) {
+      if (w8 < (int)warp) wa += sh.warp_vt[w8];
       ta += sh.warp_vt[w8];
-      tb += sh.warp_act[w8];
     }
-    if (q < ntiles) {
-      tile_vt[q] = carry_vt + wa + ia - a;
-    }
-    carry_vt += ta;
-    carry_act += tb;
+    if (q < ntiles) tile_vt[q] = carry + wa + ia - a;
+    carry += ta;
   }
-  if (threadIdx.x == 0) {
-    ctr->total_vt = carry_vt;
-  }
+  if (threadIdx.x == 0) ctr->total_vt = carry;
 }
 
-// Stage 2b: offsets.  Every tile knows its exclusive prefix (k_count's last block): block scan of the per-word records
+// Stage 2b: offsets.  Every tile knows its exclusive prefix (k_count_b's last block): block scan of the per-word records
 // -> vbase[word] (first vertex id of the word), tbase[word] (first triangle of the word).
 template <typename T>
 __global__ void __launch_bounds__(CS_THREADS) k_scan(Grid<T> g, unsigned word0, unsigned nwords_scan,
@@ -1230,6 +1188,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
   DevBuf& b_own_voff = ctx->aux[1];
   DevBuf& b_cell_id = ctx->aux[2];
   DevBuf& b_cell_toff = ctx->aux[3];
+  if (!ctx->spec_w) ctx->spec_w = std::max<size_t>((size_t)nwords / 4, 1 << 14);
   if (!ctx->spec_own) ctx->spec_own = std::max<size_t>((size_t)nwords / 2, 1 << 14);
   if (!ctx->spec_cell) ctx->spec_cell = ctx->spec_own;
   if (!ctx->spec_v) ctx->spec_v = ctx->spec_own * 2;
@@ -1241,6 +1200,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
     if ((rc = ctr_ensure(ctx, b_own_voff, ctx->spec_own * 8, true))) return rc;      // own_rk
     if ((rc = ctr_ensure(ctx, b_cell_id, ctx->spec_cell * 8, true))) return rc;
     if ((rc = ctr_ensure(ctx, b_cell_toff, ctx->spec_cell * 4, true))) return rc;
+    if ((rc = ctr_ensure(ctx, ctx->wlist, ctx->spec_w * 4, true))) return rc;
     if (geom) {
       if ((rc = ctr_ensure(ctx, ctx->verts, ctx->spec_v * 3 * gsz, true))) return rc;
       if (want_n && (rc = ctr_ensure(ctx, ctx->normals, ctx->spec_v * 3 * gsz, true))) return rc;
@@ -1252,6 +1212,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
     const unsigned cap_cell = (unsigned)std::min<size_t>(ctx->spec_cell, 0x7fffffffu);
     const unsigned cap_v = (unsigned)std::min<size_t>(ctx->spec_v, 0x7fffffffu);
     const unsigned cap_t = (unsigned)std::min<size_t>(ctx->spec_t, 0x7fffffffu);
+    const unsigned cap_w = (unsigned)std::min<size_t>(ctx->spec_w, 0x7fffffffu);
 
     if (!(phase == 2 && attempt == 0)) {                 // phase 2: attempt 0 was enqueued by phase 1
     k_reset3<<<64, 256, 0, st>>>(dctr, (uint4*)ctx->aux[4].p, (size_t)(nrows + 15) / 16, st_vt, (size_t)ntiles);
@@ -1267,12 +1228,17 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
     CTR_DBG(ctx, "k_bitplane");
     ctr_stage_mark(ctx, 2);
     if (ntiles > 0) {
-      k_count<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (uint32_t*)ctx->tbase.p, (uint2*)ctx->wdir.p,
-                                                (unsigned long long*)b_own_id.p, (unsigned long long*)b_own_voff.p,
-                                                (unsigned long long*)b_cell_id.p, (uint32_t*)b_cell_toff.p, cap_own, cap_cell,
-                                                st_vt, dctr, ntiles);
-      ctx->launches++;
-      CTR_DBG(ctx, "k_count");
+      k_count_a<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (uint32_t*)ctx->tbase.p, (uint32_t*)ctx->wlist.p, cap_w, dctr);
+      CTR_DBG(ctx, "k_count_a");
+      // the grid covers the expected list length (last run's, with head-room); blocks past the real length only take a ticket
+      const unsigned wb = (unsigned)((std::min<size_t>(cap_w, ctx->last_w + ctx->last_w / 8 + 4096) + CB_THREADS - 1) / CB_THREADS);
+      k_count_b<T><<<wb, CB_THREADS, 0, st>>>(g, word0, (const uint32_t*)ctx->wlist.p, cap_w, (uint32_t*)ctx->tbase.p,
+                                              (uint2*)ctx->wdir.p, (unsigned long long*)b_own_id.p,
+                                              (unsigned long long*)b_own_voff.p, (unsigned long long*)b_cell_id.p,
+                                              (uint32_t*)b_cell_toff.p, cap_own, cap_cell, st_vt, dctr, ntiles);
+      ctx->launches += 2;
+      ctx->cover_w = (size_t)wb * CB_THREADS;
+      CTR_DBG(ctx, "k_count_b");
       k_scan<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (const uint32_t*)ctx->tbase.p, st_vt, (uint32_t*)ctx->vbase.p,
                                                (uint32_t*)ctx->wmask.p, dctr);
       ctx->launches++;
@@ -1330,10 +1296,13 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
       return ctr_fail(ctx, CTR_ERR_OVERFLOW, "more than 2^31 vertices or triangles in one call; shard the volume");
     ctx->last_own = (size_t)nOwn;
     ctx->last_cell = (size_t)nCell;
-    const bool ok = nOwn <= cap_own && nCell <= cap_cell && (!geom || (nV <= cap_v && totT <= cap_t && nOwn <= ctx->cover_own &&
+    const size_t nWord = (size_t)h.n_word;
+    ctx->last_w = nWord;
+    const bool ok = nWord <= cap_w && nWord <= ctx->cover_w && nOwn <= cap_own && nCell <= cap_cell && (!geom || (nV <= cap_v && totT <= cap_t && nOwn <= ctx->cover_own &&
                                                                        nCell <= ctx->cover_cell));
     if (ok) break;
-    if (attempt == 2) return ctr_fail(ctx, CTR_ERR_STATE, "capacities did not converge");
+    if (attempt == 3) return ctr_fail(ctx, CTR_ERR_STATE, "capacities did not converge");
+    ctx->spec_w = std::max<size_t>(ctx->spec_w, nWord + nWord / 4 + 1024);
     ctx->spec_own = std::max<size_t>(ctx->spec_own, (size_t)nOwn + (size_t)nOwn / 4 + 1024);
     ctx->spec_cell = std::max<size_t>(ctx->spec_cell, (size_t)nCell + (size_t)nCell / 4 + 1024);
     ctx->spec_v = std::max<size_t>(ctx->spec_v, (size_t)nV + (size_t)nV / 4 + 1024);
