@@ -24,8 +24,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ISOVALUE = 0.5
-# dram__bytes_read.sum + dram__bytes_write.sum of the five kernels of one extraction, from profiles/ (ncu --set full);
-TRAFFIC_BYTES = 1014.9e6     # profiles/r1m_ncu_full_summary.txt, sum over the five kernels (algorithmic: 725.9 MB)
+# dram__bytes_read.sum + dram__bytes_write.sum of the six kernels of one extraction, from profiles/ (ncu --set full);
+TRAFFIC_BYTES = 1027.4e6     # profiles/r1o_ncu_full_summary.txt, dram read + write summed over the six kernels (algorithmic: 725.9 MB)
 METRIC = "Gvoxels/s, 512^3 fp32 marching-tetrahedra extraction (indexed mesh + normals)"
 
 
