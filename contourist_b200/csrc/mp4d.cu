@@ -5,10 +5,12 @@
 //   k4_count_scan          : per 32-hypervoxel word, from the bitplanes: distinct crossing edges (15 Kuhn
 //                            directions per owner), tetrahedra (24 pentatopes x {1,3}), decoupled-lookback scan,
 //                            compacted owner / hypervoxel lists;
-//   k4_emit_verts          : edge crossings in 4D (tetrahedral.py:471-487);
+//   k4_emit_verts          : edge crossings in 4D (tetrahedral.py:471-487); with CTR_MORPH also the fp64 grid-coordinate
+//                            vertices with binned times, the bins and their range (pentatopes.py:162-169,336-337);
 //   k4_emit_tets           : per hypervoxel, 24 pentatopes (pentatopes.py:15-26,223-291) -> tets of vertex ids;
-//   k4_bin / k4_tet_filter / k4_slice_count / k4_slice_emit : pentatopes.py:162-189, tetrahedral.py:353-375
-//                            (predicate), morph_geometry.py:145-237.
+//   k4_slice               : morph_geometry.py:145-237 slicing, single pass (look-back scan, smem-staged output), with
+//                            the instant / tiny filter (pentatopes.py:171-189, tetrahedral.py:353-375) folded in when
+//                            the integer time bins decide it; k4_tet_filter is the general (fp64) form of that filter.
 #include "bitplane.cuh"
 #include "tables.h"
 
@@ -496,44 +498,86 @@ __device__ __forceinline__ float mul_rn4(float a, float b) { return __fmul_rn(a,
 __device__ __forceinline__ double add_rn4(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ float add_rn4(float a, float b) { return __fadd_rn(a, b); }
 
+// One thread per owner point: its 1..15 crossing edges (tetrahedral.py:471-487 in 4D), world transform.
+// With mverts != nullptr the morph stage's inputs come out of the same visit of the samples: the fp64 grid-coordinate
+// vertex with its time snapped down to a bin (pentatopes.py:162-169 bin_times), the bin itself, and the range of the
+// binned times (for the zero-duration threshold, pentatopes.py:336-337).
 template <typename T, typename G>
 __global__ void __launch_bounds__(256) k4_emit_verts(Grid4<T> g, const unsigned long long* __restrict__ own_id,
                                                      const uint32_t* __restrict__ own_voff, unsigned n_own, Xform4 xf,
                                                      G* __restrict__ verts, unsigned long long* __restrict__ keys,
-                                                     uint8_t* __restrict__ lowmin) {
+                                                     uint8_t* __restrict__ lowmin, double* __restrict__ mverts,
+                                                     int* __restrict__ tbin, double bin_width, MinMaxKeys* mm) {
   const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_own) return;
-  const unsigned long long oid = own_id[a];
-  unsigned id = own_voff[a];
-  const unsigned m15 = (unsigned)oid & 0x7fffu;
-  const bool p_low = (oid >> 15) & 1u;
-  int i, j, k, w;
-  g.word_coords((unsigned)(oid >> 21), i, j, k, w);
-  const int l = w * 32 + (int)((oid >> 16) & 31u);
-  const G fp = (G)g.f[g.row_of(i, j, k) * g.n3 + l];
-  const G v = (G)g.v;
-  const unsigned long long lin = (unsigned long long)(g.row_of(i, j, k) * g.n3 + l);
+  double tmn = INFINITY, tmx = -INFINITY;
+  if (a < n_own) {
+    const unsigned long long oid = own_id[a];
+    unsigned id = own_voff[a];
+    const unsigned m15 = (unsigned)oid & 0x7fffu;
+    const bool p_low = (oid >> 15) & 1u;
+    int i, j, k, w;
+    g.word_coords((unsigned)(oid >> 21), i, j, k, w);
+    const int l = w * 32 + (int)((oid >> 16) & 31u);
+    const T fp_raw = g.f[g.row_of(i, j, k) * g.n3 + l];
+    const G fp = (G)fp_raw;
+    const G v = (G)g.v;
+    const unsigned long long lin = (unsigned long long)(g.row_of(i, j, k) * g.n3 + l);
 #pragma unroll 1
-  for (int d = 1; d <= 15; ++d) {
-    if (!((m15 >> (d - 1)) & 1u)) continue;
-    const int dd[4] = {(d >> 3) & 1, (d >> 2) & 1, (d >> 1) & 1, d & 1};
-    const G fq = (G)g.f[g.row_of(i + dd[0], j + dd[1], k + dd[2]) * g.n3 + l + dd[3]];
-    const G flow = p_low ? fp : fq, fhigh = p_low ? fq : fp;
-    const G den = fhigh - flow;
-    const G ratio = (fabs((double)den) <= 1e-8) ? (G)0.5 : (v - flow) / den;
-    const G step = p_low ? ratio : -ratio;
-    const int p0[4] = {i, j, k, l};
+    for (int d = 1; d <= 15; ++d) {
+      if (!((m15 >> (d - 1)) & 1u)) continue;
+      const int dd[4] = {(d >> 3) & 1, (d >> 2) & 1, (d >> 1) & 1, d & 1};
+      const T fq_raw = g.f[g.row_of(i + dd[0], j + dd[1], k + dd[2]) * g.n3 + l + dd[3]];
+      const int p0[4] = {i, j, k, l};
+      {
+        const G fq = (G)fq_raw;
+        const G flow = p_low ? fp : fq, fhigh = p_low ? fq : fp;
+        const G den = fhigh - flow;
+        const G ratio = (fabs((double)den) <= 1e-8) ? (G)0.5 : (v - flow) / den;
+        const G step = p_low ? ratio : -ratio;
 #pragma unroll
-    for (int ax = 0; ax < 4; ++ax) {
-      const G b0 = (G)(p_low ? p0[ax] : p0[ax] + dd[ax]);
-      const G x = dd[ax] ? add_rn4(b0, step) : b0;
-      verts[(size_t)id * 4 + ax] = add_rn4(mul_rn4(x, (G)xf.delta[ax]), (G)xf.origin[ax]);
+        for (int ax = 0; ax < 4; ++ax) {
+          const G b0 = (G)(p_low ? p0[ax] : p0[ax] + dd[ax]);
+          const G x = dd[ax] ? add_rn4(b0, step) : b0;
+          verts[(size_t)id * 4 + ax] = add_rn4(mul_rn4(x, (G)xf.delta[ax]), (G)xf.origin[ax]);
+        }
+      }
+      if (mverts) {
+        const double fpd = (double)fp_raw, fqd = (double)fq_raw;
+        const double flow = p_low ? fpd : fqd, fhigh = p_low ? fqd : fpd;
+        const double den = fhigh - flow;
+        const double ratio = (fabs(den) <= 1e-8) ? 0.5 : (g.v - flow) / den;
+        const double step = p_low ? ratio : -ratio;
+        double x[4];
+#pragma unroll
+        for (int ax = 0; ax < 4; ++ax) {
+          const double b0 = (double)(p_low ? p0[ax] : p0[ax] + dd[ax]);
+          x[ax] = dd[ax] ? __dadd_rn(b0, step) : b0;
+        }
+        const double b = trunc(x[3] / bin_width);
+        x[3] = __dmul_rn(b, bin_width);                                             // pentatopes.py:168-169
+        tbin[id] = (int)fmax(fmin(b, 1.0e9), -1.0e9);
+        reinterpret_cast<double2*>(mverts + (size_t)id * 4)[0] = make_double2(x[0], x[1]);
+        reinterpret_cast<double2*>(mverts + (size_t)id * 4)[1] = make_double2(x[2], x[3]);
+        tmn = fmin(tmn, x[3]);
+        tmx = fmax(tmx, x[3]);
+      }
+      if (keys) {
+        keys[id] = (lin << 4) | (unsigned)d;
+        lowmin[id] = p_low ? 1 : 0;
+      }
+      ++id;
     }
-    if (keys) {
-      keys[id] = (lin << 4) | (unsigned)d;
-      lowmin[id] = p_low ? 1 : 0;
+  }
+  if (mverts) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tmn = fmin(tmn, __shfl_xor_sync(0xffffffffu, tmn, o));
+      tmx = fmax(tmx, __shfl_xor_sync(0xffffffffu, tmx, o));
     }
-    ++id;
+    if (lane_id() == 0 && tmn <= tmx) {
+      atomicMin(&mm->min_key, order_key(tmn));
+      atomicMax(&mm->max_key, order_key(tmx));
+    }
   }
 }
 
@@ -622,44 +666,37 @@ __global__ void __launch_bounds__(E4_THREADS) k4_emit_tets(Grid4<T> gin, const u
 // ------------------------------------------------------------------------------------------------
 // morph stage (grid coordinates, fp64): pentatopes.py:162-189, tetrahedral.py:353-375, morph_geometry.py:145-237
 // ------------------------------------------------------------------------------------------------
-__global__ void k4_bin(double* __restrict__ verts, int* __restrict__ tbin, unsigned nv, double min_interval) {
-  const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= nv) return;
-  const double t = verts[(size_t)a * 4 + 3];
-  const double b = trunc(t / min_interval);
-  verts[(size_t)a * 4 + 3] = __dmul_rn(b, min_interval);                            // pentatopes.py:168-169
-  tbin[a] = (int)fmax(fmin(b, 1.0e9), -1.0e9);       // the bin itself: binned times compare like these integers
-}
-
 struct MorphParams {
   double inv_corner[4];
   double eps_instant, eps_tiny, eps_gap, eps_in, t_eps;
 };
 
-// keep[t] = 1 unless the tet is instantaneous (t extent < eps_instant) or tiny (every extent/corner < eps_tiny)
+// keep[t] = 1 unless the tet is instantaneous (t extent < eps_instant) or tiny (every extent/corner < eps_tiny).
+// Both verdicts need the (z, t) halves of the four vertices; x and y only matter when z and t are already tiny, which
+// almost never happens: they are loaded on that path only (half the gather traffic, half the instructions).
 __global__ void k4_tet_filter(const double* __restrict__ verts, const int* __restrict__ tets, unsigned nt, MorphParams mp,
                               uint8_t* __restrict__ keep) {
   const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nt) return;
-  double mn[4], mx[4];
-  const int4 t4 = *reinterpret_cast<const int4*>(tets + (size_t)a * 4);       // 128-bit loads: ids, then 2 per vertex
+  const int4 t4 = *reinterpret_cast<const int4*>(tets + (size_t)a * 4);
   const int tv[4] = {t4.x, t4.y, t4.z, t4.w};
+  double2 zt[4];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const double2* p = reinterpret_cast<const double2*>(verts + (size_t)tv[r] * 4);
-    const double2 xy = p[0], zt = p[1];
-    const double x[4] = {xy.x, xy.y, zt.x, zt.y};
+  for (int r = 0; r < 4; ++r) zt[r] = reinterpret_cast<const double2*>(verts + (size_t)tv[r] * 4)[1];
+  const double zmn = fmin(fmin(zt[0].x, zt[1].x), fmin(zt[2].x, zt[3].x)), zmx = fmax(fmax(zt[0].x, zt[1].x), fmax(zt[2].x, zt[3].x));
+  const double tmn = fmin(fmin(zt[0].y, zt[1].y), fmin(zt[2].y, zt[3].y)), tmx = fmax(fmax(zt[0].y, zt[1].y), fmax(zt[2].y, zt[3].y));
+  const bool instant = (tmx - tmn) < mp.eps_instant;
+  double ext = fmax(__dmul_rn(zmx - zmn, mp.inv_corner[2]), __dmul_rn(tmx - tmn, mp.inv_corner[3]));
+  bool tiny = false;
+  if (!instant && ext < mp.eps_tiny) {
+    double2 xy[4];
 #pragma unroll
-    for (int ax = 0; ax < 4; ++ax) {
-      mn[ax] = r == 0 ? x[ax] : fmin(mn[ax], x[ax]);
-      mx[ax] = r == 0 ? x[ax] : fmax(mx[ax], x[ax]);
-    }
+    for (int r = 0; r < 4; ++r) xy[r] = reinterpret_cast<const double2*>(verts + (size_t)tv[r] * 4)[0];
+    const double xmn = fmin(fmin(xy[0].x, xy[1].x), fmin(xy[2].x, xy[3].x)), xmx = fmax(fmax(xy[0].x, xy[1].x), fmax(xy[2].x, xy[3].x));
+    const double ymn = fmin(fmin(xy[0].y, xy[1].y), fmin(xy[2].y, xy[3].y)), ymx = fmax(fmax(xy[0].y, xy[1].y), fmax(xy[2].y, xy[3].y));
+    ext = fmax(ext, fmax(__dmul_rn(xmx - xmn, mp.inv_corner[0]), __dmul_rn(ymx - ymn, mp.inv_corner[1])));
+    tiny = ext < mp.eps_tiny;
   }
-  const bool instant = (mx[3] - mn[3]) < mp.eps_instant;
-  double ext = 0;
-#pragma unroll
-  for (int ax = 0; ax < 4; ++ax) ext = fmax(ext, __dmul_rn(mx[ax] - mn[ax], mp.inv_corner[ax]));
-  const bool tiny = ext < mp.eps_tiny;
   keep[a] = (instant || tiny) ? 0 : 1;
 }
 
@@ -798,16 +835,16 @@ __device__ __forceinline__ bool slice_load(const double* __restrict__ verts, con
   }
   CTR_ISWAP(v[0], v[1]) CTR_ISWAP(v[2], v[3]) CTR_ISWAP(v[0], v[2]) CTR_ISWAP(v[1], v[3]) CTR_ISWAP(v[1], v[2])
 #undef CTR_ISWAP
-  if (v[0] == v[1] || v[1] == v[2] || v[2] == v[3]) return false;
 #pragma unroll
   for (int r = 0; r < 4; ++r) tv[r] = TimeOps<TT>::load(verts, tbin, v[r]);
-  return true;
+  return !(v[0] == v[1] || v[1] == v[2] || v[2] == v[3]);
 }
 
 template <typename TT>
 __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict__ verts, const int* __restrict__ tbin,
                                                        const int* __restrict__ tets,
-                                                       const uint8_t* __restrict__ keep, unsigned nt, MorphParams mp,
+                                                       const uint8_t* __restrict__ keep, uint8_t* __restrict__ keep_out,
+                                                       unsigned nt, MorphParams mp,
                                                        unsigned long long* status, SlCounters* ctr, int ntiles,
                                                        int* __restrict__ out, unsigned cap) {
   extern __shared__ int s_out[];                     // SL_STAGE * 6 ints
@@ -831,9 +868,18 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
     swapm[u] = 0;
     vv[u][0] = vv[u][1] = vv[u][2] = vv[u][3] = 0;
     const unsigned a = a0 + u;
-    if (a < nt && keep[a]) {
+    if (a < nt && (keep_out || keep[a])) {
       TT tv[4];
-      if (slice_load<TT>(verts, tbin, tets, a, vv[u], tv)) {
+      const bool distinct = slice_load<TT>(verts, tbin, tets, a, vv[u], tv);
+      bool kept = true;
+      if (keep_out) {
+        // the instant / tiny filter folded in (host guarantees: a tetrahedron spanning two bins is neither): keep
+        // unless all four vertices share a time bin
+        typedef TimeOps<TT> Op;
+        kept = Op::gap(Op::mn(Op::mn(tv[0], tv[1]), Op::mn(tv[2], tv[3])), Op::mx(Op::mx(tv[0], tv[1]), Op::mx(tv[2], tv[3])), mp);
+        keep_out[a] = kept ? 1 : 0;
+      }
+      if (distinct && kept) {
         cnt[u] = slice_code<TT>(tv, mp, s_tab, code[u]);
 #pragma unroll
         for (int e = 0; e < 6; ++e)
@@ -891,24 +937,6 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
     for (unsigned q = threadIdx.x; q < nint; q += SL_THREADS) dst[q] = s_out[q];
   }
   if (tile == ntiles - 1 && threadIdx.x == 0) ctr->total = s_excl + blk;
-}
-
-__global__ void k4_trange(const double* __restrict__ verts, unsigned nv, MinMaxKeys* mm) {
-  double mn = INFINITY, mx = -INFINITY;
-  for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < nv; a += gridDim.x * blockDim.x) {
-    const double t = verts[(size_t)a * 4 + 3];
-    mn = fmin(mn, t);
-    mx = fmax(mx, t);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  }
-  if (lane_id() == 0 && mn <= mx) {
-    atomicMin(&mm->min_key, order_key(mn));
-    atomicMax(&mm->max_key, order_key(mx));
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1055,14 +1083,32 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
     }
     unsigned long long* dkeys = (p->flags & CTR_WANT_KEYS) ? (unsigned long long*)B.keys.p : nullptr;
     uint8_t* dlow = (p->flags & CTR_WANT_KEYS) ? (uint8_t*)B.lowmin.p : nullptr;
+    // morph stage inputs (grid coordinates, fp64: its thresholds are defined there) come out of the same kernel
+    const bool morph = (p->flags & CTR_MORPH) && totV && totT;
+    const double corner_t = (double)(n3 - 1);
+    const double bin_width = corner_t * (1.0 / p->nbins);
+    if (morph) {
+      if ((rc = ctr_ensure(ctx, B.mverts, (size_t)totV * 32 + 16))) return rc;
+      if ((rc = ctr_ensure(ctx, B.tbin, (size_t)totV * 4 + 16))) return rc;
+      if ((rc = ctr_ensure(ctx, B.keep, (size_t)totT + 16))) return rc;
+      MinMaxKeys mk0;                                  // t range of the binned vertices, filled by k4_emit_verts
+      mk0.min_key = ~0ull;
+      mk0.max_key = 0ull;
+      memcpy(ctx->counters_host, &mk0, sizeof mk0);
+      CTR_CUDA(ctx, cudaMemcpyAsync(dctr, ctx->counters_host, sizeof mk0, cudaMemcpyHostToDevice, st));
+    }
     if (nOwn) {
       const int blocks = (int)((nOwn + 255) / 256);
+      double* dmv = morph ? (double*)B.mverts.p : nullptr;
+      int* dtb = morph ? (int*)B.tbin.p : nullptr;
       if (f64)
         k4_emit_verts<T, double><<<blocks, 256, 0, st>>>(g, (const unsigned long long*)B.own_id.p, (const uint32_t*)B.own_voff.p,
-                                                         (unsigned)nOwn, xf, (double*)B.verts.p, dkeys, dlow);
+                                                         (unsigned)nOwn, xf, (double*)B.verts.p, dkeys, dlow, dmv, dtb, bin_width,
+                                                         (MinMaxKeys*)dctr);
       else
         k4_emit_verts<T, float><<<blocks, 256, 0, st>>>(g, (const unsigned long long*)B.own_id.p, (const uint32_t*)B.own_voff.p,
-                                                        (unsigned)nOwn, xf, (float*)B.verts.p, dkeys, dlow);
+                                                        (unsigned)nOwn, xf, (float*)B.verts.p, dkeys, dlow, dmv, dtb, bin_width,
+                                                        (MinMaxKeys*)dctr);
       ctx->launches++;
     }
     ctr_stage_mark(ctx, 4);
@@ -1074,29 +1120,9 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
       ctx->launches++;
     }
     ctr_stage_mark(ctx, 5);
-    // ---- morph stage: always in grid coordinates and fp64 (its thresholds are defined there)
-    if ((p->flags & CTR_MORPH) && totV && totT) {
-      if ((rc = ctr_ensure(ctx, B.mverts, (size_t)totV * 32 + 16))) return rc;
-      if ((rc = ctr_ensure(ctx, B.tbin, (size_t)totV * 4 + 16))) return rc;
-      if ((rc = ctr_ensure(ctx, B.keep, (size_t)totT + 16))) return rc;
-      Xform4 unit;
-      for (int a = 0; a < 4; ++a) {
-        unit.origin[a] = 0.0;
-        unit.delta[a] = 1.0;
-      }
-      k4_emit_verts<T, double><<<(int)((nOwn + 255) / 256), 256, 0, st>>>(g, (const unsigned long long*)B.own_id.p,
-                                                                          (const uint32_t*)B.own_voff.p, (unsigned)nOwn, unit,
-                                                                          (double*)B.mverts.p, nullptr, nullptr);
-      const double corner_t = (double)(n3 - 1);
-      const double bin_width = corner_t * (1.0 / p->nbins);
-      k4_bin<<<(int)((totV + 255) / 256), 256, 0, st>>>((double*)B.mverts.p, (int*)B.tbin.p, (unsigned)totV, bin_width);
-      // t range of the binned vertices (for the zero-duration threshold, pentatopes.py:336-337)
+    // ---- morph stage
+    if (morph) {
       MinMaxKeys mk;
-      mk.min_key = ~0ull;
-      mk.max_key = 0ull;
-      memcpy(ctx->counters_host, &mk, sizeof mk);
-      CTR_CUDA(ctx, cudaMemcpyAsync(dctr, ctx->counters_host, sizeof mk, cudaMemcpyHostToDevice, st));
-      k4_trange<<<ctx->sm_count * 4, 256, 0, st>>>((const double*)B.mverts.p, (unsigned)totV, (MinMaxKeys*)dctr);
       CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, dctr, sizeof mk, cudaMemcpyDeviceToHost, st));
       CTR_CUDA(ctx, cudaStreamSynchronize(st));
       memcpy(&mk, ctx->counters_host, sizeof mk);
@@ -1111,9 +1137,17 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
       mp.eps_gap = 1e-4;
       mp.eps_in = 1e-5;
       mp.t_eps = 1e-7 * (tmax - tmin);
-      k4_tet_filter<<<(int)((totT + 255) / 256), 256, 0, st>>>((const double*)B.mverts.p, (const int*)B.tets.p, (unsigned)totT,
-                                                               mp, (uint8_t*)B.keep.p);
-      ctx->launches += 4;
+      // integer bins decide exactly like the fp64 tolerances when the bin width dwarfs them (CTR_SLICE_FP64=1: never)
+      const bool int_times = bin_width > 100.0 * std::max(mp.eps_gap, std::max(mp.eps_in, mp.t_eps)) &&
+                             fabs(tmax) < 1.0e9 * bin_width && fabs(tmin) < 1.0e9 * bin_width && !getenv("CTR_SLICE_FP64");
+      // ... and then the filter is a by-product of the slicing: vertices in different bins are >= one bin apart, which
+      // is neither "instant" (1e-7) nor, with a bin wider than eps_tiny of the t axis, "tiny"; equal bins are instant
+      const bool fused_filter = int_times && bin_width * mp.inv_corner[3] > 2.0 * mp.eps_tiny;
+      if (!fused_filter) {
+        k4_tet_filter<<<(int)((totT + 255) / 256), 256, 0, st>>>((const double*)B.mverts.p, (const int*)B.tets.p, (unsigned)totT,
+                                                                 mp, (uint8_t*)B.keep.p);
+        ctx->launches++;
+      }
       const int sl_tiles = (int)((totT + SL_TILE - 1) / SL_TILE);
       if ((rc = ctr_ensure(ctx, B.slstate, (size_t)sl_tiles * 8 + 64))) return rc;
       size_t want = std::max<size_t>((size_t)totT * 2, 1 << 14);
@@ -1127,19 +1161,17 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
           CTR_CUDA(ctx, cudaFuncSetAttribute(k4_slice<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_STAGE * 6 * sizeof(int))));
           sl_attr = true;
         }
-        // integer bins decide exactly like the fp64 tolerances when the bin width dwarfs them (CTR_SLICE_FP64=1: never)
-        const bool int_times = bin_width > 100.0 * std::max(mp.eps_gap, std::max(mp.eps_in, mp.t_eps)) &&
-                               fabs(tmax) < 1.0e9 * bin_width && fabs(tmin) < 1.0e9 * bin_width && !getenv("CTR_SLICE_FP64");
         SlCounters* slc = (SlCounters*)((char*)B.slstate.p + (size_t)sl_tiles * 8);
         CTR_CUDA(ctx, cudaMemsetAsync(B.slstate.p, 0, (size_t)sl_tiles * 8 + 32, st));
         if (int_times)
           k4_slice<int><<<sl_tiles, SL_THREADS, SL_STAGE * 6 * sizeof(int), st>>>(
-              (const double*)B.mverts.p, (const int*)B.tbin.p, (const int*)B.tets.p, (const uint8_t*)B.keep.p, (unsigned)totT, mp,
+              (const double*)B.mverts.p, (const int*)B.tbin.p, (const int*)B.tets.p,
+              fused_filter ? nullptr : (const uint8_t*)B.keep.p, fused_filter ? (uint8_t*)B.keep.p : nullptr, (unsigned)totT, mp,
               (unsigned long long*)B.slstate.p, slc, sl_tiles, (int*)B.mtris.p, cap);
         else
           k4_slice<double><<<sl_tiles, SL_THREADS, SL_STAGE * 6 * sizeof(int), st>>>(
-              (const double*)B.mverts.p, (const int*)B.tbin.p, (const int*)B.tets.p, (const uint8_t*)B.keep.p, (unsigned)totT, mp,
-              (unsigned long long*)B.slstate.p, slc, sl_tiles, (int*)B.mtris.p, cap);
+              (const double*)B.mverts.p, (const int*)B.tbin.p, (const int*)B.tets.p, (const uint8_t*)B.keep.p, nullptr,
+              (unsigned)totT, mp, (unsigned long long*)B.slstate.p, slc, sl_tiles, (int*)B.mtris.p, cap);
         ctx->launches++;
         CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, slc, sizeof(SlCounters), cudaMemcpyDeviceToHost, st));
         CTR_CUDA(ctx, cudaStreamSynchronize(st));
