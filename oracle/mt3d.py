@@ -9,8 +9,9 @@ may import this module.  The product (contourist_b200/) never does.
 
 Parity status: PINNED.  Checked against golden vectors produced by running the
 unmodified reference in the build container (tests/golden/make_golden.py ->
-tests/golden/*.npz; tests/test_oracle_golden.py) and against the reference's own
-known-answer test (contourist/test/test_tetrahedral.py:29-37).  Normals are NOT
+tests/golden/*.npz; tests/test_oracle_golden_3d.py, tests/test_oracle_seeded_3d.py: raw
+extraction, the full C1 run, oriented final meshes, seeded tracker runs) and against the
+reference's own known-answer test (contourist/test/test_tetrahedral.py:29-37).  Normals are NOT
 computed by the reference (html_demo.py:142 "normals": []), so `normals()` below
 is parity-UNPINNED: it is the definition, not a restatement.
 
@@ -19,10 +20,11 @@ Reference lines restated here (all under /root/reference/contourist/):
   tetrahedral.py:383-394  border_voxel (active-voxel predicate)  -> active_cells
   tetrahedral.py:561-595  enumerate_tetrahedron_triangles        -> tet_cases / extract
   tetrahedral.py:471-487,506-511 contour_pair_interpolation      -> interpolate
-  tetrahedral.py:190-215  quantize_interpolations                -> postprocess
-  tetrahedral.py:353-375  remove_tiny_simplices                  -> postprocess
-  surface_geometry.py:14-50   clean_triangles                    -> postprocess
+  (tetrahedral.py:190-215,353-375 quantize / tiny and surface_geometry.py:14-50 clean depend on CPython dict / set
+   order and are not restated: SURVEY.md 8 "P-final, second tier")
   surface_geometry.py:52-140  orient_triangles                   -> orient
+  tetrahedral.py:396-441  find_initial_voxels                    -> initial_voxels
+  tetrahedral.py:443-469  expand_voxels / in_range               -> flood_fill, extract_seeded
   grid_field.py:64-84     find_contour_crossing_grid_segments    -> crossing_segments
   grid_field.py:89-93     from_grid_coordinates                  -> to_world
 
@@ -329,85 +331,6 @@ def to_world(pos, mins, delta):
 # Stage 4b: the reference's serial post-processing, restated with the engine's deterministic
 # tie-breaks (SURVEY.md section 7 hard part 1: the reference's own choices depend on CPython set/dict order).
 # ----------------------------------------------------------------------------------------------
-
-def postprocess(keys, pos, tris, corner, divisions=10000, epsilon=1e-4, clean=True):
-    """tetrahedral.py:190-215 (quantize), :353-375 (tiny), surface_geometry.py:14-50 (clean).
-
-    Deterministic rules where the reference depends on dict/set order:
-      * quantize: the representative of a bucket is the key with the LARGEST key value
-        (reference: last in dict order, tetrahedral.py:198).
-      * tiny-triangle collapse: triangles are visited in ascending (sorted index triple) order and the
-        merge point is the position of the triangle's smallest vertex index (reference: points[0] in
-        frozenset order, tetrahedral.py:368).
-      * clean: triangles visited in ascending order; vertex renumbering = first use in that order.
-    Returns (vertices[V',3] float64 grid coords, triangles int64 [T',3] unoriented (sorted rows),
-             vertex_map int64 [V] (-1 = dropped))
-    """
-    pos = np.array(pos, dtype=np.float64)
-    corner = np.asarray(corner, dtype=np.int64)
-    V = len(keys)
-    # ---- quantize (topology only; positions unchanged: reference writes a dead attribute) ----
-    expander = ((divisions * 1.0) / corner).astype(np.int64)
-    q = (pos * expander).astype(np.int64)
-    # bucket id
-    _, inv = np.unique(q, axis=0, return_inverse=True)
-    inv = inv.reshape(-1)
-    rep = np.zeros(inv.max() + 1 if V else 0, dtype=np.int64)
-    np.maximum.at(rep, inv, np.arange(V, dtype=np.int64))      # keys sorted -> largest index = largest key
-    vmap = rep[inv] if V else np.zeros(0, np.int64)
-    t = vmap[tris]
-    keep = (t[:, 0] != t[:, 1]) & (t[:, 0] != t[:, 2]) & (t[:, 1] != t[:, 2])
-    t = np.sort(t[keep], axis=1)
-    t = np.unique(t, axis=0) if len(t) else t.reshape(0, 3)
-    # ---- remove tiny simplices ----
-    inv_corner = 1.0 / corner
-    keep_rows = []
-    for r in range(len(t)):
-        pts = pos[t[r]]
-        dl = (pts.max(axis=0) - pts.min(axis=0)) * inv_corner
-        if dl.max() < epsilon:
-            pos[t[r]] = pts[0].copy()
-        else:
-            keep_rows.append(r)
-    t = t[keep_rows] if len(t) else t
-    used = np.unique(t)
-    remap = -np.ones(V, dtype=np.int64)
-    remap[used] = np.arange(len(used))
-    verts = pos[used]
-    t = remap[t]
-    if not clean:
-        vm = -np.ones(V, dtype=np.int64)
-        vm[used] = np.arange(len(used))
-        return verts, t, vm
-    # ---- clean_triangles ----
-    vertex_map = {}
-    keep_vertices = []
-    keep_tris = set()
-
-    def new_index(i):
-        if i in vertex_map:
-            return vertex_map[i]
-        vertex_map[i] = len(keep_vertices)
-        keep_vertices.append(verts[i])
-        return vertex_map[i]
-
-    for r in range(len(t)):
-        a, b, c = (int(x) for x in t[r])
-        Ap, Bp, Cp = verts[a], verts[b], verts[c]
-        cr = np.cross(Ap - Cp, Bp - Cp)
-        if np.all(np.abs(cr) <= ATOL):
-            for (i, j) in ((a, b), (a, c), (b, c)):
-                if np.all(np.abs(verts[i] - verts[j]) <= ATOL + RTOL * np.abs(verts[j])):
-                    vertex_map[j] = new_index(i)
-        else:
-            keep_tris.add(frozenset(new_index(i) for i in (a, b, c)))
-    out_t = np.array(sorted(tuple(sorted(x)) for x in keep_tris if len(x) == 3), dtype=np.int64).reshape(-1, 3)
-    vm = -np.ones(V, dtype=np.int64)
-    for i_local, i_global in enumerate(used):
-        if i_local in vertex_map:
-            vm[i_global] = vertex_map[i_local]
-    return np.array(keep_vertices, dtype=np.float64).reshape(-1, 3), out_t, vm
-
 
 def orient(verts, tris):
     """surface_geometry.py:52-140 with compatible_triangle_test = always True.

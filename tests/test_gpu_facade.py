@@ -121,7 +121,7 @@ def test_device_orientation_equals_surface_geometry(engine, geom64):
 
 def test_device_orientation_equals_oracle_dfs(engine):
     """... and against the oracle's restatement of the reference DFS itself (oracle/mt3d.py orient, pinned to the
-    reference's final sphere mesh in tests/test_oracle_mt3d.py) on closed blobs of both signs.  Triangles compared up to
+    reference's final meshes in tests/test_oracle_golden_3d.py::test_orient_matches_reference_final_mesh) on closed blobs of both signs.  Triangles compared up to
     rotation (the DFS starts every triangle at the shared edge)."""
     from contourist_b200 import engine as E
     n = 30

@@ -126,3 +126,24 @@ def test_reference_known_answer_two_dots():
                 frozenset([(-8, -7, -8), (-8, -7, -7), (-7, -7, -7)])]
     for e in expected:
         assert e in got
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
+def test_orient_matches_reference_final_mesh(path):
+    """oracle.orient (surface_geometry.py:52-140) on the reference's own final mesh must give back the reference's
+    oriented triangles (its last step is exactly this call).  Compared up to rotation of each triple.  ints7 (a
+    non-manifold integer field full of ties) is only required to agree as unoriented triangles: there the
+    reference's DFS depends on CPython set order."""
+    g = np.load(path)
+    fp, ft = g["final_points"], g["final_tris"]
+
+    def rot(t):
+        t = tuple(int(i) for i in t)
+        k = t.index(min(t))
+        return t[k:] + t[:k]
+    got = sorted(rot(t) for t in mt3d.orient(fp, ft))
+    want = sorted(rot(t) for t in ft)
+    if "ints7" in path:
+        assert sorted(tuple(sorted(t)) for t in got) == sorted(tuple(sorted(t)) for t in want)
+    else:
+        assert got == want
