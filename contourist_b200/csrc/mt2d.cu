@@ -39,9 +39,9 @@ struct Levels2D {
 };
 
 struct Counters2D {
-  unsigned long long total;     // packed: segments << 31 | active squares
+  unsigned long long total;     // packed: segments << 31 | active squares (written by k2d_tile_scan)
   unsigned long long min_key, max_key;
-  unsigned int ticket, pad;
+  unsigned int slots, pad;      // list slots handed out to the tiles (= active squares)
 };
 
 __device__ __forceinline__ unsigned long long order_key2(double x) {
@@ -101,10 +101,9 @@ __global__ void __launch_bounds__(T2_THREADS) k2d_count(const T* __restrict__ f,
                                                         Levels2D<T> lv, int tiles_j, int ntiles, int vec_ok,
                                                         uint32_t* __restrict__ sq_lin, uint32_t* __restrict__ sq_base,
                                                         uint32_t* __restrict__ sq_cls, unsigned cap,
-                                                        unsigned long long* status, Counters2D* ctr) {
+                                                        unsigned long long* __restrict__ tile_cnt, Counters2D* ctr) {
   __shared__ Shared2D sh;
   __shared__ T s_upp[MAXL + 2], s_eqp[MAXL + 1], s_lim[MAXL + 1];   // s_lim[k]: samples of class k below it carry no equality flag
-  if (threadIdx.x == 0) sh.tile = atomicAdd(&ctr->ticket, 1u);
   const int nl = lv.n;
   if ((int)threadIdx.x <= nl + 1) s_upp[threadIdx.x] = threadIdx.x == 0 ? (T)-INFINITY : ((int)threadIdx.x <= nl ? lv.up[threadIdx.x - 1] : (T)NAN);
   if ((int)threadIdx.x <= nl) {
@@ -113,7 +112,7 @@ __global__ void __launch_bounds__(T2_THREADS) k2d_count(const T* __restrict__ f,
     s_lim[threadIdx.x] = (int)threadIdx.x < nl ? (e == e ? e : lv.up[threadIdx.x]) : (T)INFINITY;
   }
   __syncthreads();
-  const int tile = (int)sh.tile;
+  const int tile = (int)blockIdx.x;
   const int ti = tile / tiles_j, tj = tile - ti * tiles_j;
   const int i0 = i_lo + ti * T2_ROWS, j0 = tj * T2_COLS;
   const int t = threadIdx.x;
@@ -241,13 +240,18 @@ __global__ void __launch_bounds__(T2_THREADS) k2d_count(const T* __restrict__ f,
     if (q < (int)warp) woff += sh.warp_sum[q];
     blk += sh.warp_sum[q];
   }
-  {
-    const unsigned long long e = lb_lookback_block<T2_THREADS>(status, tile, blk);
-    if (t == 0) sh.excl = e;
+  // The tile's list entries go to slots from one atomic counter (tiles in any order, squares of a tile in order) and
+  // carry segment offsets RELATIVE to the tile; k2d_tile_scan turns the per-tile segment counts into tile offsets, so
+  // the segment arrays come out in tile order without any tile waiting for its predecessors (a look-back scan here
+  // cost a fifth of the kernel: blocks finish out of order and sat polling).
+  if (t == 0) {
+    sh.excl = (blk & 0x7fffffffull) ? atomicAdd(&ctr->slots, (unsigned)(blk & 0x7fffffffull)) : 0u;
+    tile_cnt[tile] = blk;
   }
   __syncthreads();
-  unsigned long long run = sh.excl + woff + inc - loc;
-  // ---- compact, ordered list of active squares with their segment offsets
+  unsigned long long run = woff + inc - loc;
+  const unsigned slot0 = (unsigned)sh.excl;
+  // ---- compact list of active squares with their tile-relative segment offsets
 #pragma unroll 1
   for (int u = 0; u < 4; ++u) {
     const int q = 4 * t + u;
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(T2_THREADS) k2d_count(const T* __restrict__ f,
       const unsigned A = cls_at(sh, r, c), Bc = cls_at(sh, r, c + 1), C = cls_at(sh, r + 1, c), Dc = cls_at(sh, r + 1, c + 1);
       const unsigned n = (unsigned)(tri_count(A, C, Dc) + tri_count(A, Bc, Dc));
       if (!n) continue;
-      const unsigned slot = (unsigned)(run & 0x7fffffffull);
+      const unsigned slot = slot0 + (unsigned)(run & 0x7fffffffull);
       if (slot < cap) {
         sq_lin[slot] = (uint32_t)((size_t)(i0 + r) * n1 + (j0 + c));
         sq_base[slot] = (uint32_t)(run >> 31);
@@ -268,7 +272,31 @@ __global__ void __launch_bounds__(T2_THREADS) k2d_count(const T* __restrict__ f,
       run += ((unsigned long long)n << 31) | 1u;
     }
   }
-  if (tile == ntiles - 1 && t == 0) ctr->total = sh.excl + blk;
+}
+
+// exclusive scan of the per-tile segment counts (one block; a few thousand tiles) -> tile_off, grand totals
+__global__ void __launch_bounds__(1024) k2d_tile_scan(const unsigned long long* __restrict__ tile_cnt, int ntiles,
+                                                      uint32_t* __restrict__ tile_off, Counters2D* ctr) {
+  __shared__ unsigned long long s_warp[32];
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  unsigned long long carry = 0;
+  for (int base = 0; base < ntiles; base += 1024) {
+    const int q = base + (int)threadIdx.x;
+    const unsigned long long c = q < ntiles ? tile_cnt[q] : 0ull;
+    const unsigned long long inc = warp_incl_scan_u64(c);
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned long long woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) {
+      if (w < (int)warp) woff += s_warp[w];
+      tot += s_warp[w];
+    }
+    if (q < ntiles) tile_off[q] = (uint32_t)((carry + woff + inc - c) >> 31);
+    carry += tot;
+  }
+  if (threadIdx.x == 0) ctr->total = carry;
 }
 
 __device__ __forceinline__ double mul_rn2(double a, double b) { return __dmul_rn(a, b); }
@@ -301,7 +329,8 @@ __device__ __forceinline__ void put_end(int li, int lj, int hi_, int hj, double 
 template <typename T, typename G>
 __global__ void __launch_bounds__(128) k2d_emit(const T* __restrict__ f, int n1, long long row_offset, Levels2D<T> lv,
                                                 const uint32_t* __restrict__ sq_lin, const uint32_t* __restrict__ sq_base,
-                                                const uint32_t* __restrict__ sq_cls, unsigned n_sq, Xform2 xf,
+                                                const uint32_t* __restrict__ sq_cls, unsigned n_sq,
+                                                const uint32_t* __restrict__ tile_off, int i_lo, int tiles_j, Xform2 xf,
                                                 uint8_t* __restrict__ seg_level, unsigned long long* __restrict__ seg_keys,
                                                 G* __restrict__ seg_pos) {
   const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -309,7 +338,7 @@ __global__ void __launch_bounds__(128) k2d_emit(const T* __restrict__ f, int n1,
   const unsigned lin = sq_lin[a];
   const int i = (int)(lin / (unsigned)n1), j = (int)(lin - (unsigned)i * (unsigned)n1);
   const uint32_t cls = sq_cls[a];
-  size_t o = sq_base[a];
+  size_t o = (size_t)tile_off[((i - i_lo) / T2_ROWS) * tiles_j + j / T2_COLS] + sq_base[a];
   const double fA = (double)f[(size_t)i * n1 + j], fB = (double)f[(size_t)i * n1 + j + 1];
   const double fC = (double)f[(size_t)(i + 1) * n1 + j], fD = (double)f[(size_t)(i + 1) * n1 + j + 1];
   int lmin = 127, lmax = 0;
@@ -444,8 +473,10 @@ int run2d(ctr_ctx* ctx, const ctr_mt2d_params* p, ctr_mt2d_counts* out) {
   const int vec_ok = ((n1 & 3) == 0 && (((uintptr_t)df) & 15) == 0) ? 1 : 0;      // rows start 16-byte aligned
   if ((rc = ctr_ensure(ctx, ctx->counters, 256))) return rc;
   if (!ctx->counters_host) CTR_CUDA(ctx, cudaMallocHost(&ctx->counters_host, 256));
-  if ((rc = ctr_ensure(ctx, ctx->tile_state, (size_t)ntiles * 8 + 16))) return rc;
+  if ((rc = ctr_ensure(ctx, ctx->tile_state, (size_t)ntiles * 12 + 32))) return rc;      // per-tile counts (u64), then offsets (u32)
   Counters2D* dctr = (Counters2D*)ctx->counters.p;
+  unsigned long long* tile_cnt = (unsigned long long*)ctx->tile_state.p;
+  uint32_t* tile_off = (uint32_t*)(tile_cnt + ntiles + 1);
   DevBuf& b_lin = ctx->aux[5];
   DevBuf& b_base = ctx->aux[6];
   DevBuf& b_cls = ctx->aux[7];
@@ -462,12 +493,11 @@ int run2d(ctr_ctx* ctx, const ctr_mt2d_params* p, ctr_mt2d_counts* out) {
     init.min_key = ~0ull;
     memcpy(ctx->counters_host, &init, sizeof init);
     CTR_CUDA(ctx, cudaMemcpyAsync(dctr, ctx->counters_host, sizeof init, cudaMemcpyHostToDevice, st));
-    CTR_CUDA(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, (size_t)ntiles * 8 + 8, st));
     if (ntiles > 0) {
       k2d_count<T><<<ntiles, T2_THREADS, 0, st>>>(df, n0, n1, i_lo, i_hi, lv, tiles_j, ntiles, vec_ok, (uint32_t*)b_lin.p,
-                                               (uint32_t*)b_base.p, (uint32_t*)b_cls.p, cap,
-                                               (unsigned long long*)ctx->tile_state.p, dctr);
-      ctx->launches++;
+                                               (uint32_t*)b_base.p, (uint32_t*)b_cls.p, cap, tile_cnt, dctr);
+      k2d_tile_scan<<<1, 1024, 0, st>>>(tile_cnt, ntiles, tile_off, dctr);
+      ctx->launches += 2;
     }
     if (p->flags & CTR_WANT_MINMAX) {
       k_minmax<T><<<ctx->sm_count * 8, 256, 0, st>>>(df, nsamp, dctr);
@@ -506,12 +536,12 @@ int run2d(ctr_ctx* ctx, const ctr_mt2d_params* p, ctr_mt2d_counts* out) {
       const int blocks = (int)((nsq + 127) / 128);
       if (f64)
         k2d_emit<T, double><<<blocks, 128, 0, st>>>(df, n1, p->row_offset, lv, (const uint32_t*)b_lin.p,
-                                                    (const uint32_t*)b_base.p, (const uint32_t*)b_cls.p, (unsigned)nsq, xf,
-                                                    (uint8_t*)b_lvl.p, (unsigned long long*)b_keys.p, (double*)b_pos.p);
+                                                    (const uint32_t*)b_base.p, (const uint32_t*)b_cls.p, (unsigned)nsq, tile_off, i_lo,
+                                                    tiles_j, xf, (uint8_t*)b_lvl.p, (unsigned long long*)b_keys.p, (double*)b_pos.p);
       else
         k2d_emit<T, float><<<blocks, 128, 0, st>>>(df, n1, p->row_offset, lv, (const uint32_t*)b_lin.p,
-                                                   (const uint32_t*)b_base.p, (const uint32_t*)b_cls.p, (unsigned)nsq, xf,
-                                                   (uint8_t*)b_lvl.p, (unsigned long long*)b_keys.p, (float*)b_pos.p);
+                                                   (const uint32_t*)b_base.p, (const uint32_t*)b_cls.p, (unsigned)nsq, tile_off, i_lo,
+                                                   tiles_j, xf, (uint8_t*)b_lvl.p, (unsigned long long*)b_keys.p, (float*)b_pos.p);
       ctx->launches++;
     }
   }
