@@ -27,7 +27,7 @@ struct Counters4 {
   unsigned long long min_key, max_key;
   unsigned int pad0, pad1;
   unsigned long long n_cells, n_cross, total_vt, total_act, v_emit;
-  unsigned int ticket, pad2;
+  unsigned int n_own, n_cell;        // list slots handed out to the tiles (= lengths of the owner / hypervoxel lists)
 };
 constexpr size_t C4_STAGE2_OFFSET = 24;
 
@@ -258,17 +258,14 @@ __global__ void __launch_bounds__(C4_THREADS, 2) k4_count_scan(Grid4<T> gin, uns
                                                                uint32_t* __restrict__ own_voff,
                                                                unsigned long long* __restrict__ cell_id,
                                                                uint32_t* __restrict__ cell_toff, unsigned cap_own,
-                                                               unsigned cap_cell, unsigned long long* status_vt,
-                                                               unsigned long long* status_act, Counters4* ctr, int ntiles) {
+                                                               unsigned cap_cell, unsigned long long* __restrict__ tile_vt,
+                                                               Counters4* ctr, int ntiles) {
   __shared__ C4Shared sh;
   Grid4<T> g = gin;
   g.any_near = 0;
-  if (threadIdx.x == 0) {
-    sh.tile = atomicAdd(&ctr->ticket, 1u);
-    sh.nint = 0;
-  }
+  if (threadIdx.x == 0) sh.nint = 0;
   __syncthreads();
-  const int tile = (int)sh.tile;
+  const int tile = (int)blockIdx.x;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const unsigned tile0 = (unsigned)tile * C4_TILE;
   // ---- A: quick test
@@ -395,12 +392,16 @@ __global__ void __launch_bounds__(C4_THREADS, 2) k4_count_scan(Grid4<T> gin, uns
     blk_vt += sh.warp_vt[q];
     blk_act += sh.warp_act[q];
   }
-  if (warp == 0) {
-    unsigned long long e = lb_lookback(status_vt, tile, blk_vt);
-    if (lane == 0) sh.excl_vt = e;
-  } else if (warp == 1) {
-    unsigned long long e = lb_lookback(status_act, tile, blk_act);
-    if (lane == 0) sh.excl_act = e;
+  // No tile waits for another: vertex ids / tetrahedron offsets are written RELATIVE to the tile (k4_tile_scan turns
+  // the per-tile totals into tile offsets, k4_fix_vbase and the emit kernels add them), and the work-list slots come
+  // from two atomic counters (the lists are unordered across tiles; the mesh does not depend on their order).  A
+  // look-back scan here cost a quarter of the kernel's stall samples: blocks finish out of order and sat polling.
+  if (threadIdx.x == 0) {
+    tile_vt[tile] = blk_vt;
+    const unsigned no = (unsigned)(blk_act & 0x7fffffffull), nc = (unsigned)(blk_act >> 31);
+    const unsigned long long bo = no ? atomicAdd(&ctr->n_own, no) : 0u, bc = nc ? atomicAdd(&ctr->n_cell, nc) : 0u;
+    sh.excl_vt = 0ull;
+    sh.excl_act = bo | (bc << 31);
   }
   __syncthreads();
   unsigned long long run_vt = sh.excl_vt + woff_vt + inc_vt - loc_vt;
@@ -415,10 +416,6 @@ __global__ void __launch_bounds__(C4_THREADS, 2) k4_count_scan(Grid4<T> gin, uns
     if (tile0 + wl < nwords) vbase[tile0 + wl] = sh.pv[wl];
     run_vt += item_vt[it];
     run_act += item_act[it];
-  }
-  if (tile == ntiles - 1 && threadIdx.x == 0) {
-    ctr->total_vt = sh.excl_vt + blk_vt;
-    ctr->total_act = sh.excl_act + blk_act;
   }
   __syncthreads();
   // ---- D: lists
@@ -490,6 +487,40 @@ __global__ void __launch_bounds__(C4_THREADS, 2) k4_count_scan(Grid4<T> gin, uns
 // ------------------------------------------------------------------------------------------------
 // vertices: one thread per (owner, owned edge) pair, dealt out per warp as in mt3d.cu
 // ------------------------------------------------------------------------------------------------
+// exclusive scan of the per-tile (vertices | tetrahedra << 31) totals: one block, a few thousand tiles
+__global__ void __launch_bounds__(1024) k4_tile_scan(const unsigned long long* __restrict__ tile_vt, int ntiles,
+                                                     unsigned long long* __restrict__ tile_off, Counters4* ctr) {
+  __shared__ unsigned long long s_warp[32];
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  unsigned long long carry = 0;
+  for (int base = 0; base < ntiles; base += 1024) {
+    const int q = base + (int)threadIdx.x;
+    const unsigned long long c = q < ntiles ? tile_vt[q] : 0ull;
+    const unsigned long long inc = warp_incl_scan_u64(c);
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned long long woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) {
+      if (w < (int)warp) woff += s_warp[w];
+      tot += s_warp[w];
+    }
+    if (q < ntiles) tile_off[q] = carry + woff + inc - c;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) {
+    ctr->total_vt = carry;
+    ctr->total_act = (unsigned long long)ctr->n_own | ((unsigned long long)ctr->n_cell << 31);
+  }
+}
+
+// vbase[word]: tile-relative -> absolute first vertex id of the word
+__global__ void k4_fix_vbase(uint32_t* __restrict__ vbase, unsigned nwords, const unsigned long long* __restrict__ tile_off) {
+  const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < nwords) vbase[w] += (uint32_t)(tile_off[w / C4_TILE] & 0x7fffffffull);
+}
+
 struct Xform4 {
   double origin[4], delta[4];
 };
@@ -507,12 +538,13 @@ __global__ void __launch_bounds__(256) k4_emit_verts(Grid4<T> g, const unsigned 
                                                      const uint32_t* __restrict__ own_voff, unsigned n_own, Xform4 xf,
                                                      G* __restrict__ verts, unsigned long long* __restrict__ keys,
                                                      uint8_t* __restrict__ lowmin, double* __restrict__ mverts,
-                                                     int* __restrict__ tbin, double bin_width, MinMaxKeys* mm) {
+                                                     int* __restrict__ tbin, double bin_width, MinMaxKeys* mm,
+                                                     const unsigned long long* __restrict__ tile_off) {
   const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
   double tmn = INFINITY, tmx = -INFINITY;
   if (a < n_own) {
     const unsigned long long oid = own_id[a];
-    unsigned id = own_voff[a];
+    unsigned id = own_voff[a] + (unsigned)(tile_off[(unsigned)(oid >> 21) / C4_TILE] & 0x7fffffffull);   // tile-relative -> absolute
     const unsigned m15 = (unsigned)oid & 0x7fffu;
     const bool p_low = (oid >> 15) & 1u;
     int i, j, k, w;
@@ -590,7 +622,8 @@ template <typename T>
 __global__ void __launch_bounds__(E4_THREADS) k4_emit_tets(Grid4<T> gin, const unsigned long long* __restrict__ cell_id,
                                                            const uint32_t* __restrict__ cell_toff, unsigned n_cells,
                                                            const uint32_t* __restrict__ vbase, int* __restrict__ tets,
-                                                           uint8_t* __restrict__ codes) {
+                                                           uint8_t* __restrict__ codes,
+                                                           const unsigned long long* __restrict__ tile_off) {
   __shared__ unsigned s_ids[CTR_NEDGE4][E4_THREADS];
   Grid4<T> g = gin;
   const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -643,7 +676,7 @@ __global__ void __launch_bounds__(E4_THREADS) k4_emit_tets(Grid4<T> gin, const u
   unsigned emit = 0xffffffu;
   if (cand) emit = cell_emit_exact4(g, i, j, k, w * 32 + b, nullptr);
   if (codes) cell_emit_exact4(g, i, j, k, w * 32 + b, codes + (size_t)a * 24);
-  size_t o = cell_toff[a];
+  size_t o = (size_t)cell_toff[a] + (size_t)(tile_off[(unsigned)(cid >> 22) / C4_TILE] >> 31);   // tile-relative -> absolute
 #pragma unroll 1
   for (int p = 0; p < 24; ++p) {
     const unsigned m = pent_mask_of(c16, p);
@@ -1022,8 +1055,8 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
   g.divN1.init((unsigned)n1);
   const int ntiles = (int)((nwords + C4_TILE - 1) / C4_TILE);
   if ((rc = ctr_ensure(ctx, ctx->tile_state, (size_t)ntiles * 16 + 16))) return rc;
-  unsigned long long* st_vt = (unsigned long long*)ctx->tile_state.p;
-  unsigned long long* st_act = st_vt + ntiles;
+  unsigned long long* st_vt = (unsigned long long*)ctx->tile_state.p;       // per-tile totals
+  unsigned long long* tile_off = st_vt + ntiles;                              // their exclusive prefix
   size_t want_own = std::max<size_t>((size_t)nwords / 2, 1 << 14), want_cell = want_own;
   Counters4 h;
   unsigned long long totV = 0, totT = 0, nOwn = 0, nCell = 0;
@@ -1035,12 +1068,13 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
     const unsigned cap_own = (unsigned)std::min<size_t>(std::min(B.own_id.cap / 8, B.own_voff.cap / 4), 0x7fffffffu);
     const unsigned cap_cell = (unsigned)std::min<size_t>(std::min(B.cell_id.cap / 8, B.cell_toff.cap / 4), 0x7fffffffu);
     CTR_CUDA(ctx, cudaMemsetAsync((char*)dctr + C4_STAGE2_OFFSET, 0, sizeof(Counters4) - C4_STAGE2_OFFSET, st));
-    CTR_CUDA(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, (size_t)ntiles * 16, st));
     k4_count_scan<T><<<ntiles, C4_THREADS, 0, st>>>(g, (unsigned)nwords, (uint32_t*)ctx->vbase.p,
                                                     (unsigned long long*)B.own_id.p, (uint32_t*)B.own_voff.p,
                                                     (unsigned long long*)B.cell_id.p, (uint32_t*)B.cell_toff.p, cap_own,
-                                                    cap_cell, st_vt, st_act, dctr, ntiles);
-    ctx->launches++;
+                                                    cap_cell, st_vt, dctr, ntiles);
+    k4_tile_scan<<<1, 1024, 0, st>>>(st_vt, ntiles, tile_off, dctr);
+    k4_fix_vbase<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>((uint32_t*)ctx->vbase.p, (unsigned)nwords, tile_off);
+    ctx->launches += 3;
     CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, dctr, sizeof(Counters4), cudaMemcpyDeviceToHost, st));
     CTR_CUDA(ctx, cudaStreamSynchronize(st));
     memcpy(&h, ctx->counters_host, sizeof h);
@@ -1104,11 +1138,11 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
       if (f64)
         k4_emit_verts<T, double><<<blocks, 256, 0, st>>>(g, (const unsigned long long*)B.own_id.p, (const uint32_t*)B.own_voff.p,
                                                          (unsigned)nOwn, xf, (double*)B.verts.p, dkeys, dlow, dmv, dtb, bin_width,
-                                                         (MinMaxKeys*)dctr);
+                                                         (MinMaxKeys*)dctr, tile_off);
       else
         k4_emit_verts<T, float><<<blocks, 256, 0, st>>>(g, (const unsigned long long*)B.own_id.p, (const uint32_t*)B.own_voff.p,
                                                         (unsigned)nOwn, xf, (float*)B.verts.p, dkeys, dlow, dmv, dtb, bin_width,
-                                                        (MinMaxKeys*)dctr);
+                                                        (MinMaxKeys*)dctr, tile_off);
       ctx->launches++;
     }
     ctr_stage_mark(ctx, 4);
@@ -1116,7 +1150,7 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
       const int blocks = (int)((nCell + E4_THREADS - 1) / E4_THREADS);
       k4_emit_tets<T><<<blocks, E4_THREADS, 0, st>>>(g, (const unsigned long long*)B.cell_id.p, (const uint32_t*)B.cell_toff.p,
                                                      (unsigned)nCell, (const uint32_t*)ctx->vbase.p, (int*)B.tets.p,
-                                                     (p->flags & CTR_WANT_CODES) ? (uint8_t*)B.codes.p : nullptr);
+                                                     (p->flags & CTR_WANT_CODES) ? (uint8_t*)B.codes.p : nullptr, tile_off);
       ctx->launches++;
     }
     ctr_stage_mark(ctx, 5);
