@@ -153,14 +153,15 @@ __device__ __forceinline__ void lb_store(unsigned long long* p, unsigned long lo
 
 // Called by one full warp.  Returns the exclusive prefix of `tile` (sum of aggregates of tiles < tile)
 // and publishes the inclusive prefix.  status has one word per tile, zero-initialised.
-__device__ __forceinline__ unsigned long long lb_lookback(unsigned long long* status, int tile,
-                                                          unsigned long long aggregate) {
+// The two halves can be called apart: publish the aggregate as soon as it is known, do whatever does not need the
+// prefix, then resolve it -- by then the predecessors have usually published theirs and nobody polls.
+__device__ __forceinline__ void lb_publish(unsigned long long* status, int tile, unsigned long long aggregate) {
+  if (lane_id() == 0) lb_store(&status[tile], (tile == 0 ? CTR_LB_INC : CTR_LB_AGG) | aggregate);
+}
+
+__device__ __forceinline__ unsigned long long lb_resolve(unsigned long long* status, int tile, unsigned long long aggregate) {
   const unsigned lane = lane_id();
-  if (tile == 0) {
-    if (lane == 0) lb_store(&status[0], CTR_LB_INC | aggregate);
-    return 0ull;
-  }
-  if (lane == 0) lb_store(&status[tile], CTR_LB_AGG | aggregate);
+  if (tile == 0) return 0ull;
   unsigned long long excl = 0;
   int idx = tile - 1;
   while (true) {
@@ -187,6 +188,12 @@ __device__ __forceinline__ unsigned long long lb_lookback(unsigned long long* st
   }
   if (lane == 0) lb_store(&status[tile], CTR_LB_INC | (excl + aggregate));
   return excl;
+}
+
+__device__ __forceinline__ unsigned long long lb_lookback(unsigned long long* status, int tile,
+                                                          unsigned long long aggregate) {
+  lb_publish(status, tile, aggregate);
+  return lb_resolve(status, tile, aggregate);
 }
 
 // Block-wide look-back over two status arrays at once.  Every thread of the block polls one predecessor, so a window

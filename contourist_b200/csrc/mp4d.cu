@@ -930,15 +930,20 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
     if (q < (int)warp) woff += s_warp[q];
     blk += s_warp[q];
   }
-  if (warp == 0) {
-    unsigned long long e = lb_lookback(status, tile, blk);
-    if (lane == 0) s_excl = e;
-  }
-  __syncthreads();
-  const unsigned long long base = s_excl;
   // the tile's triangles are contiguous in the output (tetrahedron order): staged in shared memory and written out
-  // coalesced when they fit, else written directly
+  // coalesced when they fit, else written directly.  The staging does not need the tile's global offset, so the
+  // aggregate is published first and the look-back is resolved after the staging: by then the predecessors have
+  // published theirs and the warp does not sit polling.
   const bool staged = blk <= (unsigned long long)SL_STAGE;
+  if (warp == 0) {
+    lb_publish(status, tile, blk);
+    if (!staged) {
+      unsigned long long e = lb_resolve(status, tile, blk);
+      if (lane == 0) s_excl = e;
+    }
+  }
+  if (!staged) __syncthreads();
+  const unsigned long long base_direct = staged ? 0ull : s_excl;
   unsigned loc = (unsigned)(woff + inc - (unsigned long long)n);           // first triangle of this thread in the tile
 #pragma unroll
   for (int u = 0; u < SL_PER; ++u) {
@@ -947,8 +952,8 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
     const unsigned swapmask = swapm[u];
     unsigned long long c = code[u];
     for (int q = 0; q < cnt[u]; ++q, c >>= 9, ++loc) {
-      if (!staged && base + loc >= cap) continue;
-      int* o = staged ? s_out + loc * 6 : out + (base + loc) * 6;
+      if (!staged && base_direct + loc >= cap) continue;
+      int* o = staged ? s_out + loc * 6 : out + (base_direct + loc) * 6;
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const int e = (int)((c >> (3 * r)) & 7ull);
@@ -962,7 +967,12 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
     }
   }
   if (staged) {
+    if (warp == 0) {
+      unsigned long long e = lb_resolve(status, tile, blk);
+      if (lane == 0) s_excl = e;
+    }
     __syncthreads();
+    const unsigned long long base = s_excl;
     unsigned long long nb = blk;
     if (base + nb > cap) nb = base < cap ? cap - base : 0ull;
     const unsigned nint = (unsigned)nb * 6u;
