@@ -196,133 +196,4 @@ __device__ __forceinline__ unsigned long long lb_lookback(unsigned long long* st
   return lb_resolve(status, tile, aggregate);
 }
 
-// Block-wide look-back over two status arrays at once.  Every thread of the block polls one predecessor, so a window
-// of THREADS tiles is resolved per iteration -- with a few hundred tiles in flight the warp version above needs ~10
-// serial L2 round trips while the rest of the block idles at a barrier; this one needs one or two.
-// Called by all threads; returns the exclusive prefixes of `tile` and publishes the inclusive ones.
-template <int THREADS>
-__device__ __forceinline__ void lb_lookback2_block(unsigned long long* st_a, unsigned long long* st_b, int tile,
-                                                   unsigned long long agg_a, unsigned long long agg_b,
-                                                   unsigned long long& excl_a, unsigned long long& excl_b) {
-  constexpr int NW = THREADS / 32;
-  __shared__ int s_first[2][NW];
-  __shared__ unsigned long long s_sum[2][NW];
-  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  excl_a = excl_b = 0ull;
-  if (tile == 0) {                                   // block-uniform
-    if (tid == 0) {
-      lb_store(&st_a[0], CTR_LB_INC | agg_a);
-      lb_store(&st_b[0], CTR_LB_INC | agg_b);
-    }
-    return;
-  }
-  if (tid == 0) {
-    lb_store(&st_a[tile], CTR_LB_AGG | agg_a);
-    lb_store(&st_b[tile], CTR_LB_AGG | agg_b);
-  }
-  bool done_a = false, done_b = false;
-  for (int idx = tile - 1;; idx -= THREADS) {
-    const int my = idx - tid;
-    unsigned long long sa = CTR_LB_INC, sb = CTR_LB_INC;   // virtual tiles before the first: inclusive prefix 0
-    if (my >= 0) {
-      if (!done_a) do { sa = lb_load(&st_a[my]); } while ((sa >> 62) == 0ull);
-      if (!done_b) do { sb = lb_load(&st_b[my]); } while ((sb >> 62) == 0ull);
-    }
-    const unsigned ia = __ballot_sync(0xffffffffu, (sa >> 62) == 2ull), ib = __ballot_sync(0xffffffffu, (sb >> 62) == 2ull);
-    if (lane == 0) {
-      s_first[0][warp] = ia ? warp * 32 + (__ffs(ia) - 1) : THREADS;
-      s_first[1][warp] = ib ? warp * 32 + (__ffs(ib) - 1) : THREADS;
-    }
-    __syncthreads();
-    int fa = THREADS, fb = THREADS;                  // nearest inclusive predecessor in this window (thread index)
-#pragma unroll
-    for (int q = 0; q < NW; ++q) {
-      fa = min(fa, s_first[0][q]);
-      fb = min(fb, s_first[1][q]);
-    }
-    unsigned long long va = (!done_a && tid <= fa) ? (sa & CTR_LB_VAL) : 0ull;
-    unsigned long long vb = (!done_b && tid <= fb) ? (sb & CTR_LB_VAL) : 0ull;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      va += __shfl_xor_sync(0xffffffffu, va, o);
-      vb += __shfl_xor_sync(0xffffffffu, vb, o);
-    }
-    if (lane == 0) {
-      s_sum[0][warp] = va;
-      s_sum[1][warp] = vb;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < NW; ++q) {
-      excl_a += s_sum[0][q];
-      excl_b += s_sum[1][q];
-    }
-    done_a = done_a || fa < THREADS;
-    done_b = done_b || fb < THREADS;
-    __syncthreads();                                 // s_first / s_sum are rewritten by the next iteration
-    if (done_a && done_b) break;
-  }
-  if (tid == 0) {
-    lb_store(&st_a[tile], CTR_LB_INC | (excl_a + agg_a));
-    lb_store(&st_b[tile], CTR_LB_INC | (excl_b + agg_b));
-  }
-}
-
-// Single-array wide look-back: warp 0 polls THREADS predecessors per iteration (THREADS/32 loads in flight per lane),
-// the other warps park at the barrier instead of spinning.  Called by all threads.
-template <int THREADS>
-__device__ __forceinline__ unsigned long long lb_lookback_block(unsigned long long* st, int tile, unsigned long long agg) {
-  constexpr int PER = THREADS / 32;
-  __shared__ unsigned long long s_excl;
-  const int tid = (int)threadIdx.x, lane = tid & 31;
-  if (tile == 0) {                                   // block-uniform
-    if (tid == 0) lb_store(&st[0], CTR_LB_INC | agg);
-    return 0ull;
-  }
-  if (tid < 32) {
-    if (lane == 0) lb_store(&st[tile], CTR_LB_AGG | agg);
-    unsigned long long excl = 0ull;
-    for (int idx = tile - 1;; idx -= THREADS) {
-      // lane l looks at predecessors idx - (l*PER + q), q = 0..PER-1 (nearest first)
-      unsigned long long v[PER];
-      bool all_valid;
-      do {
-        all_valid = true;
-#pragma unroll
-        for (int q = 0; q < PER; ++q) {
-          const int my = idx - (lane * PER + q);
-          v[q] = my >= 0 ? lb_load(&st[my]) : CTR_LB_INC;
-          all_valid = all_valid && (v[q] >> 62) != 0ull;
-        }
-        if (!all_valid) __nanosleep(64);
-      } while (!all_valid);
-      // sum up to and including the nearest inclusive entry
-      unsigned long long sum = 0ull;
-      bool found = false;
-#pragma unroll
-      for (int q = 0; q < PER; ++q) {
-        if (!found) sum += v[q] & CTR_LB_VAL;
-        found = found || (v[q] >> 62) == 2ull;
-      }
-      const unsigned fm = __ballot_sync(0xffffffffu, found);
-      if (fm) {
-        const int first = __ffs(fm) - 1;
-        if (lane > first) sum = 0ull;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      excl += sum;
-      if (fm) break;
-    }
-    if (lane == 0) {
-      lb_store(&st[tile], CTR_LB_INC | (excl + agg));
-      s_excl = excl;
-    }
-  }
-  __syncthreads();
-  const unsigned long long e = s_excl;
-  __syncthreads();
-  return e;
-}
-
 #endif  // __CUDACC__
