@@ -304,6 +304,26 @@ def run_ours(args):
     h2d = hf.nbytes
     d2h = (outs["verts"].nbytes + outs["normals"].nbytes + outs["tris"].nbytes) if outs else 0
 
+    # ---- the mesh passes that follow an extraction (not part of the metric): reference orientation, seeded selection
+    post = None
+    if world == 1 and not args.no_e2e:
+        post = {}
+        idx = int(torch.argmax(field))
+        pi, pj, pk = idx // (shape[1] * shape[2]), (idx // shape[2]) % shape[1], idx % shape[2]
+        row = field[pi, pj].cpu().numpy()
+        while pk + 1 < shape[2] and row[pk + 1] >= ISOVALUE:
+            pk += 1                                   # last sample of the row still above the isovalue: a border voxel
+        for name in ("orient_reference", "select_seeded"):
+            ts = []
+            for _ in range(3):
+                run_c = eng.mt3d_run(field.data_ptr(), ISOVALUE, shape=shape, dtype=np.float32, flags=flags)
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                res = eng.mt3d_orient_reference() if name == "orient_reference" else \
+                    eng.mt3d_select_seeded(np.array([[min(pi, shape[0] - 2), min(pj, shape[1] - 2), min(pk, shape[2] - 2)]], np.int32))
+                ts.append((time.perf_counter() - t1) * 1e3)
+            post[name] = {"ms": min(ts), "result": list(res), "n_tris_in": int(run_c.n_tris)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -358,6 +378,7 @@ def run_ours(args):
                 "note": "Engine.mt3d_extract_host (ctr_mt3d_run + ctr_mt3d_fetch per z-slab on two contexts, page-locked host "
                         "buffers): H2D of the field and D2H of vertices, normals and triangles inside the timed region"},
         "gpu_launches": int(launches), "clocks": clocks,
+        "post_passes": post,
     }
     print(json.dumps(line))
     if world > 1:
