@@ -386,8 +386,8 @@ __device__ __forceinline__ unsigned long long rec_vt(uint32_t r) {
 //   k_count_a : every word: 128-bit quick test, record zeroed, interesting words appended to a global list (one atomic
 //               per tile; the list is ordered inside a tile's chunk);
 //   k_count_b : one interesting word per thread, dense: counts, dirpack, owner / voxel work lists (slots: one block
-//               scan and one atomicAdd per list and block), record, tile aggregate by atomicAdd; the last block turns
-//               the aggregates into exclusive tile prefixes.
+//               scan and one atomicAdd per list and block), record, tile aggregate by atomicAdd;
+//   k_tile_scan3 : one block: tile aggregates -> exclusive tile prefixes.
 // (As ONE kernel per tile of 1024 words -- quick test, then the ~70 interesting words of the tile one per thread -- three
 // quarters of every block idled through the second phase and every tile paid the latency chain planes -> counts -> two
 // global atomics -> list writes on its own: 133 us against 17 + 104 us for the pair, measured under ncu.)
@@ -460,9 +460,8 @@ constexpr int CB_THREADS = 256;                     // (128: 160 us for stage 2 
 
 struct CountBShared {
   unsigned short vox[256];
-  unsigned long long warp_vt[CB_THREADS / 32];
   unsigned warp_items[CB_THREADS / 32];
-  unsigned base_own, base_cell, last;
+  unsigned base_own, base_cell;
 };
 
 template <typename T>
@@ -609,28 +608,27 @@ __global__ void __launch_bounds__(CB_THREADS, 4) k_count_b(Grid<T> gin, unsigned
     if (cc & 0xffffffffull) atomicAdd(&ctr->n_cells, cc & 0xffffffffull);
     if (cc >> 32) atomicAdd(&ctr->n_cross, cc >> 32);
   }
-  // the block that finishes last turns the tile aggregates into exclusive prefixes
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    sh.last = (atomicAdd(&ctr->ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (!sh.last) return;
-  __threadfence();
+}
+
+// exclusive scan of the tile aggregates (vertices | triangles << 31), in place: one block, a few thousand tiles.
+// (As the last act of the last block of k_count_b this cost every block two barriers, a fence and a ticket atomic:
+// a quarter of that kernel's stall samples.)
+__global__ void __launch_bounds__(1024) k_tile_scan3(unsigned long long* __restrict__ tile_vt, int ntiles, Counters* ctr) {
+  __shared__ unsigned long long s_warp[32];
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   unsigned long long carry = 0;
-  for (int base = 0; base < ntiles; base += CB_THREADS) {
+  for (int base = 0; base < ntiles; base += 1024) {
     const int q = base + (int)threadIdx.x;
-    const unsigned long long a = q < ntiles ? lb_load(&tile_vt[q]) : 0ull;
+    const unsigned long long a = q < ntiles ? tile_vt[q] : 0ull;
     const unsigned long long ia = warp_incl_scan_u64(a);
     __syncthreads();
-    if (lane == 31) sh.warp_vt[warp] = ia;
+    if (lane == 31) s_warp[warp] = ia;
     __syncthreads();
     unsigned long long wa = 0, ta = 0;
 #pragma unroll
-    for (int w8 = 0; w8 < CB_THREADS / 32; ++w8) {
-      if (w8 < (int)warp) wa += sh.warp_vt[w8];
-      ta += sh.warp_vt[w8];
+    for (int w = 0; w < 32; ++w) {
+      if (w < (int)warp) wa += s_warp[w];
+      ta += s_warp[w];
     }
     if (q < ntiles) tile_vt[q] = carry + wa + ia - a;
     carry += ta;
@@ -1236,7 +1234,8 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
                                               (uint2*)ctx->wdir.p, (unsigned long long*)b_own_id.p,
                                               (unsigned long long*)b_own_voff.p, (unsigned long long*)b_cell_id.p,
                                               (uint32_t*)b_cell_toff.p, cap_own, cap_cell, st_vt, dctr, ntiles);
-      ctx->launches += 2;
+      k_tile_scan3<<<1, 1024, 0, st>>>(st_vt, ntiles, dctr);
+      ctx->launches += 3;
       ctx->cover_w = (size_t)wb * CB_THREADS;
       CTR_DBG(ctx, "k_count_b");
       k_scan<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (const uint32_t*)ctx->tbase.p, st_vt, (uint32_t*)ctx->vbase.p,
