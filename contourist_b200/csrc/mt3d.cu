@@ -614,24 +614,32 @@ __global__ void __launch_bounds__(CB_THREADS, 4) k_count_b(Grid<T> gin, unsigned
 // (As the last act of the last block of k_count_b this cost every block two barriers, a fence and a ticket atomic:
 // a quarter of that kernel's stall samples.)
 __global__ void __launch_bounds__(1024) k_tile_scan3(unsigned long long* __restrict__ tile_vt, int ntiles, Counters* ctr) {
-  __shared__ unsigned long long s_warp[32];
+  __shared__ unsigned long long s_warp[32], s_tot;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   unsigned long long carry = 0;
-  for (int base = 0; base < ntiles; base += 1024) {
-    const int q = base + (int)threadIdx.x;
-    const unsigned long long a = q < ntiles ? tile_vt[q] : 0ull;
-    const unsigned long long ia = warp_incl_scan_u64(a);
-    __syncthreads();
+  for (int base = 0; base < ntiles; base += 4096) {   // 4 consecutive tiles per thread: 4 K tiles per round
+    const int q = base + 4 * (int)threadIdx.x;
+    unsigned long long a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = q + u < ntiles ? tile_vt[q + u] : 0ull;
+    const unsigned long long mine = a[0] + a[1] + a[2] + a[3];
+    const unsigned long long ia = warp_incl_scan_u64(mine);
+    __syncthreads();                                  // s_warp / s_tot of the previous round are consumed
     if (lane == 31) s_warp[warp] = ia;
     __syncthreads();
-    unsigned long long wa = 0, ta = 0;
-#pragma unroll
-    for (int w = 0; w < 32; ++w) {
-      if (w < (int)warp) wa += s_warp[w];
-      ta += s_warp[w];
+    if (warp == 0) {
+      const unsigned long long w = s_warp[lane], iw = warp_incl_scan_u64(w);
+      s_warp[lane] = iw - w;                          // exclusive prefix of the warps
+      if (lane == 31) s_tot = iw;
     }
-    if (q < ntiles) tile_vt[q] = carry + wa + ia - a;
-    carry += ta;
+    __syncthreads();
+    unsigned long long run = carry + s_warp[warp] + ia - mine;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (q + u < ntiles) tile_vt[q + u] = run;
+      run += a[u];
+    }
+    carry += s_tot;
   }
   if (threadIdx.x == 0) ctr->total_vt = carry;
 }
