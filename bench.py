@@ -195,16 +195,22 @@ def run_ours(args):
     flags = E.WANT_NORMALS if not os.environ.get("CTR_BENCH_NO_NORMALS") else 0   # (diagnostic switch; the metric needs normals)
     # the collective of the path: all-gather of (n_verts, n_tris) -> exclusive scan = global vertex / triangle offsets
     # (measured: issuing it on a side stream instead costs more host time than the peer skew it hides, 0.55 vs 0.52 ms)
+    # ctr_mt3d_finish waits for the extraction only (an event behind its last kernel), not for the all-gather queued
+    # after it, so the host is already enqueueing step k+1 while the collective of step k-1 runs.  The pinned staging
+    # buffers therefore rotate: slot s is reused 4 steps later, two finishes after its copy was consumed.
     counts_dev = torch.zeros(2, dtype=torch.int64, device=dev)
-    counts_pin = torch.zeros(2, dtype=torch.int64, pin_memory=True)
+    counts_pin = [torch.zeros(2, dtype=torch.int64, pin_memory=True) for _ in range(4)]
     gathered = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+    n_gather = [0]
 
     prev = [None]
 
     def gather(c):
-        counts_pin[0] = int(c.n_verts)
-        counts_pin[1] = int(c.n_tris)
-        counts_dev.copy_(counts_pin, non_blocking=True)
+        pin = counts_pin[n_gather[0] & 3]
+        n_gather[0] += 1
+        pin[0] = int(c.n_verts)
+        pin[1] = int(c.n_tris)
+        counts_dev.copy_(pin, non_blocking=True)
         dist.all_gather_into_tensor(gathered, counts_dev)
 
     def step():

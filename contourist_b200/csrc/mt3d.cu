@@ -1289,10 +1289,13 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
     }
     if (phase == 1) {
       CTR_CUDA(ctx, cudaGetLastError());
+      if (!ctx->ev_fork) CTR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+      CTR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
       return 0;                                          // ctr_mt3d_finish picks up from here
     }
     CTR_CUDA(ctx, cudaGetLastError());
-    CTR_CUDA(ctx, cudaStreamSynchronize(st));
+    if (phase == 2 && attempt == 0) CTR_CUDA(ctx, cudaEventSynchronize(ctx->ev_fork));   // only what the enqueue queued
+    else CTR_CUDA(ctx, cudaStreamSynchronize(st));
     memcpy(&h, ctx->counters_host, sizeof h);
     totV = h.total_vt & 0x7fffffffull;
     totT = h.total_vt >> 31;
