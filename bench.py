@@ -194,7 +194,6 @@ def run_ours(args):
     eng.set_timing(True)
     flags = E.WANT_NORMALS if not os.environ.get("CTR_BENCH_NO_NORMALS") else 0   # (diagnostic switch; the metric needs normals)
     # the collective of the path: all-gather of (n_verts, n_tris) -> exclusive scan = global vertex / triangle offsets
-    # (measured: issuing it on a side stream instead costs more host time than the peer skew it hides, 0.55 vs 0.52 ms)
     # ctr_mt3d_finish waits for the extraction only (an event behind its last kernel), not for the all-gather queued
     # after it, so the host is already enqueueing step k+1 while the collective of step k-1 runs.  The pinned staging
     # buffers therefore rotate: slot s is reused 4 steps later, two finishes after its copy was consumed.
@@ -202,6 +201,9 @@ def run_ours(args):
     counts_pin = [torch.zeros(2, dtype=torch.int64, pin_memory=True) for _ in range(4)]
     gathered = torch.zeros(2 * world, dtype=torch.int64, device=dev)
     n_gather = [0]
+    # CTR_BENCH_AG_SIDE=1 (diagnostic): issue the collective on a side stream instead; measured no better at 2 GPUs
+    # (0.480 vs 0.472 ms per step)
+    side = torch.cuda.Stream(device=dev) if (world > 1 and os.environ.get("CTR_BENCH_AG_SIDE")) else None
 
     prev = [None]
 
@@ -210,8 +212,13 @@ def run_ours(args):
         n_gather[0] += 1
         pin[0] = int(c.n_verts)
         pin[1] = int(c.n_tris)
-        counts_dev.copy_(pin, non_blocking=True)
-        dist.all_gather_into_tensor(gathered, counts_dev)
+        if side is None:
+            counts_dev.copy_(pin, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, counts_dev)
+        else:
+            with torch.cuda.stream(side):
+                counts_dev.copy_(pin, non_blocking=True)
+                dist.all_gather_into_tensor(gathered, counts_dev)
 
     def step():
         if world == 1:
@@ -231,6 +238,8 @@ def run_ours(args):
         if world > 1 and prev[0] is not None:
             gather(prev[0])
             prev[0] = None
+        if side is not None:
+            stream.wait_stream(side)
 
     def barrier():
         if world > 1:
