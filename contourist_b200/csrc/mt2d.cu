@@ -88,8 +88,7 @@ struct Shared2D {
   uint32_t cls[T2_ROWS + 1][T2_THREADS + 1];         // 4 class bytes per word (columns 4t..4t+3); word 256 = halo column
   uint32_t act[T2_ROWS * (T2_COLS / 32)];            // bitmap of the squares that may emit, row-major
   unsigned long long warp_sum[T2_THREADS / 32];
-  unsigned long long excl;
-  unsigned tile;
+  unsigned long long excl;                           // first list slot of the tile
 };
 
 __device__ __forceinline__ unsigned cls_at(const Shared2D& sh, int r, int c) {   // class byte of sample (r, c) of the tile
@@ -463,7 +462,7 @@ int run2d(ctr_ctx* ctx, const ctr_mt2d_params* p, ctr_mt2d_counts* out) {
     df = (const T*)ctx->field.p;
   }
   ctr_stage_mark(ctx, 1);
-  Levels2D<T> lv;
+  Levels2D<T> lv = {};
   make_levels<T>(p->levels, p->nlevels, lv);
   make_guess<T>(lv);
   const int i_lo = (int)p->i_lo, i_hi = (int)std::min<int64_t>(p->i_hi, n0 - 1);

@@ -109,7 +109,63 @@ def chain_segments(keys2, pos2):
     return out
 
 
+def seeded_segments(value_at, z, n1, seg_keys, end_points):
+    """Which segments of a full scan the reference's tracker reaches from seed segments (triangulated.py:307-338
+    find_initial_contour_pairs / expand_contour_pairs): every seed is bisected down to adjacent points (a pair
+    "exists" iff f(low) <= z <= f(high)); the start pairs are the contour pairs with the low point as their low end or
+    the high point as their high end; a pair brings in every pair that shares its low end (as low end) or its high
+    end (as high end).  seg_keys [S,2] uint64 engine keys ((lin(min point)*4 + d) << 1 | lowmin), n1 = row length,
+    value_at(point) -> f.  Returns a bool mask over the segments."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    seg_keys = np.asarray(seg_keys, dtype=np.uint64).reshape(-1, 2)
+    keys, inv = np.unique(seg_keys.reshape(-1), return_inverse=True)
+    if len(keys) == 0:
+        assert len(end_points) == 0, "bad end points: the level has no contour"
+        return np.zeros(0, dtype=bool)
+    lowmin = (keys & np.uint64(1)).astype(np.int64)
+    kd = keys >> np.uint64(1)
+    d = (kd & np.uint64(3)).astype(np.int64)
+    lin_p = (kd >> np.uint64(2)).astype(np.int64)
+    lin_q = lin_p + ((d >> 1) & 1) * n1 + (d & 1)
+    low_lin = np.where(lowmin == 1, lin_p, lin_q)
+    high_lin = np.where(lowmin == 1, lin_q, lin_p)
+    rows, cols = [], []
+    for end in (low_lin, high_lin):                        # pairs sharing an end: consecutive after sorting by it
+        o = np.argsort(end, kind="stable")
+        same = end[o][1:] == end[o][:-1]
+        rows.append(o[:-1][same])
+        cols.append(o[1:][same])
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    _, comp = connected_components(coo_matrix((np.ones(len(rows), np.int8), (rows, cols)), shape=(len(keys), len(keys))),
+                                   directed=False)
+
+    def exists(lo, hi):
+        return value_at(lo) <= z <= value_at(hi)
+
+    wanted = set()
+    for low_point, high_point in np.array(end_points, dtype=int).reshape(-1, 2, 2):
+        if not exists(low_point, high_point):
+            (low_point, high_point) = (high_point, low_point)
+            assert exists(low_point, high_point), "bad end points " + repr((tuple(low_point), tuple(high_point)))
+        while np.any(np.abs(low_point - high_point) > 1):
+            mid_point = (low_point + high_point) // 2
+            if exists(low_point, mid_point):
+                high_point = mid_point
+            else:
+                assert exists(mid_point, high_point)
+                low_point = mid_point
+        start = (low_lin == low_point[0] * n1 + low_point[1]) | (high_lin == high_point[0] * n1 + high_point[1])
+        assert start.any()
+        wanted.update(comp[start].tolist())
+    return np.isin(comp[inv.reshape(-1, 2)[:, 0]], sorted(wanted))
+
+
 class Grid2DContour(object):
+    """Grid-coordinate front end.  segment_endpoints=None: every contour of the level (full scan); a list of seed
+    segments: only the contours the reference's tracker reaches from them (seeded_segments)."""
+
+    full_scan = False                                  # True: ignore the seeds (they are known to be every crossing)
 
     def __init__(self, horizontal_n, vertical_m, function, value, segment_endpoints=None, callback=None,
                  origin=(0.0, 0.0), delta=(1.0, 1.0)):
@@ -133,10 +189,23 @@ class Grid2DContour(object):
         g = field2d.Function2DGrid(0, 0, self.n - 1, self.m - 1, 1, 1, self.f)
         return g.samples(0)
 
+    def _value_at(self, point):
+        "f at an integer point: the callable wherever it is defined (seed segments may end outside the grid), else the array"
+        if not isinstance(self.f, np.ndarray):
+            return float(self.f(*(int(x) for x in point)))
+        i, j = int(point[0]), int(point[1])
+        if not (0 <= i < self.n and 0 <= j < self.m):
+            raise ValueError("seed point %r outside the %d x %d sample array" % ((i, j), self.n, self.m))
+        return float(self.f[i, j])
+
     def get_contour_sequences(self):
         eng = E.default_engine()
         eng.mt2d_run(self._field(), [float(self.z)], origin=self.origin, delta=self.delta, flags=E.GEOM_F64)
         self.segments = eng.mt2d_fetch()
+        if self.end_points is not None and not self.full_scan:
+            keep = seeded_segments(self._value_at, float(self.z), self.m, self.segments["keys"], self.end_points)
+            self.segments = {k: (v[keep] if isinstance(v, np.ndarray) and len(v) == len(keep) else v)
+                             for k, v in self.segments.items()}
         self.contours = [(closed, pts) for closed, pts in chain_segments(self.segments["keys"], self.segments["pos"])]
         if self.callback:
             self.callback(self)
@@ -151,8 +220,28 @@ class ContourGrid(object):
         self.grid = function_grid
         self.value = value
         self.segment_endpoints = segment_endpoints
-        self.contour_maker = self.get_contour_maker(None)
+        grid_endpoints = None
+        if segment_endpoints is not None:               # triangulated.py:92-103: world seeds -> grid seeds, else grid search
+            grid_endpoints = []
+            for (start_xy, end_xy) in segment_endpoints:
+                assert len(start_xy) == len(end_xy) == 2
+                grid_endpoint = self.to_grid_endpoint(np.array(start_xy, dtype=float), np.array(end_xy, dtype=float))
+                if grid_endpoint is not None:
+                    grid_endpoints.append(grid_endpoint)
+            if len(grid_endpoints) < 1:
+                grid_endpoints = None
+        self.contour_maker = self.get_contour_maker(grid_endpoints)
         self.grid_values = None
+
+    def to_grid_endpoint(self, start_xy, end_xy):
+        "triangulated.py:109-118: the first pair of grid vertices around the two points that straddles the value."
+        grid, value = self.grid, self.value
+        for start_grid in grid.surrounding_vertices(start_xy):
+            for end_grid in grid.surrounding_vertices(end_xy):
+                if not np.all(start_grid == end_grid):
+                    if (grid.grid_function(*start_grid) - value) * (grid.grid_function(*end_grid) - value) <= 0:
+                        return (start_grid, end_grid)
+        return None
 
 
 class DxDy2DContourGrid(ContourGrid):
@@ -161,7 +250,7 @@ class DxDy2DContourGrid(ContourGrid):
         assert self.linear_interpolate, "non-linear interpolation not implemented yet for 2d"
         grid = self.grid
         (n, m) = (int(x) for x in grid.grid_dimensions)
-        return Grid2DContour(n, m, grid.samples(0), self.value, grid_endpoints)
+        return Grid2DContour(n, m, grid.samples(0), self.value, grid_endpoints)    # None: grid search = full scan
 
     def get_contour_sequences(self):
         self.grid_contours = self.contour_maker.get_contour_sequences()

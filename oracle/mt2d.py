@@ -4,7 +4,7 @@ numpy restatement of the reference's 2D contour path as a FULL SCAN (SURVEY.md 8
 Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this.
 
 Parity status: PINNED against golden vectors made by running the unmodified reference
-(tests/golden/make_golden.py -> mt2d_*.npz) and the reference's own known answers
+(tests/golden/make_golden.py -> mt2d_*.npz, seeded2d_*.npz) and the reference's own known answers
 (contourist/test/test_triangulated.py:20-42,79-106).
 
 Reference lines restated (under /root/reference/contourist/):
@@ -14,6 +14,7 @@ Reference lines restated (under /root/reference/contourist/):
                            f(low) <= z <= f(high) (inclusive both sides); ratio 0.5 when the
                            denominator is allclose to 0, else (z - flow)/(fhigh - flow)
   triangulated.py:295-305  find_adjacencies: two keys are linked iff they are adjacent_pairs of each other
+  triangulated.py:307-338  find_initial_contour_pairs / expand_contour_pairs (seeded tracking) -> seeded_keys()
   triangulated.py:221-293  get_contour_sequences (polyline chaining)       -> polylines()
   multiple_2d_contour.py:50-75   level classification of grid edges         -> (same predicate per level)
   multiple_2d_contour.py:100-108 Linear2DContour.get_values                 -> linear_levels()
@@ -187,3 +188,61 @@ def polylines(keys, pos, seg_keys):
             closed = True
         out.append((closed, np.array(chain, dtype=np.uint64), pts))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Seeded tracking: what the reference returns for explicit seed segments
+# ---------------------------------------------------------------------------------------------------
+def seeded_keys(field, z, end_points):
+    """triangulated.py:307-338 find_initial_contour_pairs + expand_contour_pairs until nothing is new, on an array:
+    bisect every seed segment down to adjacent points (a pair "exists" iff f(low) <= z <= f(high)), start from all
+    contour pairs that have the low point as low end or the high point as high end, and keep adding the pairs that
+    share their low end (as low) or their high end (as high) with a pair already found.  Returns the sorted keys."""
+    f = np.asarray(field).astype(np.float64)
+    z = float(z)
+    r = extract_level(field, z)
+    keys = r["keys"]
+    low, high = decode_key(keys, f.shape)
+    n1 = f.shape[1]
+    by_low, by_high = {}, {}
+    for q, (lo, hi) in enumerate(zip(low[:, 0] * n1 + low[:, 1], high[:, 0] * n1 + high[:, 1])):
+        by_low.setdefault(int(lo), []).append(q)
+        by_high.setdefault(int(hi), []).append(q)
+
+    def exists(lo, hi):
+        return f[tuple(lo)] <= z <= f[tuple(hi)]
+
+    found, horizon = set(), set()
+    for low_point, high_point in np.asarray(end_points, dtype=np.int64).reshape(-1, 2, 2):
+        if not exists(low_point, high_point):
+            low_point, high_point = high_point, low_point
+            assert exists(low_point, high_point), "bad end points"
+        while np.any(np.abs(low_point - high_point) > 1):
+            mid_point = (low_point + high_point) // 2
+            if exists(low_point, mid_point):
+                high_point = mid_point
+            else:
+                assert exists(mid_point, high_point)
+                low_point = mid_point
+        new = set(by_low.get(int(low_point[0] * n1 + low_point[1]), [])) | \
+            set(by_high.get(int(high_point[0] * n1 + high_point[1]), []))
+        assert new
+        found |= new
+        horizon |= new
+    while horizon:
+        nxt = set()
+        for q in horizon:
+            nxt.update(by_low[int(low[q, 0] * n1 + low[q, 1])])
+            nxt.update(by_high[int(high[q, 0] * n1 + high[q, 1])])
+        horizon = nxt - found
+        found |= nxt
+    return keys[sorted(found)]
+
+
+def extract_level_seeded(field, z, end_points, geom_dtype=np.float64):
+    """extract_level restricted to the pairs the tracker reaches from the seed segments."""
+    r = extract_level(field, z, geom_dtype)
+    keep = np.isin(r["keys"], seeded_keys(field, z, end_points))
+    segs = r["seg_keys"]
+    sk = np.isin(segs[:, 0], r["keys"][keep]) if len(segs) else np.zeros(0, dtype=bool)
+    return dict(keys=r["keys"][keep], pos=r["pos"][keep], seg_keys=segs[sk])

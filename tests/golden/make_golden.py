@@ -247,6 +247,40 @@ def run2d(arr, levels):
     return out
 
 
+def fields_seeded2d():
+    """2D fields with several contours of one level and explicit seed segments: the reference's tracker
+    (triangulated.py:307-338) must return only the contours its seeds reach."""
+    n = 24
+    x, y = np.meshgrid(np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64), indexing="ij")
+    bumps = np.zeros((n, n))
+    for c, r in (((5.3, 5.2), 3.1), ((17.4, 6.1), 2.7), ((6.2, 17.3), 3.4), ((17.6, 17.2), 2.9)):
+        bumps += np.exp(-((x - c[0]) ** 2 + (y - c[1]) ** 2) / (r * r))
+    out = {}
+    out["bumps_one"] = (bumps, 0.5, [[(5, 5), (5, 11)]])
+    out["bumps_two"] = (bumps, 0.5, [[(17, 6), (23, 6)], [(12, 12), (18, 17)]])
+    ints = np.random.default_rng(3).integers(-2, 3, size=(14, 15)).astype(np.float64)
+    ints[4:10, 4:11] = -2.0
+    ints[6:8, 6:9] = 2.0
+    out["ints_island"] = (ints, 0.0, [[(6, 6), (6, 4)]])
+    return out
+
+
+def run_seeded2d(arr, value, seeds):
+    T = rh.load("triangulated")
+    n0, n1 = arr.shape
+
+    def f(i, j):
+        return float(arr[min(max(int(i), 0), n0 - 1), min(max(int(j), 0), n1 - 1)])
+    G = T.Grid2DContour(n0, n1, f, value, [[np.array(a), np.array(b)] for a, b in seeds])
+    seqs = G.get_contour_sequences()                      # triangulated.py:221-293 (search, expand, chain)
+    pairs = sorted(G.interpolated_contour_pairs.keys())
+    return dict(field=arr, value=np.float64(value), seeds=np.array(seeds, dtype=np.int64).reshape(-1, 2, 2),
+                low=np.array([p[0] for p in pairs], dtype=np.int64).reshape(-1, 2),
+                high=np.array([p[1] for p in pairs], dtype=np.int64).reshape(-1, 2),
+                closed=np.array([c for c, _ in seqs], dtype=np.int64), length=np.array([len(p) for _, p in seqs], dtype=np.int64),
+                pts=(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 2) for _, p in seqs]) if seqs else np.zeros((0, 2))))
+
+
 def main2d():
     for name, (arr, levels) in fields2d().items():
         g = run2d(arr, levels)
@@ -254,8 +288,17 @@ def main2d():
         print(name, arr.shape, [(k, g[k].shape) for k in sorted(g) if k.endswith("_low")], "%.1fs" % g["seconds"])
 
 
+def main_seeded2d():
+    for name, (arr, value, seeds) in fields_seeded2d().items():
+        g = run_seeded2d(arr, value, seeds)
+        np.savez_compressed(os.path.join(HERE, "seeded2d_%s.npz" % name), **g)
+        print(name, arr.shape, "pairs", len(g["low"]), "contours", len(g["closed"]), g["closed"].tolist(), g["length"].tolist())
+
+
 if __name__ == "__main__" and "2d" in sys.argv[1:]:
     main2d()
+if __name__ == "__main__" and "seeded2d" in sys.argv[1:]:
+    main_seeded2d()
 
 
 # ------------------------------------------------------------------ 4D

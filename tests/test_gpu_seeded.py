@@ -138,3 +138,47 @@ def test_select_needs_a_full_volume_run(engine):
     engine.mt3d_run(f, 0.0, i_lo=0, i_hi=6)
     with pytest.raises(E.EngineError):
         engine.mt3d_select_seeded(np.zeros((1, 3), np.int32))
+
+
+FILES2D = sorted(glob.glob(os.path.join(GOLDEN, "seeded2d_*.npz")))
+
+
+@pytest.mark.parametrize("path", FILES2D, ids=[os.path.basename(f) for f in FILES2D])
+def test_2d_reference_seeded_runs(engine, path):
+    """Grid2DContour with explicit seeds returns the contours the reference's tracker finds (triangulated.py:307-338),
+    not the full scan: same pairs as the reference run, same polylines as point sets."""
+    from contourist_b200 import triangulated
+    from oracle import mt2d
+    g = np.load(path)
+    field, z = g["field"], float(g["value"])
+    seeds = [[tuple(a), tuple(b)] for a, b in g["seeds"].tolist()]
+    G = triangulated.Grid2DContour(field.shape[0], field.shape[1], field, z, seeds)
+    got = G.get_contour_sequences()
+    want_keys = mt2d.seeded_keys(field, z, g["seeds"])
+    assert np.array_equal(np.unique(G.segments["keys"]), want_keys)
+    assert sorted(len(p) for _, p in got) == sorted(g["length"].tolist())
+    assert sorted(bool(c) for c, _ in got) == sorted(bool(c) for c in g["closed"])
+    mine = sorted(map(tuple, np.round(np.concatenate([p for _, p in got]), 9).tolist()))
+    ref = sorted(map(tuple, np.round(g["pts"], 9).tolist()))
+    assert mine == ref
+    full = triangulated.Grid2DContour(field.shape[0], field.shape[1], field, z, None).get_contour_sequences()
+    assert len(full) > len(got)
+
+
+def test_2d_world_seeds_through_the_driver(engine):
+    """DxDy2DContour with world-coordinate seeds (triangulated.py:92-118): only the dot the seed points at.  (With
+    the dots of test_triangulated.py:44-68 the tracker hops from one to the other: they share the low point (1,1).)"""
+    from contourist_b200 import triangulated
+
+    def two_dots(x, y):
+        return 1 if (x == y == -4 or x == y == 2) else -1
+    C = triangulated.DxDy2DContour(-4, -4, 4, 4, 2, 2, two_dots, 0, [[(2, 2), (4, 2)]])
+    contours = C.get_contour_sequences()
+    assert len(contours) == 1 and contours[0][0]
+    pts = sorted((int(round(x * 10)), int(round(y * 10))) for x, y in contours[0][1])
+    assert pts == sorted([(20, 30), (30, 30), (30, 20), (20, 10), (10, 10), (10, 20)])
+    assert len(triangulated.DxDy2DContour(-4, -4, 4, 4, 2, 2, two_dots, 0).get_contour_sequences()) == 2
+    # the reference's own two dots share a low point: its tracker returns both from one seed
+    def near_dots(x, y):
+        return 1 if (x == y == -4 or x == y == 0) else -1
+    assert len(triangulated.DxDy2DContour(-4, -4, 4, 4, 2, 2, near_dots, 0, [[(0, 0), (4, 0)]]).get_contour_sequences()) == 2
