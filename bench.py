@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 
 ISOVALUE = 0.5
 # dram__bytes_read.sum + dram__bytes_write.sum of the six kernels of one extraction, from profiles/ (ncu --set full);
-TRAFFIC_BYTES = 1027.4e6     # profiles/r1o_ncu_full_summary.txt, dram read + write summed over the six kernels (algorithmic: 725.9 MB)
+TRAFFIC_BYTES = 1037.3e6     # profiles/r1q_ncu_full_summary.txt, dram read + write summed over the seven kernels (algorithmic: 725.9 MB)
 METRIC = "Gvoxels/s, 512^3 fp32 marching-tetrahedra extraction (indexed mesh + normals)"
 
 
