@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ISOVALUE = 0.5
-# dram__bytes_read.sum + dram__bytes_write.sum of the six kernels of one extraction, from profiles/ (ncu --set full);
+# dram__bytes_read.sum + dram__bytes_write.sum of the seven kernels of one extraction, from profiles/ (ncu --set full);
 TRAFFIC_BYTES = 1037.3e6     # profiles/r1q_ncu_full_summary.txt, dram read + write summed over the seven kernels (algorithmic: 725.9 MB)
 METRIC = "Gvoxels/s, 512^3 fp32 marching-tetrahedra extraction (indexed mesh + normals)"
 
@@ -355,7 +355,7 @@ def run_ours(args):
                                    "gbs": (v[1] / (v[0] * 1e-3) / 1e9) if v[0] > 0 else None,
                                    "frac": (v[1] / (v[0] * 1e-3) / 1e9 / peak) if v[0] > 0 else None}
                  for k, v in stages.items()}
-    per_stage["k_count_a+k_count_b+k_scan"] = {"ms": st[2], "algorithmic_bytes": 0.0, "gbs": 0.0, "frac": 0.0}
+    per_stage["k_count_a+k_count_b+k_tile_scan3+k_scan"] = {"ms": st[2], "algorithmic_bytes": 0.0, "gbs": 0.0, "frac": 0.0}
     kern_ms = float(st[1] + st[2] + st[3] + st[4])    # the four kernels of one extraction, from CUDA events on their stream
     dom = max(per_stage, key=lambda k: per_stage[k]["ms"])
     alg_total = float(n) ** 3 * 4 + c.n_verts * 24 + c.n_tris * 12        # field + V*(3p+3p) + T*12
@@ -380,7 +380,7 @@ def run_ours(args):
                      "wall_ms_per_step": wall / args.steps * 1e3},
         # one extraction = one launch each of four kernels; SURVEY 8(d) defines the algorithmic bytes per extraction, so the
         # roofline is taken over the four launches together (the scan kernel moves no algorithmic bytes of its own)
-        "roofline": {"bound": "hbm", "kernel": "mt3d extraction = k_bitplane_tma + k_count_a + k_count_b + k_scan + k_emit_verts + k_emit_tris "
+        "roofline": {"bound": "hbm", "kernel": "mt3d extraction = k_bitplane_tma + k_count_a + k_count_b + k_tile_scan3 + k_scan + k_emit_verts + k_emit_tris "
                                                 "(largest share: %s, %.0f%% of the kernel time)" % (dom, 100.0 * per_stage[dom]["ms"] / kern_ms),
                      "achieved": alg_total / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg_total / (kern_ms * 1e-3) / 1e9 / peak, "traffic": TRAFFIC_BYTES, "peak_source": peak_src,
