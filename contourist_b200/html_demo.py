@@ -9,57 +9,82 @@ from . import wire
 
 load_three = '<script src="https://cdnjs.cloudflare.com/ajax/libs/three.js/r70/three.min.js"></script>'
 
+# A stand-alone viewer page for one indexed mesh.  Not a wire format: only the placeholders and the two number lists
+# (`vertices` = [[x, y, z], ...], `indices` = [[i, j, k], ...], formatted like Python's str(list)) follow
+# html_demo.py:118-131; the page itself is this package's own (flat-shaded BufferGeometry, orbit by dragging).
 three_html_fullscreen = """<!DOCTYPE html>
 <html>
 <head>
-    <title>%(title)s</title>
-    %(load_three)s
-    <style> body { margin: 0; overflow: hidden; } </style>
+<meta charset="utf-8">
+<title>%(title)s</title>
+%(load_three)s
+<style>html, body { height: 100%%; margin: 0; background: #f2f2f2; } #%(target_div)s { position: fixed; inset: 0; }</style>
 </head>
 <body>
 <div id="%(target_div)s"></div>
-<script type="text/javascript">
-    function init() {
-        var scene = new THREE.Scene();
-        var camera = new THREE.PerspectiveCamera(45, window.innerWidth / window.innerHeight, 0.1, 1000);
-        var webGLRenderer = new THREE.WebGLRenderer();
-        webGLRenderer.setClearColor(new THREE.Color(0xEEEEEE, 1.0));
-        webGLRenderer.setSize(window.innerWidth, window.innerHeight);
-        var triangulation = make_triangulation();
-        scene.add(triangulation);
-        camera.position.set(%(camera_x)s, %(camera_y)s, %(camera_z)s);
-        camera.lookAt(new THREE.Vector3(0, 0, 0));
-        document.getElementById("%(target_div)s").appendChild(webGLRenderer.domElement);
-        var step = 0;
-        function render() {
-            triangulation.rotation.y = step += 0.01;
-            requestAnimationFrame(render);
-            webGLRenderer.render(scene, camera);
-        };
-        render();
-    };
-    window.onload = init;
+<script>
+(function () {
+  var MESH_POINTS = %(vertices)s;
+  var MESH_FACES = %(indices)s;
+  var host = document.getElementById("%(target_div)s");
+  var renderer = new THREE.WebGLRenderer({antialias: true});
+  renderer.setClearColor(0xf2f2f2, 1);
+  host.appendChild(renderer.domElement);
+  var eye = new THREE.PerspectiveCamera(40, 1, 0.05, 5000);
+  var world = new THREE.Scene();
 
-    function make_triangulation() {
-        var vertices = %(vertices)s;
-        var indices = %(indices)s;
-        var geom = new THREE.Geometry();
-        for (var i=0; i<vertices.length; i++) {
-            var v = vertices[i];
-            geom.vertices.push(new THREE.Vector3(v[0], v[1], v[2]));
-        }
-        for (var i=0; i<indices.length; i++) {
-            var f = indices[i];
-            geom.faces.push(new THREE.Face3(f[0], f[1], f[2]));
-        }
-        geom.computeFaceNormals();
-        geom.computeVertexNormals();
-        var meshMaterial = new THREE.MeshNormalMaterial();
-        meshMaterial.side = THREE.DoubleSide;
-        var wireFrameMat = new THREE.MeshBasicMaterial();
-        wireFrameMat.wireframe = true;
-        return THREE.SceneUtils.createMultiMaterialObject(geom, [meshMaterial, wireFrameMat]);
-    };
+  // un-indexed triangle soup: one normal per face, so facets stay visible
+  var nf = MESH_FACES.length, xyz = new Float32Array(nf * 9), nrm = new Float32Array(nf * 9);
+  var lo = [Infinity, Infinity, Infinity], hi = [-Infinity, -Infinity, -Infinity];
+  for (var f = 0; f < nf; f++) {
+    var P = [MESH_POINTS[MESH_FACES[f][0]], MESH_POINTS[MESH_FACES[f][1]], MESH_POINTS[MESH_FACES[f][2]]];
+    var ux = P[1][0] - P[0][0], uy = P[1][1] - P[0][1], uz = P[1][2] - P[0][2];
+    var vx = P[2][0] - P[0][0], vy = P[2][1] - P[0][1], vz = P[2][2] - P[0][2];
+    var n = [uy * vz - uz * vy, uz * vx - ux * vz, ux * vy - uy * vx];
+    var len = Math.sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) || 1;
+    for (var c = 0; c < 3; c++) {
+      for (var a = 0; a < 3; a++) {
+        xyz[f * 9 + c * 3 + a] = P[c][a];
+        nrm[f * 9 + c * 3 + a] = n[a] / len;
+        lo[a] = Math.min(lo[a], P[c][a]);
+        hi[a] = Math.max(hi[a], P[c][a]);
+      }
+    }
+  }
+  var soup = new THREE.BufferGeometry();
+  soup.addAttribute("position", new THREE.BufferAttribute(xyz, 3));
+  soup.addAttribute("normal", new THREE.BufferAttribute(nrm, 3));
+  var skin = new THREE.Mesh(soup, new THREE.MeshNormalMaterial({side: THREE.DoubleSide}));
+  var pivot = new THREE.Object3D();
+  pivot.add(skin);
+  if (nf) skin.position.set(-(lo[0] + hi[0]) / 2, -(lo[1] + hi[1]) / 2, -(lo[2] + hi[2]) / 2);
+  world.add(pivot);
+  eye.position.set(%(camera_x)s, %(camera_y)s, %(camera_z)s);
+  eye.lookAt(new THREE.Vector3(0, 0, 0));
+
+  function fit() {
+    renderer.setSize(window.innerWidth, window.innerHeight);
+    eye.aspect = window.innerWidth / Math.max(window.innerHeight, 1);
+    eye.updateProjectionMatrix();
+  }
+  window.addEventListener("resize", fit);
+  fit();
+
+  var drag = null, spin = 0.004;
+  host.addEventListener("mousedown", function (e) { drag = [e.clientX, e.clientY]; spin = 0; });
+  window.addEventListener("mouseup", function () { drag = null; });
+  window.addEventListener("mousemove", function (e) {
+    if (!drag) return;
+    pivot.rotation.y += (e.clientX - drag[0]) * 0.01;
+    pivot.rotation.x += (e.clientY - drag[1]) * 0.01;
+    drag = [e.clientX, e.clientY];
+  });
+  (function frame() {
+    pivot.rotation.y += spin;
+    renderer.render(world, eye);
+    requestAnimationFrame(frame);
+  })();
+})();
 </script>
 </body>
 </html>

@@ -59,7 +59,8 @@ def test_isosurface_facade_equals_oracle_world_coords(engine):
     from contourist_b200 import html_demo
     d = json.loads(html_demo.emit_three_json(S))
     assert len(d["faces"]) == 4 * len(tris) and len(d["vertices"]) == 3 * len(pts)
-    assert "new THREE.Face3" in html_demo.grid_html_page(S)
+    page = html_demo.grid_html_page(S)
+    assert "THREE.BufferGeometry" in page and ("var MESH_FACES = [[%d, %d, %d]" % tuple(int(i) for i in tris[0])) in page
 
 
 def test_reference_orientation_matches_reference_on_golden_sphere(engine):

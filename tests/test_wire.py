@@ -83,7 +83,7 @@ def test_grid_html_page_lists_equal_reference():
     # html_demo.py:120-121: ",\n    ".join(map(str, map(list, points))) on rows of Python floats / ints
     vertices = "[%s]" % (",\n    ".join(map(str, ([float(c) for c in p] for p in pts))))
     indices = "[%s]" % (",\n    ".join(map(str, ([int(i) for i in t] for t in tris))))
-    assert "var vertices = %s;" % vertices in page and "var indices = %s;" % indices in page
+    assert "var MESH_POINTS = %s;" % vertices in page and "var MESH_FACES = %s;" % indices in page
 
 
 def test_flatten_json_list_bytes():
