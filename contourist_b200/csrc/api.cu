@@ -53,9 +53,7 @@ extern "C" void ctr_destroy(ctr_ctx* c) {
   if (c->counters_host) cudaFreeHost(c->counters_host);
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
-  if (c->stream2) cudaStreamDestroy(c->stream2);
-  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_enqueued) cudaEventDestroy(c->ev_enqueued);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }

@@ -19,9 +19,8 @@ struct ctr_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  cudaStream_t stream2 = nullptr;      // (unused)
-  cudaEvent_t ev_fork = nullptr;       // recorded behind everything ctr_mt3d_enqueue queued: ctr_mt3d_finish waits for
-  cudaEvent_t ev_join = nullptr;       // it, not for the stream (work queued later, e.g. a collective, is not its business)
+  cudaEvent_t ev_enqueued = nullptr;   // recorded behind everything ctr_mt3d_enqueue queued: ctr_mt3d_finish waits for it,
+                                       // not for the stream (work queued later, e.g. a collective, is not its business)
   std::string err;
   int64_t launches = 0;
   bool timing = false;

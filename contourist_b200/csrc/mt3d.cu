@@ -1289,12 +1289,12 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
     }
     if (phase == 1) {
       CTR_CUDA(ctx, cudaGetLastError());
-      if (!ctx->ev_fork) CTR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-      CTR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+      if (!ctx->ev_enqueued) CTR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_enqueued, cudaEventDisableTiming));
+      CTR_CUDA(ctx, cudaEventRecord(ctx->ev_enqueued, st));
       return 0;                                          // ctr_mt3d_finish picks up from here
     }
     CTR_CUDA(ctx, cudaGetLastError());
-    if (phase == 2 && attempt == 0) CTR_CUDA(ctx, cudaEventSynchronize(ctx->ev_fork));   // only what the enqueue queued
+    if (phase == 2 && attempt == 0) CTR_CUDA(ctx, cudaEventSynchronize(ctx->ev_enqueued));   // only what the enqueue queued
     else CTR_CUDA(ctx, cudaStreamSynchronize(st));
     memcpy(&h, ctx->counters_host, sizeof h);
     totV = h.total_vt & 0x7fffffffull;
