@@ -186,6 +186,7 @@ def run_ours(args):
         # NCCL_DEBUG=VERSION makes NCCL print its version on rank 0's stdout, in front of the one JSON line
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # whatever NCCL logs: not on the JSON line's stream
         dist.init_process_group("nccl", device_id=dev)
     n = args.n
     # this rank's slab of the (n*world) x n x n volume, with halo planes (1 below, 2 above)

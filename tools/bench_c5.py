@@ -46,6 +46,7 @@ def main():
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # whatever NCCL logs: not on the JSON line's stream
         dist.init_process_group("nccl", device_id=dev)
     n = args.n
     a_r, b_r = sharding.slab_bounds(n, world)[rank]
