@@ -162,8 +162,24 @@ def run_seeded(arr, value, seeds):
                 key_high=np.array([p[1] for p in used], dtype=np.int64).reshape(-1, 3))
 
 
+def run_clean(path):
+    """surface_geometry.py:14-50 clean_triangles of the unmodified reference on the raw mesh of a 3D golden."""
+    RS = rh.load("surface_geometry")
+    g = np.load(path)
+    geometry = RS.SurfaceGeometry([p for p in g["key_pos"]], [frozenset(int(i) for i in t) for t in g["tris"]])
+    verts, tris = geometry.clean_triangles()
+    full = sorted(tuple(sorted(t)) for t in tris if len(t) == 3)
+    return dict(vertices=np.array(verts, dtype=np.float64).reshape(-1, 3), triangles=np.array(full, dtype=np.int32).reshape(-1, 3),
+                n_degenerate=np.int64(sum(1 for t in tris if len(t) < 3)))
+
+
 def main():
     which = sys.argv[1:] or ["3d"]
+    if "clean" in which:
+        for name in ("sphere13", "wave11", "noise8", "ints7", "plateau6"):
+            g = run_clean(os.path.join(HERE, "mt3d_%s.npz" % name))
+            np.savez_compressed(os.path.join(HERE, "clean3d_%s.npz" % name), **g)
+            print(name, "vertices", len(g["vertices"]), "triangles", len(g["triangles"]), "two-vertex leftovers", int(g["n_degenerate"]))
     if "seeded" in which:
         for name, (arr, value, seeds) in fields_seeded().items():
             g = run_seeded(arr, value, seeds)
