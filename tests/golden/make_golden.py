@@ -399,5 +399,24 @@ def main4d():
               "morph", g["morph_segments"].shape, g["morph_triangles"].shape, "%.1fs" % g["seconds"])
 
 
+def main_json4d():
+    """morph_geometry.py:91-128: the unmodified reference's MorphTriangles.to_json on the morph arrays of a 4D golden."""
+    import hashlib
+    import json
+    RM = rh.load("morph_geometry")
+    out = {}
+    for name in ("morph7",):
+        g = np.load(os.path.join(HERE, "mp4d_%s.npz" % name))
+        mt = RM.MorphTriangles([p for p in g["morph_points"]], [tuple(int(x) for x in s) for s in g["morph_segments"]],
+                               [tuple(int(x) for x in t) for t in g["morph_triangles"]])
+        text = mt.to_json()
+        out[name] = {"sha256": hashlib.sha256(text.encode()).hexdigest(), "length": len(text), "head": text[:200]}
+        print(name, out[name]["length"], out[name]["sha256"])
+    with open(os.path.join(HERE, "mp4d_to_json.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__" and "4d" in sys.argv[1:]:
     main4d()
+if __name__ == "__main__" and "json4d" in sys.argv[1:]:
+    main_json4d()

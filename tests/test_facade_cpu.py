@@ -157,3 +157,17 @@ def test_clean_triangles_against_reference(name):
         assert mine == theirs
     assert len(verts) <= len(ref["vertices"])
     assert all(len(set(t)) == 3 for t in np.asarray(tris).tolist())
+
+
+def test_morph_triangles_to_json_bytes_equal_reference():
+    """MorphTriangles.to_json (morph_geometry.py:91-128; number lists through ctr_wire_format) on the morph arrays of
+    a 4D golden: byte for byte the text the unmodified reference produced (tests/golden/make_golden.py json4d)."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN
+    want = json.load(open(os.path.join(GOLDEN, "mp4d_to_json.json")))["morph7"]
+    g = np.load(os.path.join(GOLDEN, "mp4d_morph7.npz"))
+    text = morph_geometry.MorphTriangles(g["morph_points"], g["morph_segments"], g["morph_triangles"]).to_json()
+    assert text[:200] == want["head"] and len(text) == want["length"]
+    assert hashlib.sha256(text.encode()).hexdigest() == want["sha256"]
