@@ -414,6 +414,23 @@ def main_json4d():
         print(name, out[name]["length"], out[name]["sha256"])
     with open(os.path.join(HERE, "mp4d_to_json.json"), "w") as f:
         json.dump(out, f, indent=1)
+    # html_demo.py:133-161 emit_three_json of the unmodified reference on the final mesh of a 3D golden
+    RH = rh.load("html_demo")
+
+    class Holder(object):
+        def __init__(self, p, t):
+            self.p, self.t = p, t
+
+        def get_points_and_triangles(self):
+            return self.p, self.t
+    out3 = {}
+    for name in ("wave11", "sphere13"):
+        g = np.load(os.path.join(HERE, "mt3d_%s.npz" % name))
+        text = RH.emit_three_json(Holder([np.array(p) for p in g["final_points"]], [tuple(int(i) for i in t) for t in g["final_tris"]]))
+        out3[name] = {"sha256": hashlib.sha256(text.encode()).hexdigest(), "length": len(text)}
+        print(name, out3[name])
+    with open(os.path.join(HERE, "mt3d_three_json.json"), "w") as f:
+        json.dump(out3, f, indent=1)
 
 
 if __name__ == "__main__" and "4d" in sys.argv[1:]:

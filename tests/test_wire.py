@@ -90,3 +90,17 @@ def test_flatten_json_list_bytes():
     rng = np.random.default_rng(5)
     a = rng.integers(0, 999999, size=(100000, 4))
     assert morph_geometry.flatten_json_list(a) == "[%s]" % (",\n".join(",".join(str(y) for y in x) for x in a.tolist()))
+
+
+def test_emit_three_json_bytes_equal_the_reference_function():
+    """html_demo.emit_three_json against the text the unmodified reference's emit_three_json produced for the final
+    meshes of two 3D goldens (sha256 fixtures, tests/golden/make_golden.py json4d)."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN
+    want = json.load(open(os.path.join(GOLDEN, "mt3d_three_json.json")))
+    for name, w in want.items():
+        g = np.load(os.path.join(GOLDEN, "mt3d_%s.npz" % name))
+        text = html_demo.emit_three_json(FakeContour(g["final_points"], g["final_tris"]))
+        assert len(text) == w["length"] and hashlib.sha256(text.encode()).hexdigest() == w["sha256"]
