@@ -177,8 +177,8 @@ def test_svg_text_equals_reference():
     """contour_sequences_to_svg (triangulated.py:16-50): the text the unmodified reference produced for this input."""
     rng = np.random.default_rng(0)
     seqs = [(True, [np.array(p) for p in rng.uniform(-3, 7, (9, 2))]), (False, [np.array(p) for p in rng.uniform(0, 1, (4, 2))])]
-    want = ('\\n<svg height="340.1828516632472" width="300" viewBox="-2.5902647606380533 -2.972614998298519 8.222053984136918 '
-            '9.323339236176201">\\n<path stroke-width="0.09" stroke="black" fill="none" d="M3.37 -0.30 L-2.59 -2.83 L5.13 6.13 '
-            'L3.07 4.29 L2.44 6.35 L5.16 -2.97 L5.57 -2.66 L4.30 -1.24 L5.63 2.41 Z" />\\n<path stroke-width="0.09" stroke="black" '
-            'fill="none" d="M0.30 0.42 L0.03 0.12 L0.67 0.65 L0.62 0.38" />\\n</svg>\\n')
+    want = ('\n<svg height="340.1828516632472" width="300" viewBox="-2.5902647606380533 -2.972614998298519 8.222053984136918 '
+            '9.323339236176201">\n<path stroke-width="0.09" stroke="black" fill="none" d="M3.37 -0.30 L-2.59 -2.83 L5.13 6.13 '
+            'L3.07 4.29 L2.44 6.35 L5.16 -2.97 L5.57 -2.66 L4.30 -1.24 L5.63 2.41 Z" />\n<path stroke-width="0.09" stroke="black" '
+            'fill="none" d="M0.30 0.42 L0.03 0.12 L0.67 0.65 L0.62 0.38" />\n</svg>\n')
     assert triangulated.contour_sequences_to_svg(seqs) == want
