@@ -182,3 +182,26 @@ def test_svg_text_equals_reference():
             'L3.07 4.29 L2.44 6.35 L5.16 -2.97 L5.57 -2.66 L4.30 -1.24 L5.63 2.41 Z" />\n<path stroke-width="0.09" stroke="black" '
             'fill="none" d="M0.30 0.42 L0.03 0.12 L0.67 0.65 L0.62 0.38" />\n</svg>\n')
     assert triangulated.contour_sequences_to_svg(seqs) == want
+
+
+def test_morph_triangle_orientation_agrees_with_reference_on_a_smooth_field():
+    """MorphTriangles.orient_triangles (morph_geometry.py:40-67, time-compatible components, max-x rule at mid-life)
+    on the reference's own morph triangles of the smooth 4D golden, windings scrambled: the reference's winding comes
+    back for all but a handful of triangles (its DFS is order-dependent where small components tie)."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "mp4d_morph7.npz"))
+    tris = g["morph_triangles"]
+    rng = np.random.default_rng(1)
+    scrambled = np.array([t[::-1] if rng.random() < 0.5 else t for t in tris])
+    mt = morph_geometry.MorphTriangles(g["morph_points"], g["morph_segments"], scrambled)
+    mt.orient_triangles()
+
+    def rot(t):
+        t = tuple(int(i) for i in t)
+        k = t.index(min(t))
+        return t[k:] + t[:k]
+    want, got = set(rot(t) for t in tris), set(rot(t) for t in mt.triangle_segment_indices)
+    assert len(got) == len(want) == len(tris)
+    assert len(want & got) >= 0.995 * len(tris)
+    assert set(tuple(sorted(t)) for t in want) == set(tuple(sorted(t)) for t in got)
