@@ -106,3 +106,13 @@ def test_reference_known_answer_dot():
 def test_linear_levels_restates_reference_quirk():
     f = np.array([[1.0, 2.0], [3.0, 5.0]])
     assert mt2d.linear_levels(f, 4) == [1.0, 2.0, 3.0]      # (5-1)/4 * i, NOT shifted by the minimum
+
+
+def test_level_rules_known_answers_from_the_reference_classes():
+    """multiple_2d_contour.py:91-108: values the unmodified reference's Linear2DContour(breakpoints=5) and
+    Percentile2DContour(breakpoints=4) computed for f = sin(3x+y^2)+cos(4y+x^2) on [-2,2]^2, delta 0.25 (17 x 17)."""
+    f = np.array([[np.sin(3 * x + y * y) + np.cos(4 * y + x * x) for y in -2 + 0.25 * np.arange(17)] for x in -2 + 0.25 * np.arange(17)])
+    lin = mt2d.linear_levels(f, 5)
+    per = mt2d.percentile_levels(f, 4)
+    assert np.allclose(lin[:3], [0.7961310269006759, 1.5922620538013519, 2.388393080702028], rtol=1e-12, atol=0) and len(lin) == 4
+    assert np.allclose(per[:3], [-0.6838886577943704, 0.05132507684886245, 0.681422313928007], rtol=1e-12, atol=0)
