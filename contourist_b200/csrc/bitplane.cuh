@@ -402,14 +402,13 @@ int launch_bitplane(ctr_ctx* ctx, const T* dfield, unsigned nrows, int n2, int W
   rg.rc = rc;
   if (clear_rowflag) CTR_CUDA(ctx, cudaMemsetAsync(rg.rowflag, 0, (size_t)nrows, st));
   if (kind == BP_TMA) {
-    static bool attr_set[4] = {false, false, false, false};
     static const int TMA_STAGES = getenv("CTR_BP_STAGES") ? atoi(getenv("CTR_BP_STAGES")) : TMA_STAGES_DEFAULT;
     static const int ctas_per_sm = getenv("CTR_BP_CTAS") ? atoi(getenv("CTR_BP_CTAS")) : 3;
     const int smem = TMA_STAGES * TMA_CHUNK + 2 * TMA_STAGES * 8 + TMA_CONSUMER_WARPS * 32 * 4 + 64;
     const int ti = (sizeof(T) == 4 ? 0 : 1) + (MINMAX ? 2 : 0);
-    if (!attr_set[ti]) {
+    if (!(ctx->attr_mask & (1u << ti))) {
       CTR_CUDA(ctx, cudaFuncSetAttribute(k_bitplane_tma<T, MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * TMA_CHUNK + 1024));
-      attr_set[ti] = true;
+      ctx->attr_mask |= 1u << ti;
     }
     const size_t nbytes = nsamp * sizeof(T);
     const size_t nchunks = (nbytes + TMA_CHUNK - 1) / TMA_CHUNK;

@@ -28,6 +28,7 @@ struct ctr_ctx {
   bool ev_set[CTR_NSTAGE + 1] = {};
   float stage_ms[CTR_NSTAGE] = {};
   int sm_count = 148;
+  unsigned attr_mask = 0;    // cudaFuncSetAttribute calls already made on this context's device (the attribute is per device)
 
   // staging + shared scratch
   DevBuf field;              // device copy of a host field
@@ -48,6 +49,7 @@ struct ctr_ctx {
   uint32_t last_flags = 0;
   int64_t last_counts[8] = {};
   unsigned char last3_params[160] = {};   // parameters of the last completed ctr_mt3d_run
+  unsigned last3_edited = 0;              // passes that have rewritten the device mesh of that run: 1 seeded selection, 2 clean-up
   // 3D: an extraction enqueued by ctr_mt3d_enqueue and not yet finished
   bool pending3 = false;
   alignas(8) unsigned char pending3_params[160] = {};

@@ -1199,11 +1199,10 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
       for (int attempt = 0; attempt < 3; ++attempt) {
         if ((rc = ctr_ensure(ctx, B.mtris, want * 24))) return rc;
         const unsigned cap = (unsigned)std::min<size_t>(B.mtris.cap / 24, 0x7fffffffu);
-        static bool sl_attr = false;
-        if (!sl_attr) {
+        if (!(ctx->attr_mask & (1u << 8))) {
           CTR_CUDA(ctx, cudaFuncSetAttribute(k4_slice<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_STAGE * 6 * sizeof(int))));
           CTR_CUDA(ctx, cudaFuncSetAttribute(k4_slice<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_STAGE * 6 * sizeof(int))));
-          sl_attr = true;
+          ctx->attr_mask |= 1u << 8;
         }
         SlCounters* slc = (SlCounters*)((char*)B.slstate.p + (size_t)sl_tiles * 8);
         CTR_CUDA(ctx, cudaMemsetAsync(B.slstate.p, 0, (size_t)sl_tiles * 8 + 32, st));

@@ -567,6 +567,9 @@ extern "C" int ctr_mt2d_run(ctr_ctx* ctx, const ctr_mt2d_params* p, ctr_mt2d_cou
   if (p->n0 < 2 || p->n1 < 2) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "grid must have at least 2 samples per axis");
   if ((unsigned long long)p->n0 * (unsigned long long)p->n1 >= (1ull << 32))
     return ctr_fail(ctx, CTR_ERR_UNSUPPORTED, "2D field too large for 32-bit sample indices; shard it");
+  // the totals travel packed as segments << 31 | squares: the squares of one call must stay below 2^31
+  if (p->i_hi > p->i_lo && (unsigned long long)(p->i_hi - p->i_lo) * (unsigned long long)(p->n1 - 1) >= (1ull << 31) - 16)
+    return ctr_fail(ctx, CTR_ERR_UNSUPPORTED, "more than 2^31 squares in one call; pass a narrower row band [i_lo, i_hi)");
   if (p->nlevels < 1 || p->nlevels > MAXL) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "1..64 levels supported");
   for (int l = 0; l < p->nlevels; ++l) {
     if (!(p->levels[l] == p->levels[l])) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "NaN level");

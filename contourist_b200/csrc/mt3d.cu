@@ -52,6 +52,7 @@ struct Counters {                    // device counter block (mirrored to pinned
   unsigned int ticket;
   unsigned int n_word;               // interesting words listed by k_count_a
   unsigned int n_own, n_cell;        // slots handed out in the owner / voxel work lists (their lengths at the end)
+  unsigned long long tot_v, tot_t;   // the same totals, accumulated unpacked (a vertex total >= 2^31 would carry into T above)
 };
 
 
@@ -614,14 +615,19 @@ __global__ void __launch_bounds__(CB_THREADS, 4) k_count_b(Grid<T> gin, unsigned
 // (As the last act of the last block of k_count_b this cost every block two barriers, a fence and a ticket atomic:
 // a quarter of that kernel's stall samples.)
 __global__ void __launch_bounds__(1024) k_tile_scan3(unsigned long long* __restrict__ tile_vt, int ntiles, Counters* ctr) {
-  __shared__ unsigned long long s_warp[32], s_tot;
+  __shared__ unsigned long long s_warp[32], s_tot, s_v, s_t;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-  unsigned long long carry = 0;
+  unsigned long long carry = 0, my_v = 0, my_t = 0;
+  if (threadIdx.x == 0) s_v = s_t = 0ull;
   for (int base = 0; base < ntiles; base += 4096) {   // 4 consecutive tiles per thread: 4 K tiles per round
     const int q = base + 4 * (int)threadIdx.x;
     unsigned long long a[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) a[u] = q + u < ntiles ? tile_vt[q + u] : 0ull;
+    for (int u = 0; u < 4; ++u) {
+      a[u] = q + u < ntiles ? tile_vt[q + u] : 0ull;
+      my_v += a[u] & 0x7fffffffull;                    // a tile's own aggregate is far below 2^31 in both halves
+      my_t += a[u] >> 31;
+    }
     const unsigned long long mine = a[0] + a[1] + a[2] + a[3];
     const unsigned long long ia = warp_incl_scan_u64(mine);
     __syncthreads();                                  // s_warp / s_tot of the previous round are consumed
@@ -641,7 +647,21 @@ __global__ void __launch_bounds__(1024) k_tile_scan3(unsigned long long* __restr
     }
     carry += s_tot;
   }
-  if (threadIdx.x == 0) ctr->total_vt = carry;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    my_v += __shfl_xor_sync(0xffffffffu, my_v, o);
+    my_t += __shfl_xor_sync(0xffffffffu, my_t, o);
+  }
+  if (lane == 0) {
+    atomicAdd(&s_v, my_v);
+    atomicAdd(&s_t, my_t);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ctr->total_vt = carry;
+    ctr->tot_v = s_v;
+    ctr->tot_t = s_t;
+  }
 }
 
 // Stage 2b: offsets.  Every tile knows its exclusive prefix (k_count_b's last block): block scan of the per-word records
@@ -1297,8 +1317,8 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
     if (phase == 2 && attempt == 0) CTR_CUDA(ctx, cudaEventSynchronize(ctx->ev_enqueued));   // only what the enqueue queued
     else CTR_CUDA(ctx, cudaStreamSynchronize(st));
     memcpy(&h, ctx->counters_host, sizeof h);
-    totV = h.total_vt & 0x7fffffffull;
-    totT = h.total_vt >> 31;
+    totV = h.tot_v;
+    totT = h.tot_t;
     nOwn = h.n_own;
     nCell = h.n_cell;
     nV = (g.i_hiv > g.i_hi) ? h.v_emit : totV;
@@ -1349,6 +1369,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
     }
   }
   ctx->last_kind = 3;
+  ctx->last3_edited = 0;
   ctx->last_flags = p->flags;
   ctx->last_counts[0] = (int64_t)nV;
   ctx->last_counts[1] = (int64_t)totT;
@@ -1467,6 +1488,10 @@ extern "C" int ctr_mt3d_select_seeded(ctr_ctx* ctx, const int32_t* seed_voxels, 
   const ctr_mt3d_params* p = (const ctr_mt3d_params*)ctx->last3_params;
   if (p->i_lo != 0 || p->i_hi != p->n0)
     return ctr_fail(ctx, CTR_ERR_UNSUPPORTED, "seeded selection needs a full-volume run (components cross slab faces)");
+  // the selection compacts the run's mesh in place while the voxel work list keeps its per-voxel triangle offsets: it
+  // can be applied once per run
+  if (ctx->last3_edited)
+    return ctr_fail(ctx, CTR_ERR_STATE, "the mesh of this run has already been selected from or cleaned; run ctr_mt3d_run again");
   CTR_CUDA(ctx, cudaSetDevice(ctx->device));
   if (p->dtype == CTR_F32) return select_typed<float>(ctx, p, seed_voxels, n_seeds, n_verts, n_tris, n_voxels);
   return select_typed<double>(ctx, p, seed_voxels, n_seeds, n_verts, n_tris, n_voxels);

@@ -334,6 +334,7 @@ int select_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, const int32_t* seeds, i
   CTR_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->last_counts[0] = (int64_t)newV;
   ctx->last_counts[1] = (int64_t)newT;
+  ctx->last3_edited |= 1u;
   if (out_verts) *out_verts = (int64_t)newV;
   if (out_tris) *out_tris = (int64_t)newT;
   if (out_voxels) *out_voxels = (int64_t)h.pad;

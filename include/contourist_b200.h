@@ -146,7 +146,8 @@ CTR_API int ctr_mt3d_orient_reference(ctr_ctx* ctx, int64_t* n_components, int64
  * outside [0, n-2] are ignored (the reference's out-of-range "leak" voxels).  Triangles, vertices, normals and keys
  * are compacted in place (order kept, ids renumbered); case codes / cells stay those of the full scan.  Returns the
  * new counts and the number of emitting voxels selected; fetch afterwards.  With CTR_FIELD_ON_DEVICE the field must
- * still be resident.                                                                                              */
+ * still be resident.  ONE-SHOT: the run's mesh is rewritten, so a second call on the same run (or a call after
+ * ctr_mt3d_clean) returns CTR_ERR_STATE until the next ctr_mt3d_run.                                              */
 CTR_API int ctr_mt3d_select_seeded(ctr_ctx* ctx, const int32_t* seed_voxels, int64_t n_seeds, int64_t* n_verts,
                                    int64_t* n_tris, int64_t* n_voxels);
 

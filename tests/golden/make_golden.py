@@ -173,6 +173,48 @@ def run_clean(path):
                 n_degenerate=np.int64(sum(1 for t in tris if len(t) < 3)))
 
 
+def run_post(arr, value, stages=False):
+    """tetrahedral.py:541-552 of the unmodified reference -- quantize_interpolations, remove_tiny_simplices,
+    extract_points_and_triangles (clean_triangles + orient_triangles) -- on the IN-RANGE raw state (the simplices owned
+    by voxels with origin in [0, N-1], the parity domain of the engine: DESIGN.md section 2), by calling the reference's
+    own methods in the reference's own order on its own object.  `raw_*` is that state in the numbering of the mt3d_*
+    goldens (sorted pairs), so a restatement can start from exactly what the reference started from."""
+    T = rh.load("tetrahedral")
+    f = array_callable(arr)
+    corner = [s - 1 for s in arr.shape]
+    seeds = strict_seeds(arr, value)
+    G = T.Grid3DContour(corner[0], corner[1], corner[2], f, value, seeds)
+    G.find_initial_voxels()
+    while G.new_surface_voxels:
+        G.expand_voxels()
+    for triple in G.surface_voxels:
+        G.enumerate_voxel_triangles(triple)
+    corner_a = np.array(corner)
+    keep = set()
+    for s in G.simplex_sets:
+        owner = np.array([p for pair in s for p in pair]).min(axis=0)
+        if np.all(owner >= 0) and np.all(owner < corner_a):
+            keep.add(s)
+    G.simplex_sets = keep
+    used = sorted(set(pair for s in keep for pair in s))
+    G.interpolated_contour_pairs = {pair: G.interpolated_contour_pairs[pair] for pair in used}
+    kidx = {p: i for i, p in enumerate(used)}
+    raw_low = np.array([p[0] for p in used], dtype=np.int64).reshape(-1, 3)
+    raw_high = np.array([p[1] for p in used], dtype=np.int64).reshape(-1, 3)
+    raw_pos = np.array([G.interpolated_contour_pairs[p] for p in used], dtype=np.float64).reshape(-1, 3)
+    raw_tris = np.array(sorted(sorted(kidx[p] for p in s) for s in keep), dtype=np.int64).reshape(-1, 3)
+    G.quantize_interpolations()
+    n_after_q = len(G.simplex_sets)
+    G.remove_tiny_simplices()
+    n_after_t = len(G.simplex_sets)
+    pts, tris = G.extract_points_and_triangles(True)
+    return dict(field=arr, value=np.float64(value), key_low=raw_low, key_high=raw_high, key_pos=raw_pos, tris=raw_tris,
+                final_points=np.array(pts, dtype=np.float64).reshape(-1, 3),
+                final_tris=np.array(tris, dtype=np.int64).reshape(-1, 3),
+                n_after_quantize=np.int64(n_after_q), n_after_tiny=np.int64(n_after_t),
+                collapsed=np.int64(G.collapsed_simplices))
+
+
 def main():
     which = sys.argv[1:] or ["3d"]
     if "clean" in which:
@@ -180,6 +222,23 @@ def main():
             g = run_clean(os.path.join(HERE, "mt3d_%s.npz" % name))
             np.savez_compressed(os.path.join(HERE, "clean3d_%s.npz" % name), **g)
             print(name, "vertices", len(g["vertices"]), "triangles", len(g["triangles"]), "two-vertex leftovers", int(g["n_degenerate"]))
+    if "post" in which:
+        todo = dict(fields3d())
+        todo["c1"] = c1_field()
+        g32 = np.linspace(-1.0, 1.0, 33)
+        X, Y, Z = np.meshgrid(g32, g32, g32, indexing="ij")
+        todo["gyroid33"] = (np.sin(4 * X) * np.cos(4 * Y) + np.sin(4 * Y) * np.cos(4 * Z) + np.sin(4 * Z) * np.cos(4 * X), 0.0)
+        for name, (arr, value) in todo.items():
+            g = run_post(arr, value)
+            if name in ("c1",):
+                g.pop("field")                         # conftest.c1_golden regenerates it from the formula
+            for k in ("key_low", "key_high"):
+                g[k] = g[k].astype(np.int16)
+            g["tris"] = g["tris"].astype(np.int32)
+            g["final_tris"] = g["final_tris"].astype(np.int32)
+            np.savez_compressed(os.path.join(HERE, "post3d_%s.npz" % name), **g)
+            print(name, arr.shape, "raw", len(g["key_pos"]), len(g["tris"]), "after quantize", int(g["n_after_quantize"]),
+                  "after tiny", int(g["n_after_tiny"]), "final", g["final_points"].shape, g["final_tris"].shape)
     if "seeded" in which:
         for name, (arr, value, seeds) in fields_seeded().items():
             g = run_seeded(arr, value, seeds)
