@@ -43,19 +43,33 @@ __device__ __forceinline__ unsigned long long order_key(double x) {
 // ------------------------------------------------------------------------------------------------
 struct RowGeom {
   uint8_t* rowflag;
+  uint32_t* wordflag;                      // optional (3D): per row, one bit per group of `wdiv` words, see flag_rows
   FastDiv divW, divRc, divRb;
   int rb, rc;                              // row = (a*rb + b)*rc + c   (3D: a = 0, b = i, c = j)
+  int W, wdiv;
 };
 
-// a word of row `row` holds a near sample: flag every row whose 3x3(x3) row neighbourhood contains it
-__device__ __noinline__ void flag_rows(const RowGeom& rg, unsigned row) {
+// word `word` holds a near sample: flag every row whose 3x3(x3) row neighbourhood contains it.  The word flags say
+// where in those rows: bit (w / wdiv) for the words w-1, w, w+1 (an edge or voxel of word w-1 reaches sample 0 of
+// word w; the exact paths of word w+1 look back at sample 31 of word w), so that later stages take their exact path
+// for 3 words of a flagged row, not for all of it.
+__device__ __noinline__ void flag_rows(const RowGeom& rg, unsigned word) {
+  const unsigned row = rg.divW.div(word);
   const unsigned ab = rg.divRc.div(row), c = row - ab * (unsigned)rg.rc;
   const unsigned a = rg.divRb.div(ab), b = ab - a * (unsigned)rg.rb;
+  uint32_t m = 0;
+  if (rg.wordflag) {
+    const int w = (int)(word - row * (unsigned)rg.W);
+    for (int q = max(w - 1, 0); q <= min(w + 1, rg.W - 1); ++q) m |= 1u << (q / rg.wdiv);
+  }
   for (int da = 0; da < 3; ++da)
     for (int db = 0; db < 3; ++db)
       for (int dc = 0; dc < 3; ++dc)
-        if ((int)a - da >= 0 && (int)b - db >= 0 && (int)c - dc >= 0)
-          rg.rowflag[((size_t)(a - da) * rg.rb + (b - db)) * rg.rc + (c - dc)] = 1;
+        if ((int)a - da >= 0 && (int)b - db >= 0 && (int)c - dc >= 0) {
+          const size_t r = ((size_t)(a - da) * rg.rb + (b - db)) * rg.rc + (c - dc);
+          rg.rowflag[r] = 1;
+          if (rg.wordflag) atomicOr(&rg.wordflag[r], m);
+        }
 }
 
 template <typename T>
@@ -110,7 +124,7 @@ __global__ void __launch_bounds__(256) k_bitplane_generic(const T* __restrict__ 
         if (lane == 0) {
           bits[gu] = wl;
           nbits[gu] = wn;
-          if (wn) flag_rows(rg, gu / (unsigned)W);
+          if (wn) flag_rows(rg, gu);
         }
         if (ok[u]) {
           if (MINMAX) {
@@ -201,7 +215,7 @@ __global__ void __launch_bounds__(256) k_bitplane_vec(const T* __restrict__ f, s
         const size_t word = cu * VEC + lane / GROUP;
         bits[word] = wl;
         nbits[word] = wn;
-        if (wn) flag_rows(rg, rg.divW.div((unsigned)word));
+        if (wn) flag_rows(rg, (unsigned)word);
       }
     }
   }
@@ -327,7 +341,7 @@ __global__ void __launch_bounds__((TMA_CONSUMER_WARPS + 1) * 32) k_bitplane_tma(
         const unsigned wn = __ballot_sync(0xffffffffu, (val[q] >= near_lo) && (val[q] <= near_hi));
         if ((int)lane == q) {
           mine_n = wn;
-          if (wn) flag_rows(rg, rg.divW.div((unsigned)(word0 + q)));
+          if (wn) flag_rows(rg, (unsigned)(word0 + q));
         }
       }
     }
@@ -383,7 +397,8 @@ BitplaneKind bitplane_choice() {
 
 template <typename T, bool MINMAX>
 int launch_bitplane(ctr_ctx* ctx, const T* dfield, unsigned nrows, int n2, int W, int rb, int rc, double iso,
-                    uint32_t* bits, uint32_t* nbits, uint8_t* rowflag, MinMaxKeys* dctr, bool clear_rowflag = true) {
+                    uint32_t* bits, uint32_t* nbits, uint8_t* rowflag, MinMaxKeys* dctr, bool clear_rowflag = true,
+                    uint32_t* wordflag = nullptr) {
   cudaStream_t st = ctx->stream;
   T thr, nlo, nhi;
   thresholds<T>(iso, thr, nlo, nhi);
@@ -395,6 +410,9 @@ int launch_bitplane(ctr_ctx* ctx, const T* dfield, unsigned nrows, int n2, int W
   if (!linear_ok) kind = BP_GENERIC;
   RowGeom rg;
   rg.rowflag = rowflag;
+  rg.wordflag = wordflag;
+  rg.W = W;
+  rg.wdiv = (W + 31) / 32;
   rg.divW.init((unsigned)W);
   rg.divRc.init((unsigned)rc);
   rg.divRb.init((unsigned)rb);

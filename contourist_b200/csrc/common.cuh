@@ -59,7 +59,7 @@ struct ctr_ctx {
   DevBuf wlist;
 
   // 2D / 4D extra outputs are declared in their own translation units via these generic slots
-  DevBuf aux[32];
+  DevBuf aux[48];            // 0-4, 32-35: 3D; 5-10: 2D; 12-26: 4D; 27-31: mesh passes
 };
 
 static inline int ctr_fail(ctr_ctx* ctx, int code, const char* what, const char* detail = "") {

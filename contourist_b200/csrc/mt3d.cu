@@ -71,6 +71,11 @@ struct Grid {
   // conservative allclose hull; kernels copy it into any_near before touching a word of row (i, j).
   int any_near;
   const uint8_t* rowflag;
+  const uint32_t* wordflag;          // per row: bit (w / wdiv) set iff some near sample within rows +-2 and words w-1..w+1
+  int wdiv;
+  __device__ __forceinline__ int near_word(unsigned row, unsigned w) const {
+    return (int)((wordflag[row] >> (w / (unsigned)wdiv)) & 1u);
+  }
   FastDiv divW, divN1;
   __device__ __forceinline__ void word_coords(unsigned gw, int& i, int& j, int& w) const {
     unsigned row = divW.div(gw);
@@ -399,36 +404,29 @@ __device__ __forceinline__ unsigned long long rec_vt(uint32_t r) {
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(CS_THREADS) k_count_a(Grid<T> g, unsigned word0, unsigned nwords_scan,
-                                                     uint32_t* __restrict__ rec, uint32_t* __restrict__ wlist,
+                                                     uint32_t* __restrict__ wlist, uint2* __restrict__ tile_chunk,
                                                      unsigned cap_w, Counters* ctr) {
-  __shared__ unsigned s_n, s_base;
+  // the tile's interesting words in ascending word order: counts per (round, warp), prefix over those 4 x 8 counts
+  __shared__ unsigned s_cnt[CS_ITEMS][CS_THREADS / 32];
+  __shared__ unsigned s_base;
   __shared__ unsigned short s_list[CS_TILE];
-  if (threadIdx.x == 0) s_n = 0;
-  __syncthreads();
-  const unsigned lane = lane_id();
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
   const unsigned tile0 = blockIdx.x * CS_TILE;
-  if ((g.W & 3) == 0) {
-    const unsigned wl0 = threadIdx.x * CS_ITEMS;
-    const unsigned rel = tile0 + wl0;
-    unsigned m4 = 0;
-    if (rel < nwords_scan) {
-      m4 = words4_interesting(g, word0 + rel, plane_words);
-      *reinterpret_cast<uint4*>(rec + word0 + rel) = make_uint4(0u, 0u, 0u, 0u);
-    }
+  const bool vec = (g.W & 3) == 0;
+  unsigned m4 = 0, mq[CS_ITEMS] = {0, 0, 0, 0};
+  unsigned excl = 0;
+  if (vec) {
+    const unsigned rel = tile0 + threadIdx.x * CS_ITEMS;
+    if (rel < nwords_scan) m4 = words4_interesting(g, word0 + rel, plane_words);
     const unsigned cnt = __popc(m4);
     const unsigned inc = warp_incl_scan_u32(cnt);
-    unsigned base = 0;
-    if (lane == 31 && inc) base = atomicAdd(&s_n, inc);
-    base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
-#pragma unroll
-    for (int q = 0; q < CS_ITEMS; ++q)
-      if ((m4 >> q) & 1u) s_list[base++] = (unsigned short)(wl0 + q);
+    excl = inc - cnt;
+    if (lane == 31) s_cnt[0][warp] = inc;
   } else {
 #pragma unroll
     for (int q = 0; q < CS_ITEMS; ++q) {
-      const unsigned wl = (unsigned)q * CS_THREADS + threadIdx.x;
-      const unsigned rel = tile0 + wl;
+      const unsigned rel = tile0 + (unsigned)q * CS_THREADS + threadIdx.x;
       bool interesting = false;
       if (rel < nwords_scan) {
         int i, j, w;
@@ -438,19 +436,50 @@ __global__ void __launch_bounds__(CS_THREADS) k_count_a(Grid<T> g, unsigned word
         uint32_t x[7];
         cross_words(pl, x);
         interesting = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6]) != 0;
-        rec[word0 + rel] = 0u;
       }
-      const unsigned m = __ballot_sync(0xffffffffu, interesting);
-      unsigned base = 0;
-      if (lane == 0 && m) base = atomicAdd(&s_n, (unsigned)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (interesting) s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)wl;
+      mq[q] = __ballot_sync(0xffffffffu, interesting);
+      if (lane == 0) s_cnt[q][warp] = (unsigned)__popc(mq[q]);
     }
   }
   __syncthreads();
-  const unsigned nint = s_n;
+  unsigned nint = 0, before[CS_ITEMS] = {0, 0, 0, 0};
+  if (vec) {
+#pragma unroll
+    for (int w = 0; w < CS_THREADS / 32; ++w) {
+      const unsigned c = s_cnt[0][w];
+      if (w < (int)warp) before[0] += c;
+      nint += c;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < CS_ITEMS; ++q)
+#pragma unroll
+      for (int w = 0; w < CS_THREADS / 32; ++w) {
+        const unsigned c = s_cnt[q][w];
+#pragma unroll
+        for (int r = 0; r < CS_ITEMS; ++r)
+          if (q < r || (q == r && w < (int)warp)) before[r] += c;
+        nint += c;
+      }
+  }
+  if (threadIdx.x == 0) {
+    const unsigned b0 = nint ? atomicAdd(&ctr->n_word, nint) : 0u;
+    s_base = b0;
+    tile_chunk[blockIdx.x] = make_uint2(b0, nint);
+  }
   if (!nint) return;
-  if (threadIdx.x == 0) s_base = atomicAdd(&ctr->n_word, nint);
+  if (vec) {
+    unsigned base = before[0] + excl;
+    const unsigned wl0 = threadIdx.x * CS_ITEMS;
+#pragma unroll
+    for (int q = 0; q < CS_ITEMS; ++q)
+      if ((m4 >> q) & 1u) s_list[base++] = (unsigned short)(wl0 + q);
+  } else {
+#pragma unroll
+    for (int q = 0; q < CS_ITEMS; ++q)
+      if ((mq[q] >> lane) & 1u)
+        s_list[before[q] + __popc(mq[q] & ((1u << lane) - 1u))] = (unsigned short)((unsigned)q * CS_THREADS + threadIdx.x);
+  }
   __syncthreads();
   const unsigned b0 = s_base;
   for (unsigned q = threadIdx.x; q < nint; q += CS_THREADS)
@@ -467,7 +496,7 @@ struct CountBShared {
 
 template <typename T>
 __global__ void __launch_bounds__(CB_THREADS, 4) k_count_b(Grid<T> gin, unsigned word0, const uint32_t* __restrict__ wlist,
-                                                        unsigned cap_w, uint32_t* __restrict__ rec, uint2* __restrict__ wdir,
+                                                        unsigned cap_w, uint32_t* __restrict__ recc, uint2* __restrict__ wdir,
                                                         unsigned long long* __restrict__ own_id,
                                                         unsigned long long* __restrict__ own_rk,
                                                         unsigned long long* __restrict__ cell_id,
@@ -493,7 +522,7 @@ __global__ void __launch_bounds__(CB_THREADS, 4) k_count_b(Grid<T> gin, unsigned
   if (have) {
     gw = wlist[idx];
     g.word_coords(gw, i, j, w);
-    g.any_near = g.rowflag[(size_t)i * g.n1 + j];
+    g.any_near = g.near_word((unsigned)i * (unsigned)g.n1 + (unsigned)j, (unsigned)w);
     load_planes(g, g.bits, i, j, w, pl);
     owner_used(g, pl, i, j, w, x);
     unsigned v = 0;
@@ -524,10 +553,8 @@ __global__ void __launch_bounds__(CB_THREADS, 4) k_count_b(Grid<T> gin, unsigned
     }
     if (g.any_near) count_word_exact(g, pl, i, j, w, cells_ok, ncross, t, em);
     const uint32_t r = v | (t << 8);
-    if (r) {
-      rec[gw] = r;
-      atomicAdd(&tile_vt[(gw - word0) / CS_TILE], rec_vt(r));
-    }
+    recc[idx] = r;                                        // record of list entry idx (k_scan walks the list, not the words)
+    if (r) atomicAdd(&tile_vt[(gw - word0) / CS_TILE], rec_vt(r));
     if (v) wdir[gw] = dir_pack(x);
     if (gw >= emit_end) any = 0u;
     ncells += __popc(em);
@@ -664,46 +691,43 @@ __global__ void __launch_bounds__(1024) k_tile_scan3(unsigned long long* __restr
   }
 }
 
-// Stage 2b: offsets.  Every tile knows its exclusive prefix (k_count_b's last block): block scan of the per-word records
-// -> vbase[word] (first vertex id of the word), tbase[word] (first triangle of the word).
+// Stage 2b: offsets.  One warp per tile walks the tile's chunk of the interesting-word list (ascending words, k_count_a)
+// from the tile's exclusive prefix (k_tile_scan3): vbase[word] (first vertex id of the word), tbase[word] (first
+// triangle of the word) -- for interesting words only; nothing reads the others.  (A dense scan over all words read
+// and wrote 48 MB to serve the 10 % that matter.)
+constexpr int SCAN_WARPS = 8;
 template <typename T>
-__global__ void __launch_bounds__(CS_THREADS) k_scan(Grid<T> g, unsigned word0, unsigned nwords_scan,
-                                                  const uint32_t* __restrict__ rec,
-                                                  const unsigned long long* __restrict__ tile_vt,
-                                                  uint32_t* __restrict__ vbase, uint32_t* __restrict__ tbase, Counters* ctr) {
-  __shared__ unsigned long long s_warp[CS_THREADS / 32];
-  const int tile = (int)blockIdx.x;
-  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+__global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan(Grid<T> g, unsigned word0, int ntiles, const uint32_t* __restrict__ wlist,
+                                                         const uint32_t* __restrict__ recc, const uint2* __restrict__ tile_chunk,
+                                                         unsigned cap_w, const unsigned long long* __restrict__ tile_vt,
+                                                         uint32_t* __restrict__ vbase, uint32_t* __restrict__ tbase, Counters* ctr) {
+  const int tile = (int)(blockIdx.x * SCAN_WARPS + (threadIdx.x >> 5));
+  if (tile >= ntiles) return;
+  const unsigned lane = lane_id();
   const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
   const unsigned emit_end = (unsigned)g.i_hi * plane_words;
-  const unsigned rel0 = (unsigned)tile * CS_TILE + threadIdx.x * CS_ITEMS;    // thread t owns 4 consecutive words
-  unsigned long long item[CS_ITEMS], loc = 0;
-  if (rel0 + CS_ITEMS <= nwords_scan && ((word0 + rel0) & 3u) == 0) {
-    const uint4 r = *reinterpret_cast<const uint4*>(rec + word0 + rel0);
-    item[0] = rec_vt(r.x); item[1] = rec_vt(r.y); item[2] = rec_vt(r.z); item[3] = rec_vt(r.w);
-  } else {
-#pragma unroll
-    for (int it = 0; it < CS_ITEMS; ++it) item[it] = (rel0 + it < nwords_scan) ? rec_vt(rec[word0 + rel0 + it]) : 0ull;
-  }
-#pragma unroll
-  for (int it = 0; it < CS_ITEMS; ++it) loc += item[it];
-  const unsigned long long inc = warp_incl_scan_u64(loc);
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  unsigned long long woff = 0;
-#pragma unroll
-  for (int q = 0; q < CS_THREADS / 32; ++q)
-    if (q < (int)warp) woff += s_warp[q];
-  unsigned long long run = tile_vt[tile] + woff + inc - loc;
-#pragma unroll
-  for (int it = 0; it < CS_ITEMS; ++it) {
-    if (rel0 + it < nwords_scan) {
-      const uint32_t vb = (uint32_t)(run & 0x7fffffffull);
-      vbase[word0 + rel0 + it] = vb;
-      tbase[word0 + rel0 + it] = (uint32_t)(run >> 31);
-      if (g.i_hiv > g.i_hi && word0 + rel0 + it == emit_end) ctr->v_emit = vb;
+  const bool want_vemit = g.i_hiv > g.i_hi && (emit_end - word0) / CS_TILE == (unsigned)tile;
+  const uint2 ch = tile_chunk[tile];
+  unsigned long long run = tile_vt[tile];
+  unsigned long long below = 0;                        // records of this tile's words in front of emit_end
+  for (unsigned q0 = 0; q0 < ch.y; q0 += 32) {
+    const unsigned q = q0 + lane;
+    const bool have = q < ch.y && ch.x + q < cap_w;
+    const unsigned gw = have ? wlist[ch.x + q] : 0u;
+    const unsigned long long item = have ? rec_vt(recc[ch.x + q]) : 0ull;
+    const unsigned long long inc = warp_incl_scan_u64(item);
+    if (have) {
+      const unsigned long long mine = run + inc - item;
+      vbase[gw] = (uint32_t)(mine & 0x7fffffffull);
+      tbase[gw] = (uint32_t)(mine >> 31);
+      if (want_vemit && gw < emit_end) below += item;
     }
-    run += item[it];
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (want_vemit) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if (lane == 0) ctr->v_emit = (tile_vt[tile] + below) & 0x7fffffffull;
   }
 }
 
@@ -905,8 +929,11 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsig
                                                           const uint2* __restrict__ wdir, const uint32_t* __restrict__ vox_tab,
                                                           int* __restrict__ tris) {
   const unsigned n_cells = min(ctr->n_cell, cap_cell);
-  __shared__ unsigned s_ids[19][ET_THREADS];
-  __shared__ int s_stage[ET_THREADS / 32][32 * 12 * 3];   // a warp's triangles (contiguous in the output), written out coalesced
+  // per warp: the 19 edge ids of its 32 voxels (row stride 33: a round of the write-out below reads arbitrary
+  // (edge, voxel) pairs, and with stride 32 all the edges of one voxel share a bank), and the voxel of each of the
+  // warp's triangles
+  __shared__ unsigned s_ids[ET_THREADS / 32][19 * 33];
+  __shared__ uint8_t s_own[ET_THREADS / 32][32 * 12];
   unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned warp_first = a - (threadIdx.x & 31u);
   if (warp_first >= n_cells) return;                  // warp-uniform
@@ -918,7 +945,7 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsig
   const unsigned uW = (unsigned)g.W, plane_words = (unsigned)g.n1 * uW;
   const unsigned row = g.divW.div(gw0);
   const unsigned w = gw0 - row * uW;
-  const bool near = g.rowflag[row] != 0;
+  const bool near = g.near_word(row, w) != 0;
   // the voxel's 2x2 rows: word w (P) and the same rows shifted by one sample in k (S)
   const bool next_ok = (w + 1 < uW);
   const unsigned wi[4] = {gw0, gw0 + uW, gw0 + plane_words, gw0 + plane_words + uW};
@@ -970,68 +997,57 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsig
     unsigned id;
     if (s & 1) id = vb1[ab] + dir_base(dp1[ab], d - 1) + __popc(X[ab][d - 1] & below1);
     else id = vb[ab] + dir_base(dp[ab], d - 1) + __popc(X[ab][d - 1] & below);
-    s_ids[e][threadIdx.x] = id;
+    s_ids[threadIdx.x >> 5][e * 33 + (threadIdx.x & 31u)] = id;
   }
-  // 4-byte stores of a lane's own triangles would each be a partial-sector write (16 sectors per store instruction):
-  // the warp's triangles are contiguous in the output, so they are staged in shared memory and written out coalesced
+  // Triangles.  vox_tab[c8]: 12 triangles (3 edge slots x 5 bits each) of the voxel with ALL its mixed tets emitting,
+  // then (that tet mask | triangle count << 8).  A lane that wrote its own voxel's triangles would run as long as the
+  // warp's busiest voxel (2..12 triangles) and store 4 bytes at a time; instead the warp's triangles are dealt out one
+  // per lane per round: each voxel marks its triangles with its lane in shared memory, then lane q of a round takes
+  // triangle q -- its voxel from the mark, its row of the table, three ids from s_ids -- and writes it where the scan
+  // put it (tbase[word] + offset in the word + index in the voxel): no assumption about the order of the list.
   const unsigned o = valid ? tbase[gw0] + cell_toff[a] : 0u;       // cell_toff is relative to the word's first triangle
-  const unsigned lane = threadIdx.x & 31u;
-  int* stage = s_stage[threadIdx.x >> 5];
-  // vox_tab[c8]: 12 triangles (3 edge slots x 5 bits each) of the voxel with ALL its mixed tets emitting, then
-  // (that tet mask | triangle count << 8); a voxel that lost tets to the allclose rule takes the per-tet table
-  const uint32_t* tab = vox_tab + c8 * 13;
-  const uint32_t full = __ldg(tab + 12);
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned* ids = s_ids[warp];
+  const uint32_t full = __ldg(vox_tab + c8 * 13 + 12);
   const bool table_path = emit == (full & 63u);
-  unsigned nt = 0;
-  if (table_path) {
-    nt = full >> 8;
-  } else {
-    for (int t = 0; t < 6; ++t)
-      if ((emit >> t) & 1u) nt += c_tri_packed[t * 16 + tet_mask_of(c8, t)] & 3u;
-  }
-  // 4-byte stores of a lane's own triangles would each be a partial-sector write (16 sectors per store instruction).
-  // Entries of one list round are in voxel order, so a warp's triangles are usually contiguous in the output: then
-  // they are staged in shared memory and written out coalesced; a warp that straddles two rounds writes directly.
-  const unsigned last = min(31u, n_cells - 1u - warp_first);
-  const unsigned prev_end = __shfl_up_sync(0xffffffffu, o + nt, 1);
-  const bool contiguous = __all_sync(0xffffffffu, lane == 0 || lane > last || prev_end == o);
-  const unsigned first = __shfl_sync(0xffffffffu, o, 0);
-  const unsigned end = __shfl_sync(0xffffffffu, o + nt, (int)last);
-  if (valid && nt) {
-    int* dst = contiguous ? stage + (size_t)(o - first) * 3 : tris + (size_t)o * 3;
-    const bool fits = contiguous || (size_t)o + nt <= (size_t)cap_t;
-    if (fits) {
-      if (table_path) {
-        for (unsigned t = 0; t < nt; ++t, dst += 3) {
-          const uint32_t e = __ldg(tab + t);
-          dst[0] = (int)s_ids[e & 31u][threadIdx.x];
-          dst[1] = (int)s_ids[(e >> 5) & 31u][threadIdx.x];
-          dst[2] = (int)s_ids[(e >> 10) & 31u][threadIdx.x];
-        }
-      } else {
-        for (int t = 0; t < 6; ++t) {
-          if (!((emit >> t) & 1u)) continue;
-          const uint32_t e = c_tri_packed[t * 16 + tet_mask_of(c8, t)];
-          dst[0] = (int)s_ids[(e >> 2) & 31u][threadIdx.x];
-          dst[1] = (int)s_ids[(e >> 7) & 31u][threadIdx.x];
-          dst[2] = (int)s_ids[(e >> 12) & 31u][threadIdx.x];
-          if ((e & 3u) == 2u) {
-            dst[3] = (int)s_ids[(e >> 17) & 31u][threadIdx.x];
-            dst[4] = (int)s_ids[(e >> 22) & 31u][threadIdx.x];
-            dst[5] = (int)s_ids[(e >> 27) & 31u][threadIdx.x];
-          }
-          dst += (e & 3u) * 3;
-        }
+  const unsigned nt = (valid && table_path) ? full >> 8 : 0u;
+  if (valid && !table_path) {
+    // a voxel that lost tets to the allclose rule (rare): per-tet table, written by its own lane
+    unsigned tri = o;
+    for (int t = 0; t < 6; ++t) {
+      if (!((emit >> t) & 1u)) continue;
+      const uint32_t e = c_tri_packed[t * 16 + tet_mask_of(c8, t)];
+      for (unsigned h = 0; h < (e & 3u); ++h, ++tri) {
+        if (tri >= cap_t) break;
+        int* dst = tris + (size_t)tri * 3;
+        dst[0] = (int)ids[((e >> (2 + 15 * h)) & 31u) * 33 + lane];
+        dst[1] = (int)ids[((e >> (7 + 15 * h)) & 31u) * 33 + lane];
+        dst[2] = (int)ids[((e >> (12 + 15 * h)) & 31u) * 33 + lane];
       }
     }
   }
-  if (contiguous) {
-    __syncwarp();
-    const size_t gbase = (size_t)first * 3, gcap = (size_t)cap_t * 3;
-    unsigned nint = (end - first) * 3u;
-    if (gbase + nint > gcap) nint = gbase < gcap ? (unsigned)(gcap - gbase) : 0u;
-    int* out = tris + gbase;
-    for (unsigned q = lane; q < nint; q += 32) out[q] = stage[q];
+  const unsigned inc = warp_incl_scan_u32(nt);
+  const unsigned first = inc - nt;
+  const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
+  uint8_t* own = s_own[warp];
+  for (unsigned t = 0; t < nt; ++t) own[first + t] = (uint8_t)lane;
+  __syncwarp();
+  for (unsigned q0 = 0; q0 < total; q0 += 32) {
+    const unsigned q = q0 + lane;
+    const bool act = q < total;
+    const unsigned l = act ? own[q] : 0u;
+    const unsigned l_first = __shfl_sync(0xffffffffu, first, l);
+    const unsigned l_o = __shfl_sync(0xffffffffu, o, l);
+    const unsigned l_c8 = __shfl_sync(0xffffffffu, c8, l);
+    if (!act) continue;
+    const unsigned t = q - l_first;
+    const size_t tri = (size_t)l_o + t;
+    if (tri >= (size_t)cap_t) continue;
+    const uint32_t e = __ldg(vox_tab + l_c8 * 13 + t);
+    int* dst = tris + tri * 3;
+    dst[0] = (int)ids[(e & 31u) * 33 + l];
+    dst[1] = (int)ids[((e >> 5) & 31u) * 33 + l];
+    dst[2] = (int)ids[((e >> 10) & 31u) * 33 + l];
   }
 }
 
@@ -1058,7 +1074,8 @@ __global__ void __launch_bounds__(256) k_codes(Grid<T> g, const unsigned long lo
 }
 
 // one launch instead of four memsets / copies in front of every run
-__global__ void k_reset3(Counters* ctr, uint4* rowflag16, size_t n16, unsigned long long* tile_state, size_t ntile) {
+__global__ void k_reset3(Counters* ctr, uint4* rowflag16, size_t n16, uint4* wordflag16, size_t nw16,
+                         unsigned long long* tile_state, size_t ntile) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)gridDim.x * blockDim.x;
   if (t == 0) {
     Counters c;
@@ -1067,6 +1084,7 @@ __global__ void k_reset3(Counters* ctr, uint4* rowflag16, size_t n16, unsigned l
     *ctr = c;
   }
   for (size_t q = t; q < n16; q += n) rowflag16[q] = make_uint4(0u, 0u, 0u, 0u);
+  for (size_t q = t; q < nw16; q += n) wordflag16[q] = make_uint4(0u, 0u, 0u, 0u);
   for (size_t q = t; q < ntile; q += n) tile_state[q] = 0ull;
 }
 
@@ -1162,7 +1180,6 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
   if ((rc = ctr_ensure(ctx, ctx->bits, (size_t)(nwords + 4) * 4))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->nbits, (size_t)(nwords + 4) * 4))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->vbase, (size_t)(nwords + 4) * 4))) return rc;
-  if ((rc = ctr_ensure(ctx, ctx->tbase, (size_t)(nwords + 4) * 4))) return rc;     // per-word scan records
   if ((rc = ctr_ensure(ctx, ctx->wmask, (size_t)(nwords + 4) * 4))) return rc;     // tbase: first triangle of each word
   if ((rc = ctr_ensure(ctx, ctx->wdir, (size_t)(nwords + 4) * 8))) return rc;      // per-direction vertex prefix of interesting words
   if (!ctx->vox_tab.p) {
@@ -1188,11 +1205,14 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
   }
   if ((rc = ctr_ensure(ctx, ctx->counters, sizeof(Counters)))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->aux[4], (size_t)nrows + 32))) return rc;
+  if ((rc = ctr_ensure(ctx, ctx->aux[32], (size_t)nrows * 4 + 64))) return rc;      // word-level near flags
   if ((rc = ctr_ensure(ctx, ctx->tile_state, (size_t)ntiles * 16 + 16))) return rc;
   if (!ctx->counters_host) CTR_CUDA(ctx, cudaMallocHost(&ctx->counters_host, 256));
   g.bits = (const uint32_t*)ctx->bits.p;
   g.nbits = (const uint32_t*)ctx->nbits.p;
   g.rowflag = (const uint8_t*)ctx->aux[4].p;
+  g.wordflag = (const uint32_t*)ctx->aux[32].p;
+  g.wdiv = (W + 31) / 32;
   Counters* dctr = (Counters*)ctx->counters.p;
   unsigned long long* st_vt = (unsigned long long*)ctx->tile_state.p;
 
@@ -1227,6 +1247,8 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
     if ((rc = ctr_ensure(ctx, b_cell_id, ctx->spec_cell * 8, true))) return rc;
     if ((rc = ctr_ensure(ctx, b_cell_toff, ctx->spec_cell * 4, true))) return rc;
     if ((rc = ctr_ensure(ctx, ctx->wlist, ctx->spec_w * 4, true))) return rc;
+    if ((rc = ctr_ensure(ctx, ctx->aux[33], ctx->spec_w * 4, true))) return rc;                 // records of the listed words
+    if ((rc = ctr_ensure(ctx, ctx->aux[34], (size_t)ntiles * 8 + 16))) return rc;               // (first entry, entries) per tile
     if (geom) {
       if ((rc = ctr_ensure(ctx, ctx->verts, ctx->spec_v * 3 * gsz, true))) return rc;
       if (want_n && (rc = ctr_ensure(ctx, ctx->normals, ctx->spec_v * 3 * gsz, true))) return rc;
@@ -1241,24 +1263,25 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
     const unsigned cap_w = (unsigned)std::min<size_t>(ctx->spec_w, 0x7fffffffu);
 
     if (!(phase == 2 && attempt == 0)) {                 // phase 2: attempt 0 was enqueued by phase 1
-    k_reset3<<<64, 256, 0, st>>>(dctr, (uint4*)ctx->aux[4].p, (size_t)(nrows + 15) / 16, st_vt, (size_t)ntiles);
+    k_reset3<<<64, 256, 0, st>>>(dctr, (uint4*)ctx->aux[4].p, (size_t)(nrows + 15) / 16, (uint4*)ctx->aux[32].p,
+                                 (size_t)(nrows + 3) / 4, st_vt, (size_t)ntiles);
     ctx->launches++;
     CTR_DBG(ctx, "k_reset3");
     if (p->flags & CTR_WANT_MINMAX)
       rc = launch_bitplane<T, true>(ctx, dfield, (unsigned)nrows, n2, W, n0, n1, p->isovalue, (uint32_t*)ctx->bits.p,
-                                    (uint32_t*)ctx->nbits.p, (uint8_t*)ctx->aux[4].p, (MinMaxKeys*)dctr, false);
+                                    (uint32_t*)ctx->nbits.p, (uint8_t*)ctx->aux[4].p, (MinMaxKeys*)dctr, false, (uint32_t*)ctx->aux[32].p);
     else
       rc = launch_bitplane<T, false>(ctx, dfield, (unsigned)nrows, n2, W, n0, n1, p->isovalue, (uint32_t*)ctx->bits.p,
-                                     (uint32_t*)ctx->nbits.p, (uint8_t*)ctx->aux[4].p, (MinMaxKeys*)dctr, false);
+                                     (uint32_t*)ctx->nbits.p, (uint8_t*)ctx->aux[4].p, (MinMaxKeys*)dctr, false, (uint32_t*)ctx->aux[32].p);
     if (rc) return rc;
     CTR_DBG(ctx, "k_bitplane");
     ctr_stage_mark(ctx, 2);
     if (ntiles > 0) {
-      k_count_a<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (uint32_t*)ctx->tbase.p, (uint32_t*)ctx->wlist.p, cap_w, dctr);
+      k_count_a<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (uint32_t*)ctx->wlist.p, (uint2*)ctx->aux[34].p, cap_w, dctr);
       CTR_DBG(ctx, "k_count_a");
       // the grid covers the expected list length (last run's, with head-room); blocks past the real length only take a ticket
       const unsigned wb = (unsigned)((std::min<size_t>(cap_w, ctx->last_w + ctx->last_w / 8 + 4096) + CB_THREADS - 1) / CB_THREADS);
-      k_count_b<T><<<wb, CB_THREADS, 0, st>>>(g, word0, (const uint32_t*)ctx->wlist.p, cap_w, (uint32_t*)ctx->tbase.p,
+      k_count_b<T><<<wb, CB_THREADS, 0, st>>>(g, word0, (const uint32_t*)ctx->wlist.p, cap_w, (uint32_t*)ctx->aux[33].p,
                                               (uint2*)ctx->wdir.p, (unsigned long long*)b_own_id.p,
                                               (unsigned long long*)b_own_voff.p, (unsigned long long*)b_cell_id.p,
                                               (uint32_t*)b_cell_toff.p, cap_own, cap_cell, st_vt, dctr, ntiles);
@@ -1266,8 +1289,9 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
       ctx->launches += 3;
       ctx->cover_w = (size_t)wb * CB_THREADS;
       CTR_DBG(ctx, "k_count_b");
-      k_scan<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (const uint32_t*)ctx->tbase.p, st_vt, (uint32_t*)ctx->vbase.p,
-                                               (uint32_t*)ctx->wmask.p, dctr);
+      k_scan<T><<<(ntiles + SCAN_WARPS - 1) / SCAN_WARPS, SCAN_WARPS * 32, 0, st>>>(
+          g, word0, ntiles, (const uint32_t*)ctx->wlist.p, (const uint32_t*)ctx->aux[33].p, (const uint2*)ctx->aux[34].p, cap_w,
+          st_vt, (uint32_t*)ctx->vbase.p, (uint32_t*)ctx->wmask.p, dctr);
       ctx->launches++;
       CTR_DBG(ctx, "k_scan");
     }
@@ -1379,6 +1403,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
 }
 
 #include "mt3d_select.cuh"
+#include "mt3d_clean.cuh"
 
 }  // namespace
 
@@ -1495,4 +1520,27 @@ extern "C" int ctr_mt3d_select_seeded(ctr_ctx* ctx, const int32_t* seed_voxels, 
   CTR_CUDA(ctx, cudaSetDevice(ctx->device));
   if (p->dtype == CTR_F32) return select_typed<float>(ctx, p, seed_voxels, n_seeds, n_verts, n_tris, n_voxels);
   return select_typed<double>(ctx, p, seed_voxels, n_seeds, n_verts, n_tris, n_voxels);
+}
+
+extern "C" int ctr_mt3d_clean(ctr_ctx* ctx, const ctr_clean_params* cp, ctr_clean_counts* out) {
+  if (!ctx) return CTR_ERR_BAD_ARG;
+  if (!cp || !out) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "null argument");
+  memset(out, 0, sizeof *out);
+  if (ctx->last_kind != 3 || (ctx->last_flags & CTR_NO_GEOMETRY))
+    return ctr_fail(ctx, CTR_ERR_STATE, "no completed ctr_mt3d_run with geometry to clean");
+  if (ctx->last3_edited & 2u) return ctr_fail(ctx, CTR_ERR_STATE, "the mesh of this run has already been cleaned");
+  const ctr_mt3d_params* p = (const ctr_mt3d_params*)ctx->last3_params;
+  if (p->i_lo != 0 || p->i_hi != p->n0 || p->vert_id_base != 0)
+    return ctr_fail(ctx, CTR_ERR_UNSUPPORTED, "mesh clean-up needs a full-volume run (merges cross slab faces)");
+  for (int a = 0; a < 3; ++a) {
+    if (p->origin[a] != 0.0 || p->delta[a] != 1.0)
+      return ctr_fail(ctx, CTR_ERR_STATE, "mesh clean-up works in grid coordinates: run with origin 0, delta 1 and pass the transform here");
+    if (cp->corner[a] < 1) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "corner must be >= 1 on every axis");
+    if (cp->delta[a] == 0.0) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "delta must be non-zero");
+  }
+  if (cp->divisions < 1 || cp->divisions >= (1 << 21)) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "divisions must be in [1, 2^21)");
+  if (!(cp->epsilon == cp->epsilon)) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "epsilon is NaN");
+  CTR_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->last_flags & CTR_GEOM_F64) return clean_typed<double>(ctx, cp, out);
+  return clean_typed<float>(ctx, cp, out);
 }

@@ -233,6 +233,8 @@ int select_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, const int32_t* seeds, i
   g.bits = (const uint32_t*)ctx->bits.p;
   g.nbits = (const uint32_t*)ctx->nbits.p;
   g.rowflag = (const uint8_t*)ctx->aux[4].p;
+  g.wordflag = (const uint32_t*)ctx->aux[32].p;
+  g.wdiv = (W + 31) / 32;
   const unsigned nV = (unsigned)ctx->last_counts[0], nT = (unsigned)ctx->last_counts[1];
   const unsigned n_cell = (unsigned)ctx->last_cell;
   const uint32_t fl = p->flags;

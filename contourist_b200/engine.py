@@ -34,6 +34,17 @@ class Mt3dParams(ctypes.Structure):
                 ("vert_id_base", ctypes.c_int64)]
 
 
+class CleanParams(ctypes.Structure):
+    _fields_ = [("corner", ctypes.c_int64 * 3), ("divisions", ctypes.c_int32), ("flags", ctypes.c_uint32),
+                ("epsilon", ctypes.c_double), ("origin", ctypes.c_double * 3), ("delta", ctypes.c_double * 3)]
+
+
+class CleanCounts(ctypes.Structure):
+    _fields_ = [("n_verts", ctypes.c_int64), ("n_tris", ctypes.c_int64), ("n_quantized", ctypes.c_int64),
+                ("n_tiny", ctypes.c_int64), ("n_flat", ctypes.c_int64), ("n_components", ctypes.c_int64),
+                ("n_flipped", ctypes.c_int64)]
+
+
 class Mt3dCounts(ctypes.Structure):
     _fields_ = [("n_verts", ctypes.c_int64), ("n_tris", ctypes.c_int64), ("n_active_cells", ctypes.c_int64),
                 ("n_crossings", ctypes.c_int64), ("n_codes", ctypes.c_int64),
@@ -82,6 +93,8 @@ def load_library():
     lib.ctr_mt3d_orient_reference.restype = i32
     lib.ctr_mt3d_select_seeded.argtypes = [vp, vp, i64, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.ctr_mt3d_select_seeded.restype = i32
+    lib.ctr_mt3d_clean.argtypes = [vp, ctypes.POINTER(CleanParams), ctypes.POINTER(CleanCounts)]
+    lib.ctr_mt3d_clean.restype = i32
     lib.ctr_host_alloc.argtypes = [vp, ctypes.c_uint64, ctypes.POINTER(vp)]
     lib.ctr_host_alloc.restype = i32
     lib.ctr_host_free.argtypes = [vp, vp]
@@ -113,6 +126,7 @@ class Engine(object):
                 device, rc, self.lib.ctr_last_error(None).decode()))
         self.h = h
         self.device = device
+        self.run_serial = 0           # bumped by every call that replaces or rewrites the device results
 
     def close(self):
         if getattr(self, "h", None):
@@ -209,6 +223,7 @@ class Engine(object):
         (then pass shape, dtype and FIELD_ON_DEVICE).  Returns Mt3dCounts."""
         p, flags = self._mt3d_params(field, value, origin, delta, flags, i_lo, i_hi, plane_offset, shape, dtype, vert_id_base)
         c = Mt3dCounts()
+        self.run_serial += 1
         self._check(self.lib.ctr_mt3d_run(self.h, ctypes.byref(p), ctypes.byref(c)), "ctr_mt3d_run")
         self._last3 = (flags, c)
         return c
@@ -217,6 +232,7 @@ class Engine(object):
                      i_lo=0, i_hi=None, plane_offset=0, shape=None, dtype=None, vert_id_base=0):
         """Queue an extraction on the stream and return at once; mt3d_finish() waits for it and returns the counts."""
         p, flags = self._mt3d_params(field, value, origin, delta, flags, i_lo, i_hi, plane_offset, shape, dtype, vert_id_base)
+        self.run_serial += 1
         self._check(self.lib.ctr_mt3d_enqueue(self.h, ctypes.byref(p)), "ctr_mt3d_enqueue")
         self._pending3 = flags
 
@@ -230,6 +246,7 @@ class Engine(object):
         """Rewind the last run's device triangles with the reference's outward rule (surface_geometry.py:52-140);
         returns (components, triangles reversed).  Fetch afterwards."""
         nc, nf = ctypes.c_int64(), ctypes.c_int64()
+        self.run_serial += 1
         self._check(self.lib.ctr_mt3d_orient_reference(self.h, ctypes.byref(nc), ctypes.byref(nf)), "ctr_mt3d_orient_reference")
         return int(nc.value), int(nf.value)
 
@@ -239,6 +256,7 @@ class Engine(object):
         Returns (n_verts, n_tris, emitting voxels selected); fetch afterwards."""
         sv = np.ascontiguousarray(np.asarray(start_voxels, dtype=np.int32).reshape(-1, 3))
         nv, nt, nc = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        self.run_serial += 1
         self._check(self.lib.ctr_mt3d_select_seeded(self.h, _ptr(sv) if len(sv) else None, len(sv), ctypes.byref(nv),
                                                     ctypes.byref(nt), ctypes.byref(nc)), "ctr_mt3d_select_seeded")
         flags, c = self._last3
@@ -246,6 +264,29 @@ class Engine(object):
         c.n_verts, c.n_tris = int(nv.value), int(nt.value)             # what mt3d_fetch sizes its arrays from
         self._last3 = (flags, c)
         return int(nv.value), int(nt.value), int(nc.value)
+
+    def mt3d_clean(self, corner, origin=(0.0, 0.0, 0.0), delta=(1.0, 1.0, 1.0), divisions=10000, epsilon=1e-4, orient=False,
+                   triangles=True):
+        """The reference's post-processing of the last run's device mesh (tetrahedral.py:541-552: quantize, tiny, clean,
+        optionally the outward orientation, then grid -> world).  The run must have used origin 0 / delta 1; the
+        transform is applied here, last.  triangles=False skips clean_triangles (the reference's clean=False).
+        Returns CleanCounts; fetch afterwards."""
+        p = CleanParams()
+        for a in range(3):
+            p.corner[a] = int(corner[a])
+            p.origin[a] = float(origin[a])
+            p.delta[a] = float(delta[a])
+        p.divisions = int(divisions)
+        p.epsilon = float(epsilon)
+        p.flags = (1 if orient else 0) | (0 if triangles else 2)
+        c = CleanCounts()
+        self.run_serial += 1
+        self._check(self.lib.ctr_mt3d_clean(self.h, ctypes.byref(p), ctypes.byref(c)), "ctr_mt3d_clean")
+        flags, c3 = self._last3
+        c3 = type(c3).from_buffer_copy(c3)
+        c3.n_verts, c3.n_tris = int(c.n_verts), int(c.n_tris)
+        self._last3 = (flags, c3)
+        return c
 
     def mt3d_fetch(self, verts=True, normals=None, tris=True, keys=None, codes=None, pinned=False):
         """Copy the last run's outputs to host arrays.  pinned=True: the arrays live in the engine's page-locked pool
@@ -392,6 +433,7 @@ class Engine(object):
         p.i_hi = int(p.n0 if i_hi is None else i_hi)
         p.row_offset = int(row_offset)
         c = Mt2dCounts()
+        self.run_serial += 1
         self._check(self.lib.ctr_mt2d_run(self.h, ctypes.byref(p), ctypes.byref(c)), "ctr_mt2d_run")
         self._last2 = (flags, c)
         return c
@@ -434,6 +476,7 @@ class Engine(object):
             p.delta[a] = float(delta[a])
         p.nbins = int(nbins)
         c = Mp4dCounts()
+        self.run_serial += 1
         self._check(self.lib.ctr_mp4d_run(self.h, ctypes.byref(p), ctypes.byref(c)), "ctr_mp4d_run")
         self._last4 = (flags, c, tuple(int(s) for s in shape))
         return c

@@ -13,9 +13,14 @@ extract_surface_geometry().  Differences, all documented in DESIGN.md section 2:
     ignored;
   * linear_interpolate=False (the callable evaluated off-grid) is not available: NotImplementedError;
   * points / triangles come back as numpy arrays (iterate / index them like the reference's lists);
-  * the reference's serial mesh post-processing (quantize, tiny, clean, global orientation) is replaced by the
-    engine's deterministic indexed mesh, wound towards the high side; `reference_orientation=True` adds the
-    reference's per-component outward flip.
+  * get_points_and_triangles() returns what the reference returns (tetrahedral.py:541-552): the raw mesh after
+    quantize_interpolations, remove_tiny_simplices, clean_triangles (when `clean`) and orient_triangles, all on the
+    device (`ctr_mt3d_clean`), in the deterministic form of those passes ("smallest vertex id survives" wherever
+    the reference depends on CPython dict / set order; oracle/post3d.py).  `post_process = False` on the maker
+    gives the engine's raw indexed mesh instead, wound towards the high side (`reference_orientation=True` adds the
+    reference's per-component outward flip to it);
+  * search_for_endpoints() already runs the extraction (the crossing scan is its first two stages);
+    get_points_and_triangles() then only post-processes and fetches that run.
 """
 import numpy as np
 
@@ -102,6 +107,10 @@ class GridContour3d(object):
     reference_orientation = False
     want_normals = False
     full_scan = False                                  # set by search_for_endpoints(): the seeds are every crossing
+    post_process = True                                # quantize / tiny / clean / orient like the reference
+    quantize_divisions = 10000                         # tetrahedral.py:190
+    tiny_epsilon = 1e-4                                # tetrahedral.py:353
+    prefetched = None                                  # (engine, run_serial, flags, counts) of a run search_for_endpoints() made
 
     def __init__(self, corner, function, value, segment_endpoints, linear_interpolate=True, callback=None,
                  origin=(0.0, 0.0, 0.0), delta=(1.0, 1.0, 1.0)):
@@ -141,13 +150,28 @@ class GridContour3d(object):
         eng = E.default_engine()
         flags = (E.GEOM_F64 if np.dtype(self.geometry_dtype) == np.float64 else 0) | (E.WANT_NORMALS if self.want_normals else 0)
         field = self._field()
-        self.counts = eng.mt3d_run(field, self.value, origin=self.origin, delta=self.delta, flags=flags)
+        identity = tuple(float(x) for x in self.origin) == (0.0, 0.0, 0.0) and tuple(float(x) for x in self.delta) == (1.0, 1.0, 1.0)
+        # with post-processing the run is made in grid coordinates and ctr_mt3d_clean applies the transform last, like
+        # the reference (tetrahedral.py:86-90)
+        run_origin, run_delta = ((0.0, 0.0, 0.0), (1.0, 1.0, 1.0)) if self.post_process else (self.origin, self.delta)
+        pre = self.prefetched
+        self.prefetched = None
+        if (pre is not None and pre[0] is eng and pre[1] == eng.run_serial and (pre[2] & flags) == flags and
+                (pre[2] & E.GEOM_F64) == (flags & E.GEOM_F64) and (self.post_process or identity)):
+            self.counts = pre[3]                          # search_for_endpoints() made this very run: nothing to redo
+        else:
+            self.counts = eng.mt3d_run(field, self.value, origin=run_origin, delta=run_delta, flags=flags)
         if not self.full_scan and self.end_points is not None:
             # seeded tracking: only what the flood fill reaches from the seeds' start voxels (no seeds: nothing)
             self.start_voxels = initial_voxels(field, self.value, self.end_points) if len(self.end_points) else \
                 np.zeros((0, 3), np.int32)
             self.selected = eng.mt3d_select_seeded(self.start_voxels)
-        if self.reference_orientation:
+        if self.post_process:
+            # tetrahedral.py:541-552 on the device mesh: quantize, tiny, clean (if asked), orient, grid -> world
+            self.cleaned = eng.mt3d_clean(self.corner, origin=self.origin, delta=self.delta, divisions=self.quantize_divisions,
+                                          epsilon=self.tiny_epsilon, orient=True, triangles=bool(clean))
+            self.components, self.flipped = int(self.cleaned.n_components), int(self.cleaned.n_flipped)
+        elif self.reference_orientation:
             # surface_geometry.py:52-140 on the device mesh: one keep / reverse decision per edge-connected component
             self.components, self.flipped = eng.mt3d_orient_reference()
         out = eng.mt3d_fetch()
@@ -160,9 +184,10 @@ class GridContour3d(object):
     def extract_surface_geometry(self, clean=True):
         points, triangles = self.get_points_and_triangles(clean)
         geometry = surface_geometry.SurfaceGeometry(points, triangles)
-        if clean:
-            geometry.clean_triangles()
-        geometry.orient_triangles()
+        if not self.post_process:
+            if clean:
+                geometry.clean_triangles()
+            geometry.orient_triangles()
         return geometry
 
 
@@ -197,6 +222,15 @@ class Delta3DContour(object):
         maker.flatten = self.flatten
         maker.smooth = self.smooth
         maker.full_scan = True      # this facade only ever passes the complete seed set (triangulated.py:96 at HEAD)
+        maker.prefetched = getattr(grid_endpoints, "engine_run", None)
+        return self._configure(maker)
+
+    def _configure(self, maker):
+        "options set on this driver (before or after the maker was built) reach the maker"
+        for name in ("post_process", "geometry_dtype", "want_normals", "reference_orientation", "quantize_divisions",
+                     "tiny_epsilon"):
+            if hasattr(self, name):
+                setattr(maker, name, getattr(self, name))
         return maker
 
     def search_for_endpoints(self, skip=1):
@@ -206,7 +240,7 @@ class Delta3DContour(object):
 
     def get_points_and_triangles(self):
         # the engine applies grid_field.from_grid_coordinates (x*delta + mins) on the device
-        return self.contour_maker.get_points_and_triangles()
+        return self._configure(self.contour_maker).get_points_and_triangles()
 
 
 class TriangulatedIsosurfaces(Delta3DContour):

@@ -151,6 +151,32 @@ CTR_API int ctr_mt3d_orient_reference(ctr_ctx* ctx, int64_t* n_components, int64
 CTR_API int ctr_mt3d_select_seeded(ctr_ctx* ctx, const int32_t* seed_voxels, int64_t n_seeds, int64_t* n_verts,
                                    int64_t* n_tris, int64_t* n_voxels);
 
+/* The reference's mesh post-processing on the device mesh of the LAST ctr_mt3d_run:
+ *   tetrahedral.py:190-215     quantize_interpolations(divisions)   vertices in one cell of the divisions grid merge
+ *   tetrahedral.py:353-375     remove_tiny_simplices(epsilon)       tiny simplices collapse to a point and go
+ *   surface_geometry.py:14-50  clean_triangles                      zero-area triangles go, their coincident vertices merge
+ *   surface_geometry.py:52-140 orient_triangles (CTR_CLEAN_ORIENT)  = ctr_mt3d_orient_reference, in grid coordinates
+ *   grid_field.py:89-93        from_grid_coordinates                x * delta + origin, applied last (tetrahedral.py:86-90)
+ * which is what GridContour3d.get_points_and_triangles(clean=True) returns (tetrahedral.py:541-552).  The run must have
+ * been made in GRID coordinates (origin 0, delta 1), over the full volume, with vert_id_base 0.  Where the reference's
+ * result depends on CPython dict / set order the vertex of smallest id survives (oracle/post3d.py states the rules).
+ * Vertices, normals, keys and triangles are compacted in place (order kept); fetch afterwards.  One-shot per run.  */
+#define CTR_CLEAN_ORIENT 1u        /* run the orientation pass before the transform                         */
+#define CTR_CLEAN_NO_TRIANGLES 2u  /* skip clean_triangles (get_points_and_triangles(clean=False))          */
+typedef struct {
+  int64_t corner[3];       /* grid dimensions N (voxels per axis) = n - 1: self.corner of the reference            */
+  int32_t divisions;       /* 10000 in the reference; < 2^21                                                        */
+  uint32_t flags;          /* CTR_CLEAN_ORIENT, CTR_CLEAN_NO_TRIANGLES                                              */
+  double epsilon;          /* 1e-4 in the reference                                                                 */
+  double origin[3], delta[3];
+} ctr_clean_params;
+typedef struct {
+  int64_t n_verts, n_tris;           /* final mesh                                                                  */
+  int64_t n_quantized, n_tiny, n_flat;   /* triangles removed by each pass                                          */
+  int64_t n_components, n_flipped;   /* of the orientation pass (CTR_CLEAN_ORIENT)                                  */
+} ctr_clean_counts;
+CTR_API int ctr_mt3d_clean(ctr_ctx* ctx, const ctr_clean_params* params, ctr_clean_counts* out);
+
 /* ---- 2D marching triangles, all levels in one pass ------------------------------------------------
  * Replaces, for an array-backed field, the reference's
  *   multiple_2d_contour.py:63-75 + :50-61  search_grid_for_crossings / classify_endpoint_values

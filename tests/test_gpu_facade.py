@@ -38,6 +38,7 @@ def test_isosurface_facade_equals_oracle_world_coords(engine):
     def f(x, y, z):
         return x * x + y * y + z * z + 0.1 * np.sin(5 * x)
     S = tetrahedral.TriangulatedIsosurfaces([-1] * 3, [1] * 3, [0.125] * 3, f, 0.5, [])
+    S.post_process = False                 # the raw engine mesh (the reference's post-processing: tests/test_gpu_post3d.py)
     S.search_for_endpoints()
     pts, tris = S.get_points_and_triangles()
     arr = S.grid.samples(1)
@@ -69,6 +70,7 @@ def test_reference_orientation_matches_reference_on_golden_sphere(engine):
     from contourist_b200 import tetrahedral
     g = np.load(os.path.join(GOLDEN, "mt3d_sphere13.npz"))
     G = tetrahedral.Grid3DContour(12, 12, 12, g["field"], float(g["value"]), None)      # None: full scan
+    G.post_process = False
     G.reference_orientation = True
     pts, tris = G.get_points_and_triangles()
 
