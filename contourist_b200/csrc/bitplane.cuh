@@ -43,14 +43,14 @@ __device__ __forceinline__ unsigned long long order_key(double x) {
 // ------------------------------------------------------------------------------------------------
 struct RowGeom {
   uint8_t* rowflag;
-  uint32_t* wordflag;                      // optional (3D): per row, one bit per group of `wdiv` words, see flag_rows
+  uint32_t* wordflag;                      // optional (3D): per row, one bit per group of 2^wshift words, see flag_rows
   FastDiv divW, divRc, divRb;
   int rb, rc;                              // row = (a*rb + b)*rc + c   (3D: a = 0, b = i, c = j)
-  int W, wdiv;
+  int W, wshift;
 };
 
 // word `word` holds a near sample: flag every row whose 3x3(x3) row neighbourhood contains it.  The word flags say
-// where in those rows: bit (w / wdiv) for the words w-1, w, w+1 (an edge or voxel of word w-1 reaches sample 0 of
+// where in those rows: bit (w >> wshift) for the words w-1, w, w+1 (an edge or voxel of word w-1 reaches sample 0 of
 // word w; the exact paths of word w+1 look back at sample 31 of word w), so that later stages take their exact path
 // for 3 words of a flagged row, not for all of it.
 __device__ __noinline__ void flag_rows(const RowGeom& rg, unsigned word) {
@@ -60,7 +60,7 @@ __device__ __noinline__ void flag_rows(const RowGeom& rg, unsigned word) {
   uint32_t m = 0;
   if (rg.wordflag) {
     const int w = (int)(word - row * (unsigned)rg.W);
-    for (int q = max(w - 1, 0); q <= min(w + 1, rg.W - 1); ++q) m |= 1u << (q / rg.wdiv);
+    for (int q = max(w - 1, 0); q <= min(w + 1, rg.W - 1); ++q) m |= 1u << (q >> rg.wshift);
   }
   for (int da = 0; da < 3; ++da)
     for (int db = 0; db < 3; ++db)
@@ -412,7 +412,8 @@ int launch_bitplane(ctr_ctx* ctx, const T* dfield, unsigned nrows, int n2, int W
   rg.rowflag = rowflag;
   rg.wordflag = wordflag;
   rg.W = W;
-  rg.wdiv = (W + 31) / 32;
+  rg.wshift = 0;
+  while ((W >> rg.wshift) > 32) ++rg.wshift;
   rg.divW.init((unsigned)W);
   rg.divRc.init((unsigned)rc);
   rg.divRb.init((unsigned)rb);

@@ -71,11 +71,15 @@ struct Grid {
   // conservative allclose hull; kernels copy it into any_near before touching a word of row (i, j).
   int any_near;
   const uint8_t* rowflag;
-  const uint32_t* wordflag;          // per row: bit (w / wdiv) set iff some near sample within rows +-2 and words w-1..w+1
-  int wdiv;
-  __device__ __forceinline__ int near_word(unsigned row, unsigned w) const {
-    return (int)((wordflag[row] >> (w / (unsigned)wdiv)) & 1u);
-  }
+  // per row, one bit per group of 2^wshift words (a group = one word up to 1024 samples per row):
+  //   wordflag  : some near sample within rows +-2 and words w-1..w+1 (stage 1) -> stage 2 looks at the near plane;
+  //   exactflag : the exact used-edge words of some word among rows (i..i+1, j..j+1) of this group differ from the
+  //               plain crossing words (stage 2) -> stage 4 recomputes them exactly.  Practically never set.
+  const uint32_t* wordflag;
+  uint32_t* exactflag;
+  int wshift;
+  __device__ __forceinline__ int near_word(unsigned row, unsigned w) const { return (int)((wordflag[row] >> (w >> wshift)) & 1u); }
+  __device__ __forceinline__ int exact_word(unsigned row, unsigned w) const { return (int)((exactflag[row] >> (w >> wshift)) & 1u); }
   FastDiv divW, divN1;
   __device__ __forceinline__ void word_coords(unsigned gw, int& i, int& j, int& w) const {
     unsigned row = divW.div(gw);
@@ -486,6 +490,31 @@ __global__ void __launch_bounds__(CS_THREADS) k_count_a(Grid<T> g, unsigned word
     if (b0 + q < cap_w) wlist[b0 + q] = word0 + tile0 + s_list[q];
 }
 
+// The word flag of stage 1 is dilated; every exact path of stage 2 starts from the near bits of the eight words a word
+// touches, so without any of those the plain bit logic is already exact.
+template <typename T>
+__device__ __noinline__ int near_bits_around(const Grid<T>& g, int i, int j, int w, uint32_t kpt) {
+  Planes npl;
+  load_planes(g, g.nbits, i, j, w, npl);
+  return ((npl.P[0] | npl.P[1] | npl.P[2] | npl.P[3] | npl.S[0] | npl.S[1] | npl.S[2] | npl.S[3]) & kpt) != 0u;
+}
+
+// Exact used-edge words that differ from the crossing words: stage 4 ranks the edges of rows (i..i+1, j..j+1) by these
+// words, so the voxel rows that read this one are told to recompute them exactly.
+template <typename T>
+__device__ __noinline__ void flag_exact_words(const Grid<T>& g, const Planes& pl, int i, int j, int w, const uint32_t x[7]) {
+  uint32_t xs[7];
+  cross_words(pl, xs);
+  uint32_t dif = 0;
+#pragma unroll
+  for (int d = 0; d < 7; ++d) dif |= xs[d] ^ x[d];
+  if (!dif) return;
+  const uint32_t m = 1u << ((unsigned)w >> g.wshift);
+  for (int di = 0; di < 2; ++di)
+    for (int dj = 0; dj < 2; ++dj)
+      if (i - di >= 0 && j - dj >= 0) atomicOr(&g.exactflag[(size_t)(i - di) * g.n1 + (j - dj)], m);
+}
+
 constexpr int CB_THREADS = 256;                     // (128: 160 us for stage 2 instead of 153)
 
 struct CountBShared {
@@ -496,7 +525,7 @@ struct CountBShared {
 
 template <typename T>
 __global__ void __launch_bounds__(CB_THREADS, 4) k_count_b(Grid<T> gin, unsigned word0, const uint32_t* __restrict__ wlist,
-                                                        unsigned cap_w, uint32_t* __restrict__ recc, uint2* __restrict__ wdir,
+                                                        unsigned cap_w, uint32_t* __restrict__ recc, uint4* __restrict__ wrec,
                                                         unsigned long long* __restrict__ own_id,
                                                         unsigned long long* __restrict__ own_rk,
                                                         unsigned long long* __restrict__ cell_id,
@@ -524,7 +553,9 @@ __global__ void __launch_bounds__(CB_THREADS, 4) k_count_b(Grid<T> gin, unsigned
     g.word_coords(gw, i, j, w);
     g.any_near = g.near_word((unsigned)i * (unsigned)g.n1 + (unsigned)j, (unsigned)w);
     load_planes(g, g.bits, i, j, w, pl);
+    if (g.any_near) g.any_near = near_bits_around(g, i, j, w, pl.kpt);
     owner_used(g, pl, i, j, w, x);
+    if (g.any_near) flag_exact_words(g, pl, i, j, w, x);
     unsigned v = 0;
 #pragma unroll
     for (int d = 0; d < 7; ++d) {
@@ -555,7 +586,10 @@ __global__ void __launch_bounds__(CB_THREADS, 4) k_count_b(Grid<T> gin, unsigned
     const uint32_t r = v | (t << 8);
     recc[idx] = r;                                        // record of list entry idx (k_scan walks the list, not the words)
     if (r) atomicAdd(&tile_vt[(gw - word0) / CS_TILE], rec_vt(r));
-    if (v) wdir[gw] = dir_pack(x);
+    if (v) {
+      const uint2 dp = dir_pack(x);
+      *reinterpret_cast<uint2*>(&wrec[gw].z) = dp;        // (.x, .y) = (vbase, tbase): k_scan
+    }
     if (gw >= emit_end) any = 0u;
     ncells += __popc(em);
   }
@@ -700,7 +734,7 @@ template <typename T>
 __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan(Grid<T> g, unsigned word0, int ntiles, const uint32_t* __restrict__ wlist,
                                                          const uint32_t* __restrict__ recc, const uint2* __restrict__ tile_chunk,
                                                          unsigned cap_w, const unsigned long long* __restrict__ tile_vt,
-                                                         uint32_t* __restrict__ vbase, uint32_t* __restrict__ tbase, Counters* ctr) {
+                                                         uint4* __restrict__ wrec, Counters* ctr) {
   const int tile = (int)(blockIdx.x * SCAN_WARPS + (threadIdx.x >> 5));
   if (tile >= ntiles) return;
   const unsigned lane = lane_id();
@@ -718,8 +752,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan(Grid<T> g, unsigned wo
     const unsigned long long inc = warp_incl_scan_u64(item);
     if (have) {
       const unsigned long long mine = run + inc - item;
-      vbase[gw] = (uint32_t)(mine & 0x7fffffffull);
-      tbase[gw] = (uint32_t)(mine >> 31);
+      // (first vertex id, first triangle) of the word; (.z, .w) is k_count_b's dirpack
+      *reinterpret_cast<uint2*>(&wrec[gw].x) = make_uint2((uint32_t)(mine & 0x7fffffffull), (uint32_t)(mine >> 31));
       if (want_vemit && gw < emit_end) below += item;
     }
     run += __shfl_sync(0xffffffffu, inc, 31);
@@ -790,7 +824,7 @@ __device__ __forceinline__ int nth_set_bit7(unsigned m, unsigned n) {
 template <typename T, typename G>
 __global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned long long* __restrict__ own_id,
                                                     const unsigned long long* __restrict__ own_rk,
-                                                    const uint32_t* __restrict__ vbase, const uint2* __restrict__ wdir,
+                                                    const uint4* __restrict__ wrec,
                                                     const Counters* __restrict__ ctr, unsigned cap_own, unsigned cap_v, Xform xf,
                                                     G* __restrict__ verts, G* __restrict__ normals,
                                                     unsigned long long* __restrict__ keys, uint8_t* __restrict__ lowmin) {
@@ -804,8 +838,9 @@ __global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned lo
   const unsigned long long oid = have ? own_id[a] : 0ull;
   const unsigned long long ork = have ? own_rk[a] : 0ull;
   const unsigned ogw = (unsigned)(oid >> 13);
-  const unsigned vb = have ? vbase[ogw] : 0u;
-  const uint2 odp = have ? wdir[ogw] : make_uint2(0u, 0u);
+  const uint4 orec = have ? wrec[ogw] : make_uint4(0u, 0u, 0u, 0u);
+  const unsigned vb = orec.x;
+  const uint2 odp = make_uint2(orec.z, orec.w);
   const unsigned long long dp64 = ((unsigned long long)odp.y << 32) | odp.x;
   const unsigned m7 = (unsigned)oid & 127u;
   int i = 0, j = 0, w = 0;
@@ -925,8 +960,7 @@ template <typename T>
 __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsigned long long* __restrict__ cell_id,
                                                           const uint32_t* __restrict__ cell_toff, const Counters* __restrict__ ctr,
                                                           unsigned cap_cell, unsigned cap_t,
-                                                          const uint32_t* __restrict__ vbase, const uint32_t* __restrict__ tbase,
-                                                          const uint2* __restrict__ wdir, const uint32_t* __restrict__ vox_tab,
+                                                          const uint4* __restrict__ wrec, const uint32_t* __restrict__ vox_tab,
                                                           int* __restrict__ tris) {
   const unsigned n_cells = min(ctr->n_cell, cap_cell);
   // per warp: the 19 edge ids of its 32 voxels (row stride 33: a round of the write-out below reads arbitrary
@@ -945,20 +979,22 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsig
   const unsigned uW = (unsigned)g.W, plane_words = (unsigned)g.n1 * uW;
   const unsigned row = g.divW.div(gw0);
   const unsigned w = gw0 - row * uW;
-  const bool near = g.near_word(row, w) != 0;
+  const bool near = g.exact_word(row, w) != 0;
   // the voxel's 2x2 rows: word w (P) and the same rows shifted by one sample in k (S)
   const bool next_ok = (w + 1 < uW);
   const unsigned wi[4] = {gw0, gw0 + uW, gw0 + plane_words, gw0 + plane_words + uW};
   uint32_t P[4], S[4];
-  unsigned vb[4], vb1[4];
+  unsigned vb[4], vb1[4], tb0 = 0;
   uint2 dp[4], dp1[4];
 #pragma unroll
   for (int ab = 0; ab < 4; ++ab) {
     P[ab] = g.bits[wi[ab]];
     const uint32_t nx = next_ok ? g.bits[wi[ab] + 1] : 0u;
     S[ab] = __funnelshift_r(P[ab], nx, 1);
-    vb[ab] = vbase[wi[ab]] + g.id_base;
-    dp[ab] = wdir[wi[ab]];
+    const uint4 r = wrec[wi[ab]];
+    vb[ab] = r.x + g.id_base;
+    dp[ab] = make_uint2(r.z, r.w);
+    if (ab == 0) tb0 = r.y;
   }
   // used-edge words per owner row (index ab) and direction (index d-1); only the 14 that voxel edges use.  No masks:
   // bits below a valid edge's bit are valid edges of the same direction
@@ -980,8 +1016,9 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsig
     below1 = 0u;
 #pragma unroll
     for (int ab = 0; ab < 3; ++ab) {
-      vb1[ab] = vbase[wi[ab] + 1] + g.id_base;
-      dp1[ab] = wdir[wi[ab] + 1];
+      const uint4 r = wrec[wi[ab] + 1];
+      vb1[ab] = r.x + g.id_base;
+      dp1[ab] = make_uint2(r.z, r.w);
     }
   } else {
 #pragma unroll
@@ -1005,7 +1042,7 @@ __global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsig
   // per lane per round: each voxel marks its triangles with its lane in shared memory, then lane q of a round takes
   // triangle q -- its voxel from the mark, its row of the table, three ids from s_ids -- and writes it where the scan
   // put it (tbase[word] + offset in the word + index in the voxel): no assumption about the order of the list.
-  const unsigned o = valid ? tbase[gw0] + cell_toff[a] : 0u;       // cell_toff is relative to the word's first triangle
+  const unsigned o = valid ? tb0 + cell_toff[a] : 0u;       // cell_toff is relative to the word's first triangle
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned* ids = s_ids[warp];
   const uint32_t full = __ldg(vox_tab + c8 * 13 + 12);
@@ -1074,7 +1111,7 @@ __global__ void __launch_bounds__(256) k_codes(Grid<T> g, const unsigned long lo
 }
 
 // one launch instead of four memsets / copies in front of every run
-__global__ void k_reset3(Counters* ctr, uint4* rowflag16, size_t n16, uint4* wordflag16, size_t nw16,
+__global__ void k_reset3(Counters* ctr, uint4* rowflag16, size_t n16, uint4* wordflag16, uint4* exactflag16, size_t nw16,
                          unsigned long long* tile_state, size_t ntile) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)gridDim.x * blockDim.x;
   if (t == 0) {
@@ -1084,7 +1121,10 @@ __global__ void k_reset3(Counters* ctr, uint4* rowflag16, size_t n16, uint4* wor
     *ctr = c;
   }
   for (size_t q = t; q < n16; q += n) rowflag16[q] = make_uint4(0u, 0u, 0u, 0u);
-  for (size_t q = t; q < nw16; q += n) wordflag16[q] = make_uint4(0u, 0u, 0u, 0u);
+  for (size_t q = t; q < nw16; q += n) {
+    wordflag16[q] = make_uint4(0u, 0u, 0u, 0u);
+    exactflag16[q] = make_uint4(0u, 0u, 0u, 0u);
+  }
   for (size_t q = t; q < ntile; q += n) tile_state[q] = 0ull;
 }
 
@@ -1179,9 +1219,8 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
 
   if ((rc = ctr_ensure(ctx, ctx->bits, (size_t)(nwords + 4) * 4))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->nbits, (size_t)(nwords + 4) * 4))) return rc;
-  if ((rc = ctr_ensure(ctx, ctx->vbase, (size_t)(nwords + 4) * 4))) return rc;
-  if ((rc = ctr_ensure(ctx, ctx->wmask, (size_t)(nwords + 4) * 4))) return rc;     // tbase: first triangle of each word
-  if ((rc = ctr_ensure(ctx, ctx->wdir, (size_t)(nwords + 4) * 8))) return rc;      // per-direction vertex prefix of interesting words
+  // per word (first vertex id, first triangle, dirpack lo, dirpack hi): one 16-byte record, written for interesting words only
+  if ((rc = ctr_ensure(ctx, ctx->wdir, (size_t)(nwords + 4) * 16))) return rc;
   if (!ctx->vox_tab.p) {
     // corner bits -> triangle list of the whole voxel (tet order, then triangle order), then (tet mask | count << 8)
     static uint32_t tab[256 * 13];
@@ -1206,13 +1245,16 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
   if ((rc = ctr_ensure(ctx, ctx->counters, sizeof(Counters)))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->aux[4], (size_t)nrows + 32))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->aux[32], (size_t)nrows * 4 + 64))) return rc;      // word-level near flags
+  if ((rc = ctr_ensure(ctx, ctx->aux[35], (size_t)nrows * 4 + 64))) return rc;      // word-level "exact differs" flags
   if ((rc = ctr_ensure(ctx, ctx->tile_state, (size_t)ntiles * 16 + 16))) return rc;
   if (!ctx->counters_host) CTR_CUDA(ctx, cudaMallocHost(&ctx->counters_host, 256));
   g.bits = (const uint32_t*)ctx->bits.p;
   g.nbits = (const uint32_t*)ctx->nbits.p;
   g.rowflag = (const uint8_t*)ctx->aux[4].p;
   g.wordflag = (const uint32_t*)ctx->aux[32].p;
-  g.wdiv = (W + 31) / 32;
+  g.exactflag = (uint32_t*)ctx->aux[35].p;
+  g.wshift = 0;
+  while ((W >> g.wshift) > 32) ++g.wshift;
   Counters* dctr = (Counters*)ctx->counters.p;
   unsigned long long* st_vt = (unsigned long long*)ctx->tile_state.p;
 
@@ -1264,7 +1306,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
 
     if (!(phase == 2 && attempt == 0)) {                 // phase 2: attempt 0 was enqueued by phase 1
     k_reset3<<<64, 256, 0, st>>>(dctr, (uint4*)ctx->aux[4].p, (size_t)(nrows + 15) / 16, (uint4*)ctx->aux[32].p,
-                                 (size_t)(nrows + 3) / 4, st_vt, (size_t)ntiles);
+                                 (uint4*)ctx->aux[35].p, (size_t)(nrows + 3) / 4, st_vt, (size_t)ntiles);
     ctx->launches++;
     CTR_DBG(ctx, "k_reset3");
     if (p->flags & CTR_WANT_MINMAX)
@@ -1282,7 +1324,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
       // the grid covers the expected list length (last run's, with head-room); blocks past the real length only take a ticket
       const unsigned wb = (unsigned)((std::min<size_t>(cap_w, ctx->last_w + ctx->last_w / 8 + 4096) + CB_THREADS - 1) / CB_THREADS);
       k_count_b<T><<<wb, CB_THREADS, 0, st>>>(g, word0, (const uint32_t*)ctx->wlist.p, cap_w, (uint32_t*)ctx->aux[33].p,
-                                              (uint2*)ctx->wdir.p, (unsigned long long*)b_own_id.p,
+                                              (uint4*)ctx->wdir.p, (unsigned long long*)b_own_id.p,
                                               (unsigned long long*)b_own_voff.p, (unsigned long long*)b_cell_id.p,
                                               (uint32_t*)b_cell_toff.p, cap_own, cap_cell, st_vt, dctr, ntiles);
       k_tile_scan3<<<1, 1024, 0, st>>>(st_vt, ntiles, dctr);
@@ -1291,7 +1333,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
       CTR_DBG(ctx, "k_count_b");
       k_scan<T><<<(ntiles + SCAN_WARPS - 1) / SCAN_WARPS, SCAN_WARPS * 32, 0, st>>>(
           g, word0, ntiles, (const uint32_t*)ctx->wlist.p, (const uint32_t*)ctx->aux[33].p, (const uint2*)ctx->aux[34].p, cap_w,
-          st_vt, (uint32_t*)ctx->vbase.p, (uint32_t*)ctx->wmask.p, dctr);
+          st_vt, (uint4*)ctx->wdir.p, dctr);
       ctx->launches++;
       CTR_DBG(ctx, "k_scan");
     }
@@ -1304,20 +1346,19 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
       const unsigned vb = (unsigned)((std::min<size_t>(cap_own, ctx->last_own + ctx->last_own / 8 + 4096) + 255) / 256);
       const unsigned long long* oid = (const unsigned long long*)b_own_id.p;
       const unsigned long long* ovo = (const unsigned long long*)b_own_voff.p;
-      const uint32_t* dvb = (const uint32_t*)ctx->vbase.p;
-      const uint2* dwd = (const uint2*)ctx->wdir.p;
+      const uint4* dwr = (const uint4*)ctx->wdir.p;
       if (f64)
-        k_emit_verts<T, double><<<vb, 256, 0, st>>>(g, oid, ovo, dvb, dwd, dctr, vb * 256u, cap_v, xf, (double*)ctx->verts.p,
+        k_emit_verts<T, double><<<vb, 256, 0, st>>>(g, oid, ovo, dwr, dctr, vb * 256u, cap_v, xf, (double*)ctx->verts.p,
                                                     want_n ? (double*)ctx->normals.p : nullptr, dkeys, dlow);
       else
-        k_emit_verts<T, float><<<vb, 256, 0, st>>>(g, oid, ovo, dvb, dwd, dctr, vb * 256u, cap_v, xf, (float*)ctx->verts.p,
+        k_emit_verts<T, float><<<vb, 256, 0, st>>>(g, oid, ovo, dwr, dctr, vb * 256u, cap_v, xf, (float*)ctx->verts.p,
                                                    want_n ? (float*)ctx->normals.p : nullptr, dkeys, dlow);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_verts");
       ctr_stage_mark(ctx, 4);
       const unsigned tb = (unsigned)((std::min<size_t>(cap_cell, ctx->last_cell + ctx->last_cell / 8 + 4096) + ET_THREADS - 1) / ET_THREADS);
       k_emit_tris<T><<<tb, ET_THREADS, 0, st>>>(g, (const unsigned long long*)b_cell_id.p, (const uint32_t*)b_cell_toff.p, dctr,
-                                                tb * (unsigned)ET_THREADS, cap_t, (const uint32_t*)ctx->vbase.p, (const uint32_t*)ctx->wmask.p, (const uint2*)ctx->wdir.p,
+                                                tb * (unsigned)ET_THREADS, cap_t, (const uint4*)ctx->wdir.p,
                                                 (const uint32_t*)ctx->vox_tab.p, (int*)ctx->tris.p);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_tris");

@@ -118,7 +118,7 @@ __global__ void k_sel_seeds(const int* __restrict__ seeds, unsigned n_seeds, int
 }
 
 __global__ void k_sel_mark(const unsigned long long* __restrict__ cell_id, const uint32_t* __restrict__ cell_toff,
-                           unsigned n_cell, const uint32_t* __restrict__ tbase, int* parent, const uint8_t* __restrict__ flag,
+                           unsigned n_cell, const uint4* __restrict__ wrec, int* parent, const uint8_t* __restrict__ flag,
                            uint8_t* __restrict__ keep_t, unsigned n_tris, unsigned* n_sel_cells) {
   const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_cell) return;
@@ -132,7 +132,7 @@ __global__ void k_sel_mark(const unsigned long long* __restrict__ cell_id, const
 #pragma unroll
   for (int t = 0; t < 6; ++t)
     if ((emit >> t) & 1u) nt += (__popc(tet_mask_of(c8, t)) == 2) ? 2u : 1u;
-  const unsigned t0 = tbase[(unsigned)(id >> 19)] + cell_toff[c];
+  const unsigned t0 = wrec[(unsigned)(id >> 19)].y + cell_toff[c];
   for (unsigned q = 0; q < nt; ++q)
     if (t0 + q < n_tris) keep_t[t0 + q] = 1;
 }
@@ -234,7 +234,9 @@ int select_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, const int32_t* seeds, i
   g.nbits = (const uint32_t*)ctx->nbits.p;
   g.rowflag = (const uint8_t*)ctx->aux[4].p;
   g.wordflag = (const uint32_t*)ctx->aux[32].p;
-  g.wdiv = (W + 31) / 32;
+  g.exactflag = (uint32_t*)ctx->aux[35].p;
+  g.wshift = 0;
+  while ((W >> g.wshift) > 32) ++g.wshift;
   const unsigned nV = (unsigned)ctx->last_counts[0], nT = (unsigned)ctx->last_counts[1];
   const unsigned n_cell = (unsigned)ctx->last_cell;
   const uint32_t fl = p->flags;
@@ -304,7 +306,7 @@ int select_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, const int32_t* seeds, i
                                                                     nslots - 1, parent, flag);
   if (n_cell)
     k_sel_mark<<<cb, 256, 0, st>>>((const unsigned long long*)ctx->aux[2].p, (const uint32_t*)ctx->aux[3].p, n_cell,
-                                   (const uint32_t*)ctx->wmask.p, parent, flag, keep_t, nT, &dctr->pad);
+                                   (const uint4*)ctx->wdir.p, parent, flag, keep_t, nT, &dctr->pad);
   if (nT) {
     k_sel_used<<<tb, 256, 0, st>>>((const int*)ctx->tris.p, nT, keep_t, g.id_base, used_v, nV);
     k_flag_scan<<<tiles_t, SC_THREADS, 0, st>>>(keep_t, nT, idx_t, st_t, &dctr->ticket[0], &dctr->total[0], tiles_t);
