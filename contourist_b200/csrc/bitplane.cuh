@@ -424,7 +424,8 @@ int launch_bitplane(ctr_ctx* ctx, const T* dfield, unsigned nrows, int n2, int W
     static const int TMA_STAGES = getenv("CTR_BP_STAGES") ? atoi(getenv("CTR_BP_STAGES")) : TMA_STAGES_DEFAULT;
     static const int ctas_per_sm = getenv("CTR_BP_CTAS") ? atoi(getenv("CTR_BP_CTAS")) : 3;
     const int smem = TMA_STAGES * TMA_CHUNK + 2 * TMA_STAGES * 8 + TMA_CONSUMER_WARPS * 32 * 4 + 64;
-    const int ti = (sizeof(T) == 4 ? 0 : 1) + (MINMAX ? 2 : 0);
+    // this header is compiled into two translation units (anonymous namespaces): each has its own kernel instances
+    const int ti = CTR_BP_ATTR_BASE + (sizeof(T) == 4 ? 0 : 1) + (MINMAX ? 2 : 0);
     if (!(ctx->attr_mask & (1u << ti))) {
       CTR_CUDA(ctx, cudaFuncSetAttribute(k_bitplane_tma<T, MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * TMA_CHUNK + 1024));
       ctx->attr_mask |= 1u << ti;

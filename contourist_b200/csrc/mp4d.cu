@@ -11,6 +11,7 @@
 //   k4_slice               : morph_geometry.py:145-237 slicing, single pass (look-back scan, smem-staged output), with
 //                            the instant / tiny filter (pentatopes.py:171-189, tetrahedral.py:353-375) folded in when
 //                            the integer time bins decide it; k4_tet_filter is the general (fp64) form of that filter.
+#define CTR_BP_ATTR_BASE 4   // bits of ctr_ctx::attr_mask used by this file's bitplane kernels
 #include "bitplane.cuh"
 #include "tables.h"
 

@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <vector>
 
+#define CTR_BP_ATTR_BASE 0   // bits of ctr_ctx::attr_mask used by this file's bitplane kernels
 #include "bitplane.cuh"
 #include "tables.h"
 #include "uf_hash.cuh"

@@ -97,6 +97,7 @@ def test_medium_size_properties(engine):
     from contourist_b200 import engine as E
     from contourist_b200 import synthetic
     f = synthetic.morph4d(48, 12, device="cuda")
+    torch.cuda.synchronize()          # the engine has its own stream: the field must be complete before it reads it
     c = engine.mp4d_run(f.data_ptr(), 1.2, shape=tuple(f.shape), dtype=np.float32, flags=E.GEOM_F64)
     o = engine.mp4d_fetch()
     t = np.sort(o["tets"].astype(np.int64), axis=1)

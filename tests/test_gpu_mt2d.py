@@ -111,6 +111,7 @@ def test_full_size_properties_16384(engine):
     from contourist_b200 import synthetic
     n = 16384
     f = synthetic.field2d(n, device="cuda")
+    torch.cuda.synchronize()          # the engine has its own stream: the field must be complete before it reads it
     mn, mx = float(f.min()), float(f.max())
     levels = [(mx - mn) / 17 * i for i in range(1, 17)]
     c = engine.mt2d_run(f.data_ptr(), levels, shape=(n, n), dtype=np.float32)

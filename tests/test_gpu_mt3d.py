@@ -240,6 +240,7 @@ def test_full_size_properties_512(engine):
     from contourist_b200 import synthetic
     n = 512
     f = synthetic.ct_like(n, device="cuda")
+    torch.cuda.synchronize()          # the engine has its own stream: the field must be complete before it reads it
     c = engine.mt3d_run(f.data_ptr(), 0.5, shape=(n, n, n), dtype=np.float32, flags=E.WANT_NORMALS | E.WANT_KEYS)
     o = engine.mt3d_fetch()
     t = o["tris"].astype(np.int64)
@@ -273,3 +274,29 @@ def test_full_size_properties_512(engine):
     assert c_a.n_active_cells + c_b.n_active_cells == c.n_active_cells
     del f
     torch.cuda.empty_cache()
+
+
+def test_contexts_share_no_process_state(engine):
+    """Kernel attributes (dynamic shared memory opt-in of the TMA bitplane kernel, of the 4D slicer) are per device and
+    per kernel instance: a second context, a 4D run after a 3D run in the same context, and -- with two GPUs -- a
+    context on the other device must all launch.  Shapes are TMA-eligible (rows a multiple of 32 samples)."""
+    import torch
+    from contourist_b200 import engine as E
+    rng = np.random.default_rng(9)
+    f3 = rng.standard_normal((6, 5, 64)).astype(np.float32)
+    f4 = rng.standard_normal((4, 3, 3, 32)).astype(np.float32)
+    want3 = mt3d.extract(f3, 0.1, np.float32)
+    devices = [0] + ([1] if torch.cuda.device_count() > 1 else [])
+    for dev in devices:
+        a, b = E.Engine(dev), E.Engine(dev)
+        try:
+            for eng in (a, b, a):
+                c = eng.mt3d_run(f3, 0.1, flags=E.WANT_KEYS)
+                assert c.n_verts == len(want3["keys"]) and c.n_tris == len(want3["tris"])
+                c4 = eng.mp4d_run(f4, 0.1, flags=E.WANT_KEYS | E.MORPH)
+                assert c4.n_verts > 0
+                c = eng.mt3d_run(f3, 0.1, flags=E.WANT_KEYS | E.WANT_MINMAX)
+                assert np.array_equal(np.sort(eng.mt3d_fetch()["keys"]), want3["keys"])
+        finally:
+            a.close()
+            b.close()
