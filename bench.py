@@ -24,9 +24,31 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ISOVALUE = 0.5
-# dram__bytes_read.sum + dram__bytes_write.sum of the seven kernels of one extraction, from profiles/ (ncu --set full);
-TRAFFIC_BYTES = 1037.3e6     # profiles/r1q_ncu_full_summary.txt, dram read + write summed over the seven kernels (algorithmic: 725.9 MB)
 METRIC = "Gvoxels/s, 512^3 fp32 marching-tetrahedra extraction (indexed mesh + normals)"
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one extraction, from the ncu --set full capture
+    that tools/ncu_summary.py --json summarised into profiles/traffic.json (None when there is no such file)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    return float(d["total_bytes"]), d.get("source")
+
+
+def workload_config(n, world):
+    """The `config` of both arms (ours and --impl reference): the same workload, described once."""
+    n_total = n * world
+    return {"workload": "BASELINE configs[2]: %d^3 fp32 CT-like volume per GPU (48 Gaussian blobs + smoothed noise), "
+                        "isovalue 0.5, indexed mesh + gradient normals, fp32 geometry" % n,
+            "volume": [n_total, n, n],
+            "generator": "contourist_b200.synthetic.ct_like(%d, n_total=%d), seed 0" % (n, n_total),
+            "stacking": "one CT-like block (own 48 blobs) per GPU along the first axis, the neighbours' Gaussian tails "
+                        "summed in: one continuous volume, the same amount of surface in every slab",
+            "sharding": "z-slabs, 1 plane halo below / 2 above, NCCL all-gather of counts",
+            "l2": "inputs (%.0f MB field) larger than the 126 MB L2; no explicit flush" % (float(n) ** 3 * 4 / 1e6)}
 
 
 def peaks():
@@ -103,21 +125,13 @@ def _oracle_slab(args):
     return len(r["keys"]), len(r["tris"])
 
 
-def cpu_field(n_planes, n, seed=0):
-    """Host sample of the CT-like field family: n_planes x n x n fp32 (same generator family, numpy)."""
-    rng = np.random.default_rng(seed)
-    cen = rng.uniform(0.15, 0.85, size=(48, 3))
-    sig = rng.uniform(0.03, 0.12, size=(48, 3))
-    amp = rng.uniform(0.5, 1.0, size=48)
-    x = (np.arange(n_planes, dtype=np.float32) / max(n_planes - 1, 1) * 0.5 + 0.25).reshape(-1, 1, 1)
-    y = (np.arange(n, dtype=np.float32) / (n - 1)).reshape(1, -1, 1)
-    z = (np.arange(n, dtype=np.float32) / (n - 1)).reshape(1, 1, -1)
-    f = np.zeros((n_planes, n, n), dtype=np.float32)
-    for q in range(48):
-        f += np.float32(amp[q]) * np.exp(-0.5 * (((x - cen[q, 0]) / sig[q, 0]) ** 2 + ((y - cen[q, 1]) / sig[q, 1]) ** 2
-                                                 + ((z - cen[q, 2]) / sig[q, 2]) ** 2)).astype(np.float32)
-    f += (0.02 * rng.standard_normal(f.shape)).astype(np.float32) / 3.0
-    return f
+def bench_field(n):
+    """The bench's own field on the host: synthetic.ct_like(n) (generated with torch on the GPU when there is one --
+    plumbing, like in the timed arm -- else on the CPU), as a numpy array."""
+    import torch
+    from contourist_b200 import synthetic
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    return synthetic.ct_like(n, device=dev).cpu().numpy()
 
 
 def time_oracle(field, value, cores):
@@ -138,37 +152,110 @@ def time_oracle(field, value, cores):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference itself cannot
-    travel to the GPU box and would need hours at this size) on all host cores,
-    on a bounded sample of the same workload."""
+    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference itself cannot travel to the
+    GPU box and would need hours at this size) on all host cores, on the SAME 512^3 field as
+    the timed arm.  A step is a bounded sample of that workload: a z-slab of the field, sized from a calibration run
+    so that warmup + steps end within about two minutes, the slabs cycling through the volume (a step covers the whole
+    volume when that fits)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = max(1, min(os.cpu_count() or 1, 32))
-    n = 192
-    planes = max(cores * 6 + 1, 49)
-    field = cpu_field(planes, n)
-    vox = field.size
-    times = []
-    tris = 0
-    for s in range(args.warmup + args.steps):
-        dt, tris = time_oracle(field, ISOVALUE, cores)
-        if s >= args.warmup:
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    n = args.n
+    field = bench_field(n)
+    # calibration (untimed): rate of the port on a slab of the middle of the volume
+    cal = max(cores * 2 + 1, 33)
+    c0 = (n - cal) // 2
+    dt, _ = time_oracle(field[c0:c0 + cal], ISOVALUE, cores)
+    rate = (cal - 1) * n * n / dt                                   # voxels per second
+    budget = 100.0 / max(args.steps + args.warmup, 1)               # seconds per step
+    planes = int(min(n, max(cores * 2 + 1, rate * budget / (n * n))))
+    nslab = -(-n // planes)                                          # slabs that together cover the volume (they may overlap)
+    starts = [int(round(q * (n - planes) / max(nslab - 1, 1))) for q in range(nslab)]
+    times, vox, tris = [], 0, 0
+    for s_i in range(args.warmup + args.steps):
+        a = starts[s_i % len(starts)]
+        sub = field[a:a + planes]
+        dt, nt = time_oracle(sub, ISOVALUE, cores)
+        if s_i >= args.warmup:
             times.append(dt)
+            vox += (planes - 1) * (n - 1) * (n - 1)
+            tris += nt
     tot = sum(times)
-    val = vox * len(times) / tot / 1e9
-    sample = "%dx%dx%d fp32 sub-volume of the CT-like field per step, numpy oracle port, %d processes" % (planes, n, n, cores)
+    val = vox / tot / 1e9
+    sample = ("%d-plane z-slabs of the same %d^3 field per step (%d slabs, cycling), numpy oracle port "
+              "(extract + normals), %d processes" % (planes, n, len(starts), cores))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Gvoxels/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / len(times) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "512^3 fp32 CT-like volume, isovalue 0.5 (BASELINE configs[2]); bounded sample: " + sample},
-            "mtris_per_s": tris * len(times) / tot / 1e6,
+            "config": workload_config(n, max(args.gpus, 1)),
+            "mtris_per_s": tris / tot / 1e6,
             "cpu_baseline": {"value": val, "unit": "Gvoxels/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def c5_strong(eng, world, rank, dev, stream, n=2048, chunk=256, steps=2, warmup=1):
+    """BASELINE configs[4]: the 2048^3 fp32 turbulence field (isovalue 0), STRONG scaling: the volume is fixed and rank r
+    takes 1/N of the owner planes, walking them in chunks of `chunk` planes (the 32 GiB field is generated chunk by
+    chunk on the device and never resident at once; generation is not timed).  Job time = slowest rank's sum over its
+    chunks + the all-gather of the per-rank counts (tools/bench_c5.py is the stand-alone form of this leg)."""
+    import torch
+    import torch.distributed as dist
+    from contourist_b200 import engine as E
+    from contourist_b200 import sharding, synthetic
+    a_r, b_r = sharding.slab_bounds(n, world)[rank]
+    tot_ms, nv, nt = 0.0, 0, 0
+    for a in range(a_r, b_r, chunk):
+        b = min(a + chunk, b_r)
+        lo, hi, kw = sharding.slab_with_halo(a, b, n)
+        f = synthetic.turbulence(n, lo, hi, device=dev, n_total=n)
+        shape = (hi - lo, n, n)
+        run = lambda: eng.mt3d_run(f.data_ptr(), 0.0, shape=shape, dtype=np.float32, flags=E.WANT_NORMALS, **kw)
+        for _ in range(warmup):
+            c = run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            c = run()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        tot_ms += e0.elapsed_time(e1) / steps
+        nv += int(c.n_verts)
+        nt += int(c.n_tris)
+        del f
+    mine = torch.tensor([nv, nt], dtype=torch.int64, device=dev)
+    t = torch.tensor([tot_ms, 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        out = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, mine)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dist.all_gather_into_tensor(out, mine)
+        e1.record()
+        torch.cuda.synchronize()
+        t[1] = e0.elapsed_time(e1) / 10
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot = out.view(world, 2).sum(0)
+    else:
+        tot = mine
+    ms = float(t[0]) + float(t[1])
+    V, T = int(tot[0]), int(tot[1])
+    alg = float(n) ** 3 * 4 + V * 24.0 + T * 12.0
+    peak, _ = peaks()
+    torch.cuda.empty_cache()
+    return {"workload": "BASELINE configs[4]: %d^3 fp32 turbulence (64 sines), isovalue 0, z-slabs over %d GPU(s), chunks of %d planes"
+                        % (n, world, chunk), "scaling": "strong", "n_gpus": world, "ms_total": ms, "allgather_ms": float(t[1]),
+            "value": float(n) ** 3 / ms / 1e6, "unit": "Gvoxels/s", "mtris_per_s": T / ms / 1e3, "n_verts": V, "n_tris": T,
+            "steps": steps, "warmup": warmup,
+            "roofline_frac_per_gpu": alg / ms / 1e6 / world / peak}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -200,51 +287,38 @@ def run_ours(args):
     eng.set_stream(stream.cuda_stream)
     eng.set_timing(True)
     flags = E.WANT_NORMALS if not os.environ.get("CTR_BENCH_NO_NORMALS") else 0   # (diagnostic switch; the metric needs normals)
-    # the collective of the path: all-gather of (n_verts, n_tris) -> exclusive scan = global vertex / triangle offsets
-    # ctr_mt3d_finish waits for the extraction only (an event behind its last kernel), not for the all-gather queued
-    # after it, so the host is already enqueueing step k+1 while the collective of step k-1 runs.  The pinned staging
-    # buffers therefore rotate: slot s is reused 4 steps later, two finishes after its copy was consumed.
-    counts_dev = torch.zeros(2, dtype=torch.int64, device=dev)
-    counts_pin = [torch.zeros(2, dtype=torch.int64, pin_memory=True) for _ in range(4)]
-    gathered = torch.zeros(2 * world, dtype=torch.int64, device=dev)
-    n_gather = [0]
-    # CTR_BENCH_AG_SIDE=1 (diagnostic): issue the collective on a side stream instead; measured no better at 2 GPUs
-    # (0.480 vs 0.472 ms per step)
-    side = torch.cuda.Stream(device=dev) if (world > 1 and os.environ.get("CTR_BENCH_AG_SIDE")) else None
-
-    prev = [None]
-
-    def gather(c):
-        pin = counts_pin[n_gather[0] & 3]
-        n_gather[0] += 1
-        pin[0] = int(c.n_verts)
-        pin[1] = int(c.n_tris)
-        if side is None:
-            counts_dev.copy_(pin, non_blocking=True)
-            dist.all_gather_into_tensor(gathered, counts_dev)
-        else:
-            with torch.cuda.stream(side):
-                counts_dev.copy_(pin, non_blocking=True)
-                dist.all_gather_into_tensor(gathered, counts_dev)
+    # The collective of the path: all-gather of (n_verts, n_tris) -> exclusive scan = global vertex / triangle offsets.
+    # The counts never visit the host: the engine stores them on the device behind the extraction's last kernel
+    # (ctr_mt3d_publish_counts) and the all-gather is issued on a side stream behind an event recorded there, so the
+    # extraction stream never waits for a peer: skew between ranks is absorbed over the two slots below instead of being
+    # paid every step.  ctr_mt3d_finish waits for the extraction only (an event behind its last kernel).
+    counts_dev = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(2)]
+    gathered = [torch.zeros(2 * world, dtype=torch.int64, device=dev) for _ in range(2)]
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    ev_done = [torch.cuda.Event() for _ in range(2)]        # extraction of the slot finished (main stream)
+    ev_sent = [None, None]                                  # all-gather of the slot finished (side stream)
+    n_step = [0]
 
     def step():
         if world == 1:
             return eng.mt3d_run(field.data_ptr(), ISOVALUE, shape=shape, dtype=np.float32, flags=flags,
                                 i_lo=a - lo, i_hi=b - lo, plane_offset=lo)
-        # N > 1: the extraction is queued, the all-gather of the PREVIOUS step's counts is issued while the GPU works
-        # (its host-side cost is ~0.1 ms, a fifth of a step), then the host waits; flush() issues the last one
+        slot = n_step[0] & 1
+        n_step[0] += 1
+        if ev_sent[slot] is not None:
+            stream.wait_event(ev_sent[slot])                # the slot's previous counts have been sent (two steps ago)
+        eng.mt3d_publish_counts(counts_dev[slot].data_ptr())
         eng.mt3d_enqueue(field.data_ptr(), ISOVALUE, shape=shape, dtype=np.float32, flags=flags,
                          i_lo=a - lo, i_hi=b - lo, plane_offset=lo)
-        if prev[0] is not None:
-            gather(prev[0])
-        c = eng.mt3d_finish()
-        prev[0] = c
-        return c
+        ev_done[slot].record(stream)
+        with torch.cuda.stream(side):
+            side.wait_event(ev_done[slot])
+            dist.all_gather_into_tensor(gathered[slot], counts_dev[slot])
+            ev_sent[slot] = torch.cuda.Event()
+            ev_sent[slot].record(side)
+        return eng.mt3d_finish()
 
     def flush():
-        if world > 1 and prev[0] is not None:
-            gather(prev[0])
-            prev[0] = None
         if side is not None:
             stream.wait_stream(side)
 
@@ -253,8 +327,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(args.warmup):
         c = step()
+    flush()
     barrier()
     # per-stage CUDA-event times come from a separate instrumented pass (the event records and their read-back sit
     # between the kernels and after every run); the timed region below runs with the instrumentation off
@@ -304,8 +379,27 @@ def run_ours(args):
     value = vox_all / (ms_step * 1e-3) / 1e9
     n_tris_all, n_verts_all = int(tot[0].item()), int(tot[1].item())
     if world > 1:                                     # the offsets the last timed step gathered are the real ones
-        g = gathered.view(world, 2).sum(0)
+        g = gathered[(n_step[0] - 1) & 1].view(world, 2).sum(0)
         assert int(g[0]) == n_verts_all and int(g[1]) == n_tris_all, (g, n_verts_all, n_tris_all)
+
+    # ---- the same K steps with fp64 geometry (the reference's arithmetic; north_star's 1e-6 mode): secondary number
+    f64 = None
+    if world == 1 and not args.no_e2e:
+        fl64 = flags | E.GEOM_F64
+        run64 = lambda: eng.mt3d_run(field.data_ptr(), ISOVALUE, shape=shape, dtype=np.float32, flags=fl64)
+        for _ in range(3):
+            run64()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            run64()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms64 = e0.elapsed_time(e1) / args.steps
+        f64 = {"ms_per_step": ms64, "value": float(n) ** 3 / (ms64 * 1e-3) / 1e9, "unit": "Gvoxels/s",
+               "note": "positions and normals computed and stored in fp64 (CTR_GEOM_F64: 0 ulp vs the oracle), same field"}
+        eng.mt3d_run(field.data_ptr(), ISOVALUE, shape=shape, dtype=np.float32, flags=flags)   # pools back to fp32 sizes
 
     # ---- end-to-end through the C ABI with HOST buffers (H2D of the field + D2H of the mesh in the timed region)
     host_field = torch.empty(field.shape, dtype=torch.float32, pin_memory=True)
@@ -316,16 +410,11 @@ def run_ours(args):
     for s in range(0 if args.no_e2e else 2 + max(1, min(args.steps, 5))):
         barrier()
         t1 = time.perf_counter()
-        if world == 1:
-            # the host-array call of the engine: slabs uploaded / extracted / downloaded in a pipeline
-            tot_e, outs = eng.mt3d_extract_host(hf, ISOVALUE, flags=flags, nslabs=args.e2e_slabs)
-            ce = argparse.Namespace(n_verts=tot_e["n_verts"], n_tris=tot_e["n_tris"])
-        else:
-            ce = eng.mt3d_run(hf, ISOVALUE, flags=flags, i_lo=a - lo, i_hi=b - lo, plane_offset=lo)
-            outs = eng.mt3d_fetch(pinned=True)
+        # the host-array call of the engine: slabs uploaded / extracted / downloaded in a pipeline (every rank its own slab)
+        tot_e, outs = eng.mt3d_extract_host(hf, ISOVALUE, flags=flags, nslabs=args.e2e_slabs, own=(a - lo, b - lo), plane_offset=lo)
         if world > 1:
-            counts_dev.copy_(torch.tensor([ce.n_verts, ce.n_tris], dtype=torch.int64))
-            dist.all_gather_into_tensor(gathered, counts_dev)
+            counts_dev[0].copy_(torch.tensor([tot_e["n_verts"], tot_e["n_tris"]], dtype=torch.int64))
+            dist.all_gather_into_tensor(gathered[0], counts_dev[0])
         barrier()
         if s >= 2:
             e2e_times.append(time.perf_counter() - t1)
@@ -356,11 +445,21 @@ def run_ours(args):
                 ts.append((time.perf_counter() - t1) * 1e3)
             post[name] = {"ms": min(ts), "result": list(res), "n_tris_in": int(run_c.n_tris)}
 
+    # CPU baseline sample: a block from the middle of this rank's field
+    c0 = (n - 160) // 2
+    p0 = min(n // 2, shape[0] - 34)
+    sub = field[p0:p0 + 33, c0:c0 + 160, c0:c0 + 160].cpu().numpy()
+    c5 = None
+    if not args.no_c5 and not args.no_e2e:
+        del host_field, hf, field
+        torch.cuda.empty_cache()
+        c5 = c5_strong(eng, world, rank, dev, stream)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
+    traffic, traffic_src = measured_traffic()
     st = stage_acc                                    # ms: 0 H2D, 1 classify, 2 count+scan, 3 verts, 4 tris
     field_bytes = float(np.prod(shape)) * 4
     # SURVEY 8(d) algorithmic bytes: 4 B per voxel read (stage 1), 24 B per vertex (stage 3), 12 B per triangle (stage 4);
@@ -378,20 +477,16 @@ def run_ours(args):
     alg_total = float(n) ** 3 * 4 + c.n_verts * 24 + c.n_tris * 12        # field + V*(3p+3p) + T*12
     pipe_gbs = alg_total / (ms_step * 1e-3) / 1e9
     # CPU baseline: oracle port, 1 core, bounded sample of the same field family
-    sub = cpu_field(33, 160)
     t_cpu, _ = time_oracle(sub, ISOVALUE, 1) if not args.no_e2e else (float('nan'), 0)
     cpu_val = sub.size / t_cpu / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3) + n_inst + 1 + PRELOAD, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[2]: %d^3 fp32 CT-like volume per GPU (48 Gaussian blobs + smoothed noise), "
-                               "isovalue 0.5, indexed mesh + gradient normals, fp32 geometry" % n,
-                   "volume": [n_total, n, n],
-                   "stacking": "one CT-like block (own 48 blobs) per GPU along the first axis, the neighbours' Gaussian tails "
-                               "summed in: one continuous volume, the same amount of surface in every slab",
-                   "sharding": "z-slabs, 1 plane halo below / 2 above, NCCL all-gather of counts",
-                   "l2": "inputs (%.0f MB field) larger than the 126 MB L2; no explicit flush" % (field_bytes / 1e6)},
+        "config": workload_config(n, world),
+        "untimed_steps": {"warmup": args.warmup, "instrumented": n_inst + 1, "clock_preload": PRELOAD,
+                          "note": "after the W warm-up steps: a CUDA-event instrumented pass for the per-stage times, then the "
+                                  "same step repeated untimed so that nvidia-smi samples the clocks under this load"},
         "mtris_per_s": n_tris_all / (ms_step * 1e-3) / 1e6, "n_tris": n_tris_all, "n_verts": n_verts_all,
         "stage_ms": {"bitplane": st[1], "count_scan": st[2], "emit_verts": st[3], "emit_tris": st[4],
                      "wall_ms_per_step": wall / args.steps * 1e3},
@@ -400,16 +495,17 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "mt3d extraction = k_bitplane_tma + k_count_a + k_count_b + k_tile_scan3 + k_scan + k_emit_verts + k_emit_tris "
                                                 "(largest share: %s, %.0f%% of the kernel time)" % (dom, 100.0 * per_stage[dom]["ms"] / kern_ms),
                      "achieved": alg_total / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": alg_total / (kern_ms * 1e-3) / 1e9 / peak, "traffic": TRAFFIC_BYTES, "peak_source": peak_src,
+                     "frac": alg_total / (kern_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_total, "kernel_ms": kern_ms, "per_stage": per_stage},
         "pipeline_roofline": {"algorithmic_bytes": alg_total, "achieved": pipe_gbs, "frac": pipe_gbs / peak,
                               "note": "whole step: (field + V*24 + T*12) / device time of the step"},
         "cpu_baseline": {"value": cpu_val, "unit": "Gvoxels/s", "cores": 1, "kind": "port",
-                         "sample": "33x160x160 fp32 sub-volume of the CT-like field, numpy oracle port (extract + normals)"},
+                         "sample": "33x160x160 block from the middle of the same field, numpy oracle port (extract + normals)"},
         "e2e": {"value": e2e_val, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "note": "Engine.mt3d_extract_host (ctr_mt3d_run + ctr_mt3d_fetch per z-slab on two contexts, page-locked host "
                         "buffers): H2D of the field and D2H of vertices, normals and triangles inside the timed region"},
         "gpu_launches": int(launches), "clocks": clocks,
+        "f64_geom": f64, "c5_strong": c5,
         "post_passes": post,
     }
     print(json.dumps(line))
@@ -426,6 +522,7 @@ def main():
     ap.add_argument("--n", type=int, default=512)
     ap.add_argument("--e2e-slabs", type=int, default=4, help="slabs of the pipelined host-array call (1 = run + fetch)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg and the CPU baseline (profiling runs)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the 2048^3 strong-scaling leg (c5_strong)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

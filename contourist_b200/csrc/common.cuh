@@ -49,6 +49,7 @@ struct ctr_ctx {
   uint32_t last_flags = 0;
   int64_t last_counts[8] = {};
   unsigned char last3_params[160] = {};   // parameters of the last completed ctr_mt3d_run
+  long long* publish3 = nullptr;          // ctr_mt3d_publish_counts: device {n_verts, n_tris} behind every 3D run
   unsigned last3_edited = 0;              // passes that have rewritten the device mesh of that run: 1 seeded selection, 2 clean-up
   // 3D: an extraction enqueued by ctr_mt3d_enqueue and not yet finished
   bool pending3 = false;

@@ -1111,6 +1111,12 @@ __global__ void __launch_bounds__(256) k_codes(Grid<T> g, const unsigned long lo
   codes[a] = code;
 }
 
+// ctr_mt3d_publish_counts: {n_verts, n_tris} of the run for a collective that reads them on the device
+__global__ void k_publish3(const Counters* __restrict__ ctr, int sharded, long long* __restrict__ out) {
+  out[0] = (long long)(sharded ? ctr->v_emit : ctr->tot_v);
+  out[1] = (long long)ctr->tot_t;
+}
+
 // one launch instead of four memsets / copies in front of every run
 __global__ void k_reset3(Counters* ctr, uint4* rowflag16, size_t n16, uint4* wordflag16, uint4* exactflag16, size_t nw16,
                          unsigned long long* tile_state, size_t ntile) {
@@ -1339,6 +1345,10 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
       CTR_DBG(ctx, "k_scan");
     }
     CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    if (ctx->publish3) {
+      k_publish3<<<1, 1, 0, st>>>(dctr, g.i_hiv > g.i_hi ? 1 : 0, ctx->publish3);
+      ctx->launches++;
+    }
     ctr_stage_mark(ctx, 3);
     if (geom && ntiles > 0) {
       unsigned long long* dkeys = want_k ? (unsigned long long*)ctx->keys.p : nullptr;
@@ -1499,6 +1509,13 @@ extern "C" int ctr_mt3d_finish(ctr_ctx* ctx, ctr_mt3d_counts* out) {
   if (!ctx->pending3) return ctr_fail(ctx, CTR_ERR_STATE, "no ctr_mt3d_enqueue to finish");
   ctx->pending3 = false;
   return mt3d_dispatch(ctx, (const ctr_mt3d_params*)ctx->pending3_params, out, 2);
+}
+
+extern "C" int ctr_mt3d_publish_counts(ctr_ctx* ctx, void* device_counts) {
+  if (!ctx) return CTR_ERR_BAD_ARG;
+  if (((uintptr_t)device_counts) & 7u) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "device_counts must be 8-byte aligned");
+  ctx->publish3 = (long long*)device_counts;
+  return 0;
 }
 
 extern "C" int ctr_mt3d_fetch(ctr_ctx* ctx, void* verts, void* normals, int32_t* tris, uint64_t* keys,

@@ -85,6 +85,8 @@ def load_library():
     lib.ctr_mt3d_enqueue.restype = i32
     lib.ctr_mt3d_finish.argtypes = [vp, ctypes.POINTER(Mt3dCounts)]
     lib.ctr_mt3d_finish.restype = i32
+    lib.ctr_mt3d_publish_counts.argtypes = [vp, vp]
+    lib.ctr_mt3d_publish_counts.restype = i32
     lib.ctr_mt3d_fetch.argtypes = [vp] + [vp] * 7
     lib.ctr_mt3d_fetch.restype = i32
     lib.ctr_mt3d_device_ptrs.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
@@ -236,6 +238,12 @@ class Engine(object):
         self._check(self.lib.ctr_mt3d_enqueue(self.h, ctypes.byref(p)), "ctr_mt3d_enqueue")
         self._pending3 = flags
 
+    def mt3d_publish_counts(self, device_ptr):
+        """Every following 3D run also stores (n_verts, n_tris) as two int64 at this device address, on the engine's
+        stream, behind its last kernel (None: off): a collective can send the counts without a host round trip."""
+        self._check(self.lib.ctr_mt3d_publish_counts(self.h, ctypes.c_void_p(int(device_ptr)) if device_ptr else None),
+                    "ctr_mt3d_publish_counts")
+
     def mt3d_finish(self):
         c = Mt3dCounts()
         self._check(self.lib.ctr_mt3d_finish(self.h, ctypes.byref(c)), "ctr_mt3d_finish")
@@ -315,13 +323,16 @@ class Engine(object):
         out.update(verts=a_v, normals=a_n, tris=a_t, keys=a_k, lowmin=a_l, cells=a_c, codes=a_d)
         return out
 
-    def mt3d_extract_host(self, field, value, origin=(0.0, 0.0, 0.0), delta=(1.0, 1.0, 1.0), flags=0, nslabs=4):
+    def mt3d_extract_host(self, field, value, origin=(0.0, 0.0, 0.0), delta=(1.0, 1.0, 1.0), flags=0, nslabs=4, own=None,
+                          plane_offset=0):
         """Host array in, host mesh out, with the PCIe traffic of the two directions overlapped.
 
         The volume is cut into `nslabs` z-slabs (sharding.slab_with_halo, the multi-GPU decomposition); slab s is
         uploaded and extracted on one of two alternating contexts while a worker thread downloads the mesh of slab
         s-1 from the other (PCIe is full duplex; ctypes releases the GIL).  Triangle ids are global: each slab's run
-        gets the vertex count of the slabs before it as `vert_id_base`.  `field` should be page-locked
+        gets the vertex count of the slabs before it as `vert_id_base`.  own=(A, B) restricts the call to owner planes
+        [A, B) of the array (a rank's slab with its halo planes around it) and plane_offset is the global index of
+        the array's first plane, as in ctr_mt3d_params.  `field` should be page-locked
         (Engine.pinned_empty) for full transfer rate.  Returns (totals dict, arrays dict); the arrays live in the
         engine's page-locked pool and are overwritten by the next call."""
         from concurrent.futures import ThreadPoolExecutor
@@ -332,7 +343,8 @@ class Engine(object):
             raise ValueError("float32 / float64 samples expected")
         flags &= ~(FIELD_ON_DEVICE | WANT_CODES | NO_GEOMETRY)
         n0 = field.shape[0]
-        nslabs = max(1, min(int(nslabs), n0 - 1))
+        own_a, own_b = (0, n0) if own is None else (int(own[0]), int(own[1]))
+        nslabs = max(1, min(int(nslabs), own_b - own_a - 1))
         twin = self.__dict__.get("_twin")
         if twin is None or twin.h is None:
             twin = self._twin = Engine(self.device)
@@ -366,10 +378,11 @@ class Engine(object):
             totals = dict(n_active_cells=0, n_crossings=0)
             sizes = []
             overflow = False
-            for s_i, (a, b) in enumerate(sharding.slab_bounds(n0, nslabs)):
+            for s_i, (a, b) in enumerate(sharding.slab_bounds(own_b - own_a, nslabs)):
                 if b <= a:
                     continue
-                lo, hi, kw = sharding.slab_with_halo(a, b, n0)
+                lo, hi, kw = sharding.slab_with_halo(a + own_a, b + own_a, n0)
+                kw["plane_offset"] += int(plane_offset)
                 eng = engines[s_i & 1]
                 if pending[s_i & 1] is not None:
                     pending[s_i & 1].result()                 # its previous slab has been downloaded

@@ -122,6 +122,11 @@ CTR_API int ctr_mt3d_run(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts
  * counts of the previous volume (bench.py, N > 1).  Not with CTR_WANT_CODES.                                         */
 CTR_API int ctr_mt3d_enqueue(ctr_ctx* ctx, const ctr_mt3d_params* p);
 CTR_API int ctr_mt3d_finish(ctr_ctx* ctx, ctr_mt3d_counts* out);
+/* Device-side copy of the counts (the all-gather of per-rank counts -> vertex / triangle offsets needs
+ * no host round trip): from now on every ctr_mt3d_run / _enqueue also stores {n_verts, n_tris} as two int64 at
+ * `device_counts` (caller-owned device memory, 16 bytes, valid until replaced) behind its last kernel, on the context's
+ * stream -- a collective queued after an event on that stream can send them straight from there.  NULL turns it off. */
+CTR_API int ctr_mt3d_publish_counts(ctr_ctx* ctx, void* device_counts);
 /* verts/normals: [n_verts][3] float or double (CTR_GEOM_F64); tris: [n_tris][3] vertex ids, local to
  * this call (0 = first emitted vertex; ids >= n_verts refer to the next shard's vertices; vertices are numbered
  * by owner word (plane-major), then edge direction, then k -- not by key);
