@@ -289,12 +289,16 @@ def run_ours(args):
     flags = E.WANT_NORMALS if not os.environ.get("CTR_BENCH_NO_NORMALS") else 0   # (diagnostic switch; the metric needs normals)
     # The collective of the path: all-gather of (n_verts, n_tris) -> exclusive scan = global vertex / triangle offsets.
     # The counts never visit the host: the engine stores them on the device behind the extraction's last kernel
-    # (ctr_mt3d_publish_counts) and the all-gather is issued on a side stream behind an event recorded there, so the
-    # extraction stream never waits for a peer: skew between ranks is absorbed over the two slots below instead of being
-    # paid every step.  ctr_mt3d_finish waits for the extraction only (an event behind its last kernel).
+    # (ctr_mt3d_publish_counts) and the all-gather is queued on the same stream right behind it, before the host has
+    # even seen the counts; ctr_mt3d_finish waits for the extraction only (an event behind its last kernel), so the host
+    # is already enqueueing step k+1 while the collective of step k runs.  Measured on 8 B200 (profiles/): 0.417 ms per
+    # step against 0.407 on one GPU; the same collective on a side stream (CTR_BENCH_AG=side) costs more (0.458 ms:
+    # the NCCL kernel then competes with the extraction kernels), the round-1 form with a host round trip 0.553 ms.
     counts_dev = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(2)]
     gathered = [torch.zeros(2 * world, dtype=torch.int64, device=dev) for _ in range(2)]
-    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    # CTR_BENCH_AG (diagnostic): "main" (default), "side" = the same all-gather on a side stream, "none" = no collective
+    ag_mode = os.environ.get("CTR_BENCH_AG", "main")
+    side = torch.cuda.Stream(device=dev) if (world > 1 and ag_mode == "side") else None
     ev_done = [torch.cuda.Event() for _ in range(2)]        # extraction of the slot finished (main stream)
     ev_sent = [None, None]                                  # all-gather of the slot finished (side stream)
     n_step = [0]
@@ -310,12 +314,16 @@ def run_ours(args):
         eng.mt3d_publish_counts(counts_dev[slot].data_ptr())
         eng.mt3d_enqueue(field.data_ptr(), ISOVALUE, shape=shape, dtype=np.float32, flags=flags,
                          i_lo=a - lo, i_hi=b - lo, plane_offset=lo)
-        ev_done[slot].record(stream)
-        with torch.cuda.stream(side):
-            side.wait_event(ev_done[slot])
+        if side is not None:
+            ev_done[slot].record(stream)
+            with torch.cuda.stream(side):
+                side.wait_event(ev_done[slot])
+                dist.all_gather_into_tensor(gathered[slot], counts_dev[slot])
+                if ev_sent[slot] is None:
+                    ev_sent[slot] = torch.cuda.Event()
+                ev_sent[slot].record(side)
+        elif ag_mode == "main":
             dist.all_gather_into_tensor(gathered[slot], counts_dev[slot])
-            ev_sent[slot] = torch.cuda.Event()
-            ev_sent[slot].record(side)
         return eng.mt3d_finish()
 
     def flush():
@@ -380,7 +388,7 @@ def run_ours(args):
     n_tris_all, n_verts_all = int(tot[0].item()), int(tot[1].item())
     if world > 1:                                     # the offsets the last timed step gathered are the real ones
         g = gathered[(n_step[0] - 1) & 1].view(world, 2).sum(0)
-        assert int(g[0]) == n_verts_all and int(g[1]) == n_tris_all, (g, n_verts_all, n_tris_all)
+        assert ag_mode == "none" or (int(g[0]) == n_verts_all and int(g[1]) == n_tris_all), (g, n_verts_all, n_tris_all)
 
     # ---- the same K steps with fp64 geometry (the reference's arithmetic; north_star's 1e-6 mode): secondary number
     f64 = None
@@ -418,6 +426,16 @@ def run_ours(args):
         barrier()
         if s >= 2:
             e2e_times.append(time.perf_counter() - t1)
+    # what the platform gives: this rank's H2D rate while every rank copies its field at the same time
+    h2d_gbs = None
+    if not args.no_e2e:
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(3):
+            field.copy_(host_field, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbs = 3 * hf.nbytes / (time.perf_counter() - t1) / 1e9
+        barrier()
     e2e_t = torch.tensor([float(np.mean(e2e_times)) if e2e_times else float('nan')], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -502,6 +520,7 @@ def run_ours(args):
         "cpu_baseline": {"value": cpu_val, "unit": "Gvoxels/s", "cores": 1, "kind": "port",
                          "sample": "33x160x160 block from the middle of the same field, numpy oracle port (extract + normals)"},
         "e2e": {"value": e2e_val, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "h2d_copy_gbs_rank0_all_ranks_copying": h2d_gbs,
                 "note": "Engine.mt3d_extract_host (ctr_mt3d_run + ctr_mt3d_fetch per z-slab on two contexts, page-locked host "
                         "buffers): H2D of the field and D2H of vertices, normals and triangles inside the timed region"},
         "gpu_launches": int(launches), "clocks": clocks,

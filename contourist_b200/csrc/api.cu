@@ -46,6 +46,7 @@ extern "C" void ctr_destroy(ctr_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  ctr_comm_destroy(c);
   DevBuf* all[] = {&c->field, &c->bits, &c->nbits, &c->vbase, &c->tbase, &c->list_v, &c->list_t, &c->tile_state,
                    &c->counters, &c->wmask, &c->wdir, &c->wlist, &c->vox_tab, &c->verts, &c->normals, &c->tris, &c->keys, &c->lowmin, &c->cells, &c->codes};
   for (DevBuf* b : all) free_buf(*b);

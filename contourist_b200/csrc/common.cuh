@@ -15,8 +15,11 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+struct ctr_comm_state;                    // comm.cu: NCCL communicator + gathered mesh of a context
+
 struct ctr_ctx {
   int device = 0;
+  ctr_comm_state* comm = nullptr;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t ev_enqueued = nullptr;   // recorded behind everything ctr_mt3d_enqueue queued: ctr_mt3d_finish waits for it,

@@ -97,6 +97,18 @@ def load_library():
     lib.ctr_mt3d_select_seeded.restype = i32
     lib.ctr_mt3d_clean.argtypes = [vp, ctypes.POINTER(CleanParams), ctypes.POINTER(CleanCounts)]
     lib.ctr_mt3d_clean.restype = i32
+    lib.ctr_comm_unique_id.argtypes = [vp]
+    lib.ctr_comm_unique_id.restype = i32
+    lib.ctr_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.ctr_comm_init.restype = i32
+    lib.ctr_comm_destroy.argtypes = [vp]
+    lib.ctr_comm_destroy.restype = i32
+    lib.ctr_allgather_offsets.argtypes = [vp, vp, vp, vp]
+    lib.ctr_allgather_offsets.restype = i32
+    lib.ctr_gather_mesh.argtypes = [vp, i32, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.ctr_gather_mesh.restype = i32
+    lib.ctr_gathered_fetch.argtypes = [vp, vp, vp, vp]
+    lib.ctr_gathered_fetch.restype = i32
     lib.ctr_host_alloc.argtypes = [vp, ctypes.c_uint64, ctypes.POINTER(vp)]
     lib.ctr_host_alloc.restype = i32
     lib.ctr_host_free.argtypes = [vp, vp]
@@ -243,6 +255,51 @@ class Engine(object):
         stream, behind its last kernel (None: off): a collective can send the counts without a host round trip."""
         self._check(self.lib.ctr_mt3d_publish_counts(self.h, ctypes.c_void_p(int(device_ptr)) if device_ptr else None),
                     "ctr_mt3d_publish_counts")
+
+    # ------------------------------------------------------------------ multi-GPU (NCCL inside the library)
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id (rank 0 makes it, the host sends it to the other ranks by any means)."""
+        lib = load_library()
+        buf = ctypes.create_string_buffer(128)
+        rc = lib.ctr_comm_unique_id(buf)
+        if rc != 0:
+            raise EngineError("ctr_comm_unique_id failed (%d): NCCL could not be loaded" % rc)
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, nranks):
+        self._comm = (int(rank), int(nranks))
+        self._check(self.lib.ctr_comm_init(self.h, ctypes.c_char_p(bytes(unique_id)), int(rank), int(nranks)), "ctr_comm_init")
+
+    def comm_destroy(self):
+        self._check(self.lib.ctr_comm_destroy(self.h), "ctr_comm_destroy")
+
+    def allgather_offsets(self):
+        """NCCL all-gather of the last 3D run's device counts.  Returns (counts [nranks, 2], this rank's exclusive
+        (vertex, triangle) offsets, totals)."""
+        rank, nranks = self._comm
+        counts = np.zeros((nranks, 2), dtype=np.int64)
+        off = np.zeros(2, dtype=np.int64)
+        tot = np.zeros(2, dtype=np.int64)
+        self._check(self.lib.ctr_allgather_offsets(self.h, _ptr(counts), _ptr(off), _ptr(tot)), "ctr_allgather_offsets")
+        return counts, off, tot
+
+    def gather_mesh(self, root=0):
+        """Collective: the ranks' meshes to `root` (ncclSend / ncclRecv of what each rank has).  On the root returns
+        dict(verts, normals, tris) with global triangle ids; None elsewhere."""
+        rank, nranks = self._comm
+        tv, tt = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self.lib.ctr_gather_mesh(self.h, int(root), ctypes.byref(tv), ctypes.byref(tt)), "ctr_gather_mesh")
+        if rank != root:
+            return None
+        flags, _ = self._last3
+        gd = np.float64 if flags & GEOM_F64 else np.float32
+        V, T = int(tv.value), int(tt.value)
+        a_v = np.empty((V, 3), gd)
+        a_n = np.empty((V, 3), gd) if flags & WANT_NORMALS else None
+        a_t = np.empty((T, 3), np.int32)
+        self._check(self.lib.ctr_gathered_fetch(self.h, _ptr(a_v), _ptr(a_n), _ptr(a_t)), "ctr_gathered_fetch")
+        return dict(verts=a_v, normals=a_n, tris=a_t)
 
     def mt3d_finish(self):
         c = Mt3dCounts()

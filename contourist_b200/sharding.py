@@ -57,3 +57,28 @@ def extract_sharded(engine, slab, a, b, n0, value, origin=(0, 0, 0), delta=(1, 1
     if out["tris"] is not None:
         out["tris"] = out["tris"].astype(np.int64) + int(off[0])
     return c, out, off, tot
+
+
+def init_native_comm(engine):
+    """Give `engine` an NCCL communicator inside the C library (ctr_comm_init) spanning the ranks of the initialised
+    torch.distributed group: rank 0 makes the NCCL id, torch.distributed carries its 128 bytes to the others (the only
+    thing it is used for here).  Afterwards engine.allgather_offsets() / engine.gather_mesh() are the collectives of the
+    path, issued by the library on the engine's stream."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    engine.comm_init(box[0], rank, world)
+    return rank, world
+
+
+def extract_and_gather(engine, slab, a, b, n0, value, origin=(0, 0, 0), delta=(1, 1, 1), flags=0, root=0, shape=None, dtype=None):
+    """One rank's part of a sharded extraction with the mesh gathered on `root` (north_star: "NCCL ... only for an
+    allgather of per-rank triangle counts and vertex offsets, plus an optional gather of the mesh to rank 0").
+    slab holds planes slab_with_halo(a, b, n0); engine must have a native communicator (init_native_comm).
+    Returns (counts of this rank, all counts [world, 2], offsets of this rank, totals, gathered mesh or None)."""
+    lo, hi, kw = slab_with_halo(a, b, n0)
+    c = engine.mt3d_run(slab, value, origin=origin, delta=delta, flags=flags, shape=shape, dtype=dtype, **kw)
+    counts, off, tot = engine.allgather_offsets()
+    mesh = engine.gather_mesh(root)
+    return c, counts, off, tot, mesh

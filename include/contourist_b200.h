@@ -156,6 +156,26 @@ CTR_API int ctr_mt3d_orient_reference(ctr_ctx* ctx, int64_t* n_components, int64
 CTR_API int ctr_mt3d_select_seeded(ctr_ctx* ctx, const int32_t* seed_voxels, int64_t n_seeds, int64_t* n_verts,
                                    int64_t* n_tris, int64_t* n_voxels);
 
+/* ---- multi-GPU: one process per GPU, z-slabs -----------------------------------------------------
+ * Every rank runs ctr_mt3d_run on its slab (i_lo / i_hi / plane_offset) independently; NCCL carries only the counts and,
+ * optionally, the mesh.  NCCL is bound at run time (the libnccl.so.2 already in the process, else the loader path).
+ *   ctr_comm_unique_id    : rank 0 makes the 128-byte id (ncclGetUniqueId); the host distributes it by any means
+ *   ctr_comm_init         : ncclCommInitRank on the context's device; from then on every 3D run of the context
+ *                           publishes {n_verts, n_tris} on the device (as ctr_mt3d_publish_counts does)
+ *   ctr_allgather_offsets : ncclAllGather of those device counts on the context's stream (no host round trip before the
+ *                           collective) -> counts[nranks][2] (may be NULL), this rank's exclusive offsets [2], totals [2]
+ *   ctr_gather_mesh       : after ctr_allgather_offsets: positions, normals (if computed) and triangles of every rank to
+ *                           `root` by grouped ncclSend / ncclRecv of exactly the bytes each rank has; triangle ids are
+ *                           made global on the root (local id + the rank's vertex offset).  Collective: every rank calls it.
+ *   ctr_gathered_fetch    : root only: copy the gathered mesh to host buffers of total_verts x 3 (geometry type of the
+ *                           runs) and total_tris x 3 int32.                                                          */
+CTR_API int ctr_comm_unique_id(void* id128);
+CTR_API int ctr_comm_init(ctr_ctx* ctx, const void* id128, int rank, int nranks);
+CTR_API int ctr_comm_destroy(ctr_ctx* ctx);
+CTR_API int ctr_allgather_offsets(ctr_ctx* ctx, int64_t* counts, int64_t* my_offsets, int64_t* totals);
+CTR_API int ctr_gather_mesh(ctr_ctx* ctx, int root, int64_t* total_verts, int64_t* total_tris);
+CTR_API int ctr_gathered_fetch(ctr_ctx* ctx, void* verts, void* normals, int32_t* tris);
+
 /* The reference's mesh post-processing on the device mesh of the LAST ctr_mt3d_run:
  *   tetrahedral.py:190-215     quantize_interpolations(divisions)   vertices in one cell of the divisions grid merge
  *   tetrahedral.py:353-375     remove_tiny_simplices(epsilon)       tiny simplices collapse to a point and go
