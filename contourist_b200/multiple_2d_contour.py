@@ -21,19 +21,30 @@ class Multiple2DContourGrid(object):
         self.value_to_contour_sequences = None
         self.segments = None
 
+    MAX_LEVELS_PER_PASS = 64          # ctr_mt2d_params.nlevels: one GPU pass classifies against up to 64 levels
+
     def get_contours_dictionary(self):
+        """{value: [(closed, points[k, 2]), ...]} (multiple_2d_contour.py:17-30).  One GPU pass per 64 distinct levels;
+        the engine applies grid_field.from_grid_coordinates (x * delta + mins) itself, so the points come back in world
+        coordinates as arrays (iterate them like the reference's lists of points)."""
         grid = self.grid
         levels = sorted(set(float(v) for v in self.values))
         eng = E.default_engine()
-        eng.mt2d_run(grid.samples(0), levels, flags=E.GEOM_F64)
-        seg = self.segments = eng.mt2d_fetch()
-        order = np.argsort(seg["level"], kind="stable")
-        bounds = np.searchsorted(seg["level"][order], np.arange(len(levels) + 1))
+        field = grid.samples(0)
         out = {}
-        for li, value in enumerate(levels):
-            sel = order[bounds[li]:bounds[li + 1]]
-            grid_contours = triangulated.chain_segments(seg["keys"][sel], seg["pos"][sel])
-            out[value] = [(closed, [grid.from_grid_coordinates(p) for p in pts]) for closed, pts in grid_contours]
+        self.segments = []
+        for c0 in range(0, len(levels), self.MAX_LEVELS_PER_PASS):
+            chunk = levels[c0:c0 + self.MAX_LEVELS_PER_PASS]
+            eng.mt2d_run(field, chunk, origin=tuple(grid.mins), delta=tuple(grid.delta), flags=E.GEOM_F64)
+            seg = eng.mt2d_fetch()
+            self.segments.append(seg)
+            order = np.argsort(seg["level"], kind="stable")
+            bounds = np.searchsorted(seg["level"][order], np.arange(len(chunk) + 1))
+            for li, value in enumerate(chunk):
+                sel = order[bounds[li]:bounds[li + 1]]
+                out[value] = triangulated.chain_segments(seg["keys"][sel], seg["pos"][sel])
+        if len(self.segments) == 1:
+            self.segments = self.segments[0]
         self.value_to_contour_sequences = {v: out[float(v)] for v in self.values}
         return self.value_to_contour_sequences
 

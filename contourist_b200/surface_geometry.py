@@ -86,8 +86,10 @@ class SurfaceGeometry(object):
         """Consistent winding per connected component + the reference's outward rule (surface_geometry.py:52-140):
         in every component the triangle with the largest |cross.x| at the max-x vertex gets cross.x > 0.
         Winding is propagated across shared edges by solving the parity constraints on a doubled graph
-        (vectorised; the reference walks a DFS).  `link_filter(k1, k2) -> bool array` may veto links
-        (MorphTriangles uses it for time compatibility, morph_geometry.py:61-67)."""
+        (vectorised; the reference walks a DFS).  `link_filter(k1, k2) -> bool array` may veto links between triangle
+        numbers (MorphTriangles uses it for time compatibility, morph_geometry.py:61-67); the reference's own form,
+        `compatible_triangle_test(triangle1, triangle2) -> bool` on two triangles (tuples of vertex indices, as stored in
+        self.triangles; surface_geometry.py:52-56,118), is honoured the same way, one call per linked pair."""
         from scipy.sparse import coo_matrix
         from scipy.sparse.csgraph import connected_components
         V, T = self._arrays(self.vertices, self.triangles)
@@ -105,6 +107,11 @@ class SurfaceGeometry(object):
         same_edge = ks[1:] == ks[:-1]
         k1, k2 = ts[:-1][same_edge], ts[1:][same_edge]
         rel = (us[:-1][same_edge] == us[1:][same_edge]).astype(np.int64)      # same direction -> one must flip
+        if link_filter is None and compatible_triangle_test is not None:
+            as_given = [tuple(int(x) for x in t) for t in T]
+
+            def link_filter(a, b):
+                return np.array([bool(compatible_triangle_test(as_given[i], as_given[j])) for i, j in zip(a, b)], dtype=bool)
         if link_filter is not None and len(k1):
             ok = link_filter(k1, k2)
             k1, k2, rel = k1[ok], k2[ok], rel[ok]

@@ -53,22 +53,33 @@ def adjacent_pairs(low_pair, high_pair):
                tuple(int(x) for x in low + adjacency_array[(high_index + hshift) % n]))
 
 
-def chain_segments(keys2, pos2):
-    """Polylines from a segment soup.  keys2 [S,2] uint64 end keys, pos2 [S,2,2] end points.
-    Returns [(closed, points[k,2])].  Open polylines start at their smaller end key; closed ones at their smallest
-    key, towards the smaller neighbour.  Consecutive np.allclose points are dropped (triangulated.py:269)."""
-    if len(keys2) == 0:
-        return []
+def _graph(keys2, pos2):
+    "vertices (unique end keys, in key order), their points, unique undirected edges, degrees"
     flat = keys2.reshape(-1)
     uk, first, inv = np.unique(flat, return_index=True, return_inverse=True)
     pts = pos2.reshape(-1, 2)[first]
     ends = inv.reshape(-1, 2)
-    # unique undirected segments
     e = np.unique(np.sort(ends, axis=1), axis=0)
     e = e[e[:, 0] != e[:, 1]]
-    nk = len(uk)
-    deg = np.bincount(e.reshape(-1), minlength=nk)
-    # adjacency in CSR form
+    deg = np.bincount(e.reshape(-1), minlength=len(uk))
+    return uk, pts, e, deg
+
+
+def _finish(closed, p):
+    "consecutive np.allclose points dropped (triangulated.py:269); a chain that returns to its start is closed"
+    if len(p) > 1:
+        keep = np.ones(len(p), dtype=bool)
+        keep[1:] = ~np.all(np.abs(p[1:] - p[:-1]) <= 1e-8 + 1e-5 * np.abs(p[:-1]), axis=1)
+        p = p[keep]
+    if len(p) > 1 and np.allclose(p[0], p[-1]):
+        closed = True
+    return (bool(closed), p)
+
+
+def _chain_walk(pts, e, deg):
+    """The per-vertex walk (triangulated.py:236-293 with a fixed order): used when some key has more than two
+    neighbours (a sample exactly on the level), where the reference's result is a matter of visiting order."""
+    nk = len(deg)
     both = np.concatenate([e, e[:, ::-1]])
     order = np.lexsort((both[:, 1], both[:, 0]))
     both = both[order]
@@ -96,16 +107,94 @@ def chain_segments(keys2, pos2):
     for s in list(np.nonzero(deg < 2)[0]) + list(np.nonzero(deg >= 2)[0]):
         if visited[s]:
             continue
-        closed = deg[s] >= 2
-        chain = walk(s)
-        p = pts[chain]
-        if len(p) > 1:
-            keep = np.ones(len(p), dtype=bool)
-            keep[1:] = ~np.all(np.abs(p[1:] - p[:-1]) <= 1e-8 + 1e-5 * np.abs(p[:-1]), axis=1)
-            p = p[keep]
-        if len(p) > 1 and np.allclose(p[0], p[-1]):
-            closed = True
-        out.append((bool(closed), p))
+        out.append(_finish(deg[s] >= 2, pts[walk(s)]))
+    return out
+
+
+def rank_darts(e, deg):
+    """List ranking of the contours of a graph whose vertices have at most two neighbours (paths and cycles), without
+    walking them (triangulated.py:221-305 does it a vertex at a time).  Every edge {u, v} becomes two darts u->v, v->u;
+    the successor of a dart arriving at b is the dart that leaves b along b's OTHER edge, or -- at a path's end -- the
+    dart back along the same edge.  A path of m edges is then one cycle of 2m darts (there and back), a closed contour
+    of m edges two cycles of m darts (one per direction).  Pointer jumping (log2 of the longest contour rounds, each a
+    few gathers over all darts) gives every dart the first dart of its cycle and its position behind it:
+      first dart = the dart leaving the path's smaller end / the cycle's smallest vertex (vertex numbers are key ranks);
+      of a closed contour's two directions the one that starts towards the smaller neighbour is kept;
+      of a path's there-and-back tour the first half.
+    Returns (tail, head, start dart of each dart's cycle, position, cycle length, keep mask, open mask)."""
+    ne = len(e)
+    nd = 2 * ne
+    tail = np.empty(nd, dtype=np.int64)
+    head = np.empty(nd, dtype=np.int64)
+    tail[0::2], head[0::2] = e[:, 0], e[:, 1]
+    tail[1::2], head[1::2] = e[:, 1], e[:, 0]
+    # the (at most two) darts that leave each vertex
+    order = np.argsort(tail, kind="stable")
+    first = np.searchsorted(tail[order], np.arange(len(deg)))
+    out0 = order[np.minimum(first, nd - 1)]
+    out1 = np.where(deg >= 2, order[np.minimum(first + 1, nd - 1)], -1)
+    d = np.arange(nd, dtype=np.int64)
+    rev = d ^ 1
+    o0, o1 = out0[head], out1[head]
+    succ = np.where(o0 != rev, o0, o1)
+    succ = np.where(succ < 0, rev, succ)                   # a path's end: turn round
+    # first dart of every cycle: smallest (not leaving an end, tail vertex), carried with the dart's own number
+    prio = (np.where(deg[tail] == 1, 0, 1).astype(np.int64) * (len(deg) + 1) + tail) * nd + d
+    best, jump = prio.copy(), succ.copy()
+    while True:
+        nb = np.minimum(best, best[jump])
+        jump = jump[jump]
+        if np.array_equal(nb, best):
+            break
+        best = nb
+    start = best % nd
+    # position behind the first dart: cut every cycle in front of its first dart, rank the lists
+    nxt = np.where(succ == start, nd, succ)
+    dist = np.where(nxt == nd, 0, 1).astype(np.int64)
+    nxt = np.append(nxt, nd)
+    dist = np.append(dist, 0)
+    while True:
+        live = nxt[:nd] != nd
+        if not live.any():
+            break
+        dist[:nd] += dist[nxt[:nd]]
+        nxt[:nd] = nxt[nxt[:nd]]
+    dist = dist[:nd]
+    length = dist[start] + 1
+    pos = length - 1 - dist
+    twin = start[rev]
+    is_open = twin == start
+    keep = np.where(is_open, pos < length // 2, head[start] < head[twin])
+    return tail, head, start, pos, length, keep, is_open
+
+
+def chain_segments(keys2, pos2):
+    """Polylines from a segment soup.  keys2 [S,2] uint64 end keys, pos2 [S,2,2] end points.
+    Returns [(closed, points[k,2])], open polylines first.  Open polylines start at their smaller end key; closed ones
+    at their smallest key, towards the smaller neighbour.  Consecutive np.allclose points are dropped
+    (triangulated.py:269).  Vectorised list ranking (rank_darts); the per-vertex walk only where a key has more than
+    two neighbours."""
+    if len(keys2) == 0:
+        return []
+    uk, pts, e, deg = _graph(np.asarray(keys2), np.asarray(pos2))
+    if len(e) == 0:
+        return []
+    if deg.max() > 2:
+        return _chain_walk(pts, e, deg)
+    tail, head, start, pos, length, keep, is_open = rank_darts(e, deg)
+    # kept darts grouped by contour: open ones first (by their first vertex), then closed ones, each in position order
+    kd = np.nonzero(keep)[0]
+    closed_d = ~is_open[kd]
+    grp = np.lexsort((pos[kd], tail[start[kd]], closed_d))
+    kd = kd[grp]
+    first_of = np.nonzero(pos[kd] == 0)[0]                 # one per contour, in output order
+    bounds = np.append(first_of, len(kd))
+    out = []
+    for q in range(len(first_of)):
+        dd = kd[bounds[q]:bounds[q + 1]]
+        closed = not is_open[dd[0]]
+        verts = np.concatenate([[tail[dd[0]]], head[dd[:-1]] if closed else head[dd]])
+        out.append(_finish(closed, pts[verts]))
     return out
 
 

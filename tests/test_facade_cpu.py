@@ -205,3 +205,93 @@ def test_morph_triangle_orientation_agrees_with_reference_on_a_smooth_field():
     assert len(got) == len(want) == len(tris)
     assert len(want & got) >= 0.995 * len(tris)
     assert set(tuple(sorted(t)) for t in want) == set(tuple(sorted(t)) for t in got)
+
+
+def _soup(field, z):
+    from oracle import mt2d
+    r = mt2d.extract_level(field, z)
+    return r["seg_keys"], r["pos"][np.searchsorted(r["keys"], r["seg_keys"])]
+
+
+def test_vectorised_chaining_equals_the_walk():
+    """chain_segments ranks the contours by pointer jumping over darts (rank_darts); the result must be the per-vertex
+    walk's (triangulated.py:236-293 with a fixed order): same polylines, same order, same start and direction."""
+    from contourist_b200 import triangulated
+    rng = np.random.default_rng(4)
+    n_poly = 0
+    for n in (9, 33, 120, 257):
+        g = np.linspace(-2, 2, n)
+        X, Y = np.meshgrid(g, g, indexing="ij")
+        f = np.sqrt(np.sin(3 * X + Y * Y) ** 2 + np.cos(4 * Y + X * X) ** 2) + 0.08 * rng.standard_normal((n, n))
+        for z in (0.25, 0.6, 1.0):
+            k2, p2 = _soup(f, z)
+            if len(k2) == 0:
+                assert triangulated.chain_segments(k2, p2) == []
+                continue
+            uk, pts, e, deg = triangulated._graph(k2, p2)
+            assert deg.max() <= 2
+            want = triangulated._chain_walk(pts, e, deg)
+            got = triangulated.chain_segments(k2, p2)
+            assert len(got) == len(want)
+            for (ca, pa), (cb, pb) in zip(got, want):
+                assert ca == cb and np.array_equal(pa, pb)
+            n_poly += len(got)
+    assert n_poly > 500
+
+
+def test_chaining_with_junctions_takes_the_walk():
+    "a sample exactly on the level gives its keys more than two neighbours: the fixed-order walk decides"
+    from contourist_b200 import triangulated
+    rng = np.random.default_rng(1)
+    f = rng.integers(-1, 2, size=(15, 15)).astype(float)
+    k2, p2 = _soup(f, 0.0)
+    uk, pts, e, deg = triangulated._graph(k2, p2)
+    assert deg.max() > 2
+    got = triangulated.chain_segments(k2, p2)
+    want = triangulated._chain_walk(pts, e, deg)
+    assert len(got) == len(want) and all(a == b and np.array_equal(p, q) for (a, p), (b, q) in zip(got, want))
+
+
+def test_crossing_scan_with_skip_and_plateaus():
+    """_segments._scan_samples restates grid_field.py:64-84 for any skip; against a literal transcription of the loop."""
+    from contourist_b200 import _segments
+    rng = np.random.default_rng(2)
+    arr = rng.standard_normal((9, 8, 10))
+    arr[2:5, 3:6, 4:8] = 0.3 + 1e-7 * rng.standard_normal((3, 3, 4))          # an np.allclose plateau on the level
+    for skip in (1, 2, 3):
+        fmax, fmin, p, q = _segments._scan_samples(arr, 0.3, skip)
+        want = set()
+        n = [s - 1 for s in arr.shape]
+        for i in range(0, n[0], skip):
+            for j in range(0, n[1], skip):
+                for k in range(0, n[2], skip):
+                    for index in range(1, 8):
+                        o = [((index >> s) & 1) * skip for s in range(3)]
+                        v1 = (i + o[0], j + o[1], k + o[2])
+                        if all(v1[a] < arr.shape[a] for a in range(3)) and (arr[i, j, k] - 0.3) * (arr[v1] - 0.3) < 0:
+                            want.add(((i, j, k), v1))
+        got = set((tuple(int(x) for x in a), tuple(int(x) for x in b)) for a, b in zip(p, q))
+        assert got == want and len(want) > 0
+    from oracle import mt3d
+    _, _, keys = mt3d.crossing_segments(arr, 0.3)
+    _, _, p, q = _segments._scan_samples(arr, 0.3, 1)
+    assert len(keys) == len(p)
+
+
+def test_orient_triangles_honours_compatible_triangle_test():
+    """surface_geometry.py:52-56: orient_triangles(compatible_triangle_test) -- the reference's first positional
+    parameter -- vetoes links exactly like the vectorised link_filter."""
+    from contourist_b200 import surface_geometry
+    V = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [2, 0, 0], [2, 1, 0]], dtype=float)
+    T = np.array([[0, 1, 2], [1, 2, 3], [1, 4, 3], [4, 5, 3]])         # a strip of four triangles, mixed windings
+    seen = []
+
+    def veto_middle(t1, t2):
+        seen.append((t1, t2))
+        return not ({1, 3} <= set(t1) and {1, 3} <= set(t2))           # cut the strip at the edge (1, 3)
+    a = surface_geometry.SurfaceGeometry(V, T).orient_triangles(veto_middle)
+    mask = lambda k1, k2: np.array([not ({1, 3} <= set(T[i]) and {1, 3} <= set(T[j])) for i, j in zip(k1, k2)])
+    b = surface_geometry.SurfaceGeometry(V, T).orient_triangles(link_filter=mask)
+    c = surface_geometry.SurfaceGeometry(V, T).orient_triangles()
+    assert a == b and len(seen) == 3 and all(isinstance(t, tuple) for pair in seen for t in pair)
+    assert len(c) == len(a) == 4
