@@ -51,6 +51,7 @@ struct ctr_ctx {
   int last_kind = 0;         // 0 none, 3 = mt3d, 2 = mt2d, 4 = mp4d
   uint32_t last_flags = 0;
   int64_t last_counts[8] = {};
+  int64_t poly_counts[2] = {};            // 2D: polylines / points of the last ctr_mt2d_polylines
   unsigned char last3_params[160] = {};   // parameters of the last completed ctr_mt3d_run
   long long* publish3 = nullptr;          // ctr_mt3d_publish_counts: device {n_verts, n_tris} behind every 3D run
   unsigned last3_edited = 0;              // passes that have rewritten the device mesh of that run: 1 seeded selection, 2 clean-up

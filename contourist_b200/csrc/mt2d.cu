@@ -554,6 +554,7 @@ int run2d(ctr_ctx* ctx, const ctr_mt2d_params* p, ctr_mt2d_counts* out) {
     }
   }
   ctx->last_kind = 2;
+  ctx->poly_counts[0] = ctx->poly_counts[1] = 0;
   ctx->last_flags = p->flags;
   ctx->last_counts[0] = (int64_t)nseg;
   return 0;

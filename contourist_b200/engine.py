@@ -45,6 +45,10 @@ class CleanCounts(ctypes.Structure):
                 ("n_flipped", ctypes.c_int64)]
 
 
+class PolyCounts(ctypes.Structure):
+    _fields_ = [("n_polylines", ctypes.c_int64), ("n_points", ctypes.c_int64), ("junction_levels", ctypes.c_uint64)]
+
+
 class Mt3dCounts(ctypes.Structure):
     _fields_ = [("n_verts", ctypes.c_int64), ("n_tris", ctypes.c_int64), ("n_active_cells", ctypes.c_int64),
                 ("n_crossings", ctypes.c_int64), ("n_codes", ctypes.c_int64),
@@ -109,6 +113,10 @@ def load_library():
     lib.ctr_gather_mesh.restype = i32
     lib.ctr_gathered_fetch.argtypes = [vp, vp, vp, vp]
     lib.ctr_gathered_fetch.restype = i32
+    lib.ctr_mt2d_polylines.argtypes = [vp, ctypes.POINTER(PolyCounts)]
+    lib.ctr_mt2d_polylines.restype = i32
+    lib.ctr_mt2d_polylines_fetch.argtypes = [vp] + [vp] * 6
+    lib.ctr_mt2d_polylines_fetch.restype = i32
     lib.ctr_host_alloc.argtypes = [vp, ctypes.c_uint64, ctypes.POINTER(vp)]
     lib.ctr_host_alloc.restype = i32
     lib.ctr_host_free.argtypes = [vp, vp]
@@ -517,6 +525,32 @@ class Engine(object):
         pos = np.empty((S, 2, 2), dtype=gd)
         self._check(self.lib.ctr_mt2d_fetch(self.h, _ptr(lvl), _ptr(keys), _ptr(pos)), "ctr_mt2d_fetch")
         return dict(level=lvl, keys=keys, pos=pos)
+
+    def mt2d_polylines(self):
+        """Polylines of the last 2D run, chained on the device (ctr_mt2d_polylines).  Returns None when some level has a
+        key on more than two segments (the caller chains such runs with triangulated.chain_segments), else a list per
+        level index of (closed, points[k, 2]) in the canonical order: open contours first, by start key."""
+        flags, c = self._last2
+        pc = PolyCounts()
+        self._check(self.lib.ctr_mt2d_polylines(self.h, ctypes.byref(pc)), "ctr_mt2d_polylines")
+        if pc.junction_levels:
+            return None
+        P, N = int(pc.n_polylines), int(pc.n_points)
+        gd = np.float64 if flags & GEOM_F64 else np.float32
+        lvl = np.empty(P, np.int32)
+        closed = np.empty(P, np.uint8)
+        key = np.empty(P, np.uint64)
+        off = np.empty(P, np.uint32)
+        length = np.empty(P, np.uint32)
+        pts = np.empty((N, 2), gd)
+        if P:
+            self._check(self.lib.ctr_mt2d_polylines_fetch(self.h, _ptr(lvl), _ptr(closed), _ptr(key), _ptr(off), _ptr(length),
+                                                          _ptr(pts)), "ctr_mt2d_polylines_fetch")
+        nlev = len(self._keep_levels)
+        out = [[] for _ in range(nlev)]
+        for q in np.lexsort((key, closed & 1, lvl)):
+            out[int(lvl[q])].append((bool(closed[q]), pts[int(off[q]):int(off[q]) + int(length[q])]))
+        return out
 
     # ------------------------------------------------------------------ 4D
     def mp4d_run(self, field, value, origin=(0.0,) * 4, delta=(1.0,) * 4, flags=0, nbins=100, shape=None, dtype=None):

@@ -21,6 +21,7 @@ class Multiple2DContourGrid(object):
         self.value_to_contour_sequences = None
         self.segments = None
 
+    keep_segments = False             # True: fetch the segment soup (self.segments) and chain it on the host
     MAX_LEVELS_PER_PASS = 64          # ctr_mt2d_params.nlevels: one GPU pass classifies against up to 64 levels
 
     def get_contours_dictionary(self):
@@ -36,6 +37,12 @@ class Multiple2DContourGrid(object):
         for c0 in range(0, len(levels), self.MAX_LEVELS_PER_PASS):
             chunk = levels[c0:c0 + self.MAX_LEVELS_PER_PASS]
             eng.mt2d_run(field, chunk, origin=tuple(grid.mins), delta=tuple(grid.delta), flags=E.GEOM_F64)
+            polys = None if self.keep_segments else eng.mt2d_polylines()       # chained on the device
+            if polys is not None:
+                for li, value in enumerate(chunk):
+                    out[value] = polys[li]
+                continue
+            # some key lies on more than two segments (a sample exactly on a level): the fixed-order walk decides
             seg = eng.mt2d_fetch()
             self.segments.append(seg)
             order = np.argsort(seg["level"], kind="stable")
@@ -43,8 +50,7 @@ class Multiple2DContourGrid(object):
             for li, value in enumerate(chunk):
                 sel = order[bounds[li]:bounds[li + 1]]
                 out[value] = triangulated.chain_segments(seg["keys"][sel], seg["pos"][sel])
-        if len(self.segments) == 1:
-            self.segments = self.segments[0]
+        self.segments = self.segments[0] if len(self.segments) == 1 else (self.segments or None)
         self.value_to_contour_sequences = {v: out[float(v)] for v in self.values}
         return self.value_to_contour_sequences
 

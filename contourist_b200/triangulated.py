@@ -291,6 +291,13 @@ class Grid2DContour(object):
         eng = E.default_engine()
         eng.mt2d_run(self._field(), [float(self.z)], origin=self.origin, delta=self.delta, flags=E.GEOM_F64)
         self.segments = eng.mt2d_fetch()
+        if self.end_points is None or self.full_scan:
+            polys = eng.mt2d_polylines()                   # chained on the device; None: a key on more than two segments
+            if polys is not None:
+                self.contours = polys[0]
+                if self.callback:
+                    self.callback(self)
+                return self.contours
         if self.end_points is not None and not self.full_scan:
             keep = seeded_segments(self._value_at, float(self.z), self.m, self.segments["keys"], self.end_points)
             self.segments = {k: (v[keep] if isinstance(v, np.ndarray) and len(v) == len(keep) else v)

@@ -235,6 +235,24 @@ CTR_API int ctr_mt2d_run(ctr_ctx* ctx, const ctr_mt2d_params* p, ctr_mt2d_counts
  * (world coordinates of the two end points).  Order: by square, triangle, level.                          */
 CTR_API int ctr_mt2d_fetch(ctr_ctx* ctx, uint8_t* seg_level, uint64_t* seg_keys, void* seg_pos);
 
+/* Polylines of the LAST ctr_mt2d_run, on the device.  Replaces
+ *   triangulated.py:221-305  find_adjacencies / get_contour_sequences (the per-vertex chaining of contour pairs)
+ *   triangulated.py:269      consecutive np.allclose points dropped
+ * by list ranking over the segments' darts (pointer jumping).  Open contours start at their smaller end key, closed ones
+ * at their smallest key towards the smaller neighbour (the reference's order follows CPython set iteration).  A level
+ * in which some key lies on more than two segments (a sample exactly on the level) is reported in junction_levels and
+ * nothing is chained: there the order of visits decides and the binding's fixed-order walk is the definition.
+ * _fetch: per polyline its level index, closed flag (bit 0: a cycle of segments, bit 1: an open chain whose ends are
+ * np.allclose), start key, first point and number of points; points [n_points][2]
+ * in the run's geometry type.  Polylines come in no particular order (sort by level / closed / start key).           */
+typedef struct {
+  int64_t n_polylines, n_points;
+  uint64_t junction_levels;      /* bit l set: level l has a key with more than two segments; nothing was chained     */
+} ctr_poly_counts;
+CTR_API int ctr_mt2d_polylines(ctr_ctx* ctx, ctr_poly_counts* out);
+CTR_API int ctr_mt2d_polylines_fetch(ctr_ctx* ctx, int32_t* level, uint8_t* closed, uint64_t* start_key, uint32_t* offset,
+                                     uint32_t* length, void* points);
+
 /* ---- 4D marching pentatopes + morph triangles ---------------------------------------------------
  * Replaces, for an array-backed field f[i][j][k][l] (l = time, contiguous), the reference's
  *   pentatopes.py:101-106,216-291   find_tetrahedra (flood fill -> full scan), enumerate_voxel_tetrahedra,

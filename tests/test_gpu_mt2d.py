@@ -130,3 +130,70 @@ def test_full_size_properties_16384(engine):
     assert on_edge.all()
     del f
     torch.cuda.empty_cache()
+
+
+def _host_chain(o, li):
+    from contourist_b200 import triangulated
+    sel = o["level"] == li
+    return triangulated.chain_segments(o["keys"][sel], o["pos"][sel])
+
+
+@pytest.mark.parametrize("geom64", [True, False])
+def test_device_polylines_equal_host_chaining(engine, geom64):
+    """ctr_mt2d_polylines (list ranking over darts on the device) against triangulated.chain_segments on the fetched
+    segment soup (itself equal to the per-vertex walk, tests/test_facade_cpu.py): same polylines in the same order,
+    same start, same direction, same points."""
+    from contourist_b200 import engine as E
+    rng = np.random.default_rng(8)
+    total = 0
+    for n0, n1 in ((9, 9), (65, 40), (200, 333)):
+        g0, g1 = np.linspace(-2, 2, n0), np.linspace(-2, 2, n1)
+        X, Y = np.meshgrid(g0, g1, indexing="ij")
+        f = np.sqrt(np.sin(3 * X + Y * Y) ** 2 + np.cos(4 * Y + X * X) ** 2) + 0.07 * rng.standard_normal((n0, n1))
+        if not geom64:
+            f = f.astype(np.float32)
+        levels = [0.2, 0.45, 0.7, 0.95, 1.3]
+        engine.mt2d_run(f, levels, origin=(-1.0, 2.0), delta=(0.5, 0.25), flags=E.GEOM_F64 if geom64 else 0)
+        polys = engine.mt2d_polylines()
+        o = engine.mt2d_fetch()
+        assert polys is not None and len(polys) == len(levels)
+        for li in range(len(levels)):
+            want = _host_chain(o, li)
+            got = polys[li]
+            assert len(got) == len(want)
+            for (ca, pa), (cb, pb) in zip(got, want):
+                assert ca == cb and np.array_equal(pa, pb)
+            total += len(got)
+    assert total > 300
+
+
+def test_device_polylines_report_junctions(engine):
+    rng = np.random.default_rng(1)
+    f = rng.integers(-1, 2, size=(15, 15)).astype(float)
+    engine.mt2d_run(f, [0.0])
+    assert engine.mt2d_polylines() is None                    # a sample on the level: the host walk decides
+    engine.mt2d_run(f, [0.5])
+    polys = engine.mt2d_polylines()
+    o = engine.mt2d_fetch()
+    want = _host_chain(o, 0)
+    assert len(polys[0]) == len(want) and all(a == b and np.array_equal(p, q) for (a, p), (b, q) in zip(polys[0], want))
+
+
+def test_more_than_64_levels_through_the_facade(engine):
+    from contourist_b200 import multiple_2d_contour
+
+    def f(x, y):
+        return np.sqrt(np.sin(3 * x + y * y) ** 2 + np.cos(4 * y + x * x) ** 2)
+    C = multiple_2d_contour.Linear2DContour(-2, -2, 2, 2, 0.05, 0.05, f, breakpoints=100)
+    assert len(C.values) == 99
+    D = C.get_contours_dictionary()
+    assert sorted(D) == sorted(C.values)
+    arr = C.grid.samples(0)
+    for value in (C.values[3], C.values[70], C.values[98]):
+        r = mt2d.extract_level(arr, value)
+        n_keys = len(np.unique(np.concatenate([np.round(p, 12) for _, p in D[value]]), axis=0)) if D[value] else 0
+        assert (n_keys > 0) == (len(r["keys"]) > 0)
+        if D[value]:
+            allp = set(map(tuple, np.concatenate([p for _, p in D[value]])))
+            refp = set(map(tuple, r["pos"] * 0.05 - 2.0))
+            assert allp <= refp and len(refp) - len(allp) <= 0.01 * len(refp)       # consecutive np.allclose points are dropped

@@ -78,7 +78,49 @@ def main():
                       "stage_ms": {"count_scan": float(st[1]), "emit": float(st[2])},
                       "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": pk, "unit": "GB/s",
                                    "frac": alg / ms / 1e6 / pk, "algorithmic_bytes": alg, "peak_source": src}}))
-    del f
+    # ---- 2D polylines end to end (a23 / f4): host array in, {level: [(closed, points)]} out, through the drop-in class
+    from contourist_b200 import grid_field, multiple_2d_contour, triangulated
+    hf = eng.pinned_empty("bench_field2d", (n, n), np.float32)     # page-locked host field, as the e2e contract asks
+    hf[:] = f.cpu().numpy()
+    grid = grid_field.FunctionGrid((0.0, 0.0), (n - 1.0, n - 1.0), (1.0, 1.0), hf)
+    C = multiple_2d_contour.Multiple2DContourGrid(grid, levels)
+    import time
+    D = C.get_contours_dictionary()                                # warm-up (buffers)
+    ts = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        D = C.get_contours_dictionary()
+        ts.append(time.perf_counter() - t0)
+    n_poly = sum(len(v) for v in D.values())
+    n_pts = sum(len(p) for v in D.values() for _, p in v)
+    # the chaining alone on the device, and the host restatement (numpy list ranking) on one level as CPU baseline
+    eng.mt2d_run(f.data_ptr(), levels, shape=(n, n), dtype=np.float32, flags=E.GEOM_F64)
+    from contourist_b200.engine import PolyCounts
+    import ctypes
+    pc = PolyCounts()
+    tk = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.lib.ctr_mt2d_polylines(eng.h, ctypes.byref(pc))
+        tk.append(time.perf_counter() - t0)
+    seg = eng.mt2d_fetch()
+    sel = seg["level"] == 7
+    t0 = time.perf_counter()
+    host = triangulated.chain_segments(seg["keys"][sel], seg["pos"][sel])
+    t_host = time.perf_counter() - t0
+    print(json.dumps({"path": "2D polylines end to end (BASELINE configs[1]): Multiple2DContourGrid.get_contours_dictionary(), host array in, polylines out",
+                      "metric": "Gsamples/s", "value": n * n / min(ts) / 1e9, "ms_total": min(ts) * 1e3,
+                      "n_polylines": n_poly, "n_points": n_pts, "levels": 16, "dtype": "f32 field, f64 geometry",
+                      "kernel_ms": {"extract": ms, "chain_on_device (ctr_mt2d_polylines, host-timed)": min(tk) * 1e3},
+                      "e2e": {"value": n * n / min(ts) / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": int(hf.nbytes),
+                              "d2h_bytes_per_step": int(n_pts * 16 + n_poly * 21)},
+                      "cpu_baseline": {"value": int(sel.sum()) / t_host / 1e6, "unit": "Msegments/s chained", "cores": 1, "kind": "port",
+                                       "sample": "level 7 of the same run (%d segments), triangulated.chain_segments (numpy list ranking, the "
+                                                 "restatement of triangulated.py:221-305)" % int(sel.sum())},
+                      "device_chain_msegments_per_s": S / min(tk) / 1e6}))
+    del f, hf, seg, D
     torch.cuda.empty_cache()
 
     # ---- 4D: configs[3]
