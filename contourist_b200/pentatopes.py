@@ -28,6 +28,69 @@ def _pentatope_tiles():
 
 PENTATOPES = np.array(_pentatope_tiles(), dtype=int)
 HYPERCUBE = np.array([(i, j, k, l) for i in (0, 1) for j in (0, 1) for k in (0, 1) for l in (0, 1)], dtype=int)
+OFFSETS4D = np.array([(i, j, k, l) for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1) for l in (-1, 0, 1)
+                      if i != 0 or j != 0 or k != 0 or l != 0], dtype=int)
+
+
+def border_hypervoxels(samples, value):
+    "tetrahedral.py:383-394 border_voxel for every hypervoxel of a 4D sample array: not np.allclose(value, f), min <= value <= max"
+    s = np.asarray(samples, dtype=np.float64)
+    n = [k - 1 for k in s.shape]
+    mn = mx = None
+    allnear = None
+    for c in HYPERCUBE:
+        v = s[tuple(slice(int(o), int(o) + k) for o, k in zip(c, n))]
+        mn = v.copy() if mn is None else np.minimum(mn, v)
+        mx = v.copy() if mx is None else np.maximum(mx, v)
+        near = np.abs(value - v) <= 1e-8 + 1e-5 * np.abs(v)
+        allnear = near if allnear is None else (allnear & near)
+    return (~allnear) & (mn <= value) & (mx >= value)
+
+
+def initial_hypervoxels(samples, value, end_points, border):
+    """Start hypervoxels of the reference's tracker for seed segments (tetrahedral.py:396-441 with the 80 offsets of
+    pentatopes.py:32-39): bisection of every seed down to adjacent points, then each of the two points -- or the first
+    of its 80 neighbours in OFFSETS4D order -- that is a border hypervoxel, with the reference's `visited` set."""
+    samples = np.asarray(samples)
+
+    def f(p):
+        if np.any(np.asarray(p) < 0) or np.any(np.asarray(p) >= np.array(samples.shape)):
+            raise ValueError("seed point %r outside the sample array of shape %r" % (tuple(int(x) for x in p), samples.shape))
+        return float(samples[tuple(int(x) for x in p)])
+
+    def is_border(p):
+        return bool(all(0 <= int(p[a]) < border.shape[a] for a in range(4)) and border[tuple(int(x) for x in p)])
+
+    visited, found = set(), set()
+    for low_point, high_point in np.array(end_points, dtype=int).reshape(-1, 2, 4):
+        low_value, high_value = f(low_point), f(high_point)
+        if low_value > value or high_value < value:
+            (low_point, low_value, high_point, high_value) = (high_point, high_value, low_point, low_value)
+        assert low_value <= value and high_value >= value, \
+            "Bad end points " + repr((tuple(low_point), low_value, tuple(high_point), high_value, value))
+        while np.any(np.abs(low_point - high_point) > 1):
+            mid_point = (low_point + high_point) // 2
+            if f(mid_point) < value:
+                low_point = mid_point
+            else:
+                high_point = mid_point
+        for point in (low_point, high_point):
+            tpoint = tuple(int(x) for x in point)
+            if tpoint in visited:
+                continue
+            visited.add(tpoint)
+            if is_border(point):
+                found.add(tpoint)
+                continue
+            for offset_point in OFFSETS4D + point.reshape(1, 4):
+                toffset = tuple(int(x) for x in offset_point)
+                if toffset in visited:
+                    continue
+                visited.add(toffset)
+                if is_border(offset_point):
+                    found.add(toffset)
+                    break
+    return sorted(found)
 
 
 class GridContour4D(object):
@@ -35,6 +98,7 @@ class GridContour4D(object):
     minimum_ratio = 0.05
     flatten = False
     smooth = None
+    full_scan = False               # set by search_for_endpoints(): the seeds are every crossing segment
 
     def __init__(self, corner, function, value, segment_endpoints, linear_interpolate=True, callback=None):
         self.corner = np.array(corner, dtype=int)
@@ -66,10 +130,43 @@ class GridContour4D(object):
         if self.flatten or self.smooth:
             raise NotImplementedError("flatten / smooth are out of scope (tetrahedral.py:217-351)")
         eng = E.default_engine()
-        self.counts = eng.mp4d_run(self._field(), self.value, flags=E.GEOM_F64 | E.MORPH)
+        field = self._field()
+        seeded = self.end_points is not None and not self.full_scan
+        self.counts = eng.mp4d_run(field, self.value, flags=E.GEOM_F64 | E.MORPH | (E.WANT_KEYS if seeded else 0))
         self._out = eng.mp4d_fetch()
+        if seeded:
+            self._select_seeded(field)
         self.dropped_simplices = int((self._out["keep"] == 0).sum())
         return self._out
+
+    def _select_seeded(self, field):
+        """Explicit seed segments (pentatopes.py:92-106 through tetrahedral.py:396-469): keep the tetrahedra of the
+        80-connected components of border hypervoxels that contain a start hypervoxel.  The engine has extracted the full
+        scan; this restricts its output on the host (a labelling of the border mask), like the 2D seed filter.  A
+        tetrahedron's hypervoxel is the component-wise minimum over the edges of its four vertices (they touch all five
+        corners of its pentatope, the hypervoxel origin among them); components share no vertex, so a morph triangle
+        belongs to the selection iff its first vertex does."""
+        from scipy import ndimage
+        o = self._out
+        border = border_hypervoxels(field, float(self.value))
+        self.start_voxels = initial_hypervoxels(field, float(self.value), self.end_points, border) if len(self.end_points) else []
+        lab, _ = ndimage.label(border, structure=np.ones((3, 3, 3, 3), dtype=bool))
+        want = sorted(set(int(lab[v]) for v in self.start_voxels))
+        n = field.shape
+        lin = (o["keys"] >> np.uint64(4)).astype(np.int64)
+        pmin = np.stack([lin // (n[1] * n[2] * n[3]), (lin // (n[2] * n[3])) % n[1], (lin // n[3]) % n[2], lin % n[3]], axis=1)
+        tets = o["tets"].astype(np.int64)
+        vox = pmin[tets].min(axis=1) if len(tets) else np.zeros((0, 4), np.int64)
+        keep_t = np.isin(lab[tuple(vox.T)], want) if (len(tets) and want) else np.zeros(len(tets), bool)
+        used = np.zeros(len(o["keys"]), bool)
+        used[tets[keep_t].reshape(-1)] = True
+        remap = np.cumsum(used) - 1
+        mt = o["morph_tris"].astype(np.int64)
+        keep_m = used[mt[:, 0, 0]] if len(mt) else np.zeros(0, bool)
+        self._out = dict(o, verts=o["verts"][used], keys=o["keys"][used], lowmin=o["lowmin"][used], morph_verts=o["morph_verts"][used],
+                         tets=remap[tets[keep_t]].astype(np.int32), keep=o["keep"][keep_t],
+                         morph_tris=remap[mt[keep_m]].astype(np.int32))
+        self.selected_voxels = np.isin(lab, want) & border if want else np.zeros_like(border)
 
     def collect_morph_triangles(self, epsilon=1e-7):
         "pentatopes.py:314-368: unique segments, unique triangles over them, time-aware orientation."
@@ -111,6 +208,7 @@ class Delta4DContour(object):
                               linear_interpolate=self.linear_interpolate)
         maker.flatten = self.flatten
         maker.smooth = self.smooth
+        maker.full_scan = True      # this driver only ever passes the complete seed set (grid search)
         return maker
 
     def search_for_endpoints(self, skip=1):

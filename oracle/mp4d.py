@@ -275,3 +275,74 @@ def morph_triangles(v4, tets, epsilon=1e-7):
     tri_ids = sorted(tuple(sorted(sid[p] for p in tri)) for tri in keep)
     seg_arr = np.array([(i, j) if v4[i][-1] <= v4[j][-1] else (j, i) for (i, j) in segs], dtype=np.int64).reshape(-1, 2)
     return seg_arr, np.array(tri_ids, dtype=np.int64).reshape(-1, 3)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Seeded tracking in 4D: GridContour4D inherits the tracker of tetrahedral.py:396-469 with the 16-corner
+# box and the 80 offsets of pentatopes.py:32-39.  Pinned by tests/golden/seeded4d_*.npz (runs of the unmodified reference).
+# ---------------------------------------------------------------------------------------------------
+OFFSETS4D = np.array([(i, j, k, l) for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1) for l in (-1, 0, 1)
+                      if i != 0 or j != 0 or k != 0 or l != 0], dtype=np.int64)
+
+
+def initial_voxels(field, value, end_points):
+    """tetrahedral.py:396-441 find_initial_voxels on a 4D array of samples (hypervoxels whose 16 samples are not all
+    inside the array count as "not border").  Returns the set of start hypervoxel origins (tuples)."""
+    field = np.asarray(field)
+    value = float(value)
+    act = active_cells(field, value)
+    visited, new_voxels = set(), set()
+
+    def border(p):
+        return bool(all(0 <= int(p[a]) < act.shape[a] for a in range(4)) and act[tuple(int(x) for x in p)])
+
+    for low_point, high_point in np.asarray(end_points, dtype=np.int64).reshape(-1, 2, 4):
+        low_value, high_value = float(field[tuple(low_point)]), float(field[tuple(high_point)])
+        if low_value > value or high_value < value:
+            low_point, low_value, high_point, high_value = high_point, high_value, low_point, low_value
+        assert low_value <= value and high_value >= value
+        while np.any(np.abs(low_point - high_point) > 1):
+            mid_point = (low_point + high_point) // 2
+            if float(field[tuple(mid_point)]) < value:
+                low_point = mid_point
+            else:
+                high_point = mid_point
+        for point in (low_point, high_point):
+            tpoint = tuple(int(x) for x in point)
+            if tpoint in visited:
+                continue
+            visited.add(tpoint)
+            if border(point):
+                new_voxels.add(tpoint)
+                continue
+            for offset_point in OFFSETS4D + point.reshape(1, 4):
+                toffset = tuple(int(x) for x in offset_point)
+                if toffset in visited:
+                    continue
+                visited.add(toffset)
+                if border(offset_point):
+                    new_voxels.add(toffset)
+                    break
+    return new_voxels
+
+
+def flood_fill(field, value, start_voxels):
+    "tetrahedral.py:443-469 until nothing is new: border hypervoxels 80-connected, through border hypervoxels, to a start."
+    from scipy import ndimage
+    act = active_cells(np.asarray(field), float(value))
+    lab, _ = ndimage.label(act, structure=np.ones((3, 3, 3, 3), dtype=bool))
+    want = set(int(lab[tuple(v)]) for v in start_voxels if all(0 <= v[a] < act.shape[a] for a in range(4)) and act[tuple(v)])
+    return np.isin(lab, sorted(want)) & act if want else np.zeros_like(act)
+
+
+def extract_seeded(field, value, end_points, geom_dtype=np.float64):
+    "extract() restricted to the hypervoxels the tracker reaches from the seed segments; keys renumbered."
+    r = extract(field, value, geom_dtype)
+    mask = flood_fill(field, value, initial_voxels(field, value, end_points))
+    keep_t = mask.reshape(-1)[r["tet_cell"]] if len(r["tet_cell"]) else np.zeros(0, dtype=bool)
+    tets = r["tets"][keep_t]
+    used = np.unique(tets)
+    remap = -np.ones(len(r["keys"]), dtype=np.int64)
+    remap[used] = np.arange(len(used))
+    return dict(keys=r["keys"][used], lowmin=r["lowmin"][used], pos=r["pos"][used], tets=remap[tets].astype(np.int32),
+                tet_keys=r["tet_keys"][keep_t], voxels=mask)

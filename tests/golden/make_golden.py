@@ -496,3 +496,54 @@ if __name__ == "__main__" and "4d" in sys.argv[1:]:
     main4d()
 if __name__ == "__main__" and "json4d" in sys.argv[1:]:
     main_json4d()
+
+
+# ------------------------------------------------------------------ 4D seeded
+def fields_seeded4d():
+    """Two separate blobs in (x, y, z, t): explicit seeds reach one of them (SURVEY.md 8(f3) in 4D: pentatopes.py:92-106 with
+    the 80-neighbourhood OFFSETS4D, pentatopes.py:32-39)."""
+    n, nt = 9, 6
+    x, y, z, t = np.meshgrid(np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64),
+                             np.arange(nt, dtype=np.float64), indexing="ij")
+    a = np.exp(-((x - 2.2) ** 2 + (y - 2.4) ** 2 + (z - 2.1) ** 2 + 0.6 * (t - 1.3) ** 2) / 2.5)
+    b = np.exp(-((x - 6.1) ** 2 + (y - 5.8) ** 2 + (z - 6.3) ** 2 + 0.6 * (t - 3.6) ** 2) / 2.9)
+    f = a + b
+    return {"blobs_a": (f, 0.5, [[(2, 2, 2, 1), (2, 2, 7, 1)]]),
+            "blobs_b": (f, 0.5, [[(6, 6, 6, 4), (0, 6, 6, 4)], [(6, 6, 6, 3), (6, 6, 0, 3)]]),
+            "blobs_both": (f, 0.5, [[(2, 2, 2, 1), (2, 2, 7, 1)], [(6, 6, 6, 4), (0, 6, 6, 4)]])}
+
+
+def run_seeded4d(arr, value, seeds):
+    P = rh.load("pentatopes")
+    f = array_callable(arr)
+    corner = [s - 1 for s in arr.shape]
+    G = P.GridContour4D(corner, f, value, seeds)
+    G.find_initial_voxels()
+    initial = sorted(G.new_surface_voxels)
+    while G.new_surface_voxels:
+        G.expand_voxels()
+    for quad in G.surface_voxels:
+        G.enumerate_voxel_tetrahedra(quad)
+    inr = lambda v: all(0 <= v[a] < corner[a] for a in range(4))
+    vox = np.array(sorted(v for v in G.surface_voxels if inr(v)), dtype=np.int64).reshape(-1, 4)
+    corner_a = np.array(corner)
+    simplices = []
+    for s in G.simplex_sets:
+        pts = np.array([p for pair in s for p in pair])
+        owner = pts.min(axis=0)
+        if np.all(owner >= 0) and np.all(owner < corner_a) and len(s) == 4:
+            simplices.append(sorted(s))
+    used = sorted(set(pair for s in simplices for pair in s))
+    return dict(field=arr, value=np.float64(value), seeds=np.array(seeds, dtype=np.int64).reshape(-1, 2, 4),
+                initial=np.array(initial, dtype=np.int64).reshape(-1, 4), voxels=vox,
+                n_leak=np.int64(len(G.surface_voxels) - len(vox)), n_keys=np.int64(len(used)), n_tets=np.int64(len(simplices)),
+                key_low=np.array([p[0] for p in used], dtype=np.int16).reshape(-1, 4),
+                key_high=np.array([p[1] for p in used], dtype=np.int16).reshape(-1, 4))
+
+
+if __name__ == "__main__" and "seeded4d" in sys.argv[1:]:
+    for name, (arr, value, seeds) in fields_seeded4d().items():
+        g = run_seeded4d(arr, value, seeds)
+        np.savez_compressed(os.path.join(HERE, "seeded4d_%s.npz" % name), **g)
+        print(name, arr.shape, "initial", g["initial"].tolist(), "voxels", len(g["voxels"]), "leak", int(g["n_leak"]),
+              "keys", int(g["n_keys"]), "tets", int(g["n_tets"]))

@@ -123,3 +123,32 @@ def test_medium_size_properties(engine):
     assert on.all()
     del f
     torch.cuda.empty_cache()
+
+
+SEEDED4D = sorted(glob.glob(os.path.join(GOLDEN, "seeded4d_*.npz")))
+
+
+@pytest.mark.parametrize("path", SEEDED4D, ids=[os.path.basename(f) for f in SEEDED4D])
+def test_facade_4d_seeded_equals_reference_tracker(engine, path):
+    """GridContour4D with explicit seed segments returns what the reference's tracker reaches from them (pentatopes.py:92-106,
+    tetrahedral.py:396-469 with the 80 offsets): same start hypervoxels, same reached hypervoxels, same edge keys, same
+    number of tetrahedra as the run of the unmodified reference; tetrahedra and positions equal to the oracle's."""
+    from contourist_b200 import pentatopes
+    g = np.load(path)
+    field, value = g["field"], float(g["value"])
+    seeds = [[tuple(a), tuple(b)] for a, b in g["seeds"].tolist()]
+    G = pentatopes.GridContour4D([s - 1 for s in field.shape], field, value, seeds)
+    o = G.find_tetrahedra()
+    assert [tuple(v) for v in G.start_voxels] == [tuple(v) for v in g["initial"].tolist()]
+    assert np.array_equal(np.argwhere(G.selected_voxels), g["voxels"])
+    r = mp4d.extract_seeded(field, value, g["seeds"])
+    assert np.array_equal(o["keys"], r["keys"]) and len(o["tets"]) == int(g["n_tets"]) == len(r["tets"])
+    assert np.array_equal(np.sort(o["tets"], axis=1), np.sort(r["tets"], axis=1))
+    assert np.array_equal(o["verts"], r["pos"])
+    full = pentatopes.GridContour4D([s - 1 for s in field.shape], field, value, None).find_tetrahedra()
+    assert (len(o["tets"]) < len(full["tets"])) == ("both" not in path)
+    # the morph triangles of the selection are the full scan's restricted to it
+    mt = G.collect_morph_triangles()
+    assert len(mt.triangle_segment_indices) > 0 and mt.points4d.shape == (len(o["keys"]), 4)
+    if "both" in path:
+        assert len(o["morph_tris"]) == len(full["morph_tris"])
