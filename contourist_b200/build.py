@@ -28,26 +28,29 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    "defines / out: experiment builds (-DNAME=VALUE ...) into another file; the product build uses neither"
+    if not force and not stale() and not defines and out is None:
         return LIB
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build" if out is None else "build_" + os.path.basename(out))
+    os.makedirs(bdir, exist_ok=True)
     for src in sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(obj)
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if verbose or p.returncode:
-            sys.stderr.write(out.decode())
+            sys.stderr.write(log.decode())
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
-    cmd = [NVCC] + FLAGS + ["-shared", "-o", LIB] + objs
+    lib = LIB if out is None else out
+    cmd = [NVCC] + FLAGS + ["-shared", "-o", lib] + objs
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

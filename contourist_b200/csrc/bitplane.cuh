@@ -252,6 +252,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigne
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// The field is read exactly once: its lines enter L2 marked evict-first, so that they do not push out the bitplanes this
+// kernel writes (32 MiB that stage 2 reads right away) nor the dirty lines of the previous extraction's mesh.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void* dst, const void* src, unsigned bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
 
 constexpr int TMA_STAGES_DEFAULT = 3;              // x 16 KiB per CTA; 3 CTAs per SM (measured best of 1..6 x 2..6)
 constexpr int TMA_CHUNK = 16384;                 // bytes per stage
@@ -262,7 +275,7 @@ __global__ void __launch_bounds__((TMA_CONSUMER_WARPS + 1) * 32) k_bitplane_tma(
                                                                                   T thr, T near_lo, T near_hi,
                                                                                   uint32_t* __restrict__ bits,
                                                                                   uint32_t* __restrict__ nbits, RowGeom rg,
-                                                                                  MinMaxKeys* ctr, int TMA_STAGES) {
+                                                                                  MinMaxKeys* ctr, int TMA_STAGES, int l2_hint) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)TMA_STAGES * TMA_CHUNK);
   uint64_t* empty = full + TMA_STAGES;
@@ -280,6 +293,7 @@ __global__ void __launch_bounds__((TMA_CONSUMER_WARPS + 1) * 32) k_bitplane_tma(
   if (warp == TMA_CONSUMER_WARPS) {
     if (lane == 0) {
       unsigned it = 0;
+      const uint64_t pol = l2_evict_first_policy();
       for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
         const int s = it % TMA_STAGES;
         const unsigned ph = (it / TMA_STAGES) & 1u;
@@ -287,7 +301,8 @@ __global__ void __launch_bounds__((TMA_CONSUMER_WARPS + 1) * 32) k_bitplane_tma(
         size_t off = c * (size_t)TMA_CHUNK;
         unsigned bytes = (unsigned)((nbytes - off) < (size_t)TMA_CHUNK ? (nbytes - off) : (size_t)TMA_CHUNK);
         mbar_expect_tx(&full[s], bytes);
-        tma_bulk_g2s(smem + (size_t)s * TMA_CHUNK, src + off, bytes, &full[s]);
+        if (l2_hint) tma_bulk_g2s_hint(smem + (size_t)s * TMA_CHUNK, src + off, bytes, &full[s], pol);
+        else tma_bulk_g2s(smem + (size_t)s * TMA_CHUNK, src + off, bytes, &full[s]);
       }
     }
     return;
@@ -423,6 +438,7 @@ int launch_bitplane(ctr_ctx* ctx, const T* dfield, unsigned nrows, int n2, int W
   if (kind == BP_TMA) {
     static const int TMA_STAGES = getenv("CTR_BP_STAGES") ? atoi(getenv("CTR_BP_STAGES")) : TMA_STAGES_DEFAULT;
     static const int ctas_per_sm = getenv("CTR_BP_CTAS") ? atoi(getenv("CTR_BP_CTAS")) : 3;
+    static const int l2_hint = getenv("CTR_BP_L2HINT") ? atoi(getenv("CTR_BP_L2HINT")) : 1;   // 0.428 -> 0.418 ms per 512^3 step
     const int smem = TMA_STAGES * TMA_CHUNK + 2 * TMA_STAGES * 8 + TMA_CONSUMER_WARPS * 32 * 4 + 64;
     // this header is compiled into two translation units (anonymous namespaces): each has its own kernel instances
     const int ti = CTR_BP_ATTR_BASE + (sizeof(T) == 4 ? 0 : 1) + (MINMAX ? 2 : 0);
@@ -433,7 +449,7 @@ int launch_bitplane(ctr_ctx* ctx, const T* dfield, unsigned nrows, int n2, int W
     const size_t nbytes = nsamp * sizeof(T);
     const size_t nchunks = (nbytes + TMA_CHUNK - 1) / TMA_CHUNK;
     int blocks = (int)std::min<size_t>(nchunks, (size_t)ctx->sm_count * ctas_per_sm);
-    k_bitplane_tma<T, MINMAX><<<blocks, (TMA_CONSUMER_WARPS + 1) * 32, smem, st>>>(dfield, nbytes, thr, nlo, nhi, bits, nbits, rg, dctr, TMA_STAGES);
+    k_bitplane_tma<T, MINMAX><<<blocks, (TMA_CONSUMER_WARPS + 1) * 32, smem, st>>>(dfield, nbytes, thr, nlo, nhi, bits, nbits, rg, dctr, TMA_STAGES, l2_hint);
   } else if (kind == BP_VEC) {
     const size_t nchunks = (nsamp + 32 * Vec16<T>::VEC - 1) / (32 * Vec16<T>::VEC);
     size_t need = (nchunks + 8 * 4 - 1) / (8 * 4);

@@ -524,8 +524,11 @@ struct CountBShared {
   unsigned base_own, base_cell;
 };
 
+#ifndef CTR_CB_MINB
+#define CTR_CB_MINB 3          // 80 registers: stage 2 131 us (4 -> 64 registers with spills: 135; 5: 143; 6: 156)
+#endif
 template <typename T>
-__global__ void __launch_bounds__(CB_THREADS, 4) k_count_b(Grid<T> gin, unsigned word0, const uint32_t* __restrict__ wlist,
+__global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin, unsigned word0, const uint32_t* __restrict__ wlist,
                                                         unsigned cap_w, uint32_t* __restrict__ recc, uint4* __restrict__ wrec,
                                                         unsigned long long* __restrict__ own_id,
                                                         unsigned long long* __restrict__ own_rk,
@@ -822,8 +825,13 @@ __device__ __forceinline__ int nth_set_bit7(unsigned m, unsigned n) {
   return b;
 }
 
+#ifdef CTR_EV_MINB
+#define CTR_EV_BOUNDS __launch_bounds__(256, CTR_EV_MINB)
+#else
+#define CTR_EV_BOUNDS __launch_bounds__(256)
+#endif
 template <typename T, typename G>
-__global__ void __launch_bounds__(256) k_emit_verts(Grid<T> g, const unsigned long long* __restrict__ own_id,
+__global__ void CTR_EV_BOUNDS k_emit_verts(Grid<T> g, const unsigned long long* __restrict__ own_id,
                                                     const unsigned long long* __restrict__ own_rk,
                                                     const uint4* __restrict__ wrec,
                                                     const Counters* __restrict__ ctr, unsigned cap_own, unsigned cap_v, Xform xf,
@@ -957,8 +965,13 @@ __device__ __noinline__ void rows_used_exact(const Grid<T>& gin, int i, int j, i
 // One thread per emitting voxel.  The id of each of the voxel's 19 edges is vbase[owner word] + dirbase + rank of the
 // owner bit in that direction's used-edge word -- all from the 2x2 rows of bit words the voxel touches (8 loads) and
 // the (vbase, dirpack) records of those rows.
+#ifdef CTR_ET_MINB
+#define CTR_ET_BOUNDS __launch_bounds__(ET_THREADS, CTR_ET_MINB)
+#else
+#define CTR_ET_BOUNDS __launch_bounds__(ET_THREADS)
+#endif
 template <typename T>
-__global__ void __launch_bounds__(ET_THREADS) k_emit_tris(Grid<T> g, const unsigned long long* __restrict__ cell_id,
+__global__ void CTR_ET_BOUNDS k_emit_tris(Grid<T> g, const unsigned long long* __restrict__ cell_id,
                                                           const uint32_t* __restrict__ cell_toff, const Counters* __restrict__ ctr,
                                                           unsigned cap_cell, unsigned cap_t,
                                                           const uint4* __restrict__ wrec, const uint32_t* __restrict__ vox_tab,
