@@ -519,6 +519,7 @@ __device__ __noinline__ void flag_exact_words(const Grid<T>& g, const Planes& pl
 constexpr int CB_THREADS = 256;                     // (128: 160 us for stage 2 instead of 153)
 
 struct CountBShared {
+  unsigned long long spread[128];     // 7-bit direction mask -> 7 x 5-bit fields with a one where the mask has a bit
   unsigned short vox[256];
   unsigned warp_items[CB_THREADS / 32];
   unsigned base_own, base_cell;
@@ -539,6 +540,12 @@ __global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin
   Grid<T> g = gin;
   g.any_near = 0;
   for (unsigned q = threadIdx.x; q < 256u; q += CB_THREADS) sh.vox[q] = c_vox[q];
+  if (threadIdx.x < 128) {
+    unsigned long long sp = 0;
+#pragma unroll
+    for (int d = 0; d < 7; ++d) sp |= (unsigned long long)((threadIdx.x >> d) & 1u) << (5 * d);
+    sh.spread[threadIdx.x] = sp;
+  }
   __syncthreads();
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
@@ -616,17 +623,19 @@ __global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin
   unsigned orun = sh.base_own + (excl & 0xffffu), crun = sh.base_cell + (excl >> 16);
   if (any) {
     uint32_t mo = any;
+    // the ranks of an owner's edges within their directions = how many used edges of each direction came before it in
+    // the word: seven 5-bit running counts, bumped per owner through a 128-entry table (a count reaches 32 only behind
+    // the word's last owner)
+    unsigned long long run = 0;
     while (mo) {
       const int b = __ffs(mo) - 1;
       mo &= mo - 1;
+      const unsigned m7 = gather7(x, b);
       if (orun < cap_own) {
-        const uint32_t below = (1u << b) - 1u;
-        unsigned long long rk = 0;
-#pragma unroll
-        for (int d = 0; d < 7; ++d) rk |= (unsigned long long)__popc(x[d] & below) << (5 * d);
-        own_id[orun] = ((unsigned long long)gw << 13) | ((unsigned)b << 8) | (((pl.P[0] >> b) & 1u) << 7) | gather7(x, b);
-        own_rk[orun] = rk;
+        own_id[orun] = ((unsigned long long)gw << 13) | ((unsigned)b << 8) | (((pl.P[0] >> b) & 1u) << 7) | m7;
+        own_rk[orun] = run;
       }
+      run += sh.spread[m7];
       ++orun;
     }
   }
@@ -635,13 +644,14 @@ __global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin
     unsigned trun = 0;
     Planes npl;
     if (g.any_near) load_planes(g, g.nbits, i, j, w, npl);
+    // corner bits (k, k+1) of row ab = bits (b, b+1) of the row's 33-bit window: one funnel shift per row
+    const uint32_t hi[4] = {pl.S[0] >> 31, pl.S[1] >> 31, pl.S[2] >> 31, pl.S[3] >> 31};
     while (me) {
       const int b = __ffs(me) - 1;
       me &= me - 1;
       unsigned c8 = 0;
 #pragma unroll
-      for (int ab = 0; ab < 4; ++ab)
-        c8 |= (((pl.P[ab] >> b) & 1u) | (((pl.S[ab] >> b) & 1u) << 1)) << (2 * ab);
+      for (int ab = 0; ab < 4; ++ab) c8 |= (__funnelshift_r(pl.P[ab], hi[ab], b) & 3u) << (2 * ab);
       const unsigned en = sh.vox[c8];
       unsigned emit = en & 63u, nt = en >> 8;
       if (g.any_near) {
