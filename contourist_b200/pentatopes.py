@@ -185,6 +185,32 @@ class GridContour4D(object):
         return result
 
 
+    # ---- the legacy wire format (pentatopes.py:370-444; misc/morph_sequence.js)
+    def iterate_morph_geometry(self):
+        "One MorphGeometry per interval between consecutive distinct vertex times (pentatopes.py:370-413)."
+        if self._out is None:
+            self.find_tetrahedra()
+        tets = self._out["tets"][self._out["keep"].astype(bool)]
+        return morph_geometry.morph_sequence(self._out["morph_verts"], tets)
+
+    def json_stats(self, morphs=None):
+        morphs = list(self.iterate_morph_geometry()) if morphs is None else morphs
+        return (morphs, morphs[0].min_value, morphs[-1].max_value)
+
+    def json_data(self, morphs=None):
+        (morphs, min_value, max_value) = self.json_stats(morphs)
+        return {"min_value": min_value, "max_value": max_value, "morph_descriptions": [m.json_data() for m in morphs]}
+
+    def to_json0(self, morphs=None):
+        import json
+        return json.dumps(self.json_data(morphs), indent=4, default=lambda x: x.item() if hasattr(x, "item") else list(x))
+
+    def to_json(self, morphs=None):
+        '"Sequence of morphing triangularizations." (pentatopes.py:430-444)'
+        (morphs, _, _) = self.json_stats(morphs)
+        return morph_geometry.morph_sequence_json(morphs)
+
+
 class Delta4DContour(object):
 
     flatten = False

@@ -547,3 +547,56 @@ if __name__ == "__main__" and "seeded4d" in sys.argv[1:]:
         np.savez_compressed(os.path.join(HERE, "seeded4d_%s.npz" % name), **g)
         print(name, arr.shape, "initial", g["initial"].tolist(), "voxels", len(g["voxels"]), "leak", int(g["n_leak"]),
               "keys", int(g["n_keys"]), "tets", int(g["n_tets"]))
+
+
+# ------------------------------------------------------------------ 4D legacy "sequence of morphing triangularizations"
+def run_seq4d(arr, value):
+    """pentatopes.py:370-444 iterate_morph_geometry / json_data of the unmodified reference (the format misc/morph_sequence.js
+    loads) on the in-range state of a 4D golden, after the reference's own find_tetrahedra post-processing."""
+    import contextlib
+    import io
+    P = rh.load("pentatopes")
+    f = array_callable(arr)
+    corner = [s - 1 for s in arr.shape]
+    G = P.GridContour4D(corner, f, value, strict_seeds(arr, value))
+    G.find_initial_voxels()
+    while G.new_surface_voxels:
+        G.expand_voxels()
+    for quad in G.surface_voxels:
+        G.enumerate_voxel_tetrahedra(quad)
+    corner_a = np.array(corner)
+    simplices = []
+    for s in G.simplex_sets:
+        owner = np.array([p for pair in s for p in pair]).min(axis=0)
+        if np.all(owner >= 0) and np.all(owner < corner_a):
+            simplices.append(sorted(s))
+    used = sorted(set(pair for s in simplices for pair in s))
+    G.simplex_sets = set(frozenset(s) for s in simplices)
+    G.interpolated_contour_pairs = {p: G.interpolated_contour_pairs[p] for p in used}
+    with contextlib.redirect_stdout(io.StringIO()):
+        G.bin_times()
+        G.drop_instant_tetrahedra()
+        G.remove_tiny_simplices(epsilon=1e-3)
+        kidx = {p: i for i, p in enumerate(used)}
+        pos = np.array([np.array(G.interpolated_contour_pairs[p]) for p in used], dtype=np.float64).reshape(-1, 4)
+        tets = np.array(sorted(sorted(kidx[p] for p in s) for s in G.simplex_sets if len(s) == 4), dtype=np.int64).reshape(-1, 4)
+        morphs = list(G.iterate_morph_geometry())
+        data = [m.json_data(integral=True, lists_only=True) for m in morphs]
+    out = dict(field=arr, value=np.float64(value), pos=pos, tets=tets,
+               minmax=np.array([[d["min_value"], d["max_value"]] for d in data], dtype=np.float64).reshape(-1, 2),
+               scale=np.array([d["scale"] for d in data], dtype=np.float64).reshape(-1, 3),
+               shift=np.array([d["shift"] for d in data], dtype=np.float64).reshape(-1, 3),
+               vert_off=np.cumsum([0] + [len(d["start_positions"]) for d in data]).astype(np.int64),
+               tri_off=np.cumsum([0] + [len(d["triangles"]) for d in data]).astype(np.int64),
+               start=np.concatenate([np.array(d["start_positions"], dtype=np.int32).reshape(-1, 3) for d in data]),
+               end=np.concatenate([np.array(d["end_positions"], dtype=np.int32).reshape(-1, 3) for d in data]),
+               tris=np.concatenate([np.array([list(t) for t in d["triangles"]], dtype=np.int32).reshape(-1, 3) for d in data]))
+    return out
+
+
+if __name__ == "__main__" and "seq4d" in sys.argv[1:]:
+    for name in ("morph7",):
+        arr, value = fields4d()[name]
+        g = run_seq4d(arr, value)
+        np.savez_compressed(os.path.join(HERE, "seq4d_%s.npz" % name), **g)
+        print(name, "morphs", len(g["minmax"]), "vertices", int(g["vert_off"][-1]), "triangles", int(g["tri_off"][-1]))

@@ -7,7 +7,8 @@ at run time (the GPU box has no /root/reference).
 The shim does no algorithmic edits:
   * numpy aliases removed in numpy>=1.24: np.int, np.float, np.sometrue
   * Python-2 syntax in pentatopes.py / morph_geometry.py: print statements and one
-    bare-tuple comprehension are rewritten textually at import time
+    bare-tuple comprehension are rewritten textually at import time; one dict.keys() that Python 2
+    returns as a list (and the code indexes) is wrapped in list()
   * the reference's implicit-relative imports are satisfied by putting the package
     directory itself on sys.path under a private module namespace.
 """
@@ -44,6 +45,8 @@ def _py3_source(src):
         if m:
             line = "%sprint(%s)" % (m.group(1), m.group(2))
         line = line.replace("for l in 0,1]", "for l in (0,1)]")
+        # Python 2's dict.keys() is a list (morph_geometry.py:245 indexes it)
+        line = line.replace("pair_order = active_pairs.keys()", "pair_order = list(active_pairs.keys())")
         out.append(line)
     return "\n".join(out)
 
