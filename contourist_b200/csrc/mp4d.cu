@@ -847,6 +847,34 @@ __device__ __forceinline__ int slice_code(const TT tv[4], const MorphParams& mp,
   return n;
 }
 
+// On integer time bins the whole slicing of a tetrahedron depends only on how its four bins compare pairwise: a weak
+// ordering of four elements (75 of them).  The pattern -- 2 bits (less, equal) per pair (0,1),(0,2),(0,3),(1,2),(1,3),(2,3)
+// -- indexes a table built once by running slice_code on one representative per pattern:
+//   entry = triangle code (54 bits) | triangle count << 54 | low-t-first flags of the six edges << 57.
+__device__ __forceinline__ unsigned order_pattern(const int tv[4]) {
+  unsigned p = 0;
+#pragma unroll
+  for (int e = 0; e < 6; ++e) {
+    const int a = tv[EA(e)], b = tv[EB(e)];
+    p |= ((a < b ? 1u : 0u) | (a == b ? 2u : 0u)) << (2 * e);
+  }
+  return p;
+}
+
+__global__ void k4_slice_table(unsigned long long* __restrict__ tab, MorphParams mp) {
+  __shared__ unsigned s_tab[64];
+  if (threadIdx.x < 64) s_tab[threadIdx.x] = slice_entry(threadIdx.x);
+  __syncthreads();
+  const int tv[4] = {(int)(threadIdx.x & 3u), (int)((threadIdx.x >> 2) & 3u), (int)((threadIdx.x >> 4) & 3u), (int)(threadIdx.x >> 6)};
+  unsigned long long code;
+  const int n = slice_code<int>(tv, mp, s_tab, code);
+  unsigned swapm = 0;
+#pragma unroll
+  for (int e = 0; e < 6; ++e)
+    if (tv[EA(e)] > tv[EB(e)]) swapm |= 1u << e;
+  tab[order_pattern(tv)] = code | ((unsigned long long)n << 54) | ((unsigned long long)swapm << 57);   // equal patterns, equal entries
+}
+
 struct SlCounters {
   unsigned long long total;
   unsigned int ticket, pad;
@@ -854,7 +882,16 @@ struct SlCounters {
 
 constexpr int SL_PER = 4;                            // consecutive tetrahedra per thread (10^5 tiles of 256 would
 constexpr int SL_TILE = SL_THREADS * SL_PER;         // serialise on the ticket atomic and on the look-back)
-constexpr int SL_STAGE = 2048;                       // triangles staged in shared memory per tile (48 KB)
+constexpr int SL_MAXTRI = SL_TILE * 6;               // a tetrahedron gives at most 3 slices x 2 triangles
+
+// what the write-out needs of one tetrahedron: id-sorted corners, triangle code, low-t-first flags | first triangle << 8
+struct __align__(16) SlRec {
+  int v[4];
+  unsigned long long code;
+  unsigned swap_first;
+  unsigned pad;
+};
+constexpr int SL_SMEM = SL_TILE * (int)sizeof(SlRec) + SL_MAXTRI * 2;     // records + the tetrahedron of every triangle
 
 template <typename TT>
 __device__ __forceinline__ bool slice_load(const double* __restrict__ verts, const int* __restrict__ tbin,
@@ -874,14 +911,36 @@ __device__ __forceinline__ bool slice_load(const double* __restrict__ verts, con
   return !(v[0] == v[1] || v[1] == v[2] || v[2] == v[3]);
 }
 
+// fp64 times: the reference's tolerances, evaluated; integer bins: the pattern table
+template <typename TT>
+__device__ __forceinline__ void slice_lookup(const TT tv[4], const MorphParams& mp, const unsigned* __restrict__ s_tab,
+                                             const unsigned long long* __restrict__, unsigned long long& code, int& cnt, unsigned& swapm) {
+  cnt = slice_code<TT>(tv, mp, s_tab, code);
+#pragma unroll
+  for (int e = 0; e < 6; ++e)
+    if (tv[EA(e)] > tv[EB(e)]) swapm |= 1u << e;                  // morph_geometry.py:13-17: low t first
+}
+template <>
+__device__ __forceinline__ void slice_lookup<int>(const int tv[4], const MorphParams&, const unsigned* __restrict__,
+                                                  const unsigned long long* __restrict__ pattern_tab, unsigned long long& code,
+                                                  int& cnt, unsigned& swapm) {
+  const unsigned long long ent = __ldg(pattern_tab + order_pattern(tv));
+  code = ent & ((1ull << 54) - 1ull);
+  cnt = (int)((ent >> 54) & 7ull);
+  swapm = (unsigned)(ent >> 57) & 63u;
+}
+
 template <typename TT>
 __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict__ verts, const int* __restrict__ tbin,
                                                        const int* __restrict__ tets,
                                                        const uint8_t* __restrict__ keep, uint8_t* __restrict__ keep_out,
                                                        unsigned nt, MorphParams mp,
                                                        unsigned long long* status, SlCounters* ctr, int ntiles,
-                                                       int* __restrict__ out, unsigned cap) {
-  extern __shared__ int s_out[];                     // SL_STAGE * 6 ints
+                                                       int* __restrict__ out, unsigned cap,
+                                                       const unsigned long long* __restrict__ pattern_tab) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  SlRec* s_rec = reinterpret_cast<SlRec*>(s_dyn);                            // [SL_TILE]
+  unsigned short* s_own = reinterpret_cast<unsigned short*>(s_dyn + SL_TILE * sizeof(SlRec));   // [SL_MAXTRI]
   __shared__ unsigned s_tile;
   __shared__ unsigned s_tab[64];
   __shared__ unsigned long long s_warp[SL_THREADS / 32], s_excl;
@@ -913,12 +972,7 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
         kept = Op::gap(Op::mn(Op::mn(tv[0], tv[1]), Op::mn(tv[2], tv[3])), Op::mx(Op::mx(tv[0], tv[1]), Op::mx(tv[2], tv[3])), mp);
         keep_out[a] = kept ? 1 : 0;
       }
-      if (distinct && kept) {
-        cnt[u] = slice_code<TT>(tv, mp, s_tab, code[u]);
-#pragma unroll
-        for (int e = 0; e < 6; ++e)
-          if (tv[EA(e)] > tv[EB(e)]) swapm[u] |= 1u << e;           // morph_geometry.py:13-17: low t first
-      }
+      if (distinct && kept) slice_lookup<TT>(tv, mp, s_tab, pattern_tab, code[u], cnt[u], swapm[u]);
     }
     n += cnt[u];
   }
@@ -931,54 +985,46 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
     if (q < (int)warp) woff += s_warp[q];
     blk += s_warp[q];
   }
-  // the tile's triangles are contiguous in the output (tetrahedron order): staged in shared memory and written out
-  // coalesced when they fit, else written directly.  The staging does not need the tile's global offset, so the
-  // aggregate is published first and the look-back is resolved after the staging: by then the predecessors have
-  // published theirs and the warp does not sit polling.
-  const bool staged = blk <= (unsigned long long)SL_STAGE;
-  if (warp == 0) {
-    lb_publish(status, tile, blk);
-    if (!staged) {
-      unsigned long long e = lb_resolve(status, tile, blk);
-      if (lane == 0) s_excl = e;
-    }
-  }
-  if (!staged) __syncthreads();
-  const unsigned long long base_direct = staged ? 0ull : s_excl;
+  // The tile's aggregate is published at once; the look-back is resolved after the records below have been staged: by
+  // then the predecessors have published theirs and the warp does not sit polling.
+  if (warp == 0) lb_publish(status, tile, blk);
+  // A thread that wrote its own triangles would run as long as the warp's busiest lane (0..24 triangles) with most
+  // lanes idle; instead every tetrahedron leaves a record in shared memory and marks its triangles with its number,
+  // and the tile's triangles are then dealt out one per thread per round.
   unsigned loc = (unsigned)(woff + inc - (unsigned long long)n);           // first triangle of this thread in the tile
 #pragma unroll
   for (int u = 0; u < SL_PER; ++u) {
-    if (!cnt[u]) continue;
-    const int* v = vv[u];
-    const unsigned swapmask = swapm[u];
-    unsigned long long c = code[u];
-    for (int q = 0; q < cnt[u]; ++q, c >>= 9, ++loc) {
-      if (!staged && base_direct + loc >= cap) continue;
-      int* o = staged ? s_out + loc * 6 : out + (base_direct + loc) * 6;
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int e = (int)((c >> (3 * r)) & 7ull);
-        // corners of edge e: EA = {0,0,0,1,1,2}, EB = {1,2,3,2,3,3} as 2-bit fields
-        const int ca = (0x940 >> (2 * e)) & 3, cb = (0xfb9 >> (2 * e)) & 3;
-        const int i0 = pick4(v, ca), i1 = pick4(v, cb);
-        const bool swap = (swapmask >> e) & 1u;
-        o[r * 2 + 0] = swap ? i1 : i0;
-        o[r * 2 + 1] = swap ? i0 : i1;
-      }
-    }
+    const unsigned tl = (unsigned)u * SL_THREADS + threadIdx.x;        // lane stride = one record: no 32-way bank conflict
+    SlRec r;
+    r.v[0] = vv[u][0]; r.v[1] = vv[u][1]; r.v[2] = vv[u][2]; r.v[3] = vv[u][3];
+    r.code = code[u];
+    r.swap_first = swapm[u] | (loc << 8);
+    r.pad = 0;
+    s_rec[tl] = r;
+    for (int q = 0; q < cnt[u]; ++q) s_own[loc + q] = (unsigned short)tl;
+    loc += (unsigned)cnt[u];
   }
-  if (staged) {
-    if (warp == 0) {
-      unsigned long long e = lb_resolve(status, tile, blk);
-      if (lane == 0) s_excl = e;
+  if (warp == 0) {
+    unsigned long long e = lb_resolve(status, tile, blk);
+    if (lane == 0) s_excl = e;
+  }
+  __syncthreads();
+  const unsigned long long base = s_excl;
+  const unsigned nb = (unsigned)blk;
+  for (unsigned q = threadIdx.x; q < nb; q += SL_THREADS) {
+    if (base + q >= cap) break;
+    const SlRec& r = s_rec[s_own[q]];
+    const unsigned idx = q - (r.swap_first >> 8);
+    const unsigned t9 = (unsigned)(r.code >> (9 * idx)) & 511u;
+    int2* o = reinterpret_cast<int2*>(out + (base + q) * 6);
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) {
+      const unsigned e = (t9 >> (3 * rr)) & 7u;
+      // corners of edge e: EA = {0,0,0,1,1,2}, EB = {1,2,3,2,3,3} as 2-bit fields
+      const int i0 = r.v[(0x940u >> (2 * e)) & 3u], i1 = r.v[(0xfb9u >> (2 * e)) & 3u];
+      const bool swap = (r.swap_first >> e) & 1u;
+      o[rr] = swap ? make_int2(i1, i0) : make_int2(i0, i1);
     }
-    __syncthreads();
-    const unsigned long long base = s_excl;
-    unsigned long long nb = blk;
-    if (base + nb > cap) nb = base < cap ? cap - base : 0ull;
-    const unsigned nint = (unsigned)nb * 6u;
-    int* dst = out + base * 6;
-    for (unsigned q = threadIdx.x; q < nint; q += SL_THREADS) dst[q] = s_out[q];
   }
   if (tile == ntiles - 1 && threadIdx.x == 0) ctr->total = s_excl + blk;
 }
@@ -1194,28 +1240,33 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
         ctx->launches++;
       }
       const int sl_tiles = (int)((totT + SL_TILE - 1) / SL_TILE);
-      if ((rc = ctr_ensure(ctx, B.slstate, (size_t)sl_tiles * 8 + 64))) return rc;
+      if ((rc = ctr_ensure(ctx, B.slstate, (size_t)sl_tiles * 8 + 64 + 256 + 4096 * 8))) return rc;      // + the pattern table
       size_t want = std::max<size_t>((size_t)totT * 2, 1 << 14);
       unsigned long long nmt = 0;
       for (int attempt = 0; attempt < 3; ++attempt) {
         if ((rc = ctr_ensure(ctx, B.mtris, want * 24))) return rc;
         const unsigned cap = (unsigned)std::min<size_t>(B.mtris.cap / 24, 0x7fffffffu);
         if (!(ctx->attr_mask & (1u << 8))) {
-          CTR_CUDA(ctx, cudaFuncSetAttribute(k4_slice<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_STAGE * 6 * sizeof(int))));
-          CTR_CUDA(ctx, cudaFuncSetAttribute(k4_slice<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_STAGE * 6 * sizeof(int))));
+          CTR_CUDA(ctx, cudaFuncSetAttribute(k4_slice<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM));
+          CTR_CUDA(ctx, cudaFuncSetAttribute(k4_slice<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM));
           ctx->attr_mask |= 1u << 8;
         }
         SlCounters* slc = (SlCounters*)((char*)B.slstate.p + (size_t)sl_tiles * 8);
+        unsigned long long* ptab = (unsigned long long*)((char*)B.slstate.p + (((size_t)sl_tiles * 8 + 64 + 255) & ~(size_t)255));
         CTR_CUDA(ctx, cudaMemsetAsync(B.slstate.p, 0, (size_t)sl_tiles * 8 + 32, st));
+        if (int_times) {
+          k4_slice_table<<<1, 256, 0, st>>>(ptab, mp);
+          ctx->launches++;
+        }
         if (int_times)
-          k4_slice<int><<<sl_tiles, SL_THREADS, SL_STAGE * 6 * sizeof(int), st>>>(
+          k4_slice<int><<<sl_tiles, SL_THREADS, SL_SMEM, st>>>(
               (const double*)B.mverts.p, (const int*)B.tbin.p, (const int*)B.tets.p,
               fused_filter ? nullptr : (const uint8_t*)B.keep.p, fused_filter ? (uint8_t*)B.keep.p : nullptr, (unsigned)totT, mp,
-              (unsigned long long*)B.slstate.p, slc, sl_tiles, (int*)B.mtris.p, cap);
+              (unsigned long long*)B.slstate.p, slc, sl_tiles, (int*)B.mtris.p, cap, ptab);
         else
-          k4_slice<double><<<sl_tiles, SL_THREADS, SL_STAGE * 6 * sizeof(int), st>>>(
+          k4_slice<double><<<sl_tiles, SL_THREADS, SL_SMEM, st>>>(
               (const double*)B.mverts.p, (const int*)B.tbin.p, (const int*)B.tets.p, (const uint8_t*)B.keep.p, nullptr,
-              (unsigned)totT, mp, (unsigned long long*)B.slstate.p, slc, sl_tiles, (int*)B.mtris.p, cap);
+              (unsigned)totT, mp, (unsigned long long*)B.slstate.p, slc, sl_tiles, (int*)B.mtris.p, cap, ptab);
         ctx->launches++;
         CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, slc, sizeof(SlCounters), cudaMemcpyDeviceToHost, st));
         CTR_CUDA(ctx, cudaStreamSynchronize(st));
