@@ -765,7 +765,6 @@ __device__ __forceinline__ unsigned slice_entry(unsigned mask) {
 
 constexpr int SL_THREADS = 256;
 
-__device__ __forceinline__ int pick4(const int v[4], int i) { return i == 0 ? v[0] : i == 1 ? v[1] : i == 2 ? v[2] : v[3]; }
 
 // The time comparisons of the slicing, on the binned times themselves (fp64, the reference's tolerances) or -- when
 // the bin width dwarfs every tolerance, i.e. always in practice -- on the integer bins: binned times are bin * width, so
@@ -1083,7 +1082,7 @@ int run4d(ctr_ctx* ctx, const ctr_mp4d_params* p, ctr_mp4d_counts* out) {
   if ((rc = ctr_ensure(ctx, ctx->vbase, (size_t)(nwords + 4) * 4))) return rc;
   if ((rc = ctr_ensure(ctx, ctx->counters, 256))) return rc;
   if ((rc = ctr_ensure(ctx, B.rowflag, (size_t)nrows + 16))) return rc;
-  if (!ctx->counters_host) CTR_CUDA(ctx, cudaMallocHost(&ctx->counters_host, 256));
+  if (!ctx->counters_host) CTR_CUDA(ctx, cudaMallocHost(&ctx->counters_host, 1024));
   Counters4 init;
   memset(&init, 0, sizeof init);
   init.min_key = ~0ull;

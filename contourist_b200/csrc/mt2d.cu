@@ -471,7 +471,7 @@ int run2d(ctr_ctx* ctx, const ctr_mt2d_params* p, ctr_mt2d_counts* out) {
   const int ntiles = tiles_i * tiles_j;
   const int vec_ok = ((n1 & 3) == 0 && (((uintptr_t)df) & 15) == 0) ? 1 : 0;      // rows start 16-byte aligned
   if ((rc = ctr_ensure(ctx, ctx->counters, 256))) return rc;
-  if (!ctx->counters_host) CTR_CUDA(ctx, cudaMallocHost(&ctx->counters_host, 256));
+  if (!ctx->counters_host) CTR_CUDA(ctx, cudaMallocHost(&ctx->counters_host, 1024));
   if ((rc = ctr_ensure(ctx, ctx->tile_state, (size_t)ntiles * 12 + 32))) return rc;      // per-tile counts (u64), then offsets (u32)
   Counters2D* dctr = (Counters2D*)ctx->counters.p;
   unsigned long long* tile_cnt = (unsigned long long*)ctx->tile_state.p;
