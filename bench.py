@@ -521,8 +521,9 @@ def run_ours(args):
                          "sample": "33x160x160 block from the middle of the same field, numpy oracle port (extract + normals)"},
         "e2e": {"value": e2e_val, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "h2d_copy_gbs_rank0_all_ranks_copying": h2d_gbs,
-                "note": "Engine.mt3d_extract_host (ctr_mt3d_run + ctr_mt3d_fetch per z-slab on two contexts, page-locked host "
-                        "buffers): H2D of the field and D2H of vertices, normals and triangles inside the timed region"},
+                "note": "Engine.mt3d_extract_host (ctr_mt3d_enqueue / _finish / _fetch per z-slab on two contexts, slab s+1 queued "
+                        "while slab s runs, page-locked host buffers): H2D of the field and D2H of vertices, normals and "
+                        "triangles inside the timed region"},
         "gpu_launches": int(launches), "clocks": clocks,
         "f64_geom": f64, "c5_strong": c5,
         "post_passes": post,
@@ -539,7 +540,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=512)
-    ap.add_argument("--e2e-slabs", type=int, default=4, help="slabs of the pipelined host-array call (1 = run + fetch)")
+    ap.add_argument("--e2e-slabs", type=int, default=8, help="slabs of the pipelined host-array call (1 = run + fetch)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg and the CPU baseline (profiling runs)")
     ap.add_argument("--no-c5", action="store_true", help="skip the 2048^3 strong-scaling leg (c5_strong)")
     args = ap.parse_args()

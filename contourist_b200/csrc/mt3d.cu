@@ -1134,6 +1134,12 @@ __global__ void __launch_bounds__(256) k_codes(Grid<T> g, const unsigned long lo
   codes[a] = code;
 }
 
+// ctr_mt3d_offset_ids: vertex ids of the run's triangles shifted by a base that became known after the run was queued
+__global__ void k_offset_ids(int* __restrict__ tris, size_t n, int base) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) tris[q] += base;
+}
+
 // ctr_mt3d_publish_counts: {n_verts, n_tris} of the run for a collective that reads them on the device
 __global__ void k_publish3(const Counters* __restrict__ ctr, int sharded, long long* __restrict__ out) {
   out[0] = (long long)(sharded ? ctr->v_emit : ctr->tot_v);
@@ -1532,6 +1538,19 @@ extern "C" int ctr_mt3d_finish(ctr_ctx* ctx, ctr_mt3d_counts* out) {
   if (!ctx->pending3) return ctr_fail(ctx, CTR_ERR_STATE, "no ctr_mt3d_enqueue to finish");
   ctx->pending3 = false;
   return mt3d_dispatch(ctx, (const ctr_mt3d_params*)ctx->pending3_params, out, 2);
+}
+
+extern "C" int ctr_mt3d_offset_ids(ctr_ctx* ctx, int64_t base) {
+  if (!ctx) return CTR_ERR_BAD_ARG;
+  if (ctx->last_kind != 3 || (ctx->last_flags & CTR_NO_GEOMETRY)) return ctr_fail(ctx, CTR_ERR_STATE, "no completed ctr_mt3d_run with geometry");
+  if (base < 0 || base > 0x7fffffffll) return ctr_fail(ctx, CTR_ERR_BAD_ARG, "id base out of range");
+  const size_t n = (size_t)ctx->last_counts[1] * 3;
+  if (!n || !base) return 0;
+  CTR_CUDA(ctx, cudaSetDevice(ctx->device));
+  k_offset_ids<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((int*)ctx->tris.p, n, (int)base);
+  ctx->launches++;
+  CTR_CUDA(ctx, cudaGetLastError());
+  return 0;                                            // stream-ordered: the fetch that follows sees the shifted ids
 }
 
 extern "C" int ctr_mt3d_publish_counts(ctr_ctx* ctx, void* device_counts) {

@@ -89,6 +89,8 @@ def load_library():
     lib.ctr_mt3d_enqueue.restype = i32
     lib.ctr_mt3d_finish.argtypes = [vp, ctypes.POINTER(Mt3dCounts)]
     lib.ctr_mt3d_finish.restype = i32
+    lib.ctr_mt3d_offset_ids.argtypes = [vp, i64]
+    lib.ctr_mt3d_offset_ids.restype = i32
     lib.ctr_mt3d_publish_counts.argtypes = [vp, vp]
     lib.ctr_mt3d_publish_counts.restype = i32
     lib.ctr_mt3d_fetch.argtypes = [vp] + [vp] * 7
@@ -388,14 +390,15 @@ class Engine(object):
         out.update(verts=a_v, normals=a_n, tris=a_t, keys=a_k, lowmin=a_l, cells=a_c, codes=a_d)
         return out
 
-    def mt3d_extract_host(self, field, value, origin=(0.0, 0.0, 0.0), delta=(1.0, 1.0, 1.0), flags=0, nslabs=4, own=None,
+    def mt3d_extract_host(self, field, value, origin=(0.0, 0.0, 0.0), delta=(1.0, 1.0, 1.0), flags=0, nslabs=8, own=None,
                           plane_offset=0):
         """Host array in, host mesh out, with the PCIe traffic of the two directions overlapped.
 
         The volume is cut into `nslabs` z-slabs (sharding.slab_with_halo, the multi-GPU decomposition); slab s is
         uploaded and extracted on one of two alternating contexts while a worker thread downloads the mesh of slab
-        s-1 from the other (PCIe is full duplex; ctypes releases the GIL).  Triangle ids are global: each slab's run
-        gets the vertex count of the slabs before it as `vert_id_base`.  own=(A, B) restricts the call to owner planes
+        s-1 from the other (PCIe is full duplex; ctypes releases the GIL), and slab s+1 is already queued
+        (`ctr_mt3d_enqueue`) when the host waits for slab s, so the upload engine never idles.  Triangle ids are global:
+        the vertex count of the slabs before a slab is added on the device (`ctr_mt3d_offset_ids`) before its download.  own=(A, B) restricts the call to owner planes
         [A, B) of the array (a rank's slab with its halo planes around it) and plane_offset is the global index of
         the array's first plane, as in ctr_mt3d_params.  `field` should be page-locked
         (Engine.pinned_empty) for full transfer rate.  Returns (totals dict, arrays dict); the arrays live in the
@@ -443,22 +446,36 @@ class Engine(object):
             totals = dict(n_active_cells=0, n_crossings=0)
             sizes = []
             overflow = False
-            for s_i, (a, b) in enumerate(sharding.slab_bounds(own_b - own_a, nslabs)):
-                if b <= a:
-                    continue
-                lo, hi, kw = sharding.slab_with_halo(a + own_a, b + own_a, n0)
-                kw["plane_offset"] += int(plane_offset)
-                eng = engines[s_i & 1]
-                if pending[s_i & 1] is not None:
-                    pending[s_i & 1].result()                 # its previous slab has been downloaded
-                    pending[s_i & 1] = None
-                c = eng.mt3d_run(field[lo:hi], value, origin=origin, delta=delta, flags=flags, vert_id_base=vsum, **kw)
+            slabs = []
+            for (a, b) in sharding.slab_bounds(own_b - own_a, nslabs):
+                if b > a:
+                    lo, hi, kw = sharding.slab_with_halo(a + own_a, b + own_a, n0)
+                    kw["plane_offset"] += int(plane_offset)
+                    slabs.append((lo, hi, kw))
+
+            def enqueue(k):
+                # queued, not waited for: the upload of slab k runs while the kernels of slab k-1 do.  Its vertex ids
+                # start at 0; the base (vertices of the slabs before it) is added on the device once it is known.
+                lo, hi, kw = slabs[k]
+                if pending[k & 1] is not None:
+                    pending[k & 1].result()                   # the context's previous slab has been downloaded
+                    pending[k & 1] = None
+                engines[k & 1].mt3d_enqueue(field[lo:hi], value, origin=origin, delta=delta, flags=flags, **kw)
+
+            enqueue(0)
+            for k in range(len(slabs)):
+                if k + 1 < len(slabs):
+                    enqueue(k + 1)
+                eng = engines[k & 1]
+                c = eng.mt3d_finish()
                 nv, nt = int(c.n_verts), int(c.n_tris)
                 sizes.append((nv, nt))
                 totals["n_active_cells"] += int(c.n_active_cells)
                 totals["n_crossings"] += int(c.n_crossings)
+                if vsum:
+                    eng._check(eng.lib.ctr_mt3d_offset_ids(eng.h, vsum), "ctr_mt3d_offset_ids")
                 if not overflow and vsum + nv <= cap_v and tsum + nt <= cap_t:
-                    pending[s_i & 1] = pool.submit(fetch, eng, vsum, tsum, nv, nt)
+                    pending[k & 1] = pool.submit(fetch, eng, vsum, tsum, nv, nt)
                 else:
                     overflow = True                           # first call (sizes unknown) or a larger mesh than before
                 vsum += nv

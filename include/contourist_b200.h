@@ -127,6 +127,10 @@ CTR_API int ctr_mt3d_finish(ctr_ctx* ctx, ctr_mt3d_counts* out);
  * `device_counts` (caller-owned device memory, 16 bytes, valid until replaced) behind its last kernel, on the context's
  * stream -- a collective queued after an event on that stream can send them straight from there.  NULL turns it off. */
 CTR_API int ctr_mt3d_publish_counts(ctr_ctx* ctx, void* device_counts);
+/* Adds `base` to every vertex id of the last run's device triangles (stream-ordered, no wait): what vert_id_base does,
+ * for a base that was not known yet when the run was queued -- slab k+1 of a pipelined host-array extraction is queued
+ * (its upload overlapping the kernels of slab k) before slab k's vertex count exists.  Not part of the reference.  */
+CTR_API int ctr_mt3d_offset_ids(ctr_ctx* ctx, int64_t base);
 /* verts/normals: [n_verts][3] float or double (CTR_GEOM_F64); tris: [n_tris][3] vertex ids, local to
  * this call (0 = first emitted vertex; ids >= n_verts refer to the next shard's vertices; vertices are numbered
  * by owner word (plane-major), then edge direction, then k -- not by key);
