@@ -452,14 +452,21 @@ def run_ours(args):
         row = field[pi, pj].cpu().numpy()
         while pk + 1 < shape[2] and row[pk + 1] >= ISOVALUE:
             pk += 1                                   # last sample of the row still above the isovalue: a border voxel
-        for name in ("orient_reference", "select_seeded"):
+        for name in ("orient_reference", "select_seeded", "clean_reference"):
             ts = []
             for _ in range(3):
                 run_c = eng.mt3d_run(field.data_ptr(), ISOVALUE, shape=shape, dtype=np.float32, flags=flags)
                 torch.cuda.synchronize()
                 t1 = time.perf_counter()
-                res = eng.mt3d_orient_reference() if name == "orient_reference" else \
-                    eng.mt3d_select_seeded(np.array([[min(pi, shape[0] - 2), min(pj, shape[1] - 2), min(pk, shape[2] - 2)]], np.int32))
+                if name == "orient_reference":
+                    res = eng.mt3d_orient_reference()
+                elif name == "select_seeded":
+                    res = eng.mt3d_select_seeded(np.array([[min(pi, shape[0] - 2), min(pj, shape[1] - 2), min(pk, shape[2] - 2)]], np.int32))
+                else:
+                    # the reference's whole post-processing (quantize, tiny, clean, orient; tetrahedral.py:541-552); at 511
+                    # voxels per axis its quantum is 1/19 of a voxel, so it merges a lot -- faithfully
+                    cc = eng.mt3d_clean([shape[0] - 1, shape[1] - 1, shape[2] - 1], orient=True)
+                    res = [int(cc.n_verts), int(cc.n_tris), int(cc.n_quantized), int(cc.n_tiny), int(cc.n_flat), int(cc.n_components)]
                 ts.append((time.perf_counter() - t1) * 1e3)
             post[name] = {"ms": min(ts), "result": list(res), "n_tris_in": int(run_c.n_tris)}
 

@@ -73,18 +73,40 @@ def main():
     st = acc / args.steps
     S = int(c.n_segments)
     alg = n * n * 4.0 + S * (1 + 16 + 16)                        # field once for all levels + level tag, 2 keys, 2 fp32 points
+    # CPU baseline (oracle port, 1 core, bounded sample of the same field) and end to end with host buffers
+    import time
+    from oracle import mt2d as o2, mp4d as o4           # the cpu_baseline leg: the oracle as the thing timed beside, never the product
+    c0 = n // 2 - 512
+    sub = f[c0:c0 + 1024, c0:c0 + 1024].cpu().numpy()
+    t0 = time.perf_counter()
+    for z in levels:
+        o2.extract_level(sub, z, np.float32)
+    cpu2 = sub.size / (time.perf_counter() - t0) / 1e9
+    hf2 = eng.pinned_empty("bench_field2d", (n, n), np.float32)
+    hf2[:] = f.cpu().numpy()
+    e2 = []
+    for _ in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.mt2d_run(hf2, levels)
+        o2d = eng.mt2d_fetch()
+        e2.append(time.perf_counter() - t0)
+    e2e2 = {"value": n * n / min(e2[1:]) / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": int(hf2.nbytes),
+            "d2h_bytes_per_step": int(o2d["level"].nbytes + o2d["keys"].nbytes + o2d["pos"].nbytes)}
+    del o2d
     print(json.dumps({"path": "2D marching triangles (BASELINE configs[1])", "metric": "Gsamples/s", "value": n * n / ms / 1e6,
+                      "cpu_baseline": {"value": cpu2, "unit": "Gsamples/s", "cores": 1, "kind": "port",
+                                       "sample": "1024^2 block from the middle of the same field, 16 levels, numpy oracle port"},
+                      "e2e": e2e2,
                       "msegments_per_s": S / ms / 1e3, "ms_per_step": ms, "n_segments": S, "levels": 16, "dtype": "f32",
                       "stage_ms": {"count_scan": float(st[1]), "emit": float(st[2])},
                       "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": pk, "unit": "GB/s",
                                    "frac": alg / ms / 1e6 / pk, "algorithmic_bytes": alg, "peak_source": src}}))
     # ---- 2D polylines end to end (a23 / f4): host array in, {level: [(closed, points)]} out, through the drop-in class
     from contourist_b200 import grid_field, multiple_2d_contour, triangulated
-    hf = eng.pinned_empty("bench_field2d", (n, n), np.float32)     # page-locked host field, as the e2e contract asks
-    hf[:] = f.cpu().numpy()
+    hf = hf2                                                       # page-locked host field, as the e2e contract asks
     grid = grid_field.FunctionGrid((0.0, 0.0), (n - 1.0, n - 1.0), (1.0, 1.0), hf)
     C = multiple_2d_contour.Multiple2DContourGrid(grid, levels)
-    import time
     D = C.get_contours_dictionary()                                # warm-up (buffers)
     ts = []
     for _ in range(3):
@@ -120,7 +142,7 @@ def main():
                                        "sample": "level 7 of the same run (%d segments), triangulated.chain_segments (numpy list ranking, the "
                                                  "restatement of triangulated.py:221-305)" % int(sel.sum())},
                       "device_chain_msegments_per_s": S / min(tk) / 1e6}))
-    del f, hf, seg, D
+    del f, hf, hf2, seg, D
     torch.cuda.empty_cache()
 
     # ---- 4D: configs[3]
@@ -137,7 +159,27 @@ def main():
     V, T, M = int(c.n_verts), int(c.n_tets), int(c.n_morph_tris)
     nsamp = float(np.prod(shape))
     alg = nsamp * 4 + V * 16 + T * 16 + M * 24                   # field + 4D points + tetrahedra + morph triangles (3 segments x 2 ids)
+    sub4 = f[56:72, 56:72, 56:72, 0:40].cpu().numpy()
+    t0 = time.perf_counter()
+    r4 = o4.extract(sub4, 1.2, np.float32)
+    bp = o4.bin_times(r4["pos"].astype(np.float64), sub4.shape[3] - 1)
+    cpu4 = sub4.size / (time.perf_counter() - t0) / 1e9
+    hf4 = eng.pinned_empty("bench_field4d", shape, np.float32)
+    hf4[:] = f.cpu().numpy()
+    e4 = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.mp4d_run(hf4, 1.2, flags=E.MORPH)
+        o4d = eng.mp4d_fetch()
+        e4.append(time.perf_counter() - t0)
+    e2e4 = {"value": nsamp / min(e4[1:]) / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": int(hf4.nbytes),
+            "d2h_bytes_per_step": int(sum(v.nbytes for v in o4d.values() if isinstance(v, np.ndarray)))}
+    del o4d
     print(json.dumps({"path": "4D marching pentatopes + morph triangles (BASELINE configs[3])", "metric": "Gsamples/s",
+                      "cpu_baseline": {"value": cpu4, "unit": "Gsamples/s", "cores": 1, "kind": "port",
+                                       "sample": "16x16x16x40 block of the same field, numpy oracle port (extract + bin_times)"},
+                      "e2e": e2e4,
                       "value": nsamp / ms / 1e6, "mtets_per_s": T / ms / 1e3, "ms_per_step": ms, "shape": list(shape),
                       "n_verts": V, "n_tets": T, "n_morph_tris": M, "dtype": "f32",
                       "stage_ms": {"bitplane": float(st[1]), "count_scan": float(st[2]), "emit_verts": float(st[3]),
