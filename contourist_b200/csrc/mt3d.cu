@@ -106,7 +106,7 @@ __device__ __forceinline__ double sample(const Grid<T>& g, int i, int j, int k) 
 
 // 6-bit mask of the tets of voxel (i,j,k) that emit triangles; also returns the 30-bit case code.
 template <typename T>
-__device__ __noinline__ unsigned cell_emit_exact(const Grid<T>& g, int i, int j, int k, unsigned* code_out) {
+__device__ __noinline__ unsigned cell_emit_exact(const Grid<T> g, int i, int j, int k, unsigned* code_out) {
   if (code_out) *code_out = 0;
   if (i < 0 || j < 0 || k < 0 || i >= g.n0 - 1 || j >= g.n1 - 1 || k >= g.n2 - 1) return 0;
   double fv[8];
@@ -139,7 +139,7 @@ __device__ __noinline__ unsigned cell_emit_exact(const Grid<T>& g, int i, int j,
 
 // Is the crossing edge p -> p+d used by any emitted triangle?  (OR over the voxels / tets that contain it.)
 template <typename T>
-__device__ __noinline__ bool edge_used_exact(const Grid<T>& g, int i, int j, int k, int d) {
+__device__ __noinline__ bool edge_used_exact(const Grid<T> g, int i, int j, int k, int d) {
   for (int s = 0; s < 8; ++s) {
     if (s & d) continue;
     unsigned tm = c_tetmask[d][s];
@@ -237,8 +237,18 @@ __device__ __forceinline__ void tet_words(const Planes& pl, const Planes* npl, u
 // ------------------------------------------------------------------------------------------------
 // used-edge words of an owner word (index d-1), allclose-ambiguous edges resolved exactly (serial, rare)
 // ------------------------------------------------------------------------------------------------
+// The out-of-line exact paths take and return their data BY VALUE: a reference or pointer to a kernel's registers
+// (the grid descriptor, the bit planes, the used-edge words) would pin those to local memory for the whole kernel --
+// measured: 1.9 M local-memory wave-fronts per extraction in k_emit_tris, 1.6 M in k_count_b, on paths that never run.
+struct W7 {
+  uint32_t x[7];
+};
+
 template <typename T>
-__device__ __noinline__ void resolve_used_exact(const Grid<T>& g, int i, int j, int w, uint32_t used[7]) {
+__device__ __noinline__ W7 resolve_used_exact(const Grid<T> g, int i, int j, int w, W7 in) {
+  uint32_t used[7];
+#pragma unroll
+  for (int d = 0; d < 7; ++d) used[d] = in.x[d];
   Planes npl;
   load_planes(g, g.nbits, i, j, w, npl);
   for (int d = 1; d <= 7; ++d) {
@@ -249,12 +259,23 @@ __device__ __noinline__ void resolve_used_exact(const Grid<T>& g, int i, int j, 
       if (!edge_used_exact(g, i, j, w * 32 + b, d)) used[d - 1] &= ~(1u << b);
     }
   }
+  W7 out;
+#pragma unroll
+  for (int d = 0; d < 7; ++d) out.x[d] = used[d];
+  return out;
 }
 
 template <typename T>
 __device__ __forceinline__ void owner_used(const Grid<T>& g, const Planes& pl, int i, int j, int w, uint32_t used[7]) {
   cross_words(pl, used);
-  if (g.any_near) resolve_used_exact(g, i, j, w, used);
+  if (g.any_near) {
+    W7 in;
+#pragma unroll
+    for (int d = 0; d < 7; ++d) in.x[d] = used[d];
+    const W7 out = resolve_used_exact(g, i, j, w, in);
+#pragma unroll
+    for (int d = 0; d < 7; ++d) used[d] = out.x[d];
+  }
 }
 
 __device__ __forceinline__ unsigned gather7(const uint32_t u[7], int b) {
@@ -272,9 +293,16 @@ __device__ __forceinline__ unsigned tet_mask_of(unsigned corner8, int t) {
 }
 
 // strict-crossing correction and exact tet counts of one word: the rare, allclose-dependent part of stage 2
+struct WordExact {
+  unsigned ncross, ntri;
+  uint32_t emitting;
+};
+
 template <typename T>
-__device__ __noinline__ void count_word_exact(const Grid<T>& g, const Planes& pl, int i, int j, int w, bool cells_ok,
-                                              unsigned& ncross, unsigned& ntri, uint32_t& emitting) {
+__device__ __noinline__ WordExact count_word_exact(const Grid<T> g, const Planes pl, int i, int j, int w, bool cells_ok,
+                                                   WordExact in) {
+  unsigned ncross = in.ncross, ntri = in.ntri;
+  uint32_t emitting = in.emitting;
   Planes npl;
   load_planes(g, g.nbits, i, j, w, npl);
   if (cells_ok) {
@@ -307,6 +335,11 @@ __device__ __noinline__ void count_word_exact(const Grid<T>& g, const Planes& pl
         if ((e >> q) & 1u) ntri += ((odd[q] >> b) & 1u) ? 1u : 2u;
     }
   }
+  WordExact out;
+  out.ncross = ncross;
+  out.ntri = ntri;
+  out.emitting = emitting;
+  return out;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -494,7 +527,7 @@ __global__ void __launch_bounds__(CS_THREADS) k_count_a(Grid<T> g, unsigned word
 // The word flag of stage 1 is dilated; every exact path of stage 2 starts from the near bits of the eight words a word
 // touches, so without any of those the plain bit logic is already exact.
 template <typename T>
-__device__ __noinline__ int near_bits_around(const Grid<T>& g, int i, int j, int w, uint32_t kpt) {
+__device__ __noinline__ int near_bits_around(const Grid<T> g, int i, int j, int w, uint32_t kpt) {
   Planes npl;
   load_planes(g, g.nbits, i, j, w, npl);
   return ((npl.P[0] | npl.P[1] | npl.P[2] | npl.P[3] | npl.S[0] | npl.S[1] | npl.S[2] | npl.S[3]) & kpt) != 0u;
@@ -503,7 +536,8 @@ __device__ __noinline__ int near_bits_around(const Grid<T>& g, int i, int j, int
 // Exact used-edge words that differ from the crossing words: stage 4 ranks the edges of rows (i..i+1, j..j+1) by these
 // words, so the voxel rows that read this one are told to recompute them exactly.
 template <typename T>
-__device__ __noinline__ void flag_exact_words(const Grid<T>& g, const Planes& pl, int i, int j, int w, const uint32_t x[7]) {
+__device__ __noinline__ void flag_exact_words(const Grid<T> g, const Planes pl, int i, int j, int w, const W7 x7) {
+  const uint32_t* x = x7.x;
   uint32_t xs[7];
   cross_words(pl, xs);
   uint32_t dif = 0;
@@ -566,7 +600,12 @@ __global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin
     load_planes(g, g.bits, i, j, w, pl);
     if (g.any_near) g.any_near = near_bits_around(g, i, j, w, pl.kpt);
     owner_used(g, pl, i, j, w, x);
-    if (g.any_near) flag_exact_words(g, pl, i, j, w, x);
+    if (g.any_near) {
+      W7 x7;
+#pragma unroll
+      for (int d = 0; d < 7; ++d) x7.x[d] = x[d];
+      flag_exact_words(g, pl, i, j, w, x7);
+    }
     unsigned v = 0;
 #pragma unroll
     for (int d = 0; d < 7; ++d) {
@@ -593,7 +632,16 @@ __global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin
         em |= odd[q] | two[q];
       }
     }
-    if (g.any_near) count_word_exact(g, pl, i, j, w, cells_ok, ncross, t, em);
+    if (g.any_near) {
+      WordExact we;
+      we.ncross = ncross;
+      we.ntri = t;
+      we.emitting = em;
+      we = count_word_exact(g, pl, i, j, w, cells_ok, we);
+      ncross = we.ncross;
+      t = we.ntri;
+      em = we.emitting;
+    }
     const uint32_t r = v | (t << 8);
     recc[idx] = r;                                        // record of list entry idx (k_scan walks the list, not the words)
     if (r) atomicAdd(&tile_vt[(gw - word0) / CS_TILE], rec_vt(r));
@@ -961,25 +1009,29 @@ __device__ __forceinline__ constexpr int edge_d(int e) {
 }
 
 // used-edge words of the voxel's four owner rows when some sample nearby is allclose to the isovalue (rare)
+struct W28 {
+  uint32_t x[4][7];
+};
+
 template <typename T>
-__device__ __noinline__ void rows_used_exact(const Grid<T>& gin, int i, int j, int w, uint32_t X[4][7]) {
-  Grid<T> g = gin;
+__device__ __noinline__ W28 rows_used_exact(Grid<T> g, int i, int j, int w) {
+  W28 out;
   g.any_near = 1;
   for (int ab = 0; ab < 4; ++ab) {
     Planes pl;
     load_planes(g, g.bits, i + (ab >> 1), j + (ab & 1), w, pl);
-    owner_used(g, pl, i + (ab >> 1), j + (ab & 1), w, X[ab]);
+    owner_used(g, pl, i + (ab >> 1), j + (ab & 1), w, out.x[ab]);
   }
+  return out;
 }
 
 // One thread per emitting voxel.  The id of each of the voxel's 19 edges is vbase[owner word] + dirbase + rank of the
 // owner bit in that direction's used-edge word -- all from the 2x2 rows of bit words the voxel touches (8 loads) and
 // the (vbase, dirpack) records of those rows.
-#ifdef CTR_ET_MINB
-#define CTR_ET_BOUNDS __launch_bounds__(ET_THREADS, CTR_ET_MINB)
-#else
-#define CTR_ET_BOUNDS __launch_bounds__(ET_THREADS)
+#ifndef CTR_ET_MINB
+#define CTR_ET_MINB 6           // 80 registers: 64.5 us (unbounded 124 registers: 72.7; 5 -> 96: 68.6)
 #endif
+#define CTR_ET_BOUNDS __launch_bounds__(ET_THREADS, CTR_ET_MINB)
 template <typename T>
 __global__ void CTR_ET_BOUNDS k_emit_tris(Grid<T> g, const unsigned long long* __restrict__ cell_id,
                                                           const uint32_t* __restrict__ cell_toff, const Counters* __restrict__ ctr,
@@ -1022,16 +1074,21 @@ __global__ void CTR_ET_BOUNDS k_emit_tris(Grid<T> g, const unsigned long long* _
   }
   // used-edge words per owner row (index ab) and direction (index d-1); only the 14 that voxel edges use.  No masks:
   // bits below a valid edge's bit are valid edges of the same direction
+  // (registers: only ever indexed by compile-time constants, and never handed out by address)
   uint32_t X[4][7];
+  X[0][0] = P[0] ^ S[0]; X[0][1] = P[0] ^ P[1]; X[0][2] = P[0] ^ S[1]; X[0][3] = P[0] ^ P[2];
+  X[0][4] = P[0] ^ S[2]; X[0][5] = P[0] ^ P[3]; X[0][6] = P[0] ^ S[3];
+  X[1][0] = P[1] ^ S[1]; X[1][3] = P[1] ^ P[3]; X[1][4] = P[1] ^ S[3];
+  X[2][0] = P[2] ^ S[2]; X[2][1] = P[2] ^ P[3]; X[2][2] = P[2] ^ S[3];
+  X[3][0] = P[3] ^ S[3];
   if (near) {
     const unsigned i = g.divN1.div(row);
-    rows_used_exact(g, (int)i, (int)(row - i * (unsigned)g.n1), (int)w, X);
-  } else {
-    X[0][0] = P[0] ^ S[0]; X[0][1] = P[0] ^ P[1]; X[0][2] = P[0] ^ S[1]; X[0][3] = P[0] ^ P[2];
-    X[0][4] = P[0] ^ S[2]; X[0][5] = P[0] ^ P[3]; X[0][6] = P[0] ^ S[3];
-    X[1][0] = P[1] ^ S[1]; X[1][3] = P[1] ^ P[3]; X[1][4] = P[1] ^ S[3];
-    X[2][0] = P[2] ^ S[2]; X[2][1] = P[2] ^ P[3]; X[2][2] = P[2] ^ S[3];
-    X[3][0] = P[3] ^ S[3];
+    const W28 e = rows_used_exact(g, (int)i, (int)(row - i * (unsigned)g.n1), (int)w);
+    X[0][0] = e.x[0][0]; X[0][1] = e.x[0][1]; X[0][2] = e.x[0][2]; X[0][3] = e.x[0][3];
+    X[0][4] = e.x[0][4]; X[0][5] = e.x[0][5]; X[0][6] = e.x[0][6];
+    X[1][0] = e.x[1][0]; X[1][3] = e.x[1][3]; X[1][4] = e.x[1][4];
+    X[2][0] = e.x[2][0]; X[2][1] = e.x[2][1]; X[2][2] = e.x[2][2];
+    X[3][0] = e.x[3][0];
   }
   // owner points at k+1: bit b+1 of the same word, or (b == 31) bit 0 of the next word, which has rank 0
   const uint32_t below = (1u << b) - 1u;
