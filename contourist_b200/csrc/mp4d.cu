@@ -883,14 +883,11 @@ constexpr int SL_PER = 4;                            // consecutive tetrahedra p
 constexpr int SL_TILE = SL_THREADS * SL_PER;         // serialise on the ticket atomic and on the look-back)
 constexpr int SL_MAXTRI = SL_TILE * 6;               // a tetrahedron gives at most 3 slices x 2 triangles
 
-// what the write-out needs of one tetrahedron: id-sorted corners, triangle code, low-t-first flags | first triangle << 8
-struct __align__(16) SlRec {
-  int v[4];
-  unsigned long long code;
-  unsigned swap_first;
-  unsigned pad;
-};
-constexpr int SL_SMEM = SL_TILE * (int)sizeof(SlRec) + SL_MAXTRI * 2;     // records + the tetrahedron of every triangle
+// What the write-out needs of one tetrahedron, as arrays over the tile's tetrahedra (structure of arrays: a round of
+// the write-out reads the records of ~32 consecutive tetrahedra, one word per lane and field -> no bank conflicts):
+// id-sorted corners v[0..3], triangle code (two halves), low-t-first flags | first triangle << 8.
+constexpr int SL_FIELDS = 7;
+constexpr int SL_SMEM = SL_TILE * SL_FIELDS * 4 + SL_MAXTRI * 2;        // records + the tetrahedron of every triangle
 
 template <typename TT>
 __device__ __forceinline__ bool slice_load(const double* __restrict__ verts, const int* __restrict__ tbin,
@@ -938,8 +935,8 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
                                                        int* __restrict__ out, unsigned cap,
                                                        const unsigned long long* __restrict__ pattern_tab) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  SlRec* s_rec = reinterpret_cast<SlRec*>(s_dyn);                            // [SL_TILE]
-  unsigned short* s_own = reinterpret_cast<unsigned short*>(s_dyn + SL_TILE * sizeof(SlRec));   // [SL_MAXTRI]
+  unsigned* s_f = reinterpret_cast<unsigned*>(s_dyn);                        // [SL_FIELDS][SL_TILE]
+  unsigned short* s_own = reinterpret_cast<unsigned short*>(s_dyn + SL_TILE * SL_FIELDS * 4);   // [SL_MAXTRI]
   __shared__ unsigned s_tile;
   __shared__ unsigned s_tab[64];
   __shared__ unsigned long long s_warp[SL_THREADS / 32], s_excl;
@@ -947,19 +944,21 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
   if (threadIdx.x < 64) s_tab[threadIdx.x] = slice_entry(threadIdx.x);
   __syncthreads();
   const int tile = (int)s_tile;
-  const unsigned a0 = (unsigned)tile * SL_TILE + threadIdx.x * SL_PER;
+  const unsigned tile0 = (unsigned)tile * SL_TILE;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  // tetrahedron u of this thread is number u * 256 + thread in the tile: consecutive lanes, consecutive tetrahedra
   unsigned long long code[SL_PER];
-  int cnt[SL_PER], n = 0;
+  int cnt[SL_PER];
   int vv[SL_PER][4];                                  // id-sorted corners and low-t-first flags, kept for the write phase
   unsigned swapm[SL_PER];
+  unsigned long long n4 = 0;                          // the four counts, 16 bits each (a quarter tile has <= 1536 triangles)
 #pragma unroll
   for (int u = 0; u < SL_PER; ++u) {
     cnt[u] = 0;
     code[u] = 0ull;
     swapm[u] = 0;
     vv[u][0] = vv[u][1] = vv[u][2] = vv[u][3] = 0;
-    const unsigned a = a0 + u;
+    const unsigned a = tile0 + (unsigned)u * SL_THREADS + threadIdx.x;
     if (a < nt && (keep_out || keep[a])) {
       TT tv[4];
       const bool distinct = slice_load<TT>(verts, tbin, tets, a, vv[u], tv);
@@ -973,55 +972,64 @@ __global__ void __launch_bounds__(SL_THREADS) k4_slice(const double* __restrict_
       }
       if (distinct && kept) slice_lookup<TT>(tv, mp, s_tab, pattern_tab, code[u], cnt[u], swapm[u]);
     }
-    n += cnt[u];
+    n4 |= (unsigned long long)cnt[u] << (16 * u);
   }
-  const unsigned long long inc = warp_incl_scan_u64((unsigned long long)n);
+  // one packed scan gives the prefix of every quarter (threads of one u) at once
+  const unsigned long long inc = warp_incl_scan_u64(n4);
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
-  unsigned long long woff = 0, blk = 0;
+  unsigned long long woff = 0, tot4 = 0;
 #pragma unroll
   for (int q = 0; q < SL_THREADS / 32; ++q) {
     if (q < (int)warp) woff += s_warp[q];
-    blk += s_warp[q];
+    tot4 += s_warp[q];
+  }
+  const unsigned long long excl4 = woff + inc - n4;           // per quarter: triangles of the threads before this one
+  unsigned qbase[SL_PER], blk = 0;
+#pragma unroll
+  for (int u = 0; u < SL_PER; ++u) {
+    qbase[u] = blk;                                            // triangles of the quarters before quarter u
+    blk += (unsigned)(tot4 >> (16 * u)) & 0xffffu;
   }
   // The tile's aggregate is published at once; the look-back is resolved after the records below have been staged: by
   // then the predecessors have published theirs and the warp does not sit polling.
-  if (warp == 0) lb_publish(status, tile, blk);
-  // A thread that wrote its own triangles would run as long as the warp's busiest lane (0..24 triangles) with most
-  // lanes idle; instead every tetrahedron leaves a record in shared memory and marks its triangles with its number,
-  // and the tile's triangles are then dealt out one per thread per round.
-  unsigned loc = (unsigned)(woff + inc - (unsigned long long)n);           // first triangle of this thread in the tile
+  if (warp == 0) lb_publish(status, tile, (unsigned long long)blk);
+  // A thread that wrote its own triangles would run as long as the warp's busiest lane with most lanes idle; instead
+  // every tetrahedron leaves a record in shared memory and marks its triangles with its number, and the tile's
+  // triangles are then dealt out one per thread per round.
 #pragma unroll
   for (int u = 0; u < SL_PER; ++u) {
-    const unsigned tl = (unsigned)u * SL_THREADS + threadIdx.x;        // lane stride = one record: no 32-way bank conflict
-    SlRec r;
-    r.v[0] = vv[u][0]; r.v[1] = vv[u][1]; r.v[2] = vv[u][2]; r.v[3] = vv[u][3];
-    r.code = code[u];
-    r.swap_first = swapm[u] | (loc << 8);
-    r.pad = 0;
-    s_rec[tl] = r;
+    const unsigned tl = (unsigned)u * SL_THREADS + threadIdx.x;
+    const unsigned loc = qbase[u] + ((unsigned)(excl4 >> (16 * u)) & 0xffffu);
+    s_f[0 * SL_TILE + tl] = (unsigned)vv[u][0];
+    s_f[1 * SL_TILE + tl] = (unsigned)vv[u][1];
+    s_f[2 * SL_TILE + tl] = (unsigned)vv[u][2];
+    s_f[3 * SL_TILE + tl] = (unsigned)vv[u][3];
+    s_f[4 * SL_TILE + tl] = (unsigned)(code[u] & 0xffffffffull);
+    s_f[5 * SL_TILE + tl] = (unsigned)(code[u] >> 32);
+    s_f[6 * SL_TILE + tl] = swapm[u] | (loc << 8);
     for (int q = 0; q < cnt[u]; ++q) s_own[loc + q] = (unsigned short)tl;
-    loc += (unsigned)cnt[u];
   }
   if (warp == 0) {
-    unsigned long long e = lb_resolve(status, tile, blk);
+    unsigned long long e = lb_resolve(status, tile, (unsigned long long)blk);
     if (lane == 0) s_excl = e;
   }
   __syncthreads();
   const unsigned long long base = s_excl;
-  const unsigned nb = (unsigned)blk;
-  for (unsigned q = threadIdx.x; q < nb; q += SL_THREADS) {
+  for (unsigned q = threadIdx.x; q < blk; q += SL_THREADS) {
     if (base + q >= cap) break;
-    const SlRec& r = s_rec[s_own[q]];
-    const unsigned idx = q - (r.swap_first >> 8);
-    const unsigned t9 = (unsigned)(r.code >> (9 * idx)) & 511u;
+    const unsigned tl = s_own[q];
+    const unsigned sf = s_f[6 * SL_TILE + tl];
+    const unsigned idx = q - (sf >> 8);
+    const unsigned long long c = ((unsigned long long)s_f[5 * SL_TILE + tl] << 32) | s_f[4 * SL_TILE + tl];
+    const unsigned t9 = (unsigned)(c >> (9 * idx)) & 511u;
     int2* o = reinterpret_cast<int2*>(out + (base + q) * 6);
 #pragma unroll
     for (int rr = 0; rr < 3; ++rr) {
       const unsigned e = (t9 >> (3 * rr)) & 7u;
       // corners of edge e: EA = {0,0,0,1,1,2}, EB = {1,2,3,2,3,3} as 2-bit fields
-      const int i0 = r.v[(0x940u >> (2 * e)) & 3u], i1 = r.v[(0xfb9u >> (2 * e)) & 3u];
-      const bool swap = (r.swap_first >> e) & 1u;
+      const int i0 = (int)s_f[((0x940u >> (2 * e)) & 3u) * SL_TILE + tl], i1 = (int)s_f[((0xfb9u >> (2 * e)) & 3u) * SL_TILE + tl];
+      const bool swap = (sf >> e) & 1u;
       o[rr] = swap ? make_int2(i1, i0) : make_int2(i0, i1);
     }
   }
