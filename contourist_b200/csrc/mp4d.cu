@@ -65,7 +65,7 @@ __device__ __forceinline__ bool near_a4(double f, double v) {
 
 // 24-bit mask of the pentatopes of hypervoxel (i,j,k,l) that emit tetrahedra (exact, fp64, from the samples)
 template <typename T>
-__device__ __noinline__ unsigned cell_emit_exact4(const Grid4<T>& g, int i, int j, int k, int l, uint8_t* codes24) {
+__device__ __noinline__ unsigned cell_emit_exact4(const Grid4<T> g, int i, int j, int k, int l, uint8_t* codes24) {
   if (i < 0 || j < 0 || k < 0 || l < 0 || i >= g.n0 - 1 || j >= g.n1 - 1 || k >= g.n2 - 1 || l >= g.n3 - 1) {
     if (codes24)
       for (int p = 0; p < 24; ++p) codes24[p] = 0;
@@ -94,7 +94,7 @@ __device__ __noinline__ unsigned cell_emit_exact4(const Grid4<T>& g, int i, int 
 }
 
 template <typename T>
-__device__ __noinline__ bool edge_used_exact4(const Grid4<T>& g, int i, int j, int k, int l, int d) {
+__device__ __noinline__ bool edge_used_exact4(const Grid4<T> g, int i, int j, int k, int l, int d) {
   for (int s = 0; s < 16; ++s) {
     if (s & d) continue;
     const unsigned pm = c4_pentmask[d][s];
@@ -179,8 +179,17 @@ __device__ __forceinline__ void pent_words4(const Planes4& pl, const Planes4* np
   }
 }
 
+// The out-of-line exact paths take and return their data BY VALUE: a reference to a kernel's registers (grid
+// descriptor, bit planes, used-edge words) would pin those to local memory for the whole kernel (mt3d.cu, same note).
+struct W15 {
+  uint32_t x[15];
+};
+
 template <typename T>
-__device__ __noinline__ void resolve_used_exact4(const Grid4<T>& g, int i, int j, int k, int w, uint32_t used[15]) {
+__device__ __noinline__ W15 resolve_used_exact4(const Grid4<T> g, int i, int j, int k, int w, W15 in) {
+  uint32_t used[15];
+#pragma unroll
+  for (int d = 0; d < 15; ++d) used[d] = in.x[d];
   Planes4 npl;
   load_planes4(g, g.nbits, i, j, k, w, npl);
   for (int d = 1; d <= 15; ++d) {
@@ -192,12 +201,23 @@ __device__ __noinline__ void resolve_used_exact4(const Grid4<T>& g, int i, int j
       if (!edge_used_exact4(g, i, j, k, w * 32 + b, d)) used[d - 1] &= ~(1u << b);
     }
   }
+  W15 out;
+#pragma unroll
+  for (int d = 0; d < 15; ++d) out.x[d] = used[d];
+  return out;
 }
 
 template <typename T>
 __device__ __forceinline__ void owner_used4(const Grid4<T>& g, const Planes4& pl, int i, int j, int k, int w, uint32_t used[15]) {
   cross_words4(pl, used);
-  if (g.any_near) resolve_used_exact4(g, i, j, k, w, used);
+  if (g.any_near) {
+    W15 in;
+#pragma unroll
+    for (int d = 0; d < 15; ++d) in.x[d] = used[d];
+    const W15 out = resolve_used_exact4(g, i, j, k, w, in);
+#pragma unroll
+    for (int d = 0; d < 15; ++d) used[d] = out.x[d];
+  }
 }
 
 __device__ __forceinline__ unsigned gather15(const uint32_t u[15], int b) {
@@ -219,9 +239,16 @@ __device__ __forceinline__ unsigned ntet_of_mask(unsigned m) {       // pentatop
   return (n == 0 || n == 5) ? 0u : ((n == 1 || n == 4) ? 1u : 3u);
 }
 
+struct WordExact4 {
+  unsigned ntet;
+  uint32_t emitting;
+};
+
 template <typename T>
-__device__ __noinline__ void count_word_exact4(const Grid4<T>& g, const Planes4& pl, int i, int j, int k, int w,
-                                               unsigned& ntet, uint32_t& emitting, uint32_t cand) {
+__device__ __noinline__ WordExact4 count_word_exact4(const Grid4<T> g, const Planes4 pl, int i, int j, int k, int w,
+                                                     WordExact4 in, uint32_t cand) {
+  unsigned ntet = in.ntet;
+  uint32_t emitting = in.emitting;
   while (cand) {
     const int b = __ffs(cand) - 1;
     cand &= cand - 1;
@@ -234,6 +261,10 @@ __device__ __noinline__ void count_word_exact4(const Grid4<T>& g, const Planes4&
     for (int p = 0; p < 24; ++p)
       if ((e >> p) & 1u) ntet += ntet_of_mask(pent_mask_of(c16, p));
   }
+  WordExact4 out;
+  out.ntet = ntet;
+  out.emitting = emitting;
+  return out;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -351,7 +382,14 @@ __global__ void __launch_bounds__(C4_THREADS, 2) k4_count_scan(Grid4<T> gin, uns
       }
       uint32_t cand;
       pent_words4(pl, g.any_near ? &npl : nullptr, pl.kp1, t, em, cand);
-      if (cand) count_word_exact4(g, pl, i, j, k, w, t, em, cand);
+      if (cand) {
+        WordExact4 we;
+        we.ntet = t;
+        we.emitting = em;
+        we = count_word_exact4(g, pl, i, j, k, w, we, cand);
+        t = we.ntet;
+        em = we.emitting;
+      }
     }
     sh.cv[wl] = (unsigned short)v;
     sh.ct[wl] = (unsigned short)t;
@@ -619,8 +657,12 @@ __global__ void __launch_bounds__(256) k4_emit_verts(Grid4<T> g, const unsigned 
 // ------------------------------------------------------------------------------------------------
 constexpr int E4_THREADS = 64;
 
+#ifndef CTR_E4_MINB
+#define CTR_E4_MINB 8           // 128 registers: 0.565 ms (unbounded 161: 0.615; 10 -> 96: 0.681; 12 -> 80: 0.744)
+#endif
+#define CTR_E4_BOUNDS __launch_bounds__(E4_THREADS, CTR_E4_MINB)
 template <typename T>
-__global__ void __launch_bounds__(E4_THREADS) k4_emit_tets(Grid4<T> gin, const unsigned long long* __restrict__ cell_id,
+__global__ void CTR_E4_BOUNDS k4_emit_tets(Grid4<T> gin, const unsigned long long* __restrict__ cell_id,
                                                            const uint32_t* __restrict__ cell_toff, unsigned n_cells,
                                                            const uint32_t* __restrict__ vbase, int* __restrict__ tets,
                                                            uint8_t* __restrict__ codes,
