@@ -1441,21 +1441,24 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
       uint8_t* dlow = want_k ? (uint8_t*)ctx->lowmin.p : nullptr;
       // grids cover the expected list lengths (last run's, with head-room); blocks past the real length return at once
       const unsigned vb = (unsigned)((std::min<size_t>(cap_own, ctx->last_own + ctx->last_own / 8 + 4096) + 255) / 256);
+      // the kernels read list entries below min(list length, this bound): the grid's cover rounded up to whole blocks
+      // may pass the list's capacity, and entries behind the capacity do not exist
+      const unsigned bound_own = std::min(vb * 256u, cap_own);
       const unsigned long long* oid = (const unsigned long long*)b_own_id.p;
       const unsigned long long* ovo = (const unsigned long long*)b_own_voff.p;
       const uint4* dwr = (const uint4*)ctx->wdir.p;
       if (f64)
-        k_emit_verts<T, double><<<vb, 256, 0, st>>>(g, oid, ovo, dwr, dctr, vb * 256u, cap_v, xf, (double*)ctx->verts.p,
+        k_emit_verts<T, double><<<vb, 256, 0, st>>>(g, oid, ovo, dwr, dctr, bound_own, cap_v, xf, (double*)ctx->verts.p,
                                                     want_n ? (double*)ctx->normals.p : nullptr, dkeys, dlow);
       else
-        k_emit_verts<T, float><<<vb, 256, 0, st>>>(g, oid, ovo, dwr, dctr, vb * 256u, cap_v, xf, (float*)ctx->verts.p,
+        k_emit_verts<T, float><<<vb, 256, 0, st>>>(g, oid, ovo, dwr, dctr, bound_own, cap_v, xf, (float*)ctx->verts.p,
                                                    want_n ? (float*)ctx->normals.p : nullptr, dkeys, dlow);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_verts");
       ctr_stage_mark(ctx, 4);
       const unsigned tb = (unsigned)((std::min<size_t>(cap_cell, ctx->last_cell + ctx->last_cell / 8 + 4096) + ET_THREADS - 1) / ET_THREADS);
       k_emit_tris<T><<<tb, ET_THREADS, 0, st>>>(g, (const unsigned long long*)b_cell_id.p, (const uint32_t*)b_cell_toff.p, dctr,
-                                                tb * (unsigned)ET_THREADS, cap_t, (const uint4*)ctx->wdir.p,
+                                                std::min(tb * (unsigned)ET_THREADS, cap_cell), cap_t, (const uint4*)ctx->wdir.p,
                                                 (const uint32_t*)ctx->vox_tab.p, (int*)ctx->tris.p);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_tris");

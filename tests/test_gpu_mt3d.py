@@ -211,6 +211,27 @@ def test_enqueue_finish_equals_run(engine):
     fresh.close()
 
 
+def test_pools_grow_from_a_tiny_first_run(engine):
+    """A context whose pools were sized by a tiny run meets volumes whose lists overflow them several times over: the
+    speculative stages must stay inside the capacities (never read list entries behind them) and the redo must give the
+    mesh of a context that has always been large."""
+    from contourist_b200 import engine as E
+    rng = np.random.default_rng(77)
+    flags = E.WANT_KEYS | E.WANT_NORMALS
+    small = E.Engine(0)
+    small.mt3d_run(rng.standard_normal((6, 7, 9)), 0.0, flags=flags)
+    for shape in ((40, 33, 70), (64, 96, 160), (150, 130, 257)):
+        f = rng.standard_normal(shape).astype(np.float32)
+        c0 = small.mt3d_run(f, 0.0, flags=flags)
+        o0 = small.mt3d_fetch()
+        c1 = engine.mt3d_run(f, 0.0, flags=flags)
+        o1 = engine.mt3d_fetch()
+        assert (c0.n_verts, c0.n_tris, c0.n_active_cells, c0.n_crossings) == (c1.n_verts, c1.n_tris, c1.n_active_cells, c1.n_crossings)
+        for name in ("keys", "lowmin", "verts", "normals", "tris"):
+            assert np.array_equal(o0[name], o1[name]), name
+    small.close()
+
+
 def test_pipelined_host_extraction_equals_single_run(engine):
     """engine.mt3d_extract_host (slab-by-slab upload / extract / download on two contexts, global triangle ids via
     vert_id_base) returns exactly the mesh of one ctr_mt3d_run + ctr_mt3d_fetch."""
