@@ -528,7 +528,7 @@ def run_ours(args):
                          "sample": "33x160x160 block from the middle of the same field, numpy oracle port (extract + normals)"},
         "e2e": {"value": e2e_val, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "h2d_copy_gbs_rank0_all_ranks_copying": h2d_gbs,
-                "note": "Engine.mt3d_extract_host (ctr_mt3d_enqueue / _finish / _fetch per z-slab on two contexts, slab s+1 queued "
+                "note": "Engine.mt3d_extract_host (volume uploaded once, plane by plane, by ctr_stage_upload on an upload context; ctr_mt3d_enqueue / _finish / _fetch per z-slab on two contexts, slab s+1 queued "
                         "while slab s runs, page-locked host buffers): H2D of the field and D2H of vertices, normals and "
                         "triangles inside the timed region"},
         "gpu_launches": int(launches), "clocks": clocks,

@@ -55,6 +55,7 @@ extern "C" void ctr_destroy(ctr_ctx* c) {
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
   if (c->ev_enqueued) cudaEventDestroy(c->ev_enqueued);
+  if (c->ev_tail) cudaEventDestroy(c->ev_tail);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -100,5 +101,30 @@ extern "C" int ctr_host_alloc(ctr_ctx* c, uint64_t bytes, void** out) {
 extern "C" int ctr_host_free(ctr_ctx* c, void* p) {
   if (!c) return CTR_ERR_BAD_ARG;
   if (p) CTR_CUDA(c, cudaFreeHost(p));
+  return 0;
+}
+
+extern "C" int ctr_stage_upload(ctr_ctx* c, const void* host, uint64_t dst_offset, uint64_t bytes, uint64_t total_bytes,
+                                void** device_base) {
+  if (!c) return CTR_ERR_BAD_ARG;
+  if (!device_base || (bytes && !host)) return ctr_fail(c, CTR_ERR_BAD_ARG, "null argument");
+  if (dst_offset > total_bytes || bytes > total_bytes - dst_offset) return ctr_fail(c, CTR_ERR_BAD_ARG, "piece outside the staging buffer");
+  CTR_CUDA(c, cudaSetDevice(c->device));
+  int rc;
+  if ((rc = ctr_ensure(c, c->field, total_bytes ? total_bytes : 1))) return rc;
+  *device_base = c->field.p;
+  if (bytes)
+    CTR_CUDA(c, cudaMemcpyAsync((char*)c->field.p + dst_offset, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
+extern "C" int ctr_wait_for(ctr_ctx* c, ctr_ctx* other) {
+  if (!c || !other) return CTR_ERR_BAD_ARG;
+  if (c->device != other->device) return ctr_fail(c, CTR_ERR_BAD_ARG, "contexts on different devices");
+  if (c == other || c->stream == other->stream) return 0;          // one stream: already ordered
+  CTR_CUDA(c, cudaSetDevice(c->device));
+  if (!other->ev_tail) CTR_CUDA(c, cudaEventCreateWithFlags(&other->ev_tail, cudaEventDisableTiming));
+  CTR_CUDA(c, cudaEventRecord(other->ev_tail, other->stream));
+  CTR_CUDA(c, cudaStreamWaitEvent(c->stream, other->ev_tail, 0));
   return 0;
 }

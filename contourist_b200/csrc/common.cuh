@@ -24,6 +24,7 @@ struct ctr_ctx {
   bool own_stream = false;
   cudaEvent_t ev_enqueued = nullptr;   // recorded behind everything ctr_mt3d_enqueue queued: ctr_mt3d_finish waits for it,
                                        // not for the stream (work queued later, e.g. a collective, is not its business)
+  cudaEvent_t ev_tail = nullptr;       // ctr_wait_for(other context, this): marks this stream's tail for the other stream
   std::string err;
   int64_t launches = 0;
   bool timing = false;

@@ -1029,7 +1029,7 @@ __device__ __noinline__ W28 rows_used_exact(Grid<T> g, int i, int j, int w) {
 // owner bit in that direction's used-edge word -- all from the 2x2 rows of bit words the voxel touches (8 loads) and
 // the (vbase, dirpack) records of those rows.
 #ifndef CTR_ET_MINB
-#define CTR_ET_MINB 6           // 80 registers: 64.5 us (unbounded 124 registers: 72.7; 5 -> 96: 68.6)
+#define CTR_ET_MINB 10          // 48 registers: 56.4 us (12 -> 40: 57.3; 8 -> 64: 59.5; 7: 60.5; 6 -> 80 registers: 64.5; 5 -> 96: 68.6; unbounded 124: 72.7)
 #endif
 #define CTR_ET_BOUNDS __launch_bounds__(ET_THREADS, CTR_ET_MINB)
 template <typename T>

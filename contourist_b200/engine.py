@@ -123,6 +123,10 @@ def load_library():
     lib.ctr_host_alloc.restype = i32
     lib.ctr_host_free.argtypes = [vp, vp]
     lib.ctr_host_free.restype = i32
+    lib.ctr_stage_upload.argtypes = [vp, vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(vp)]
+    lib.ctr_stage_upload.restype = i32
+    lib.ctr_wait_for.argtypes = [vp, vp]
+    lib.ctr_wait_for.restype = i32
     _bind_optional(lib)
     _lib = lib
     return lib
@@ -157,9 +161,10 @@ class Engine(object):
             if self.__dict__.get("_xpool") is not None:
                 self._xpool.shutdown(wait=True)
                 self._xpool = None
-            if self.__dict__.get("_twin") is not None:
-                self._twin.close()
-                self._twin = None
+            for name in ("_twin", "_uploader"):
+                if self.__dict__.get(name) is not None:
+                    self.__dict__[name].close()
+                    self.__dict__[name] = None
             for ptr, _ in getattr(self, "_pinned", {}).values():
                 self.lib.ctr_host_free(self.h, ptr)
             self._pinned = {}
@@ -210,6 +215,18 @@ class Engine(object):
 
     def kernel_launches(self):
         return int(self.lib.ctr_kernel_launches(self.h))
+
+    def stage_upload(self, host, dst_offset, total_bytes):
+        """Queue the copy of the C-contiguous array `host` to byte offset dst_offset of this context's staging buffer
+        (grown to total_bytes first) and return the buffer's device address without waiting (ctr_stage_upload)."""
+        base = ctypes.c_void_p()
+        self._check(self.lib.ctr_stage_upload(self.h, ctypes.c_void_p(host.ctypes.data), int(dst_offset), int(host.nbytes),
+                                              int(total_bytes), ctypes.byref(base)), "ctr_stage_upload")
+        return int(base.value)
+
+    def wait_for(self, other):
+        """Work queued on this engine from now on starts when what `other` has queued so far is done (device-side)."""
+        self._check(self.lib.ctr_wait_for(self.h, other.h), "ctr_wait_for")
 
     # ------------------------------------------------------------------ 3D
     def _mt3d_params(self, field, value, origin, delta, flags, i_lo, i_hi, plane_offset, shape, dtype, vert_id_base):
@@ -394,11 +411,14 @@ class Engine(object):
                           plane_offset=0):
         """Host array in, host mesh out, with the PCIe traffic of the two directions overlapped.
 
-        The volume is cut into `nslabs` z-slabs (sharding.slab_with_halo, the multi-GPU decomposition); slab s is
-        uploaded and extracted on one of two alternating contexts while a worker thread downloads the mesh of slab
-        s-1 from the other (PCIe is full duplex; ctypes releases the GIL), and slab s+1 is already queued
-        (`ctr_mt3d_enqueue`) when the host waits for slab s, so the upload engine never idles.  Triangle ids are global:
-        the vertex count of the slabs before a slab is added on the device (`ctr_mt3d_offset_ids`) before its download.  own=(A, B) restricts the call to owner planes
+        The volume is cut into `nslabs` z-slabs (sharding.slab_with_halo, the multi-GPU decomposition).  An upload
+        context sends the planes to the device ONCE, in slab order, on its own stream (ctr_stage_upload: a slab's halo
+        planes are already there from its neighbour, so the host sends n0 planes, not n0 + 3 per slab); slab s is
+        extracted from the staged planes on one of two alternating contexts as soon as its last plane has arrived
+        (ctr_wait_for), while a worker thread downloads the mesh of slab s-1 from the other (PCIe is full duplex; ctypes
+        releases the GIL), and slab s+1 is already queued (`ctr_mt3d_enqueue`) when the host waits for slab s, so the
+        upload engine never idles.  Triangle ids are global: the vertex count of the slabs before a slab is added on
+        the device (`ctr_mt3d_offset_ids`) before its download.  own=(A, B) restricts the call to owner planes
         [A, B) of the array (a rank's slab with its halo planes around it) and plane_offset is the global index of
         the array's first plane, as in ctr_mt3d_params.  `field` should be page-locked
         (Engine.pinned_empty) for full transfer rate.  Returns (totals dict, arrays dict); the arrays live in the
@@ -417,6 +437,10 @@ class Engine(object):
         if twin is None or twin.h is None:
             twin = self._twin = Engine(self.device)
         engines = (self, twin)
+        up = self.__dict__.get("_uploader")
+        if up is None or up.h is None:
+            up = self._uploader = Engine(self.device)
+        plane_bytes = field.shape[1] * field.shape[2] * field.itemsize
         pool = self.__dict__.setdefault("_xpool", ThreadPoolExecutor(max_workers=1))
         gd = np.float64 if flags & GEOM_F64 else np.float32
         gsz = np.dtype(gd).itemsize
@@ -453,14 +477,23 @@ class Engine(object):
                     kw["plane_offset"] += int(plane_offset)
                     slabs.append((lo, hi, kw))
 
+            first = slabs[0][0] if slabs else 0              # planes [first, last) of the array are staged at offset 0
+            last = slabs[-1][1] if slabs else 0
+            sent = [first]
+
             def enqueue(k):
-                # queued, not waited for: the upload of slab k runs while the kernels of slab k-1 do.  Its vertex ids
-                # start at 0; the base (vertices of the slabs before it) is added on the device once it is known.
+                # queued, not waited for: the planes slab k still lacks go up on the upload stream while the kernels of
+                # slab k-1 run.  Its vertex ids start at 0; the base (vertices of the slabs before it) is added on the
+                # device once it is known.
                 lo, hi, kw = slabs[k]
                 if pending[k & 1] is not None:
                     pending[k & 1].result()                   # the context's previous slab has been downloaded
                     pending[k & 1] = None
-                engines[k & 1].mt3d_enqueue(field[lo:hi], value, origin=origin, delta=delta, flags=flags, **kw)
+                base = up.stage_upload(field[sent[0]:max(hi, sent[0])], (sent[0] - first) * plane_bytes, (last - first) * plane_bytes)
+                sent[0] = max(hi, sent[0])
+                engines[k & 1].wait_for(up)
+                engines[k & 1].mt3d_enqueue(base + (lo - first) * plane_bytes, value, origin=origin, delta=delta, flags=flags,
+                                            shape=(hi - lo,) + tuple(field.shape[1:]), dtype=field.dtype, **kw)
 
             enqueue(0)
             for k in range(len(slabs)):
@@ -475,7 +508,8 @@ class Engine(object):
                 if vsum:
                     eng._check(eng.lib.ctr_mt3d_offset_ids(eng.h, vsum), "ctr_mt3d_offset_ids")
                 if not overflow and vsum + nv <= cap_v and tsum + nt <= cap_t:
-                    pending[k & 1] = pool.submit(fetch, eng, vsum, tsum, nv, nt)
+                    if nv or nt:                              # (an empty slab has nothing to download; on a context's
+                        pending[k & 1] = pool.submit(fetch, eng, vsum, tsum, nv, nt)   # first call there are no buffers yet)
                 else:
                     overflow = True                           # first call (sizes unknown) or a larger mesh than before
                 vsum += nv

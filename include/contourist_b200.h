@@ -79,6 +79,18 @@ CTR_API int64_t ctr_kernel_launches(const ctr_ctx* ctx);
 CTR_API int ctr_host_alloc(ctr_ctx* ctx, uint64_t bytes, void** out);
 CTR_API int ctr_host_free(ctr_ctx* ctx, void* p);
 
+/* Pipelines that span contexts (engine.py: mt3d_extract_host uploads a host volume ONCE on an upload context while
+ * two extraction contexts work through its slabs, instead of re-sending each slab's halo planes).
+ * ctr_stage_upload: queue, on ctx's stream, the copy of `bytes` from host memory to byte offset `dst_offset` of the
+ *   context's staging buffer, which is first grown to `total_bytes` (growing waits for the stream and discards the
+ *   content: pass the final size with the first piece).  *device_base receives the buffer's device address; it is
+ *   valid until the buffer grows or the context is destroyed.  Returns without waiting for the copy.
+ * ctr_wait_for: whatever is queued on ctx after this call starts only when everything queued on `other` so far has
+ *   finished (event record + stream wait on the device; the host does not wait).  Both contexts on the same device. */
+CTR_API int ctr_stage_upload(ctr_ctx* ctx, const void* host, uint64_t dst_offset, uint64_t bytes, uint64_t total_bytes,
+                             void** device_base);
+CTR_API int ctr_wait_for(ctr_ctx* ctx, ctr_ctx* other);
+
 /* ---- 3D marching tetrahedra ---------------------------------------------------------------------
  * Replaces, for an array-backed field, the reference's
  *   grid_field.py:64-84     FunctionGrid.find_contour_crossing_grid_segments  (n_crossings, fmin, fmax)

@@ -252,6 +252,25 @@ def test_pipelined_host_extraction_equals_single_run(engine):
                 assert np.array_equal(out[name], ref[name]), (name, nslabs, rep)
 
 
+def test_pipelined_host_extraction_with_empty_slabs_on_a_new_context(engine):
+    """The surface lies in the last planes only: the first slabs of a context's first call produce nothing (no output
+    buffers exist yet), later calls run overlapped; the halo planes are uploaded once."""
+    from contourist_b200 import engine as E
+    f = np.full((48, 20, 40), -1.0, dtype=np.float32)
+    f[40:] = np.linspace(-1, 1, 8 * 20 * 40, dtype=np.float32).reshape(8, 20, 40)
+    flags = E.WANT_KEYS | E.WANT_NORMALS
+    c = engine.mt3d_run(f, 0.25, flags=flags)
+    ref = engine.mt3d_fetch()
+    assert c.n_tris > 0
+    fresh = E.Engine(0)
+    for rep in range(2):
+        tot, out = fresh.mt3d_extract_host(f, 0.25, flags=flags, nslabs=12)
+        assert tot["slabs"][0] == (0, 0) and tot["n_verts"] == c.n_verts and tot["n_tris"] == c.n_tris
+        for name in ("keys", "lowmin", "verts", "normals", "tris"):
+            assert np.array_equal(out[name], ref[name]), (name, rep)
+    fresh.close()
+
+
 def test_full_size_properties_512(engine):
     """BASELINE config 3 size: 512^3 fp32 CT-like volume.  Size-independent properties: the mesh is a closed
     2-manifold away from the domain boundary (every interior edge shared by exactly 2 triangles with opposite
