@@ -92,6 +92,7 @@ template <typename T, int UNROLL, bool MINMAX>
 __global__ void __launch_bounds__(256) k_bitplane_generic(const T* __restrict__ f, unsigned nrows, int n2, int W,
                                                           T thr, T near_lo, T near_hi, uint32_t* __restrict__ bits,
                                                           uint32_t* __restrict__ nbits, RowGeom rg, MinMaxKeys* ctr) {
+  ctr_pdl_enter();
   const unsigned lane = lane_id();
   const unsigned nwords = nrows * (unsigned)W;
   const unsigned warps = gridDim.x * (blockDim.x >> 5);
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(256) k_bitplane_vec(const T* __restrict__ f, s
   typedef typename Vec16<T>::type V;
   constexpr int VEC = Vec16<T>::VEC;
   constexpr int GROUP = 32 / VEC;               // lanes per output word
+  ctr_pdl_enter();
   const unsigned lane = lane_id();
   const size_t nchunks = (nsamp + 32 * VEC - 1) / (32 * VEC);
   const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
@@ -317,6 +319,10 @@ __global__ void __launch_bounds__((TMA_CONSUMER_WARPS + 1) * 32) k_bitplane_tma(
   T mn = INFINITY, mx = -INFINITY;
   const bool anynear = false;
   unsigned it = 0;
+  // The producer above starts fetching at once: the field is complete before the kernel in front of this one passed its
+  // own wait (common.cuh, rule 2).  The consumers wait here, in front of their first write: the flags they set are
+  // zeroed by that kernel, and the bit planes may still be read by the previous run's last kernel.
+  ctr_pdl_enter();
   for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
     const int s = it % TMA_STAGES;
     const unsigned ph = (it / TMA_STAGES) & 1u;
@@ -449,7 +455,8 @@ int launch_bitplane(ctr_ctx* ctx, const T* dfield, unsigned nrows, int n2, int W
     const size_t nbytes = nsamp * sizeof(T);
     const size_t nchunks = (nbytes + TMA_CHUNK - 1) / TMA_CHUNK;
     int blocks = (int)std::min<size_t>(nchunks, (size_t)ctx->sm_count * ctas_per_sm);
-    k_bitplane_tma<T, MINMAX><<<blocks, (TMA_CONSUMER_WARPS + 1) * 32, smem, st>>>(dfield, nbytes, thr, nlo, nhi, bits, nbits, rg, dctr, TMA_STAGES, l2_hint);
+    ctr_launch_dep(k_bitplane_tma<T, MINMAX>, blocks, (TMA_CONSUMER_WARPS + 1) * 32, smem, st, dfield, nbytes, thr, nlo, nhi, bits, nbits, rg,
+                   dctr, (int)TMA_STAGES, (int)l2_hint);
   } else if (kind == BP_VEC) {
     const size_t nchunks = (nsamp + 32 * Vec16<T>::VEC - 1) / (32 * Vec16<T>::VEC);
     size_t need = (nchunks + 8 * 4 - 1) / (8 * 4);

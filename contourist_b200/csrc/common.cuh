@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 
 #include "../../include/contourist_b200.h"
 
@@ -124,6 +125,37 @@ static inline void ctr_stage_mark(ctr_ctx* ctx, int idx) {
 #ifdef __CUDACC__
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// Programmatic dependent launch.  The kernels of one extraction run back to back on one stream, several of them for a
+// few microseconds only; launched with ctr_launch_dep a kernel's blocks may become resident (and run their prologue:
+// shared-memory tables, mbarrier set-up) while the previous kernel drains.  Rules that keep this equal to plain stream
+// order: (1) ctr_pdl_wait() -- returns when every earlier kernel has completed and its writes are visible -- precedes
+// the first access to anything an earlier kernel of the stream writes or reads; (2) ctr_pdl_trigger() comes after the
+// wait, so a kernel that has started implies that everything in front of its predecessor is complete.
+#ifndef CTR_PDL
+#define CTR_PDL 1
+#endif
+__device__ __forceinline__ void ctr_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void ctr_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void ctr_pdl_enter() {
+  ctr_pdl_wait();
+  ctr_pdl_trigger();
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ctr_launch_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = CTR_PDL;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 __device__ __forceinline__ unsigned long long warp_incl_scan_u64(unsigned long long v) {
 #pragma unroll

@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(CS_THREADS) k_count_a(Grid<T> g, unsigned word
   __shared__ unsigned s_cnt[CS_ITEMS][CS_THREADS / 32];
   __shared__ unsigned s_base;
   __shared__ unsigned short s_list[CS_TILE];
+  ctr_pdl_enter();
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
   const unsigned tile0 = blockIdx.x * CS_TILE;
@@ -581,6 +582,7 @@ __global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin
     sh.spread[threadIdx.x] = sp;
   }
   __syncthreads();
+  ctr_pdl_enter();                                     // the tables above come from constants: filled while k_count_a drains
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
   const unsigned emit_end = (unsigned)g.i_hi * plane_words;
@@ -739,6 +741,7 @@ __global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin
 // a quarter of that kernel's stall samples.)
 __global__ void __launch_bounds__(1024) k_tile_scan3(unsigned long long* __restrict__ tile_vt, int ntiles, Counters* ctr) {
   __shared__ unsigned long long s_warp[32], s_tot, s_v, s_t;
+  ctr_pdl_enter();
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   unsigned long long carry = 0, my_v = 0, my_t = 0;
   if (threadIdx.x == 0) s_v = s_t = 0ull;
@@ -797,6 +800,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan(Grid<T> g, unsigned wo
                                                          const uint32_t* __restrict__ recc, const uint2* __restrict__ tile_chunk,
                                                          unsigned cap_w, const unsigned long long* __restrict__ tile_vt,
                                                          uint4* __restrict__ wrec, Counters* ctr) {
+  ctr_pdl_enter();
   const int tile = (int)(blockIdx.x * SCAN_WARPS + (threadIdx.x >> 5));
   if (tile >= ntiles) return;
   const unsigned lane = lane_id();
@@ -895,6 +899,7 @@ __global__ void CTR_EV_BOUNDS k_emit_verts(Grid<T> g, const unsigned long long* 
                                                     const Counters* __restrict__ ctr, unsigned cap_own, unsigned cap_v, Xform xf,
                                                     G* __restrict__ verts, G* __restrict__ normals,
                                                     unsigned long long* __restrict__ keys, uint8_t* __restrict__ lowmin) {
+  ctr_pdl_enter();
   // the list length comes from the device counters: the launch may precede the host's read of the counts
   const unsigned n_own = min(ctr->n_own, cap_own);
   const unsigned lane = lane_id();
@@ -1038,6 +1043,7 @@ __global__ void CTR_ET_BOUNDS k_emit_tris(Grid<T> g, const unsigned long long* _
                                                           unsigned cap_cell, unsigned cap_t,
                                                           const uint4* __restrict__ wrec, const uint32_t* __restrict__ vox_tab,
                                                           int* __restrict__ tris) {
+  ctr_pdl_enter();
   const unsigned n_cells = min(ctr->n_cell, cap_cell);
   // per warp: the 19 edge ids of its 32 voxels (row stride 33: a round of the write-out below reads arbitrary
   // (edge, voxel) pairs, and with stride 32 all the edges of one voxel share a bank), and the voxel of each of the
@@ -1199,6 +1205,7 @@ __global__ void k_offset_ids(int* __restrict__ tris, size_t n, int base) {
 
 // ctr_mt3d_publish_counts: {n_verts, n_tris} of the run for a collective that reads them on the device
 __global__ void k_publish3(const Counters* __restrict__ ctr, int sharded, long long* __restrict__ out) {
+  ctr_pdl_enter();
   out[0] = (long long)(sharded ? ctr->v_emit : ctr->tot_v);
   out[1] = (long long)ctr->tot_t;
 }
@@ -1206,6 +1213,7 @@ __global__ void k_publish3(const Counters* __restrict__ ctr, int sharded, long l
 // one launch instead of four memsets / copies in front of every run
 __global__ void k_reset3(Counters* ctr, uint4* rowflag16, size_t n16, uint4* wordflag16, uint4* exactflag16, size_t nw16,
                          unsigned long long* tile_state, size_t ntile) {
+  ctr_pdl_enter();
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)gridDim.x * blockDim.x;
   if (t == 0) {
     Counters c;
@@ -1398,8 +1406,8 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
     const unsigned cap_w = (unsigned)std::min<size_t>(ctx->spec_w, 0x7fffffffu);
 
     if (!(phase == 2 && attempt == 0)) {                 // phase 2: attempt 0 was enqueued by phase 1
-    k_reset3<<<64, 256, 0, st>>>(dctr, (uint4*)ctx->aux[4].p, (size_t)(nrows + 15) / 16, (uint4*)ctx->aux[32].p,
-                                 (uint4*)ctx->aux[35].p, (size_t)(nrows + 3) / 4, st_vt, (size_t)ntiles);
+    ctr_launch_dep(k_reset3, 64, 256, 0, st, dctr, (uint4*)ctx->aux[4].p, (size_t)(nrows + 15) / 16, (uint4*)ctx->aux[32].p,
+                   (uint4*)ctx->aux[35].p, (size_t)(nrows + 3) / 4, st_vt, (size_t)ntiles);
     ctx->launches++;
     CTR_DBG(ctx, "k_reset3");
     if (p->flags & CTR_WANT_MINMAX)
@@ -1412,28 +1420,22 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
     CTR_DBG(ctx, "k_bitplane");
     ctr_stage_mark(ctx, 2);
     if (ntiles > 0) {
-      k_count_a<T><<<ntiles, CS_THREADS, 0, st>>>(g, word0, nscan, (uint32_t*)ctx->wlist.p, (uint2*)ctx->aux[34].p, cap_w, dctr);
+      ctr_launch_dep(k_count_a<T>, ntiles, CS_THREADS, 0, st, g, word0, nscan, (uint32_t*)ctx->wlist.p, (uint2*)ctx->aux[34].p, cap_w, dctr);
       CTR_DBG(ctx, "k_count_a");
       // the grid covers the expected list length (last run's, with head-room); blocks past the real length only take a ticket
       const unsigned wb = (unsigned)((std::min<size_t>(cap_w, ctx->last_w + ctx->last_w / 8 + 4096) + CB_THREADS - 1) / CB_THREADS);
-      k_count_b<T><<<wb, CB_THREADS, 0, st>>>(g, word0, (const uint32_t*)ctx->wlist.p, cap_w, (uint32_t*)ctx->aux[33].p,
-                                              (uint4*)ctx->wdir.p, (unsigned long long*)b_own_id.p,
-                                              (unsigned long long*)b_own_voff.p, (unsigned long long*)b_cell_id.p,
-                                              (uint32_t*)b_cell_toff.p, cap_own, cap_cell, st_vt, dctr, ntiles);
-      k_tile_scan3<<<1, 1024, 0, st>>>(st_vt, ntiles, dctr);
+      ctr_launch_dep(k_count_b<T>, wb, CB_THREADS, 0, st, g, word0, (const uint32_t*)ctx->wlist.p, cap_w, (uint32_t*)ctx->aux[33].p,
+                     (uint4*)ctx->wdir.p, (unsigned long long*)b_own_id.p, (unsigned long long*)b_own_voff.p,
+                     (unsigned long long*)b_cell_id.p, (uint32_t*)b_cell_toff.p, cap_own, cap_cell, st_vt, dctr, ntiles);
+      ctr_launch_dep(k_tile_scan3, 1, 1024, 0, st, st_vt, ntiles, dctr);
       ctx->launches += 3;
       ctx->cover_w = (size_t)wb * CB_THREADS;
       CTR_DBG(ctx, "k_count_b");
-      k_scan<T><<<(ntiles + SCAN_WARPS - 1) / SCAN_WARPS, SCAN_WARPS * 32, 0, st>>>(
-          g, word0, ntiles, (const uint32_t*)ctx->wlist.p, (const uint32_t*)ctx->aux[33].p, (const uint2*)ctx->aux[34].p, cap_w,
-          st_vt, (uint4*)ctx->wdir.p, dctr);
+      ctr_launch_dep(k_scan<T>, (ntiles + SCAN_WARPS - 1) / SCAN_WARPS, SCAN_WARPS * 32, 0, st,
+                     g, word0, ntiles, (const uint32_t*)ctx->wlist.p, (const uint32_t*)ctx->aux[33].p, (const uint2*)ctx->aux[34].p, cap_w,
+                     st_vt, (uint4*)ctx->wdir.p, dctr);
       ctx->launches++;
       CTR_DBG(ctx, "k_scan");
-    }
-    CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-    if (ctx->publish3) {
-      k_publish3<<<1, 1, 0, st>>>(dctr, g.i_hiv > g.i_hi ? 1 : 0, ctx->publish3);
-      ctx->launches++;
     }
     ctr_stage_mark(ctx, 3);
     if (geom && ntiles > 0) {
@@ -1448,18 +1450,18 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
       const unsigned long long* ovo = (const unsigned long long*)b_own_voff.p;
       const uint4* dwr = (const uint4*)ctx->wdir.p;
       if (f64)
-        k_emit_verts<T, double><<<vb, 256, 0, st>>>(g, oid, ovo, dwr, dctr, bound_own, cap_v, xf, (double*)ctx->verts.p,
-                                                    want_n ? (double*)ctx->normals.p : nullptr, dkeys, dlow);
+        ctr_launch_dep(k_emit_verts<T, double>, vb, 256, 0, st, g, oid, ovo, dwr, dctr, bound_own, cap_v, xf, (double*)ctx->verts.p,
+                       want_n ? (double*)ctx->normals.p : (double*)nullptr, dkeys, dlow);
       else
-        k_emit_verts<T, float><<<vb, 256, 0, st>>>(g, oid, ovo, dwr, dctr, bound_own, cap_v, xf, (float*)ctx->verts.p,
-                                                   want_n ? (float*)ctx->normals.p : nullptr, dkeys, dlow);
+        ctr_launch_dep(k_emit_verts<T, float>, vb, 256, 0, st, g, oid, ovo, dwr, dctr, bound_own, cap_v, xf, (float*)ctx->verts.p,
+                       want_n ? (float*)ctx->normals.p : (float*)nullptr, dkeys, dlow);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_verts");
       ctr_stage_mark(ctx, 4);
       const unsigned tb = (unsigned)((std::min<size_t>(cap_cell, ctx->last_cell + ctx->last_cell / 8 + 4096) + ET_THREADS - 1) / ET_THREADS);
-      k_emit_tris<T><<<tb, ET_THREADS, 0, st>>>(g, (const unsigned long long*)b_cell_id.p, (const uint32_t*)b_cell_toff.p, dctr,
-                                                std::min(tb * (unsigned)ET_THREADS, cap_cell), cap_t, (const uint4*)ctx->wdir.p,
-                                                (const uint32_t*)ctx->vox_tab.p, (int*)ctx->tris.p);
+      ctr_launch_dep(k_emit_tris<T>, tb, ET_THREADS, 0, st, g, (const unsigned long long*)b_cell_id.p, (const uint32_t*)b_cell_toff.p, dctr,
+                     std::min(tb * (unsigned)ET_THREADS, cap_cell), cap_t, (const uint4*)ctx->wdir.p,
+                     (const uint32_t*)ctx->vox_tab.p, (int*)ctx->tris.p);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_tris");
       ctr_stage_mark(ctx, 5);
@@ -1471,6 +1473,13 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
       ctr_stage_mark(ctx, 5);
       ctx->cover_own = ctx->cover_cell = (size_t)-1;
     }
+    // the counts travel behind the last kernel (nothing sits between the kernels of a run: each may start under the tail
+    // of the one before, ctr_launch_dep); the host reads them after its single wait anyway
+    if (ctx->publish3) {
+      ctr_launch_dep(k_publish3, 1, 1, 0, st, (const Counters*)dctr, g.i_hiv > g.i_hi ? 1 : 0, ctx->publish3);
+      ctx->launches++;
+    }
+    CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     }
     if (phase == 1) {
       CTR_CUDA(ctx, cudaGetLastError());
