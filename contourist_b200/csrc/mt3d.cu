@@ -51,9 +51,12 @@ struct Counters {                    // device counter block (mirrored to pinned
   unsigned long long total_vt;       // packed totals over the scanned range: T << 31 | V
   unsigned long long v_emit;         // vertex count at the start of plane i_hi (vertices this call emits)
   unsigned int ticket;
-  unsigned int n_word;               // interesting words listed by k_count_a
-  unsigned int n_own, n_cell;        // slots handed out in the owner / voxel work lists (their lengths at the end)
   unsigned long long tot_v, tot_t;   // the same totals, accumulated unpacked (a vertex total >= 2^31 would carry into T above)
+  // every tile of k_count_a adds to each of these three: one 128-byte line each, so that the atomics of different
+  // counters go to different L2 slices instead of queueing behind one address line
+  alignas(128) unsigned int n_word;  // interesting words listed by k_count_a
+  alignas(128) unsigned int n_own;   // slots handed out in the owner / voxel work lists (their lengths at the end)
+  alignas(128) unsigned int n_cell;
 };
 
 
@@ -376,8 +379,14 @@ __device__ __forceinline__ unsigned dir_base(uint2 dp, int q) {   // q = d-1 in 
 
 // Quick test of 4 consecutive words of one row (W % 4 == 0, gw % 4 == 0): does any of their 7 x 32 owned edges cross?
 // 128-bit loads of the four rows the words touch; returns a 4-bit mask.
+// The quick test of stage 2a for words gw .. gw+3 of one row (gw a multiple of 4, W a multiple of 4): bit q of the
+// result = word gw+q owns a crossing edge.  For such a word byte q of own4 / cell4 is the number of its owner points
+// (points with a crossing owned edge, planes below i_hi) and of its emitting voxels (corner bits not all equal) by the
+// plain bit logic -- the slots the word needs in the two work lists.  A word under a near flag gets none here: its
+// exact counts may be smaller, k_count_b takes its slots itself.
 template <typename T>
-__device__ __forceinline__ unsigned words4_interesting(const Grid<T>& g, unsigned gw, unsigned plane_words) {
+__device__ __forceinline__ unsigned words4_interesting(const Grid<T>& g, unsigned gw, unsigned plane_words, unsigned& own4,
+                                                       unsigned& cell4) {
   const unsigned row = g.divW.div(gw);
   const unsigned w = gw - row * (unsigned)g.W;
   const unsigned i = g.divN1.div(row);
@@ -407,6 +416,7 @@ __device__ __forceinline__ unsigned words4_interesting(const Grid<T>& g, unsigne
   }
   const uint32_t mj = hj ? 0xffffffffu : 0u, mi = hi ? 0xffffffffu : 0u, mij = mi & mj;
   unsigned out = 0;
+  uint32_t any[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int rem = g.n2 - (int)(w + q) * 32;
@@ -415,9 +425,40 @@ __device__ __forceinline__ unsigned words4_interesting(const Grid<T>& g, unsigne
     const uint32_t t = ((A ^ b[q]) & mj) | ((A ^ c[q]) & mi) | ((A ^ d[q]) & mij);
     const uint32_t u = (A ^ __funnelshift_r(a[q], a[q + 1], 1)) | ((A ^ __funnelshift_r(b[q], b[q + 1], 1)) & mj) |
                        ((A ^ __funnelshift_r(c[q], c[q + 1], 1)) & mi) | ((A ^ __funnelshift_r(d[q], d[q + 1], 1)) & mij);
-    if (((t & kpt) | (u & kp1)) != 0) out |= 1u << q;
+    any[q] = (t & kpt) | (u & kp1);                     // OR of the seven crossing words (cross_words)
+    if (any[q] != 0) out |= 1u << q;
+  }
+  own4 = cell4 = 0;
+  if (out && (int)i < g.i_hi) {                         // planes from i_hi on are scanned for their vertex ids only
+    const uint32_t nf = g.wordflag[row];
+    if (nf) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if ((nf >> ((w + q) >> g.wshift)) & 1u) any[q] = 0u;
+    }
+    own4 = (unsigned)__popc(any[0]) | ((unsigned)__popc(any[1]) << 8) | ((unsigned)__popc(any[2]) << 16) | ((unsigned)__popc(any[3]) << 24);
+    // voxels: the same points, except the row's last sample (k + 1 == n2), which can only sit in the row's last word
+    if (hi && hj) cell4 = own4 - (hw ? 0u : (unsigned)__popc(any[3] & ~low_mask(g.n2 - (int)(w + 3) * 32 - 1)) << 24);
   }
   return out;
+}
+
+// the same for one word of any grid (rows whose word count is no multiple of 4)
+template <typename T>
+__device__ __forceinline__ bool word_interesting(const Grid<T>& g, unsigned gw, unsigned& own, unsigned& cell) {
+  int i, j, w;
+  g.word_coords(gw, i, j, w);
+  Planes pl;
+  load_planes(g, g.bits, i, j, w, pl);
+  uint32_t x[7];
+  cross_words(pl, x);
+  const uint32_t any = x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6];
+  own = cell = 0;
+  if (any && i < g.i_hi && !g.near_word((unsigned)i * (unsigned)g.n1 + (unsigned)j, (unsigned)w)) {
+    own = (unsigned)__popc(any);
+    if (pl.has_i1 && pl.has_j1) cell = (unsigned)__popc(any & pl.kp1);
+  }
+  return any != 0;
 }
 
 // per-word record of the scan: vertices | triangles << 8
@@ -442,87 +483,75 @@ __device__ __forceinline__ unsigned long long rec_vt(uint32_t r) {
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(CS_THREADS) k_count_a(Grid<T> g, unsigned word0, unsigned nwords_scan,
-                                                     uint32_t* __restrict__ wlist, uint2* __restrict__ tile_chunk,
-                                                     unsigned cap_w, Counters* ctr) {
-  // the tile's interesting words in ascending word order: counts per (round, warp), prefix over those 4 x 8 counts
-  __shared__ unsigned s_cnt[CS_ITEMS][CS_THREADS / 32];
-  __shared__ unsigned s_base;
+                                                     uint32_t* __restrict__ wlist, uint2* __restrict__ wslot,
+                                                     uint2* __restrict__ tile_chunk, unsigned cap_w, Counters* ctr) {
+  // the tile's interesting words in ascending word order, each with the first slot of its owner points and of its
+  // emitting voxels in the work lists: one block prefix over (words, owner points, voxels) and three atomics per tile
+  __shared__ unsigned long long s_warp[CS_THREADS / 32];
+  __shared__ unsigned s_base[3];
   __shared__ unsigned short s_list[CS_TILE];
+  __shared__ unsigned s_slot[CS_TILE];                 // tile-relative (owner slot | voxel slot << 16) of a listed word
   ctr_pdl_enter();
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
-  const unsigned tile0 = blockIdx.x * CS_TILE;
-  const bool vec = (g.W & 3) == 0;
-  unsigned m4 = 0, mq[CS_ITEMS] = {0, 0, 0, 0};
-  unsigned excl = 0;
-  if (vec) {
-    const unsigned rel = tile0 + threadIdx.x * CS_ITEMS;
-    if (rel < nwords_scan) m4 = words4_interesting(g, word0 + rel, plane_words);
-    const unsigned cnt = __popc(m4);
-    const unsigned inc = warp_incl_scan_u32(cnt);
-    excl = inc - cnt;
-    if (lane == 31) s_cnt[0][warp] = inc;
+  const unsigned rel = blockIdx.x * CS_TILE + threadIdx.x * CS_ITEMS;      // this thread's four consecutive words
+  unsigned m4 = 0, own4 = 0, cell4 = 0;
+  if ((g.W & 3) == 0) {
+    if (rel < nwords_scan) m4 = words4_interesting(g, word0 + rel, plane_words, own4, cell4);
   } else {
 #pragma unroll
     for (int q = 0; q < CS_ITEMS; ++q) {
-      const unsigned rel = tile0 + (unsigned)q * CS_THREADS + threadIdx.x;
-      bool interesting = false;
-      if (rel < nwords_scan) {
-        int i, j, w;
-        g.word_coords(word0 + rel, i, j, w);
-        Planes pl;
-        load_planes(g, g.bits, i, j, w, pl);
-        uint32_t x[7];
-        cross_words(pl, x);
-        interesting = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6]) != 0;
-      }
-      mq[q] = __ballot_sync(0xffffffffu, interesting);
-      if (lane == 0) s_cnt[q][warp] = (unsigned)__popc(mq[q]);
+      unsigned o = 0, c = 0;
+      if (rel + q < nwords_scan && word_interesting(g, word0 + rel + q, o, c)) m4 |= 1u << q;
+      own4 |= o << (8 * q);
+      cell4 |= c << (8 * q);
     }
   }
+  // byte sums: a word has at most 32 owner points / 31 voxels, four words stay below 256
+  const unsigned own_n = (own4 * 0x01010101u) >> 24, cell_n = (cell4 * 0x01010101u) >> 24;
+  const unsigned long long mine = (unsigned long long)__popc(m4) | ((unsigned long long)own_n << 16) | ((unsigned long long)cell_n << 32);
+  const unsigned long long inc = warp_incl_scan_u64(mine);
+  if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
-  unsigned nint = 0, before[CS_ITEMS] = {0, 0, 0, 0};
-  if (vec) {
+  unsigned long long before = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < CS_THREADS / 32; ++w) {
-      const unsigned c = s_cnt[0][w];
-      if (w < (int)warp) before[0] += c;
-      nint += c;
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < CS_ITEMS; ++q)
-#pragma unroll
-      for (int w = 0; w < CS_THREADS / 32; ++w) {
-        const unsigned c = s_cnt[q][w];
-#pragma unroll
-        for (int r = 0; r < CS_ITEMS; ++r)
-          if (q < r || (q == r && w < (int)warp)) before[r] += c;
-        nint += c;
-      }
+  for (int w = 0; w < CS_THREADS / 32; ++w) {
+    const unsigned long long c = s_warp[w];
+    if (w < (int)warp) before += c;
+    total += c;
   }
-  if (threadIdx.x == 0) {
+  const unsigned nint = (unsigned)total & 0xffffu, n_own = (unsigned)(total >> 16) & 0xffffu, n_cell = (unsigned)(total >> 32);
+  if (threadIdx.x == 0) {                              // three warps, one atomic each: the round trips overlap
     const unsigned b0 = nint ? atomicAdd(&ctr->n_word, nint) : 0u;
-    s_base = b0;
+    s_base[0] = b0;
     tile_chunk[blockIdx.x] = make_uint2(b0, nint);
+  } else if (threadIdx.x == 32) {
+    s_base[1] = n_own ? atomicAdd(&ctr->n_own, n_own) : 0u;
+  } else if (threadIdx.x == 64) {
+    s_base[2] = n_cell ? atomicAdd(&ctr->n_cell, n_cell) : 0u;
   }
   if (!nint) return;
-  if (vec) {
-    unsigned base = before[0] + excl;
-    const unsigned wl0 = threadIdx.x * CS_ITEMS;
+  {
+    const unsigned long long ex = before + inc - mine;
+    unsigned base = (unsigned)ex & 0xffffu, orun = (unsigned)(ex >> 16) & 0xffffu, crun = (unsigned)(ex >> 32);
 #pragma unroll
     for (int q = 0; q < CS_ITEMS; ++q)
-      if ((m4 >> q) & 1u) s_list[base++] = (unsigned short)(wl0 + q);
-  } else {
-#pragma unroll
-    for (int q = 0; q < CS_ITEMS; ++q)
-      if ((mq[q] >> lane) & 1u)
-        s_list[before[q] + __popc(mq[q] & ((1u << lane) - 1u))] = (unsigned short)((unsigned)q * CS_THREADS + threadIdx.x);
+      if ((m4 >> q) & 1u) {
+        s_list[base] = (unsigned short)(threadIdx.x * CS_ITEMS + q);
+        s_slot[base] = orun | (crun << 16);
+        ++base;
+        orun += (own4 >> (8 * q)) & 255u;
+        crun += (cell4 >> (8 * q)) & 255u;
+      }
   }
   __syncthreads();
-  const unsigned b0 = s_base;
+  const unsigned b0 = s_base[0], o0 = s_base[1], c0 = s_base[2];
   for (unsigned q = threadIdx.x; q < nint; q += CS_THREADS)
-    if (b0 + q < cap_w) wlist[b0 + q] = word0 + tile0 + s_list[q];
+    if (b0 + q < cap_w) {
+      wlist[b0 + q] = word0 + blockIdx.x * CS_TILE + s_list[q];
+      const unsigned sl = s_slot[q];
+      wslot[b0 + q] = make_uint2(o0 + (sl & 0xffffu), c0 + (sl >> 16));
+    }
 }
 
 // The word flag of stage 1 is dilated; every exact path of stage 2 starts from the near bits of the eight words a word
@@ -551,20 +580,22 @@ __device__ __noinline__ void flag_exact_words(const Grid<T> g, const Planes pl, 
       if (i - di >= 0 && j - dj >= 0) atomicOr(&g.exactflag[(size_t)(i - di) * g.n1 + (j - dj)], m);
 }
 
-constexpr int CB_THREADS = 256;                     // (128: 160 us for stage 2 instead of 153)
+#ifndef CTR_CB_THREADS
+#define CTR_CB_THREADS 128          // without the slot barrier the block size is free: 128 x 5 blocks: stage 2 110.7 -> 106.5 us
+#endif
+constexpr int CB_THREADS = CTR_CB_THREADS;
 
 struct CountBShared {
   unsigned long long spread[128];     // 7-bit direction mask -> 7 x 5-bit fields with a one where the mask has a bit
   unsigned short vox[256];
-  unsigned warp_items[CB_THREADS / 32];
-  unsigned base_own, base_cell;
 };
 
 #ifndef CTR_CB_MINB
-#define CTR_CB_MINB 3          // 80 registers: stage 2 131 us (4 -> 64 registers with spills: 135; 5: 143; 6: 156)
+#define CTR_CB_MINB 5          // 96 registers (128 threads x 6 -> 80: 108.3 us; x 4 -> 128: 109.2; 64 threads x 10: 107.8)
 #endif
 template <typename T>
 __global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin, unsigned word0, const uint32_t* __restrict__ wlist,
+                                                        const uint2* __restrict__ wslot,
                                                         unsigned cap_w, uint32_t* __restrict__ recc, uint4* __restrict__ wrec,
                                                         unsigned long long* __restrict__ own_id,
                                                         unsigned long long* __restrict__ own_rk,
@@ -575,15 +606,15 @@ __global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin
   Grid<T> g = gin;
   g.any_near = 0;
   for (unsigned q = threadIdx.x; q < 256u; q += CB_THREADS) sh.vox[q] = c_vox[q];
-  if (threadIdx.x < 128) {
+  for (unsigned q = threadIdx.x; q < 128u; q += CB_THREADS) {
     unsigned long long sp = 0;
 #pragma unroll
-    for (int d = 0; d < 7; ++d) sp |= (unsigned long long)((threadIdx.x >> d) & 1u) << (5 * d);
-    sh.spread[threadIdx.x] = sp;
+    for (int d = 0; d < 7; ++d) sp |= (unsigned long long)((q >> d) & 1u) << (5 * d);
+    sh.spread[q] = sp;
   }
   __syncthreads();
   ctr_pdl_enter();                                     // the tables above come from constants: filled while k_count_a drains
-  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const unsigned lane = lane_id();
   const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
   const unsigned emit_end = (unsigned)g.i_hi * plane_words;
   const unsigned nint = min(ctr->n_word, cap_w);
@@ -595,10 +626,14 @@ __global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin
   Planes pl;
   uint32_t x[7] = {0, 0, 0, 0, 0, 0, 0};
   uint32_t any = 0, em = 0;
+  uint2 slot = make_uint2(0u, 0u);
+  bool flagged = false;
   if (have) {
     gw = wlist[idx];
+    slot = wslot[idx];
     g.word_coords(gw, i, j, w);
     g.any_near = g.near_word((unsigned)i * (unsigned)g.n1 + (unsigned)j, (unsigned)w);
+    flagged = g.any_near != 0;
     load_planes(g, g.bits, i, j, w, pl);
     if (g.any_near) g.any_near = near_bits_around(g, i, j, w, pl.kpt);
     owner_used(g, pl, i, j, w, x);
@@ -654,23 +689,15 @@ __global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin
     if (gw >= emit_end) any = 0u;
     ncells += __popc(em);
   }
-  const unsigned items = (unsigned)__popc(any) | ((unsigned)__popc(em) << 16);
-  const unsigned inc = warp_incl_scan_u32(items);
-  if (lane == 31) sh.warp_items[warp] = inc;
-  __syncthreads();
-  unsigned woff = 0, tot = 0;
-#pragma unroll
-  for (int q = 0; q < CB_THREADS / 32; ++q) {
-    if (q < (int)warp) woff += sh.warp_items[q];
-    tot += sh.warp_items[q];
+  // The slots of the word's owner points and voxels in the work lists come from k_count_a (prefix over the tile's
+  // words: no block scan and no barrier here; with them a fifth of this kernel's stall samples sat at the barrier in
+  // front of the slot allocation).  A word under a near flag has none -- its exact counts may be smaller than the
+  // plain ones -- and takes them from the counters itself (rare).
+  unsigned orun = slot.x, crun = slot.y;
+  if (flagged) {
+    orun = any ? atomicAdd(&ctr->n_own, (unsigned)__popc(any)) : 0u;
+    crun = em ? atomicAdd(&ctr->n_cell, (unsigned)__popc(em)) : 0u;
   }
-  if (threadIdx.x == 0) {
-    sh.base_own = (tot & 0xffffu) ? atomicAdd(&ctr->n_own, tot & 0xffffu) : 0u;
-    sh.base_cell = (tot >> 16) ? atomicAdd(&ctr->n_cell, tot >> 16) : 0u;
-  }
-  __syncthreads();
-  const unsigned excl = woff + inc - items;
-  unsigned orun = sh.base_own + (excl & 0xffffu), crun = sh.base_cell + (excl >> 16);
   if (any) {
     uint32_t mo = any;
     // the ranks of an owner's edges within their directions = how many used edges of each direction came before it in
@@ -791,43 +818,101 @@ __global__ void __launch_bounds__(1024) k_tile_scan3(unsigned long long* __restr
 }
 
 // Stage 2b: offsets.  One warp per tile walks the tile's chunk of the interesting-word list (ascending words, k_count_a)
-// from the tile's exclusive prefix (k_tile_scan3): vbase[word] (first vertex id of the word), tbase[word] (first
-// triangle of the word) -- for interesting words only; nothing reads the others.  (A dense scan over all words read
-// and wrote 48 MB to serve the 10 % that matter.)
+// from the tile's exclusive prefix: vbase[word] (first vertex id of the word), tbase[word] (first triangle of the word)
+// -- for interesting words only; nothing reads the others.  (A dense scan over all words read and wrote 48 MB to serve
+// the 10 % that matter.)
+// The tile prefix: up to SCAN_FUSE_TILES tiles every block sums the aggregates of the tiles in front of its own (a few
+// KB from L2, all loads independent) instead of waiting for a one-block scan kernel in front of it (k_tile_scan3:
+// 7 us of pure latency in a 0.36 ms step); that is quadratic in the tile count, so larger volumes keep the scan kernel.
 constexpr int SCAN_WARPS = 8;
+constexpr int SCAN_FUSE_TILES = 8192;              // 512^3 has 4096
 template <typename T>
 __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan(Grid<T> g, unsigned word0, int ntiles, const uint32_t* __restrict__ wlist,
                                                          const uint32_t* __restrict__ recc, const uint2* __restrict__ tile_chunk,
                                                          unsigned cap_w, const unsigned long long* __restrict__ tile_vt,
-                                                         uint4* __restrict__ wrec, Counters* ctr) {
+                                                         uint4* __restrict__ wrec, Counters* ctr, int fused) {
+  __shared__ unsigned long long s_acc[SCAN_WARPS], s_av[SCAN_WARPS];
   ctr_pdl_enter();
-  const int tile = (int)(blockIdx.x * SCAN_WARPS + (threadIdx.x >> 5));
-  if (tile >= ntiles) return;
-  const unsigned lane = lane_id();
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const int first = (int)(blockIdx.x * SCAN_WARPS);
+  const int tile = first + (int)warp;
+  unsigned long long run = 0;
+  if (fused) {
+    // packed (vertices | triangles << 31) and, for the overflow check, the vertices alone:
+    // the tiles in front of the block, strided over all its threads ...
+    unsigned long long acc = 0, av = 0;
+    for (int q = (int)threadIdx.x; q < first; q += SCAN_WARPS * 32) {
+      const unsigned long long a = tile_vt[q];
+      acc += a;
+      av += a & 0x7fffffffull;
+    }
+    // ... and the block's own tiles in front of this warp's
+    unsigned long long own_acc = (lane < warp && first + (int)lane < ntiles) ? tile_vt[first + (int)lane] : 0ull;
+    unsigned long long own_av = own_acc & 0x7fffffffull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      av += __shfl_xor_sync(0xffffffffu, av, o);
+      own_acc += __shfl_xor_sync(0xffffffffu, own_acc, o);
+      own_av += __shfl_xor_sync(0xffffffffu, own_av, o);
+    }
+    if (lane == 0) {
+      s_acc[warp] = acc;
+      s_av[warp] = av;
+    }
+    __syncthreads();
+    unsigned long long base = 0, base_v = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_WARPS; ++w) {
+      base += s_acc[w];
+      base_v += s_av[w];
+    }
+    run = base + own_acc;
+    if (tile == ntiles - 1 && lane == 0) {             // totals of the run: everything in front of the last tile + the last tile
+      const unsigned long long a = tile_vt[tile];
+      const unsigned long long tot = run + a, tv = base_v + own_av + (a & 0x7fffffffull);
+      ctr->total_vt = tot;
+      ctr->tot_v = tv;
+      ctr->tot_t = (tot - tv) >> 31;
+    }
+    if (tile >= ntiles) return;
+  } else {
+    if (tile >= ntiles) return;
+    run = tile_vt[tile];                               // scanned in place by k_tile_scan3
+  }
+  const unsigned long long run0 = run;
   const unsigned plane_words = (unsigned)g.n1 * (unsigned)g.W;
   const unsigned emit_end = (unsigned)g.i_hi * plane_words;
   const bool want_vemit = g.i_hiv > g.i_hi && (emit_end - word0) / CS_TILE == (unsigned)tile;
   const uint2 ch = tile_chunk[tile];
-  unsigned long long run = tile_vt[tile];
   unsigned long long below = 0;                        // records of this tile's words in front of emit_end
-  for (unsigned q0 = 0; q0 < ch.y; q0 += 32) {
-    const unsigned q = q0 + lane;
-    const bool have = q < ch.y && ch.x + q < cap_w;
-    const unsigned gw = have ? wlist[ch.x + q] : 0u;
-    const unsigned long long item = have ? rec_vt(recc[ch.x + q]) : 0ull;
-    const unsigned long long inc = warp_incl_scan_u64(item);
-    if (have) {
-      const unsigned long long mine = run + inc - item;
-      // (first vertex id, first triangle) of the word; (.z, .w) is k_count_b's dirpack
-      *reinterpret_cast<uint2*>(&wrec[gw].x) = make_uint2((uint32_t)(mine & 0x7fffffffull), (uint32_t)(mine >> 31));
-      if (want_vemit && gw < emit_end) below += item;
+  for (unsigned q0 = 0; q0 < ch.y; q0 += 64) {         // two rounds per trip: the loads of the second do not wait for the first
+    unsigned gw[2];
+    unsigned long long item[2];
+    bool have[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned q = q0 + 32u * u + lane;
+      have[u] = q < ch.y && ch.x + q < cap_w;
+      gw[u] = have[u] ? wlist[ch.x + q] : 0u;
+      item[u] = have[u] ? rec_vt(recc[ch.x + q]) : 0ull;
     }
-    run += __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned long long inc = warp_incl_scan_u64(item[u]);
+      if (have[u]) {
+        const unsigned long long mine = run + inc - item[u];
+        // (first vertex id, first triangle) of the word; (.z, .w) is k_count_b's dirpack
+        *reinterpret_cast<uint2*>(&wrec[gw[u]].x) = make_uint2((uint32_t)(mine & 0x7fffffffull), (uint32_t)(mine >> 31));
+        if (want_vemit && gw[u] < emit_end) below += item[u];
+      }
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
   }
   if (want_vemit) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
-    if (lane == 0) ctr->v_emit = (tile_vt[tile] + below) & 0x7fffffffull;
+    if (lane == 0) ctr->v_emit = (run0 + below) & 0x7fffffffull;
   }
 }
 
@@ -896,10 +981,13 @@ template <typename T, typename G>
 __global__ void CTR_EV_BOUNDS k_emit_verts(Grid<T> g, const unsigned long long* __restrict__ own_id,
                                                     const unsigned long long* __restrict__ own_rk,
                                                     const uint4* __restrict__ wrec,
-                                                    const Counters* __restrict__ ctr, unsigned cap_own, unsigned cap_v, Xform xf,
+                                                    const Counters* __restrict__ ctr, unsigned cap_own, unsigned cap_v, unsigned w_bound, Xform xf,
                                                     G* __restrict__ verts, G* __restrict__ normals,
                                                     unsigned long long* __restrict__ keys, uint8_t* __restrict__ lowmin) {
   ctr_pdl_enter();
+  // more interesting words than k_count_b went through: some slots of the work lists were never written (the host
+  // redoes the run with larger pools); nothing to do here
+  if (ctr->n_word > w_bound) return;
   // the list length comes from the device counters: the launch may precede the host's read of the counts
   const unsigned n_own = min(ctr->n_own, cap_own);
   const unsigned lane = lane_id();
@@ -1040,10 +1128,11 @@ __device__ __noinline__ W28 rows_used_exact(Grid<T> g, int i, int j, int w) {
 template <typename T>
 __global__ void CTR_ET_BOUNDS k_emit_tris(Grid<T> g, const unsigned long long* __restrict__ cell_id,
                                                           const uint32_t* __restrict__ cell_toff, const Counters* __restrict__ ctr,
-                                                          unsigned cap_cell, unsigned cap_t,
+                                                          unsigned cap_cell, unsigned cap_t, unsigned w_bound,
                                                           const uint4* __restrict__ wrec, const uint32_t* __restrict__ vox_tab,
                                                           int* __restrict__ tris) {
   ctr_pdl_enter();
+  if (ctr->n_word > w_bound) return;                  // work lists incomplete (see k_emit_verts)
   const unsigned n_cells = min(ctr->n_cell, cap_cell);
   // per warp: the 19 edge ids of its 32 voxels (row stride 33: a round of the write-out below reads arbitrary
   // (edge, voxel) pairs, and with stride 32 all the edges of one voxel share a bank), and the voxel of each of the
@@ -1391,6 +1480,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
     if ((rc = ctr_ensure(ctx, b_cell_toff, ctx->spec_cell * 4, true))) return rc;
     if ((rc = ctr_ensure(ctx, ctx->wlist, ctx->spec_w * 4, true))) return rc;
     if ((rc = ctr_ensure(ctx, ctx->aux[33], ctx->spec_w * 4, true))) return rc;                 // records of the listed words
+    if ((rc = ctr_ensure(ctx, ctx->aux[41], ctx->spec_w * 8, true))) return rc;                 // their first slots in the work lists
     if ((rc = ctr_ensure(ctx, ctx->aux[34], (size_t)ntiles * 8 + 16))) return rc;               // (first entry, entries) per tile
     if (geom) {
       if ((rc = ctr_ensure(ctx, ctx->verts, ctx->spec_v * 3 * gsz, true))) return rc;
@@ -1420,20 +1510,23 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
     CTR_DBG(ctx, "k_bitplane");
     ctr_stage_mark(ctx, 2);
     if (ntiles > 0) {
-      ctr_launch_dep(k_count_a<T>, ntiles, CS_THREADS, 0, st, g, word0, nscan, (uint32_t*)ctx->wlist.p, (uint2*)ctx->aux[34].p, cap_w, dctr);
+      ctr_launch_dep(k_count_a<T>, ntiles, CS_THREADS, 0, st, g, word0, nscan, (uint32_t*)ctx->wlist.p, (uint2*)ctx->aux[41].p,
+                     (uint2*)ctx->aux[34].p, cap_w, dctr);
       CTR_DBG(ctx, "k_count_a");
       // the grid covers the expected list length (last run's, with head-room); blocks past the real length only take a ticket
       const unsigned wb = (unsigned)((std::min<size_t>(cap_w, ctx->last_w + ctx->last_w / 8 + 4096) + CB_THREADS - 1) / CB_THREADS);
-      ctr_launch_dep(k_count_b<T>, wb, CB_THREADS, 0, st, g, word0, (const uint32_t*)ctx->wlist.p, cap_w, (uint32_t*)ctx->aux[33].p,
+      ctr_launch_dep(k_count_b<T>, wb, CB_THREADS, 0, st, g, word0, (const uint32_t*)ctx->wlist.p, (const uint2*)ctx->aux[41].p, cap_w,
+                     (uint32_t*)ctx->aux[33].p,
                      (uint4*)ctx->wdir.p, (unsigned long long*)b_own_id.p, (unsigned long long*)b_own_voff.p,
                      (unsigned long long*)b_cell_id.p, (uint32_t*)b_cell_toff.p, cap_own, cap_cell, st_vt, dctr, ntiles);
-      ctr_launch_dep(k_tile_scan3, 1, 1024, 0, st, st_vt, ntiles, dctr);
-      ctx->launches += 3;
+      const int fused = ntiles <= SCAN_FUSE_TILES ? 1 : 0;
+      if (!fused) ctr_launch_dep(k_tile_scan3, 1, 1024, 0, st, st_vt, ntiles, dctr);
+      ctx->launches += 3 - fused;
       ctx->cover_w = (size_t)wb * CB_THREADS;
       CTR_DBG(ctx, "k_count_b");
       ctr_launch_dep(k_scan<T>, (ntiles + SCAN_WARPS - 1) / SCAN_WARPS, SCAN_WARPS * 32, 0, st,
                      g, word0, ntiles, (const uint32_t*)ctx->wlist.p, (const uint32_t*)ctx->aux[33].p, (const uint2*)ctx->aux[34].p, cap_w,
-                     st_vt, (uint4*)ctx->wdir.p, dctr);
+                     (const unsigned long long*)st_vt, (uint4*)ctx->wdir.p, dctr, fused);
       ctx->launches++;
       CTR_DBG(ctx, "k_scan");
     }
@@ -1446,21 +1539,22 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
       // the kernels read list entries below min(list length, this bound): the grid's cover rounded up to whole blocks
       // may pass the list's capacity, and entries behind the capacity do not exist
       const unsigned bound_own = std::min(vb * 256u, cap_own);
+      const unsigned w_bound = (unsigned)std::min<size_t>(cap_w, ctx->cover_w);
       const unsigned long long* oid = (const unsigned long long*)b_own_id.p;
       const unsigned long long* ovo = (const unsigned long long*)b_own_voff.p;
       const uint4* dwr = (const uint4*)ctx->wdir.p;
       if (f64)
-        ctr_launch_dep(k_emit_verts<T, double>, vb, 256, 0, st, g, oid, ovo, dwr, dctr, bound_own, cap_v, xf, (double*)ctx->verts.p,
+        ctr_launch_dep(k_emit_verts<T, double>, vb, 256, 0, st, g, oid, ovo, dwr, dctr, bound_own, cap_v, w_bound, xf, (double*)ctx->verts.p,
                        want_n ? (double*)ctx->normals.p : (double*)nullptr, dkeys, dlow);
       else
-        ctr_launch_dep(k_emit_verts<T, float>, vb, 256, 0, st, g, oid, ovo, dwr, dctr, bound_own, cap_v, xf, (float*)ctx->verts.p,
+        ctr_launch_dep(k_emit_verts<T, float>, vb, 256, 0, st, g, oid, ovo, dwr, dctr, bound_own, cap_v, w_bound, xf, (float*)ctx->verts.p,
                        want_n ? (float*)ctx->normals.p : (float*)nullptr, dkeys, dlow);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_verts");
       ctr_stage_mark(ctx, 4);
       const unsigned tb = (unsigned)((std::min<size_t>(cap_cell, ctx->last_cell + ctx->last_cell / 8 + 4096) + ET_THREADS - 1) / ET_THREADS);
       ctr_launch_dep(k_emit_tris<T>, tb, ET_THREADS, 0, st, g, (const unsigned long long*)b_cell_id.p, (const uint32_t*)b_cell_toff.p, dctr,
-                     std::min(tb * (unsigned)ET_THREADS, cap_cell), cap_t, (const uint4*)ctx->wdir.p,
+                     std::min(tb * (unsigned)ET_THREADS, cap_cell), cap_t, w_bound, (const uint4*)ctx->wdir.p,
                      (const uint32_t*)ctx->vox_tab.p, (int*)ctx->tris.p);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_tris");

@@ -227,3 +227,31 @@ def test_c2_field16384_subblocks_equal_oracle(engine):
                                        rtol=1e-4, atol=1e-4)
             checked += len(want)
     assert checked > 10000
+
+
+def test_large_single_run_equals_its_slabs(engine):
+    """272 x 1024 x 1024 samples in ONE call (8704 tiles of 1024 words: past the size up to which the offset kernel sums
+    the tile aggregates itself, so the one-block tile scan runs) against the same planes cut into four z-slabs (each
+    below that size): identical keys, positions and triangles."""
+    import torch
+    from contourist_b200 import engine as E
+    from contourist_b200 import sharding, synthetic
+    n, n0 = 1024, 272
+    f = synthetic.turbulence(n, 0, n0, n_total=n)
+    torch.cuda.synchronize()
+    flags = E.WANT_KEYS
+    c = engine.mt3d_run(f.data_ptr(), 0.0, flags=flags, shape=(n0, n, n), dtype=np.float32)
+    ref = engine.mt3d_fetch()
+    assert c.n_tris > 1000000
+    keys, verts, tris, voff = [], [], [], 0
+    plane = n * n * 4
+    for (a, b) in sharding.slab_bounds(n0, 4):
+        lo, hi, kw = sharding.slab_with_halo(a, b, n0)
+        cs = engine.mt3d_run(f.data_ptr() + lo * plane, 0.0, flags=flags, shape=(hi - lo, n, n), dtype=np.float32, **kw)
+        o = engine.mt3d_fetch()
+        keys.append(o["keys"]); verts.append(o["verts"]); tris.append(o["tris"].astype(np.int64) + voff)
+        voff += cs.n_verts
+    assert voff == c.n_verts
+    assert np.array_equal(np.concatenate(keys), ref["keys"])
+    assert np.array_equal(np.concatenate(verts), ref["verts"])
+    assert np.array_equal(np.concatenate(tris), ref["tris"].astype(np.int64))
