@@ -352,8 +352,8 @@ __device__ __noinline__ WordExact count_word_exact(const Grid<T> g, const Planes
 //   B  interesting words are dealt out evenly: vertex / triangle / owner / voxel counts per word;
 //   C  block scan + decoupled look-back across tiles -> exclusive offsets per word;
 //   D  interesting words again: write vbase and the compacted, ordered lists of
-//        active owners (own_id = word<<13 | bit<<8 | p_low<<7 | mask7, own_voff = first vertex id)
-//        active voxels (cell_id = word<<19 | bit<<14 | emit6<<8 | corner8, cell_toff = first triangle).
+//        active owners (16-byte entries: word<<13 | bit<<8 | p_low<<7 | mask7, and the 7 x 5-bit ranks)
+//        active voxels (cell_id = word<<28 | first triangle<<19 | bit<<14 | emit6<<8 | corner8).
 // ------------------------------------------------------------------------------------------------
 constexpr int CS_THREADS = 256;
 constexpr int CS_ITEMS = 4;
@@ -476,8 +476,9 @@ __device__ __forceinline__ unsigned long long rec_vt(uint32_t r) {
 // (As ONE kernel per tile of 1024 words -- quick test, then the ~70 interesting words of the tile one per thread -- three
 // quarters of every block idled through the second phase and every tile paid the latency chain planes -> counts -> two
 // global atomics -> list writes on its own: 133 us against 17 + 104 us for the pair, measured under ncu.)
-// Owner entries:  own_id = word<<13 | bit<<8 | p_low<<7 | mask7, own_rk = 7 x 5-bit ranks within the directions.
-// Voxel entries:  cell_id = word<<19 | bit<<14 | emit6<<8 | corner8, cell_toff = first triangle RELATIVE to tbase[word].
+// Owner entries (16 bytes):  .x = word<<13 | bit<<8 | p_low<<7 | mask7, .y = 7 x 5-bit ranks within the directions.
+// Voxel entries (8 bytes):  word<<28 | toff<<19 | bit<<14 | emit6<<8 | corner8, toff (9 bits, <= 31 x 12) = first triangle
+// RELATIVE to tbase[word].  One store per entry in k_count_b, one load per entry in stages 3 / 4.
 // Neither needs the scan: vertex ids are vbase[word] + dirbase + rank, triangle offsets tbase[word] + relative.
 // The lists are ordered inside a block and unordered across blocks; the mesh does not depend on their order.
 // ------------------------------------------------------------------------------------------------
@@ -597,10 +598,9 @@ template <typename T>
 __global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin, unsigned word0, const uint32_t* __restrict__ wlist,
                                                         const uint2* __restrict__ wslot,
                                                         unsigned cap_w, uint32_t* __restrict__ recc, uint4* __restrict__ wrec,
-                                                        unsigned long long* __restrict__ own_id,
-                                                        unsigned long long* __restrict__ own_rk,
+                                                        ulonglong2* __restrict__ own,
                                                         unsigned long long* __restrict__ cell_id,
-                                                        uint32_t* __restrict__ cell_toff, unsigned cap_own, unsigned cap_cell,
+                                                        unsigned cap_own, unsigned cap_cell,
                                                         unsigned long long* __restrict__ tile_vt, Counters* ctr, int ntiles) {
   __shared__ CountBShared sh;
   Grid<T> g = gin;
@@ -709,8 +709,7 @@ __global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin
       mo &= mo - 1;
       const unsigned m7 = gather7(x, b);
       if (orun < cap_own) {
-        own_id[orun] = ((unsigned long long)gw << 13) | ((unsigned)b << 8) | (((pl.P[0] >> b) & 1u) << 7) | m7;
-        own_rk[orun] = run;
+        own[orun] = make_ulonglong2(((unsigned long long)gw << 13) | ((unsigned)b << 8) | (((pl.P[0] >> b) & 1u) << 7) | m7, run);
       }
       run += sh.spread[m7];
       ++orun;
@@ -747,8 +746,7 @@ __global__ void __launch_bounds__(CB_THREADS, CTR_CB_MINB) k_count_b(Grid<T> gin
         }
       }
       if (crun < cap_cell) {
-        cell_id[crun] = ((unsigned long long)gw << 19) | ((unsigned)b << 14) | (emit << 8) | c8;
-        cell_toff[crun] = trun;
+        cell_id[crun] = ((unsigned long long)gw << 28) | ((unsigned long long)trun << 19) | ((unsigned)b << 14) | (emit << 8) | c8;
       }
       ++crun;
       trun += nt;
@@ -978,8 +976,7 @@ __device__ __forceinline__ int nth_set_bit7(unsigned m, unsigned n) {
 #define CTR_EV_BOUNDS __launch_bounds__(256)
 #endif
 template <typename T, typename G>
-__global__ void CTR_EV_BOUNDS k_emit_verts(Grid<T> g, const unsigned long long* __restrict__ own_id,
-                                                    const unsigned long long* __restrict__ own_rk,
+__global__ void CTR_EV_BOUNDS k_emit_verts(Grid<T> g, const ulonglong2* __restrict__ own,
                                                     const uint4* __restrict__ wrec,
                                                     const Counters* __restrict__ ctr, unsigned cap_own, unsigned cap_v, unsigned w_bound, Xform xf,
                                                     G* __restrict__ verts, G* __restrict__ normals,
@@ -995,8 +992,8 @@ __global__ void CTR_EV_BOUNDS k_emit_verts(Grid<T> g, const unsigned long long* 
   const unsigned warp_first = a - lane;
   if (warp_first >= n_own) return;
   const bool have = a < n_own;
-  const unsigned long long oid = have ? own_id[a] : 0ull;
-  const unsigned long long ork = have ? own_rk[a] : 0ull;
+  const ulonglong2 oent = have ? own[a] : make_ulonglong2(0ull, 0ull);
+  const unsigned long long oid = oent.x, ork = oent.y;
   const unsigned ogw = (unsigned)(oid >> 13);
   const uint4 orec = have ? wrec[ogw] : make_uint4(0u, 0u, 0u, 0u);
   const unsigned vb = orec.x;
@@ -1127,7 +1124,7 @@ __device__ __noinline__ W28 rows_used_exact(Grid<T> g, int i, int j, int w) {
 #define CTR_ET_BOUNDS __launch_bounds__(ET_THREADS, CTR_ET_MINB)
 template <typename T>
 __global__ void CTR_ET_BOUNDS k_emit_tris(Grid<T> g, const unsigned long long* __restrict__ cell_id,
-                                                          const uint32_t* __restrict__ cell_toff, const Counters* __restrict__ ctr,
+                                                          const Counters* __restrict__ ctr,
                                                           unsigned cap_cell, unsigned cap_t, unsigned w_bound,
                                                           const uint4* __restrict__ wrec, const uint32_t* __restrict__ vox_tab,
                                                           int* __restrict__ tris) {
@@ -1146,7 +1143,7 @@ __global__ void CTR_ET_BOUNDS k_emit_tris(Grid<T> g, const unsigned long long* _
   const unsigned long long cid = valid ? cell_id[a] : 0ull;   // lanes past the end run voxel 0 with nothing to emit
   const unsigned c8 = (unsigned)cid & 255u, emit = (unsigned)(cid >> 8) & 63u;
   const int b = (int)((cid >> 14) & 31u);
-  const unsigned gw0 = (unsigned)(cid >> 19);
+  const unsigned gw0 = (unsigned)(cid >> 28);
   const unsigned uW = (unsigned)g.W, plane_words = (unsigned)g.n1 * uW;
   const unsigned row = g.divW.div(gw0);
   const unsigned w = gw0 - row * uW;
@@ -1218,7 +1215,7 @@ __global__ void CTR_ET_BOUNDS k_emit_tris(Grid<T> g, const unsigned long long* _
   // per lane per round: each voxel marks its triangles with its lane in shared memory, then lane q of a round takes
   // triangle q -- its voxel from the mark, its row of the table, three ids from s_ids -- and writes it where the scan
   // put it (tbase[word] + offset in the word + index in the voxel): no assumption about the order of the list.
-  const unsigned o = valid ? tb0 + cell_toff[a] : 0u;       // cell_toff is relative to the word's first triangle
+  const unsigned o = valid ? tb0 + ((unsigned)(cid >> 19) & 511u) : 0u;   // the entry's offset is relative to the word's first triangle
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned* ids = s_ids[warp];
   const uint32_t full = __ldg(vox_tab + c8 * 13 + 12);
@@ -1275,7 +1272,7 @@ __global__ void __launch_bounds__(256) k_codes(Grid<T> g, const unsigned long lo
   if (a >= n_cells) return;
   const unsigned long long cid = cell_id[a];
   const int b = (int)((cid >> 14) & 31u);
-  const unsigned gw = (unsigned)(cid >> 19);
+  const unsigned gw = (unsigned)(cid >> 28);
   const unsigned row = gw / (unsigned)g.W;
   const int w = (int)(gw - row * (unsigned)g.W);
   const int i = (int)(row / (unsigned)g.n1), j = (int)(row - (unsigned)i * (unsigned)g.n1);
@@ -1462,10 +1459,8 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
   // every stage is enqueued against them without waiting for the counts -- kernels read the list lengths from the
   // device counters and never write past a capacity -- and the counts are checked after the single synchronisation
   // at the end.  Only when a capacity turns out too small are the buffers grown and the affected stages redone.
-  DevBuf& b_own_id = ctx->aux[0];
-  DevBuf& b_own_voff = ctx->aux[1];
+  DevBuf& b_own = ctx->aux[0];
   DevBuf& b_cell_id = ctx->aux[2];
-  DevBuf& b_cell_toff = ctx->aux[3];
   if (!ctx->spec_w) ctx->spec_w = std::max<size_t>((size_t)nwords / 4, 1 << 14);
   if (!ctx->spec_own) ctx->spec_own = std::max<size_t>((size_t)nwords / 2, 1 << 14);
   if (!ctx->spec_cell) ctx->spec_cell = ctx->spec_own;
@@ -1474,10 +1469,8 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
   Counters h;
   unsigned long long totV = 0, totT = 0, nOwn = 0, nCell = 0, nV = 0;
   for (int attempt = 0;; ++attempt) {
-    if ((rc = ctr_ensure(ctx, b_own_id, ctx->spec_own * 8, true))) return rc;
-    if ((rc = ctr_ensure(ctx, b_own_voff, ctx->spec_own * 8, true))) return rc;      // own_rk
+    if ((rc = ctr_ensure(ctx, b_own, ctx->spec_own * 16, true))) return rc;
     if ((rc = ctr_ensure(ctx, b_cell_id, ctx->spec_cell * 8, true))) return rc;
-    if ((rc = ctr_ensure(ctx, b_cell_toff, ctx->spec_cell * 4, true))) return rc;
     if ((rc = ctr_ensure(ctx, ctx->wlist, ctx->spec_w * 4, true))) return rc;
     if ((rc = ctr_ensure(ctx, ctx->aux[33], ctx->spec_w * 4, true))) return rc;                 // records of the listed words
     if ((rc = ctr_ensure(ctx, ctx->aux[41], ctx->spec_w * 8, true))) return rc;                 // their first slots in the work lists
@@ -1517,8 +1510,7 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
       const unsigned wb = (unsigned)((std::min<size_t>(cap_w, ctx->last_w + ctx->last_w / 8 + 4096) + CB_THREADS - 1) / CB_THREADS);
       ctr_launch_dep(k_count_b<T>, wb, CB_THREADS, 0, st, g, word0, (const uint32_t*)ctx->wlist.p, (const uint2*)ctx->aux[41].p, cap_w,
                      (uint32_t*)ctx->aux[33].p,
-                     (uint4*)ctx->wdir.p, (unsigned long long*)b_own_id.p, (unsigned long long*)b_own_voff.p,
-                     (unsigned long long*)b_cell_id.p, (uint32_t*)b_cell_toff.p, cap_own, cap_cell, st_vt, dctr, ntiles);
+                     (uint4*)ctx->wdir.p, (ulonglong2*)b_own.p, (unsigned long long*)b_cell_id.p, cap_own, cap_cell, st_vt, dctr, ntiles);
       const int fused = ntiles <= SCAN_FUSE_TILES ? 1 : 0;
       if (!fused) ctr_launch_dep(k_tile_scan3, 1, 1024, 0, st, st_vt, ntiles, dctr);
       ctx->launches += 3 - fused;
@@ -1540,20 +1532,19 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
       // may pass the list's capacity, and entries behind the capacity do not exist
       const unsigned bound_own = std::min(vb * 256u, cap_own);
       const unsigned w_bound = (unsigned)std::min<size_t>(cap_w, ctx->cover_w);
-      const unsigned long long* oid = (const unsigned long long*)b_own_id.p;
-      const unsigned long long* ovo = (const unsigned long long*)b_own_voff.p;
+      const ulonglong2* oid = (const ulonglong2*)b_own.p;
       const uint4* dwr = (const uint4*)ctx->wdir.p;
       if (f64)
-        ctr_launch_dep(k_emit_verts<T, double>, vb, 256, 0, st, g, oid, ovo, dwr, dctr, bound_own, cap_v, w_bound, xf, (double*)ctx->verts.p,
+        ctr_launch_dep(k_emit_verts<T, double>, vb, 256, 0, st, g, oid, dwr, dctr, bound_own, cap_v, w_bound, xf, (double*)ctx->verts.p,
                        want_n ? (double*)ctx->normals.p : (double*)nullptr, dkeys, dlow);
       else
-        ctr_launch_dep(k_emit_verts<T, float>, vb, 256, 0, st, g, oid, ovo, dwr, dctr, bound_own, cap_v, w_bound, xf, (float*)ctx->verts.p,
+        ctr_launch_dep(k_emit_verts<T, float>, vb, 256, 0, st, g, oid, dwr, dctr, bound_own, cap_v, w_bound, xf, (float*)ctx->verts.p,
                        want_n ? (float*)ctx->normals.p : (float*)nullptr, dkeys, dlow);
       ctx->launches++;
       CTR_DBG(ctx, "k_emit_verts");
       ctr_stage_mark(ctx, 4);
       const unsigned tb = (unsigned)((std::min<size_t>(cap_cell, ctx->last_cell + ctx->last_cell / 8 + 4096) + ET_THREADS - 1) / ET_THREADS);
-      ctr_launch_dep(k_emit_tris<T>, tb, ET_THREADS, 0, st, g, (const unsigned long long*)b_cell_id.p, (const uint32_t*)b_cell_toff.p, dctr,
+      ctr_launch_dep(k_emit_tris<T>, tb, ET_THREADS, 0, st, g, (const unsigned long long*)b_cell_id.p, (const Counters*)dctr,
                      std::min(tb * (unsigned)ET_THREADS, cap_cell), cap_t, w_bound, (const uint4*)ctx->wdir.p,
                      (const uint32_t*)ctx->vox_tab.p, (int*)ctx->tris.p);
       ctx->launches++;

@@ -37,7 +37,7 @@ __global__ void k_sel_cells(Grid<T> g, const unsigned long long* __restrict__ ce
   if (c >= n_cell) return;
   const unsigned long long id = cell_id[c];
   int i, j, w;
-  g.word_coords((unsigned)(id >> 19), i, j, w);
+  g.word_coords((unsigned)(id >> 28), i, j, w);
   node_vox[c] = vox_key(g, i, j, w * 32 + (int)((id >> 14) & 31u));
 }
 
@@ -117,8 +117,7 @@ __global__ void k_sel_seeds(const int* __restrict__ seeds, unsigned n_seeds, int
   if (s->key == key) flag[ufh::uf_find(parent, s->tri)] = 1;
 }
 
-__global__ void k_sel_mark(const unsigned long long* __restrict__ cell_id, const uint32_t* __restrict__ cell_toff,
-                           unsigned n_cell, const uint4* __restrict__ wrec, int* parent, const uint8_t* __restrict__ flag,
+__global__ void k_sel_mark(const unsigned long long* __restrict__ cell_id, unsigned n_cell, const uint4* __restrict__ wrec, int* parent, const uint8_t* __restrict__ flag,
                            uint8_t* __restrict__ keep_t, unsigned n_tris, unsigned* n_sel_cells) {
   const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_cell) return;
@@ -132,7 +131,7 @@ __global__ void k_sel_mark(const unsigned long long* __restrict__ cell_id, const
 #pragma unroll
   for (int t = 0; t < 6; ++t)
     if ((emit >> t) & 1u) nt += (__popc(tet_mask_of(c8, t)) == 2) ? 2u : 1u;
-  const unsigned t0 = wrec[(unsigned)(id >> 19)].y + cell_toff[c];
+  const unsigned t0 = wrec[(unsigned)(id >> 28)].y + ((unsigned)(id >> 19) & 511u);
   for (unsigned q = 0; q < nt; ++q)
     if (t0 + q < n_tris) keep_t[t0 + q] = 1;
 }
@@ -305,7 +304,7 @@ int select_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, const int32_t* seeds, i
     k_sel_seeds<<<(unsigned)((n_seeds + 255) / 256), 256, 0, st>>>((const int*)b_seeds.p, (unsigned)n_seeds, n0, n1, n2, tab,
                                                                     nslots - 1, parent, flag);
   if (n_cell)
-    k_sel_mark<<<cb, 256, 0, st>>>((const unsigned long long*)ctx->aux[2].p, (const uint32_t*)ctx->aux[3].p, n_cell,
+    k_sel_mark<<<cb, 256, 0, st>>>((const unsigned long long*)ctx->aux[2].p, n_cell,
                                    (const uint4*)ctx->wdir.p, parent, flag, keep_t, nT, &dctr->pad);
   if (nT) {
     k_sel_used<<<tb, 256, 0, st>>>((const int*)ctx->tris.p, nT, keep_t, g.id_base, used_v, nV);
