@@ -1013,22 +1013,24 @@ __global__ void CTR_EV_BOUNDS k_emit_verts(Grid<T> g, const ulonglong2* __restri
   const unsigned excl = incl - cnt;
   const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
   const G v = (G)g.v;
+  // what a vertex lane needs to know about its owner, in one word: prefix (8 bits) | edge mask (7) | low flag (1) | bit (5)
+  const unsigned opack = excl | (((unsigned)oid & 0xffu) << 8) | ((unsigned)((oid >> 8) & 31u) << 16);
   for (unsigned base = 0; base < total; base += 32) {
     const unsigned vtx = base + lane;
     const bool act = vtx < total;
-    // owner o = last lane whose exclusive prefix <= vtx  (binary search over the warp's prefixes)
-    int o = 0;
-#pragma unroll
-    for (int step = 16; step > 0; step >>= 1) {
-      const int probe = o + step;
-      const unsigned e = __shfl_sync(0xffffffffu, excl, probe & 31);
-      if (probe < 32 && e <= vtx) o = probe;
-    }
-    // owners with zero vertices never appear in the list (cnt >= 1), so prefixes are strictly increasing
-    const unsigned o_excl = __shfl_sync(0xffffffffu, excl, o);
-    const unsigned o_m7 = __shfl_sync(0xffffffffu, m7, o);
-    const unsigned o_lo = __shfl_sync(0xffffffffu, (unsigned)((oid >> 7) & 1u), o);
-    const int oi = __shfl_sync(0xffffffffu, i, o), oj = __shfl_sync(0xffffffffu, j, o), ok = __shfl_sync(0xffffffffu, k, o);
+    // owner o = last lane whose exclusive prefix <= vtx.  Every listed owner has at least one vertex, so the prefixes
+    // are strictly increasing and the owners (lanes 0 .. m-1) are counted by their first vertices: those in front of
+    // this round (one ballot) plus those up to this lane's vertex (one warp OR of start bits) -- instead of a
+    // five-step binary search by shuffles
+    const bool starts_here = cnt > 0 && excl >= base && excl < base + 32u;
+    const unsigned starts = __reduce_or_sync(0xffffffffu, starts_here ? 1u << (excl - base) : 0u);
+    const unsigned before = __popc(__ballot_sync(0xffffffffu, cnt > 0 && excl < base));
+    const int o = (int)(before + __popc(starts & (0xffffffffu >> (31u - lane)))) - 1;
+    const unsigned op = __shfl_sync(0xffffffffu, opack, o);
+    const unsigned o_excl = op & 255u, o_m7 = (op >> 8) & 127u, o_lo = (op >> 15) & 1u;
+    int oi, oj, ow;
+    g.word_coords(__shfl_sync(0xffffffffu, ogw, o), oi, oj, ow);
+    const int ok = ow * 32 + (int)((op >> 16) & 31u);
     const G ofp = shfl_g(fp, o);
     G ogp[3];
     if (normals) {
