@@ -303,14 +303,13 @@ def run_ours(args):
     ev_sent = [None, None]                                  # all-gather of the slot finished (side stream)
     n_step = [0]
 
-    # One GPU: two contexts on the same stream take the steps in turn and step k+1 is queued (ctr_mt3d_enqueue) before
-    # the host waits for step k (ctr_mt3d_finish), so the device never waits for the host's wake-up and first launch
-    # between two extractions (~10 us per 0.35 ms step with the synchronous ctr_mt3d_run); every step still is one
-    # complete extraction with its counts read back by the host.
-    eng_b = None
-    if world == 1:
-        eng_b = E.Engine(local)
-        eng_b.set_stream(stream.cuda_stream)
+    # Two contexts on the same stream take the steps in turn and step k+1 is queued (ctr_mt3d_enqueue, and behind it the
+    # all-gather of its counts) before the host waits for step k (ctr_mt3d_finish), so the device never waits for the
+    # host's wake-up and first launch between two extractions (~10 us per 0.35 ms step with a synchronous step); every
+    # step still is one complete extraction with its counts read back by the host (and, on several GPUs, all-gathered).
+    eng_b = E.Engine(local)
+    eng_b.set_stream(stream.cuda_stream)
+    engines = (eng, eng_b)
     pending = [None]
 
     def step_sync():
@@ -318,21 +317,16 @@ def run_ours(args):
                             i_lo=a - lo, i_hi=b - lo, plane_offset=lo)
 
     def step():
-        if world == 1:
-            e = eng if (n_step[0] & 1) == 0 else eng_b
-            n_step[0] += 1
-            e.mt3d_enqueue(field.data_ptr(), ISOVALUE, shape=shape, dtype=np.float32, flags=flags,
-                           i_lo=a - lo, i_hi=b - lo, plane_offset=lo)
-            prev, pending[0] = pending[0], e
-            return prev.mt3d_finish() if prev is not None else None
         slot = n_step[0] & 1
         n_step[0] += 1
-        if ev_sent[slot] is not None:
-            stream.wait_event(ev_sent[slot])                # the slot's previous counts have been sent (two steps ago)
-        eng.mt3d_publish_counts(counts_dev[slot].data_ptr())
-        eng.mt3d_enqueue(field.data_ptr(), ISOVALUE, shape=shape, dtype=np.float32, flags=flags,
-                         i_lo=a - lo, i_hi=b - lo, plane_offset=lo)
-        if side is not None:
+        e = engines[slot]
+        if world > 1:
+            if ev_sent[slot] is not None:
+                stream.wait_event(ev_sent[slot])            # the slot's previous counts have been sent (two steps ago)
+            e.mt3d_publish_counts(counts_dev[slot].data_ptr())
+        e.mt3d_enqueue(field.data_ptr(), ISOVALUE, shape=shape, dtype=np.float32, flags=flags,
+                       i_lo=a - lo, i_hi=b - lo, plane_offset=lo)
+        if world > 1 and side is not None:
             ev_done[slot].record(stream)
             with torch.cuda.stream(side):
                 side.wait_event(ev_done[slot])
@@ -340,9 +334,10 @@ def run_ours(args):
                 if ev_sent[slot] is None:
                     ev_sent[slot] = torch.cuda.Event()
                 ev_sent[slot].record(side)
-        elif ag_mode == "main":
+        elif world > 1 and ag_mode == "main":
             dist.all_gather_into_tensor(gathered[slot], counts_dev[slot])
-        return eng.mt3d_finish()
+        prev, pending[0] = pending[0], e
+        return prev.mt3d_finish() if prev is not None else None
 
     def flush():
         if side is not None:
@@ -357,7 +352,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 2 if world == 1 else 0)):     # (both contexts size their pools)
+    for _ in range(max(args.warmup, 2)):              # (both contexts size their pools)
         step()
     flush()
     barrier()
@@ -366,7 +361,7 @@ def run_ours(args):
     stage_acc = np.zeros(8)
     n_inst = max(3, min(args.steps, 10))
     for _ in range(n_inst):
-        c = step_sync() if world == 1 else step()
+        c = step_sync()                               # (no collective: the same on every rank)
         stage_acc += np.array(eng.stage_times(8)) / n_inst
     eng.set_timing(False)
     step()
@@ -382,7 +377,7 @@ def run_ours(args):
     for _ in range(PRELOAD):
         step()
     c = flush() or c
-    l0 = eng.kernel_launches() + (eng_b.kernel_launches() if eng_b is not None else 0)
+    l0 = eng.kernel_launches() + eng_b.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
@@ -396,7 +391,7 @@ def run_ours(args):
     wall = time.perf_counter() - t0
     sampler.mark()
     dev_ms = ev0.elapsed_time(ev1)
-    launches = eng.kernel_launches() + (eng_b.kernel_launches() if eng_b is not None else 0) - l0
+    launches = eng.kernel_launches() + eng_b.kernel_launches() - l0
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "%d untimed steps of the same loop directly before the timed region, and the timed region" % PRELOAD
@@ -555,9 +550,9 @@ def run_ours(args):
                         "while slab s runs, page-locked host buffers): H2D of the field and D2H of vertices, normals and "
                         "triangles inside the timed region"},
         "gpu_launches": int(launches), "clocks": clocks,
-        "stepping": ("one GPU: two contexts on one stream take the steps in turn, step k+1 is queued before the host waits for "
-                     "the counts of step k (every step one complete extraction)" if world == 1 else
-                     "every step: enqueue, all-gather of the device counts on the same stream, host waits for the extraction"),
+        "stepping": "two contexts on one stream take the steps in turn; step k+1 (and, on several GPUs, the all-gather of its "
+                    "device counts behind it) is queued before the host waits for the counts of step k; every step is one "
+                    "complete extraction",
         "f64_geom": f64, "c5_strong": c5,
         "post_passes": post,
     }
