@@ -1130,7 +1130,11 @@ __global__ void CTR_ET_BOUNDS k_emit_tris(Grid<T> g, const unsigned long long* _
                                                           unsigned cap_cell, unsigned cap_t, unsigned w_bound,
                                                           const uint4* __restrict__ wrec, const uint32_t* __restrict__ vox_tab,
                                                           int* __restrict__ tris) {
-  ctr_pdl_enter();
+  // No wait here: this kernel reads what stage 2 left (lists, records, counters) and nothing that k_emit_verts, the
+  // kernel in front of it, writes.  Its blocks are released once every block of k_emit_verts has passed ITS wait, i.e.
+  // once stage 2 is complete (common.cuh, rule 2), and fill the SMs that k_emit_verts' last wave leaves idle.  Whatever
+  // follows in the stream (the copy of the counts, k_publish3) waits for both kernels / reads the counters only.
+  ctr_pdl_trigger();
   if (ctr->n_word > w_bound) return;                  // work lists incomplete (see k_emit_verts)
   const unsigned n_cells = min(ctr->n_cell, cap_cell);
   // per warp: the 19 edge ids of its 32 voxels (row stride 33: a round of the write-out below reads arbitrary

@@ -232,6 +232,34 @@ def test_pools_grow_from_a_tiny_first_run(engine):
     small.close()
 
 
+def test_alternating_fields_on_one_context(engine):
+    """Two different fields of one shape run in turn on the same context: every buffer of a run is rewritten by the next
+    at the same addresses.  The kernels of a run are chained with programmatic dependent launch and some start under the
+    tail of the one in front; a kernel that read anything stale (a bit plane, a record, a list entry of the run before)
+    would give another mesh than a context that has only ever seen that field."""
+    from contourist_b200 import engine as E
+    rng = np.random.default_rng(99)
+    shape = (96, 80, 160)
+    fa = rng.standard_normal(shape).astype(np.float32)
+    g = np.linspace(-1, 1, 160)
+    fb = (np.sin(7 * g)[None, None, :] * np.cos(5 * g[:80])[None, :, None] + g[:96, None, None] ** 2
+          + 0.2 * rng.standard_normal(shape)).astype(np.float32)
+    flags = E.WANT_KEYS | E.WANT_NORMALS
+    refs = []
+    for f in (fa, fb):
+        fresh = E.Engine(0)
+        c = fresh.mt3d_run(f, 0.1, flags=flags)
+        refs.append((c.n_verts, c.n_tris, fresh.mt3d_fetch()))
+        fresh.close()
+    for rep in range(8):
+        for f, (nv, nt, ref) in zip((fa, fb), refs):
+            c = engine.mt3d_run(f, 0.1, flags=flags)
+            out = engine.mt3d_fetch()
+            assert (c.n_verts, c.n_tris) == (nv, nt)
+            for name in ("keys", "lowmin", "verts", "normals", "tris"):
+                assert np.array_equal(out[name], ref[name]), (name, rep)
+
+
 def test_pipelined_host_extraction_equals_single_run(engine):
     """engine.mt3d_extract_host (slab-by-slab upload / extract / download on two contexts, global triangle ids via
     vert_id_base) returns exactly the mesh of one ctr_mt3d_run + ctr_mt3d_fetch."""
