@@ -529,13 +529,19 @@ __global__ void __launch_bounds__(C4_THREADS, 2) k4_count_scan(Grid4<T> gin, uns
 // exclusive scan of the per-tile (vertices | tetrahedra << 31) totals: one block, a few thousand tiles
 __global__ void __launch_bounds__(1024) k4_tile_scan(const unsigned long long* __restrict__ tile_vt, int ntiles,
                                                      unsigned long long* __restrict__ tile_off, Counters4* ctr) {
+  constexpr int PER = 4;                               // consecutive tiles per thread: 4096 tiles in one round
   __shared__ unsigned long long s_warp[32];
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   unsigned long long carry = 0;
-  for (int base = 0; base < ntiles; base += 1024) {
-    const int q = base + (int)threadIdx.x;
-    const unsigned long long c = q < ntiles ? tile_vt[q] : 0ull;
-    const unsigned long long inc = warp_incl_scan_u64(c);
+  for (int base = 0; base < ntiles; base += 1024 * PER) {
+    const int q = base + (int)threadIdx.x * PER;
+    unsigned long long c[PER], mine = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      c[u] = q + u < ntiles ? tile_vt[q + u] : 0ull;
+      mine += c[u];
+    }
+    const unsigned long long inc = warp_incl_scan_u64(mine);
     __syncthreads();
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
@@ -545,7 +551,12 @@ __global__ void __launch_bounds__(1024) k4_tile_scan(const unsigned long long* _
       if (w < (int)warp) woff += s_warp[w];
       tot += s_warp[w];
     }
-    if (q < ntiles) tile_off[q] = carry + woff + inc - c;
+    unsigned long long run = carry + woff + inc - mine;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      if (q + u < ntiles) tile_off[q + u] = run;
+      run += c[u];
+    }
     carry += tot;
   }
   if (threadIdx.x == 0) {

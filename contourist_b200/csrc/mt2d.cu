@@ -276,13 +276,21 @@ __global__ void __launch_bounds__(T2_THREADS) k2d_count(const T* __restrict__ f,
 // exclusive scan of the per-tile segment counts (one block; a few thousand tiles) -> tile_off, grand totals
 __global__ void __launch_bounds__(1024) k2d_tile_scan(const unsigned long long* __restrict__ tile_cnt, int ntiles,
                                                       uint32_t* __restrict__ tile_off, Counters2D* ctr) {
+  // 8 consecutive tiles per thread, so the 8192 tiles of a 16384^2 field are one round of independent loads, one warp
+  // scan and two barriers (one tile per thread took eight such rounds one after the other: 20 us of pure latency)
+  constexpr int PER = 8;
   __shared__ unsigned long long s_warp[32];
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   unsigned long long carry = 0;
-  for (int base = 0; base < ntiles; base += 1024) {
-    const int q = base + (int)threadIdx.x;
-    const unsigned long long c = q < ntiles ? tile_cnt[q] : 0ull;
-    const unsigned long long inc = warp_incl_scan_u64(c);
+  for (int base = 0; base < ntiles; base += 1024 * PER) {
+    const int q = base + (int)threadIdx.x * PER;
+    unsigned long long c[PER], mine = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      c[u] = q + u < ntiles ? tile_cnt[q + u] : 0ull;
+      mine += c[u];
+    }
+    const unsigned long long inc = warp_incl_scan_u64(mine);
     __syncthreads();
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
@@ -292,7 +300,12 @@ __global__ void __launch_bounds__(1024) k2d_tile_scan(const unsigned long long* 
       if (w < (int)warp) woff += s_warp[w];
       tot += s_warp[w];
     }
-    if (q < ntiles) tile_off[q] = (uint32_t)((carry + woff + inc - c) >> 31);
+    unsigned long long run = carry + woff + inc - mine;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      if (q + u < ntiles) tile_off[q + u] = (uint32_t)(run >> 31);
+      run += c[u];
+    }
     carry += tot;
   }
   if (threadIdx.x == 0) ctr->total = carry;
