@@ -1133,7 +1133,7 @@ __global__ void CTR_ET_BOUNDS k_emit_tris(Grid<T> g, const unsigned long long* _
   // No wait here: this kernel reads what stage 2 left (lists, records, counters) and nothing that k_emit_verts, the
   // kernel in front of it, writes.  Its blocks are released once every block of k_emit_verts has passed ITS wait, i.e.
   // once stage 2 is complete (common.cuh, rule 2), and fill the SMs that k_emit_verts' last wave leaves idle.  Whatever
-  // follows in the stream (the copy of the counts, k_publish3) waits for both kernels / reads the counters only.
+  // follows in the stream reads the counters only (k_counts_out) or waits for both kernels (copies, events, plain launches).
   ctr_pdl_trigger();
   if (ctr->n_word > w_bound) return;                  // work lists incomplete (see k_emit_verts)
   const unsigned n_cells = min(ctr->n_cell, cap_cell);
@@ -1295,11 +1295,20 @@ __global__ void k_offset_ids(int* __restrict__ tris, size_t n, int base) {
   if (q < n) tris[q] += base;
 }
 
-// ctr_mt3d_publish_counts: {n_verts, n_tris} of the run for a collective that reads them on the device
-__global__ void k_publish3(const Counters* __restrict__ ctr, int sharded, long long* __restrict__ out) {
+static_assert(sizeof(Counters) <= 1024 && sizeof(Counters) % 4 == 0, "pinned counter mirror is 1 KiB");
+
+// Last kernel of a run: the counter block goes to its page-locked mirror on the host (written through the mapping: a
+// cudaMemcpyAsync here put a copy-engine hop between this run's last kernel and the next run's first) and, for
+// ctr_mt3d_publish_counts, {n_verts, n_tris} to the device address a collective reads them from.
+__global__ void __launch_bounds__(128) k_counts_out(const Counters* __restrict__ ctr, uint32_t* __restrict__ host_mirror, int sharded,
+                                                    long long* __restrict__ pub) {
   ctr_pdl_enter();
-  out[0] = (long long)(sharded ? ctr->v_emit : ctr->tot_v);
-  out[1] = (long long)ctr->tot_t;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(ctr);
+  for (unsigned q = threadIdx.x; q < sizeof(Counters) / 4; q += blockDim.x) host_mirror[q] = src[q];
+  if (pub && threadIdx.x == 0) {
+    pub[0] = (long long)(sharded ? ctr->v_emit : ctr->tot_v);
+    pub[1] = (long long)ctr->tot_t;
+  }
 }
 
 // one launch instead of four memsets / copies in front of every run
@@ -1566,11 +1575,12 @@ int run_typed(ctr_ctx* ctx, const ctr_mt3d_params* p, ctr_mt3d_counts* out, int 
     }
     // the counts travel behind the last kernel (nothing sits between the kernels of a run: each may start under the tail
     // of the one before, ctr_launch_dep); the host reads them after its single wait anyway
-    if (ctx->publish3) {
-      ctr_launch_dep(k_publish3, 1, 1, 0, st, (const Counters*)dctr, g.i_hiv > g.i_hi ? 1 : 0, ctx->publish3);
+    {
+      void* mirror = nullptr;
+      CTR_CUDA(ctx, cudaHostGetDevicePointer(&mirror, ctx->counters_host, 0));
+      ctr_launch_dep(k_counts_out, 1, 128, 0, st, (const Counters*)dctr, (uint32_t*)mirror, g.i_hiv > g.i_hi ? 1 : 0, ctx->publish3);
       ctx->launches++;
     }
-    CTR_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     }
     if (phase == 1) {
       CTR_CUDA(ctx, cudaGetLastError());
