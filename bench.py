@@ -545,7 +545,7 @@ def run_ours(args):
                      "wall_ms_per_step": wall / args.steps * 1e3},
         # one extraction = one launch each of four kernels; SURVEY 8(d) defines the algorithmic bytes per extraction, so the
         # roofline is taken over the four launches together (the scan kernel moves no algorithmic bytes of its own)
-        "roofline": {"bound": "hbm", "kernel": "mt3d extraction = k_reset3 + k_bitplane_tma + k_count_a + k_count_b + k_scan + k_emit_verts + k_emit_tris "
+        "roofline": {"bound": "hbm", "kernel": "mt3d extraction = k_reset3 + k_bitplane_tma + k_count_a + k_count_b + k_scan + k_emit_verts + k_emit_tris + k_counts_out "
                                                 "(largest share: %s, %.0f%% of the kernel time)" % (dom, 100.0 * per_stage[dom]["ms"] / kern_ms),
                      "achieved": alg_total / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg_total / (kern_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
